@@ -1,0 +1,156 @@
+// b2s_internal.h -- internal types shared by the CUDA translation units of libb200sph.
+// Not part of the ABI (include/b2s.h is).  Bit encodings restate the reference's contracts
+// (src/source/DualSphDef.h:150-241 typecode; JDsDcellDef.h:27-43 dcell) -- they must be
+// reproduced exactly for Case.bi4 / Part_XXXX.bi4 interchange and bit-exact cell tables.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/b2s.h"
+
+typedef uint16_t typecode;
+
+// ---- particle code (DualSphDef.h:150-181) ---------------------------------------------------
+#define B2S_CODE_MASKSPECIAL   0xe000u
+#define B2S_CODE_NORMAL        0x0000u
+#define B2S_CODE_PERIODIC      0x2000u
+#define B2S_CODE_OUTIGNORE     0x4000u
+#define B2S_CODE_OUTMOV        0x6000u
+#define B2S_CODE_OUTPOS        0x8000u
+#define B2S_CODE_OUTRHO        0xA000u
+#define B2S_CODE_MASKTYPE      0x1800u
+#define B2S_CODE_TYPE_FIXED    0x0000u
+#define B2S_CODE_TYPE_MOVING   0x0800u
+#define B2S_CODE_TYPE_FLOATING 0x1000u
+#define B2S_CODE_TYPE_FLUID    0x1800u
+#define B2S_CODE_MASKVALUE     0x07ffu
+#define B2S_CODE_SPECIAL(c)    ((c)&B2S_CODE_MASKSPECIAL)
+#define B2S_CODE_TYPE(c)       ((c)&B2S_CODE_MASKTYPE)
+#define B2S_CODE_TYPEVALUE(c)  ((c)&B2S_CODE_MASKVALUE)
+#define B2S_CODE_SETNORMAL(c)  ((c)&(~B2S_CODE_MASKSPECIAL))
+#define B2S_CODE_ISFLUID(c)    (B2S_CODE_TYPE(c)==B2S_CODE_TYPE_FLUID)
+#define B2S_CODE_ISFLOATING(c) (B2S_CODE_TYPE(c)==B2S_CODE_TYPE_FLOATING)
+#define B2S_CODE_ISNORMAL(c)   (B2S_CODE_SPECIAL(c)==B2S_CODE_NORMAL)
+
+// ---- dcell (JDsDcellDef.h:32-43) ------------------------------------------------------------
+#define B2S_DCEL_MAPOUT 0xffffffffu
+#define B2S_DCEL_GETCODE(sx,sy,sz) ((((sx)+1)<<25)|((sy)<<20)|((sz)<<15)|(((sy)+(sz))<<10)|(((sx)+1+(sz))<<5)|((sx)+1+(sy)))
+#define B2S_DCEL_CELLX(dcc,cel) ((cel)>>(((dcc)>>10)&31))
+#define B2S_DCEL_CELLY(dcc,cel) (((cel)<<((dcc)>>25))>>(((dcc)>>5)&31))
+#define B2S_DCEL_CELLZ(dcc,cel) (((cel)<<((dcc)&31))>>((dcc)&31))
+#define B2S_DCEL_CELL(dcc,cx,cy,cz) (((cx)<<(((dcc)>>10)&31))|((cy)<<(((dcc)>>15)&31))|(cz))
+
+#define B2S_ALMOSTZERO 1e-18f      // DualSphDef.h:114
+
+// ---- constants passed by value to every kernel (replaces __constant__ CTE, JSphGpu_ker.cu:39) ----
+struct DevCte {
+  float kernelh, ovkernelh, kernelsize2, awen, bwenh;
+  float cub_a2, cub_a24, cub_c1, cub_d1, cub_c2, cub_od_wdeltap;
+  float cteb, gamma, ovgamma, rhopzero, ovrhopzero, cs0, eta2, massf, massb;
+  float ddtkh, ddtgz, spssmag, spsblin;
+  float scell, movlimit, rhopoutmin, rhopoutmax;
+  float visco_f, visco_b;          // Visco and Visco*ViscoBoundFactor (JSphGpuSingle.cpp:609)
+  float gravity[3];
+  float ddt_c1, ddt_c2, ddt_c3;    // series coefficients of (1+x)^(1/gamma)-1
+  double scell_d;                  // double(float scell): divisor of the cell hash (JSphGpu_ker.cu:387-389)
+  double domposmin[3], maprealposmin[3], maprealsize[3];
+  double cs0_d, kernelh_d, cfl, dtmin;
+  uint32_t domcellcode, domcells[3];
+  int32_t  scelldiv, tkernel, tvisco, tdensity, tboundary, tstep, use_floating, dt_allparticles, refsem, simulate2d;
+  int32_t  gamma_is7;
+};
+
+// ---- device-resident state of the last cell divide (JCellDivGpu members, JCellDivGpu.h:86-138) ----
+struct DivState {
+  uint32_t flim[6];        // fluid  cell min(x,y,z), max(x,y,z) of valid particles (atomics)
+  uint32_t blim[6];        // bound  cell limits (cached until boundary changes)
+  uint32_t cellmin[3], cellmax[3];
+  uint32_t ncx, ncy, ncz, nsheet, nct, nctt;
+  uint32_t box_boundignore, box_fluid, box_boundout, box_fluidout, box_boundoutignore, box_fluidoutignore;
+  uint32_t nptot;          // particles entering the divide
+  uint32_t np, npb, npbok; // after the divide
+  uint32_t npb_ignore, npb_out, npf_out, npb_outignore, npf_outignore;
+  uint32_t npf_out_total;
+  uint32_t error;          // !=0: boundary particle excluded etc.
+};
+
+// ---- device-resident step scalars (dt maxima as ordered uints for atomicMax) ----
+struct StepState {
+  uint32_t velmax2_bits, acemax2_bits, viscdtmax_bits, pad;
+  double   dt, dt_p, dt_c, symplectic_dtpre, timestep, dt_last;
+  double   velmax, acemax;
+  float    viscdtmax;
+  uint32_t nstep, verletstep, dtmodif;
+  int32_t  error;
+  unsigned long long pairs_checked, pairs_real;
+};
+
+// One set of per-particle arrays in cell-sorted order (element layouts of JSphGpu.h:125-209).
+struct PartSet {
+  uint32_t* idp; typecode* code; uint32_t* dcell;
+  double2* posxy; double* posz; float4* velrho;
+};
+
+struct Motion {
+  uint32_t idbegin, count;
+  double freq[3], ampl[3], phase[3], tstart, tend;
+};
+
+struct b2s_ctx {
+  b2s_params prm;
+  DevCte cte;
+  int device;
+  cudaStream_t stream;
+  uint32_t cap;                 // particle capacity
+  uint32_t np_host, npb_host, npbok_host;   // host mirrors (upper bounds for launches)
+  uint32_t nct_max, nctt_max;   // table capacity
+  std::string err;
+  uint64_t launches;
+  int variant;
+  // particle arrays: current + sort scratch
+  PartSet cur, alt;
+  // symplectic predictor copies (+scratch) / verlet m1 (+scratch)
+  double2* pospre_xy; double* pospre_z; float4* velrhopre;
+  double2* pospre_xy_alt; double* pospre_z_alt; float4* velrhopre_alt;
+  float4* velrhom1; float4* velrhom1_alt;
+  bool pre_active;
+  // SPS
+  float* spstau; float* spstau_alt; float* spstau_new;   // 6 floats per particle
+  // mDBC
+  float4* boundnor; float4* boundnor_alt;                 // xyz normal, w unused
+  // interaction inputs/outputs
+  float4* posp;      // (x,y,z) relative to own cell origin, w = pressure
+  float4* acear;     // ace.xyz, ar
+  // neighbour list
+  uint32_t* cellpart; uint32_t* sortpart; uint32_t* cellpart_alt; uint32_t* sortpart_alt;
+  int2* begincell;
+  uint32_t* radix_counts; size_t radix_counts_len;
+  uint32_t* ridp;    // index by id for moving+floating (CalcRidp)
+  // device state
+  DivState* div; StepState* step;
+  DivState* div_h; StepState* step_h;   // pinned host mirrors
+  bool bound_changed;
+  uint32_t verletstep;          // JSphGpu::VerletStep (host counter)
+  // floatings
+  uint32_t ftcount; std::vector<b2s_floating> fts; float* ft_massp_dev; float* ft_sums_dev; float* ft_sums_h;
+  void* ft_dev; // device copy of per-floating update data
+  std::vector<Motion> motions;
+  // scratch for byid download
+  void* scratch; size_t scratch_bytes;
+};
+
+// ---- helpers -------------------------------------------------------------------------------
+int  b2s_fail(b2s_ctx* ctx, int code, const char* fmt, ...);
+#define B2S_CUDA(ctx, expr) do{ cudaError_t _e=(expr); if(_e!=cudaSuccess) return b2s_fail(ctx,(int)_e,"%s failed: %s (%s:%d)",#expr,cudaGetErrorString(_e),__FILE__,__LINE__); }while(0)
+#define B2S_LAUNCHED(ctx) do{ (ctx)->launches++; }while(0)
+static inline unsigned b2s_blocks(size_t n, unsigned bs){ return (unsigned)((n+bs-1)/bs); }
+
+// implemented in the .cu files
+int b2s_celldiv_impl(b2s_ctx* ctx);
+int b2s_forces_impl(b2s_ctx* ctx, int interstep);
+int b2s_integrate_impl(b2s_ctx* ctx, int mode, double dt, bool dt_from_device);   // mode: 0 verlet,1 sympre,2 symcorr
+int b2s_mdbc_impl(b2s_ctx* ctx);
+int b2s_floating_impl(b2s_ctx* ctx, double dt, bool predictor, bool dt_from_device);
+int b2s_motion_impl(b2s_ctx* ctx, double timestep, double dt);
+int b2s_sync_info(b2s_ctx* ctx);

@@ -1,0 +1,375 @@
+// celldiv.cu -- cell-linked neighbour list for sm_100a.
+//
+// Replaces JSphGpuSingle::RunCellDivide (src/source/JSphGpuSingle.cpp:372-498) and everything under it:
+//   JCellDivGpuSingle::Divide/CalcCellDomain/MergeMapCellBoundFluid/PrepareNct (JCellDivGpuSingle.cpp:47-235)
+//   cudiv::LimitsCell (JCellDivGpu_ker.cu:362-526)        -> k_limits (warp redux + 6 atomics)
+//   cudiv::PreSortFull (JCellDivGpuSingle_ker.cu:41-109)    -> k_presort
+//   cudiv::Sort = thrust::stable_sort_by_key (JCellDivGpu_ker.cu:120-127) -> hand-written stable LSD radix sort
+//   cudiv::CalcBeginEndCell (JCellDivGpu_ker.cu:533-570)     -> k_beginend
+//   cudiv::SortDataParticles x9 (JCellDivGpu_ker.cu:577-711) + cusphs::UpdatePosCell (JSphGpuSimple_ker.cu:41-69)
+//     + cusph::ComputeVelMod/ReduMaxFloat (JSphGpu_ker.cu:295,75) + CalcRidp (:1582)      -> ONE gather kernel k_reorder
+// Design: no host round trip anywhere in the divide.  The cell domain, Nct, the box layout and the
+// particle counts live in a device-resident DivState that the later kernels read; the host mirrors it
+// once per step.  The divide is always "full" (boundary re-sorted too); the result is identical to the
+// reference's fluid-only divide because its boundary block is already in cell order (JCellDivGpuSingle.cpp:193-197).
+#include "b2s_internal.h"
+#include <stdio.h>
+
+#define DIV_BS 256
+
+// ------------------------------------------------------------------------------------------------
+// Limits: min/max cell of valid particles (code special < OUTIGNORE), LimitsCellBound/Fluid
+// (JCellDivCpu.cpp:269-352 is the readable statement of the same loop).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_limits_reset(DivState* ds, int resetbound){
+  if(threadIdx.x<3){ ds->flim[threadIdx.x]=0xffffffffu; ds->flim[3+threadIdx.x]=0u;
+    if(resetbound){ ds->blim[threadIdx.x]=0xffffffffu; ds->blim[3+threadIdx.x]=0u; } }
+}
+
+__global__ void __launch_bounds__(DIV_BS) k_limits(uint32_t n, uint32_t pini, const uint32_t* __restrict__ dcell,
+  const typecode* __restrict__ code, uint32_t dcc, uint32_t* lim)
+{
+  uint32_t mn[3]={0xffffffffu,0xffffffffu,0xffffffffu}, mx[3]={0,0,0};
+  for(uint32_t i=blockIdx.x*blockDim.x+threadIdx.x; i<n; i+=gridDim.x*blockDim.x){
+    const uint32_t p=pini+i;
+    const typecode c=code[p];
+    if(B2S_CODE_SPECIAL(c)<B2S_CODE_OUTIGNORE){
+      const uint32_t rc=dcell[p];
+      const uint32_t cx=B2S_DCEL_CELLX(dcc,rc), cy=B2S_DCEL_CELLY(dcc,rc), cz=B2S_DCEL_CELLZ(dcc,rc);
+      mn[0]=min(mn[0],cx); mn[1]=min(mn[1],cy); mn[2]=min(mn[2],cz);
+      mx[0]=max(mx[0],cx); mx[1]=max(mx[1],cy); mx[2]=max(mx[2],cz);
+    }
+  }
+  #pragma unroll
+  for(int k=0;k<3;k++){
+    const uint32_t a=__reduce_min_sync(0xffffffffu,mn[k]);
+    const uint32_t b=__reduce_max_sync(0xffffffffu,mx[k]);
+    if((threadIdx.x&31)==0){ if(a!=0xffffffffu)atomicMin(&lim[k],a); if(b)atomicMax(&lim[3+k],b); }
+  }
+}
+
+// CalcCellDomain + MergeMapCellBoundFluid + PrepareNct (JCellDivGpuSingle.cpp:47-125), one thread.
+__global__ void k_divstate(DivState* ds, uint32_t dcx, uint32_t dcy, uint32_t dcz, uint32_t scelldiv){
+  if(threadIdx.x||blockIdx.x)return;
+  const uint32_t nptot=ds->np;   // particles entering the divide = survivors of the previous one (device-side count)
+  const uint32_t dom[3]={dcx,dcy,dcz};
+  uint32_t cbmin[3],cbmax[3],cfmin[3],cfmax[3];
+  const bool bnone=(ds->blim[0]>ds->blim[3]);   // no valid particles: min>max (cmin.x>cmax.x test)
+  const bool fnone=(ds->flim[0]>ds->flim[3]);
+  for(int k=0;k<3;k++){
+    cbmin[k]=(bnone? dom[k]: ds->blim[k]);  cbmax[k]=(bnone? 0u: ds->blim[3+k]);
+    cfmin[k]=(fnone? dom[k]: ds->flim[k]);  cfmax[k]=(fnone? 0u: ds->flim[3+k]);
+  }
+  uint32_t cmin[3],cmax[3];
+  for(int k=0;k<3;k++){
+    cmin[k]=max(min(cbmin[k],cfmin[k]),(cfmin[k]>=scelldiv? cfmin[k]-scelldiv: 0u));
+    cmax[k]=min(max(cbmax[k],cfmax[k]),cfmax[k]+scelldiv);
+    if(cmax[k]>=dom[k])cmax[k]=dom[k]-1;
+  }
+  if(cmin[0]>cmax[0] || cmin[1]>cmax[1] || cmin[2]>cmax[2]){ for(int k=0;k<3;k++)cmin[k]=cmax[k]=0; }
+  for(int k=0;k<3;k++){ ds->cellmin[k]=cmin[k]; ds->cellmax[k]=cmax[k]; }
+  ds->ncx=cmax[0]-cmin[0]+1; ds->ncy=cmax[1]-cmin[1]+1; ds->ncz=cmax[2]-cmin[2]+1;
+  ds->nsheet=ds->ncx*ds->ncy; ds->nct=ds->nsheet*ds->ncz; ds->nctt=ds->nct*2+5+1;
+  ds->box_boundignore=ds->nct;
+  ds->box_fluid=ds->box_boundignore+1;
+  ds->box_boundout=ds->box_fluid+ds->nct;
+  ds->box_fluidout=ds->box_boundout+1;
+  ds->box_boundoutignore=ds->box_fluidout+1;
+  ds->box_fluidoutignore=ds->box_boundoutignore+1;
+  ds->nptot=nptot;
+}
+
+// PreSortFull (JCellDivGpuSingle_ker.cu:41-109; CPU statement JCellDivCpuSingle.cpp:137-170).
+__global__ void __launch_bounds__(DIV_BS) k_presort(const DivState* __restrict__ ds, const uint32_t* __restrict__ dcell,
+  const typecode* __restrict__ code, uint32_t dcc, uint32_t* __restrict__ cellpart, uint32_t* __restrict__ sortpart)
+{
+  const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
+  if(p>=ds->nptot)return;
+  const uint32_t rcell=dcell[p];
+  const uint32_t cx=B2S_DCEL_CELLX(dcc,rcell)-ds->cellmin[0];
+  const uint32_t cy=B2S_DCEL_CELLY(dcc,rcell)-ds->cellmin[1];
+  const uint32_t cz=B2S_DCEL_CELLZ(dcc,rcell)-ds->cellmin[2];
+  const uint32_t cellsort=cx+cy*ds->ncx+cz*ds->nsheet;
+  const typecode rcode=code[p];
+  const uint32_t codetype=B2S_CODE_TYPE(rcode);
+  const uint32_t codeout=B2S_CODE_SPECIAL(rcode);
+  uint32_t box;
+  if(codetype<B2S_CODE_TYPE_FLOATING){
+    box=(codeout<B2S_CODE_OUTIGNORE? ((cx<ds->ncx && cy<ds->ncy && cz<ds->ncz)? cellsort: ds->box_boundignore)
+        : (codeout==B2S_CODE_OUTIGNORE? ds->box_boundoutignore: ds->box_boundout));
+  }
+  else{
+    box=(codeout<=B2S_CODE_OUTIGNORE? (codeout<B2S_CODE_OUTIGNORE? ds->box_fluid+cellsort: ds->box_fluidoutignore)
+        : (codetype==B2S_CODE_TYPE_FLOATING? ds->box_boundout: ds->box_fluidout));
+  }
+  cellpart[p]=box;
+  sortpart[p]=p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stable LSD radix sort, 8-bit digits, (key=cellpart, value=sortpart).  The permutation of a stable
+// sort is unique, so it equals the reference's counting sort (JCellDivCpuSingle.cpp:186-238) and
+// thrust::stable_sort_by_key (-stable) bit for bit.
+//   pass = k_radix_hist (tile digit histograms) -> k_scan (exclusive, digit-major) -> k_radix_scatter.
+// Traffic per pass: 4 B (hist) + 8 B in + 8 B out per particle; 2-3 passes cover log2(2*Nct+5) bits.
+// ------------------------------------------------------------------------------------------------
+#define RDX_ITEMS 16
+#define RDX_TILE (DIV_BS*RDX_ITEMS)
+
+__global__ void __launch_bounds__(DIV_BS) k_radix_hist(const uint32_t* __restrict__ keys, const DivState* __restrict__ ds,
+  int shift, uint32_t ntiles, uint32_t* __restrict__ counts)
+{
+  __shared__ uint32_t h[256];
+  const uint32_t n=ds->nptot;
+  h[threadIdx.x]=0;
+  __syncthreads();
+  const uint32_t base=blockIdx.x*RDX_TILE;
+  #pragma unroll
+  for(int r=0;r<RDX_ITEMS;r++){
+    const uint32_t i=base+r*DIV_BS+threadIdx.x;
+    if(i<n)atomicAdd(&h[(keys[i]>>shift)&255u],1u);
+  }
+  __syncthreads();
+  counts[threadIdx.x*ntiles+blockIdx.x]=h[threadIdx.x];
+}
+
+// Single-block exclusive scan of n uints (n = 256*ntiles, a few 1e5): warp shuffles + carry.
+__global__ void __launch_bounds__(1024) k_scan_excl(uint32_t* data, uint32_t n){
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry_s;
+  if(threadIdx.x==0)carry_s=0;
+  __syncthreads();
+  const int lane=threadIdx.x&31, w=threadIdx.x>>5;
+  for(uint32_t base=0; base<n; base+=1024*4){
+    // each thread owns 4 consecutive elements
+    const uint32_t i0=base+threadIdx.x*4;
+    uint32_t v[4];
+    #pragma unroll
+    for(int k=0;k<4;k++)v[k]=(i0+k<n? data[i0+k]: 0u);
+    const uint32_t tsum=v[0]+v[1]+v[2]+v[3];
+    uint32_t x=tsum;
+    #pragma unroll
+    for(int o=1;o<32;o<<=1){ const uint32_t y=__shfl_up_sync(0xffffffffu,x,o); if(lane>=o)x+=y; }
+    if(lane==31)wsum[w]=x;
+    __syncthreads();
+    if(w==0){
+      uint32_t s=wsum[lane];
+      #pragma unroll
+      for(int o=1;o<32;o<<=1){ const uint32_t y=__shfl_up_sync(0xffffffffu,s,o); if(lane>=o)s+=y; }
+      wsum[lane]=s;
+    }
+    __syncthreads();
+    const uint32_t carry=carry_s;
+    uint32_t excl=carry+(w? wsum[w-1]: 0u)+(x-tsum);
+    #pragma unroll
+    for(int k=0;k<4;k++){ if(i0+k<n)data[i0+k]=excl; excl+=v[k]; }
+    __syncthreads();
+    if(threadIdx.x==1023)carry_s=carry+wsum[31];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(DIV_BS) k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ offsets,
+  const DivState* __restrict__ ds, int shift, uint32_t ntiles)
+{
+  __shared__ uint32_t s_base[256];
+  __shared__ uint32_t s_wc[DIV_BS/32][256];
+  const uint32_t n=ds->nptot;
+  const int lane=threadIdx.x&31, w=threadIdx.x>>5;
+  s_base[threadIdx.x]=offsets[threadIdx.x*ntiles+blockIdx.x];
+  const uint32_t base=blockIdx.x*RDX_TILE;
+  for(int r=0;r<RDX_ITEMS;r++){
+    const uint32_t i=base+r*DIV_BS+threadIdx.x;
+    const bool valid=(i<n);
+    const uint32_t key=(valid? keys_in[i]: 0u);
+    const uint32_t val=(valid? vals_in[i]: 0u);
+    const uint32_t digit=(key>>shift)&255u;
+    #pragma unroll
+    for(int k=0;k<DIV_BS/32;k++)s_wc[k][threadIdx.x]=0;
+    __syncthreads();
+    const uint32_t peers=__match_any_sync(0xffffffffu,(valid? digit: (256u+lane)));
+    const uint32_t lower=peers&((1u<<lane)-1u);
+    if(valid && lower==0)s_wc[w][digit]=__popc(peers);
+    __syncthreads();
+    if(valid){
+      uint32_t pre=0;
+      for(int k=0;k<w;k++)pre+=s_wc[k][digit];
+      const uint32_t pos=s_base[digit]+pre+__popc(lower);
+      keys_out[pos]=key; vals_out[pos]=val;
+    }
+    __syncthreads();
+    uint32_t tot=0;
+    #pragma unroll
+    for(int k=0;k<DIV_BS/32;k++)tot+=s_wc[k][threadIdx.x];
+    s_base[threadIdx.x]+=tot;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Begin table (CalcBeginEndCell, JCellDivGpu_ker.cu:533-570).  Stored in the CPU form
+// begincell[box] = first particle of box, begincell[nctt-1] = nptot (JCellDivCpu.h BeginCell), which
+// makes a row of x-contiguous cells one [begin[c0], begin[c1+1]) range (JCellSearch_iker.h:155-167).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DIV_BS) k_beginend(const DivState* __restrict__ ds, const uint32_t* __restrict__ keys, uint32_t* __restrict__ beg){
+  const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
+  const uint32_t n=ds->nptot;
+  if(n==0){ if(p<ds->nctt)beg[p]=0; return; }
+  if(p>=n)return;
+  const uint32_t cur=keys[p];
+  const uint32_t first=(p? keys[p-1]+1: 0u);
+  for(uint32_t c=first;c<=cur;c++)beg[c]=p;
+  if(p==n-1)for(uint32_t c=cur+1;c<ds->nctt;c++)beg[c]=n;
+}
+
+// Particle counts after the divide (JCellDivGpuSingle.cpp:218-231), one thread.
+__global__ void k_divcounts(DivState* ds, const uint32_t* __restrict__ beg){
+  if(threadIdx.x||blockIdx.x)return;
+  const uint32_t npb_in=ds->npb;
+  #define CSIZE(b) (beg[(b)+1]-beg[(b)])
+  ds->npb_ignore=CSIZE(ds->box_boundignore);
+  ds->npb_out=CSIZE(ds->box_boundout);
+  ds->npf_out=CSIZE(ds->box_fluidout);
+  ds->npb_outignore=CSIZE(ds->box_boundoutignore);
+  ds->npf_outignore=CSIZE(ds->box_fluidoutignore);
+  #undef CSIZE
+  ds->np=ds->nptot-ds->npb_out-ds->npf_out-ds->npb_outignore-ds->npf_outignore;
+  ds->npb=npb_in-ds->npb_outignore;
+  ds->npbok=ds->npb-ds->npb_ignore;
+  ds->npf_out_total+=ds->npf_out;
+  if(ds->npb_out)ds->error=1;   // JSphGpuSingle::AbortBoundOut (JSphGpuSingle.cpp:505)
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused gather: every persistent array through sortpart, + cell-relative position and pressure for
+// the interaction (UpdatePosCell + the CPU path's Press_c, JSphCpu.cpp:537-547), + |v|^2 max
+// (PreInteraction_Forces, JSphGpu.cpp:898-903), + ridp for moving/floating ids (CalcRidp).
+// Algorithmic traffic: 4 (sortpart) + 2x(4+2+4+16+8+16)=100 B + 16 B (posp) per particle.
+// ------------------------------------------------------------------------------------------------
+struct ReorderArgs {
+  PartSet src, dst;
+  const double2* pre_xy_s; const double* pre_z_s; const float4* pre_v_s;
+  double2* pre_xy_d; double* pre_z_d; float4* pre_v_d;
+  const float4* m1_s; float4* m1_d;
+  const float* tau_s; float* tau_d;
+  const float4* nor_s; float4* nor_d;
+  float4* posp; uint32_t* ridp;
+  uint32_t casenfixed, casenbound;
+};
+
+__device__ __forceinline__ float b2s_press(float rho, const DevCte& c){
+  // Tait EOS as the CPU path evaluates it (FunSphEos.h:37-39): cteb*(powf(rho/rho0,gamma)-1).
+  // gamma==7: exact product chain in double, rounded once (== correctly rounded powf to <1ulp).
+  const float r=rho*c.ovrhopzero;
+  float pw;
+  if(c.gamma_is7){ const double d=(double)r; const double d2=d*d; const double d4=d2*d2; pw=(float)(d4*d2*d); }
+  else pw=(float)pow((double)r,(double)c.gamma);
+  return c.cteb*(pw-1.0f);
+}
+
+__global__ void __launch_bounds__(DIV_BS) k_reorder(const DivState* __restrict__ ds, StepState* st, const uint32_t* __restrict__ sortpart,
+  ReorderArgs a, const __grid_constant__ DevCte cte)
+{
+  const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
+  const uint32_t n=ds->nptot;
+  float v2=0.f;
+  if(p<n){
+    const uint32_t s=sortpart[p];
+    const uint32_t id=a.src.idp[s];
+    const typecode cod=a.src.code[s];
+    const uint32_t dc=a.src.dcell[s];
+    const double2 xy=a.src.posxy[s];
+    const double z=a.src.posz[s];
+    const float4 vr=a.src.velrho[s];
+    a.dst.idp[p]=id; a.dst.code[p]=cod; a.dst.dcell[p]=dc; a.dst.posxy[p]=xy; a.dst.posz[p]=z; a.dst.velrho[p]=vr;
+    if(a.pre_v_s){ a.pre_xy_d[p]=a.pre_xy_s[s]; a.pre_z_d[p]=a.pre_z_s[s]; a.pre_v_d[p]=a.pre_v_s[s]; }
+    if(a.m1_s)a.m1_d[p]=a.m1_s[s];
+    if(a.tau_s){
+      const float2* ts=(const float2*)(a.tau_s+size_t(s)*6); float2* td=(float2*)(a.tau_d+size_t(p)*6);
+      td[0]=ts[0]; td[1]=ts[1]; td[2]=ts[2];
+    }
+    if(a.nor_s)a.nor_d[p]=a.nor_s[s];
+    if(p<ds->np){
+      // position relative to the origin of the particle's own cell (PosCell idea, JSphGpuSimple_ker.cu:46-57)
+      const uint32_t cx=B2S_DCEL_CELLX(cte.domcellcode,dc), cy=B2S_DCEL_CELLY(cte.domcellcode,dc), cz=B2S_DCEL_CELLZ(cte.domcellcode,dc);
+      float4 pp;
+      pp.x=float((xy.x-cte.domposmin[0])-cte.scell_d*double(cx));
+      pp.y=float((xy.y-cte.domposmin[1])-cte.scell_d*double(cy));
+      pp.z=float((z   -cte.domposmin[2])-cte.scell_d*double(cz));
+      pp.w=b2s_press(vr.w,cte);
+      a.posp[p]=pp;
+      if(p>=ds->npb || cte.dt_allparticles)v2=vr.x*vr.x+vr.y*vr.y+vr.z*vr.z;
+      if(a.ridp && id>=a.casenfixed && id<a.casenbound)a.ridp[id-a.casenfixed]=p;
+    }
+  }
+  // block max -> one atomic per warp (values >=0 so uint order == float order)
+  #pragma unroll
+  for(int o=16;o;o>>=1)v2=fmaxf(v2,__shfl_xor_sync(0xffffffffu,v2,o));
+  if((threadIdx.x&31)==0 && v2>0.f)atomicMax(&st->velmax2_bits,__float_as_uint(v2));
+}
+
+__global__ void k_reset_step_maxima(StepState* st){
+  st->velmax2_bits=0; st->acemax2_bits=0; st->viscdtmax_bits=0;
+}
+
+// ------------------------------------------------------------------------------------------------
+static inline int radix_passes(uint32_t maxkey){ int bits=1; while((maxkey>>bits)!=0)bits++; return (bits+7)/8; }
+
+int b2s_celldiv_impl(b2s_ctx* ctx){
+  cudaStream_t s=ctx->stream;
+  const uint32_t nptot=ctx->np_host;      // upper bound known to the host; == device np (outs already dropped)
+  const uint32_t npb=ctx->npb_host;
+  const DevCte& c=ctx->cte;
+  if(nptot==0)return B2S_OK;
+  // 1. limits
+  k_limits_reset<<<1,32,0,s>>>(ctx->div,ctx->bound_changed? 1: 0); B2S_LAUNCHED(ctx);
+  const unsigned gl=min(b2s_blocks(nptot,DIV_BS),148u*8u);
+  if(ctx->bound_changed && npb){ k_limits<<<gl,DIV_BS,0,s>>>(npb,0,ctx->cur.dcell,ctx->cur.code,c.domcellcode,ctx->div->blim); B2S_LAUNCHED(ctx); }
+  if(nptot>npb){ k_limits<<<gl,DIV_BS,0,s>>>(nptot-npb,npb,ctx->cur.dcell,ctx->cur.code,c.domcellcode,ctx->div->flim); B2S_LAUNCHED(ctx); }
+  k_divstate<<<1,32,0,s>>>(ctx->div,c.domcells[0],c.domcells[1],c.domcells[2],(uint32_t)c.scelldiv); B2S_LAUNCHED(ctx);
+  // 2. keys
+  k_presort<<<b2s_blocks(nptot,DIV_BS),DIV_BS,0,s>>>(ctx->div,ctx->cur.dcell,ctx->cur.code,c.domcellcode,ctx->cellpart,ctx->sortpart); B2S_LAUNCHED(ctx);
+  // 3. stable radix sort
+  const uint32_t ntiles=b2s_blocks(nptot,RDX_TILE);
+  const int passes=radix_passes(2u*ctx->nct_max+5u);
+  uint32_t *kin=ctx->cellpart,*vin=ctx->sortpart,*kout=ctx->cellpart_alt,*vout=ctx->sortpart_alt;
+  for(int ps=0;ps<passes;ps++){
+    k_radix_hist<<<ntiles,DIV_BS,0,s>>>(kin,ctx->div,ps*8,ntiles,ctx->radix_counts); B2S_LAUNCHED(ctx);
+    k_scan_excl<<<1,1024,0,s>>>(ctx->radix_counts,256u*ntiles); B2S_LAUNCHED(ctx);
+    k_radix_scatter<<<ntiles,DIV_BS,0,s>>>(kin,vin,kout,vout,ctx->radix_counts,ctx->div,ps*8,ntiles); B2S_LAUNCHED(ctx);
+    uint32_t* t=kin; kin=kout; kout=t; t=vin; vin=vout; vout=t;
+  }
+  if(kin!=ctx->cellpart){ // odd number of passes: sorted data sits in the alt buffers -> swap names
+    uint32_t* t=ctx->cellpart; ctx->cellpart=ctx->cellpart_alt; ctx->cellpart_alt=t;
+    t=ctx->sortpart; ctx->sortpart=ctx->sortpart_alt; ctx->sortpart_alt=t;
+  }
+  // 4. begin table + counts
+  k_beginend<<<b2s_blocks(max(nptot,1u),DIV_BS),DIV_BS,0,s>>>(ctx->div,ctx->cellpart,(uint32_t*)ctx->begincell); B2S_LAUNCHED(ctx);
+  k_divcounts<<<1,32,0,s>>>(ctx->div,(const uint32_t*)ctx->begincell); B2S_LAUNCHED(ctx);
+  // 5. fused gather
+  k_reset_step_maxima<<<1,1,0,s>>>(ctx->step); B2S_LAUNCHED(ctx);
+  ReorderArgs a; memset(&a,0,sizeof(a));
+  a.src=ctx->cur; a.dst=ctx->alt;
+  if(ctx->pre_active){
+    a.pre_xy_s=ctx->pospre_xy; a.pre_z_s=ctx->pospre_z; a.pre_v_s=ctx->velrhopre;
+    a.pre_xy_d=ctx->pospre_xy_alt; a.pre_z_d=ctx->pospre_z_alt; a.pre_v_d=ctx->velrhopre_alt;
+  }
+  if(ctx->velrhom1){ a.m1_s=ctx->velrhom1; a.m1_d=ctx->velrhom1_alt; }
+  if(ctx->spstau){ a.tau_s=ctx->spstau; a.tau_d=ctx->spstau_alt; }
+  if(ctx->boundnor){ a.nor_s=ctx->boundnor; a.nor_d=ctx->boundnor_alt; }
+  a.posp=ctx->posp;
+  a.ridp=(ctx->prm.casenmoving+ctx->prm.casenfloat? ctx->ridp: NULL);
+  a.casenfixed=ctx->prm.casenfixed; a.casenbound=ctx->prm.casenbound;
+  k_reorder<<<b2s_blocks(nptot,DIV_BS),DIV_BS,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte); B2S_LAUNCHED(ctx);
+  { PartSet t=ctx->cur; ctx->cur=ctx->alt; ctx->alt=t; }
+  if(ctx->pre_active){
+    std::swap(ctx->pospre_xy,ctx->pospre_xy_alt); std::swap(ctx->pospre_z,ctx->pospre_z_alt); std::swap(ctx->velrhopre,ctx->velrhopre_alt);
+  }
+  if(ctx->velrhom1)std::swap(ctx->velrhom1,ctx->velrhom1_alt);
+  if(ctx->spstau)std::swap(ctx->spstau,ctx->spstau_alt);
+  if(ctx->boundnor)std::swap(ctx->boundnor,ctx->boundnor_alt);
+  ctx->bound_changed=false;
+  B2S_CUDA(ctx,cudaGetLastError());
+  return B2S_OK;
+}

@@ -1,0 +1,226 @@
+/* b2s.h -- C-ABI of libb200sph: the B200-native WCSPH time-step hot path.
+ *
+ * Drop-in boundary: the reference calls its GPU kernels through free
+ * functions in the namespaces cusph:: / cusphs:: / cudiv:: taking POD structs and raw device
+ * pointers (all file:line below are relative to /root/reference/src/source).  This header
+ * declares the coarser, fusable entry points that replace them; every function cites the
+ * reference interface it stands in for.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, <0 = b2s error (B2S_ERR_*), >0 = cudaError_t.
+ *   - b2s_last_error(ctx) returns a static/ctx-owned message; no exception crosses the ABI.
+ *   - one ctx per GPU; a ctx is not thread-safe, different ctxs are independent.
+ *   - the ctx owns all device memory (the reference's JArraysGpu/JCellDivGpu pools,
+ *     JArraysGpu.h, JCellDivGpu.h:86-138); callers see host copies through the getters.
+ *   - there is NO CPU fallback: without a CUDA device b2s_create fails with
+ *     B2S_ERR_NODEVICE and nothing else can be called.
+ */
+#ifndef B2S_H_
+#define B2S_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_VERSION 100
+
+/* error codes */
+#define B2S_OK              0
+#define B2S_ERR_ARG        -1
+#define B2S_ERR_NODEVICE   -2
+#define B2S_ERR_NOMEM      -3
+#define B2S_ERR_STATE      -4
+#define B2S_ERR_UNSUPPORTED -5
+#define B2S_ERR_DTINVALID  -6   /* dt is NaN/Inf: JSphGpu.cpp:1122-1129 */
+#define B2S_ERR_BOUNDOUT   -7   /* boundary particle left the domain: JSphGpuSingle.cpp:505 */
+#define B2S_ERR_IO         -8
+#define B2S_ERR_NAME       -9
+
+/* enums: same numeric values as the reference (DualSphDef.h:435-566, JViscosityDef.h) */
+enum { B2S_KERNEL_CUBIC = 1, B2S_KERNEL_WENDLAND = 2 };                    /* TpKernel   */
+enum { B2S_STEP_VERLET = 1, B2S_STEP_SYMPLECTIC = 2 };                     /* TpStep     */
+enum { B2S_VISCO_ARTIFICIAL = 1, B2S_VISCO_LAMINARSPS = 2, B2S_VISCO_LAMINAR = 3 }; /* TpVisco */
+enum { B2S_DDT_NONE = 0, B2S_DDT_MOLTENI = 1, B2S_DDT_FOURTAKAS = 2, B2S_DDT_FOURTAKASFULL = 3 }; /* TpDensity */
+enum { B2S_BC_DBC = 1, B2S_BC_MDBC = 2 };                                  /* TpBoundary */
+enum { B2S_SLIP_VEL0 = 1, B2S_SLIP_NOSLIP = 2, B2S_SLIP_FREESLIP = 3 };    /* TpSlipMode */
+enum { B2S_INTER_VERLET = 1, B2S_INTER_SYMPREDICTOR = 2, B2S_INTER_SYMCORRECTOR = 3 }; /* TpInterStep */
+/* Which reference build a semantic detail follows where CPU and GPU differ
+ * (DDT2 near DBC boundaries, JSphCpu.cpp:1318-1340 vs JSphGpu_ker.cu:939-946). */
+enum { B2S_REFSEM_CPU = 0, B2S_REFSEM_GPU = 1 };
+
+/* Constants + configuration of one simulation.  Replaces StCteInteraction (JSphGpu_cte.h:27-63)
+ * + the members of JSph that ConfigConstants1/2, ConfigCellDivision, SelecDomain fill
+ * (JSph.cpp:1481-1546,1877-1946).  Filled by b2s_config_finalize() from the primary values. */
+typedef struct b2s_params {
+  /* ---- primary values (case XML: constants + parameters) ---- */
+  int32_t  simulate2d;
+  int32_t  tkernel, tstep, tvisco, tdensity, tboundary, slipmode;
+  int32_t  verletsteps;
+  int32_t  cellmode_half;      /* 0: cells of 2h (CELLMODE_Full), 1: cells of h (CELLMODE_Half) */
+  int32_t  dt_allparticles;
+  int32_t  mdbc_corrector;
+  int32_t  refsem;             /* B2S_REFSEM_* */
+  int32_t  use_floating;       /* casenfloat>0 */
+  int32_t  reserved_i[3];
+  float    kernelh, cteb, gamma, rhopzero, massfluid, massbound;
+  float    visco, viscoboundfactor, ddtvalue;
+  float    rhopoutmin, rhopoutmax;
+  float    gravity[3];
+  double   dp, cflnumber, dtini, dtmin, coefdtmin, ftpause;
+  double   maprealposmin[3], maprealposmax[3];   /* after ResizeMapLimits (JSph.cpp:1445-1476) */
+  uint32_t casenp, casenfixed, casenmoving, casenfloat, casenfluid;
+  /* ---- derived values (b2s_config_finalize) ---- */
+  float    kernelsize, kernelsize2, awen, bwenh;            /* FunSphKernel.h:198-209 */
+  float    cubic_a1, cubic_a2, cubic_aa, cubic_a24, cubic_c1, cubic_d1, cubic_c2, cubic_od_wdeltap; /* :45-85 */
+  float    eta2, ddtkh, ddtgz, spssmag, spsblin, scell, movlimit, ovrhopzero;
+  double   cs0;
+  double   map_posmin[3], map_posmax[3], map_size[3];       /* == maprealpos without periodic */
+  double   maprealsize[3];
+  uint32_t map_cells[3];                                     /* ceil(map_size/scell) */
+  uint32_t domcells[3];                                      /* single domain: == map_cells */
+  uint32_t domcellcode;                                      /* DCEL_GetCode (JDsDcellDef.h:32) */
+  int32_t  scelldiv;                                         /* 1 full, 2 half */
+  double   domposmin[3], domrealposmin[3], domrealposmax[3];
+  float    poscellsize;                                      /* JSph.cpp:1949-1990 */
+  uint32_t casenbound, casenpb;
+} b2s_params;
+
+/* Floating body data: StFloatingData (DualSphDef.h) subset used by FtComputeAceVel (JSph.cpp:2565-2704) */
+typedef struct b2s_floating {
+  uint32_t begin, count;        /* id range of its particles */
+  float    mass, massp, radius;
+  int32_t  constraints;         /* bit mask: 1 movx,2 movy,4 movz,8 rotx,16 roty,32 rotz blocked */
+  double   center[3];
+  float    angles[3];
+  float    fvel[3], fomega[3];
+  float    facelin[3], faceang[3];
+  float    inertiaini[9];       /* row-major 3x3 */
+} b2s_floating;
+
+/* Run-time counters and maxima, one coherent snapshot (replaces the blocking scalar
+ * cudaMemcpy calls of JSphGpu_ker.cu:117,178 and JCellDivGpu.cpp:297-309). */
+typedef struct b2s_info {
+  uint32_t np, npb, npbok, npf_out_total;
+  uint32_t ncx, ncy, ncz, nct;
+  uint32_t cellmin[3], cellmax[3];
+  uint32_t npb_ignore, npf_out_last, npb_out_last, nstep;
+  double   timestep, dt_last, dt_p, dt_c, symplectic_dtpre;
+  double   velmax, acemax;
+  float    viscdtmax, pad0;
+  uint32_t verletstep, dtmodif;
+  uint64_t pairs_checked, pairs_real;   /* filled only by b2s_count_pairs */
+} b2s_info;
+
+typedef struct b2s_ctx b2s_ctx;
+
+/* ---- configuration (host math; no device needed) ---------------------------------------- */
+/* Fills the derived block of *p from its primary block.  Mirrors JSph::ConfigConstants1/2,
+ * ConfigCellDivision, SelecDomain, ConfigPosCellGpu, JDsDcell::CalcCellCode
+ * (JSph.cpp:1481-1546,1877-1990; JDsDcell.cpp:41-67). */
+int b2s_config_finalize(b2s_params* p);
+const char* b2s_error_string(int code);
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* device<0: current device.  capacity_np: particle slots to allocate (>= np + halo slack). */
+int b2s_create(const b2s_params* p, int device, uint32_t capacity_np, b2s_ctx** out);
+int b2s_destroy(b2s_ctx* ctx);
+const char* b2s_last_error(const b2s_ctx* ctx);
+int b2s_get_params(const b2s_ctx* ctx, b2s_params* out);
+
+/* ---- particle data up / down (JSphGpu::ParticlesDataUp/Down, JSphGpu.cpp:606-686) -------- */
+/* Host arrays in the reference's element layouts: idp u32, code u16 (typecode), pos double[3],
+ * velrho float[4]; boundnor float[3] optional (NULL unless mDBC).  Particles must be ordered
+ * [bound(fixed,moving) | floating | fluid] as JPartsLoad4 guarantees (JPartsLoad4.cpp:131-140).
+ * Computes dcell (JSph::LoadDcellParticles, JSph.cpp:1794-1820) and runs the first cell divide
+ * like JSphGpuSingle::ConfigDomain (JSphGpuSingle.cpp:151-240). */
+int b2s_upload_particles(b2s_ctx* ctx, uint32_t np, const uint32_t* idp, const uint16_t* code,
+                         const double* pos, const float* velrho, const float* boundnor);
+/* Copies the current state (cell-sorted order) to host arrays (any may be NULL). Returns np in *np_out. */
+int b2s_download_particles(b2s_ctx* ctx, uint32_t* np_out, uint32_t* idp, uint16_t* code,
+                           double* pos, float* velrho);
+/* Same but ordered by idp and only non-excluded particles: what SaveData writes (JSphGpuSingle.cpp:1053). */
+int b2s_download_particles_byid(b2s_ctx* ctx, uint32_t* np_out, uint32_t* idp, double* pos,
+                                float* vel, float* rhop);
+
+/* Named read-back of any ctx-owned device array (test entry point; replaces the debug dumps of
+ * JDebugSphGpu).  Names: idp code dcell pos velrho cellpart sortpart begincell(int2 table)
+ * ace ar press poscell velrhopre pospre velrhom1 spstau boundnor.  *count_out = elements copied;
+ * fails with B2S_ERR_ARG if capacity_bytes is too small. */
+int b2s_get_array(b2s_ctx* ctx, const char* name, void* dst, size_t capacity_bytes, size_t* count_out);
+int b2s_get_info(b2s_ctx* ctx, b2s_info* out);
+
+/* ---- neighbour list: JSphGpuSingle::RunCellDivide (JSphGpuSingle.cpp:372-498) ------------ */
+/* = cudiv::LimitsCell + PreSortFull/Fluid + Sort + CalcBeginEndCell + SortDataParticles +
+ *   cusphs::UpdatePosCell (+CalcRidp)  (JCellDivGpu_ker.cu:439,120,533,577; JCellDivGpuSingle_ker.cu:41;
+ *   JSphGpuSimple_ker.cu:41). */
+int b2s_celldiv(b2s_ctx* ctx);
+
+/* ---- interaction: PreInteraction_Forces + cusph::Interaction_Forces + reductions ---------- */
+/* (JSphGpu.cpp:846-913, JSphGpu_ker.cu:1043-1179, JSphGpuSingle.cpp:590-727).  interstep =
+ * B2S_INTER_*.  Runs mDBC correction first when tboundary==MDBC (JSphGpuSingle.cpp:686-712),
+ * then fluid and boundary force kernels, SPS tau, and the fused max reductions; computes
+ * dt = DtVariable() on the device (JSphGpu.cpp:1103-1147). */
+int b2s_interaction(b2s_ctx* ctx, int interstep);
+
+/* ---- integrators (cusphs::ComputeStepVerlet/SymplecticPre/Cor + cusph::ComputeStepPos[2]) - */
+/* (JSphGpuSimple_ker.cu:132-553, JSphGpu_ker.cu:1476-1570; callers JSphGpu.cpp:939-1097). */
+int b2s_compute_verlet(b2s_ctx* ctx, double dt);
+int b2s_compute_symplectic_pre(b2s_ctx* ctx, double dt);
+int b2s_compute_symplectic_corr(b2s_ctx* ctx, double dt);
+
+/* ---- whole step: JSphGpuSingle::ComputeStep + the Run-loop tail (JSphGpuSingle.cpp:761-819,998-1010)
+ * = ComputeStep_Sym/Ver, RunMotion for registered linear motions, RunCellDivide, TimeStep+=dt.
+ * One host synchronisation per call (to return dt).  nsteps>1 runs several steps back to back. */
+int b2s_compute_step(b2s_ctx* ctx, double* dt_out);
+int b2s_run_steps(b2s_ctx* ctx, uint32_t nsteps, double* time_out);
+
+/* ---- moving boundaries: cusph::MoveLinBound (JSphGpu_ker.cu:1671-1700) via RunMotion (JSphGpu.cpp:1173-1225)
+ * Registers a sinusoidal rectilinear motion (JMotionMovRectSinu) for the id block [idbegin,idbegin+count):
+ * pos(t)=ampl*sin(2*pi*freq*t+phase) per axis; applied every step with the step's dt. */
+int b2s_add_motion_rectsinu(b2s_ctx* ctx, uint32_t idbegin, uint32_t count, const double freq[3],
+                            const double ampl[3], const double phase[3], double tstart, double tend);
+/* Direct form: displace a block now (MOTT_Linear data: JDsMotionDef.h). */
+int b2s_move_linear(b2s_ctx* ctx, uint32_t idbegin, uint32_t count, const double mvpos[3], const float mvvel[3]);
+
+/* ---- floating bodies: FtPartsSumAce / FtComputeAceVel / FtPartsUpdate ---------------------- */
+/* (JSphGpu_ker.cu:1938-2101, JSph.cpp:2565-2704, JSphGpuSingle.cpp:827-907). */
+int b2s_set_floatings(b2s_ctx* ctx, uint32_t ftcount, const b2s_floating* fts);
+int b2s_get_floatings(b2s_ctx* ctx, uint32_t ftcount, b2s_floating* fts);
+
+/* ---- measurement helpers ------------------------------------------------------------------ */
+/* Counts candidate / real (r<2h) pairs of the current neighbour list (what JDsPips reports,
+ * JDsPips.cpp:116-142) for the flop model. */
+int b2s_count_pairs(b2s_ctx* ctx, uint64_t* checked, uint64_t* real);
+/* Times `reps` launches of the fluid interaction kernel alone on the ctx stream with CUDA events;
+ * returns mean milliseconds per launch (used by bench.py's roofline leg). */
+int b2s_time_interaction(b2s_ctx* ctx, int reps, float* ms_per_launch);
+/* Number of kernel launches issued by this ctx since creation / since last reset. */
+int b2s_launch_count(b2s_ctx* ctx, uint64_t* launches, int reset);
+/* CUDA stream the ctx launches on (cudaStream_t cast to void*), for external event timing. */
+int b2s_get_stream(b2s_ctx* ctx, void** stream_out);
+/* Selects the fluid interaction kernel variant: 0 = gather (one thread per particle, reference
+ * summation order), 1 = cell-tile (shared-memory staged). */
+int b2s_set_interaction_variant(b2s_ctx* ctx, int variant);
+
+/* ---- slab decomposition over several GPUs (no reference counterpart) ----------- */
+/* rank/nranks: position of this ctx in the slab chain along x.  The ctx keeps only particles with
+ * cell-x in [cx_begin,cx_end) plus one halo layer of scelldiv cells on each inner face. */
+int b2s_slab_config(b2s_ctx* ctx, int rank, int nranks, uint32_t cx_begin, uint32_t cx_end);
+/* Packs the particles lying in the halo layers next to the left/right cut into a contiguous device
+ * buffer (device pointers returned) for an NCCL send; counts in particles. Record layout:
+ * b2s_halo_rec (48 B). */
+int b2s_slab_pack_halo(b2s_ctx* ctx, int side, void** dev_buf, uint32_t* count);
+int b2s_slab_unpack_halo(b2s_ctx* ctx, int side, const void* dev_buf, uint32_t count);
+int b2s_slab_pack_migrants(b2s_ctx* ctx, int side, void** dev_buf, uint32_t* count);
+int b2s_slab_unpack_migrants(b2s_ctx* ctx, int side, const void* dev_buf, uint32_t count);
+/* dt maxima {acemax^2, viscdtmax, velmax^2} as device floats for ncclAllReduce(max), and apply. */
+int b2s_slab_dt_buffer(b2s_ctx* ctx, void** dev_float3);
+int b2s_slab_apply_dt(b2s_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2S_H_ */
