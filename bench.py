@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- WCSPH time-step throughput on B200 (metric of BASELINE.json: particle-steps/s, whole box).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own CPU/OpenMP path
+
+A "step" is one full ComputeStep of the synthetic 3-D dam-break block (BASELINE.json configs[1]: ~10M particles,
+Symplectic, Wendland, artificial viscosity 0.1, Fourtakas DDT, DBC), i.e. 2 cell divides + 2 interactions +
+predictor/corrector.  Prints ONE JSON line.  Keys beyond the base contract:
+  roofline      dominant kernel (fluid interaction) against its binding roof (FP32 issue)
+                + "hbm" views: the same kernel's algorithmic HBM bytes and the whole step's 0.71 KB/particle-step
+  cpu_baseline  the compiled reference CPU solver (oracle/_ref) on this box's host cores, bounded sample
+  e2e           same metric through the public API with HOST buffers: per step upload (pinned H2D) + step + download
+"""
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/sec (whole box) at 1/2/4/8 B200; interaction-kernel roofline fraction"
+UNIT = "particle-steps/s"
+OPTIONS = "-symplectic -wendland -viscoart:0.1 -ddt:2 -ddtvalue:0.1 -dbc"
+NP_TARGET = int(os.environ.get("B2S_BENCH_NP", "10000000"))
+CPU_SAMPLE_NP = int(os.environ.get("B2S_BENCH_CPU_NP", "1000000"))
+# flop model of SURVEY 8(d): per checked pair 16 flop, per real pair (r<2h) 90 flop
+FLOP_CHK, FLOP_REAL = 16.0, 90.0
+# algorithmic HBM bytes: interaction pass 50 B per fluid particle; whole Symplectic step 0.71 KB per particle
+BYTES_INTER, BYTES_STEP = 50.0, 710.0
+
+
+def peaks():
+    f = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(f):
+        d = json.load(open(f))
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+def make_case(np_target, tag):
+    from dualsphysics_b200 import casegen
+    d = os.path.join(tempfile.gettempdir(), f"b2s_bench_{tag}_{np_target}")
+    if not os.path.exists(os.path.join(d, "Case.bi4")):
+        dp = casegen.dp_for_target(np_target)
+        casegen.write_case(d, "Case", casegen.DamBreakSpec(dp=dp, params={"TimeMax": 10.0}))
+    return os.path.join(d, "Case")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if "Active" in r[5 + k] and "Not" not in r[5 + k]:
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def run_reference_sample(np_target, steps, warmup, threads=None):
+    """Times the compiled reference CPU solver (oracle/_ref/dsph_ref_probe, unmodified DualSPHysics v5.4 objects)."""
+    from oracle import oracle as orc
+    if not os.path.exists(orc.REF_PROBE):
+        return None
+    case = make_case(np_target, "cpu")
+    ncores = os.cpu_count() or 1
+    th = min(threads or ncores, 64)          # OMP_MAXTHREADS 64 (src/source/OmpDefs.h:39)
+    out = tempfile.mkdtemp(prefix="b2s_ref_")
+
+    def once(n):
+        cmd = [orc.REF_PROBE, case, out, str(n), "-dumplevel:0", "-sv:none", f"-ompthreads:{th}"] + OPTIONS.split()
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        m = re.search(r"PROBE_RESULT steps=(\d+) np=(\d+) seconds=([0-9.eE+-]+) omp_threads=(\d+)", r.stdout)
+        if not m:
+            raise RuntimeError("reference probe failed: " + r.stdout[-2000:])
+        return int(m.group(1)), int(m.group(2)), float(m.group(3)), int(m.group(4))
+    # the probe always starts from t=0; warm-up steps are timed separately and subtracted
+    s_w, npc, t_w, thr = once(warmup) if warmup else (0, 0, 0.0, th)
+    s_a, npc, t_a, thr = once(warmup + steps)
+    secs = max(t_a - t_w, 1e-9)
+    return {"value": npc * steps / secs, "np": npc, "steps": steps, "seconds": secs, "cores": thr,
+            "ms_per_step": secs / steps * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--np", type=int, default=NP_TARGET)
+    ap.add_argument("--variant", type=int, default=int(os.environ.get("B2S_VARIANT", "-1")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        res = run_reference_sample(CPU_SAMPLE_NP, max(1, min(a.steps, 5)), min(a.warmup, 1))
+        if res is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (needs /root/reference in the build container)"}))
+            return 0
+        sample = f"{res['np']} particles x {res['steps']} steps of the same dam-break block (lattice start), {res['cores']} OpenMP threads"
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": res["steps"],
+                "warmup": min(a.warmup, 1), "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"synthetic 3D dam-break block, {OPTIONS}; reference CPU/OpenMP build on a bounded sample", "np": res["np"]},
+                "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference", "sample": sample},
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ this repo's arm
+    import torch
+    import numpy as np
+    import dualsphysics_b200 as dsb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+    hbm_gbs, sm_max_mhz, peak_src = peaks()
+
+    case = make_case(a.np, "gpu") if rank == 0 or True else None
+    sim = dsb.Simulation(case, options=OPTIONS, device=dev)
+    ctx = sim.ctx
+    if a.variant >= 0:
+        ctx.set_variant(a.variant)
+    else:
+        try:
+            ctx.set_variant(1)
+            ctx.interaction(dsb.lib.INTER_SYMPREDICTOR)
+        except dsb.B2SError:
+            ctx.set_variant(0)
+    p = sim.params
+    info0 = ctx.info()
+    np_total = info0.np
+    npf = info0.np - info0.npb
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    ctx.run_steps(warmup)
+    # ---- timed steps: wall clock bracketed by barrier+synchronize, max over ranks
+    sampler = ClockSampler(dev) if rank == 0 else None
+    ctx.launch_count(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    ctx.run_steps(a.steps)
+    barrier()
+    secs = time.perf_counter() - t0
+    launches = ctx.launch_count()
+    if dist is not None:
+        t = torch.tensor([secs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+        cnt = torch.tensor([float(np_total), float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        np_all, launches_all = int(cnt[0].item()), int(cnt[1].item())
+    else:
+        np_all, launches_all = np_total, launches
+    value = np_all * a.steps / secs
+    clocks = sampler.stop() if sampler else None
+
+    line = None
+    if rank == 0:
+        # ---- dominant kernel alone: CUDA events on the ctx stream (b2s_time_interaction), flop model from pair counts
+        ms_k = ctx.time_interaction(5)
+        chk, real = ctx.count_pairs()
+        flops = FLOP_CHK * chk + FLOP_REAL * real
+        tf_ach = flops / (ms_k * 1e-3) / 1e12
+        fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12      # 148 SMs x 128 lanes x 2 flop x max SM clock
+        gbs_k = BYTES_INTER * npf / (ms_k * 1e-3) / 1e9
+        gbs_step = BYTES_STEP * np_total / (secs / a.steps) / 1e9
+        roofline = {"kernel": "k_forces_fluid (fluid<-fluid+bound interaction)", "bound": "fp32", "achieved": tf_ach, "peak": fp32_peak,
+                    "unit": "TFLOP/s", "frac": tf_ach / fp32_peak, "traffic": None, "peak_source": "148 SM x 128 FP32 lanes x 2 x clocks.max.sm (non-tensor)",
+                    "ms_per_launch": ms_k, "pairs_checked": chk, "pairs_real": real, "flop_model": "16*checked + 90*real (SURVEY 8d)",
+                    "share_of_step": 2 * ms_k / (secs / a.steps * 1e3),
+                    "hbm": {"bound": "hbm", "achieved": gbs_k, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs_k / hbm_gbs,
+                            "algorithmic_bytes_per_particle": BYTES_INTER, "peak_source": peak_src},
+                    "hbm_whole_step": {"bound": "hbm", "achieved": gbs_step, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs_step / hbm_gbs,
+                                       "algorithmic_bytes_per_particle_step": BYTES_STEP, "peak_source": peak_src}}
+        # ---- e2e: host buffers in, host buffers out, every step (pinned memory; copies inside the timed region)
+        e2e = None
+        if not a.no_e2e:
+            n = np_total
+            h_idp = torch.empty(n, dtype=torch.int32).pin_memory()
+            h_code = torch.empty(n, dtype=torch.int16).pin_memory()
+            h_pos = torch.empty(n * 3, dtype=torch.float64).pin_memory()
+            h_vr = torch.empty(n * 4, dtype=torch.float32).pin_memory()
+            lib = dsb.load_library()
+            import ctypes as C
+
+            def download():
+                cnt_ = C.c_uint32(0)
+                r = lib.b2s_download_particles(ctx._h, C.byref(cnt_), h_idp.data_ptr(), h_code.data_ptr(), h_pos.data_ptr(), h_vr.data_ptr())
+                assert r == 0, r
+                return cnt_.value
+            n = download()
+            ksteps = max(2, min(a.steps, 5))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(ksteps):
+                ctx.upload_ptrs(n, h_idp.data_ptr(), h_code.data_ptr(), h_pos.data_ptr(), h_vr.data_ptr())
+                ctx.compute_step()
+                n = download()
+            torch.cuda.synchronize()
+            se = time.perf_counter() - t0
+            e2e = {"value": n * ksteps / se, "unit": UNIT, "h2d_bytes_per_step": n * (4 + 2 + 24 + 16), "d2h_bytes_per_step": n * (4 + 2 + 24 + 16),
+                   "steps": ksteps, "note": "per step: b2s_upload_particles (pinned host -> device, incl. first cell divide) + b2s_compute_step + b2s_download_particles"}
+        # ---- CPU baseline: the reference's own CPU solver on this box's cores, bounded sample
+        cpu = None
+        if not a.no_cpu_baseline and world == 1:
+            try:
+                res = run_reference_sample(CPU_SAMPLE_NP, 3, 1)
+                if res:
+                    cpu = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
+                           "sample": f"{res['np']} particles x {res['steps']} steps of the same dam-break block, oracle/_ref/dsph_ref_probe (unmodified DualSPHysics v5.4 CPU objects), {res['cores']} OpenMP threads"}
+            except Exception as ex:  # noqa: BLE001
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warmup,
+                "ms_per_step": secs / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"synthetic 3D dam-break block (BASELINE configs[1]), {OPTIONS}, lattice start", "np_per_gpu": np_total,
+                           "np_total": np_all, "fluid_per_gpu": npf, "interaction_variant": ctx._lib and (a.variant if a.variant >= 0 else "auto"),
+                           "parallelism": "single GPU" if world == 1 else f"{world} independent slab replicas (halo exchange not built this round)",
+                           "l2_note": "working set ~2.3 GB per GPU >> 126 MB L2"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks}
+    sim.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

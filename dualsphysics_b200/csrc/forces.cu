@@ -239,18 +239,12 @@ __global__ void __launch_bounds__(F_BS) k_forces_fluid_gather(ForcesArgs g, cons
       }
     }
     //-Store (JSphCpu.cpp:1086-1102 fluid pass then bound pass; JSphGpu_ker.cu:939-950 for the GPU semantics).
-    float arf=af.ar, arb=ab.ar;
-    if(TDENS!=B2S_DDT_NONE){
-      if(c.refsem==B2S_REFSEM_GPU){
-        if(af.delta!=FLT_MAX && ab.delta!=FLT_MAX)arb+=af.delta+ab.delta;
-      }
-      else{
-        if(af.delta!=FLT_MAX)arf+=af.delta;
-        if(ab.delta!=FLT_MAX)arb+=ab.delta;
-      }
-    }
+    // The density-diffusion sum is kept apart and added last, and a DBC boundary neighbour (FLT_MAX marker)
+    // discards it completely: this is what both reference builds do (GPU: one running deltap1, JSphGpu_ker.cu:939-946;
+    // CPU: DDTArray=true on CPU, JSph.cpp:927, Delta_c added after both passes, JSphCpuSingle.cpp:723-731).
     float4 res;
-    res.x=af.ax+ab.ax; res.y=af.ay+ab.ay; res.z=af.az+ab.az; res.w=arf+arb;
+    res.x=af.ax+ab.ax; res.y=af.ay+ab.ay; res.z=af.az+ab.az; res.w=af.ar+ab.ar;
+    if(TDENS!=B2S_DDT_NONE && af.delta!=FLT_MAX && ab.delta!=FLT_MAX)res.w+=(af.delta+ab.delta);
     if(c.simulate2d)res.y=0.f;
     g.acear[p1]=res;
     viscmax=fmaxf(af.visc,ab.visc);

@@ -1,0 +1,483 @@
+// sim.cpp -- C++ host driver: GenCase case in (Case.xml + Case.bi4), Part_XXXX.bi4 out, Run/ComputeStep loop.
+//
+// Mirrors, for the hot path only, the host side of the reference (all under /root/reference/src/source):
+//   JSph::LoadCaseConfig / LoadConfigCtes / LoadConfigParameters / LoadConfigCommands   JSph.cpp:553-1003
+//   JCaseEParms (parameters + <simulationdomain>)                                       JCaseEParms.cpp:150-439
+//   JCaseParts::ReadXml (particle blocks)                                               JCaseParts.cpp:79-84,274-297,540-567
+//   JSphMk (particle code per block)                                                    JSphMk.cpp:95-125
+//   JPartsLoad4::LoadParticles + JSph::LoadCaseParticles / ResizeMapLimits              JPartsLoad4.cpp:164-290, JSph.cpp:1445-1476,2151-2198
+//   JSphGpuSingle::Run main loop + SaveData                                             JSphGpuSingle.cpp:950-1118
+//   JSph::SavePartData (Part_XXXX.bi4, Part_Head.ibi4 omitted values documented in DESIGN.md)  JSph.cpp:3062-3146
+// Everything numerical happens behind the C-ABI (include/b2s.h); this file owns no CUDA code.
+#include "../../../include/b2s.h"
+#include "../../../include/b2s_host.h"
+#include "xml_lite.h"
+#include "bi4.h"
+#include <cmath>
+#include <cfloat>
+#include <cstring>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include <sstream>
+#include <stdexcept>
+#include <algorithm>
+#include <sys/stat.h>
+
+using namespace b2s;
+
+struct PartBlock { int type; unsigned mktype, mk, begin, count; // type: 0 fixed,1 moving,2 floating,3 fluid
+  double massbody, masspart, center[3], inertia[9], linvelini[3], angvelini[3]; int transfree[3], rotfree[3]; unsigned refmotion; };
+struct MotionCfg { unsigned ref; double freq[3], ampl[3], phase[3], tstart, tend; };
+
+struct b2s_sim {
+  std::string casepath, casename, dirout, dirdata, err;
+  b2s_params prm;
+  b2s_ctx* ctx;
+  std::vector<PartBlock> blocks;
+  std::vector<MotionCfg> motions;
+  // run control (JSph members)
+  double timemax, timepart, timepartnext; unsigned part, nstepsbreak; bool svallsteps, svposdouble, svdata;
+  double casedp, caseh, caseb, caserhop0, casegamma, casemassb, casemassf;
+  double caseposmin[3], caseposmax[3];
+  unsigned np0;
+  b2s_sim():ctx(NULL),timemax(0),timepart(0),timepartnext(0),part(0),nstepsbreak(0),svallsteps(false),svposdouble(false),svdata(true),np0(0){ memset(&prm,0,sizeof(prm)); }
+};
+
+static std::string g_host_err;
+
+// ---- small helpers ------------------------------------------------------------------------------------
+static std::string lower(std::string s){ for(auto& c:s)c=char(tolower((unsigned char)c)); return s; }
+static std::string upper(std::string s){ for(auto& c:s)c=char(toupper((unsigned char)c)); return s; }
+static double todouble(const std::string& s){ return atof(s.c_str()); }
+static bool read_xyz(const XmlNode* n,double v[3]){ if(!n)return false; v[0]=todouble(n->attr("x","0")); v[1]=todouble(n->attr("y","0")); v[2]=todouble(n->attr("z","0")); return true; }
+static void mkdirs(const std::string& d){ std::string cur; for(size_t i=0;i<d.size();i++){ cur+=d[i]; if(d[i]=='/'||i+1==d.size())mkdir(cur.c_str(),0777); } }
+
+// JCaseEParms::CheckPosValue (JCaseEParms.cpp:374-414): mode 0 default, 1 fixed, 2 default+-value, 3 default+-percent
+static int parse_posvalue(const std::string& value,bool isposmin,double& out){
+  std::string v; for(char c:value)if(c!=' '&&c!='\t')v+=char(tolower((unsigned char)c));
+  out=0;
+  if(v=="default"||v.empty())return 0;
+  if(v.compare(0,8,"default+")==0 || v.compare(0,8,"default-")==0){
+    const char sign=v[7];
+    if((isposmin && sign=='+') || (!isposmin && sign=='-'))throw std::runtime_error("simulationdomain: wrong sign in '"+value+"'");
+    const bool prc=(!v.empty() && v[v.size()-1]=='%');
+    out=atof(v.substr(8,v.size()-(prc? 9: 8)).c_str());
+    return prc? 3: 2;
+  }
+  out=atof(v.c_str());
+  return 1;
+}
+
+struct EParms {
+  std::vector<std::pair<std::string,std::string>> kv;
+  std::string posmin[3], posmax[3];
+  bool exists(const std::string& k)const{ for(auto& p:kv)if(p.first==k)return true; return false; }
+  std::string str(const std::string& k,const std::string& def="")const{ for(auto& p:kv)if(p.first==k)return p.second; return def; }
+  double num(const std::string& k,double def)const{ return exists(k)? todouble(str(k)): def; }
+  int inum(const std::string& k,int def)const{ return exists(k)? atoi(str(k).c_str()): def; }
+};
+
+// ---- case loading --------------------------------------------------------------------------------------
+static void load_case(b2s_sim* s,const std::string& options){
+  const std::string filexml=s->casepath+".xml";
+  std::unique_ptr<XmlNode> root=xml_load(filexml);
+  if(root->name!="case")throw std::runtime_error("Case.xml: root element <case> not found");
+  const XmlNode* exe=root->child("execution");
+  if(!exe)throw std::runtime_error("Case.xml: <execution> not found");
+  b2s_params& p=s->prm;
+  // -- constants (JCaseCtes::ReadXmlRun)
+  const XmlNode* ct=exe->child("constants");
+  if(!ct)throw std::runtime_error("Case.xml: <execution><constants> not found");
+  auto cval=[&](const char* n,bool opt=false,double def=0){ const XmlNode* e=ct->child(n); if(!e){ if(opt)return def; throw std::runtime_error(std::string("Case.xml: constant missing: ")+n); } return todouble(e->attr("value","0")); };
+  { const XmlNode* e=ct->child("data2d"); const std::string v=(e? lower(e->attr("value","false")): "false"); p.simulate2d=(v=="true"||v=="1")? 1: 0; }
+  if(p.simulate2d)throw std::runtime_error("2-D cases are not supported by this build");
+  double g[3]; if(!read_xyz(ct->child("gravity"),g))throw std::runtime_error("Case.xml: gravity missing");
+  for(int k=0;k<3;k++)p.gravity[k]=float(g[k]);
+  p.cflnumber=cval("cflnumber"); p.gamma=float(cval("gamma")); p.rhopzero=float(cval("rhop0")); p.dp=cval("dp");
+  p.kernelh=float(cval("h")); p.cteb=float(cval("b")); p.massbound=float(cval("massbound")); p.massfluid=float(cval("massfluid"));
+  // -- parameters (JCaseEParms + JSph::LoadConfigParameters)
+  EParms ep;
+  const XmlNode* pr=exe->child("parameters");
+  if(!pr)throw std::runtime_error("Case.xml: <execution><parameters> not found");
+  for(auto& c:pr->children){
+    if(c->name=="parameter")ep.kv.emplace_back(c->attr("key"),c->attr("value"));
+    else if(c->name=="simulationdomain"){
+      const XmlNode* a=c->child("posmin"); const XmlNode* b=c->child("posmax");
+      const char* ax[3]={"x","y","z"};
+      for(int k=0;k<3;k++){ ep.posmin[k]=(a? a->attr(ax[k],"default"): "default"); ep.posmax[k]=(b? b->attr(ax[k],"default"): "default"); }
+    }
+  }
+  switch(ep.inum("Kernel",2)){ case 1: p.tkernel=B2S_KERNEL_CUBIC; break; case 2: p.tkernel=B2S_KERNEL_WENDLAND; break; default: throw std::runtime_error("Kernel choice is not valid."); }
+  if(ep.inum("RigidAlgorithm",1)!=1)throw std::runtime_error("only RigidAlgorithm=1 (SPH) is supported");
+  switch(ep.inum("StepAlgorithm",1)){ case 1: p.tstep=B2S_STEP_VERLET; break; case 2: p.tstep=B2S_STEP_SYMPLECTIC; break; default: throw std::runtime_error("Step algorithm is not valid."); }
+  p.verletsteps=ep.inum("VerletSteps",40);
+  switch(ep.inum("ViscoTreatment",1)){ case 1: p.tvisco=B2S_VISCO_ARTIFICIAL; break; case 2: p.tvisco=B2S_VISCO_LAMINARSPS; break; case 3: p.tvisco=B2S_VISCO_LAMINAR; break; default: throw std::runtime_error("Viscosity treatment is not valid."); }
+  if(!ep.exists("Visco"))throw std::runtime_error("parameter Visco missing");
+  p.visco=float(ep.num("Visco",0)); p.viscoboundfactor=float(ep.num("ViscoBoundFactor",1));
+  switch(ep.inum("Boundary",1)){ case 1: p.tboundary=B2S_BC_DBC; break; case 2: p.tboundary=B2S_BC_MDBC; break; default: throw std::runtime_error("Boundary Condition method is not valid."); }
+  p.slipmode=0;
+  if(p.tboundary==B2S_BC_MDBC)p.slipmode=ep.inum("SlipMode",1);
+  { const int tddt=ep.inum("DensityDT",0); if(tddt<0||tddt>3)throw std::runtime_error("Density Diffusion Term mode is not valid."); p.tdensity=tddt; p.ddtvalue=float(ep.num("DensityDTvalue",0.1)); }
+  if(ep.inum("Shifting",0)!=0)throw std::runtime_error("Shifting is not supported by this build (out of the hot-path scope)");
+  p.ftpause=ep.num("FtPause",0);
+  s->timemax=ep.num("TimeMax",0); s->timepart=ep.num("TimeOut",0);
+  p.dtini=std::max(0.0,ep.num("DtIni",0)); p.dtmin=std::max(0.0,ep.num("DtMin",0)); p.coefdtmin=double(float(ep.num("CoefDtMin",0.05)));
+  p.dt_allparticles=(ep.inum("DtAllParticles",0)==1);
+  if(ep.num("DtFixed",0)!=0)throw std::runtime_error("DtFixed is not supported by this build");
+  p.rhopoutmin=float(ep.num("RhopOutMin",700)); p.rhopoutmax=float(ep.num("RhopOutMax",1300));
+  s->svposdouble=(ep.inum("SavePosDouble",0)!=0);
+  for(const char* k:{"XPeriodicIncY","XPeriodicIncZ","YPeriodicIncX","YPeriodicIncZ","ZPeriodicIncX","ZPeriodicIncY","XYPeriodic","XZPeriodic","YZPeriodic"})
+    if(ep.exists(k))throw std::runtime_error("periodic boundaries are not supported by this build (SURVEY 8f 'next' row)");
+  // -- command-line style overrides (JSphCfgRun::LoadArgv + JSph::LoadConfigCommands)
+  int cellmode_half=0; int opt_boundary=-1, opt_slip=1;
+  {
+    std::stringstream ss(options); std::string tok;
+    while(ss>>tok){
+      if(tok[0]!='-')throw std::runtime_error("invalid option '"+tok+"'");
+      std::string w=tok.substr(1), a; size_t c=w.find(':'); if(c!=std::string::npos){ a=w.substr(c+1); w=w.substr(0,c); }
+      w=upper(w);
+      auto a2=[&](int i){ std::string t=a; for(int k=0;k<i;k++){ size_t q=t.find(':'); t=(q==std::string::npos? "": t.substr(q+1)); } size_t q=t.find(':'); return q==std::string::npos? t: t.substr(0,q); };
+      if(w=="GPU"||w=="CPU"||w=="STABLE"||w=="SVRES"||w=="SVTIMERS"||w=="NORTIMES"||w=="OMPTHREADS"||w=="SVDOMAINVTK"){}
+      else if(w=="SYMPLECTIC")p.tstep=B2S_STEP_SYMPLECTIC;
+      else if(w=="VERLET"){ p.tstep=B2S_STEP_VERLET; if(!a.empty())p.verletsteps=atoi(a.c_str()); }
+      else if(w=="WENDLAND")p.tkernel=B2S_KERNEL_WENDLAND;
+      else if(w=="CUBIC")p.tkernel=B2S_KERNEL_CUBIC;
+      else if(w=="VISCOART"){ p.tvisco=B2S_VISCO_ARTIFICIAL; p.visco=float(atof(a.c_str())); }
+      else if(w=="VISCOLAM"){ p.tvisco=B2S_VISCO_LAMINAR; p.visco=float(atof(a.c_str())); }
+      else if(w=="VISCOLAMSPS"){ p.tvisco=B2S_VISCO_LAMINARSPS; p.visco=float(atof(a.c_str())); }
+      else if(w=="VISCOBOUNDFACTOR")p.viscoboundfactor=float(atof(a.c_str()));
+      else if(w=="DDT"){ p.tdensity=atoi(a.c_str()); if(p.tdensity<0||p.tdensity>3)throw std::runtime_error("Density Diffusion Term mode is not valid."); if(p.ddtvalue==0)p.ddtvalue=0.1f; }
+      else if(w=="DDTVALUE")p.ddtvalue=float(atof(a.c_str()));
+      else if(w=="DBC"){ opt_boundary=1; }
+      else if(w=="MDBC"){ opt_boundary=2; opt_slip=1; }
+      else if(w=="MDBC_NOSLIP"){ opt_boundary=2; opt_slip=2; }
+      else if(w=="MDBC_FREESLIP"){ opt_boundary=2; opt_slip=3; }
+      else if(w=="CELLMODE"){ const std::string u=upper(a); if(u=="HALF"||u=="H")cellmode_half=1; else if(u=="FULL"||u=="2H")cellmode_half=0; else throw std::runtime_error("invalid cellmode"); }
+      else if(w=="RHOPOUT"){ p.rhopoutmin=float(atof(a2(0).c_str())); p.rhopoutmax=float(atof(a2(1).c_str())); }
+      else if(w=="CFL")p.cflnumber=atof(a.c_str());
+      else if(w=="FTPAUSE")p.ftpause=atof(a.c_str());
+      else if(w=="TMAX")s->timemax=atof(a.c_str());
+      else if(w=="TOUT")s->timepart=atof(a.c_str());
+      else if(w=="NSTEPS")s->nstepsbreak=unsigned(atoi(a.c_str()));
+      else if(w=="SVSTEPS")s->svallsteps=(a.empty()||atoi(a.c_str())!=0);
+      else if(w=="SAVEPOSDOUBLE")s->svposdouble=(a.empty()||atoi(a.c_str())!=0);
+      else if(w=="SV"){ s->svdata=(lower(a).find("none")==std::string::npos); }
+      else throw std::runtime_error("option not supported by this build: "+tok);
+    }
+  }
+  if(opt_boundary>0){ p.tboundary=(opt_boundary==2? B2S_BC_MDBC: B2S_BC_DBC); p.slipmode=(opt_boundary==2? opt_slip: 0); }
+  if(p.tboundary==B2S_BC_MDBC && p.slipmode!=B2S_SLIP_VEL0)throw std::runtime_error("mDBC slip modes 2/3 (mDBC2) are not supported by this build; use SlipMode=1");
+  p.mdbc_corrector=(p.slipmode>=B2S_SLIP_NOSLIP)? 1: 0;   // MdbcCorrector (JSph.cpp:899)
+  if(p.tdensity==B2S_DDT_NONE)p.ddtvalue=0;
+  p.cellmode_half=cellmode_half;
+  if(!(p.rhopoutmin<p.rhopoutmax)){ p.rhopoutmin=-FLT_MAX; p.rhopoutmax=FLT_MAX; }
+  // -- particles (JCaseParts::ReadXml)
+  const XmlNode* pa=exe->child("particles");
+  if(!pa)throw std::runtime_error("Case.xml: <execution><particles> not found");
+  unsigned cnt[4]={0,0,0,0};
+  for(auto& c:pa->children){
+    int t=-1;
+    if(c->name=="fixed")t=0; else if(c->name=="moving")t=1; else if(c->name=="floating")t=2; else if(c->name=="fluid")t=3;
+    else if(c->name=="properties"||c->name[0]=='_')continue;
+    else throw std::runtime_error("Case.xml: unknown particle block <"+c->name+">");
+    PartBlock b; memset(&b,0,sizeof(b));
+    b.type=t; b.mktype=unsigned(atoi(c->attr(t==3? "mkfluid": "mkbound","0").c_str())); b.mk=unsigned(atoi(c->attr("mk","0").c_str()));
+    b.begin=unsigned(strtoul(c->attr("begin","0").c_str(),NULL,10)); b.count=unsigned(strtoul(c->attr("count","0").c_str(),NULL,10));
+    if(t==1)b.refmotion=unsigned(atoi(c->attr("refmotion","0").c_str()));
+    if(t==2){
+      const XmlNode* e;
+      if(!(e=c->child("massbody")))throw std::runtime_error("floating: massbody missing"); b.massbody=todouble(e->attr("value"));
+      if(!(e=c->child("masspart")))throw std::runtime_error("floating: masspart missing"); b.masspart=todouble(e->attr("value"));
+      if(!read_xyz(c->child("center"),b.center))throw std::runtime_error("floating: center missing");
+      e=c->child("inertia"); if(!e)throw std::runtime_error("floating: inertia missing");
+      if(e->has("x")&&e->has("y")&&e->has("z")){ double v[3]; read_xyz(e,v); b.inertia[0]=v[0]; b.inertia[4]=v[1]; b.inertia[8]=v[2]; }
+      else{
+        for(int r=1;r<=3;r++)for(int q=1;q<=3;q++){
+          char nm[8]; snprintf(nm,sizeof(nm),"v%d%d",r,q);
+          if(e->has(nm))b.inertia[(r-1)*3+q-1]=todouble(e->attr(nm));
+          for(const XmlNode* row:e->childs("values"))if(row->has(nm))b.inertia[(r-1)*3+q-1]=todouble(row->attr(nm));
+        }
+      }
+      for(int k=0;k<3;k++){ b.transfree[k]=1; b.rotfree[k]=1; }
+      const XmlNode* tf=(c->child("translation")? c->child("translation"): c->child("translationDOF"));
+      const XmlNode* rf=(c->child("rotation")? c->child("rotation"): c->child("rotationDOF"));
+      double v[3];
+      if(tf && read_xyz(tf,v))for(int k=0;k<3;k++)b.transfree[k]=(v[k]!=0);
+      if(rf && read_xyz(rf,v))for(int k=0;k<3;k++)b.rotfree[k]=(v[k]!=0);
+      const XmlNode* lv=(c->child("linearvelini")? c->child("linearvelini"): c->child("velini"));
+      const XmlNode* av=(c->child("angularvelini")? c->child("angularvelini"): c->child("omegaini"));
+      if(lv)read_xyz(lv,b.linvelini);
+      if(av)read_xyz(av,b.angvelini);
+      if(c->child("linearvel")||c->child("angularvel")||c->child("linearforce")||c->child("angularforce"))
+        throw std::runtime_error("floating: imposed velocity/force is not supported by this build");
+    }
+    cnt[t]+=b.count;
+    s->blocks.push_back(b);
+  }
+  p.casenfixed=cnt[0]; p.casenmoving=cnt[1]; p.casenfloat=cnt[2]; p.casenfluid=cnt[3]; p.casenp=cnt[0]+cnt[1]+cnt[2]+cnt[3];
+  { const unsigned np=unsigned(strtoul(pa->attr("np","0").c_str(),NULL,10)), nb=unsigned(strtoul(pa->attr("nb","0").c_str(),NULL,10)), nbf=unsigned(strtoul(pa->attr("nbf","0").c_str(),NULL,10));
+    if(np!=p.casenp || nb!=p.casenp-p.casenfluid || nbf!=p.casenfixed)throw std::runtime_error("The amount of particles does not match the header."); }
+  // -- motion (JMotion::ReadXml subset: objreal + mvrectsinu)
+  if(const XmlNode* mo=exe->child("motion")){
+    for(const XmlNode* o:mo->childs("objreal")){
+      const unsigned ref=unsigned(atoi(o->attr("ref","0").c_str()));
+      std::vector<std::pair<int,double>> begins;   // (mov id, start)
+      for(const XmlNode* b:o->childs("begin"))begins.emplace_back(atoi(b->attr("mov","0").c_str()),todouble(b->attr("start","0")));
+      for(auto& c:o->children){
+        if(c->name=="begin"||c->name[0]=='_')continue;
+        if(c->name!="mvrectsinu")throw std::runtime_error("motion <"+c->name+"> is not supported by this build (only mvrectsinu)");
+        MotionCfg m; memset(&m,0,sizeof(m)); m.ref=ref;
+        const int id=atoi(c->attr("id","0").c_str());
+        const double duration=todouble(c->attr("duration","0"));
+        if(atoi(c->attr("next","0").c_str())!=0)throw std::runtime_error("motion chains (next=) are not supported by this build");
+        if(!read_xyz(c->child("freq"),m.freq)||!read_xyz(c->child("ampl"),m.ampl))throw std::runtime_error("mvrectsinu: freq/ampl missing");
+        if(c->child("phase"))read_xyz(c->child("phase"),m.phase);
+        const bool deg=(c->attr("anglesunits","degrees")=="degrees");
+        if(deg)for(int k=0;k<3;k++)m.phase[k]*=M_PI/180.0;
+        bool started=false;
+        for(auto& b:begins)if(b.first==id){ m.tstart=b.second; m.tend=b.second+duration; started=true; }
+        if(started)s->motions.push_back(m);
+      }
+    }
+  }
+}
+
+static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capacity){
+  b2s_params& p=s->prm;
+  std::unique_ptr<Bi4Item> data=bi4_load(s->casepath+".bi4");
+  if(data->name!="JPartDataBi4")throw std::runtime_error("Case.bi4: root item JPartDataBi4 not found");
+  const Bi4Item* part=data->item("PART_0000");
+  if(!part)throw std::runtime_error("Case.bi4: PART_0000 not found");
+  if(data->get_uint("CaseNp")!=p.casenp || data->get_uint("CaseNfixed")!=p.casenfixed || data->get_uint("CaseNmoving")!=p.casenmoving
+     || data->get_uint("CaseNfloat")!=p.casenfloat || data->get_uint("CaseNfluid")!=p.casenfluid)
+    throw std::runtime_error("Particle number does not match the configuration of the case.");
+  if(data->get_bool("Data2d"))throw std::runtime_error("Data file does not match the dimension of the case (2D/3D).");
+  const unsigned np=unsigned(part->get_uint("Npok"));
+  const Bi4Array* aid=part->array("Idp"); const Bi4Array* apd=part->array("Posd"); const Bi4Array* apf=part->array("Pos");
+  const Bi4Array* avel=part->array("Vel"); const Bi4Array* arho=part->array("Rhop"); const Bi4Array* anor=part->array("BoundNor");
+  if(!aid)throw std::runtime_error("Only Idp (32 bits) is valid at the moment.");
+  if((!apd&&!apf)||!avel||!arho)throw std::runtime_error("Case.bi4: particle arrays missing");
+  if(aid->count!=np||avel->count!=np||arho->count!=np)throw std::runtime_error("Case.bi4: array sizes do not match Npok");
+  const uint32_t* idp=(const uint32_t*)aid->ptr();
+  std::vector<double> pos(size_t(np)*3);
+  if(apd)memcpy(pos.data(),apd->ptr(),size_t(np)*24);
+  else{ const float* f=(const float*)apf->ptr(); for(size_t i=0;i<size_t(np)*3;i++)pos[i]=double(f[i]); }
+  const float* vel=(const float*)avel->ptr(); const float* rho=(const float*)arho->ptr();
+  std::vector<float> velrho(size_t(np)*4);
+  for(unsigned i=0;i<np;i++){ velrho[size_t(i)*4]=vel[size_t(i)*3]; velrho[size_t(i)*4+1]=vel[size_t(i)*3+1]; velrho[size_t(i)*4+2]=vel[size_t(i)*3+2]; velrho[size_t(i)*4+3]=rho[i]; }
+  // CheckSortParticles: boundary ids occupy the first slots (JPartsLoad4.cpp:131-140)
+  const unsigned nbound=p.casenfixed+p.casenmoving+p.casenfloat;
+  { unsigned lastbound=0; for(unsigned i=0;i<np;i++)if(idp[i]<nbound && i>lastbound)lastbound=i; if(nbound && lastbound+1!=nbound)throw std::runtime_error("Order of boundary (fixed, moving and floating) particles is invalid."); }
+  // CheckRhoLimits (JSph.cpp:2136-2145)
+  for(unsigned i=0;i<np;i++)if(idp[i]>=nbound && (rho[i]<p.rhopoutmin || rho[i]>p.rhopoutmax))throw std::runtime_error("Initial fluid density is out of limits.");
+  // particle codes (JSphMk)
+  std::vector<uint16_t> code(np);
+  {
+    unsigned idx[4]={0,0,0,0};
+    const uint16_t tcode[4]={0x0000,0x0800,0x1000,0x1800};
+    std::vector<uint16_t> codeofid(p.casenp,0);
+    for(auto& b:s->blocks){ const uint16_t c=uint16_t(tcode[b.type]|idx[b.type]); idx[b.type]++; for(unsigned k=0;k<b.count;k++){ if(b.begin+k>=p.casenp)throw std::runtime_error("particle block exceeds np"); codeofid[b.begin+k]=c; } }
+    for(unsigned i=0;i<np;i++){ if(idp[i]>=p.casenp)throw std::runtime_error("particle id exceeds np"); code[i]=codeofid[idp[i]]; }
+  }
+  // map limits: CalculeLimits(KernelH*BORDER_MAP) + ResizeMapLimits (JSph.cpp:2174-2178,1445-1476)
+  double cmin[3],cmax[3];
+  if(!data->get_double3("CasePosMin",cmin) || !data->get_double3("CasePosMax",cmax) || (cmin[0]==cmax[0]&&cmin[1]==cmax[1]&&cmin[2]==cmax[2])){
+    for(int k=0;k<3;k++){ cmin[k]=DBL_MAX; cmax[k]=-DBL_MAX; }
+    for(unsigned i=0;i<np;i++)for(int k=0;k<3;k++){ cmin[k]=std::min(cmin[k],pos[size_t(i)*3+k]); cmax[k]=std::max(cmax[k],pos[size_t(i)*3+k]); }
+  }
+  for(int k=0;k<3;k++){ s->caseposmin[k]=cmin[k]; s->caseposmax[k]=cmax[k]; }
+  double mpmin[3],mpmax[3]; bool mapsize=false;
+  if(data->get_double3("MapPosMin",mpmin) && data->get_double3("MapPosMax",mpmax))mapsize=!(mpmin[0]==mpmax[0]&&mpmin[1]==mpmax[1]&&mpmin[2]==mpmax[2]);
+  if(mapsize){ for(int k=0;k<3;k++){ p.maprealposmin[k]=mpmin[k]; p.maprealposmax[k]=mpmax[k]; } }
+  else{
+    const double border=double(p.kernelh)*0.05;   // BORDER_MAP (DualSphDef.h:112)
+    double dmin[3],dmax[3],rmin[3],rmax[3];
+    for(int k=0;k<3;k++){ rmin[k]=cmin[k]-border; rmax[k]=cmax[k]+border; dmin[k]=rmin[k]; dmax[k]=rmax[k]; }
+    // re-read <simulationdomain> to apply default+-value / default+-% / fixed
+    std::unique_ptr<XmlNode> root=xml_load(s->casepath+".xml");
+    const XmlNode* sd=root->path("execution.parameters.simulationdomain");
+    const char* ax[3]={"x","y","z"};
+    double prcmin[3]={0,0,0},prcmax[3]={0,0,0},valmin[3]={0,0,0},valmax[3]={0,0,0},fixmin[3],fixmax[3]; bool hasfixmin[3]={false,false,false},hasfixmax[3]={false,false,false};
+    if(sd)for(int k=0;k<3;k++){
+      double v; int m;
+      const XmlNode* a=sd->child("posmin"); const XmlNode* b=sd->child("posmax");
+      m=parse_posvalue(a? a->attr(ax[k],"default"): "default",true,v);  if(m==1){ fixmin[k]=v; hasfixmin[k]=true; } else if(m==2)valmin[k]=v; else if(m==3)prcmin[k]=v/100;
+      m=parse_posvalue(b? b->attr(ax[k],"default"): "default",false,v); if(m==1){ fixmax[k]=v; hasfixmax[k]=true; } else if(m==2)valmax[k]=v; else if(m==3)prcmax[k]=v/100;
+    }
+    for(int k=0;k<3;k++){
+      const double dif=dmax[k]-dmin[k];
+      double a=dmin[k]-dif*prcmin[k], b=dmax[k]+dif*prcmax[k];
+      a=a-valmin[k]; b=b+valmax[k];
+      if(hasfixmin[k])a=fixmin[k];
+      if(hasfixmax[k])b=fixmax[k];
+      if(a>rmin[k] || b<rmax[k])throw std::runtime_error("Domain limits are not valid.");
+      p.maprealposmin[k]=a; p.maprealposmax[k]=b;
+    }
+  }
+  s->casedp=data->get_double("Dp",p.dp); s->caseh=data->get_double("H",p.kernelh); s->caseb=data->get_double("B",p.cteb);
+  s->caserhop0=data->get_double("Rhop0",p.rhopzero); s->casegamma=data->get_double("Gamma",p.gamma);
+  s->casemassb=data->get_double("MassBound",p.massbound); s->casemassf=data->get_double("MassFluid",p.massfluid);
+  int r=b2s_config_finalize(&p);
+  if(r)throw std::runtime_error(std::string("configuration failed: ")+b2s_error_string(r));
+  r=b2s_create(&p,device,np+extra_capacity,&s->ctx);
+  if(r)throw std::runtime_error(std::string("b2s_create failed: ")+b2s_error_string(r));
+  // floating bodies (JSph::InitFloatings subset, JSph.cpp:1190-1290)
+  if(p.casenfloat){
+    std::vector<b2s_floating> fts;
+    for(auto& b:s->blocks)if(b.type==2){
+      b2s_floating f; memset(&f,0,sizeof(f));
+      f.begin=b.begin; f.count=b.count; f.mass=float(b.massbody); f.massp=float(b.masspart);
+      f.constraints=(b.transfree[0]?0:1)|(b.transfree[1]?0:2)|(b.transfree[2]?0:4)|(b.rotfree[0]?0:8)|(b.rotfree[1]?0:16)|(b.rotfree[2]?0:32);
+      for(int k=0;k<3;k++){ f.center[k]=b.center[k]; f.fvel[k]=float(b.linvelini[k]); f.fomega[k]=float(b.angvelini[k]); }
+      for(int k=0;k<9;k++)f.inertiaini[k]=float(b.inertia[k]);
+      // radius = max distance particle-centre (JSph::InitFloatings)
+      double r2max=0;
+      for(unsigned i=0;i<np;i++)if(idp[i]>=b.begin && idp[i]<b.begin+b.count){ double d2=0; for(int k=0;k<3;k++){ const double d=pos[size_t(i)*3+k]-b.center[k]; d2+=d*d; } r2max=std::max(r2max,d2); }
+      f.radius=float(sqrt(r2max));
+      fts.push_back(f);
+    }
+    r=b2s_set_floatings(s->ctx,unsigned(fts.size()),fts.data());
+    if(r)throw std::runtime_error(std::string("b2s_set_floatings failed: ")+b2s_last_error(s->ctx));
+  }
+  for(auto& m:s->motions){
+    const PartBlock* blk=NULL;
+    for(auto& b:s->blocks)if(b.type==1 && b.refmotion==m.ref)blk=&b;
+    if(!blk)continue;
+    r=b2s_add_motion_rectsinu(s->ctx,blk->begin,blk->count,m.freq,m.ampl,m.phase,m.tstart,m.tend);
+    if(r)throw std::runtime_error(std::string("b2s_add_motion_rectsinu failed: ")+b2s_last_error(s->ctx));
+  }
+  std::vector<float> nor;
+  const float* norp=NULL;
+  if(p.tboundary==B2S_BC_MDBC){
+    if(!anor)throw std::runtime_error("No normal data for mDBC in the input file.");
+    if(anor->count!=nbound)throw std::runtime_error("Size of loaded BoundNor data does not match number of boundary particles.");
+    nor.assign((const float*)anor->ptr(),(const float*)anor->ptr()+size_t(nbound)*3);
+    for(auto& v:nor)v*=2.f;   // boundary->interface normals doubled to reach the ghost node (JSph.cpp:1417)
+    norp=nor.data();
+  }
+  r=b2s_upload_particles(s->ctx,np,idp,code.data(),pos.data(),velrho.data(),norp);
+  if(r)throw std::runtime_error(std::string("b2s_upload_particles failed: ")+b2s_last_error(s->ctx));
+  s->np0=np;
+}
+
+// ---- PART output (JSph::SavePartData / JPartDataBi4) ----------------------------------------------------
+static void save_part(b2s_sim* s){
+  const b2s_params& p=s->prm;
+  const unsigned cap=p.casenp;
+  std::vector<uint32_t> idp(cap); std::vector<double> pos(size_t(cap)*3); std::vector<float> vel(size_t(cap)*3), rho(cap);
+  uint32_t n=0;
+  int r=b2s_download_particles_byid(s->ctx,&n,idp.data(),pos.data(),vel.data(),rho.data());
+  if(r)throw std::runtime_error(std::string("download failed: ")+b2s_last_error(s->ctx));
+  b2s_info inf; b2s_get_info(s->ctx,&inf);
+  Bi4Item d("JPartDataBi4");
+  const double zero3[3]={0,0,0};
+  d.set_uint("Piece",0); d.set_uint("Npiece",1); d.set_text("RunCode","00000000"); d.set_text("Date","???");
+  d.set_text("AppName","b200sph"); d.set_text("CaseName",s->casename); d.set_bool("Data2d",false); d.set_double("Data2dPosY",0);
+  d.set_double3("MapPosMin",p.maprealposmin); d.set_double3("MapPosMax",p.maprealposmax);
+  d.set_int("PeriMode",0); d.set_double3("PeriXinc",zero3); d.set_double3("PeriYinc",zero3); d.set_double3("PeriZinc",zero3);
+  d.set_int("AxisDiv",0);
+  d.set_ullong("CaseNp",p.casenp); d.set_ullong("CaseNfixed",p.casenfixed); d.set_ullong("CaseNmoving",p.casenmoving);
+  d.set_ullong("CaseNfloat",p.casenfloat); d.set_ullong("CaseNfluid",p.casenfluid);
+  d.set_double3("CasePosMin",s->caseposmin); d.set_double3("CasePosMax",s->caseposmax);
+  d.set_bool("NpDynamic",false); d.set_bool("ReuseIds",false);
+  d.set_double("Dp",s->casedp); d.set_double("H",s->caseh); d.set_double("B",s->caseb); d.set_double("Rhop0",s->caserhop0);
+  d.set_double("Gamma",s->casegamma); d.set_double("MassBound",s->casemassb); d.set_double("MassFluid",s->casemassf);
+  d.set_bool("Symmetry",false); d.set_bool("Splitting",false);
+  char nm[32]; snprintf(nm,sizeof(nm),"PART_%04u",s->part);
+  Bi4Item* pt=d.add_item(nm);
+  pt->set_uint("Cpart",s->part); pt->set_double("TimeStep",inf.timestep); pt->set_uint("Npok",n); pt->set_uint("Nout",p.casenp-n);
+  pt->set_uint("Step",inf.nstep); pt->set_double("RunTime",0);
+  pt->set_double3("DomainMin",p.maprealposmin); pt->set_double3("DomainMax",p.maprealposmax);
+  if(p.tstep==B2S_STEP_SYMPLECTIC)pt->set_double("SymplecticDtPre",inf.symplectic_dtpre);
+  std::vector<float> posf;
+  pt->add_array_ext("Idp",BT_UINT,n,idp.data());
+  if(s->svposdouble)pt->add_array_ext("Posd",BT_DOUBLE3,n,pos.data());
+  else{ posf.resize(size_t(n)*3); for(size_t i=0;i<size_t(n)*3;i++)posf[i]=float(pos[i]); pt->add_array_ext("Pos",BT_FLOAT3,n,posf.data()); }
+  pt->add_array_ext("Vel",BT_FLOAT3,n,vel.data());
+  pt->add_array_ext("Rhop",BT_FLOAT,n,rho.data());
+  char fn[64]; snprintf(fn,sizeof(fn),"Part_%04u.bi4",s->part);
+  bi4_save(s->dirdata+fn,d,"JPartDataBi4");
+  if(s->part==0){
+    // Part_Head.ibi4 (JPartDataHead): same head values + MK blocks
+    Bi4Item h("JPartDataHead");
+    h.set_text("AppName","b200sph"); h.set_text("CaseName",s->casename); h.set_bool("Data2d",false); h.set_double("Data2dPosY",0);
+    h.set_double3("CasePosMin",s->caseposmin); h.set_double3("CasePosMax",s->caseposmax); h.set_bool("NpDynamic",false); h.set_bool("ReuseIds",false);
+    h.set_double3("MapPosMin",p.maprealposmin); h.set_double3("MapPosMax",p.maprealposmax);
+    h.set_double("Dp",s->casedp); h.set_double("H",s->caseh); h.set_double("B",s->caseb); h.set_double("Rhop0",s->caserhop0); h.set_double("Gamma",s->casegamma);
+    h.set_double("MassBound",s->casemassb); h.set_double("MassFluid",s->casemassf);
+    h.set_uint("MkListSize",unsigned(s->blocks.size()));
+    unsigned c=0;
+    for(auto& b:s->blocks){
+      char bn[32]; snprintf(bn,sizeof(bn),"MkBlock_%03u",c++);
+      Bi4Item* it=h.add_item(bn);
+      static const char* tn[4]={"Fixed","Moving","Floating","Fluid"};
+      it->set_text("Type",tn[b.type]); it->set_uint("Mk",b.mk); it->set_uint("MkType",b.mktype); it->set_uint("Begin",b.begin); it->set_uint("Count",b.count);
+    }
+    bi4_save(s->dirdata+"Part_Head.ibi4",h,"JPartDataHead");
+  }
+}
+
+// ---- C entry points ---------------------------------------------------------------------------------------
+extern "C" const char* b2s_host_last_error(void){ return g_host_err.c_str(); }
+
+extern "C" int b2s_sim_load(const char* casepath,const char* dirout,const char* options,int device,uint32_t extra_capacity,b2s_sim** out){
+  if(!casepath||!out)return B2S_ERR_ARG;
+  *out=NULL;
+  b2s_sim* s=new b2s_sim();
+  try{
+    s->casepath=casepath;
+    if(s->casepath.size()>4 && lower(s->casepath.substr(s->casepath.size()-4))==".xml")s->casepath.resize(s->casepath.size()-4);
+    size_t sl=s->casepath.find_last_of('/');
+    s->casename=(sl==std::string::npos? s->casepath: s->casepath.substr(sl+1));
+    s->dirout=(dirout&&dirout[0]? dirout: "");
+    if(!s->dirout.empty()){ if(s->dirout[s->dirout.size()-1]!='/')s->dirout+='/'; s->dirdata=s->dirout+"data/"; mkdirs(s->dirdata); }
+    load_case(s,options? options: "");
+    load_particles_and_create(s,device,extra_capacity);
+    s->timepartnext=0;
+  }
+  catch(const std::exception& e){ g_host_err=e.what(); if(s->ctx)b2s_destroy(s->ctx); delete s; return B2S_ERR_IO; }
+  *out=s;
+  return B2S_OK;
+}
+extern "C" int b2s_sim_free(b2s_sim* s){ if(!s)return B2S_OK; if(s->ctx)b2s_destroy(s->ctx); delete s; return B2S_OK; }
+extern "C" int b2s_sim_ctx(b2s_sim* s,b2s_ctx** out){ if(!s||!out)return B2S_ERR_ARG; *out=s->ctx; return B2S_OK; }
+extern "C" int b2s_sim_params(b2s_sim* s,b2s_params* out){ if(!s||!out)return B2S_ERR_ARG; *out=s->prm; return B2S_OK; }
+extern "C" int b2s_sim_save_part(b2s_sim* s){
+  if(!s)return B2S_ERR_ARG;
+  if(s->dirdata.empty()){ g_host_err="no output directory configured"; return B2S_ERR_STATE; }
+  try{ save_part(s); s->part++; }catch(const std::exception& e){ g_host_err=e.what(); return B2S_ERR_IO; }
+  return B2S_OK;
+}
+
+// JSphGpuSingle::Run main loop (JSphGpuSingle.cpp:998-1041): step, PART output at TimeOut, stop at TimeMax / nsteps.
+extern "C" int b2s_sim_run(b2s_sim* s,uint32_t nsteps_break,double* time_out,uint32_t* steps_out){
+  if(!s)return B2S_ERR_ARG;
+  const unsigned nbreak=(nsteps_break? nsteps_break: s->nstepsbreak);
+  const bool save=(s->svdata && !s->dirdata.empty());
+  try{
+    b2s_info inf; int r=b2s_get_info(s->ctx,&inf); if(r){ g_host_err=b2s_last_error(s->ctx); return r; }
+    if(save && s->part==0){ save_part(s); s->part++; s->timepartnext=(s->svallsteps? inf.timestep: s->timepart); }
+    unsigned nstep=0;
+    double t=inf.timestep;
+    while(t<s->timemax){
+      double dt=0;
+      r=b2s_compute_step(s->ctx,&dt);
+      if(r){ g_host_err=b2s_last_error(s->ctx); return r; }
+      r=b2s_get_info(s->ctx,&inf); if(r){ g_host_err=b2s_last_error(s->ctx); return r; }
+      t=inf.timestep; nstep++;
+      if(save && t>=s->timepartnext){
+        save_part(s); s->part++;
+        if(s->svallsteps)s->timepartnext=t;
+        else{ unsigned ct=unsigned(t/s->timepart); double tn=s->timepart*ct; for(;tn<=t;ct++)tn=s->timepart*ct; s->timepartnext=tn; }  // JDsOutputTime::GetNextTime
+      }
+      if(inf.np<=inf.npb){ g_host_err="no fluid particles left"; break; }
+      if(nbreak && nstep>=nbreak)break;
+    }
+    if(time_out)*time_out=t;
+    if(steps_out)*steps_out=nstep;
+  }
+  catch(const std::exception& e){ g_host_err=e.what(); return B2S_ERR_IO; }
+  return B2S_OK;
+}

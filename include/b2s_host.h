@@ -1,0 +1,30 @@
+/* b2s_host.h -- C entry points of the C++ host driver (case interface kept drop-in).
+ *
+ * The driver reads the GenCase output the reference solver reads (Case.xml + Case.bi4), owns a b2s_ctx
+ * (include/b2s.h) and runs the JSphGpuSingle-style loop (src/source/JSphGpuSingle.cpp:950-1041), writing
+ * dirout/data/Part_XXXX.bi4 + Part_Head.ibi4 like JSph::SavePartData (src/source/JSph.cpp:3062-3146).
+ * `options` is a blank-separated string of the reference's own command-line switches
+ * (src/source/JSphCfgRun.cpp:312-524), e.g. "-symplectic -wendland -viscoart:0.1 -ddt:2 -tmax:0.5";
+ * unsupported switches are an error, never ignored.
+ */
+#ifndef B2S_HOST_H_
+#define B2S_HOST_H_
+#include "b2s.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct b2s_sim b2s_sim;
+/* casepath: path of the case without extension (".xml" accepted). dirout may be NULL/"" (no PART output). */
+int b2s_sim_load(const char* casepath, const char* dirout, const char* options, int device,
+                 uint32_t extra_capacity, b2s_sim** out);
+int b2s_sim_free(b2s_sim* sim);
+int b2s_sim_ctx(b2s_sim* sim, b2s_ctx** out);            /* borrowed: freed by b2s_sim_free */
+int b2s_sim_params(b2s_sim* sim, b2s_params* out);
+int b2s_sim_save_part(b2s_sim* sim);                     /* writes the next Part_XXXX.bi4 */
+/* Runs until TimeMax or nsteps_break steps (0: use -nsteps option / none). */
+int b2s_sim_run(b2s_sim* sim, uint32_t nsteps_break, double* time_out, uint32_t* steps_out);
+const char* b2s_host_last_error(void);
+#ifdef __cplusplus
+}
+#endif
+#endif

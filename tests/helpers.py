@@ -1,0 +1,142 @@
+"""Shared helpers for the test-suite: case generation, host-side parameter loading, comparisons."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import dualsphysics_b200 as dsb  # noqa: E402
+from dualsphysics_b200 import bi4, b2sd, casegen  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def have_ref() -> bool:
+    return os.path.exists(orc.REF_PROBE)
+
+
+def have_gpu() -> bool:
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def write_case(dirpath, name="Case", **kw):
+    spec = casegen.DamBreakSpec(**kw)
+    return casegen.write_case(str(dirpath), name, spec), spec
+
+
+def params_from_case(casepath: str, options: dict | None = None):
+    """Python twin of the C++ host loader (csrc/host/sim.cpp) for CPU-only tests: Params + particle arrays."""
+    root = ET.parse(casepath + ".xml").getroot()
+    exe = root.find("execution")
+    ct = exe.find("constants")
+    prm = {p.get("key"): p.get("value") for p in exe.find("parameters").findall("parameter")}
+    if options:
+        prm.update({k: str(v) for k, v in options.items()})
+    p = dsb.Params()
+    g = ct.find("gravity")
+    p.gravity[0], p.gravity[1], p.gravity[2] = float(g.get("x")), float(g.get("y")), float(g.get("z"))
+    val = lambda n: float(ct.find(n).get("value"))  # noqa: E731
+    p.cflnumber, p.gamma, p.rhopzero, p.dp = val("cflnumber"), val("gamma"), val("rhop0"), val("dp")
+    p.kernelh, p.cteb, p.massbound, p.massfluid = val("h"), val("b"), val("massbound"), val("massfluid")
+    p.tkernel = int(prm.get("Kernel", 2))
+    p.tstep = int(prm.get("StepAlgorithm", 1))
+    p.verletsteps = int(prm.get("VerletSteps", 40))
+    p.tvisco = int(prm.get("ViscoTreatment", 1))
+    p.visco = float(prm["Visco"])
+    p.viscoboundfactor = float(prm.get("ViscoBoundFactor", 1))
+    p.tboundary = int(prm.get("Boundary", 1))
+    p.slipmode = int(prm.get("SlipMode", 1)) if p.tboundary == 2 else 0
+    p.tdensity = int(prm.get("DensityDT", 0))
+    p.ddtvalue = float(prm.get("DensityDTvalue", 0.1)) if p.tdensity else 0.0
+    p.coefdtmin = float(np.float32(prm.get("CoefDtMin", 0.05)))
+    p.dtini = max(0.0, float(prm.get("DtIni", 0)))
+    p.dtmin = max(0.0, float(prm.get("DtMin", 0)))
+    p.dt_allparticles = 1 if int(prm.get("DtAllParticles", 0)) == 1 else 0
+    p.rhopoutmin, p.rhopoutmax = float(prm.get("RhopOutMin", 700)), float(prm.get("RhopOutMax", 1300))
+    p.cellmode_half = int(prm.get("_cellmode_half", 0))
+    pa = exe.find("particles")
+    cnt = {"fixed": 0, "moving": 0, "floating": 0, "fluid": 0}
+    blocks = []
+    for b in pa:
+        if b.tag in cnt:
+            cnt[b.tag] += int(b.get("count"))
+            blocks.append((b.tag, int(b.get("begin")), int(b.get("count")), b))
+    p.casenfixed, p.casenmoving, p.casenfloat, p.casenfluid = cnt["fixed"], cnt["moving"], cnt["floating"], cnt["fluid"]
+    p.casenp = sum(cnt.values())
+    data = bi4.load_part(casepath + ".bi4")
+    pos = data["pos"]
+    idp = data["Idp"]
+    cmin, cmax = np.array(data["head"]["CasePosMin"]), np.array(data["head"]["CasePosMax"])
+    border = float(np.float32(p.kernelh)) * 0.05
+    rmin, rmax = cmin - border, cmax + border
+    sd = exe.find("parameters").find("simulationdomain")
+    lo, hi = rmin.copy(), rmax.copy()
+    for k, ax in enumerate("xyz"):
+        for node, ismin in ((sd.find("posmin") if sd is not None else None, True),
+                            (sd.find("posmax") if sd is not None else None, False)):
+            v = (node.get(ax, "default") if node is not None else "default").replace(" ", "").lower()
+            if v == "default":
+                continue
+            dif = rmax[k] - rmin[k]
+            if v.startswith("default"):
+                prc = v.endswith("%")
+                num = float(v[8:-1] if prc else v[8:])
+                inc = dif * num / 100 if prc else num
+                if ismin:
+                    lo[k] = rmin[k] - inc
+                else:
+                    hi[k] = rmax[k] + inc
+            else:
+                if ismin:
+                    lo[k] = float(v)
+                else:
+                    hi[k] = float(v)
+    for k in range(3):
+        p.maprealposmin[k], p.maprealposmax[k] = lo[k], hi[k]
+    lib = dsb.load_library()
+    r = lib.b2s_config_finalize(C.byref(p))
+    assert r == 0, r
+    # particle codes (JSphMk): type | index within type
+    tcode = {"fixed": 0x0000, "moving": 0x0800, "floating": 0x1000, "fluid": 0x1800}
+    idx = {k: 0 for k in tcode}
+    codeofid = np.zeros(p.casenp, np.uint16)
+    ftmassp = []
+    for tag, beg, n, node in blocks:
+        codeofid[beg:beg + n] = tcode[tag] | idx[tag]
+        idx[tag] += 1
+        if tag == "floating":
+            ftmassp.append(float(node.find("masspart").get("value")))
+    code = codeofid[idp]
+    velrho = np.concatenate([data["Vel"], data["Rhop"][:, None]], axis=1).astype(np.float32)
+    arrays = {"idp": idp, "code": code, "pos": pos, "velrho": velrho, "boundnor": data.get("BoundNor"),
+              "ftmassp": np.array(ftmassp, np.float32)}
+    return p, arrays
+
+
+def oracle_sim_from_case(casepath: str, options: dict | None = None) -> "orc.OracleSim":
+    p, a = params_from_case(casepath, options)
+    cte = orc.cte_from_params(p)
+    return orc.OracleSim(cte, a["idp"], a["code"], a["pos"], a["velrho"], npb=p.casenpb, dtini=p.dtini,
+                         verletsteps=p.verletsteps, ftomassp=a["ftmassp"] if len(a["ftmassp"]) else None)
+
+
+def rel_err(a, b, floor=None):
+    """max |a-b| / max(|b|) -- error relative to the field's magnitude (the tolerance form SURVEY 7(2) asks for)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    scale = np.max(np.abs(b)) if floor is None else max(np.max(np.abs(b)), floor)
+    if scale == 0:
+        return float(np.max(np.abs(a - b)))
+    return float(np.max(np.abs(a - b)) / scale)
