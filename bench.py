@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "particle-steps/sec (whole box) at 1/2/4/8 B200; interaction-kernel roofline fraction"
 UNIT = "particle-steps/s"
-OPTIONS = "-symplectic -wendland -viscoart:0.1 -ddt:2 -ddtvalue:0.1 -dbc"
+OPTIONS = "-symplectic -wendland -viscoart:0.1 -ddt:2 -ddtvalue:0.1 -dbc" + os.environ.get("B2S_BENCH_EXTRA_OPTS", "")
 NP_TARGET = int(os.environ.get("B2S_BENCH_NP", "10000000"))
 CPU_SAMPLE_NP = int(os.environ.get("B2S_BENCH_CPU_NP", "1000000"))
 # flop model of SURVEY 8(d): per checked pair 16 flop, per real pair (r<2h) 90 flop

@@ -136,6 +136,8 @@ struct b2s_ctx {
   uint32_t ftcount; std::vector<b2s_floating> fts; float* ft_massp_dev; float* ft_sums_dev; float* ft_sums_h;
   void* ft_dev; // device copy of per-floating update data
   std::vector<Motion> motions;
+  // tile interaction variant (forces_tile.cu)
+  uint32_t* tile_seglist; uint32_t* tile_nseg; uint32_t tile_nseg_max; bool tile_seglist_valid; bool tile_attr_set[2][2][4][4];
   // scratch for byid download
   void* scratch; size_t scratch_bytes;
 };
@@ -145,6 +147,18 @@ int  b2s_fail(b2s_ctx* ctx, int code, const char* fmt, ...);
 #define B2S_CUDA(ctx, expr) do{ cudaError_t _e=(expr); if(_e!=cudaSuccess) return b2s_fail(ctx,(int)_e,"%s failed: %s (%s:%d)",#expr,cudaGetErrorString(_e),__FILE__,__LINE__); }while(0)
 #define B2S_LAUNCHED(ctx) do{ (ctx)->launches++; }while(0)
 static inline unsigned b2s_blocks(size_t n, unsigned bs){ return (unsigned)((n+bs-1)/bs); }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float b2s_press(float rho, const DevCte& c){
+  // Tait EOS as the CPU path evaluates it (FunSphEos.h:37-39): cteb*(powf(rho/rho0,gamma)-1).
+  // gamma==7: exact product chain in double, rounded once (== correctly rounded powf to <1ulp).
+  const float r=rho*c.ovrhopzero;
+  float pw;
+  if(c.gamma_is7){ const double d=(double)r; const double d2=d*d; const double d4=d2*d2; pw=(float)(d4*d2*d); }
+  else pw=(float)pow((double)r,(double)c.gamma);
+  return c.cteb*(pw-1.0f);
+}
+#endif
 
 // implemented in the .cu files
 int b2s_celldiv_impl(b2s_ctx* ctx);

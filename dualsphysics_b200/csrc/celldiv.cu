@@ -258,15 +258,6 @@ struct ReorderArgs {
   uint32_t casenfixed, casenbound;
 };
 
-__device__ __forceinline__ float b2s_press(float rho, const DevCte& c){
-  // Tait EOS as the CPU path evaluates it (FunSphEos.h:37-39): cteb*(powf(rho/rho0,gamma)-1).
-  // gamma==7: exact product chain in double, rounded once (== correctly rounded powf to <1ulp).
-  const float r=rho*c.ovrhopzero;
-  float pw;
-  if(c.gamma_is7){ const double d=(double)r; const double d2=d*d; const double d4=d2*d2; pw=(float)(d4*d2*d); }
-  else pw=(float)pow((double)r,(double)c.gamma);
-  return c.cteb*(pw-1.0f);
-}
 
 __global__ void __launch_bounds__(DIV_BS) k_reorder(const DivState* __restrict__ ds, StepState* st, const uint32_t* __restrict__ sortpart,
   ReorderArgs a, const __grid_constant__ DevCte cte)
@@ -370,6 +361,7 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   if(ctx->spstau)std::swap(ctx->spstau,ctx->spstau_alt);
   if(ctx->boundnor)std::swap(ctx->boundnor,ctx->boundnor_alt);
   ctx->bound_changed=false;
+  ctx->tile_seglist_valid=false;
   B2S_CUDA(ctx,cudaGetLastError());
   return B2S_OK;
 }

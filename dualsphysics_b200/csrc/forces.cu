@@ -16,157 +16,7 @@
 //   variant 0 "gather": one thread per particle walking the 3x3(x5x5) cell rows in the reference order
 //             (bit-comparable summation order; the parity anchor).
 //   variant 1 "tile":   see forces_tile.cu (shared-memory staged, sm_100a tuned).
-#include "b2s_internal.h"
-#include <float.h>
-
-#define F_BS 128
-
-struct ForcesArgs {
-  const DivState* ds; StepState* st;
-  const uint32_t* beg;            // begincell (CPU form)
-  const uint32_t* dcell; const typecode* code;
-  const float4* posp; const float4* velrho;
-  const float* tau; float* tau_new;   // 6 floats/particle (xx,xy,xz,yy,yz,zz) or NULL
-  const float* ftomassp;
-  float4* acear;
-};
-
-__device__ __forceinline__ float b2s_rcp(float x){ float r; asm("rcp.approx.ftz.f32 %0, %1;":"=f"(r):"f"(x)); return r; }
-__device__ __forceinline__ float b2s_rsqrt(float x){ float r; asm("rsqrt.approx.ftz.f32 %0, %1;":"=f"(r):"f"(x)); return r; }
-
-// fac = |grad W|/r  (FunSphKernel.h:53-65 cubic, :218-223 Wendland)
-template<int TKER> __device__ __forceinline__ float kernel_fac(float rr2, const DevCte& c){
-  const float rad=rr2*b2s_rsqrt(rr2);
-  const float qq=rad*c.ovkernelh;
-  if(TKER==B2S_KERNEL_WENDLAND){
-    const float wqq1=1.f-0.5f*qq;
-    return c.bwenh*wqq1*wqq1*wqq1;
-  }
-  else{
-    if(rad>c.kernelh){ const float wqq1=2.0f-qq; const float wqq2=wqq1*wqq1; return c.cub_c2*wqq2*b2s_rcp(rad); }
-    else{ const float wqq2=qq*qq; return (c.cub_c1*qq+c.cub_d1*wqq2)*b2s_rcp(rad); }
-  }
-}
-// Cubic-spline tensile correction (FunSphKernel.h:88-97)
-__device__ __forceinline__ float cubic_tensil(float rr2,float rhop1,float pressp1,float rhop2,float pressp2,const DevCte& c){
-  const float rad=rr2*b2s_rsqrt(rr2);
-  const float qq=rad*c.ovkernelh;
-  float wab;
-  if(rad>c.kernelh){ const float wqq1=2.0f-qq; const float wqq2=wqq1*wqq1; wab=c.cub_a24*(wqq2*wqq1); }
-  else{ const float wqq2=qq*qq; wab=c.cub_a2*(1.0f+(0.75f*qq-1.5f)*wqq2); }
-  float fab=wab*c.cub_od_wdeltap;
-  fab*=fab; fab*=fab;
-  const float tensilp1=(pressp1/(rhop1*rhop1))*(pressp1>0? 0.01f: -0.2f);
-  const float tensilp2=(pressp2/(rhop2*rhop2))*(pressp2>0? 0.01f: -0.2f);
-  return fab*(tensilp1+tensilp2);
-}
-
-struct PairAcc {
-  float ax,ay,az,ar,visc,delta;
-  float sxx,sxy,sxz,syy,syz,szz;   // 2*strain (SPS)
-};
-
-// One fluid/floating particle p1 against one neighbour p2 (JSphCpu.cpp:822-1041).
-template<int TKER,int TVISCO,int TDENS,bool FLOATING,bool BOUNDP2>
-__device__ __forceinline__ void pair_fluid(const DevCte& c, float drx,float dry,float drz,float rr2,
-  const float4 velrhop1,float pressp1,bool ftp1,const float* taup1,
-  const float4 velrhop2,float pressp2,typecode codep2,const float* __restrict__ taug,uint32_t p2,
-  const float* __restrict__ ftomassp,float visco,PairAcc& a)
-{
-  const float fac=kernel_fac<TKER>(rr2,c);
-  const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
-  float massp2=(BOUNDP2? c.massb: c.massf);
-  bool ftp2=false;
-  if(FLOATING){
-    ftp2=B2S_CODE_ISFLOATING(codep2);
-    if(ftp2)massp2=ftomassp[B2S_CODE_TYPEVALUE(codep2)];
-    if(ftp2 && TDENS==B2S_DDT_MOLTENI && massp2<=(c.massf*1.2f))a.delta=FLT_MAX;   // DELTA_HEAVYFLOATING (DualSphDef.h:104)
-  }
-  const float rhop1=velrhop1.w, rhop2=velrhop2.w;
-  const float ovrhop2=b2s_rcp(rhop2);
-  //-Momentum equation.
-  {
-    float prs=(pressp1+pressp2)*(b2s_rcp(rhop1)*ovrhop2);
-    if(TKER==B2S_KERNEL_CUBIC)prs+=cubic_tensil(rr2,rhop1,pressp1,rhop2,pressp2,c);
-    const float p_vpm=-prs*massp2;
-    a.ax+=p_vpm*frx; a.ay+=p_vpm*fry; a.az+=p_vpm*frz;
-  }
-  //-Continuity equation.
-  const float dvx=velrhop1.x-velrhop2.x, dvy=velrhop1.y-velrhop2.y, dvz=velrhop1.z-velrhop2.z;
-  a.ar+=massp2*(dvx*frx+dvy*fry+dvz*frz)*(rhop1*ovrhop2);
-  const float ovrr2eta=b2s_rcp(rr2+c.eta2);
-  const float dot3=(TDENS!=B2S_DDT_NONE || TVISCO!=B2S_VISCO_ARTIFICIAL? drx*frx+dry*fry+drz*frz: 0.f);
-  //-Density diffusion: Molteni & Colagrossi (JSphCpu.cpp:934-941).
-  if(TDENS==B2S_DDT_MOLTENI && a.delta!=FLT_MAX){
-    const float rhop1over2=rhop1*ovrhop2;
-    const float visc_densi=c.ddtkh*c.cs0*(rhop1over2-1.f)*ovrr2eta;
-    const float delta=visc_densi*dot3*massp2;
-    a.delta=(BOUNDP2 && c.tboundary==B2S_BC_DBC? FLT_MAX: a.delta+delta);
-  }
-  //-Density diffusion: Fourtakas et al. (JSphCpu.cpp:943-950).
-  if((TDENS==B2S_DDT_FOURTAKAS || (TDENS==B2S_DDT_FOURTAKASFULL && !BOUNDP2)) && a.delta!=FLT_MAX && !ftp2){
-    const float rh=1.f+c.ddtgz*drz;
-    // rh^(1/gamma) as fl32(1+series(rh-1)): |rh-1|<~1e-2, series error < 1e-9 relative, then the same
-    // fl32 rounding and rho0*pw-rho0 cancellation as the reference's pow() ("DDT2 hydrostatic term").
-    const float x=rh-1.f;
-    const float pw=1.f+x*(c.ddt_c1+x*(c.ddt_c2+x*c.ddt_c3));
-    const float drho=c.rhopzero*pw-c.rhopzero;
-    const float visc_densi=c.ddtkh*c.cs0*((rhop2-rhop1)-drho)*ovrr2eta;
-    const float delta=visc_densi*dot3*massp2*ovrhop2;
-    a.delta=(BOUNDP2? FLT_MAX: a.delta-delta);
-  }
-  //-Viscosity.
-  {
-    const float dot=drx*dvx+dry*dvy+drz*dvz;
-    const float dot_rr2=dot*ovrr2eta;
-    a.visc=fmaxf(dot_rr2,a.visc);
-    if(TVISCO==B2S_VISCO_ARTIFICIAL){
-      if(dot<0){
-        const float amubar=c.kernelh*dot_rr2;
-        const float robar=(rhop1+rhop2)*0.5f;
-        const float pi_visc=(-visco*c.cs0*amubar*b2s_rcp(robar))*massp2;
-        a.ax-=pi_visc*frx; a.ay-=pi_visc*fry; a.az-=pi_visc*frz;
-      }
-    }
-    else{
-      const float robar2=(rhop1+rhop2);
-      const float temp=4.f*visco*b2s_rcp((rr2+c.eta2)*robar2);
-      const float vtemp=massp2*temp*dot3;
-      a.ax+=vtemp*dvx; a.ay+=vtemp*dvy; a.az+=vtemp*dvz;
-    }
-    if(TVISCO==B2S_VISCO_LAMINARSPS){
-      float sxx=taup1[0],sxy=taup1[1],sxz=taup1[2],syy=taup1[3],syz=taup1[4],szz=taup1[5];
-      if(!BOUNDP2 && !ftp2){
-        const float2* t2=(const float2*)(taug+size_t(p2)*6);
-        const float2 t0=t2[0],t1=t2[1],t3=t2[2];
-        sxx+=t0.x; sxy+=t0.y; sxz+=t1.x; syy+=t1.y; syz+=t3.x; szz+=t3.y;
-      }
-      a.ax+=massp2*(sxx*frx+sxy*fry+sxz*frz);
-      a.ay+=massp2*(sxy*frx+syy*fry+syz*frz);
-      a.az+=massp2*(sxz*frx+syz*fry+szz*frz);
-      if(!ftp1){
-        const float volp2=-massp2*ovrhop2;
-        float dv=dvx*volp2; a.sxx+=dv*frx; a.sxy+=dv*fry; a.sxz+=dv*frz;
-              dv=dvy*volp2; a.sxy+=dv*frx; a.syy+=dv*fry; a.syz+=dv*frz;
-              dv=dvz*volp2; a.sxz+=dv*frx; a.syz+=dv*fry; a.szz+=dv*frz;
-      }
-    }
-  }
-}
-
-// Neighbour cell ranges of cunsearch::InitCte (JCellSearch_iker.h:34-57), cells relative to cellmin.
-struct CellRange { int cx,cy,cz,xini,xfin,yini,yfin,zini,zfin; };
-__device__ __forceinline__ CellRange cell_range(uint32_t dcell,const DevCte& c,const DivState* ds){
-  CellRange r;
-  r.cx=int(B2S_DCEL_CELLX(c.domcellcode,dcell))-int(ds->cellmin[0]);
-  r.cy=int(B2S_DCEL_CELLY(c.domcellcode,dcell))-int(ds->cellmin[1]);
-  r.cz=int(B2S_DCEL_CELLZ(c.domcellcode,dcell))-int(ds->cellmin[2]);
-  const int d=c.scelldiv, ncx=int(ds->ncx), ncy=int(ds->ncy), ncz=int(ds->ncz);
-  r.xini=r.cx-min(r.cx,d); r.xfin=r.cx+min(ncx-r.cx-1,d)+1;
-  r.yini=r.cy-min(r.cy,d); r.yfin=r.cy+min(ncy-r.cy-1,d)+1;
-  r.zini=r.cz-min(r.cz,d); r.zfin=r.cz+min(ncz-r.cz-1,d)+1;
-  return r;
-}
+#include "forces_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Variant 0: gather kernel, one thread per fluid/floating particle.
@@ -206,8 +56,8 @@ __global__ void __launch_bounds__(F_BS) k_forces_fluid_gather(ForcesArgs g, cons
           const float offx=c.scell*float(r.cx-x);
           for(uint32_t p2=pini;p2<pfin;p2++){
             const float4 pp2=g.posp[p2];
-            const float drx=(pp1.x-pp2.x)+offx, dry=(pp1.y-pp2.y)+offy, drz=(pp1.z-pp2.z)+offz;
-            const float rr2=drx*drx+dry*dry+drz*drz;
+            const float drx=b2s_dr(pp1.x,pp2.x,offx), dry=b2s_dr(pp1.y,pp2.y,offy), drz=b2s_dr(pp1.z,pp2.z,offz);
+            const float rr2=b2s_rr2(drx,dry,drz);
             if(rr2<=c.kernelsize2 && rr2>=B2S_ALMOSTZERO){
               const typecode cod2=(FLOATING? g.code[p2]: typecode(0));
               pair_fluid<TKER,TVISCO,TDENS,FLOATING,false>(c,drx,dry,drz,rr2,velrhop1,pressp1,ftp1,taup1,
@@ -228,8 +78,8 @@ __global__ void __launch_bounds__(F_BS) k_forces_fluid_gather(ForcesArgs g, cons
           const float offx=c.scell*float(r.cx-x);
           for(uint32_t p2=pini;p2<pfin;p2++){
             const float4 pp2=g.posp[p2];
-            const float drx=(pp1.x-pp2.x)+offx, dry=(pp1.y-pp2.y)+offy, drz=(pp1.z-pp2.z)+offz;
-            const float rr2=drx*drx+dry*dry+drz*drz;
+            const float drx=b2s_dr(pp1.x,pp2.x,offx), dry=b2s_dr(pp1.y,pp2.y,offy), drz=b2s_dr(pp1.z,pp2.z,offz);
+            const float rr2=b2s_rr2(drx,dry,drz);
             if(rr2<=c.kernelsize2 && rr2>=B2S_ALMOSTZERO){
               pair_fluid<TKER,TVISCO,TDENS,FLOATING,true>(c,drx,dry,drz,rr2,velrhop1,pressp1,ftp1,taup1,
                 g.velrho[p2],pp2.w,typecode(0),g.tau,p2,g.ftomassp,c.visco_b,ab);
@@ -238,34 +88,7 @@ __global__ void __launch_bounds__(F_BS) k_forces_fluid_gather(ForcesArgs g, cons
         }
       }
     }
-    //-Store (JSphCpu.cpp:1086-1102 fluid pass then bound pass; JSphGpu_ker.cu:939-950 for the GPU semantics).
-    // The density-diffusion sum is kept apart and added last, and a DBC boundary neighbour (FLT_MAX marker)
-    // discards it completely: this is what both reference builds do (GPU: one running deltap1, JSphGpu_ker.cu:939-946;
-    // CPU: DDTArray=true on CPU, JSph.cpp:927, Delta_c added after both passes, JSphCpuSingle.cpp:723-731).
-    float4 res;
-    res.x=af.ax+ab.ax; res.y=af.ay+ab.ay; res.z=af.az+ab.az; res.w=af.ar+ab.ar;
-    if(TDENS!=B2S_DDT_NONE && af.delta!=FLT_MAX && ab.delta!=FLT_MAX)res.w+=(af.delta+ab.delta);
-    if(c.simulate2d)res.y=0.f;
-    g.acear[p1]=res;
-    viscmax=fmaxf(af.visc,ab.visc);
-    if(B2S_CODE_ISNORMAL(g.code[p1]))ace2=res.x*res.x+res.y*res.y+res.z*res.z;
-    if(TVISCO==B2S_VISCO_LAMINARSPS){
-      // ComputeSpsTau (JSphCpu.cpp:1279-1307) on the accumulated 2*strain of both passes.
-      const float sxx=af.sxx+ab.sxx, sxy=af.sxy+ab.sxy, sxz=af.sxz+ab.sxz, syy=af.syy+ab.syy, syz=af.syz+ab.syz, szz=af.szz+ab.szz;
-      const float pow1=sxx*sxx+syy*syy+szz*szz;
-      const float prr=sxy*sxy+sxz*sxz+syz*syz+pow1+pow1;
-      const float visc_sps=c.spssmag*sqrtf(prr);
-      const float div_u=sxx+syy+szz;
-      const float sps_k=visc_sps*div_u;
-      const float sps_blin=c.spsblin*prr;
-      const float sumsps=-(sps_k+sps_blin);
-      const float twovisc_sps=visc_sps+visc_sps;
-      const float one_rho=1.0f/velrhop1.w;
-      float2* tn=(float2*)(g.tau_new+size_t(p1)*6);
-      tn[0]=make_float2(one_rho*(twovisc_sps*sxx+sumsps),one_rho*(visc_sps*sxy));
-      tn[1]=make_float2(one_rho*(visc_sps*sxz),one_rho*(twovisc_sps*syy+sumsps));
-      tn[2]=make_float2(one_rho*(visc_sps*syz),one_rho*(twovisc_sps*szz+sumsps));
-    }
+    finalize_store<TVISCO,TDENS>(g,c,p1,velrhop1,af,ab,ace2,viscmax);
   }
   //-Fused maxima: ViscDtMax and AceMax^2 (replaces ReduMaxFloat x2 + cudaMemcpy, JSphGpu_ker.cu:75-125).
   #pragma unroll
@@ -302,8 +125,8 @@ __global__ void __launch_bounds__(F_BS) k_forces_bound(ForcesArgs g, const __gri
           const float offx=c.scell*float(r.cx-x);
           for(uint32_t p2=pini;p2<pfin;p2++){
             const float4 pp2=g.posp[p2];
-            const float drx=(pp1.x-pp2.x)+offx, dry=(pp1.y-pp2.y)+offy, drz=(pp1.z-pp2.z)+offz;
-            const float rr2=drx*drx+dry*dry+drz*drz;
+            const float drx=b2s_dr(pp1.x,pp2.x,offx), dry=b2s_dr(pp1.y,pp2.y,offy), drz=b2s_dr(pp1.z,pp2.z,offz);
+            const float rr2=b2s_rr2(drx,dry,drz);
             if(rr2<=c.kernelsize2 && rr2>=B2S_ALMOSTZERO){
               const float fac=kernel_fac<TKER>(rr2,c);
               const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
@@ -371,6 +194,7 @@ fluid_kernel_t b2s_pick_fluid_gather(const DevCte& c){
 }
 
 int b2s_forces_tile_launch(b2s_ctx* ctx, const ForcesArgs& g);   // forces_tile.cu
+int b2s_forces_queue_launch(b2s_ctx* ctx, const ForcesArgs& g);  // forces_queue.cu
 
 int b2s_forces_fluid_only(b2s_ctx* ctx){
   ForcesArgs g;
@@ -379,6 +203,7 @@ int b2s_forces_fluid_only(b2s_ctx* ctx){
   const uint32_t npf=(ctx->np_host>ctx->npb_host? ctx->np_host-ctx->npb_host: 0u);
   if(!npf)return B2S_OK;
   if(ctx->variant==1)return b2s_forces_tile_launch(ctx,g);
+  if(ctx->variant==2)return b2s_forces_queue_launch(ctx,g);
   fluid_kernel_t k=b2s_pick_fluid_gather(ctx->cte);
   k<<<b2s_blocks(npf,F_BS),F_BS,0,ctx->stream>>>(g,ctx->cte); B2S_LAUNCHED(ctx);
   return B2S_OK;

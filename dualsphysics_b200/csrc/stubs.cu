@@ -1,8 +1,5 @@
 // stubs.cu -- entry points not built yet in this round; they fail loudly (B2S_ERR_UNSUPPORTED), never fall back.
 #include "b2s_internal.h"
-struct ForcesArgs;
-int b2s_forces_tile_launch(b2s_ctx* ctx, const ForcesArgs&){ return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"tile interaction variant not built"); }
-int b2s_mdbc_impl(b2s_ctx* ctx){ return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"mDBC not built"); }
 int b2s_floating_impl(b2s_ctx* ctx,double,bool,bool){ return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"floating bodies not built"); }
 extern "C" int b2s_set_floatings(b2s_ctx* ctx,uint32_t,const b2s_floating*){ return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"floating bodies not built"); }
 extern "C" int b2s_get_floatings(b2s_ctx* ctx,uint32_t,b2s_floating*){ return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"floating bodies not built"); }

@@ -202,7 +202,8 @@ int b2s_launch_count(b2s_ctx* ctx, uint64_t* launches, int reset);
 /* CUDA stream the ctx launches on (cudaStream_t cast to void*), for external event timing. */
 int b2s_get_stream(b2s_ctx* ctx, void** stream_out);
 /* Selects the fluid interaction kernel variant: 0 = gather (one thread per particle, reference
- * summation order), 1 = cell-tile (shared-memory staged). */
+ * summation order), 1 = cell-tile (FP16 staged filter + exact body), 2 = warp-uniform stream + per-lane hit queue.
+ * All variants visit neighbours in the same order and are bit-identical. */
 int b2s_set_interaction_variant(b2s_ctx* ctx, int variant);
 
 /* ---- slab decomposition over several GPUs (no reference counterpart) ----------- */

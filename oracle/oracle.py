@@ -103,7 +103,7 @@ class OracleSim:
     """Whole-step CPU oracle over numpy arrays (cell-sorted order, like the solver's state)."""
 
     def __init__(self, cte: Cte, idp, code, pos, velrho, npb: int, dtini: float, verletsteps: int = 40,
-                 ftomassp=None):
+                 ftomassp=None, boundnor=None, mdbc_corrector=False):
         self.L = lib()
         self.c = cte
         self.idp = np.ascontiguousarray(idp, np.uint32).copy()
@@ -117,6 +117,13 @@ class OracleSim:
         self.velrhom1 = self.velrho.copy() if self.tstep == 1 else None
         self.tau = np.zeros((self.np_, 6), np.float32) if cte.tvisco == 2 else None
         self.ftomassp = None if ftomassp is None else np.ascontiguousarray(ftomassp, np.float32)
+        self.boundnor = None
+        if cte.tboundary == 2:
+            self.boundnor = np.zeros((self.np_, 3), np.float32)
+            if boundnor is not None:
+                bn = np.asarray(boundnor, np.float32).reshape(-1, 3)
+                self.boundnor[:bn.shape[0]] = bn
+        self.mdbc_corrector = mdbc_corrector
         self.symplectic_dtpre = float(dtini)
         self.timestep, self.nstep, self.verletstep, self.verletsteps = 0.0, 0, 0, verletsteps
         self.div = Div()
@@ -135,7 +142,7 @@ class OracleSim:
                                _p(self.sortpart), _p(self.begincell), C.byref(self.div))
         assert r == 0
         sp = self.sortpart[:n]
-        for name in ("idp", "code", "dcell", "pos", "velrho", "velrhom1", "tau", "pospre", "velrhopre"):
+        for name in ("idp", "code", "dcell", "pos", "velrho", "velrhom1", "tau", "pospre", "velrhopre", "boundnor"):
             a = getattr(self, name)
             if a is not None:
                 setattr(self, name, np.ascontiguousarray(a[:n][sp]))
@@ -144,8 +151,18 @@ class OracleSim:
         if self.div.npb_out:
             raise RuntimeError("oracle: boundary particles excluded")
 
-    def interaction(self):
+    def mdbc(self):
+        """MdbcBoundCorrection (JSphCpuSingle.cpp:745-760), SlipMode vel0."""
+        if self.boundnor is None:
+            return
+        n = self.np_ if self.c.use_floating else int(self.div.npbok)
+        self.L.orc_mdbc_vel0(C.byref(self.c), C.byref(self.div), n, _p(self.begincell), _p(self.pos), _p(self.code),
+                             _p(self.boundnor), _p(self.velrho))
+
+    def interaction(self, corrector=False):
         n = self.np_
+        if not corrector or self.mdbc_corrector:
+            self.mdbc()
         self.ace = np.zeros((n, 3), np.float32)
         self.ar = np.zeros(n, np.float32)
         self.press = np.zeros(n, np.float32)
@@ -168,7 +185,7 @@ class OracleSim:
                                       _p(self.ar), _p(self.ace), _p(self.pos), _p(self.velrho), _p(self.dcell), _p(self.code))
             self.celldiv()
             n = self.np_
-            dt_c = self.interaction()
+            dt_c = self.interaction(corrector=True)
             self.L.orc_symplectic_corr(C.byref(self.c), n, self.npb, C.c_double(dt), _p(self.pospre), _p(self.velrhopre),
                                        _p(self.ar), _p(self.ace), _p(self.pos), _p(self.velrho), _p(self.dcell), _p(self.code))
             self.pospre = self.velrhopre = None

@@ -495,3 +495,96 @@ int orc_num_threads(void){
 }
 size_t orc_sizeof_cte(void){ return sizeof(orc_cte); }
 size_t orc_sizeof_div(void){ return sizeof(orc_div); }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* fsph::GetKernel_WabFac (FunSphKernel.h:71-85 cubic, :235-245 Wendland) */
+static inline float kernel_wabfac(const orc_cte* c, float rr2, float* fac){
+  const float rad=sqrtf(rr2), qq=rad/c->kernelh;
+  if(c->tkernel==2){
+    const float wqq1=1.f-0.5f*qq, wqq2=wqq1*wqq1;
+    *fac=c->bwenh*wqq2*wqq1;
+    const float wqq=qq+qq+1.f;
+    return c->awen*wqq*wqq2*wqq2;
+  }
+  if(rad>c->kernelh){ const float wqq1=2.0f-qq, wqq2=wqq1*wqq1; *fac=(c->cub_c2*wqq2/rad); return c->cub_a24*(wqq2*wqq1); }
+  { const float wqq2=qq*qq; *fac=((c->cub_c1*qq+c->cub_d1*wqq2)/rad); return c->cub_a2*(1.0f+(0.75f*qq-1.5f)*wqq2); }
+}
+
+/* JSphCpu::InteractionMdbcCorrectionT2<tker,sim2d=false> (JSphCpu_mdbc.cpp:36-150), SlipMode=1 (vel0).
+ * boundnor holds the doubled normals (boundary -> ghost node, JSph.cpp:1417), 3 floats per particle. */
+void orc_mdbc_vel0(const orc_cte* c, const orc_div* d, uint32_t n, const uint32_t* begincell, const double* pos,
+  const typecode* code, const float* boundnor, float* velrho)
+{
+  const uint32_t* beg=begincell+d->box_fluid;
+  #pragma omp parallel for schedule(guided)
+  for(int64_t p1=0;p1<(int64_t)n;p1++){
+    const float* nr=boundnor+3*p1;
+    if(nr[0]==0 && nr[1]==0 && nr[2]==0)continue;
+    float rhofinal=FLT_MAX;
+    const double gx=pos[3*p1]+(double)nr[0], gy=pos[3*p1+1]+(double)nr[1], gz=pos[3*p1+2]+(double)nr[2];
+    float rhop1=0, grx=0, gry=0, grz=0;
+    double a[4][4]; memset(a,0,sizeof(a));
+    /* nsearch::Init(pos,...) (JCellSearch_inline.h:54-69) */
+    const int cx=(int)((gx-c->domposmin[0])/c->scell)-(int)d->cellmin[0];
+    const int cy=(int)((gy-c->domposmin[1])/c->scell)-(int)d->cellmin[1];
+    const int cz=(int)((gz-c->domposmin[2])/c->scell)-(int)d->cellmin[2];
+    const int s=c->scelldiv, ncx=(int)d->ncx, ncy=(int)d->ncy, ncz=(int)d->ncz;
+    const int xini=cx-(cx<s? cx: s), xfin=cx+(ncx-cx-1<s? ncx-cx-1: s)+1;
+    const int yini=cy-(cy<s? cy: s), yfin=cy+(ncy-cy-1<s? ncy-cy-1: s)+1;
+    const int zini=cz-(cz<s? cz: s), zfin=cz+(ncz-cz-1<s? ncz-cz-1: s)+1;
+    if(xfin>xini && xini>=0 && yini>=0 && zini>=0)
+    for(int z=zini;z<zfin;z++)for(int y=yini;y<yfin;y++){
+      const uint32_t pini=beg[xini+y*ncx+z*(int)d->nsheet], pfin=beg[xfin+y*ncx+z*(int)d->nsheet];
+      for(uint32_t p2=pini;p2<pfin;p2++){
+        const float drx=(float)(gx-pos[3*(size_t)p2]), dry=(float)(gy-pos[3*(size_t)p2+1]), drz=(float)(gz-pos[3*(size_t)p2+2]);
+        const float rr2=(drx*drx+dry*dry+drz*drz);
+        if(rr2<=c->kernelsize2 && CODE_TYPE(code[p2])==CODE_TYPE_FLUID){
+          float fac; const float wab=kernel_wabfac(c,rr2,&fac);
+          const float frx=fac*drx,fry=fac*dry,frz=fac*drz;
+          const float massp2=c->massfluid, volp2=massp2/velrho[4*(size_t)p2+3];
+          rhop1+=massp2*wab; grx+=massp2*frx; gry+=massp2*fry; grz+=massp2*frz;
+          const float vwab=wab*volp2,vfrx=frx*volp2,vfry=fry*volp2,vfrz=frz*volp2;
+          a[0][0]+=vwab; a[0][1]+=drx*vwab; a[0][2]+=dry*vwab; a[0][3]+=drz*vwab;
+          a[1][0]+=vfrx; a[1][1]+=drx*vfrx; a[1][2]+=dry*vfrx; a[1][3]+=drz*vfrx;
+          a[2][0]+=vfry; a[2][1]+=drx*vfry; a[2][2]+=dry*vfry; a[2][3]+=drz*vfry;
+          a[3][0]+=vfrz; a[3][1]+=drx*vfrz; a[3][2]+=dry*vfrz; a[3][3]+=drz*vfrz;
+        }
+      }
+    }
+    {
+      #define A(i,j) a[i-1][j-1]
+      const double det=(A(1,4)*A(2,3)*A(3,2)*A(4,1) - A(1,3)*A(2,4)*A(3,2)*A(4,1) - A(1,4)*A(2,2)*A(3,3)*A(4,1) + A(1,2)*A(2,4)*A(3,3)*A(4,1) +
+                        A(1,3)*A(2,2)*A(3,4)*A(4,1) - A(1,2)*A(2,3)*A(3,4)*A(4,1) - A(1,4)*A(2,3)*A(3,1)*A(4,2) + A(1,3)*A(2,4)*A(3,1)*A(4,2) +
+                        A(1,4)*A(2,1)*A(3,3)*A(4,2) - A(1,1)*A(2,4)*A(3,3)*A(4,2) - A(1,3)*A(2,1)*A(3,4)*A(4,2) + A(1,1)*A(2,3)*A(3,4)*A(4,2) +
+                        A(1,4)*A(2,2)*A(3,1)*A(4,3) - A(1,2)*A(2,4)*A(3,1)*A(4,3) - A(1,4)*A(2,1)*A(3,2)*A(4,3) + A(1,1)*A(2,4)*A(3,2)*A(4,3) +
+                        A(1,2)*A(2,1)*A(3,4)*A(4,3) - A(1,1)*A(2,2)*A(3,4)*A(4,3) - A(1,3)*A(2,2)*A(3,1)*A(4,4) + A(1,2)*A(2,3)*A(3,1)*A(4,4) +
+                        A(1,3)*A(2,1)*A(3,2)*A(4,4) - A(1,1)*A(2,3)*A(3,2)*A(4,4) - A(1,2)*A(2,1)*A(3,3)*A(4,4) + A(1,1)*A(2,2)*A(3,3)*A(4,4));
+      if(fabs(det)>=(double)1e-3f){
+        const double i11=(A(2,2)*(A(3,3)*A(4,4)-A(3,4)*A(4,3))+A(2,3)*(A(3,4)*A(4,2)-A(3,2)*A(4,4))+A(2,4)*(A(3,2)*A(4,3)-A(3,3)*A(4,2)))/det;
+        const double i21=(A(2,1)*(A(3,4)*A(4,3)-A(3,3)*A(4,4))+A(2,3)*(A(3,1)*A(4,4)-A(3,4)*A(4,1))+A(2,4)*(A(3,3)*A(4,1)-A(3,1)*A(4,3)))/det;
+        const double i31=(A(2,1)*(A(3,2)*A(4,4)-A(3,4)*A(4,2))+A(2,2)*(A(3,4)*A(4,1)-A(3,1)*A(4,4))+A(2,4)*(A(3,1)*A(4,2)-A(3,2)*A(4,1)))/det;
+        const double i41=(A(2,1)*(A(3,3)*A(4,2)-A(3,2)*A(4,3))+A(2,2)*(A(3,1)*A(4,3)-A(3,3)*A(4,1))+A(2,3)*(A(3,2)*A(4,1)-A(3,1)*A(4,2)))/det;
+        const double i12=(A(1,2)*(A(3,4)*A(4,3)-A(3,3)*A(4,4))+A(1,3)*(A(3,2)*A(4,4)-A(3,4)*A(4,2))+A(1,4)*(A(3,3)*A(4,2)-A(3,2)*A(4,3)))/det;
+        const double i22=(A(1,1)*(A(3,3)*A(4,4)-A(3,4)*A(4,3))+A(1,3)*(A(3,4)*A(4,1)-A(3,1)*A(4,4))+A(1,4)*(A(3,1)*A(4,3)-A(3,3)*A(4,1)))/det;
+        const double i32=(A(1,1)*(A(3,4)*A(4,2)-A(3,2)*A(4,4))+A(1,2)*(A(3,1)*A(4,4)-A(3,4)*A(4,1))+A(1,4)*(A(3,2)*A(4,1)-A(3,1)*A(4,2)))/det;
+        const double i42=(A(1,1)*(A(3,2)*A(4,3)-A(3,3)*A(4,2))+A(1,2)*(A(3,3)*A(4,1)-A(3,1)*A(4,3))+A(1,3)*(A(3,1)*A(4,2)-A(3,2)*A(4,1)))/det;
+        const double i13=(A(1,2)*(A(2,3)*A(4,4)-A(2,4)*A(4,3))+A(1,3)*(A(2,4)*A(4,2)-A(2,2)*A(4,4))+A(1,4)*(A(2,2)*A(4,3)-A(2,3)*A(4,2)))/det;
+        const double i23=(A(1,1)*(A(2,4)*A(4,3)-A(2,3)*A(4,4))+A(1,3)*(A(2,1)*A(4,4)-A(2,4)*A(4,1))+A(1,4)*(A(2,3)*A(4,1)-A(2,1)*A(4,3)))/det;
+        const double i33=(A(1,1)*(A(2,2)*A(4,4)-A(2,4)*A(4,2))+A(1,2)*(A(2,4)*A(4,1)-A(2,1)*A(4,4))+A(1,4)*(A(2,1)*A(4,2)-A(2,2)*A(4,1)))/det;
+        const double i43=(A(1,1)*(A(2,3)*A(4,2)-A(2,2)*A(4,3))+A(1,2)*(A(2,1)*A(4,3)-A(2,3)*A(4,1))+A(1,3)*(A(2,2)*A(4,1)-A(2,1)*A(4,2)))/det;
+        const double i14=(A(1,2)*(A(2,4)*A(3,3)-A(2,3)*A(3,4))+A(1,3)*(A(2,2)*A(3,4)-A(2,4)*A(3,2))+A(1,4)*(A(2,3)*A(3,2)-A(2,2)*A(3,3)))/det;
+        const double i24=(A(1,1)*(A(2,3)*A(3,4)-A(2,4)*A(3,3))+A(1,3)*(A(2,4)*A(3,1)-A(2,1)*A(3,4))+A(1,4)*(A(2,1)*A(3,3)-A(2,3)*A(3,1)))/det;
+        const double i34=(A(1,1)*(A(2,4)*A(3,2)-A(2,2)*A(3,4))+A(1,2)*(A(2,1)*A(3,4)-A(2,4)*A(3,1))+A(1,4)*(A(2,2)*A(3,1)-A(2,1)*A(3,2)))/det;
+        const double i44=(A(1,1)*(A(2,2)*A(3,3)-A(2,3)*A(3,2))+A(1,2)*(A(2,3)*A(3,1)-A(2,1)*A(3,3))+A(1,3)*(A(2,1)*A(3,2)-A(2,2)*A(3,1)))/det;
+        const float rhoghost=(float)(i11*rhop1+i12*grx+i13*gry+i14*grz);
+        const float ggx=-(float)(i21*rhop1+i22*grx+i23*gry+i24*grz);
+        const float ggy=-(float)(i31*rhop1+i32*grx+i33*gry+i34*grz);
+        const float ggz=-(float)(i41*rhop1+i42*grx+i43*gry+i44*grz);
+        rhofinal=(rhoghost+ggx*(-nr[0])+ggy*(-nr[1])+ggz*(-nr[2]));
+      }
+      else if(A(1,1)>0)rhofinal=(float)(rhop1/A(1,1));
+      #undef A
+    }
+    velrho[4*p1+3]=(rhofinal!=FLT_MAX? rhofinal: c->rhopzero);
+  }
+}

@@ -129,7 +129,8 @@ def oracle_sim_from_case(casepath: str, options: dict | None = None) -> "orc.Ora
     p, a = params_from_case(casepath, options)
     cte = orc.cte_from_params(p)
     return orc.OracleSim(cte, a["idp"], a["code"], a["pos"], a["velrho"], npb=p.casenpb, dtini=p.dtini,
-                         verletsteps=p.verletsteps, ftomassp=a["ftmassp"] if len(a["ftmassp"]) else None)
+                         verletsteps=p.verletsteps, ftomassp=a["ftmassp"] if len(a["ftmassp"]) else None,
+                         boundnor=None if a["boundnor"] is None else 2.0 * np.asarray(a["boundnor"], np.float32))
 
 
 def rel_err(a, b, floor=None):

@@ -49,7 +49,7 @@ def _check_tables(ctx, g, npb, label):
     assert np.array_equal(ctx.array("code"), g["code"]), label + ": code"
 
 
-def _check_forces(ctx, g, p, label, report):
+def _check_forces(ctx, g, p, label, report, wide=False):
     ace, ar, press = ctx.array("ace"), ctx.array("ar"), ctx.array("press")
     gace = g["ace"].reshape(-1, 3)
     floor = float(p.rhopzero) * p.cs0 / float(p.kernelh) * 1e-4
@@ -59,13 +59,15 @@ def _check_forces(ctx, g, p, label, report):
     e["viscdtmax"] = abs(info.viscdtmax - float(g["viscdtmax"])) / max(float(g["viscdtmax"]), 1e-6)
     e["velmax"] = abs(info.velmax - float(g["velmax"])) / max(float(g["velmax"]), 1e-6)
     report[label] = e
-    assert e["press"] < TOL_PRESS, (label, e)
-    assert e["ace"] < TOL_ACE, (label, e)
-    assert e["ar"] < TOL_ACE, (label, e)
-    assert e["acemax"] < TOL_ACE and e["velmax"] < 1e-4 and e["viscdtmax"] < 1e-3, (label, e)
+    # mDBC fixtures: ill-conditioned 4x4 inverse per boundary particle -> wider pressure/ace tolerance (see test_oracle_vs_ref)
+    tp, ta = (2e-3, 2e-3) if wide else (TOL_PRESS, TOL_ACE)
+    assert e["press"] < tp, (label, e)
+    assert e["ace"] < ta, (label, e)
+    assert e["ar"] < ta, (label, e)
+    assert e["acemax"] < ta and e["velmax"] < 1e-4 and e["viscdtmax"] < 1e-3, (label, e)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("fx", FIXTURES)
 def test_golden_reference_parity(fx, variant, tmp_path, built_lib):
     meta = json.load(open(os.path.join(H.GOLDEN, fx, "fixture.json")))
@@ -99,7 +101,7 @@ def test_golden_reference_parity(fx, variant, tmp_path, built_lib):
             if e.code == dsb.lib.ERR_UNSUPPORTED:
                 pytest.skip(str(e))
             raise
-        _check_forces(sim2.ctx, gp, p, tag, report)
+        _check_forces(sim2.ctx, gp, p, tag, report, wide=("mdbc" in fx))
         key = "dt_p" if "dt_p" in gp else "dt"
         assert abs(sim2.ctx.info().dt_last - float(gp[key])) <= TOL_DT * float(gp[key])
         sim2.close()
@@ -178,3 +180,26 @@ def test_errors_are_loud(tmp_path, built_lib):
     with pytest.raises(KeyError):
         sim.ctx.array("nonexistent")
     sim.close()
+
+
+@pytest.mark.parametrize("opts", [{}, {"ViscoTreatment": 2, "Visco": 1e-6, "DensityDT": 3}, {"Kernel": 1, "DensityDT": 1}])
+def test_tile_variant_is_bit_identical_to_gather(opts, tmp_path, built_lib):
+    """Variant 1 (FP16 filter + exact body) visits hits in the reference order, so ace/ar must equal variant 0 bit for bit."""
+    H.write_case(tmp_path, dp=0.02, params=opts)
+    case = str(tmp_path / "Case")
+    res = []
+    for variant in (0, 1, 2):
+        sim = dsb.Simulation(case)
+        sim.ctx.set_variant(variant)
+        sim.ctx.run_steps(6)
+        inter = dsb.lib.INTER_SYMPREDICTOR
+        sim.ctx.interaction(inter)
+        info = sim.ctx.info()
+        res.append((sim.ctx.array("acear").copy(), sim.ctx.array("velrho").copy(), info.acemax, info.viscdtmax, info.dt_last))
+        sim.close()
+    a0, a1, a2 = res
+    assert np.array_equal(a0[1].view(np.uint32), a1[1].view(np.uint32)), "state after 6 steps differs between variants"
+    assert np.array_equal(a0[0].view(np.uint32), a1[0].view(np.uint32)), "ace/ar differ between variants"
+    assert a0[2:] == a1[2:]
+    assert np.array_equal(a0[0].view(np.uint32), a2[0].view(np.uint32)), "ace/ar differ between variants 0 and 2"
+    assert np.array_equal(a0[1].view(np.uint32), a2[1].view(np.uint32)) and a0[2:] == a2[2:]
