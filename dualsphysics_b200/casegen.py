@@ -203,8 +203,9 @@ def write_case(dirpath: str, name: str, spec: DamBreakSpec) -> dict:
         pf = pos[nfixed + nmoving:nbound]
         masspart = c["massbound"] * spec.floating_rel_density
         massbody = masspart * nfloat
-        center = pf.mean(axis=0)
+        center = np.array([float(v) for v in pf.mean(axis=0)])
         d = pf - center
+        center = [float(v) for v in center]
         # inertia tensor of the particle cloud (GenCase convention: sum of point masses)
         ixx = masspart * float(np.sum(d[:, 1] ** 2 + d[:, 2] ** 2))
         iyy = masspart * float(np.sum(d[:, 0] ** 2 + d[:, 2] ** 2))
@@ -212,7 +213,7 @@ def write_case(dirpath: str, name: str, spec: DamBreakSpec) -> dict:
         ixy = -masspart * float(np.sum(d[:, 0] * d[:, 1]))
         ixz = -masspart * float(np.sum(d[:, 0] * d[:, 2]))
         iyz = -masspart * float(np.sum(d[:, 1] * d[:, 2]))
-        ft = {"massbody": massbody, "masspart": masspart, "center": center.tolist(),
+        ft = {"massbody": massbody, "masspart": masspart, "center": list(center),
               "inertia": [[ixx, ixy, ixz], [ixy, iyy, iyz], [ixz, iyz, izz]]}
         x.append(f'      <floating mkbound="{mkb}" mk="{11 + mkb}" begin="{begin}" count="{nfloat}">')
         x.append(f'        <massbody value="{massbody!r}" />')
@@ -220,7 +221,7 @@ def write_case(dirpath: str, name: str, spec: DamBreakSpec) -> dict:
         x.append(f'        <center x="{center[0]!r}" y="{center[1]!r}" z="{center[2]!r}" />')
         x.append('        <inertia>')
         for r, row in enumerate(ft["inertia"]):
-            x.append(f'          <values{r + 1} v{r + 1}1="{row[0]!r}" v{r + 1}2="{row[1]!r}" v{r + 1}3="{row[2]!r}" />')
+            x.append(f'          <values v{r + 1}1="{row[0]!r}" v{r + 1}2="{row[1]!r}" v{r + 1}3="{row[2]!r}" />')
         x.append('        </inertia>')
         x.append('      </floating>')
         begin += nfloat

@@ -1,8 +1,5 @@
 // stubs.cu -- entry points not built yet in this round; they fail loudly (B2S_ERR_UNSUPPORTED), never fall back.
 #include "b2s_internal.h"
-int b2s_floating_impl(b2s_ctx* ctx,double,bool,bool){ return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"floating bodies not built"); }
-extern "C" int b2s_set_floatings(b2s_ctx* ctx,uint32_t,const b2s_floating*){ return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"floating bodies not built"); }
-extern "C" int b2s_get_floatings(b2s_ctx* ctx,uint32_t,b2s_floating*){ return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"floating bodies not built"); }
 extern "C" int b2s_slab_config(b2s_ctx* ctx,int,int,uint32_t,uint32_t){ return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"slab decomposition not built"); }
 extern "C" int b2s_slab_pack_halo(b2s_ctx* ctx,int,void**,uint32_t*){ return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"slab decomposition not built"); }
 extern "C" int b2s_slab_unpack_halo(b2s_ctx* ctx,int,const void*,uint32_t){ return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"slab decomposition not built"); }

@@ -77,6 +77,7 @@ class Probe : public JSphCpuSingle{
 public:
   string DirProbe;
   int DumpLevel;   // 0: dt/maxima only, 1: + ace/ar + state, 2: + cell tables
+  vector<double> FtDump; vector<float> FtDumpF;
 
   void DumpCellDiv(Dump& d){
     JCellDivCpuSingle* cd=CellDivSingle;
@@ -95,6 +96,18 @@ public:
   void DumpState(Dump& d){
     d.u32("np",Np); d.u32("npb",Npb); d.u32("npbok",NpbOk); d.u32("nstep",Nstep);
     d.f64("timestep",TimeStep); d.f64("symplectic_dtpre",SymplecticDtPre);
+    if(FtCount){
+      // floating bodies: center (f64 x3), fvel, fomega, angles (f32 x3) per body, flattened
+      FtDump.assign(size_t(FtCount)*3,0); FtDumpF.assign(size_t(FtCount)*9,0);
+      for(unsigned cf=0;cf<FtCount;cf++){
+        FtDump[cf*3]=FtObjs[cf].center.x; FtDump[cf*3+1]=FtObjs[cf].center.y; FtDump[cf*3+2]=FtObjs[cf].center.z;
+        FtDumpF[cf*9+0]=FtObjs[cf].fvel.x;   FtDumpF[cf*9+1]=FtObjs[cf].fvel.y;   FtDumpF[cf*9+2]=FtObjs[cf].fvel.z;
+        FtDumpF[cf*9+3]=FtObjs[cf].fomega.x; FtDumpF[cf*9+4]=FtObjs[cf].fomega.y; FtDumpF[cf*9+5]=FtObjs[cf].fomega.z;
+        FtDumpF[cf*9+6]=FtObjs[cf].angles.x; FtDumpF[cf*9+7]=FtObjs[cf].angles.y; FtDumpF[cf*9+8]=FtObjs[cf].angles.z;
+      }
+      d.add("ft_center",5,FtDump.size(),FtDump.data());
+      d.add("ft_velomegaang",4,FtDumpF.size(),FtDumpF.data());
+    }
     if(DumpLevel>=1){
       d.add("idp",2,Np,Idp_c->cptr());
       d.add("code",1,Np,Code_c->cptr());
