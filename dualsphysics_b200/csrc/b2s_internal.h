@@ -73,6 +73,7 @@ struct DivState {
   uint32_t npb_ignore, npb_out, npf_out, npb_outignore, npf_outignore;
   uint32_t npf_out_total;
   uint32_t error;          // !=0: boundary particle excluded etc.
+  uint32_t slab_nbound_tmp; // boundary-type particles appended by the last slab unpack
 };
 
 // ---- device-resident step scalars (dt maxima as ordered uints for atomicMax) ----
@@ -136,6 +137,8 @@ struct b2s_ctx {
   uint32_t ftcount; std::vector<b2s_floating> fts; float* ft_massp_dev; float* ft_sums_dev; float* ft_sums_h;
   void* ft_dev; // device copy of per-floating update data
   std::vector<Motion> motions;
+  // slab decomposition (slab.cu)
+  bool slab_on; int slab_rank, slab_nranks; uint32_t slab_cxa, slab_cxb; uint32_t* slab_counts; uint8_t* slab_flags; size_t slab_counts_len;
   // tile interaction variant (forces_tile.cu)
   uint32_t* tile_seglist; uint32_t* tile_nseg; uint32_t tile_nseg_max; bool tile_seglist_valid; bool tile_attr_set[2][2][4][4];
   // scratch for byid download

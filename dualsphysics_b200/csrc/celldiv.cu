@@ -48,6 +48,35 @@ __global__ void __launch_bounds__(DIV_BS) k_limits(uint32_t n, uint32_t pini, co
   }
 }
 
+// Slab mode: ghost/migrant particles are appended behind the owned ones, so boundary and fluid particles are no longer
+// two index ranges; the limits are then selected by particle type in one pass.
+__global__ void __launch_bounds__(DIV_BS) k_limits_bytype(DivState* ds, const uint32_t* __restrict__ dcell,
+  const typecode* __restrict__ code, uint32_t dcc)
+{
+  const uint32_t n=ds->np;
+  uint32_t mn[2][3]={{0xffffffffu,0xffffffffu,0xffffffffu},{0xffffffffu,0xffffffffu,0xffffffffu}}, mx[2][3]={{0,0,0},{0,0,0}};
+  for(uint32_t p=blockIdx.x*blockDim.x+threadIdx.x; p<n; p+=gridDim.x*blockDim.x){
+    const typecode c=code[p];
+    if(B2S_CODE_SPECIAL(c)<B2S_CODE_OUTIGNORE){
+      const int t=(B2S_CODE_TYPE(c)<B2S_CODE_TYPE_FLOATING? 0: 1);
+      const uint32_t rc=dcell[p];
+      const uint32_t cx=B2S_DCEL_CELLX(dcc,rc), cy=B2S_DCEL_CELLY(dcc,rc), cz=B2S_DCEL_CELLZ(dcc,rc);
+      mn[t][0]=min(mn[t][0],cx); mn[t][1]=min(mn[t][1],cy); mn[t][2]=min(mn[t][2],cz);
+      mx[t][0]=max(mx[t][0],cx); mx[t][1]=max(mx[t][1],cy); mx[t][2]=max(mx[t][2],cz);
+    }
+  }
+  #pragma unroll
+  for(int t=0;t<2;t++){
+    uint32_t* lim=(t==0? ds->blim: ds->flim);
+    #pragma unroll
+    for(int k=0;k<3;k++){
+      const uint32_t a=__reduce_min_sync(0xffffffffu,mn[t][k]);
+      const uint32_t b=__reduce_max_sync(0xffffffffu,mx[t][k]);
+      if((threadIdx.x&31)==0){ if(a!=0xffffffffu)atomicMin(&lim[k],a); if(b)atomicMax(&lim[3+k],b); }
+    }
+  }
+}
+
 // CalcCellDomain + MergeMapCellBoundFluid + PrepareNct (JCellDivGpuSingle.cpp:47-125), one thread.
 __global__ void k_divstate(DivState* ds, uint32_t dcx, uint32_t dcy, uint32_t dcz, uint32_t scelldiv){
   if(threadIdx.x||blockIdx.x)return;
@@ -290,7 +319,7 @@ __global__ void __launch_bounds__(DIV_BS) k_reorder(const DivState* __restrict__
       pp.z=float((z   -cte.domposmin[2])-cte.scell_d*double(cz));
       pp.w=b2s_press(vr.w,cte);
       a.posp[p]=pp;
-      if(p>=ds->npb || cte.dt_allparticles)v2=vr.x*vr.x+vr.y*vr.y+vr.z*vr.z;
+      if((p>=ds->npb || cte.dt_allparticles) && B2S_CODE_ISNORMAL(cod))v2=vr.x*vr.x+vr.y*vr.y+vr.z*vr.z;   // ghosts (slab halos) excluded
       if(a.ridp && id>=a.casenfixed && id<a.casenbound)a.ridp[id-a.casenfixed]=p;
     }
   }
@@ -314,10 +343,11 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   const DevCte& c=ctx->cte;
   if(nptot==0)return B2S_OK;
   // 1. limits
-  k_limits_reset<<<1,32,0,s>>>(ctx->div,ctx->bound_changed? 1: 0); B2S_LAUNCHED(ctx);
+  k_limits_reset<<<1,32,0,s>>>(ctx->div,(ctx->bound_changed || ctx->slab_on)? 1: 0); B2S_LAUNCHED(ctx);
   const unsigned gl=min(b2s_blocks(nptot,DIV_BS),148u*8u);
-  if(ctx->bound_changed && npb){ k_limits<<<gl,DIV_BS,0,s>>>(npb,0,ctx->cur.dcell,ctx->cur.code,c.domcellcode,ctx->div->blim); B2S_LAUNCHED(ctx); }
-  if(nptot>npb){ k_limits<<<gl,DIV_BS,0,s>>>(nptot-npb,npb,ctx->cur.dcell,ctx->cur.code,c.domcellcode,ctx->div->flim); B2S_LAUNCHED(ctx); }
+  if(ctx->slab_on){ k_limits_bytype<<<gl,DIV_BS,0,s>>>(ctx->div,ctx->cur.dcell,ctx->cur.code,c.domcellcode); B2S_LAUNCHED(ctx); }
+  else if(ctx->bound_changed && npb){ k_limits<<<gl,DIV_BS,0,s>>>(npb,0,ctx->cur.dcell,ctx->cur.code,c.domcellcode,ctx->div->blim); B2S_LAUNCHED(ctx); }
+  if(!ctx->slab_on && nptot>npb){ k_limits<<<gl,DIV_BS,0,s>>>(nptot-npb,npb,ctx->cur.dcell,ctx->cur.code,c.domcellcode,ctx->div->flim); B2S_LAUNCHED(ctx); }
   k_divstate<<<1,32,0,s>>>(ctx->div,c.domcells[0],c.domcells[1],c.domcells[2],(uint32_t)c.scelldiv); B2S_LAUNCHED(ctx);
   // 2. keys
   k_presort<<<b2s_blocks(nptot,DIV_BS),DIV_BS,0,s>>>(ctx->div,ctx->cur.dcell,ctx->cur.code,c.domcellcode,ctx->cellpart,ctx->sortpart); B2S_LAUNCHED(ctx);
@@ -352,6 +382,7 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   a.posp=ctx->posp;
   a.ridp=(ctx->prm.casenmoving+ctx->prm.casenfloat? ctx->ridp: NULL);
   a.casenfixed=ctx->prm.casenfixed; a.casenbound=ctx->prm.casenbound;
+  if(a.ridp)B2S_CUDA(ctx,cudaMemsetAsync(ctx->ridp,0xff,size_t(ctx->prm.casenmoving+ctx->prm.casenfloat)*4,s));
   k_reorder<<<b2s_blocks(nptot,DIV_BS),DIV_BS,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte); B2S_LAUNCHED(ctx);
   { PartSet t=ctx->cur; ctx->cur=ctx->alt; ctx->alt=t; }
   if(ctx->pre_active){
@@ -365,3 +396,5 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   B2S_CUDA(ctx,cudaGetLastError());
   return B2S_OK;
 }
+
+void b2s_launch_scan_excl(cudaStream_t s, uint32_t* data, uint32_t n){ k_scan_excl<<<1,1024,0,s>>>(data,n); }

@@ -71,6 +71,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   ctx->np_host=ctx->npb_host=ctx->npbok_host=0;
   ctx->launches=0; ctx->variant=0; ctx->pre_active=false; ctx->bound_changed=true; ctx->ftcount=0;
   ctx->verletstep=0;
+  ctx->slab_on=false; ctx->slab_rank=0; ctx->slab_nranks=1; ctx->slab_cxa=0; ctx->slab_cxb=0; ctx->slab_counts=NULL; ctx->slab_flags=NULL; ctx->slab_counts_len=0;
   ctx->tile_seglist=NULL; ctx->tile_nseg=NULL; ctx->tile_nseg_max=0; ctx->tile_seglist_valid=false; memset(ctx->tile_attr_set,0,sizeof(ctx->tile_attr_set));
   ctx->ft_massp_dev=NULL; ctx->ft_sums_dev=NULL; ctx->ft_sums_h=NULL; ctx->ft_dev=NULL; ctx->scratch=NULL; ctx->scratch_bytes=0;
   ctx->pospre_xy=ctx->pospre_xy_alt=NULL; ctx->pospre_z=ctx->pospre_z_alt=NULL; ctx->velrhopre=ctx->velrhopre_alt=NULL;
@@ -125,7 +126,7 @@ extern "C" int b2s_destroy(b2s_ctx* ctx){
   cudaFree(ctx->cellpart); cudaFree(ctx->sortpart); cudaFree(ctx->cellpart_alt); cudaFree(ctx->sortpart_alt);
   cudaFree(ctx->begincell); cudaFree(ctx->radix_counts); cudaFree(ctx->ridp);
   cudaFree(ctx->div); cudaFree(ctx->step);
-  cudaFree(ctx->tile_seglist); cudaFree(ctx->tile_nseg);
+  cudaFree(ctx->tile_seglist); cudaFree(ctx->tile_nseg); cudaFree(ctx->slab_counts); cudaFree(ctx->slab_flags);
   cudaFree(ctx->ft_massp_dev); cudaFree(ctx->ft_sums_dev); cudaFree(ctx->ft_dev); cudaFree(ctx->scratch);
   if(ctx->ft_sums_h)cudaFreeHost(ctx->ft_sums_h);
   if(ctx->div_h)cudaFreeHost(ctx->div_h);
@@ -496,4 +497,35 @@ extern "C" int b2s_time_interaction(b2s_ctx* ctx, int reps, float* ms_per_launch
   *ms_per_launch=ms/float(reps);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return B2S_OK;
+}
+
+// ---- slab-mode step pieces (see include/b2s.h; orchestration in dualsphysics_b200/slab.py) ------------------------------
+int b2s_dtvariable_impl(b2s_ctx* ctx, int interstep);
+
+extern "C" int b2s_slab_forces(b2s_ctx* ctx, int interstep){
+  if(!ctx)return B2S_ERR_ARG;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  if(ctx->prm.tboundary==B2S_BC_MDBC && (ctx->prm.mdbc_corrector || interstep!=B2S_INTER_SYMCORRECTOR)){ int r=b2s_mdbc_impl(ctx); if(r)return r; }
+  return b2s_forces_impl(ctx,-1);     // -1: no DtVariable yet (the maxima are all-reduced first)
+}
+extern "C" int b2s_slab_apply_dt(b2s_ctx* ctx, int interstep){
+  if(!ctx)return B2S_ERR_ARG;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  return b2s_dtvariable_impl(ctx,interstep);
+}
+extern "C" int b2s_slab_integrate(b2s_ctx* ctx, int mode){
+  if(!ctx || mode<0 || mode>2)return B2S_ERR_ARG;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  if(mode==1)b2s_set_dt_device(ctx,0);        // dt=SymplecticDtPre at the start of the step
+  else if(mode==0)b2s_set_dt_device(ctx,1);   // Verlet: dt=DtVariable(true)
+  return b2s_integrate_impl(ctx,mode,0,true);
+}
+extern "C" int b2s_slab_step_end(b2s_ctx* ctx, double* dt_out){
+  if(!ctx)return B2S_ERR_ARG;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  if(!ctx->motions.empty()){ int r=b2s_motion_impl(ctx,0,0); if(r)return r; }
+  k_step_end<<<1,1,0,ctx->stream>>>(ctx->step,ctx->prm.tstep==B2S_STEP_SYMPLECTIC? 1: 0); B2S_LAUNCHED(ctx);
+  int r=b2s_sync_info(ctx);
+  if(dt_out)*dt_out=ctx->step_h->dt;
+  return r;
 }

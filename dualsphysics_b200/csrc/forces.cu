@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(F_BS) k_forces_bound(ForcesArgs g, const __gri
       }
     }
     g.acear[p1]=make_float4(0.f,0.f,0.f,arp1);
+    if(!B2S_CODE_ISNORMAL(g.code[p1]))visc=0.f;
   }
   #pragma unroll
   for(int o=16;o;o>>=1)visc=fmaxf(visc,__shfl_xor_sync(0xffffffffu,visc,o));
@@ -227,7 +228,14 @@ int b2s_forces_impl(b2s_ctx* ctx, int interstep){
     B2S_LAUNCHED(ctx);
   }
   if(ctx->cte.tvisco==B2S_VISCO_LAMINARSPS)std::swap(ctx->spstau,ctx->spstau_new);
-  k_dtvariable<<<1,1,0,s>>>(ctx->step,(interstep==B2S_INTER_SYMPREDICTOR? 0: 1),ctx->cte); B2S_LAUNCHED(ctx);
+  if(interstep>=0){ k_dtvariable<<<1,1,0,s>>>(ctx->step,(interstep==B2S_INTER_SYMPREDICTOR? 0: 1),ctx->cte); B2S_LAUNCHED(ctx); }
+  B2S_CUDA(ctx,cudaGetLastError());
+  return B2S_OK;
+}
+
+// DtVariable alone (slab mode: called after the maxima have been all-reduced over the ranks).
+int b2s_dtvariable_impl(b2s_ctx* ctx, int interstep){
+  k_dtvariable<<<1,1,0,ctx->stream>>>(ctx->step,(interstep==B2S_INTER_SYMPREDICTOR? 0: 1),ctx->cte); B2S_LAUNCHED(ctx);
   B2S_CUDA(ctx,cudaGetLastError());
   return B2S_OK;
 }

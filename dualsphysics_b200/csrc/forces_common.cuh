@@ -189,8 +189,9 @@ __device__ __forceinline__ void finalize_store(const ForcesArgs& g,const DevCte&
   }
   if(c.simulate2d)res.y=0.f;
   g.acear[p1]=res;
-  viscmax=fmaxf(af.visc,ab.visc);
-  if(B2S_CODE_ISNORMAL(g.code[p1]))ace2=res.x*res.x+res.y*res.y+res.z*res.z;
+  const bool owned=B2S_CODE_ISNORMAL(g.code[p1]);   // slab halo ghosts carry CODE_PERIODIC and do not enter the dt maxima
+  viscmax=(owned? fmaxf(af.visc,ab.visc): 0.f);
+  if(owned)ace2=res.x*res.x+res.y*res.y+res.z*res.z;
   if(TVISCO==B2S_VISCO_LAMINARSPS){
     // ComputeSpsTau (JSphCpu.cpp:1279-1307) on the accumulated 2*strain of both passes.
     const float sxx=af.sxx+ab.sxx, sxy=af.sxy+ab.sxy, sxz=af.sxz+ab.sxz, syy=af.syy+ab.syy, syz=af.syz+ab.syz, szz=af.szz+ab.szz;

@@ -52,6 +52,11 @@ __device__ __forceinline__ void update_pos(const DevCte& c, double rx,double ry,
 __global__ void __launch_bounds__(I_BS) k_sym_pre(IntegArgs a, const __grid_constant__ DevCte c){
   const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
   if(p>=a.ds->np)return;
+  if(B2S_CODE_SPECIAL(a.code[p])==B2S_CODE_PERIODIC){ // slab halo ghost: frozen, dropped by the next cell divide
+    a.velrho_w[p]=a.velrho_r[p]; a.posxy_w[p]=a.posxy_r[p]; a.posz_w[p]=a.posz_r[p];
+    a.code[p]=typecode(B2S_CODE_SETNORMAL(a.code[p])|B2S_CODE_OUTIGNORE);
+    return;
+  }
   const double dt05=a.st->dt*.5;
   const float4 pre=a.velrho_r[p];
   const float4 acear=a.acear[p];
@@ -87,6 +92,11 @@ __global__ void __launch_bounds__(I_BS) k_sym_pre(IntegArgs a, const __grid_cons
 __global__ void __launch_bounds__(I_BS) k_sym_corr(IntegArgs a, const __grid_constant__ DevCte c){
   const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
   if(p>=a.ds->np)return;
+  if(B2S_CODE_SPECIAL(a.code[p])==B2S_CODE_PERIODIC){ // slab halo ghost: frozen, dropped by the next cell divide
+    a.velrho_w[p]=a.velrho_aux[p];
+    a.code[p]=typecode(B2S_CODE_SETNORMAL(a.code[p])|B2S_CODE_OUTIGNORE);
+    return;
+  }
   const double dt=a.st->dt, dt05=dt*.5;
   const float4 pre=a.velrho_r[p];
   const float4 acear=a.acear[p];
@@ -124,6 +134,11 @@ __global__ void __launch_bounds__(I_BS) k_sym_corr(IntegArgs a, const __grid_con
 __global__ void __launch_bounds__(I_BS) k_verlet(IntegArgs a, const __grid_constant__ DevCte c){
   const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
   if(p>=a.ds->np)return;
+  if(B2S_CODE_SPECIAL(a.code[p])==B2S_CODE_PERIODIC){ // slab halo ghost: frozen, dropped by the next cell divide
+    a.velrho_w[p]=a.velrho_r[p];
+    a.code[p]=typecode(B2S_CODE_SETNORMAL(a.code[p])|B2S_CODE_OUTIGNORE);
+    return;
+  }
   const double dt=a.st->dt;
   const double dt2=(a.euler? dt: dt+dt);
   const float4 v1=a.velrho_r[p];

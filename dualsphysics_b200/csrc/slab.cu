@@ -1,0 +1,213 @@
+// slab.cu -- 1-D slab decomposition along x for several GPUs (one process / one ctx per GPU).
+//
+// No reference counterpart: DualSPHysics v5.4 is single-GPU (AVAILABLE_MGPU is hard-false, src/source/DualSphDef.h:96-101).
+// The mechanism mirrors the reference's periodic-boundary ghosts (JSphGpuSingle::RunPeriodic, src/source/JSphGpuSingle.cpp:276-366;
+// KerPeriodicDuplicate*, src/source/JSphGpu_ker.cu:2267-2399): neighbours' particles within one cell layer of a cut are
+// appended as CODE_PERIODIC duplicates before the cell divide, take part in the interaction as neighbours, are frozen by
+// the integrators and dropped (CODE_OUTIGNORE) by the next divide.  Particles that cross a cut migrate with their full
+// state.  All ranks use the SAME global cell grid (domposmin, dcell code), so cell coordinates are bit-identical to the
+// single-GPU run.  The transport (NCCL send/recv over NVLink, or device copies in the single-process test) is the
+// caller's: this file only packs/unpacks contiguous device buffers -- deterministic order (scan-based compaction).
+//
+// Record layout (little endian, 8-byte aligned): u32 idp | u16 code | u16 0 | f64 pos[3] | f32 velrho[4]   (48 B)
+//   migrants append: [f64 pospre[3] f32 velrhopre[4]] (Symplectic, predictor active) | [f32 velrhom1[4]] (Verlet)
+//   both append:     [f32 tau[6]] (Laminar+SPS) | [f32 boundnor[4]] (mDBC)
+#include "b2s_internal.h"
+
+#define S_BS 256
+
+void b2s_launch_scan_excl(cudaStream_t s, uint32_t* data, uint32_t n);   // celldiv.cu
+
+struct SlabLayout { uint32_t bytes, off_pre, off_m1, off_tau, off_nor; };
+
+static SlabLayout slab_layout(const b2s_ctx* ctx, int kind){
+  SlabLayout l; l.bytes=48; l.off_pre=l.off_m1=l.off_tau=l.off_nor=0;
+  if(kind==1 && ctx->pre_active){ l.off_pre=l.bytes; l.bytes+=40; }
+  if(kind==1 && ctx->velrhom1){ l.off_m1=l.bytes; l.bytes+=16; }
+  if(ctx->spstau){ l.off_tau=l.bytes; l.bytes+=24; }
+  if(ctx->boundnor){ l.off_nor=l.bytes; l.bytes+=16; }
+  return l;
+}
+
+struct SlabArrays {
+  uint32_t* idp; typecode* code; uint32_t* dcell; double2* posxy; double* posz; float4* velrho;
+  double2* pre_xy; double* pre_z; float4* pre_v; float4* m1; float* tau; float4* nor;
+};
+
+// flags: bit0 -> goes to the left neighbour, bit1 -> right neighbour
+__global__ void __launch_bounds__(S_BS) k_slab_flag(const DivState* __restrict__ ds, const typecode* __restrict__ code, const uint32_t* __restrict__ dcell,
+  uint32_t dcc, int kind, int has_left, int has_right, uint32_t cxa, uint32_t cxb, uint32_t d, uint8_t* flags, uint32_t* counts, uint32_t nblocks)
+{
+  __shared__ uint32_t cl, cr;
+  if(threadIdx.x==0){ cl=0; cr=0; }
+  __syncthreads();
+  const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
+  uint8_t f=0;
+  if(p<ds->np){
+    const typecode c=code[p];
+    if(B2S_CODE_SPECIAL(c)==B2S_CODE_NORMAL){
+      const uint32_t cx=B2S_DCEL_CELLX(dcc,dcell[p]);
+      if(kind==0){ // halo: owned particles in the cell layers next to a cut
+        if(has_left && cx>=cxa && cx<cxa+d)f|=1;
+        if(has_right && cx<cxb && cx+d>=cxb)f|=2;
+      }
+      else{        // migrants: owned particles whose cell left the slab
+        if(has_left && cx<cxa)f|=1;
+        if(has_right && cx>=cxb)f|=2;
+      }
+    }
+    flags[p]=f;
+  }
+  const uint32_t bl=__ballot_sync(0xffffffffu,f&1), br=__ballot_sync(0xffffffffu,f&2);
+  if((threadIdx.x&31)==0){ if(bl)atomicAdd(&cl,__popc(bl)); if(br)atomicAdd(&cr,__popc(br)); }
+  __syncthreads();
+  if(threadIdx.x==0){ counts[blockIdx.x]=cl; counts[nblocks+1+blockIdx.x]=cr; }
+}
+
+__device__ __forceinline__ void slab_write(char* rec, const SlabLayout& l, const SlabArrays& a, uint32_t p){
+  *reinterpret_cast<uint32_t*>(rec)=a.idp[p];
+  *reinterpret_cast<uint32_t*>(rec+4)=uint32_t(a.code[p]);
+  double* d=reinterpret_cast<double*>(rec+8);
+  const double2 xy=a.posxy[p]; d[0]=xy.x; d[1]=xy.y; d[2]=a.posz[p];
+  *reinterpret_cast<float4*>(rec+32)=a.velrho[p];
+  if(l.off_pre){ double* q=reinterpret_cast<double*>(rec+l.off_pre); const double2 pxy=a.pre_xy[p]; q[0]=pxy.x; q[1]=pxy.y; q[2]=a.pre_z[p]; *reinterpret_cast<float4*>(rec+l.off_pre+24)=a.pre_v[p]; }
+  if(l.off_m1)*reinterpret_cast<float4*>(rec+l.off_m1)=a.m1[p];
+  if(l.off_tau){ float2* t=reinterpret_cast<float2*>(rec+l.off_tau); const float2* s=reinterpret_cast<const float2*>(a.tau+size_t(p)*6); t[0]=s[0]; t[1]=s[1]; t[2]=s[2]; }
+  if(l.off_nor)*reinterpret_cast<float4*>(rec+l.off_nor)=a.nor[p];
+}
+
+__global__ void __launch_bounds__(S_BS) k_slab_scatter(const DivState* __restrict__ ds, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ offs,
+  uint32_t nblocks, SlabLayout l, SlabArrays a, int kind, char* left, char* right, uint32_t cap)
+{
+  __shared__ uint32_t wl[S_BS/32], wr[S_BS/32];
+  const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
+  const int lane=threadIdx.x&31, w=threadIdx.x>>5;
+  const uint8_t f=(p<ds->np? flags[p]: uint8_t(0));
+  const uint32_t bl=__ballot_sync(0xffffffffu,f&1), br=__ballot_sync(0xffffffffu,f&2);
+  if(lane==0){ wl[w]=__popc(bl); wr[w]=__popc(br); }
+  __syncthreads();
+  uint32_t pl=0, pr=0;
+  for(int k=0;k<w;k++){ pl+=wl[k]; pr+=wr[k]; }
+  const uint32_t lm=(1u<<lane)-1u;
+  if(f&1){ const uint32_t i=offs[blockIdx.x]+pl+__popc(bl&lm); if(i<cap)slab_write(left+size_t(i)*l.bytes,l,a,p); }
+  if(f&2){ const uint32_t i=offs[nblocks+1+blockIdx.x]+pr+__popc(br&lm); if(i<cap)slab_write(right+size_t(i)*l.bytes,l,a,p); }
+  if(kind==1 && f)a.code[p]=typecode(B2S_CODE_SETNORMAL(a.code[p])|B2S_CODE_OUTIGNORE);   // migrated away: dropped by the next divide
+}
+
+__global__ void __launch_bounds__(S_BS) k_slab_unpack(DivState* ds, const char* __restrict__ buf, uint32_t n, SlabLayout l, SlabArrays a, int kind,
+  const __grid_constant__ DevCte c)
+{
+  const uint32_t i=blockIdx.x*blockDim.x+threadIdx.x;
+  if(i>=n)return;
+  const uint32_t p=ds->np+i;
+  const char* rec=buf+size_t(i)*l.bytes;
+  const uint32_t id=*reinterpret_cast<const uint32_t*>(rec);
+  typecode cod=typecode(*reinterpret_cast<const uint32_t*>(rec+4));
+  if(kind==0)cod=typecode(B2S_CODE_SETNORMAL(cod)|B2S_CODE_PERIODIC);   // halo ghost
+  const double* d=reinterpret_cast<const double*>(rec+8);
+  a.idp[p]=id; a.code[p]=cod; a.posxy[p]=make_double2(d[0],d[1]); a.posz[p]=d[2];
+  a.velrho[p]=*reinterpret_cast<const float4*>(rec+32);
+  a.dcell[p]=B2S_DCEL_CELL(c.domcellcode,uint32_t((d[0]-c.domposmin[0])/c.scell_d),uint32_t((d[1]-c.domposmin[1])/c.scell_d),uint32_t((d[2]-c.domposmin[2])/c.scell_d));
+  if(l.off_pre){ const double* q=reinterpret_cast<const double*>(rec+l.off_pre); a.pre_xy[p]=make_double2(q[0],q[1]); a.pre_z[p]=q[2]; a.pre_v[p]=*reinterpret_cast<const float4*>(rec+l.off_pre+24); }
+  else if(a.pre_v){ a.pre_xy[p]=make_double2(d[0],d[1]); a.pre_z[p]=d[2]; a.pre_v[p]=*reinterpret_cast<const float4*>(rec+32); }
+  if(l.off_m1)a.m1[p]=*reinterpret_cast<const float4*>(rec+l.off_m1);
+  else if(a.m1)a.m1[p]=*reinterpret_cast<const float4*>(rec+32);
+  if(l.off_tau){ const float2* s=reinterpret_cast<const float2*>(rec+l.off_tau); float2* t=reinterpret_cast<float2*>(a.tau+size_t(p)*6); t[0]=s[0]; t[1]=s[1]; t[2]=s[2]; }
+  if(l.off_nor)a.nor[p]=*reinterpret_cast<const float4*>(rec+l.off_nor);
+  if(B2S_CODE_TYPE(cod)<B2S_CODE_TYPE_FLOATING)atomicAdd(&ds->slab_nbound_tmp,1u);
+}
+__global__ void k_slab_unpack_commit(DivState* ds, uint32_t n){ ds->np+=n; ds->npb+=ds->slab_nbound_tmp; ds->slab_nbound_tmp=0; }
+
+// keeps only the particles of this slab (initial distribution): everything outside [cxa,cxb) is marked OUTIGNORE
+__global__ void __launch_bounds__(S_BS) k_slab_select(const DivState* __restrict__ ds, typecode* code, const uint32_t* __restrict__ dcell, uint32_t dcc, uint32_t cxa, uint32_t cxb){
+  const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
+  if(p>=ds->np)return;
+  const typecode c=code[p];
+  if(B2S_CODE_SPECIAL(c)!=B2S_CODE_NORMAL)return;
+  const uint32_t cx=B2S_DCEL_CELLX(dcc,dcell[p]);
+  if(cx<cxa || cx>=cxb)code[p]=typecode(B2S_CODE_SETNORMAL(c)|B2S_CODE_OUTIGNORE);
+}
+__global__ void k_slab_fix_counts(DivState* ds){ ds->npf_out_total=0; }
+
+static SlabArrays slab_arrays(b2s_ctx* ctx){
+  SlabArrays a;
+  a.idp=ctx->cur.idp; a.code=ctx->cur.code; a.dcell=ctx->cur.dcell; a.posxy=ctx->cur.posxy; a.posz=ctx->cur.posz; a.velrho=ctx->cur.velrho;
+  a.pre_xy=(ctx->pre_active? ctx->pospre_xy: NULL); a.pre_z=(ctx->pre_active? ctx->pospre_z: NULL); a.pre_v=(ctx->pre_active? ctx->velrhopre: NULL);
+  a.m1=ctx->velrhom1; a.tau=ctx->spstau; a.nor=ctx->boundnor;
+  return a;
+}
+
+extern "C" int b2s_slab_config(b2s_ctx* ctx, int rank, int nranks, uint32_t cx_begin, uint32_t cx_end){
+  if(!ctx || nranks<1 || rank<0 || rank>=nranks || cx_begin>=cx_end || cx_end>ctx->prm.domcells[0])return B2S_ERR_ARG;
+  if(ctx->ftcount)return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"floating bodies are single-GPU only in this round");
+  // mDBC would need the boundary ghosts' extrapolated rho AFTER the owner's mdbc pass (a second, boundary-only halo exchange)
+  if(ctx->prm.tboundary==B2S_BC_MDBC)return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"mDBC is single-GPU only in this round");
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  ctx->slab_on=true; ctx->slab_rank=rank; ctx->slab_nranks=nranks; ctx->slab_cxa=cx_begin; ctx->slab_cxb=cx_end;
+  const size_t nb=b2s_blocks(ctx->cap,S_BS);
+  if(!ctx->slab_counts){
+    ctx->slab_counts_len=2*(nb+1);
+    B2S_CUDA(ctx,cudaMalloc((void**)&ctx->slab_counts,ctx->slab_counts_len*4));
+    B2S_CUDA(ctx,cudaMalloc((void**)&ctx->slab_flags,ctx->cap));
+  }
+  // drop everything that does not belong to this slab and re-divide
+  k_slab_select<<<b2s_blocks(ctx->np_host,S_BS),S_BS,0,ctx->stream>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,cx_begin,cx_end); B2S_LAUNCHED(ctx);
+  ctx->bound_changed=true;
+  int r=b2s_celldiv_impl(ctx); if(r)return r;
+  k_slab_fix_counts<<<1,1,0,ctx->stream>>>(ctx->div); B2S_LAUNCHED(ctx);
+  return b2s_sync_info(ctx);
+}
+
+extern "C" int b2s_slab_record_bytes(b2s_ctx* ctx, int kind, uint32_t* bytes){
+  if(!ctx || !bytes || kind<0 || kind>1)return B2S_ERR_ARG;
+  *bytes=slab_layout(ctx,kind).bytes;
+  return B2S_OK;
+}
+
+extern "C" int b2s_slab_pack(b2s_ctx* ctx, int kind, void* dev_left, void* dev_right, uint32_t cap_records, uint32_t* nleft, uint32_t* nright){
+  if(!ctx || !ctx->slab_on || kind<0 || kind>1 || !nleft || !nright)return B2S_ERR_ARG;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  cudaStream_t s=ctx->stream;
+  const uint32_t n=ctx->np_host;
+  *nleft=*nright=0;
+  if(!n)return B2S_OK;
+  const uint32_t nb=b2s_blocks(n,S_BS);
+  const int hl=(ctx->slab_rank>0), hr=(ctx->slab_rank<ctx->slab_nranks-1);
+  B2S_CUDA(ctx,cudaMemsetAsync(ctx->slab_counts,0,size_t(2)*(nb+1)*4,s));
+  k_slab_flag<<<nb,S_BS,0,s>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,kind,hl,hr,ctx->slab_cxa,ctx->slab_cxb,uint32_t(ctx->cte.scelldiv),
+    ctx->slab_flags,ctx->slab_counts,nb); B2S_LAUNCHED(ctx);
+  b2s_launch_scan_excl(s,ctx->slab_counts,nb+1); B2S_LAUNCHED(ctx);
+  b2s_launch_scan_excl(s,ctx->slab_counts+nb+1,nb+1); B2S_LAUNCHED(ctx);
+  uint32_t tot[2]={0,0};
+  B2S_CUDA(ctx,cudaMemcpyAsync(&tot[0],ctx->slab_counts+nb,4,cudaMemcpyDeviceToHost,s));
+  B2S_CUDA(ctx,cudaMemcpyAsync(&tot[1],ctx->slab_counts+2*nb+1,4,cudaMemcpyDeviceToHost,s));
+  B2S_CUDA(ctx,cudaStreamSynchronize(s));
+  if(tot[0]>cap_records || tot[1]>cap_records)return b2s_fail(ctx,B2S_ERR_NOMEM,"slab exchange buffer too small: need %u/%u records, have %u",tot[0],tot[1],cap_records);
+  if((tot[0] && !dev_left) || (tot[1] && !dev_right))return B2S_ERR_ARG;
+  const SlabLayout l=slab_layout(ctx,kind);
+  k_slab_scatter<<<nb,S_BS,0,s>>>(ctx->div,ctx->slab_flags,ctx->slab_counts,nb,l,slab_arrays(ctx),kind,(char*)dev_left,(char*)dev_right,cap_records); B2S_LAUNCHED(ctx);
+  B2S_CUDA(ctx,cudaGetLastError());
+  *nleft=tot[0]; *nright=tot[1];
+  return B2S_OK;
+}
+
+extern "C" int b2s_slab_unpack(b2s_ctx* ctx, int kind, const void* dev_buf, uint32_t count){
+  if(!ctx || !ctx->slab_on || kind<0 || kind>1)return B2S_ERR_ARG;
+  if(!count)return B2S_OK;
+  if(!dev_buf)return B2S_ERR_ARG;
+  if(uint64_t(ctx->np_host)+count>ctx->cap)return b2s_fail(ctx,B2S_ERR_NOMEM,"particle capacity %u exceeded by %u incoming slab particles",ctx->cap,count);
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  const SlabLayout l=slab_layout(ctx,kind);
+  k_slab_unpack<<<b2s_blocks(count,S_BS),S_BS,0,ctx->stream>>>(ctx->div,(const char*)dev_buf,count,l,slab_arrays(ctx),kind,ctx->cte); B2S_LAUNCHED(ctx);
+  k_slab_unpack_commit<<<1,1,0,ctx->stream>>>(ctx->div,count); B2S_LAUNCHED(ctx);
+  ctx->np_host+=count; ctx->npb_host+=count;   // host mirrors are upper bounds until the next sync
+  ctx->bound_changed=true;
+  B2S_CUDA(ctx,cudaGetLastError());
+  return B2S_OK;
+}
+
+extern "C" int b2s_slab_dt_buffer(b2s_ctx* ctx, void** dev_u32x3){
+  if(!ctx || !dev_u32x3)return B2S_ERR_ARG;
+  *dev_u32x3=(void*)ctx->step;    // StepState starts with {velmax2_bits, acemax2_bits, viscdtmax_bits}: ordered uints, all-reduce with MAX
+  return B2S_OK;
+}

@@ -90,8 +90,8 @@ ABI_SYMBOLS = [
     "b2s_compute_symplectic_corr", "b2s_compute_step", "b2s_run_steps", "b2s_add_motion_rectsinu",
     "b2s_move_linear", "b2s_set_floatings", "b2s_get_floatings", "b2s_count_pairs", "b2s_time_interaction",
     "b2s_launch_count", "b2s_get_stream", "b2s_set_interaction_variant", "b2s_slab_config",
-    "b2s_slab_pack_halo", "b2s_slab_unpack_halo", "b2s_slab_pack_migrants", "b2s_slab_unpack_migrants",
-    "b2s_slab_dt_buffer", "b2s_slab_apply_dt",
+    "b2s_slab_record_bytes", "b2s_slab_pack", "b2s_slab_unpack", "b2s_slab_dt_buffer", "b2s_slab_forces",
+    "b2s_slab_apply_dt", "b2s_slab_integrate", "b2s_slab_step_end",
     "b2s_sim_load", "b2s_sim_free", "b2s_sim_ctx", "b2s_sim_params", "b2s_sim_save_part", "b2s_sim_run",
     "b2s_host_last_error",
 ]
@@ -144,6 +144,15 @@ def load_library():
     lib.b2s_launch_count.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
     lib.b2s_get_stream.argtypes = [vp, C.POINTER(vp)]
     lib.b2s_set_interaction_variant.argtypes = [vp, C.c_int]
+    lib.b2s_slab_config.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32]
+    lib.b2s_slab_record_bytes.argtypes = [vp, C.c_int, u32p]
+    lib.b2s_slab_pack.argtypes = [vp, C.c_int, vp, vp, C.c_uint32, u32p, u32p]
+    lib.b2s_slab_unpack.argtypes = [vp, C.c_int, vp, C.c_uint32]
+    lib.b2s_slab_dt_buffer.argtypes = [vp, C.POINTER(vp)]
+    lib.b2s_slab_forces.argtypes = [vp, C.c_int]
+    lib.b2s_slab_apply_dt.argtypes = [vp, C.c_int]
+    lib.b2s_slab_integrate.argtypes = [vp, C.c_int]
+    lib.b2s_slab_step_end.argtypes = [vp, C.POINTER(C.c_double)]
     lib.b2s_sim_load.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_uint32, C.POINTER(vp)]
     lib.b2s_sim_free.argtypes = [vp]
     lib.b2s_sim_ctx.argtypes = [vp, C.POINTER(vp)]
@@ -282,6 +291,47 @@ class Context:
 
     def set_variant(self, v: int):
         self._chk(self._lib.b2s_set_interaction_variant(self._h, v))
+
+    # ---- slab decomposition (include/b2s.h, "slab" section) ----
+    def slab_config(self, rank, nranks, cx_begin, cx_end):
+        self._chk(self._lib.b2s_slab_config(self._h, rank, nranks, cx_begin, cx_end))
+
+    def slab_record_bytes(self, kind):
+        b = C.c_uint32(0)
+        self._chk(self._lib.b2s_slab_record_bytes(self._h, kind, C.byref(b)))
+        return b.value
+
+    def slab_pack(self, kind, left_ptr, right_ptr, cap_records):
+        a, b = C.c_uint32(0), C.c_uint32(0)
+        self._chk(self._lib.b2s_slab_pack(self._h, kind, left_ptr, right_ptr, cap_records, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def slab_unpack(self, kind, ptr, count):
+        self._chk(self._lib.b2s_slab_unpack(self._h, kind, ptr, count))
+
+    def slab_dt_buffer(self):
+        p = C.c_void_p()
+        self._chk(self._lib.b2s_slab_dt_buffer(self._h, C.byref(p)))
+        return p.value
+
+    def slab_forces(self, interstep):
+        self._chk(self._lib.b2s_slab_forces(self._h, interstep))
+
+    def slab_apply_dt(self, interstep):
+        self._chk(self._lib.b2s_slab_apply_dt(self._h, interstep))
+
+    def slab_integrate(self, mode):
+        self._chk(self._lib.b2s_slab_integrate(self._h, mode))
+
+    def slab_step_end(self):
+        dt = C.c_double(0)
+        self._chk(self._lib.b2s_slab_step_end(self._h, C.byref(dt)))
+        return dt.value
+
+    def stream(self):
+        p = C.c_void_p()
+        self._chk(self._lib.b2s_get_stream(self._h, C.byref(p)))
+        return p.value
 
     def set_floatings(self, fts):
         arr = (Floating * len(fts))(*fts)

@@ -1,0 +1,264 @@
+"""Slab-decomposed multi-GPU driver: one process (rank) per GPU, NCCL send/recv over NVLink for halos and migrants,
+NCCL all-reduce(MAX) for the global dt.  No reference counterpart (DualSPHysics v5.4 is single-GPU).
+
+Design:
+  * the domain is cut at cell planes along x; cuts come from the prefix sum of particles per x cell plane so that every
+    rank owns ~Np/G particles (``compute_cuts``);
+  * per interaction: migrants (particles that left the slab, full state) then halos (one cell layer each side, appended
+    as CODE_PERIODIC ghosts) are packed into contiguous device buffers by the CUDA side (csrc/slab.cu) and exchanged with
+    the two neighbours; then the usual cell divide + interaction run on owned+ghost particles;
+  * the three dt maxima are all-reduced with MAX so that every rank integrates with the same dt.
+The transport is pluggable: ``TorchDistTransport`` (NCCL, one process per GPU) or ``LocalTransport`` (all ranks in one
+process on one GPU -- used by the tests to check the protocol against the single-context result).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import lib as L
+
+HALO, MIGRANT = 0, 1
+
+
+def compute_cuts(cellx: np.ndarray, ncells_x: int, nranks: int) -> list:
+    """Cut planes [c0=0, c1, ..., cN=ncells_x] balancing the particle count per slab (prefix sum over x cell planes)."""
+    hist = np.bincount(np.asarray(cellx, np.int64), minlength=ncells_x).astype(np.int64)
+    cum = np.cumsum(hist)
+    total = int(cum[-1])
+    cuts = [0]
+    for r in range(1, nranks):
+        target = total * r / nranks
+        c = int(np.searchsorted(cum, target, side="left")) + 1          # first cut with cum[c-1] >= target ...
+        if c >= 2 and abs(cum[c - 2] - target) < abs(cum[c - 1] - target):
+            c -= 1                                                        # ... or the plane before, whichever is nearer
+        c = max(c, cuts[-1] + 1)
+        c = min(c, ncells_x - (nranks - r))
+        cuts.append(c)
+    cuts.append(ncells_x)
+    return cuts
+
+
+class LocalTransport:
+    """All ranks live in this process (same device); exchanges are plain device copies.  For tests."""
+
+    def __init__(self, nranks):
+        self.nranks = nranks
+        self.mail = {}
+
+    def exchange_counts(self, rank, nleft, nright):
+        self.mail[("cnt", rank)] = (nleft, nright)
+
+    def counts_from(self, rank):
+        left = self.mail[("cnt", rank - 1)][1] if rank > 0 else 0
+        right = self.mail[("cnt", rank + 1)][0] if rank < self.nranks - 1 else 0
+        return left, right
+
+
+class SlabRank:
+    """One slab: a Simulation restricted to [cxa,cxb) + its exchange buffers (torch uint8 tensors on the device)."""
+
+    def __init__(self, casepath, options, rank, nranks, cuts, device=0, slack=0.25):
+        import torch
+        self.torch = torch
+        self.rank, self.nranks = rank, nranks
+        self.dev = torch.device("cuda", device)
+        self.sim = L.Simulation(casepath, options=options, device=device, extra_capacity=0)
+        self.ctx = self.sim.ctx
+        self.p = self.sim.params
+        if cuts is None:
+            cuts = cuts_from_ctx(self.ctx, self.p, nranks)
+        self.cuts = list(cuts)
+        self.cxa, self.cxb = int(cuts[rank]), int(cuts[rank + 1])
+        self.ctx.slab_config(rank, nranks, self.cxa, self.cxb)
+        info = self.ctx.info()
+        # buffer capacity: a generous bound on one cell layer of the cross-section + migrants
+        ncy, ncz = self.p.map_cells[1], self.p.map_cells[2]
+        percell = 64 * (2 if self.p.scelldiv == 1 else 1)
+        self.cap_records = int(max(4096, ncy * ncz * percell * self.p.scelldiv * (1 + slack)))
+        self.symplectic = (self.p.tstep == L.STEP_SYMPLECTIC)
+        maxbytes = 48 + 40 + 16 + 24 + 16
+        mk = lambda: torch.empty(self.cap_records * maxbytes, dtype=torch.uint8, device=self.dev)  # noqa: E731
+        self.send_l, self.send_r, self.recv_l, self.recv_r = mk(), mk(), mk(), mk()
+        self.owned0 = info.np
+
+    def pack(self, kind):
+        return self.ctx.slab_pack(kind, self.send_l.data_ptr(), self.send_r.data_ptr(), self.cap_records)
+
+    def unpack(self, kind, nl, nr):
+        if nl:
+            self.ctx.slab_unpack(kind, self.recv_l.data_ptr(), nl)
+        if nr:
+            self.ctx.slab_unpack(kind, self.recv_r.data_ptr(), nr)
+
+    def sync(self):
+        self.torch.cuda.synchronize(self.dev)
+
+    def dt_tensor(self):
+        """The three dt maxima as an int32 view over the ctx's device memory (zero-copy, via __cuda_array_interface__)."""
+        ptr = self.ctx.slab_dt_buffer()
+
+        class _W:
+            __cuda_array_interface__ = {"shape": (3,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+        return self.torch.as_tensor(_W(), device=self.dev)
+
+    def close(self):
+        self.sim.close()
+
+
+def _exchange_local(ranks, kind):
+    """Pack on every rank, copy buffers to the neighbours, unpack (single-process transport)."""
+    counts = [r.pack(kind) for r in ranks]
+    for r in ranks:
+        r.sync()
+    rb = ranks[0].ctx.slab_record_bytes(kind)
+    for i, r in enumerate(ranks):
+        nl = counts[i - 1][1] if i > 0 else 0
+        nr = counts[i + 1][0] if i < len(ranks) - 1 else 0
+        if nl:
+            r.recv_l[:nl * rb].copy_(ranks[i - 1].send_r[:nl * rb])
+        if nr:
+            r.recv_r[:nr * rb].copy_(ranks[i + 1].send_l[:nr * rb])
+        r.sync()
+        r.unpack(kind, nl, nr)
+    return counts
+
+
+def _exchange_dist(rank: SlabRank, kind, dist):
+    """Pack, exchange counts and payloads with the two neighbours over NCCL (batched isend/irecv), unpack."""
+    torch = rank.torch
+    nl_s, nr_s = rank.pack(kind)
+    rb = rank.ctx.slab_record_bytes(kind)
+    me, n = rank.rank, rank.nranks
+    cnt_send = torch.tensor([nl_s, nr_s], dtype=torch.int64, device=rank.dev)
+    cnt_recv = torch.zeros(2, dtype=torch.int64, device=rank.dev)
+    ops = []
+    if me > 0:
+        ops += [dist.P2POp(dist.isend, cnt_send[0:1], me - 1), dist.P2POp(dist.irecv, cnt_recv[0:1], me - 1)]
+    if me < n - 1:
+        ops += [dist.P2POp(dist.isend, cnt_send[1:2], me + 1), dist.P2POp(dist.irecv, cnt_recv[1:2], me + 1)]
+    rank.sync()   # the pack kernels run on the ctx stream; NCCL runs on torch's stream
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    nl_r, nr_r = int(cnt_recv[0].item()), int(cnt_recv[1].item())
+    ops = []
+    if me > 0:
+        if nl_s:
+            ops.append(dist.P2POp(dist.isend, rank.send_l[:nl_s * rb], me - 1))
+        if nl_r:
+            ops.append(dist.P2POp(dist.irecv, rank.recv_l[:nl_r * rb], me - 1))
+    if me < n - 1:
+        if nr_s:
+            ops.append(dist.P2POp(dist.isend, rank.send_r[:nr_s * rb], me + 1))
+        if nr_r:
+            ops.append(dist.P2POp(dist.irecv, rank.recv_r[:nr_r * rb], me + 1))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    rank.sync()
+    rank.unpack(kind, nl_r, nr_r)
+    return (nl_s, nr_s, nl_r, nr_r)
+
+
+class SlabSimulation:
+    """Drives N slabs through ComputeStep_Sym / ComputeStep_Ver (JSphGpuSingle.cpp:761-819) with the exchanges in between.
+
+    ``dist`` = torch.distributed (already initialised, NCCL): this process owns ONE rank.
+    ``dist`` = None: all ranks are created in this process on ``device`` (LocalTransport, for tests)."""
+
+    def __init__(self, casepath, options="", nranks=1, dist=None, device=0, cuts=None):
+        import torch
+        self.torch, self.dist = torch, dist
+        if dist is None:
+            self.ranks = [SlabRank(casepath, options, r, nranks, cuts, device=device) for r in range(nranks)]
+        else:
+            self.ranks = [SlabRank(casepath, options, dist.get_rank(), nranks, cuts, device=device)]
+        self.symplectic = self.ranks[0].symplectic
+        self.exchanged_bytes = 0
+        self.cuts = self.ranks[0].cuts
+        self._exchange(first=True)
+
+    # migrants then halos, then the cell divide (RunCellDivide with the ghosts in place)
+    def _exchange(self, first=False):
+        for kind in ((HALO,) if first else (MIGRANT, HALO)):
+            if self.dist is None:
+                c = _exchange_local(self.ranks, kind)
+                rb = self.ranks[0].ctx.slab_record_bytes(kind)
+                self.exchanged_bytes += sum(a + b for a, b in c) * rb
+            else:
+                c = _exchange_dist(self.ranks[0], kind, self.dist)
+                self.exchanged_bytes += (c[0] + c[1]) * self.ranks[0].ctx.slab_record_bytes(kind)
+        for r in self.ranks:
+            r.ctx.celldiv()
+
+    def _allreduce_dt(self):
+        if self.dist is None:
+            ts = [r.dt_tensor() for r in self.ranks]
+            for r in self.ranks:
+                r.sync()
+            m = self.torch.stack(ts).max(dim=0).values
+            for t in ts:
+                t.copy_(m)
+            for r in self.ranks:
+                r.sync()
+        else:
+            r = self.ranks[0]
+            r.sync()
+            t = r.dt_tensor()
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            r.sync()
+
+    def _interaction(self, interstep):
+        for r in self.ranks:
+            r.ctx.slab_forces(interstep)
+        self._allreduce_dt()
+        for r in self.ranks:
+            r.ctx.slab_apply_dt(interstep)
+
+    def step(self) -> float:
+        if self.symplectic:
+            self._interaction(L.INTER_SYMPREDICTOR)
+            for r in self.ranks:
+                r.ctx.slab_integrate(1)
+            self._exchange()
+            self._interaction(L.INTER_SYMCORRECTOR)
+            for r in self.ranks:
+                r.ctx.slab_integrate(2)
+        else:
+            self._interaction(L.INTER_VERLET)
+            for r in self.ranks:
+                r.ctx.slab_integrate(0)
+        dts = [r.ctx.slab_step_end() for r in self.ranks]
+        self._exchange()
+        return dts[0]
+
+    def gather_byid(self):
+        """Owned particles of the local ranks, sorted by id: (idp, pos, velrho)."""
+        ids, pos, vr = [], [], []
+        for r in self.ranks:
+            code = r.ctx.array("code")
+            own = (code & 0xe000) == 0
+            ids.append(r.ctx.array("idp")[own]); pos.append(r.ctx.array("pos")[own]); vr.append(r.ctx.array("velrho")[own])
+        ids, pos, vr = np.concatenate(ids), np.concatenate(pos), np.concatenate(vr)
+        o = np.argsort(ids, kind="stable")
+        return ids[o], pos[o], vr[o]
+
+    def owned_counts(self):
+        out = []
+        for r in self.ranks:
+            code = r.ctx.array("code")
+            out.append(int(((code & 0xe000) == 0).sum()))
+        return out
+
+    def close(self):
+        for r in self.ranks:
+            r.close()
+
+
+def cuts_from_ctx(ctx, params, nranks):
+    """Balanced cuts from the particles a freshly loaded context holds (every rank loads the same case, so every rank
+    derives the same cuts without communication).  Cell x comes from dcell (JDsDcellDef.h:38 DCEL_Cellx)."""
+    dcell = ctx.array("dcell")
+    dcc = int(params.domcellcode)
+    cellx = dcell[dcell != 0xFFFFFFFF] >> ((dcc >> 10) & 31)
+    return compute_cuts(cellx, int(params.domcells[0]), nranks)

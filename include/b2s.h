@@ -207,19 +207,31 @@ int b2s_get_stream(b2s_ctx* ctx, void** stream_out);
 int b2s_set_interaction_variant(b2s_ctx* ctx, int variant);
 
 /* ---- slab decomposition over several GPUs (no reference counterpart) ----------- */
-/* rank/nranks: position of this ctx in the slab chain along x.  The ctx keeps only particles with
- * cell-x in [cx_begin,cx_end) plus one halo layer of scelldiv cells on each inner face. */
+/* One ctx per GPU owns the particles whose cell-x lies in [cx_begin,cx_end) of the GLOBAL cell grid.  Before every
+ * interaction the owner ranks exchange (1) migrants = owned particles whose cell left the slab (full state) and
+ * (2) halos = owned particles within scelldiv cell layers of a cut (appended on the neighbour as CODE_PERIODIC
+ * ghosts, like the reference's periodic duplicates, JSphGpu_ker.cu:2267-2399).  The transport is the caller's
+ * (ncclSend/ncclRecv through torch.distributed, see dualsphysics_b200/slab.py); these entry points only pack into /
+ * unpack from contiguous DEVICE buffers, in deterministic particle order.
+ * kind: 0 = halo, 1 = migrants.  rank 0 has no left neighbour, rank nranks-1 no right neighbour. */
 int b2s_slab_config(b2s_ctx* ctx, int rank, int nranks, uint32_t cx_begin, uint32_t cx_end);
-/* Packs the particles lying in the halo layers next to the left/right cut into a contiguous device
- * buffer (device pointers returned) for an NCCL send; counts in particles. Record layout:
- * b2s_halo_rec (48 B). */
-int b2s_slab_pack_halo(b2s_ctx* ctx, int side, void** dev_buf, uint32_t* count);
-int b2s_slab_unpack_halo(b2s_ctx* ctx, int side, const void* dev_buf, uint32_t count);
-int b2s_slab_pack_migrants(b2s_ctx* ctx, int side, void** dev_buf, uint32_t* count);
-int b2s_slab_unpack_migrants(b2s_ctx* ctx, int side, const void* dev_buf, uint32_t count);
-/* dt maxima {acemax^2, viscdtmax, velmax^2} as device floats for ncclAllReduce(max), and apply. */
-int b2s_slab_dt_buffer(b2s_ctx* ctx, void** dev_float3);
-int b2s_slab_apply_dt(b2s_ctx* ctx);
+int b2s_slab_record_bytes(b2s_ctx* ctx, int kind, uint32_t* bytes);
+int b2s_slab_pack(b2s_ctx* ctx, int kind, void* dev_left, void* dev_right, uint32_t cap_records,
+                  uint32_t* nleft, uint32_t* nright);
+int b2s_slab_unpack(b2s_ctx* ctx, int kind, const void* dev_buf, uint32_t count);
+/* Device address of the three dt maxima {velmax^2, acemax^2, viscdtmax} stored as order-preserving uint32 bit
+ * patterns (non-negative floats): all-reduce them with MAX (ncclMax on int32) between b2s_slab_forces and
+ * b2s_slab_apply_dt so that every rank computes the same DtVariable (JSphGpu.cpp:1103-1147). */
+int b2s_slab_dt_buffer(b2s_ctx* ctx, void** dev_u32x3);
+/* The step of JSphGpuSingle::ComputeStep_Sym/Ver cut at the points where ranks must talk:
+ *   b2s_slab_forces     = MdbcBoundCorrection + Interaction_Forces without the dt computation
+ *   b2s_slab_apply_dt   = DtVariable from the (all-reduced) maxima; interstep as in b2s_interaction
+ *   b2s_slab_integrate  = mode 0 ComputeVerlet, 1 ComputeSymplecticPre, 2 ComputeSymplecticCorr with the device dt
+ *   b2s_slab_step_end   = SymplecticDtPre=min(dt_p,dt_c), TimeStep+=dt, Nstep++ ; returns dt (one host sync) */
+int b2s_slab_forces(b2s_ctx* ctx, int interstep);
+int b2s_slab_apply_dt(b2s_ctx* ctx, int interstep);
+int b2s_slab_integrate(b2s_ctx* ctx, int mode);
+int b2s_slab_step_end(b2s_ctx* ctx, double* dt_out);
 
 #ifdef __cplusplus
 }

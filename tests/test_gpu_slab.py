@@ -1,0 +1,60 @@
+"""Slab decomposition on ONE GPU: N contexts in one process exchange halos/migrants through plain device
+copies (dualsphysics_b200.slab.LocalTransport path) and must reproduce the single-context run.
+
+The pair sums of a particle next to a cut visit its neighbours in a different order (ghosts are appended before the
+stable sort), so floats agree to rounding, not bit for bit: pos 1e-7 m, vel/rho 2e-6 of max|field| after 10 steps (the
+same tolerances the single-GPU path holds against the reference).  Particle SETS (ids) and the dt sequence are checked too.
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+import dualsphysics_b200 as dsb
+from dualsphysics_b200 import slab
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("sym_art", 0.03, {}, "", 2),
+    ("sym_art_3slabs", 0.03, {}, "", 3),
+    ("sym_art_half", 0.03, {}, "-cellmode:half", 2),
+    ("ver_cubic", 0.03, {"StepAlgorithm": 1, "Kernel": 1, "DensityDT": 1}, "", 2),
+    ("sym_lamsps", 0.03, {"ViscoTreatment": 2, "Visco": 1e-6, "DensityDT": 3}, "", 2),
+]
+
+
+@pytest.mark.parametrize("name,dp,opts,options,nranks", CASES, ids=[c[0] for c in CASES])
+def test_slabs_match_single_context(name, dp, opts, options, nranks, tmp_path, built_lib):
+    H.write_case(tmp_path, dp=dp, params=opts)
+    case = str(tmp_path / "Case")
+    ref = dsb.Simulation(case, options=options)
+    ss = slab.SlabSimulation(case, options=options, nranks=nranks, dist=None)
+    assert len(ss.cuts) == nranks + 1 and all(b > a for a, b in zip(ss.cuts, ss.cuts[1:]))
+    n0 = ref.ctx.info().np
+    assert sum(ss.owned_counts()) == n0, "slabs do not partition the particle set"
+    nsteps = 10
+    for s in range(nsteps):
+        dt_ref = ref.ctx.compute_step()
+        dt = ss.step()
+        assert abs(dt - dt_ref) <= 2e-5 * dt_ref, (s, dt, dt_ref)
+    ids, pos, vr = ss.gather_byid()
+    rid = ref.ctx.array("idp"); o = np.argsort(rid, kind="stable")
+    rpos, rvr = ref.ctx.array("pos")[o], ref.ctx.array("velrho")[o]
+    assert np.array_equal(ids, rid[o]), "particle set differs from the single-context run"
+    epos = float(np.max(np.abs(pos - rpos)))
+    evr = H.rel_err(vr, rvr)
+    print(f"\n[slab {name} x{nranks}] cuts={ss.cuts} owned={ss.owned_counts()} pos_err={epos:.3e} velrho_err={evr:.3e} "
+          f"exchanged={ss.exchanged_bytes / nsteps / 1e3:.1f} kB/step")
+    assert epos < 1e-7 and evr < 2e-6
+    # load balance of the cuts: a whole cell plane is the granularity, so the densest plane bounds the imbalance
+    oc = np.array(ss.owned_counts(), np.float64)
+    p = ref.params
+    planes = np.bincount(ref.ctx.array("dcell") >> ((int(p.domcellcode) >> 10) & 31))
+    assert oc.max() <= oc.mean() + planes.max()
+    ss.close(); ref.close()
+
+
+def test_slab_unsupported_is_loud(tmp_path, built_lib):
+    H.write_case(tmp_path, dp=0.05, floating_box=(0.15, 0.25, 0.2, 0.1, 0.15, 0.1), floating_rel_density=0.5)
+    with pytest.raises(dsb.B2SError):
+        slab.SlabSimulation(str(tmp_path / "Case"), nranks=2, dist=None)
