@@ -27,7 +27,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "particle-steps/sec (whole box) at 1/2/4/8 B200; interaction-kernel roofline fraction"
 UNIT = "particle-steps/s"
-OPTIONS = "-symplectic -wendland -viscoart:0.1 -ddt:2 -ddtvalue:0.1 -dbc" + os.environ.get("B2S_BENCH_EXTRA_OPTS", "")
+OPTIONS = "-symplectic -wendland -viscoart:0.1 -ddt:2 -ddtvalue:0.1 -dbc -cellmode:half" + os.environ.get("B2S_BENCH_EXTRA_OPTS", "")
+# DRAM bytes of ONE launch of the fluid interaction kernel at the 10M-particle workload (profiles/r01_ncu_forces_gather_half.csv)
+NCU_TRAFFIC_BYTES = None
 NP_TARGET = int(os.environ.get("B2S_BENCH_NP", "10000000"))
 CPU_SAMPLE_NP = int(os.environ.get("B2S_BENCH_CPU_NP", "1000000"))
 # flop model of SURVEY 8(d): per checked pair 16 flop, per real pair (r<2h) 90 flop
@@ -44,12 +46,15 @@ def peaks():
     return 6650.0, 1965.0, "fallback"
 
 
-def make_case(np_target, tag):
+def make_case(np_target, tag, xscale=1):
+    """The dam-break block at ~np_target particles per unit of xscale (tank and column stretched along x for weak scaling)."""
     from dualsphysics_b200 import casegen
-    d = os.path.join(tempfile.gettempdir(), f"b2s_bench_{tag}_{np_target}")
-    if not os.path.exists(os.path.join(d, "Case.bi4")):
+    d = os.path.join(tempfile.gettempdir(), f"b2s_bench_{tag}_{np_target}_x{xscale}")
+    if not os.path.exists(os.path.join(d, "Case.done")):
         dp = casegen.dp_for_target(np_target)
-        casegen.write_case(d, "Case", casegen.DamBreakSpec(dp=dp, params={"TimeMax": 10.0}))
+        casegen.write_case(d, "Case", casegen.DamBreakSpec(dp=dp, tank=(1.6 * xscale, 0.67, 0.4), fluid=(0.4 * xscale, 0.67, 0.3),
+                                                           params={"TimeMax": 10.0}))
+        open(os.path.join(d, "Case.done"), "w").write("ok")
     return os.path.join(d, "Case")
 
 
@@ -125,7 +130,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--np", type=int, default=NP_TARGET)
-    ap.add_argument("--variant", type=int, default=int(os.environ.get("B2S_VARIANT", "-1")))
+    ap.add_argument("--variant", type=int, default=int(os.environ.get("B2S_VARIANT", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
@@ -154,8 +159,8 @@ def main():
 
     # ------------------------------------------------------------------ this repo's arm
     import torch
-    import numpy as np
     import dualsphysics_b200 as dsb
+    from dualsphysics_b200 import slab
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no fallback")
     dist = None
@@ -169,21 +174,35 @@ def main():
     torch.cuda.set_device(dev)
     hbm_gbs, sm_max_mhz, peak_src = peaks()
 
-    case = make_case(a.np, "gpu") if rank == 0 or True else None
-    sim = dsb.Simulation(case, options=OPTIONS, device=dev)
-    ctx = sim.ctx
-    if a.variant >= 0:
-        ctx.set_variant(a.variant)
+    # weak scaling: the block (tank and water column) is `world` times longer along x, ~a.np particles per GPU
+    if rank == 0:
+        case = make_case(a.np, "gpu", xscale=world)
+    if dist is not None:
+        dist.barrier()
+    case = make_case(a.np, "gpu", xscale=world)
+    ss = None
+    if world == 1:
+        sim = dsb.Simulation(case, options=OPTIONS, device=dev)
+        ctx = sim.ctx
     else:
-        try:
-            ctx.set_variant(1)
-            ctx.interaction(dsb.lib.INTER_SYMPREDICTOR)
-        except dsb.B2SError:
-            ctx.set_variant(0)
-    p = sim.params
+        ss = slab.SlabSimulation(case, options=OPTIONS, nranks=world, dist=dist, device=dev)
+        sim = ss.ranks[0].sim
+        ctx = ss.ranks[0].ctx
+    ctx.set_variant(a.variant)
     info0 = ctx.info()
-    np_total = info0.np
-    npf = info0.np - info0.npb
+    if ss is None:
+        np_total, npf = info0.np, info0.np - info0.npb
+    else:
+        code = ctx.array("code")
+        own = (code & 0xe000) == 0
+        np_total, npf = int(own.sum()), int((own & ((code & 0x1800) == 0x1800)).sum())
+
+    def run(n):
+        if ss is None:
+            ctx.run_steps(n)
+        else:
+            for _ in range(n):
+                ss.step()
 
     def barrier():
         if dist is not None:
@@ -191,74 +210,114 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up
-    ctx.run_steps(warmup)
-    # ---- timed steps: wall clock bracketed by barrier+synchronize, max over ranks
+    run(warmup)
+    # ---- timed steps: CUDA events on the stream the kernels are launched on (the ctx stream), bracketed by
+    #      barrier + synchronize; max over ranks.  Wall clock is taken too and must agree.
+    kstream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", dev))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(dev) if rank == 0 else None
     ctx.launch_count(reset=True)
+    if ss is not None:
+        ss.exchanged_bytes = 0
     barrier()
     t0 = time.perf_counter()
-    ctx.run_steps(a.steps)
+    ev0.record(kstream)
+    run(a.steps)
+    ev1.record(kstream)
     barrier()
-    secs = time.perf_counter() - t0
+    wall = time.perf_counter() - t0
+    secs = ev0.elapsed_time(ev1) * 1e-3
     launches = ctx.launch_count()
+    xbytes = ss.exchanged_bytes if ss is not None else 0
     if dist is not None:
-        t = torch.tensor([secs], device="cuda", dtype=torch.float64)
+        t = torch.tensor([secs, wall], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        secs = float(t.item())
-        cnt = torch.tensor([float(np_total), float(launches)], device="cuda", dtype=torch.float64)
+        secs, wall = float(t[0].item()), float(t[1].item())
+        cnt = torch.tensor([float(np_total), float(launches), float(xbytes)], device="cuda", dtype=torch.float64)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        np_all, launches_all = int(cnt[0].item()), int(cnt[1].item())
+        np_all, launches_all, xbytes_all = int(cnt[0].item()), int(cnt[1].item()), int(cnt[2].item())
+        allnp = [torch.zeros(1, device="cuda", dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allnp, torch.tensor([float(np_total)], device="cuda", dtype=torch.float64))
+        np_per_rank = [int(x.item()) for x in allnp]
     else:
-        np_all, launches_all = np_total, launches
+        np_all, launches_all, xbytes_all, np_per_rank = np_total, launches, 0, [np_total]
     value = np_all * a.steps / secs
     clocks = sampler.stop() if sampler else None
 
+    # ---- dominant kernel alone: CUDA events on the ctx stream (b2s_time_interaction), flop model from pair counts
+    ms_k = ctx.time_interaction(5)
+    chk, real = ctx.count_pairs()
+    # ---- e2e: host buffers in, host buffers out, every step (pinned memory; copies inside the timed region)
+    e2e = None
+    if not a.no_e2e:
+        import ctypes as C
+        n = ctx.info().np
+        cap = int(n * 1.3) + 4096
+        h_idp = torch.empty(cap, dtype=torch.int32).pin_memory()
+        h_code = torch.empty(cap, dtype=torch.int16).pin_memory()
+        h_pos = torch.empty(cap * 3, dtype=torch.float64).pin_memory()
+        h_vr = torch.empty(cap * 4, dtype=torch.float32).pin_memory()
+        lib = dsb.load_library()
+
+        def download():
+            cnt_ = C.c_uint32(0)
+            if ss is not None:
+                ss.host_roundtrip_begin()
+                assert ctx.info().np <= cap
+            r = lib.b2s_download_particles(ctx._h, C.byref(cnt_), h_idp.data_ptr(), h_code.data_ptr(), h_pos.data_ptr(), h_vr.data_ptr())
+            assert r == 0, r
+            return cnt_.value
+
+        def upload(n_):
+            ctx.upload_ptrs(n_, h_idp.data_ptr(), h_code.data_ptr(), h_pos.data_ptr(), h_vr.data_ptr())
+            if ss is not None:
+                ss.host_roundtrip_end()
+        if ss is not None:
+            ss.step(final_exchange=False)
+        n = download()
+        ksteps = max(2, min(a.steps, 5))
+        moved = 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            upload(n)
+            moved += n
+            if ss is None:
+                ctx.compute_step()
+            else:
+                ss.step(final_exchange=False)
+            n = download()
+        barrier()
+        se = time.perf_counter() - t0
+        tot = torch.tensor([float(moved), se], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            mx = tot.clone()
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            se = float(mx[1].item())
+        moved_all = int(tot[0].item())
+        e2e = {"value": moved_all / se, "unit": UNIT, "h2d_bytes_per_step": moved_all // ksteps * (4 + 2 + 24 + 16),
+               "d2h_bytes_per_step": moved_all // ksteps * (4 + 2 + 24 + 16), "steps": ksteps,
+               "note": "per step and per rank: b2s_upload_particles (pinned host -> device, incl. cell divide)"
+                       + ("" if ss is None else " + migrant/halo exchange") + " + one full step + b2s_download_particles (all owned particles)"}
+
     line = None
     if rank == 0:
-        # ---- dominant kernel alone: CUDA events on the ctx stream (b2s_time_interaction), flop model from pair counts
-        ms_k = ctx.time_interaction(5)
-        chk, real = ctx.count_pairs()
         flops = FLOP_CHK * chk + FLOP_REAL * real
         tf_ach = flops / (ms_k * 1e-3) / 1e12
         fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12      # 148 SMs x 128 lanes x 2 flop x max SM clock
         gbs_k = BYTES_INTER * npf / (ms_k * 1e-3) / 1e9
         gbs_step = BYTES_STEP * np_total / (secs / a.steps) / 1e9
-        roofline = {"kernel": "k_forces_fluid (fluid<-fluid+bound interaction)", "bound": "fp32", "achieved": tf_ach, "peak": fp32_peak,
-                    "unit": "TFLOP/s", "frac": tf_ach / fp32_peak, "traffic": None, "peak_source": "148 SM x 128 FP32 lanes x 2 x clocks.max.sm (non-tensor)",
+        roofline = {"kernel": "k_forces_fluid_gather (fluid<-fluid+bound interaction)", "bound": "fp32", "achieved": tf_ach, "peak": fp32_peak,
+                    "unit": "TFLOP/s", "frac": tf_ach / fp32_peak, "traffic": NCU_TRAFFIC_BYTES,
+                    "traffic_note": "dram__bytes_read.sum+dram__bytes_write.sum of one launch at this size from profiles/ (ncu --set full)",
+                    "peak_source": "148 SM x 128 FP32 lanes x 2 x clocks.max.sm (non-tensor FP32 issue; tensor cores do not apply to pairwise SPH)",
                     "ms_per_launch": ms_k, "pairs_checked": chk, "pairs_real": real, "flop_model": "16*checked + 90*real (SURVEY 8d)",
                     "share_of_step": 2 * ms_k / (secs / a.steps * 1e3),
                     "hbm": {"bound": "hbm", "achieved": gbs_k, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs_k / hbm_gbs,
                             "algorithmic_bytes_per_particle": BYTES_INTER, "peak_source": peak_src},
                     "hbm_whole_step": {"bound": "hbm", "achieved": gbs_step, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs_step / hbm_gbs,
                                        "algorithmic_bytes_per_particle_step": BYTES_STEP, "peak_source": peak_src}}
-        # ---- e2e: host buffers in, host buffers out, every step (pinned memory; copies inside the timed region)
-        e2e = None
-        if not a.no_e2e:
-            n = np_total
-            h_idp = torch.empty(n, dtype=torch.int32).pin_memory()
-            h_code = torch.empty(n, dtype=torch.int16).pin_memory()
-            h_pos = torch.empty(n * 3, dtype=torch.float64).pin_memory()
-            h_vr = torch.empty(n * 4, dtype=torch.float32).pin_memory()
-            lib = dsb.load_library()
-            import ctypes as C
-
-            def download():
-                cnt_ = C.c_uint32(0)
-                r = lib.b2s_download_particles(ctx._h, C.byref(cnt_), h_idp.data_ptr(), h_code.data_ptr(), h_pos.data_ptr(), h_vr.data_ptr())
-                assert r == 0, r
-                return cnt_.value
-            n = download()
-            ksteps = max(2, min(a.steps, 5))
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(ksteps):
-                ctx.upload_ptrs(n, h_idp.data_ptr(), h_code.data_ptr(), h_pos.data_ptr(), h_vr.data_ptr())
-                ctx.compute_step()
-                n = download()
-            torch.cuda.synchronize()
-            se = time.perf_counter() - t0
-            e2e = {"value": n * ksteps / se, "unit": UNIT, "h2d_bytes_per_step": n * (4 + 2 + 24 + 16), "d2h_bytes_per_step": n * (4 + 2 + 24 + 16),
-                   "steps": ksteps, "note": "per step: b2s_upload_particles (pinned host -> device, incl. first cell divide) + b2s_compute_step + b2s_download_particles"}
         # ---- CPU baseline: the reference's own CPU solver on this box's cores, bounded sample
         cpu = None
         if not a.no_cpu_baseline and world == 1:
@@ -272,12 +331,18 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warmup,
                 "ms_per_step": secs / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"synthetic 3D dam-break block (BASELINE configs[1]), {OPTIONS}, lattice start", "np_per_gpu": np_total,
-                           "np_total": np_all, "fluid_per_gpu": npf, "interaction_variant": ctx._lib and (a.variant if a.variant >= 0 else "auto"),
-                           "parallelism": "single GPU" if world == 1 else f"{world} independent slab replicas (halo exchange not built this round)",
-                           "l2_note": "working set ~2.3 GB per GPU >> 126 MB L2"},
+                "config": {"workload": f"synthetic 3D dam-break block (BASELINE configs[1]), {OPTIONS}, lattice start"
+                                       + ("" if world == 1 else f", block {world}x longer along x"),
+                           "np_per_gpu": np_per_rank, "np_total": np_all, "fluid_rank0": npf, "interaction_variant": a.variant,
+                           "parallelism": "single GPU" if world == 1 else f"{world} slabs along x, one rank per GPU; per interaction: migrants+halos over NCCL send/recv, dt by all-reduce(MAX)",
+                           "exchanged_bytes_per_step": xbytes_all // max(a.steps, 1),
+                           "l2_note": "inputs larger than L2: working set ~2.3 GB per GPU >> 126 MB L2",
+                           "timing": "CUDA events on the kernel stream, max over ranks", "wall_ms_per_step": wall / a.steps * 1e3},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks}
-    sim.close()
+    if ss is not None:
+        ss.close()
+    else:
+        sim.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

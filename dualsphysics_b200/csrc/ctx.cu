@@ -219,7 +219,10 @@ extern "C" int b2s_upload_particles(b2s_ctx* ctx, uint32_t np, const uint32_t* i
     }
   }
   // npb = bound particles = non-floating boundary (fixed+moving), they come first
-  const uint32_t npb=std::min(np,ctx->prm.casenpb);
+  // (found by bisection on the type bits: callers may upload a subset of the case, e.g. one slab, so CaseNpb is only a bound)
+  uint32_t npb=0;
+  { uint32_t lo=0,hi=np; while(lo<hi){ const uint32_t mid=lo+(hi-lo)/2; if(B2S_CODE_TYPE(code[mid])<B2S_CODE_TYPE_FLOATING)lo=mid+1; else hi=mid; } npb=lo; }
+  if(npb>ctx->prm.casenpb)return b2s_fail(ctx,B2S_ERR_ARG,"%u boundary particles uploaded but the case has %u",npb,ctx->prm.casenpb);
   int* derr=(int*)((char*)ctx->scratch+ctx->scratch_bytes-8);
   B2S_CUDA(ctx,cudaStreamSynchronize(s));
   B2S_CUDA(ctx,cudaMemsetAsync(derr,0,4,s));

@@ -42,7 +42,8 @@ struct b2s_sim {
   double casedp, caseh, caseb, caserhop0, casegamma, casemassb, casemassf;
   double caseposmin[3], caseposmax[3];
   unsigned np0;
-  b2s_sim():ctx(NULL),timemax(0),timepart(0),timepartnext(0),part(0),nstepsbreak(0),svallsteps(false),svposdouble(false),svdata(true),np0(0){ memset(&prm,0,sizeof(prm)); }
+  std::vector<uint32_t> slab_cuts; uint32_t slab_maxplane;   // slab loading (b2s_sim_load_slab)
+  b2s_sim():slab_maxplane(0),ctx(NULL),timemax(0),timepart(0),timepartnext(0),part(0),nstepsbreak(0),svallsteps(false),svposdouble(false),svdata(true),np0(0){ memset(&prm,0,sizeof(prm)); }
 };
 
 static std::string g_host_err;
@@ -244,7 +245,26 @@ static void load_case(b2s_sim* s,const std::string& options){
   }
 }
 
-static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capacity){
+// Balanced cut planes along x: prefix sum of the particles per x cell plane, every cut at the plane whose cumulative count
+// is nearest to r*Np/G (the same rule as dualsphysics_b200/slab.py compute_cuts; tests compare both).
+static std::vector<uint32_t> slab_compute_cuts(const std::vector<uint64_t>& hist,int nranks){
+  const uint32_t ncx=uint32_t(hist.size());
+  std::vector<uint64_t> cum(ncx); uint64_t t=0; for(uint32_t i=0;i<ncx;i++){ t+=hist[i]; cum[i]=t; }
+  std::vector<uint32_t> cuts; cuts.push_back(0);
+  for(int r=1;r<nranks;r++){
+    const double target=double(t)*r/nranks;
+    uint32_t i=0; while(i<ncx && double(cum[i])<target)i++;      // searchsorted(cum,target,'left')
+    uint32_t c=i+1;
+    if(c>=2 && c-1<ncx && fabs(double(cum[c-2])-target)<fabs(double(cum[c-1])-target))c--;
+    if(c<cuts.back()+1)c=cuts.back()+1;
+    if(c>ncx-uint32_t(nranks-r))c=ncx-uint32_t(nranks-r);
+    cuts.push_back(c);
+  }
+  cuts.push_back(ncx);
+  return cuts;
+}
+
+static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capacity,int slab_rank=0,int slab_nranks=0){
   b2s_params& p=s->prm;
   std::unique_ptr<Bi4Item> data=bi4_load(s->casepath+".bi4");
   if(data->name!="JPartDataBi4")throw std::runtime_error("Case.bi4: root item JPartDataBi4 not found");
@@ -321,7 +341,32 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   s->casemassb=data->get_double("MassBound",p.massbound); s->casemassf=data->get_double("MassFluid",p.massfluid);
   int r=b2s_config_finalize(&p);
   if(r)throw std::runtime_error(std::string("configuration failed: ")+b2s_error_string(r));
-  r=b2s_create(&p,device,np+extra_capacity,&s->ctx);
+  // slab loading: only the particles of [cuts[rank],cuts[rank+1]) reach the device; capacity is sized for the slab
+  unsigned npsel=np;
+  std::vector<uint32_t> sel_idp;
+  if(slab_nranks>0){
+    if(p.casenfloat)throw std::runtime_error("floating bodies are single-GPU only in this round");
+    if(p.tboundary==B2S_BC_MDBC)throw std::runtime_error("mDBC is single-GPU only in this round");
+    const uint32_t ncx=p.domcells[0];
+    if(uint32_t(slab_nranks)>ncx)throw std::runtime_error("more slabs than cell planes along x");
+    const double sc=double(p.scell);
+    std::vector<uint32_t> cx(np);
+    std::vector<uint64_t> hist(ncx,0);
+    for(unsigned i=0;i<np;i++){ const double d=(pos[size_t(i)*3]-p.domposmin[0])/sc; uint32_t c=(d<0? 0u: uint32_t(d)); if(c>=ncx)c=ncx-1; cx[i]=c; hist[c]++; }
+    s->slab_cuts=slab_compute_cuts(hist,slab_nranks);
+    s->slab_maxplane=uint32_t(*std::max_element(hist.begin(),hist.end()));
+    const uint32_t ca=s->slab_cuts[slab_rank], cb=s->slab_cuts[slab_rank+1];
+    unsigned w=0;
+    sel_idp.resize(np);
+    for(unsigned i=0;i<np;i++)if(cx[i]>=ca && cx[i]<cb){
+      sel_idp[w]=idp[i]; code[w]=code[i]; for(int k=0;k<3;k++)pos[size_t(w)*3+k]=pos[size_t(i)*3+k]; for(int k=0;k<4;k++)velrho[size_t(w)*4+k]=velrho[size_t(i)*4+k];
+      w++;
+    }
+    npsel=w; idp=sel_idp.data();
+    // room for: ghosts (scelldiv planes each side), migrants, and a 25% drift of the owned count before re-cutting
+    extra_capacity+=npsel/4+4u*unsigned(p.scelldiv)*s->slab_maxplane+4096u;
+  }
+  r=b2s_create(&p,device,npsel+extra_capacity,&s->ctx);
   if(r)throw std::runtime_error(std::string("b2s_create failed: ")+b2s_error_string(r));
   // floating bodies (JSph::InitFloatings subset, JSph.cpp:1190-1290)
   if(p.casenfloat){
@@ -357,9 +402,13 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
     for(auto& v:nor)v*=2.f;   // boundary->interface normals doubled to reach the ghost node (JSph.cpp:1417)
     norp=nor.data();
   }
-  r=b2s_upload_particles(s->ctx,np,idp,code.data(),pos.data(),velrho.data(),norp);
+  r=b2s_upload_particles(s->ctx,npsel,idp,code.data(),pos.data(),velrho.data(),norp);
   if(r)throw std::runtime_error(std::string("b2s_upload_particles failed: ")+b2s_last_error(s->ctx));
   s->np0=np;
+  if(slab_nranks>0){
+    r=b2s_slab_config(s->ctx,slab_rank,slab_nranks,s->slab_cuts[slab_rank],s->slab_cuts[slab_rank+1]);
+    if(r)throw std::runtime_error(std::string("b2s_slab_config failed: ")+b2s_last_error(s->ctx));
+  }
 }
 
 // ---- PART output (JSph::SavePartData / JPartDataBi4) ----------------------------------------------------
@@ -439,6 +488,30 @@ extern "C" int b2s_sim_load(const char* casepath,const char* dirout,const char* 
   }
   catch(const std::exception& e){ g_host_err=e.what(); if(s->ctx)b2s_destroy(s->ctx); delete s; return B2S_ERR_IO; }
   *out=s;
+  return B2S_OK;
+}
+// Slab loading for one rank of a multi-GPU run: every rank reads the same case, derives the same cuts from the particle
+// histogram along x, and uploads only its own slab (device capacity sized for the slab, not for the whole case).
+extern "C" int b2s_sim_load_slab(const char* casepath,const char* options,int device,int rank,int nranks,b2s_sim** out){
+  if(!casepath||!out||nranks<1||rank<0||rank>=nranks)return B2S_ERR_ARG;
+  *out=NULL;
+  b2s_sim* s=new b2s_sim();
+  try{
+    s->casepath=casepath;
+    if(s->casepath.size()>4 && lower(s->casepath.substr(s->casepath.size()-4))==".xml")s->casepath.resize(s->casepath.size()-4);
+    size_t sl=s->casepath.find_last_of('/');
+    s->casename=(sl==std::string::npos? s->casepath: s->casepath.substr(sl+1));
+    load_case(s,options? options: "");
+    load_particles_and_create(s,device,0,rank,nranks);
+  }
+  catch(const std::exception& e){ g_host_err=e.what(); if(s->ctx)b2s_destroy(s->ctx); delete s; return B2S_ERR_IO; }
+  *out=s;
+  return B2S_OK;
+}
+extern "C" int b2s_sim_slab_info(b2s_sim* s,uint32_t* cuts,uint32_t ncuts,uint32_t* max_plane_particles){
+  if(!s||s->slab_cuts.empty())return B2S_ERR_STATE;
+  if(cuts){ if(ncuts!=s->slab_cuts.size())return B2S_ERR_ARG; for(uint32_t i=0;i<ncuts;i++)cuts[i]=s->slab_cuts[i]; }
+  if(max_plane_particles)*max_plane_particles=s->slab_maxplane;
   return B2S_OK;
 }
 extern "C" int b2s_sim_free(b2s_sim* s){ if(!s)return B2S_OK; if(s->ctx)b2s_destroy(s->ctx); delete s; return B2S_OK; }

@@ -10,8 +10,8 @@
 // caller's: this file only packs/unpacks contiguous device buffers -- deterministic order (scan-based compaction).
 //
 // Record layout (little endian, 8-byte aligned): u32 idp | u16 code | u16 0 | f64 pos[3] | f32 velrho[4]   (48 B)
-//   migrants append: [f64 pospre[3] f32 velrhopre[4]] (Symplectic, predictor active) | [f32 velrhom1[4]] (Verlet)
-//   both append:     [f32 tau[6]] (Laminar+SPS) | [f32 boundnor[4]] (mDBC)
+//   migrants append: [f32 velrhopre[4] f64 pospre[3] pad8] (Symplectic, predictor active) | [f32 velrhom1[4]] (Verlet)
+//   both append:     [f32 boundnor[4]] (mDBC) | [f32 tau[6] pad8] (Laminar+SPS); records are multiples of 16 B
 #include "b2s_internal.h"
 
 #define S_BS 256
@@ -22,10 +22,11 @@ struct SlabLayout { uint32_t bytes, off_pre, off_m1, off_tau, off_nor; };
 
 static SlabLayout slab_layout(const b2s_ctx* ctx, int kind){
   SlabLayout l; l.bytes=48; l.off_pre=l.off_m1=l.off_tau=l.off_nor=0;
-  if(kind==1 && ctx->pre_active){ l.off_pre=l.bytes; l.bytes+=40; }
+  // every float4 field sits on a 16-byte boundary and the record size is a multiple of 16 (vector loads/stores)
+  if(kind==1 && ctx->pre_active){ l.off_pre=l.bytes; l.bytes+=48; }   // f32 velrhopre[4] | f64 pospre[3] | 8 B pad
   if(kind==1 && ctx->velrhom1){ l.off_m1=l.bytes; l.bytes+=16; }
-  if(ctx->spstau){ l.off_tau=l.bytes; l.bytes+=24; }
   if(ctx->boundnor){ l.off_nor=l.bytes; l.bytes+=16; }
+  if(ctx->spstau){ l.off_tau=l.bytes; l.bytes+=32; }                  // f32 tau[6] | 8 B pad
   return l;
 }
 
@@ -70,7 +71,7 @@ __device__ __forceinline__ void slab_write(char* rec, const SlabLayout& l, const
   double* d=reinterpret_cast<double*>(rec+8);
   const double2 xy=a.posxy[p]; d[0]=xy.x; d[1]=xy.y; d[2]=a.posz[p];
   *reinterpret_cast<float4*>(rec+32)=a.velrho[p];
-  if(l.off_pre){ double* q=reinterpret_cast<double*>(rec+l.off_pre); const double2 pxy=a.pre_xy[p]; q[0]=pxy.x; q[1]=pxy.y; q[2]=a.pre_z[p]; *reinterpret_cast<float4*>(rec+l.off_pre+24)=a.pre_v[p]; }
+  if(l.off_pre){ double* q=reinterpret_cast<double*>(rec+l.off_pre+16); const double2 pxy=a.pre_xy[p]; q[0]=pxy.x; q[1]=pxy.y; q[2]=a.pre_z[p]; *reinterpret_cast<float4*>(rec+l.off_pre)=a.pre_v[p]; }
   if(l.off_m1)*reinterpret_cast<float4*>(rec+l.off_m1)=a.m1[p];
   if(l.off_tau){ float2* t=reinterpret_cast<float2*>(rec+l.off_tau); const float2* s=reinterpret_cast<const float2*>(a.tau+size_t(p)*6); t[0]=s[0]; t[1]=s[1]; t[2]=s[2]; }
   if(l.off_nor)*reinterpret_cast<float4*>(rec+l.off_nor)=a.nor[p];
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(S_BS) k_slab_unpack(DivState* ds, const char* 
   a.idp[p]=id; a.code[p]=cod; a.posxy[p]=make_double2(d[0],d[1]); a.posz[p]=d[2];
   a.velrho[p]=*reinterpret_cast<const float4*>(rec+32);
   a.dcell[p]=B2S_DCEL_CELL(c.domcellcode,uint32_t((d[0]-c.domposmin[0])/c.scell_d),uint32_t((d[1]-c.domposmin[1])/c.scell_d),uint32_t((d[2]-c.domposmin[2])/c.scell_d));
-  if(l.off_pre){ const double* q=reinterpret_cast<const double*>(rec+l.off_pre); a.pre_xy[p]=make_double2(q[0],q[1]); a.pre_z[p]=q[2]; a.pre_v[p]=*reinterpret_cast<const float4*>(rec+l.off_pre+24); }
+  if(l.off_pre){ const double* q=reinterpret_cast<const double*>(rec+l.off_pre+16); a.pre_xy[p]=make_double2(q[0],q[1]); a.pre_z[p]=q[2]; a.pre_v[p]=*reinterpret_cast<const float4*>(rec+l.off_pre); }
   else if(a.pre_v){ a.pre_xy[p]=make_double2(d[0],d[1]); a.pre_z[p]=d[2]; a.pre_v[p]=*reinterpret_cast<const float4*>(rec+32); }
   if(l.off_m1)a.m1[p]=*reinterpret_cast<const float4*>(rec+l.off_m1);
   else if(a.m1)a.m1[p]=*reinterpret_cast<const float4*>(rec+32);

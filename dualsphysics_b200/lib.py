@@ -92,7 +92,7 @@ ABI_SYMBOLS = [
     "b2s_launch_count", "b2s_get_stream", "b2s_set_interaction_variant", "b2s_slab_config",
     "b2s_slab_record_bytes", "b2s_slab_pack", "b2s_slab_unpack", "b2s_slab_dt_buffer", "b2s_slab_forces",
     "b2s_slab_apply_dt", "b2s_slab_integrate", "b2s_slab_step_end",
-    "b2s_sim_load", "b2s_sim_free", "b2s_sim_ctx", "b2s_sim_params", "b2s_sim_save_part", "b2s_sim_run",
+    "b2s_sim_load", "b2s_sim_load_slab", "b2s_sim_slab_info", "b2s_sim_free", "b2s_sim_ctx", "b2s_sim_params", "b2s_sim_save_part", "b2s_sim_run",
     "b2s_host_last_error",
 ]
 
@@ -153,6 +153,8 @@ def load_library():
     lib.b2s_slab_apply_dt.argtypes = [vp, C.c_int]
     lib.b2s_slab_integrate.argtypes = [vp, C.c_int]
     lib.b2s_slab_step_end.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.b2s_sim_load_slab.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.b2s_sim_slab_info.argtypes = [vp, u32p, C.c_uint32, u32p]
     lib.b2s_sim_load.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_uint32, C.POINTER(vp)]
     lib.b2s_sim_free.argtypes = [vp]
     lib.b2s_sim_ctx.argtypes = [vp, C.POINTER(vp)]
@@ -347,11 +349,15 @@ class Simulation:
     """The C++ host driver: Case.xml + Case.bi4 in, Part_XXXX.bi4 out (JSphGpuSingle::Run-style)."""
 
     def __init__(self, casepath: str, dirout: str | None = None, options: str = "", device: int = -1,
-                 extra_capacity: int = 0):
+                 extra_capacity: int = 0, slab: tuple | None = None):
+        """slab=(rank, nranks): load only this rank's slab (b2s_sim_load_slab)."""
         self._lib = load_library()
         self._h = C.c_void_p()
-        r = self._lib.b2s_sim_load(casepath.encode(), (dirout or "").encode(), options.encode(), device,
-                                   extra_capacity, C.byref(self._h))
+        if slab is not None:
+            r = self._lib.b2s_sim_load_slab(casepath.encode(), options.encode(), device, slab[0], slab[1], C.byref(self._h))
+        else:
+            r = self._lib.b2s_sim_load(casepath.encode(), (dirout or "").encode(), options.encode(), device,
+                                       extra_capacity, C.byref(self._h))
         if r:
             raise B2SError(r, self._lib.b2s_host_last_error().decode())
         ch = C.c_void_p()
@@ -363,6 +369,14 @@ class Simulation:
         p = Params()
         self._lib.b2s_sim_params(self._h, C.byref(p))
         return p
+
+    def slab_info(self, nranks: int):
+        cuts = (C.c_uint32 * (nranks + 1))()
+        mp = C.c_uint32(0)
+        r = self._lib.b2s_sim_slab_info(self._h, cuts, nranks + 1, C.byref(mp))
+        if r:
+            raise B2SError(r, "b2s_sim_slab_info")
+        return list(cuts), mp.value
 
     def run(self, nsteps: int = 0):
         t, n = C.c_double(0), C.c_uint32(0)

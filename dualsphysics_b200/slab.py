@@ -57,29 +57,22 @@ class LocalTransport:
 class SlabRank:
     """One slab: a Simulation restricted to [cxa,cxb) + its exchange buffers (torch uint8 tensors on the device)."""
 
-    def __init__(self, casepath, options, rank, nranks, cuts, device=0, slack=0.25):
+    def __init__(self, casepath, options, rank, nranks, device=0):
         import torch
         self.torch = torch
         self.rank, self.nranks = rank, nranks
         self.dev = torch.device("cuda", device)
-        self.sim = L.Simulation(casepath, options=options, device=device, extra_capacity=0)
+        self.sim = L.Simulation(casepath, options=options, device=device, slab=(rank, nranks))   # uploads only this slab
         self.ctx = self.sim.ctx
         self.p = self.sim.params
-        if cuts is None:
-            cuts = cuts_from_ctx(self.ctx, self.p, nranks)
-        self.cuts = list(cuts)
-        self.cxa, self.cxb = int(cuts[rank]), int(cuts[rank + 1])
-        self.ctx.slab_config(rank, nranks, self.cxa, self.cxb)
-        info = self.ctx.info()
-        # buffer capacity: a generous bound on one cell layer of the cross-section + migrants
-        ncy, ncz = self.p.map_cells[1], self.p.map_cells[2]
-        percell = 64 * (2 if self.p.scelldiv == 1 else 1)
-        self.cap_records = int(max(4096, ncy * ncz * percell * self.p.scelldiv * (1 + slack)))
+        self.cuts, maxplane = self.sim.slab_info(nranks)
+        self.cxa, self.cxb = self.cuts[rank], self.cuts[rank + 1]
+        # exchange buffers: scelldiv cell planes of halo per side, or the migrants of one step (far fewer)
+        self.cap_records = int(2 * self.p.scelldiv * maxplane + 4096)
         self.symplectic = (self.p.tstep == L.STEP_SYMPLECTIC)
-        maxbytes = 48 + 40 + 16 + 24 + 16
+        maxbytes = 48 + 48 + 16 + 16 + 32     # largest record csrc/slab.cu can produce (the size varies with the step phase)
         mk = lambda: torch.empty(self.cap_records * maxbytes, dtype=torch.uint8, device=self.dev)  # noqa: E731
         self.send_l, self.send_r, self.recv_l, self.recv_r = mk(), mk(), mk(), mk()
-        self.owned0 = info.np
 
     def pack(self, kind):
         return self.ctx.slab_pack(kind, self.send_l.data_ptr(), self.send_r.data_ptr(), self.cap_records)
@@ -166,15 +159,16 @@ class SlabSimulation:
     ``dist`` = torch.distributed (already initialised, NCCL): this process owns ONE rank.
     ``dist`` = None: all ranks are created in this process on ``device`` (LocalTransport, for tests)."""
 
-    def __init__(self, casepath, options="", nranks=1, dist=None, device=0, cuts=None):
+    def __init__(self, casepath, options="", nranks=1, dist=None, device=0):
         import torch
         self.torch, self.dist = torch, dist
         if dist is None:
-            self.ranks = [SlabRank(casepath, options, r, nranks, cuts, device=device) for r in range(nranks)]
+            self.ranks = [SlabRank(casepath, options, r, nranks, device=device) for r in range(nranks)]
         else:
-            self.ranks = [SlabRank(casepath, options, dist.get_rank(), nranks, cuts, device=device)]
+            self.ranks = [SlabRank(casepath, options, dist.get_rank(), nranks, device=device)]
         self.symplectic = self.ranks[0].symplectic
         self.exchanged_bytes = 0
+        self.migrated = 0
         self.cuts = self.ranks[0].cuts
         self._exchange(first=True)
 
@@ -185,9 +179,13 @@ class SlabSimulation:
                 c = _exchange_local(self.ranks, kind)
                 rb = self.ranks[0].ctx.slab_record_bytes(kind)
                 self.exchanged_bytes += sum(a + b for a, b in c) * rb
+                if kind == MIGRANT:
+                    self.migrated += sum(a + b for a, b in c)
             else:
                 c = _exchange_dist(self.ranks[0], kind, self.dist)
                 self.exchanged_bytes += (c[0] + c[1]) * self.ranks[0].ctx.slab_record_bytes(kind)
+                if kind == MIGRANT:
+                    self.migrated += c[0] + c[1]
         for r in self.ranks:
             r.ctx.celldiv()
 
@@ -215,7 +213,7 @@ class SlabSimulation:
         for r in self.ranks:
             r.ctx.slab_apply_dt(interstep)
 
-    def step(self) -> float:
+    def step(self, final_exchange=True) -> float:
         if self.symplectic:
             self._interaction(L.INTER_SYMPREDICTOR)
             for r in self.ranks:
@@ -229,8 +227,19 @@ class SlabSimulation:
             for r in self.ranks:
                 r.ctx.slab_integrate(0)
         dts = [r.ctx.slab_step_end() for r in self.ranks]
-        self._exchange()
+        if final_exchange:
+            self._exchange()
         return dts[0]
+
+    def host_roundtrip_begin(self):
+        """After ``step(final_exchange=False)``: drop the ghosts (they were marked by the integrator) so that a download
+        returns exactly the particles this rank owns (would-be migrants included)."""
+        for r in self.ranks:
+            r.ctx.celldiv()
+
+    def host_roundtrip_end(self):
+        """After re-uploading the owned particles: move migrants, rebuild halos, divide."""
+        self._exchange()
 
     def gather_byid(self):
         """Owned particles of the local ranks, sorted by id: (idp, pos, velrho)."""

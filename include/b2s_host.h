@@ -17,6 +17,12 @@ typedef struct b2s_sim b2s_sim;
 /* casepath: path of the case without extension (".xml" accepted). dirout may be NULL/"" (no PART output). */
 int b2s_sim_load(const char* casepath, const char* dirout, const char* options, int device,
                  uint32_t extra_capacity, b2s_sim** out);
+/* One rank of a slab-decomposed multi-GPU run (no reference counterpart: DualSPHysics v5.4 is single-GPU).  Every rank
+ * reads the same case, derives the same balanced cut planes along x from the particle histogram, uploads ONLY its slab
+ * and calls b2s_slab_config.  Floating bodies and mDBC are rejected (single-GPU only). */
+int b2s_sim_load_slab(const char* casepath, const char* options, int device, int rank, int nranks, b2s_sim** out);
+/* cuts[nranks+1] (cell planes along x) and the particle count of the densest plane (sizes the exchange buffers). */
+int b2s_sim_slab_info(b2s_sim* sim, uint32_t* cuts, uint32_t ncuts, uint32_t* max_plane_particles);
 int b2s_sim_free(b2s_sim* sim);
 int b2s_sim_ctx(b2s_sim* sim, b2s_ctx** out);            /* borrowed: freed by b2s_sim_free */
 int b2s_sim_params(b2s_sim* sim, b2s_params* out);

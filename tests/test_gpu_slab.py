@@ -54,6 +54,33 @@ def test_slabs_match_single_context(name, dp, opts, options, nranks, tmp_path, b
     ss.close(); ref.close()
 
 
+@pytest.mark.parametrize("options", ["-symplectic", "-verlet", "-symplectic -viscolamsps:1e-6 -ddt:3"])
+def test_slab_migration(options, tmp_path, built_lib):
+    """Long enough for the collapsing column to push particles across the cuts: migrants carry the full integrator state
+    (predictor copies / Verlet m1 / SPS tau).  A migrant is appended at the end of its new cell, so pair sums are taken
+    in a different order than in the single-context run and rounding differences grow with the steps: the bound here is
+    1e-3 of max|v| / 1e-5 m (dp/4000) after 400 steps, not the 10-step tolerance (measured on B200: Symplectic 3e-7 m and
+    4e-7, Verlet 1.2e-6 m and 1.2e-5 -- Verlet damps perturbations less)."""
+    H.write_case(tmp_path, dp=0.04)
+    case = str(tmp_path / "Case")
+    options += " -cellmode:half"
+    ref = dsb.Simulation(case, options=options)
+    ss = slab.SlabSimulation(case, options=options, nranks=3, dist=None)
+    nsteps = 400
+    for s in range(nsteps):
+        dt_ref, dt = ref.ctx.compute_step(), ss.step()
+        assert abs(dt - dt_ref) <= 1e-3 * dt_ref, (s, dt, dt_ref)
+    ids, pos, vr = ss.gather_byid()
+    rid = ref.ctx.array("idp"); o = np.argsort(rid, kind="stable")
+    assert np.array_equal(ids, rid[o]), "particles lost or duplicated by the migration"
+    epos = float(np.max(np.abs(pos - ref.ctx.array("pos")[o])))
+    evr = H.rel_err(vr, ref.ctx.array("velrho")[o])
+    print(f"\n[slab migration {options}] migrated={ss.migrated} owned={ss.owned_counts()} pos_err={epos:.3e} velrho_err={evr:.3e}")
+    assert ss.migrated > 0, "the case did not exercise migration"
+    assert epos < 1e-5 and evr < 1e-3
+    ss.close(); ref.close()
+
+
 def test_slab_unsupported_is_loud(tmp_path, built_lib):
     H.write_case(tmp_path, dp=0.05, floating_box=(0.15, 0.25, 0.2, 0.1, 0.15, 0.1), floating_rel_density=0.5)
     with pytest.raises(dsb.B2SError):
