@@ -50,6 +50,7 @@ struct DevCte {
   float cteb, gamma, ovgamma, rhopzero, ovrhopzero, cs0, eta2, massf, massb;
   float ddtkh, ddtgz, spssmag, spsblin;
   float scell, movlimit, rhopoutmin, rhopoutmax;
+  float scell_blk;                 // scell*2^B2S_XBLK: x origin step of posp (see b2s_posp_x)
   float visco_f, visco_b;          // Visco and Visco*ViscoBoundFactor (JSphGpuSingle.cpp:609)
   float gravity[3];
   float ddt_c1, ddt_c2, ddt_c3;    // series coefficients of (1+x)^(1/gamma)-1
@@ -139,8 +140,7 @@ struct b2s_ctx {
   std::vector<Motion> motions;
   // slab decomposition (slab.cu)
   bool slab_on; int slab_rank, slab_nranks; uint32_t slab_cxa, slab_cxb; uint32_t* slab_counts; uint8_t* slab_flags; size_t slab_counts_len;
-  // tile interaction variant (forces_tile.cu)
-  uint32_t* tile_seglist; uint32_t* tile_nseg; uint32_t tile_nseg_max; bool tile_seglist_valid; bool tile_attr_set[2][2][4][4];
+  bool defer_attr_set;   // forces_defer.cu: dynamic shared memory opt-in done
   // scratch for byid download
   void* scratch; size_t scratch_bytes;
 };
@@ -151,7 +151,13 @@ int  b2s_fail(b2s_ctx* ctx, int code, const char* fmt, ...);
 #define B2S_LAUNCHED(ctx) do{ (ctx)->launches++; }while(0)
 static inline unsigned b2s_blocks(size_t n, unsigned bs){ return (unsigned)((n+bs-1)/bs); }
 
+// posp frame: y,z relative to the origin of the particle's own cell; x relative to the origin of its BLOCK of 2^B2S_XBLK
+// cells along x (absolute domain cells).  A whole row of neighbour cells [cx-d,cx+d] then needs at most two x offsets,
+// so the interaction kernels walk a row as ONE index range instead of one range per cell.  Precision: FP32 of a length
+// < 8*scell, i.e. the same order as the reference's PosCell frame (JSphGpuSimple_ker.cu:46-57).
+#define B2S_XBLK 3
 #ifdef __CUDACC__
+__device__ __forceinline__ float b2s_offx(const DevCte& c,int cx1_abs,int cx2_abs){ return c.scell_blk*float((cx1_abs>>B2S_XBLK)-(cx2_abs>>B2S_XBLK)); }
 __device__ __forceinline__ float b2s_press(float rho, const DevCte& c){
   // Tait EOS as the CPU path evaluates it (FunSphEos.h:37-39): cteb*(powf(rho/rho0,gamma)-1).
   // gamma==7: exact product chain in double, rounded once (== correctly rounded powf to <1ulp).

@@ -311,10 +311,10 @@ __global__ void __launch_bounds__(DIV_BS) k_reorder(const DivState* __restrict__
     }
     if(a.nor_s)a.nor_d[p]=a.nor_s[s];
     if(p<ds->np){
-      // position relative to the origin of the particle's own cell (PosCell idea, JSphGpuSimple_ker.cu:46-57)
+      // position relative to the origin of the particle's own cell (x: of its block of cells) (PosCell idea, JSphGpuSimple_ker.cu:46-57)
       const uint32_t cx=B2S_DCEL_CELLX(cte.domcellcode,dc), cy=B2S_DCEL_CELLY(cte.domcellcode,dc), cz=B2S_DCEL_CELLZ(cte.domcellcode,dc);
       float4 pp;
-      pp.x=float((xy.x-cte.domposmin[0])-cte.scell_d*double(cx));
+      pp.x=float((xy.x-cte.domposmin[0])-cte.scell_d*double((cx>>B2S_XBLK)<<B2S_XBLK));   // block-relative x (b2s_internal.h)
       pp.y=float((xy.y-cte.domposmin[1])-cte.scell_d*double(cy));
       pp.z=float((z   -cte.domposmin[2])-cte.scell_d*double(cz));
       pp.w=b2s_press(vr.w,cte);
@@ -392,7 +392,6 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   if(ctx->spstau)std::swap(ctx->spstau,ctx->spstau_alt);
   if(ctx->boundnor)std::swap(ctx->boundnor,ctx->boundnor_alt);
   ctx->bound_changed=false;
-  ctx->tile_seglist_valid=false;
   B2S_CUDA(ctx,cudaGetLastError());
   return B2S_OK;
 }

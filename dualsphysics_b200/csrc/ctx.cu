@@ -36,7 +36,7 @@ static void make_devcte(const b2s_params& p, DevCte& c){
   // (1+x)^a - 1 = a x + a(a-1)/2 x^2 + a(a-1)(a-2)/6 x^3,  a = 1/gamma   (DDT2 hydrostatic term)
   const double a=1.0/double(p.gamma);
   c.ddt_c1=float(a); c.ddt_c2=float(a*(a-1.)/2.); c.ddt_c3=float(a*(a-1.)*(a-2.)/6.);
-  c.scell_d=double(p.scell);
+  c.scell_d=double(p.scell); c.scell_blk=p.scell*float(1<<B2S_XBLK);
   c.cs0_d=p.cs0; c.kernelh_d=double(p.kernelh); c.cfl=p.cflnumber; c.dtmin=p.dtmin;
   c.domcellcode=p.domcellcode; c.scelldiv=p.scelldiv; c.tkernel=p.tkernel; c.tvisco=p.tvisco; c.tdensity=p.tdensity;
   c.tboundary=p.tboundary; c.tstep=p.tstep; c.use_floating=p.use_floating; c.dt_allparticles=p.dt_allparticles;
@@ -72,7 +72,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   ctx->launches=0; ctx->variant=0; ctx->pre_active=false; ctx->bound_changed=true; ctx->ftcount=0;
   ctx->verletstep=0;
   ctx->slab_on=false; ctx->slab_rank=0; ctx->slab_nranks=1; ctx->slab_cxa=0; ctx->slab_cxb=0; ctx->slab_counts=NULL; ctx->slab_flags=NULL; ctx->slab_counts_len=0;
-  ctx->tile_seglist=NULL; ctx->tile_nseg=NULL; ctx->tile_nseg_max=0; ctx->tile_seglist_valid=false; memset(ctx->tile_attr_set,0,sizeof(ctx->tile_attr_set));
+  ctx->defer_attr_set=false;
   ctx->ft_massp_dev=NULL; ctx->ft_sums_dev=NULL; ctx->ft_sums_h=NULL; ctx->ft_dev=NULL; ctx->scratch=NULL; ctx->scratch_bytes=0;
   ctx->pospre_xy=ctx->pospre_xy_alt=NULL; ctx->pospre_z=ctx->pospre_z_alt=NULL; ctx->velrhopre=ctx->velrhopre_alt=NULL;
   ctx->velrhom1=ctx->velrhom1_alt=NULL; ctx->spstau=ctx->spstau_alt=ctx->spstau_new=NULL; ctx->boundnor=ctx->boundnor_alt=NULL;
@@ -126,7 +126,7 @@ extern "C" int b2s_destroy(b2s_ctx* ctx){
   cudaFree(ctx->cellpart); cudaFree(ctx->sortpart); cudaFree(ctx->cellpart_alt); cudaFree(ctx->sortpart_alt);
   cudaFree(ctx->begincell); cudaFree(ctx->radix_counts); cudaFree(ctx->ridp);
   cudaFree(ctx->div); cudaFree(ctx->step);
-  cudaFree(ctx->tile_seglist); cudaFree(ctx->tile_nseg); cudaFree(ctx->slab_counts); cudaFree(ctx->slab_flags);
+  cudaFree(ctx->slab_counts); cudaFree(ctx->slab_flags);
   cudaFree(ctx->ft_massp_dev); cudaFree(ctx->ft_sums_dev); cudaFree(ctx->ft_dev); cudaFree(ctx->scratch);
   if(ctx->ft_sums_h)cudaFreeHost(ctx->ft_sums_h);
   if(ctx->div_h)cudaFreeHost(ctx->div_h);
@@ -140,7 +140,7 @@ extern "C" const char* b2s_last_error(const b2s_ctx* ctx){ return ctx? ctx->err.
 extern "C" int b2s_get_params(const b2s_ctx* ctx, b2s_params* out){ if(!ctx||!out)return B2S_ERR_ARG; *out=ctx->prm; return B2S_OK; }
 extern "C" int b2s_get_stream(b2s_ctx* ctx, void** s){ if(!ctx||!s)return B2S_ERR_ARG; *s=(void*)ctx->stream; return B2S_OK; }
 extern "C" int b2s_launch_count(b2s_ctx* ctx, uint64_t* l, int reset){ if(!ctx)return B2S_ERR_ARG; if(l)*l=ctx->launches; if(reset)ctx->launches=0; return B2S_OK; }
-extern "C" int b2s_set_interaction_variant(b2s_ctx* ctx, int v){ if(!ctx||v<0||v>2)return B2S_ERR_ARG; ctx->variant=v; return B2S_OK; }
+extern "C" int b2s_set_interaction_variant(b2s_ctx* ctx, int v){ if(!ctx||(v!=0&&v!=3))return B2S_ERR_ARG; ctx->variant=v; return B2S_OK; }
 
 // Copies DivState+StepState to pinned memory, synchronises, refreshes the host mirrors and checks device flags.
 int b2s_sync_info(b2s_ctx* ctx){

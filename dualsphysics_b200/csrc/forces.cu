@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(F_BS) k_forces_fluid_gather(ForcesArgs g, cons
       taup1[0]=t0.x; taup1[1]=t0.y; taup1[2]=t1.x; taup1[3]=t1.y; taup1[4]=t2.x; taup1[5]=t2.y;
     }
     const CellRange r=cell_range(g.dcell[p1],c,ds);
-    const int ncx=int(ds->ncx), nsheet=int(ds->nsheet);
+    const int ncx=int(ds->ncx), nsheet=int(ds->nsheet), cmx=int(ds->cellmin[0]);
+    const float xin=pp1.x-c.scell*float((r.cx+cmx)&((1<<B2S_XBLK)-1));   // x inside the own cell (row_trim only)
     PairAcc af={0,0,0,0,0,0,0,0,0,0,0,0};
     PairAcc ab={0,0,0,0,0,0,0,0,0,0,0,0};
     if(FLOATING && ftp1 && TDENS!=B2S_DDT_NONE){ af.delta=FLT_MAX; ab.delta=FLT_MAX; }
@@ -51,9 +52,11 @@ __global__ void __launch_bounds__(F_BS) k_forces_fluid_gather(ForcesArgs g, cons
       for(int z=r.zini;z<r.zfin;z++)for(int y=r.yini;y<r.yfin;y++){
         const int row=y*ncx+z*nsheet;
         const float offy=c.scell*float(r.cy-y), offz=c.scell*float(r.cz-z);
-        for(int x=r.xini;x<r.xfin;x++){
+        int xa,xb;
+        if(!row_trim(c,r,xin,FADD(pp1.y,offy),FADD(pp1.z,offz),xa,xb))continue;
+        for(int x=xa;x<xb;x++){
           const uint32_t pini=beg[row+x], pfin=beg[row+x+1];
-          const float offx=c.scell*float(r.cx-x);
+          const float offx=b2s_offx(c,r.cx+cmx,x+cmx);
           for(uint32_t p2=pini;p2<pfin;p2++){
             const float4 pp2=g.posp[p2];
             const float drx=b2s_dr(pp1.x,pp2.x,offx), dry=b2s_dr(pp1.y,pp2.y,offy), drz=b2s_dr(pp1.z,pp2.z,offz);
@@ -73,9 +76,11 @@ __global__ void __launch_bounds__(F_BS) k_forces_fluid_gather(ForcesArgs g, cons
       for(int z=r.zini;z<r.zfin;z++)for(int y=r.yini;y<r.yfin;y++){
         const int row=y*ncx+z*nsheet;
         const float offy=c.scell*float(r.cy-y), offz=c.scell*float(r.cz-z);
-        for(int x=r.xini;x<r.xfin;x++){
+        int xa,xb;
+        if(!row_trim(c,r,xin,FADD(pp1.y,offy),FADD(pp1.z,offz),xa,xb))continue;
+        for(int x=xa;x<xb;x++){
           const uint32_t pini=beg[row+x], pfin=beg[row+x+1];
-          const float offx=c.scell*float(r.cx-x);
+          const float offx=b2s_offx(c,r.cx+cmx,x+cmx);
           for(uint32_t p2=pini;p2<pfin;p2++){
             const float4 pp2=g.posp[p2];
             const float drx=b2s_dr(pp1.x,pp2.x,offx), dry=b2s_dr(pp1.y,pp2.y,offy), drz=b2s_dr(pp1.z,pp2.z,offz);
@@ -115,14 +120,14 @@ __global__ void __launch_bounds__(F_BS) k_forces_bound(ForcesArgs g, const __gri
       const float4 pp1=g.posp[p1];
       const float4 velrhop1=g.velrho[p1];
       const CellRange r=cell_range(g.dcell[p1],c,ds);
-      const int ncx=int(ds->ncx), nsheet=int(ds->nsheet);
+      const int ncx=int(ds->ncx), nsheet=int(ds->nsheet), cmx=int(ds->cellmin[0]);
       const uint32_t* beg=g.beg+ds->box_fluid;
       for(int z=r.zini;z<r.zfin;z++)for(int y=r.yini;y<r.yfin;y++){
         const int row=y*ncx+z*nsheet;
         const float offy=c.scell*float(r.cy-y), offz=c.scell*float(r.cz-z);
         for(int x=r.xini;x<r.xfin;x++){
           const uint32_t pini=beg[row+x], pfin=beg[row+x+1];
-          const float offx=c.scell*float(r.cx-x);
+          const float offx=b2s_offx(c,r.cx+cmx,x+cmx);
           for(uint32_t p2=pini;p2<pfin;p2++){
             const float4 pp2=g.posp[p2];
             const float drx=b2s_dr(pp1.x,pp2.x,offx), dry=b2s_dr(pp1.y,pp2.y,offy), drz=b2s_dr(pp1.z,pp2.z,offz);
@@ -194,8 +199,7 @@ fluid_kernel_t b2s_pick_fluid_gather(const DevCte& c){
   return c.tkernel==B2S_KERNEL_WENDLAND? pick_visco<B2S_KERNEL_WENDLAND>(c.tvisco,c.tdensity,ft): pick_visco<B2S_KERNEL_CUBIC>(c.tvisco,c.tdensity,ft);
 }
 
-int b2s_forces_tile_launch(b2s_ctx* ctx, const ForcesArgs& g);   // forces_tile.cu
-int b2s_forces_queue_launch(b2s_ctx* ctx, const ForcesArgs& g);  // forces_queue.cu
+int b2s_forces_defer_launch(b2s_ctx* ctx, const ForcesArgs& g);  // forces_defer.cu
 
 int b2s_forces_fluid_only(b2s_ctx* ctx){
   ForcesArgs g;
@@ -203,8 +207,7 @@ int b2s_forces_fluid_only(b2s_ctx* ctx){
   g.posp=ctx->posp; g.velrho=ctx->cur.velrho; g.tau=ctx->spstau; g.tau_new=ctx->spstau_new; g.ftomassp=ctx->ft_massp_dev; g.acear=ctx->acear;
   const uint32_t npf=(ctx->np_host>ctx->npb_host? ctx->np_host-ctx->npb_host: 0u);
   if(!npf)return B2S_OK;
-  if(ctx->variant==1)return b2s_forces_tile_launch(ctx,g);
-  if(ctx->variant==2)return b2s_forces_queue_launch(ctx,g);
+  if(ctx->variant==3 && ctx->np_host<(1u<<26))return b2s_forces_defer_launch(ctx,g);   // queue entries hold 26-bit indices
   fluid_kernel_t k=b2s_pick_fluid_gather(ctx->cte);
   k<<<b2s_blocks(npf,F_BS),F_BS,0,ctx->stream>>>(g,ctx->cte); B2S_LAUNCHED(ctx);
   return B2S_OK;

@@ -61,7 +61,8 @@ struct PairAcc {
 #define FFMA(a,b,c) __fmaf_rn((a),(b),(c))
 __device__ __forceinline__ float b2s_dot3(float ax,float ay,float az,float bx,float by,float bz){ return FFMA(az,bz,FFMA(ay,by,FMUL(ax,bx))); }
 __device__ __forceinline__ float b2s_rr2(float dx,float dy,float dz){ return FFMA(dz,dz,FFMA(dy,dy,FMUL(dx,dx))); }
-__device__ __forceinline__ float b2s_dr(float a,float b,float off){ return FADD(FSUB(a,b),off); }
+// dr=(a+off)-b: a+off only depends on the target and on the neighbour row, so every kernel hoists it out of its pair loop
+__device__ __forceinline__ float b2s_dr(float a,float b,float off){ return FSUB(FADD(a,off),b); }
 
 // One fluid/floating particle p1 against one neighbour p2 (JSphCpu.cpp:822-1041).
 template<int TKER,int TVISCO,int TDENS,bool FLOATING,bool BOUNDP2>
@@ -166,6 +167,20 @@ __device__ __forceinline__ CellRange cell_range(uint32_t dcell,const DevCte& c,c
   return r;
 }
 
+// Trims a row of neighbour cells (fixed y,z) to the cells [xa,xb) the kernel sphere of the target can reach.
+// sy,sz = target y,z in the frame of the row's cells (pp1.y+offy): a neighbour there has y in [0,scell), so its distance
+// in y is at least max(0,sy-scell,-sy), same in z; what is left of (2h)^2 bounds |dx|.  The 2e-4 margins keep the trim
+// conservative: it only drops cells whose particles would all fail rr2<=4h^2, so results do not depend on it.
+// xin = target x inside its own cell.  Returns false when the whole row is out of reach.
+__device__ __forceinline__ bool row_trim(const DevCte& c,const CellRange& r,float xin,float sy,float sz,int& xa,int& xb){
+  const float dy=fmaxf(0.f,fmaxf(sy-c.scell,-sy)), dz=fmaxf(0.f,fmaxf(sz-c.scell,-sz));
+  const float xh2=c.kernelsize2*1.0002f-dy*dy-dz*dz;
+  if(xh2<=0.f)return false;
+  const float xh=sqrtf(xh2)+c.scell*1e-4f, ovs=1.0f/c.scell;
+  xa=max(r.xini,r.cx+int(floorf((xin-xh)*ovs)));
+  xb=min(r.xfin,r.cx+int(floorf((xin+xh)*ovs))+1);
+  return xa<xb;
+}
 
 // Store of one fluid/floating particle after both passes + SPS tau + the values for the fused maxima.
 // (JSphCpu.cpp:1086-1102 fluid pass then bound pass; JSphGpu_ker.cu:939-950.)

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(M_BS) k_mdbc_vel0(const DivState* __restrict__
   const int yini=cy-(cy<d? cy: d), yfin=cy+(ncy-cy-1<d? ncy-cy-1: d)+1;
   const int zini=cz-(cz<d? cz: d), zfin=cz+(ncz-cz-1<d? ncz-cz-1: d)+1;
   //-Ghost position relative to its own cell origin (same frame as posp).
-  const float grx=float((gx-c.domposmin[0])-c.scell_d*double(gcx));
+  const float grx=float((gx-c.domposmin[0])-c.scell_d*double((gcx>>B2S_XBLK)<<B2S_XBLK));
   const float gry=float((gy-c.domposmin[1])-c.scell_d*double(gcy));
   const float grz=float((gz-c.domposmin[2])-c.scell_d*double(gcz));
   float rhop1=0.f, grdx=0.f, grdy=0.f, grdz=0.f;
@@ -67,10 +67,10 @@ __global__ void __launch_bounds__(M_BS) k_mdbc_vel0(const DivState* __restrict__
     const float offy=c.scell*float(cy-y), offz=c.scell*float(cz-z);
     for(int x=xini;x<xfin;x++){
       const uint32_t pini=beg[row+x], pfin=beg[row+x+1];
-      const float offx=c.scell*float(cx-x);
+      const float offx=b2s_offx(c,gcx,x+int(ds->cellmin[0]));
       for(uint32_t p2=pini;p2<pfin;p2++){
         const float4 pp2=posp[p2];
-        const float drx=(grx-pp2.x)+offx, dry=(gry-pp2.y)+offy, drz=(grz-pp2.z)+offz;
+        const float drx=(grx+offx)-pp2.x, dry=(gry+offy)-pp2.y, drz=(grz+offz)-pp2.z;
         const float rr2=drx*drx+dry*dry+drz*drz;
         if(rr2<=c.kernelsize2 && (!c.use_floating || B2S_CODE_ISFLUID(code[p2]))){
           float fac;

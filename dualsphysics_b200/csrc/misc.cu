@@ -108,10 +108,10 @@ __global__ void __launch_bounds__(128) k_count_pairs(const DivState* __restrict_
       const uint32_t* beg=begt+(pass==0? ds->box_fluid: 0u);
       for(int z=zini;z<zfin;z++)for(int y=yini;y<yfin;y++)for(int x=xini;x<xfin;x++){
         const uint32_t pini=beg[y*ncx+z*nsheet+x], pfin=beg[y*ncx+z*nsheet+x+1];
-        const float ox=c.scell*float(cx-x), oy=c.scell*float(cy-y), oz=c.scell*float(cz-z);
+        const float ox=b2s_offx(c,cx+int(ds->cellmin[0]),x+int(ds->cellmin[0])), oy=c.scell*float(cy-y), oz=c.scell*float(cz-z);
         for(uint32_t p2=pini;p2<pfin;p2++){
           const float4 pp2=posp[p2];
-          const float drx=(pp1.x-pp2.x)+ox, dry=(pp1.y-pp2.y)+oy, drz=(pp1.z-pp2.z)+oz;
+          const float drx=__fsub_rn(__fadd_rn(pp1.x,ox),pp2.x), dry=__fsub_rn(__fadd_rn(pp1.y,oy),pp2.y), drz=__fsub_rn(__fadd_rn(pp1.z,oz),pp2.z);
           const float rr2=drx*drx+dry*dry+drz*drz;
           chk++;
           if(rr2<=c.kernelsize2 && rr2>=B2S_ALMOSTZERO)real++;

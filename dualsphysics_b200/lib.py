@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200sph.so")
+# B2S_LIB_PATH: developer override used by the kernel-tuning scripts (tools/tune_defer.sh) to load an alternative build
+LIB_PATH = os.environ.get("B2S_LIB_PATH") or os.path.join(_HERE, "lib", "libb200sph.so")
 
 # enums (same numeric values as the reference)
 KERNEL_CUBIC, KERNEL_WENDLAND = 1, 2
