@@ -162,40 +162,75 @@ __global__ void __launch_bounds__(DIV_BS) k_radix_hist(const uint32_t* __restric
   counts[threadIdx.x*ntiles+blockIdx.x]=h[threadIdx.x];
 }
 
-// Single-block exclusive scan of n uints (n = 256*ntiles, a few 1e5): warp shuffles + carry.
+// Exclusive scan of n uints (n = 256*ntiles, ~6e5 at 10M particles).  Blocks of 4096 elements:
+//   k_scan_partial (block totals) -> k_scan_excl on the totals (single block, tiny) -> k_scan_final (local scan + block offset).
+// Small inputs (n <= 4096*4) use the single-block kernel alone.
+#define SCAN_BLK 4096
+__device__ __forceinline__ uint32_t block_excl_scan4(uint32_t (&v)[4], uint32_t* wsum, uint32_t& total){
+  // each of the 1024 threads owns 4 consecutive elements; returns the exclusive prefix of v[0] inside the block
+  const int lane=threadIdx.x&31, w=threadIdx.x>>5;
+  const uint32_t tsum=v[0]+v[1]+v[2]+v[3];
+  uint32_t x=tsum;
+  #pragma unroll
+  for(int o=1;o<32;o<<=1){ const uint32_t y=__shfl_up_sync(0xffffffffu,x,o); if(lane>=o)x+=y; }
+  if(lane==31)wsum[w]=x;
+  __syncthreads();
+  if(w==0){
+    uint32_t s=wsum[lane];
+    #pragma unroll
+    for(int o=1;o<32;o<<=1){ const uint32_t y=__shfl_up_sync(0xffffffffu,s,o); if(lane>=o)s+=y; }
+    wsum[lane]=s;
+  }
+  __syncthreads();
+  total=wsum[31];
+  return (w? wsum[w-1]: 0u)+(x-tsum);
+}
 __global__ void __launch_bounds__(1024) k_scan_excl(uint32_t* data, uint32_t n){
   __shared__ uint32_t wsum[32];
-  __shared__ uint32_t carry_s;
-  if(threadIdx.x==0)carry_s=0;
-  __syncthreads();
-  const int lane=threadIdx.x&31, w=threadIdx.x>>5;
-  for(uint32_t base=0; base<n; base+=1024*4){
-    // each thread owns 4 consecutive elements
+  uint32_t carry=0;
+  for(uint32_t base=0; base<n; base+=SCAN_BLK){
     const uint32_t i0=base+threadIdx.x*4;
     uint32_t v[4];
     #pragma unroll
     for(int k=0;k<4;k++)v[k]=(i0+k<n? data[i0+k]: 0u);
-    const uint32_t tsum=v[0]+v[1]+v[2]+v[3];
-    uint32_t x=tsum;
-    #pragma unroll
-    for(int o=1;o<32;o<<=1){ const uint32_t y=__shfl_up_sync(0xffffffffu,x,o); if(lane>=o)x+=y; }
-    if(lane==31)wsum[w]=x;
-    __syncthreads();
-    if(w==0){
-      uint32_t s=wsum[lane];
-      #pragma unroll
-      for(int o=1;o<32;o<<=1){ const uint32_t y=__shfl_up_sync(0xffffffffu,s,o); if(lane>=o)s+=y; }
-      wsum[lane]=s;
-    }
-    __syncthreads();
-    const uint32_t carry=carry_s;
-    uint32_t excl=carry+(w? wsum[w-1]: 0u)+(x-tsum);
+    uint32_t total;
+    uint32_t excl=carry+block_excl_scan4(v,wsum,total);
     #pragma unroll
     for(int k=0;k<4;k++){ if(i0+k<n)data[i0+k]=excl; excl+=v[k]; }
-    __syncthreads();
-    if(threadIdx.x==1023)carry_s=carry+wsum[31];
+    carry+=total;
     __syncthreads();
   }
+}
+__global__ void __launch_bounds__(1024) k_scan_partial(const uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ bsum){
+  __shared__ uint32_t wsum[32];
+  const uint32_t i0=blockIdx.x*SCAN_BLK+threadIdx.x*4;
+  uint32_t t=0;
+  if(i0+3<n){ const uint4 q=*reinterpret_cast<const uint4*>(data+i0); t=q.x+q.y+q.z+q.w; }
+  else for(int k=0;k<4;k++)if(i0+k<n)t+=data[i0+k];
+  t=__reduce_add_sync(0xffffffffu,t);
+  if((threadIdx.x&31)==0)wsum[threadIdx.x>>5]=t;
+  __syncthreads();
+  if(threadIdx.x<32){ t=__reduce_add_sync(0xffffffffu,wsum[threadIdx.x]); if(threadIdx.x==0)bsum[blockIdx.x]=t; }
+}
+__global__ void __launch_bounds__(1024) k_scan_final(uint32_t* data, uint32_t n, const uint32_t* __restrict__ bsum_excl){
+  __shared__ uint32_t wsum[32];
+  const uint32_t i0=blockIdx.x*SCAN_BLK+threadIdx.x*4;
+  uint32_t v[4];
+  #pragma unroll
+  for(int k=0;k<4;k++)v[k]=(i0+k<n? data[i0+k]: 0u);
+  uint32_t total;
+  uint32_t excl=bsum_excl[blockIdx.x]+block_excl_scan4(v,wsum,total);
+  #pragma unroll
+  for(int k=0;k<4;k++){ if(i0+k<n)data[i0+k]=excl; excl+=v[k]; }
+}
+// scratch: at least n/SCAN_BLK+1 uints (may be NULL for n <= 4*SCAN_BLK).  Returns the number of launches.
+int b2s_scan_excl(cudaStream_t s, uint32_t* data, uint32_t n, uint32_t* scratch){
+  if(n<=4u*SCAN_BLK || !scratch){ k_scan_excl<<<1,1024,0,s>>>(data,n); return 1; }
+  const uint32_t nb=(n+SCAN_BLK-1)/SCAN_BLK;
+  k_scan_partial<<<nb,1024,0,s>>>(data,n,scratch);
+  k_scan_excl<<<1,1024,0,s>>>(scratch,nb);
+  k_scan_final<<<nb,1024,0,s>>>(data,n,scratch);
+  return 3;
 }
 
 __global__ void __launch_bounds__(DIV_BS) k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
@@ -357,7 +392,7 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   uint32_t *kin=ctx->cellpart,*vin=ctx->sortpart,*kout=ctx->cellpart_alt,*vout=ctx->sortpart_alt;
   for(int ps=0;ps<passes;ps++){
     k_radix_hist<<<ntiles,DIV_BS,0,s>>>(kin,ctx->div,ps*8,ntiles,ctx->radix_counts); B2S_LAUNCHED(ctx);
-    k_scan_excl<<<1,1024,0,s>>>(ctx->radix_counts,256u*ntiles); B2S_LAUNCHED(ctx);
+    ctx->launches+=b2s_scan_excl(s,ctx->radix_counts,256u*ntiles,ctx->radix_counts+ctx->radix_counts_len);
     k_radix_scatter<<<ntiles,DIV_BS,0,s>>>(kin,vin,kout,vout,ctx->radix_counts,ctx->div,ps*8,ntiles); B2S_LAUNCHED(ctx);
     uint32_t* t=kin; kin=kout; kout=t; t=vin; vin=vout; vout=t;
   }
@@ -396,4 +431,4 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   return B2S_OK;
 }
 
-void b2s_launch_scan_excl(cudaStream_t s, uint32_t* data, uint32_t n){ k_scan_excl<<<1,1024,0,s>>>(data,n); }
+void b2s_launch_scan_excl(cudaStream_t s, uint32_t* data, uint32_t n){ k_scan_excl<<<1,1024,0,s>>>(data,n); }   // small inputs (slab.cu)

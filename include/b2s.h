@@ -201,9 +201,9 @@ int b2s_time_interaction(b2s_ctx* ctx, int reps, float* ms_per_launch);
 int b2s_launch_count(b2s_ctx* ctx, uint64_t* launches, int reset);
 /* CUDA stream the ctx launches on (cudaStream_t cast to void*), for external event timing. */
 int b2s_get_stream(b2s_ctx* ctx, void** stream_out);
-/* Selects the fluid interaction kernel variant: 0 = gather (one thread per particle, reference
- * summation order), 1 = cell-tile (FP16 staged filter + exact body), 2 = warp-uniform stream + per-lane hit queue.
- * All variants visit neighbours in the same order and are bit-identical. */
+/* Selects the fluid interaction kernel variant: 0 = gather (one thread per particle, reference summation order; default),
+ * 3 = gather with deferred pair bodies (csrc/forces_defer.cu; experimental, used below 2^26 particles).
+ * Both visit neighbours in the same order and are bit-identical.  Other values: B2S_ERR_ARG. */
 int b2s_set_interaction_variant(b2s_ctx* ctx, int variant);
 
 /* ---- slab decomposition over several GPUs (no reference counterpart) ----------- */
