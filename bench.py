@@ -130,10 +130,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--np", type=int, default=NP_TARGET)
-    ap.add_argument("--variant", type=int, default=int(os.environ.get("B2S_VARIANT", "0")))
+    ap.add_argument("--variant", type=int, default=int(os.environ.get("B2S_VARIANT", "4")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
+    # the contract is ONE JSON line on stdout: libraries that write to fd 1 (NCCL prints its version there) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -145,7 +154,7 @@ def main():
             return 0
         res = run_reference_sample(CPU_SAMPLE_NP, max(1, min(a.steps, 5)), min(a.warmup, 1))
         if res is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (needs /root/reference in the build container)"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref was not built (needs /root/reference in the build container)"})
             return 0
         sample = f"{res['np']} particles x {res['steps']} steps of the same dam-break block (lattice start), {res['cores']} OpenMP threads"
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": res["steps"],
@@ -154,7 +163,7 @@ def main():
                 "config": {"workload": f"synthetic 3D dam-break block, {OPTIONS}; reference CPU/OpenMP build on a bounded sample", "np": res["np"]},
                 "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference", "sample": sample},
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ this repo's arm
@@ -347,7 +356,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     return 0
 
 

@@ -176,7 +176,7 @@ __device__ __forceinline__ bool row_trim(const DevCte& c,const CellRange& r,floa
   const float dy=fmaxf(0.f,fmaxf(sy-c.scell,-sy)), dz=fmaxf(0.f,fmaxf(sz-c.scell,-sz));
   const float xh2=c.kernelsize2*1.0002f-dy*dy-dz*dz;
   if(xh2<=0.f)return false;
-  const float xh=sqrtf(xh2)+c.scell*1e-4f, ovs=1.0f/c.scell;
+  const float xh=xh2*b2s_rsqrt(xh2)+c.scell*1e-4f, ovs=1.0f/c.scell;   // approximate sqrt (2 ulp) is covered by the margins
   xa=max(r.xini,r.cx+int(floorf((xin-xh)*ovs)));
   xb=min(r.xfin,r.cx+int(floorf((xin+xh)*ovs))+1);
   return xa<xb;

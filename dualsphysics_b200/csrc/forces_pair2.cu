@@ -1,0 +1,251 @@
+// forces_pair2.cu -- interaction variant 4: two neighbours per lane and iteration, pair arithmetic in packed FP32 (sm_100a).
+//
+// Same physics as variant 0 (forces.cu / forces_common.cuh pair_fluid), which restates cusph::Interaction_Forces /
+// KerInteractionForcesFluid (src/source/JSphGpu_ker.cu:673-964) and JSphCpu::InteractionForcesFluid (src/source/JSphCpu.cpp:736-1125).
+//
+// Why: variant 0 is bound by FP32 *issue slots* (profiles/README.md: 80% of the slots busy, FMA pipe 45%, 19 of 32 lanes active
+// because the ~70-instruction pair body sits under the rr2<(2h)^2 branch).  Blackwell's fma/mul/add.rn.f32x2 do two FP32
+// operations per issue slot (tools/microbench.cu: same FMA throughput as FFMA, half the slots).  Here every lane takes TWO
+// consecutive candidates of its row per iteration; the body runs when either is a hit and evaluates both in f32x2 registers,
+// the miss (if any) being neutralised by a 0/1 mask on the kernel gradient instead of a branch.  Per element the operations
+// and their rounding are exactly those of pair_fluid; only the grouping of the sums differs (even/odd candidates accumulate
+// in the two halves and are added at the end), so results agree with variant 0 to rounding, not bit for bit.
+//   * rows of neighbour cells are walked as ONE index range (block-relative x, b2s_internal.h B2S_XBLK) and trimmed to the
+//     cells the kernel sphere reaches (row_trim);
+//   * built for Wendland + artificial viscosity without floating bodies (every DDT mode, DBC and mDBC); other
+//     configurations run variant 0.
+#include "forces_common.cuh"
+
+#define P2_BS 128
+#ifndef P2_MINB
+#define P2_MINB 5            // resident blocks per SM the register allocation aims at
+#endif
+#ifndef P2_MASK
+#define P2_MASK 1            // 1: hits of a row chunk are first collected in a bit mask, then evaluated two at a time
+#endif
+#ifndef P2_EARLYV
+#define P2_EARLYV 0          // 1: load velrho of both candidates together with posp (no dependent load inside the body)
+#endif
+
+// ---- f32x2 helpers (PTX ISA 8.6+, sm_100): a 64-bit register holds (lo,hi) ----------------------------------------------
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo,float hi){ f2 r; asm("mov.b64 %0, {%1,%2};":"=l"(r):"f"(lo),"f"(hi)); return r; }
+__device__ __forceinline__ f2 pk1(float v){ return pk(v,v); }
+__device__ __forceinline__ float lo(f2 a){ float x,y; asm("mov.b64 {%0,%1}, %2;":"=f"(x),"=f"(y):"l"(a)); return x; }
+__device__ __forceinline__ float hi(f2 a){ float x,y; asm("mov.b64 {%0,%1}, %2;":"=f"(x),"=f"(y):"l"(a)); return y; }
+__device__ __forceinline__ f2 mul2(f2 a,f2 b){ f2 d; asm("mul.rn.f32x2 %0, %1, %2;":"=l"(d):"l"(a),"l"(b)); return d; }
+__device__ __forceinline__ f2 add2(f2 a,f2 b){ f2 d; asm("add.rn.f32x2 %0, %1, %2;":"=l"(d):"l"(a),"l"(b)); return d; }
+__device__ __forceinline__ f2 sub2(f2 a,f2 b){ f2 d; asm("sub.rn.f32x2 %0, %1, %2;":"=l"(d):"l"(a),"l"(b)); return d; }
+__device__ __forceinline__ f2 fma2(f2 a,f2 b,f2 c){ f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;":"=l"(d):"l"(a),"l"(b),"l"(c)); return d; }
+__device__ __forceinline__ f2 dot3_2(f2 ax,f2 ay,f2 az,f2 bx,f2 by,f2 bz){ return fma2(az,bz,fma2(ay,by,mul2(ax,bx))); }   // b2s_dot3 order
+
+struct Acc2 { f2 ax,ay,az,ar,delta; float visc; bool mark; };
+
+// Two neighbours (a: p2a, b: p2b) of target p1.  ha/hb: which of them are real pairs.  Follows pair_fluid operation by operation.
+template<int TDENS,bool BOUNDP2>
+__device__ __forceinline__ void pair2_body(const DevCte& c,f2 drx,f2 dry,f2 drz,f2 rr2,bool ha,bool hb,
+  const float4 velrhop1,float pressp1,const float4 va,const float4 vb,float pressa,float pressb,float visco,Acc2& a)
+{
+  const float massp2=(BOUNDP2? c.massb: c.massf);
+  const f2 mass2=pk1(massp2);
+  //-Misses are evaluated at rr2=(2h)^2 (finite everywhere) and removed by the 0/1 mask on the gradient.
+  const f2 rr2s=pk(ha? lo(rr2): c.kernelsize2, hb? hi(rr2): c.kernelsize2);
+  const f2 m2=pk(ha? 1.f: 0.f, hb? 1.f: 0.f);
+  //-kernel_fac<WENDLAND>: rad=rr2*rsqrt(rr2); qq=rad/h; wqq1=1-0.5qq; fac=((bwenh*wqq1)*wqq1)*wqq1
+  const f2 rad=mul2(rr2s,pk(b2s_rsqrt(lo(rr2s)),b2s_rsqrt(hi(rr2s))));
+  const f2 qq=mul2(rad,pk1(c.ovkernelh));
+  const f2 wqq1=fma2(pk1(-0.5f),qq,pk1(1.f));
+  f2 fac=mul2(mul2(mul2(pk1(c.bwenh),wqq1),wqq1),wqq1);
+  fac=mul2(fac,m2);
+  const f2 frx=mul2(fac,drx), fry=mul2(fac,dry), frz=mul2(fac,drz);
+  const float rhop1=velrhop1.w;
+  const f2 ovrhop2=pk(b2s_rcp(va.w),b2s_rcp(vb.w));
+  //-Momentum equation.
+  {
+    const f2 prs=mul2(pk(FADD(pressp1,pressa),FADD(pressp1,pressb)),mul2(pk1(b2s_rcp(rhop1)),ovrhop2));
+    const f2 p_vpm=mul2(prs,pk1(-massp2));
+    a.ax=fma2(p_vpm,frx,a.ax); a.ay=fma2(p_vpm,fry,a.ay); a.az=fma2(p_vpm,frz,a.az);
+  }
+  //-Continuity equation.
+  const f2 dvx=pk(FSUB(velrhop1.x,va.x),FSUB(velrhop1.x,vb.x)), dvy=pk(FSUB(velrhop1.y,va.y),FSUB(velrhop1.y,vb.y)), dvz=pk(FSUB(velrhop1.z,va.z),FSUB(velrhop1.z,vb.z));
+  a.ar=fma2(mul2(mass2,dot3_2(dvx,dvy,dvz,frx,fry,frz)),mul2(pk1(rhop1),ovrhop2),a.ar);
+  const f2 rr2eta=add2(rr2s,pk1(c.eta2));
+  const f2 ovrr2eta=pk(b2s_rcp(lo(rr2eta)),b2s_rcp(hi(rr2eta)));
+  //-Density diffusion.
+  if(TDENS==B2S_DDT_MOLTENI){
+    if(BOUNDP2 && c.tboundary==B2S_BC_DBC)a.mark=true;
+    else{
+      const f2 dot3=dot3_2(drx,dry,drz,frx,fry,frz);
+      const f2 visc_densi=mul2(mul2(pk1(FMUL(c.ddtkh,c.cs0)),sub2(mul2(pk1(rhop1),ovrhop2),pk1(1.f))),ovrr2eta);
+      a.delta=add2(a.delta,mul2(mul2(visc_densi,dot3),mass2));
+    }
+  }
+  if(TDENS==B2S_DDT_FOURTAKAS || (TDENS==B2S_DDT_FOURTAKASFULL && !BOUNDP2)){
+    if(BOUNDP2)a.mark=true;
+    else{
+      const f2 dot3=dot3_2(drx,dry,drz,frx,fry,frz);
+      const f2 one=pk1(1.f);
+      const f2 x=sub2(fma2(pk1(c.ddtgz),drz,one),one);
+      const f2 pw=fma2(x,fma2(x,fma2(x,pk1(c.ddt_c3),pk1(c.ddt_c2)),pk1(c.ddt_c1)),one);
+      const f2 rho0=pk1(c.rhopzero);
+      const f2 drho=sub2(mul2(rho0,pw),rho0);
+      const f2 visc_densi=mul2(mul2(pk1(FMUL(c.ddtkh,c.cs0)),sub2(pk(FSUB(va.w,rhop1),FSUB(vb.w,rhop1)),drho)),ovrr2eta);
+      a.delta=sub2(a.delta,mul2(mul2(mul2(visc_densi,dot3),mass2),ovrhop2));
+    }
+  }
+  //-Viscosity (artificial).
+  {
+    const f2 dot=dot3_2(drx,dry,drz,dvx,dvy,dvz);
+    const f2 dot_rr2=mul2(dot,ovrr2eta);
+    const f2 dm=mul2(dot_rr2,m2);                       // misses contribute 0 to the maximum (visc starts at 0)
+    a.visc=fmaxf(a.visc,fmaxf(lo(dm),hi(dm)));
+    const f2 amubar=mul2(pk1(c.kernelh),dot_rr2);
+    const f2 robar=mul2(pk(FADD(rhop1,va.w),FADD(rhop1,vb.w)),pk1(0.5f));
+    const f2 pi_visc=mul2(mul2(mul2(pk1(FMUL(-visco,c.cs0)),amubar),pk(b2s_rcp(lo(robar)),b2s_rcp(hi(robar)))),mass2);
+    const f2 npi=pk(lo(dot)<0.f? -lo(pi_visc): 0.f, hi(dot)<0.f? -hi(pi_visc): 0.f);   // only approaching pairs (dot<0)
+    a.ax=fma2(npi,frx,a.ax); a.ay=fma2(npi,fry,a.ay); a.az=fma2(npi,frz,a.az);
+  }
+}
+
+template<int TDENS>
+__global__ void __launch_bounds__(P2_BS,P2_MINB) k_forces_fluid_pair2(ForcesArgs g, const __grid_constant__ DevCte c)
+{
+  const DivState* ds=g.ds;
+  const uint32_t npb=ds->npb, np=ds->np;
+  const uint32_t p1=npb+blockIdx.x*blockDim.x+threadIdx.x;
+  const bool valid=(p1<np);
+  const uint32_t plast=np-1u;
+  float ace2=0.f, viscmax=0.f;
+  float4 pp1=make_float4(0,0,0,0), velrhop1=make_float4(0,0,0,1.f);
+  CellRange r; r.cx=r.cy=r.cz=0; r.xini=r.xfin=r.yini=r.yfin=r.zini=r.zfin=0;
+  if(valid){ pp1=g.posp[p1]; velrhop1=g.velrho[p1]; r=cell_range(g.dcell[p1],c,ds); }
+  const float pressp1=pp1.w;
+  const int d=c.scelldiv, ncx=int(ds->ncx), nsheet=int(ds->nsheet), cmx=int(ds->cellmin[0]);
+  const float xin=pp1.x-c.scell*float((r.cx+cmx)&((1<<B2S_XBLK)-1));   // x inside the own cell (row_trim only)
+  // the untrimmed x window touches at most two blocks of 2^B2S_XBLK cells: A (of xini) and B (of xfin-1)
+  const bool oneblk=(((r.xini+cmx)>>B2S_XBLK)==((r.xfin-1+cmx)>>B2S_XBLK));
+  const int xmid0=(((r.xfin-1+cmx)>>B2S_XBLK)<<B2S_XBLK)-cmx;          // first cell of block B
+  const float sxA=FADD(pp1.x,b2s_offx(c,r.cx+cmx,r.xini+cmx)), sxB=FADD(pp1.x,b2s_offx(c,r.cx+cmx,r.xfin-1+cmx));
+  // The boundary pass runs FIRST and its six sums are parked in shared memory, so that only one set of packed accumulators
+  // is alive in the (long) fluid pass: fewer registers, more resident warps.  finalize_store gets both sets as before.
+  __shared__ float stash[6][P2_BS];
+  Acc2 acc;
+  acc.ax=acc.ay=acc.az=acc.ar=acc.delta=0ull; acc.visc=0.f; acc.mark=false;
+  #pragma unroll 1
+  for(int pass=1;pass>=0;pass--){
+    const uint32_t* beg=(pass==0? g.beg+ds->box_fluid: g.beg);   // pass 1: boundary neighbours (first), pass 0: fluid neighbours
+    #pragma unroll 1
+    for(int z=r.cz-d;z<=r.cz+d;z++){
+      const float sz=FADD(pp1.z,c.scell*float(r.cz-z));
+      #pragma unroll 1
+      for(int y=r.cy-d;y<=r.cy+d;y++){
+        const float sy=FADD(pp1.y,c.scell*float(r.cy-y));
+        uint32_t pbeg=0,pend=0,pmid=0;
+        int xa,xb;
+        if(z>=r.zini && z<r.zfin && y>=r.yini && y<r.yfin && row_trim(c,r,xin,sy,sz,xa,xb)){
+          const uint32_t* brow=beg+(y*ncx+z*nsheet);
+          pbeg=brow[xa]; pend=brow[xb];
+          pmid=(oneblk || xmid0<=xa? pbeg: (xmid0>=xb? pend: brow[xmid0]));
+        }
+        const uint32_t lenmax=__reduce_max_sync(0xffffffffu,pend-pbeg);
+#if P2_MASK
+        //-Two phases per chunk of up to 32 candidates: (1) check every candidate and record the hits in a per-lane bit mask,
+        // (2) evaluate the hits two at a time.  Phase 2 only iterates as long as the lane with most hits needs, so the packed
+        // body runs on real pairs (both halves used) instead of on whatever two consecutive candidates happen to be.
+        #pragma unroll 1
+        for(uint32_t k0=0;k0<lenmax;k0+=32){
+          const uint32_t n=min(32u,lenmax-k0), pb0=pbeg+k0;
+          uint32_t mask=0;
+          #pragma unroll 4
+          for(uint32_t k=0;k<n;k++){
+            const uint32_t p2=pb0+k;
+            const float4 pp2=__ldg(g.posp+min(p2,plast));
+            const float drx=FSUB(p2>=pmid? sxB: sxA,pp2.x), dry=FSUB(sy,pp2.y), drz=FSUB(sz,pp2.z);
+            const float rr2=b2s_rr2(drx,dry,drz);
+            if(p2<pend && rr2<=c.kernelsize2 && rr2>=B2S_ALMOSTZERO)mask|=(1u<<k);
+          }
+          #pragma unroll 1
+          for(uint32_t it=(__reduce_max_sync(0xffffffffu,uint32_t(__popc(mask)))+1u)>>1;it;it--){
+            if(mask){
+              const uint32_t ka=__ffs(mask)-1u; mask&=mask-1u;
+              const bool hb=(mask!=0u);
+              const uint32_t kb=(hb? __ffs(mask)-1u: ka); mask&=mask-1u;
+              const uint32_t p2a=pb0+ka, p2b=pb0+kb;
+              const float4 pa=__ldg(g.posp+p2a), pb=__ldg(g.posp+p2b);
+              const float4 va=__ldg(g.velrho+p2a), vb=__ldg(g.velrho+p2b);
+              const f2 drx=pk(FSUB(p2a>=pmid? sxB: sxA,pa.x),FSUB(p2b>=pmid? sxB: sxA,pb.x));
+              const f2 dry=pk(FSUB(sy,pa.y),FSUB(sy,pb.y)), drz=pk(FSUB(sz,pa.z),FSUB(sz,pb.z));
+              const f2 rr2=fma2(drz,drz,fma2(dry,dry,mul2(drx,drx)));   // b2s_rr2 order
+              if(pass==0)pair2_body<TDENS,false>(c,drx,dry,drz,rr2,true,hb,velrhop1,pressp1,va,vb,pa.w,pb.w,c.visco_f,acc);
+              else       pair2_body<TDENS,true >(c,drx,dry,drz,rr2,true,hb,velrhop1,pressp1,va,vb,pa.w,pb.w,c.visco_b,acc);
+            }
+          }
+        }
+#else
+        #pragma unroll 2
+        for(uint32_t k=0;k<lenmax;k+=2){
+          const uint32_t p2a=pbeg+k, p2b=p2a+1u;
+          const uint32_t qa=min(p2a,plast), qb=min(p2b,plast);      // loads always hit real particles (finite data)
+          const float4 pa=__ldg(g.posp+qa), pb=__ldg(g.posp+qb);
+#if P2_EARLYV
+          const float4 va=__ldg(g.velrho+qa), vb=__ldg(g.velrho+qb);
+#endif
+          const f2 drx=pk(FSUB(p2a>=pmid? sxB: sxA,pa.x),FSUB(p2b>=pmid? sxB: sxA,pb.x));
+          const f2 dry=pk(FSUB(sy,pa.y),FSUB(sy,pb.y)), drz=pk(FSUB(sz,pa.z),FSUB(sz,pb.z));
+          const f2 rr2=fma2(drz,drz,fma2(dry,dry,mul2(drx,drx)));   // b2s_rr2 order
+          const float ra=lo(rr2), rb=hi(rr2);
+          const bool ha=(p2a<pend && ra<=c.kernelsize2 && ra>=B2S_ALMOSTZERO);
+          const bool hb=(p2b<pend && rb<=c.kernelsize2 && rb>=B2S_ALMOSTZERO);
+          if(ha||hb){
+#if !P2_EARLYV
+            const float4 va=__ldg(g.velrho+qa), vb=__ldg(g.velrho+qb);
+#endif
+            if(pass==0)pair2_body<TDENS,false>(c,drx,dry,drz,rr2,ha,hb,velrhop1,pressp1,va,vb,pa.w,pb.w,c.visco_f,acc);
+            else       pair2_body<TDENS,true >(c,drx,dry,drz,rr2,ha,hb,velrhop1,pressp1,va,vb,pa.w,pb.w,c.visco_b,acc);
+          }
+        }
+#endif
+      }
+    }
+    if(pass==1){ // park the boundary sums, restart the accumulators for the fluid pass
+      stash[0][threadIdx.x]=FADD(lo(acc.ax),hi(acc.ax)); stash[1][threadIdx.x]=FADD(lo(acc.ay),hi(acc.ay)); stash[2][threadIdx.x]=FADD(lo(acc.az),hi(acc.az));
+      stash[3][threadIdx.x]=FADD(lo(acc.ar),hi(acc.ar)); stash[4][threadIdx.x]=(acc.mark? FLT_MAX: FADD(lo(acc.delta),hi(acc.delta))); stash[5][threadIdx.x]=acc.visc;
+      acc.ax=acc.ay=acc.az=acc.ar=acc.delta=0ull; acc.visc=0.f; acc.mark=false;
+    }
+  }
+  if(valid){
+    PairAcc sf={0,0,0,0,0,0,0,0,0,0,0,0}, sb={0,0,0,0,0,0,0,0,0,0,0,0};
+    sf.ax=FADD(lo(acc.ax),hi(acc.ax)); sf.ay=FADD(lo(acc.ay),hi(acc.ay)); sf.az=FADD(lo(acc.az),hi(acc.az)); sf.ar=FADD(lo(acc.ar),hi(acc.ar));
+    sf.delta=(acc.mark? FLT_MAX: FADD(lo(acc.delta),hi(acc.delta))); sf.visc=acc.visc;
+    sb.ax=stash[0][threadIdx.x]; sb.ay=stash[1][threadIdx.x]; sb.az=stash[2][threadIdx.x]; sb.ar=stash[3][threadIdx.x];
+    sb.delta=stash[4][threadIdx.x]; sb.visc=stash[5][threadIdx.x];
+    finalize_store<B2S_VISCO_ARTIFICIAL,TDENS>(g,c,p1,velrhop1,sf,sb,ace2,viscmax);
+  }
+  //-Fused maxima: ViscDtMax and AceMax^2 (replaces ReduMaxFloat x2 + cudaMemcpy, JSphGpu_ker.cu:75-125).
+  #pragma unroll
+  for(int o=16;o;o>>=1){ viscmax=fmaxf(viscmax,__shfl_xor_sync(0xffffffffu,viscmax,o)); ace2=fmaxf(ace2,__shfl_xor_sync(0xffffffffu,ace2,o)); }
+  if((threadIdx.x&31)==0){
+    if(viscmax>0.f)atomicMax(&g.st->viscdtmax_bits,__float_as_uint(viscmax));
+    if(ace2>0.f)atomicMax(&g.st->acemax2_bits,__float_as_uint(ace2));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+bool b2s_forces_pair2_supported(const DevCte& c){
+  return c.tkernel==B2S_KERNEL_WENDLAND && c.tvisco==B2S_VISCO_ARTIFICIAL && !c.use_floating && (2*c.scelldiv+1)<=5;
+}
+
+int b2s_forces_pair2_launch(b2s_ctx* ctx, const ForcesArgs& g){
+  const DevCte& c=ctx->cte;
+  const uint32_t npf=ctx->np_host-ctx->npb_host;
+  const unsigned gb=b2s_blocks(npf,P2_BS);
+  switch(c.tdensity){
+    case B2S_DDT_NONE:      k_forces_fluid_pair2<B2S_DDT_NONE><<<gb,P2_BS,0,ctx->stream>>>(g,c); break;
+    case B2S_DDT_MOLTENI:   k_forces_fluid_pair2<B2S_DDT_MOLTENI><<<gb,P2_BS,0,ctx->stream>>>(g,c); break;
+    case B2S_DDT_FOURTAKAS: k_forces_fluid_pair2<B2S_DDT_FOURTAKAS><<<gb,P2_BS,0,ctx->stream>>>(g,c); break;
+    default:                k_forces_fluid_pair2<B2S_DDT_FOURTAKASFULL><<<gb,P2_BS,0,ctx->stream>>>(g,c); break;
+  }
+  B2S_LAUNCHED(ctx);
+  B2S_CUDA(ctx,cudaGetLastError());
+  return B2S_OK;
+}

@@ -67,7 +67,7 @@ def _check_forces(ctx, g, p, label, report, wide=False):
     assert e["acemax"] < ta and e["velmax"] < 1e-4 and e["viscdtmax"] < 1e-3, (label, e)
 
 
-@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("variant", [0, 3, 4])
 @pytest.mark.parametrize("fx", FIXTURES)
 def test_golden_reference_parity(fx, variant, tmp_path, built_lib):
     meta = json.load(open(os.path.join(H.GOLDEN, fx, "fixture.json")))
@@ -213,3 +213,35 @@ def test_deferred_variant_is_bit_identical_to_gather(opts, options, tmp_path, bu
     assert np.array_equal(a0[1].view(np.uint32), a3[1].view(np.uint32)), "state after 6 steps differs between variants"
     assert np.array_equal(a0[0].view(np.uint32), a3[0].view(np.uint32)), "ace/ar differ between variants"
     assert a0[2:] == a3[2:]
+
+
+@pytest.mark.parametrize("options", ["", "-cellmode:half", "-cellmode:half -ddt:1", "-cellmode:half -ddt:3", "-ddt:0"])
+def test_packed_variant_matches_gather(options, tmp_path, built_lib):
+    """Variant 4 (two hits per lane in f32x2 registers, csrc/forces_pair2.cu) performs per pair exactly the operations of
+    variant 0 but adds the two halves of its packed accumulators at the end, so on the SAME state it agrees to summation
+    rounding: 5e-6 of max|ace|, dt 1e-6; ar 2e-4 of its floor scale rho0*cs0/h*1e-4 (at rest ar is a sum of cancelling
+    density-diffusion terms, so the order of the additions shows; the reference tolerance on the same scale is 5e-4).  After 6 independent steps the two runs differ by
+    1e-6 in the state, which the Tait EOS turns into ~1e-4 in ace (same effect as between the reference builds)."""
+    H.write_case(tmp_path, dp=0.02)
+    case = str(tmp_path / "Case")
+    inter = dsb.lib.INTER_SYMPREDICTOR
+    for nsteps, tol_ace, tol_state in ((0, 5e-6, 0.0), (6, 5e-4, 1e-6)):
+        res = []
+        for variant in (0, 4):
+            sim = dsb.Simulation(case, options=options)
+            sim.ctx.set_variant(variant)
+            if nsteps:
+                sim.ctx.run_steps(nsteps)
+            sim.ctx.interaction(inter)
+            info = sim.ctx.info()
+            p = sim.params
+            res.append((sim.ctx.array("acear").copy(), sim.ctx.array("velrho").copy(), info.acemax, info.viscdtmax, info.dt_last,
+                        float(p.rhopzero) * p.cs0 / float(p.kernelh) * 1e-4))
+            sim.close()
+        a0, a4 = res
+        e_ace = H.rel_err(a4[0][:, :3], a0[0][:, :3])
+        e_ar = H.rel_err(a4[0][:, 3], a0[0][:, 3], floor=a0[5])
+        e_state = H.rel_err(a4[1], a0[1])
+        print(f"\n[variant 4 vs 0, {options!r}, after {nsteps} steps] ace {e_ace:.2e} ar {e_ar:.2e} state {e_state:.2e} dt {a0[4]} {a4[4]}")
+        assert e_ace < tol_ace and e_ar < max(tol_ace, 2e-4) and e_state <= tol_state
+        assert abs(a4[4] - a0[4]) <= (1e-6 if nsteps == 0 else 2e-5) * a0[4]
