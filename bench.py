@@ -28,8 +28,10 @@ sys.path.insert(0, ROOT)
 METRIC = "particle-steps/sec (whole box) at 1/2/4/8 B200; interaction-kernel roofline fraction"
 UNIT = "particle-steps/s"
 OPTIONS = "-symplectic -wendland -viscoart:0.1 -ddt:2 -ddtvalue:0.1 -dbc -cellmode:half" + os.environ.get("B2S_BENCH_EXTRA_OPTS", "")
-# DRAM bytes of ONE launch of the fluid interaction kernel at the 10M-particle workload (profiles/r01_ncu_forces_gather_half.csv)
-NCU_TRAFFIC_BYTES = None
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the fluid interaction kernel at the 10M-particle
+# workload, from the `ncu --set full` capture summarised in profiles/r01_ncu_forces_pair2_10M.txt (451.1 MB + 139.3 MB);
+# scaled by the fluid count when the bench runs another size
+NCU_TRAFFIC_BYTES, NCU_TRAFFIC_NPF = 590437888, 9281220
 NP_TARGET = int(os.environ.get("B2S_BENCH_NP", "10000000"))
 CPU_SAMPLE_NP = int(os.environ.get("B2S_BENCH_CPU_NP", "1000000"))
 # flop model of SURVEY 8(d): per checked pair 16 flop, per real pair (r<2h) 90 flop
@@ -66,7 +68,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -317,9 +319,9 @@ def main():
         fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12      # 148 SMs x 128 lanes x 2 flop x max SM clock
         gbs_k = BYTES_INTER * npf / (ms_k * 1e-3) / 1e9
         gbs_step = BYTES_STEP * np_total / (secs / a.steps) / 1e9
-        roofline = {"kernel": "k_forces_fluid_gather (fluid<-fluid+bound interaction)", "bound": "fp32", "achieved": tf_ach, "peak": fp32_peak,
-                    "unit": "TFLOP/s", "frac": tf_ach / fp32_peak, "traffic": NCU_TRAFFIC_BYTES,
-                    "traffic_note": "dram__bytes_read.sum+dram__bytes_write.sum of one launch at this size from profiles/ (ncu --set full)",
+        roofline = {"kernel": "k_forces_fluid_pair2 (fluid<-fluid+bound interaction, variant 4)" if a.variant == 4 else "k_forces_fluid_gather (fluid<-fluid+bound interaction)", "bound": "fp32", "achieved": tf_ach, "peak": fp32_peak,
+                    "unit": "TFLOP/s", "frac": tf_ach / fp32_peak, "traffic": int(NCU_TRAFFIC_BYTES * npf / NCU_TRAFFIC_NPF),
+                    "traffic_note": "dram__bytes_read.sum+dram__bytes_write.sum per launch from profiles/r01_ncu_forces_pair2_10M.txt (ncu --set full), scaled by fluid count; algorithmic bytes = 50 B x fluid particles",
                     "peak_source": "148 SM x 128 FP32 lanes x 2 x clocks.max.sm (non-tensor FP32 issue; tensor cores do not apply to pairwise SPH)",
                     "ms_per_launch": ms_k, "pairs_checked": chk, "pairs_real": real, "flop_model": "16*checked + 90*real (SURVEY 8d)",
                     "share_of_step": 2 * ms_k / (secs / a.steps * 1e3),

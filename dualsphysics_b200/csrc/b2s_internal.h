@@ -123,6 +123,7 @@ struct b2s_ctx {
   float4* boundnor; float4* boundnor_alt;                 // xyz normal, w unused
   // interaction inputs/outputs
   float4* posp;      // (x,y,z) relative to own cell origin, w = pressure
+  uint4*  posh;      // FP16 copy of posp.xyz in cell units, two particles per 16 B: (x0,x1)(y0,y1)(z0,z1)(-) -- pre-filter of forces_pair2.cu
   float4* acear;     // ace.xyz, ar
   // neighbour list
   uint32_t* cellpart; uint32_t* sortpart; uint32_t* cellpart_alt; uint32_t* sortpart_alt;
@@ -152,10 +153,11 @@ int  b2s_fail(b2s_ctx* ctx, int code, const char* fmt, ...);
 static inline unsigned b2s_blocks(size_t n, unsigned bs){ return (unsigned)((n+bs-1)/bs); }
 
 // posp frame: y,z relative to the origin of the particle's own cell; x relative to the origin of its BLOCK of 2^B2S_XBLK
-// cells along x (absolute domain cells).  A whole row of neighbour cells [cx-d,cx+d] then needs at most two x offsets,
+// cells along x (absolute domain cells).  A whole row of neighbour cells [cx-d,cx+d] (at most 5 cells = 2^B2S_XBLK+1, so it
+// touches at most two blocks) then needs at most two x offsets,
 // so the interaction kernels walk a row as ONE index range instead of one range per cell.  Precision: FP32 of a length
-// < 8*scell, i.e. the same order as the reference's PosCell frame (JSphGpuSimple_ker.cu:46-57).
-#define B2S_XBLK 3
+// < 4*scell, i.e. the same order as the reference's PosCell frame (JSphGpuSimple_ker.cu:46-57).
+#define B2S_XBLK 2
 #ifdef __CUDACC__
 __device__ __forceinline__ float b2s_offx(const DevCte& c,int cx1_abs,int cx2_abs){ return c.scell_blk*float((cx1_abs>>B2S_XBLK)-(cx2_abs>>B2S_XBLK)); }
 __device__ __forceinline__ float b2s_press(float rho, const DevCte& c){

@@ -14,6 +14,7 @@
 // reference's fluid-only divide because its boundary block is already in cell order (JCellDivGpuSingle.cpp:193-197).
 #include "b2s_internal.h"
 #include <stdio.h>
+#include <cuda_fp16.h>
 
 #define DIV_BS 256
 
@@ -318,7 +319,7 @@ struct ReorderArgs {
   const float4* m1_s; float4* m1_d;
   const float* tau_s; float* tau_d;
   const float4* nor_s; float4* nor_d;
-  float4* posp; uint32_t* ridp;
+  float4* posp; uint4* posh; uint32_t* ridp;
   uint32_t casenfixed, casenbound;
 };
 
@@ -354,6 +355,11 @@ __global__ void __launch_bounds__(DIV_BS) k_reorder(const DivState* __restrict__
       pp.z=float((z   -cte.domposmin[2])-cte.scell_d*double(cz));
       pp.w=b2s_press(vr.w,cte);
       a.posp[p]=pp;
+      { // FP16 pre-filter copy in cell units (pair-interleaved, see b2s_internal.h posh)
+        __half* h=reinterpret_cast<__half*>(a.posh+(p>>1))+(p&1u);
+        const float ovs=1.0f/cte.scell;
+        h[0]=__float2half_rn(pp.x*ovs); h[2]=__float2half_rn(pp.y*ovs); h[4]=__float2half_rn(pp.z*ovs);
+      }
       if((p>=ds->npb || cte.dt_allparticles) && B2S_CODE_ISNORMAL(cod))v2=vr.x*vr.x+vr.y*vr.y+vr.z*vr.z;   // ghosts (slab halos) excluded
       if(a.ridp && id>=a.casenfixed && id<a.casenbound)a.ridp[id-a.casenfixed]=p;
     }
@@ -414,7 +420,7 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   if(ctx->velrhom1){ a.m1_s=ctx->velrhom1; a.m1_d=ctx->velrhom1_alt; }
   if(ctx->spstau){ a.tau_s=ctx->spstau; a.tau_d=ctx->spstau_alt; }
   if(ctx->boundnor){ a.nor_s=ctx->boundnor; a.nor_d=ctx->boundnor_alt; }
-  a.posp=ctx->posp;
+  a.posp=ctx->posp; a.posh=ctx->posh;
   a.ridp=(ctx->prm.casenmoving+ctx->prm.casenfloat? ctx->ridp: NULL);
   a.casenfixed=ctx->prm.casenfixed; a.casenbound=ctx->prm.casenbound;
   if(a.ridp)B2S_CUDA(ctx,cudaMemsetAsync(ctx->ridp,0xff,size_t(ctx->prm.casenmoving+ctx->prm.casenfloat)*4,s));

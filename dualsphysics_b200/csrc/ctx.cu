@@ -95,7 +95,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
     if(e==cudaSuccess){ cudaMemset(ctx->spstau,0,cap*24); cudaMemset(ctx->spstau_alt,0,cap*24); cudaMemset(ctx->spstau_new,0,cap*24); }
   }
   if(q.tboundary==B2S_BC_MDBC){ TRY(dalloc(ctx->boundnor,cap)); TRY(dalloc(ctx->boundnor_alt,cap)); if(e==cudaSuccess){ cudaMemset(ctx->boundnor,0,cap*16); cudaMemset(ctx->boundnor_alt,0,cap*16);} }
-  TRY(dalloc(ctx->posp,cap)); TRY(dalloc(ctx->acear,cap));
+  TRY(dalloc(ctx->posp,cap)); TRY(dalloc(ctx->acear,cap)); TRY(dalloc(ctx->posh,size_t(cap)/2+2));
   TRY(dalloc(ctx->cellpart,cap)); TRY(dalloc(ctx->sortpart,cap)); TRY(dalloc(ctx->cellpart_alt,cap)); TRY(dalloc(ctx->sortpart_alt,cap));
   { uint32_t* b=NULL; TRY(dalloc(b,size_t(ctx->nctt_max)+2)); ctx->begincell=(int2*)b; }
   ctx->radix_counts_len=size_t(256)*((cap+4095)/4096+1);
@@ -122,7 +122,7 @@ extern "C" int b2s_destroy(b2s_ctx* ctx){
   cudaFree(ctx->velrhom1); cudaFree(ctx->velrhom1_alt);
   cudaFree(ctx->spstau); cudaFree(ctx->spstau_alt); cudaFree(ctx->spstau_new);
   cudaFree(ctx->boundnor); cudaFree(ctx->boundnor_alt);
-  cudaFree(ctx->posp); cudaFree(ctx->acear);
+  cudaFree(ctx->posp); cudaFree(ctx->acear); cudaFree(ctx->posh);
   cudaFree(ctx->cellpart); cudaFree(ctx->sortpart); cudaFree(ctx->cellpart_alt); cudaFree(ctx->sortpart_alt);
   cudaFree(ctx->begincell); cudaFree(ctx->radix_counts); cudaFree(ctx->ridp);
   cudaFree(ctx->div); cudaFree(ctx->step);

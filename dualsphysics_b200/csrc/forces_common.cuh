@@ -11,7 +11,7 @@ struct ForcesArgs {
   const DivState* ds; StepState* st;
   const uint32_t* beg;            // begincell (CPU form)
   const uint32_t* dcell; const typecode* code;
-  const float4* posp; const float4* velrho;
+  const float4* posp; const float4* velrho; const uint4* posh;
   const float* tau; float* tau_new;   // 6 floats/particle (xx,xy,xz,yy,yz,zz) or NULL
   const float* ftomassp;
   float4* acear;

@@ -15,13 +15,17 @@
 //   * built for Wendland + artificial viscosity without floating bodies (every DDT mode, DBC and mDBC); other
 //     configurations run variant 0.
 #include "forces_common.cuh"
+#include <cuda_fp16.h>
 
+#ifndef P2_BS
 #define P2_BS 128
+#endif
 #ifndef P2_MINB
-#define P2_MINB 5            // resident blocks per SM the register allocation aims at
+#define P2_MINB 6            // resident blocks per SM the register allocation aims at
 #endif
 #ifndef P2_MASK
-#define P2_MASK 1            // 1: hits of a row chunk are first collected in a bit mask, then evaluated two at a time
+#define P2_MASK 2            // 1: hits of a row chunk are collected in a bit mask (FP32 test), then evaluated two at a time;
+                             // 2: same with the FP16 pre-filter on posh; 0: two consecutive candidates per iteration
 #endif
 #ifndef P2_EARLYV
 #define P2_EARLYV 0          // 1: load velrho of both candidates together with posp (no dependent load inside the body)
@@ -38,6 +42,14 @@ __device__ __forceinline__ f2 add2(f2 a,f2 b){ f2 d; asm("add.rn.f32x2 %0, %1, %
 __device__ __forceinline__ f2 sub2(f2 a,f2 b){ f2 d; asm("sub.rn.f32x2 %0, %1, %2;":"=l"(d):"l"(a),"l"(b)); return d; }
 __device__ __forceinline__ f2 fma2(f2 a,f2 b,f2 c){ f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;":"=l"(d):"l"(a),"l"(b),"l"(c)); return d; }
 __device__ __forceinline__ f2 dot3_2(f2 ax,f2 ay,f2 az,f2 bx,f2 by,f2 bz){ return fma2(az,bz,fma2(ay,by,mul2(ax,bx))); }   // b2s_dot3 order
+
+// FP16 pre-filter: rr2 of two candidates (half2) against the threshold; sets bit0/bit1 in mask for lo/hi
+__device__ __forceinline__ void hit2_or(uint32_t& mask,uint32_t rr2,uint32_t thr2,uint32_t bit0,uint32_t bit1){
+  asm("{\n .reg .pred p,q;\n setp.le.f16x2 p|q, %1, %2;\n @p or.b32 %0, %0, %3;\n @q or.b32 %0, %0, %4;\n}"
+      :"+r"(mask):"r"(rr2),"r"(thr2),"r"(bit0),"r"(bit1));
+}
+__device__ __forceinline__ uint32_t h2u(__half2 h){ return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 u2h(uint32_t u){ return *reinterpret_cast<__half2*>(&u); }
 
 struct Acc2 { f2 ax,ay,az,ar,delta; float visc; bool mark; };
 
@@ -126,6 +138,13 @@ __global__ void __launch_bounds__(P2_BS,P2_MINB) k_forces_fluid_pair2(ForcesArgs
   const bool oneblk=(((r.xini+cmx)>>B2S_XBLK)==((r.xfin-1+cmx)>>B2S_XBLK));
   const int xmid0=(((r.xfin-1+cmx)>>B2S_XBLK)<<B2S_XBLK)-cmx;          // first cell of block B
   const float sxA=FADD(pp1.x,b2s_offx(c,r.cx+cmx,r.xini+cmx)), sxB=FADD(pp1.x,b2s_offx(c,r.cx+cmx,r.xfin-1+cmx));
+  // FP16 pre-filter constants (cell units): target x for the two blocks, threshold with margin
+  const float ovs=1.0f/c.scell;
+  const uint32_t jlast=(np-1u)>>1;
+  const __half hA=__float2half_rn(sxA*ovs), hB=__float2half_rn(sxB*ovs);
+  const uint32_t hAA=h2u(__halves2half2(hA,hA)), hBB=h2u(__halves2half2(hB,hB)), hAB=h2u(__halves2half2(hA,hB));
+  const float kc=c.kernelsize2*ovs*ovs;
+  const uint32_t thr2=h2u(__float2half2_rn(kc*1.015f+0.02f));
   // The boundary pass runs FIRST and its six sums are parked in shared memory, so that only one set of packed accumulators
   // is alive in the (long) fluid pass: fewer registers, more resident warps.  finalize_store gets both sets as before.
   __shared__ float stash[6][P2_BS];
@@ -148,7 +167,52 @@ __global__ void __launch_bounds__(P2_BS,P2_MINB) k_forces_fluid_pair2(ForcesArgs
           pmid=(oneblk || xmid0<=xa? pbeg: (xmid0>=xb? pend: brow[xmid0]));
         }
         const uint32_t lenmax=__reduce_max_sync(0xffffffffu,pend-pbeg);
-#if P2_MASK
+#if P2_MASK==2
+        //-Two phases per chunk of 16 candidate PAIRS (32 particles, aligned to even indices):
+        // (1) FP16 pre-filter in cell units on the pair-interleaved posh array: one 16-byte load and ~8 instructions per
+        //     candidate pair; the threshold carries a margin above the FP16 error (b2s_internal.h posh), so no real pair is lost;
+        // (2) the set bits are evaluated two at a time in FP32 exactly like variant 0 (false positives drop out at the exact test).
+        const uint32_t jb=pbeg>>1, npair=((pend+1u)>>1)-jb;
+        const uint32_t npmax=__reduce_max_sync(0xffffffffu,npair);
+        const uint32_t sy2=h2u(__float2half2_rn(sy*ovs)), sz2=h2u(__float2half2_rn(sz*ovs));
+        #pragma unroll 1
+        for(uint32_t j0=0;j0<npmax;j0+=16){
+          const uint32_t n=min(16u,npmax-j0), pb0=(jb+j0)<<1;
+          uint32_t mask=0, bit=1u;
+          #pragma unroll 4
+          for(uint32_t k=0;k<n;k++,bit<<=2){
+            const uint32_t p=pb0+2u*k;
+            const uint4 w=__ldg(g.posh+min(jb+j0+k,jlast));
+            const uint32_t sx2=(p+1u<pmid? hAA: (p>=pmid? hBB: hAB));
+            const __half2 dx=__hsub2(u2h(sx2),u2h(w.x)), dy=__hsub2(u2h(sy2),u2h(w.y)), dz=__hsub2(u2h(sz2),u2h(w.z));
+            const __half2 rr=__hfma2(dz,dz,__hfma2(dy,dy,__hmul2(dx,dx)));
+            hit2_or(mask,h2u(rr),thr2,bit,bit+bit);
+          }
+          //-Bits of particles outside [pbeg,pend) (first/last pair of the row) are cleared.
+          if(pb0<pbeg)mask&=~1u;
+          { const uint32_t v=(pend>pb0? pend-pb0: 0u); if(v<32u)mask&=((1u<<v)-1u); }
+          #pragma unroll 1
+          for(uint32_t it=(__reduce_max_sync(0xffffffffu,uint32_t(__popc(mask)))+1u)>>1;it;it--){
+            if(mask){
+              const uint32_t ka=__ffs(mask)-1u; mask&=mask-1u;
+              const bool two=(mask!=0u);
+              const uint32_t kb=(two? __ffs(mask)-1u: ka); mask&=mask-1u;
+              const uint32_t p2a=pb0+ka, p2b=pb0+kb;
+              const float4 pa=__ldg(g.posp+p2a), pb=__ldg(g.posp+p2b);
+              const float4 va=__ldg(g.velrho+p2a), vb=__ldg(g.velrho+p2b);   // issued with posp: one load latency per round, not two
+              const f2 drx=pk(FSUB(p2a>=pmid? sxB: sxA,pa.x),FSUB(p2b>=pmid? sxB: sxA,pb.x));
+              const f2 dry=pk(FSUB(sy,pa.y),FSUB(sy,pb.y)), drz=pk(FSUB(sz,pa.z),FSUB(sz,pb.z));
+              const f2 rr2=fma2(drz,drz,fma2(dry,dry,mul2(drx,drx)));   // b2s_rr2 order
+              const float ra=lo(rr2), rb=hi(rr2);
+              const bool ha=(ra<=c.kernelsize2 && ra>=B2S_ALMOSTZERO), hb=(two && rb<=c.kernelsize2 && rb>=B2S_ALMOSTZERO);
+              if(ha||hb){
+                if(pass==0)pair2_body<TDENS,false>(c,drx,dry,drz,rr2,ha,hb,velrhop1,pressp1,va,vb,pa.w,pb.w,c.visco_f,acc);
+                else       pair2_body<TDENS,true >(c,drx,dry,drz,rr2,ha,hb,velrhop1,pressp1,va,vb,pa.w,pb.w,c.visco_b,acc);
+              }
+            }
+          }
+        }
+#elif P2_MASK==1
         //-Two phases per chunk of up to 32 candidates: (1) check every candidate and record the hits in a per-lane bit mask,
         // (2) evaluate the hits two at a time.  Phase 2 only iterates as long as the lane with most hits needs, so the packed
         // body runs on real pairs (both halves used) instead of on whatever two consecutive candidates happen to be.
