@@ -351,6 +351,9 @@ def main():
                            "timing": "CUDA events on the kernel stream, max over ranks", "wall_ms_per_step": wall / a.steps * 1e3},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks}
     if ss is not None:
+        rep = ss.profile_report()
+        if rep and rank == 0:
+            print("slab phase profile (ms per step, rank 0, includes warm-up and e2e steps): " + json.dumps(rep), file=sys.stderr)
         ss.close()
     else:
         sim.close()

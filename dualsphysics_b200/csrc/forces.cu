@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(F_BS) k_forces_fluid_gather(ForcesArgs g, cons
   const uint32_t npb=ds->npb, np=ds->np;
   const uint32_t p1=npb+blockIdx.x*blockDim.x+threadIdx.x;
   float ace2=0.f, viscmax=0.f;
-  if(p1<np){
+  if(p1<np && B2S_CODE_ISNORMAL(g.code[p1])){   // slab halo ghosts (CODE_PERIODIC) are neighbours only
     const float4 pp1=g.posp[p1];
     const float4 velrhop1=g.velrho[p1];
     const float pressp1=pp1.w;

@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(P2_BS,P2_MINB) k_forces_fluid_pair2(ForcesArgs
   const DivState* ds=g.ds;
   const uint32_t npb=ds->npb, np=ds->np;
   const uint32_t p1=npb+blockIdx.x*blockDim.x+threadIdx.x;
-  const bool valid=(p1<np);
+  // slab halo ghosts (CODE_PERIODIC) are neighbours only: their own sums would be thrown away by the integrator
+  const bool valid=(p1<np && B2S_CODE_ISNORMAL(g.code[p1]));
   const uint32_t plast=np-1u;
   float ace2=0.f, viscmax=0.f;
   float4 pp1=make_float4(0,0,0,0), velrhop1=make_float4(0,0,0,1.f);

@@ -73,6 +73,15 @@ class SlabRank:
         maxbytes = 48 + 48 + 16 + 16 + 32     # largest record csrc/slab.cu can produce (the size varies with the step phase)
         mk = lambda: torch.empty(self.cap_records * maxbytes, dtype=torch.uint8, device=self.dev)  # noqa: E731
         self.send_l, self.send_r, self.recv_l, self.recv_r = mk(), mk(), mk(), mk()
+        self._ext = None
+        self._dt_t = None
+
+    def on_stream(self):
+        """Context that makes the ctx's CUDA stream torch's current stream: NCCL operations issued inside are ordered with
+        the ctx's kernels by stream semantics (no host synchronisation between pack -> send/recv -> unpack)."""
+        if self._ext is None:
+            self._ext = self.torch.cuda.ExternalStream(self.ctx.stream(), device=self.dev)
+        return self.torch.cuda.stream(self._ext)
 
     def pack(self, kind):
         return self.ctx.slab_pack(kind, self.send_l.data_ptr(), self.send_r.data_ptr(), self.cap_records)
@@ -88,11 +97,13 @@ class SlabRank:
 
     def dt_tensor(self):
         """The three dt maxima as an int32 view over the ctx's device memory (zero-copy, via __cuda_array_interface__)."""
-        ptr = self.ctx.slab_dt_buffer()
+        if self._dt_t is None:
+            ptr = self.ctx.slab_dt_buffer()
 
-        class _W:
-            __cuda_array_interface__ = {"shape": (3,), "typestr": "<i4", "data": (ptr, False), "version": 2}
-        return self.torch.as_tensor(_W(), device=self.dev)
+            class _W:
+                __cuda_array_interface__ = {"shape": (3,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+            self._dt_t = self.torch.as_tensor(_W(), device=self.dev)
+        return self._dt_t
 
     def close(self):
         self.sim.close()
@@ -116,40 +127,41 @@ def _exchange_local(ranks, kind):
     return counts
 
 
-def _exchange_dist(rank: SlabRank, kind, dist):
-    """Pack, exchange counts and payloads with the two neighbours over NCCL (batched isend/irecv), unpack."""
+def _exchange_dist(rank, kind, dist):
+    """Pack, exchange counts and payloads with the two neighbours (batched isend/irecv), unpack.  Everything is issued on
+    the ctx's stream (``rank.on_stream()``), so the only host synchronisations are the two that make counts visible to
+    the host: the packed counts (inside b2s_slab_pack) and the neighbours' counts."""
     torch = rank.torch
-    nl_s, nr_s = rank.pack(kind)
-    rb = rank.ctx.slab_record_bytes(kind)
     me, n = rank.rank, rank.nranks
-    cnt_send = torch.tensor([nl_s, nr_s], dtype=torch.int64, device=rank.dev)
-    cnt_recv = torch.zeros(2, dtype=torch.int64, device=rank.dev)
-    ops = []
-    if me > 0:
-        ops += [dist.P2POp(dist.isend, cnt_send[0:1], me - 1), dist.P2POp(dist.irecv, cnt_recv[0:1], me - 1)]
-    if me < n - 1:
-        ops += [dist.P2POp(dist.isend, cnt_send[1:2], me + 1), dist.P2POp(dist.irecv, cnt_recv[1:2], me + 1)]
-    rank.sync()   # the pack kernels run on the ctx stream; NCCL runs on torch's stream
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-    nl_r, nr_r = int(cnt_recv[0].item()), int(cnt_recv[1].item())
-    ops = []
-    if me > 0:
-        if nl_s:
-            ops.append(dist.P2POp(dist.isend, rank.send_l[:nl_s * rb], me - 1))
-        if nl_r:
-            ops.append(dist.P2POp(dist.irecv, rank.recv_l[:nl_r * rb], me - 1))
-    if me < n - 1:
-        if nr_s:
-            ops.append(dist.P2POp(dist.isend, rank.send_r[:nr_s * rb], me + 1))
-        if nr_r:
-            ops.append(dist.P2POp(dist.irecv, rank.recv_r[:nr_r * rb], me + 1))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-    rank.sync()
-    rank.unpack(kind, nl_r, nr_r)
+    with rank.on_stream():
+        nl_s, nr_s = rank.pack(kind)
+        rb = rank.ctx.slab_record_bytes(kind)
+        cnt_send = torch.tensor([nl_s, nr_s], dtype=torch.int64, device=rank.dev)
+        cnt_recv = torch.zeros(2, dtype=torch.int64, device=rank.dev)
+        ops = []
+        if me > 0:
+            ops += [dist.P2POp(dist.isend, cnt_send[0:1], me - 1), dist.P2POp(dist.irecv, cnt_recv[0:1], me - 1)]
+        if me < n - 1:
+            ops += [dist.P2POp(dist.isend, cnt_send[1:2], me + 1), dist.P2POp(dist.irecv, cnt_recv[1:2], me + 1)]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        nl_r, nr_r = (int(v) for v in cnt_recv.tolist())
+        ops = []
+        if me > 0:
+            if nl_s:
+                ops.append(dist.P2POp(dist.isend, rank.send_l[:nl_s * rb], me - 1))
+            if nl_r:
+                ops.append(dist.P2POp(dist.irecv, rank.recv_l[:nl_r * rb], me - 1))
+        if me < n - 1:
+            if nr_s:
+                ops.append(dist.P2POp(dist.isend, rank.send_r[:nr_s * rb], me + 1))
+            if nr_r:
+                ops.append(dist.P2POp(dist.irecv, rank.recv_r[:nr_r * rb], me + 1))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        rank.unpack(kind, nl_r, nr_r)
     return (nl_s, nr_s, nl_r, nr_r)
 
 
@@ -169,6 +181,8 @@ class SlabSimulation:
         self.symplectic = self.ranks[0].symplectic
         self.exchanged_bytes = 0
         self.migrated = 0
+        import os
+        self._prof = [] if (os.environ.get("B2S_SLAB_PROFILE") and dist is not None) else None
         self.cuts = self.ranks[0].cuts
         self._exchange(first=True)
 
@@ -201,10 +215,8 @@ class SlabSimulation:
                 r.sync()
         else:
             r = self.ranks[0]
-            r.sync()
-            t = r.dt_tensor()
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-            r.sync()
+            with r.on_stream():     # ordered after the interaction kernels and before k_dtvariable by the stream itself
+                self.dist.all_reduce(r.dt_tensor(), op=self.dist.ReduceOp.MAX)
 
     def _interaction(self, interstep):
         for r in self.ranks:
@@ -213,22 +225,55 @@ class SlabSimulation:
         for r in self.ranks:
             r.ctx.slab_apply_dt(interstep)
 
+    def _mark(self, name):
+        """B2S_SLAB_PROFILE=1: CUDA events on the ctx stream at the phase boundaries of a step (rank 0 of this process)."""
+        if self._prof is None:
+            return
+        ev = self.torch.cuda.Event(enable_timing=True)
+        with self.ranks[0].on_stream():
+            ev.record()
+        self._prof.append((name, ev))
+
+    def profile_report(self):
+        """Mean milliseconds per phase since construction (None unless B2S_SLAB_PROFILE=1)."""
+        if not self._prof:
+            return None
+        self.torch.cuda.synchronize()
+        acc, cnt = {}, {}
+        for (n0, e0), (n1, e1) in zip(self._prof, self._prof[1:]):
+            if n1 == "begin":
+                continue
+            acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1)
+            cnt[n1] = cnt.get(n1, 0) + 1
+        nsteps = max(cnt.get("step_end", 1), 1)
+        return {k: v / nsteps for k, v in acc.items()}
+
     def step(self, final_exchange=True) -> float:
+        self._mark("begin")
         if self.symplectic:
             self._interaction(L.INTER_SYMPREDICTOR)
+            self._mark("interaction_pre")
             for r in self.ranks:
                 r.ctx.slab_integrate(1)
+            self._mark("integrate_pre")
             self._exchange()
+            self._mark("exchange_mid+celldiv")
             self._interaction(L.INTER_SYMCORRECTOR)
+            self._mark("interaction_corr")
             for r in self.ranks:
                 r.ctx.slab_integrate(2)
+            self._mark("integrate_corr")
         else:
             self._interaction(L.INTER_VERLET)
+            self._mark("interaction")
             for r in self.ranks:
                 r.ctx.slab_integrate(0)
+            self._mark("integrate")
         dts = [r.ctx.slab_step_end() for r in self.ranks]
+        self._mark("step_end")
         if final_exchange:
             self._exchange()
+            self._mark("exchange_end+celldiv")
         return dts[0]
 
     def host_roundtrip_begin(self):
