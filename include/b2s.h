@@ -202,8 +202,10 @@ int b2s_launch_count(b2s_ctx* ctx, uint64_t* launches, int reset);
 /* CUDA stream the ctx launches on (cudaStream_t cast to void*), for external event timing. */
 int b2s_get_stream(b2s_ctx* ctx, void** stream_out);
 /* Selects the fluid interaction kernel variant: 0 = gather (one thread per particle, reference summation order; default),
- * 3 = gather with deferred pair bodies (csrc/forces_defer.cu; experimental, used below 2^26 particles).
- * Both visit neighbours in the same order and are bit-identical.  Other values: B2S_ERR_ARG. */
+ * 3 = gather with deferred pair bodies (csrc/forces_defer.cu; experimental, used below 2^26 particles; bit-identical to 0),
+ * 4 = two hits per lane in packed FP32 with FP16 pre-filter (csrc/forces_pair2.cu; fastest; Wendland + artificial viscosity
+ * without floating bodies, other configurations run variant 0; equal to 0 within summation rounding).
+ * Other values: B2S_ERR_ARG. */
 int b2s_set_interaction_variant(b2s_ctx* ctx, int variant);
 
 /* ---- slab decomposition over several GPUs (no reference counterpart) ----------- */
