@@ -28,6 +28,9 @@ void Bi4Item::set_bool(const std::string& n,bool v){ Bi4Value* x=upsert(values,n
 void Bi4Item::set_int(const std::string& n,int v){ Bi4Value* x=upsert(values,n); x->type=BT_INT; x->i=v; }
 void Bi4Item::set_uint(const std::string& n,unsigned v){ Bi4Value* x=upsert(values,n); x->type=BT_UINT; x->u=v; }
 void Bi4Item::set_ullong(const std::string& n,uint64_t v){ Bi4Value* x=upsert(values,n); x->type=BT_ULLONG; x->u=v; }
+void Bi4Item::set_llong(const std::string& n,int64_t v){ Bi4Value* x=upsert(values,n); x->type=BT_LLONG; x->i=v; }
+void Bi4Item::set_float(const std::string& n,float v){ Bi4Value* x=upsert(values,n); x->type=BT_FLOAT; x->d=v; }
+void Bi4Item::set_float3(const std::string& n,const float v[3]){ Bi4Value* x=upsert(values,n); x->type=BT_FLOAT3; x->d3[0]=v[0]; x->d3[1]=v[1]; x->d3[2]=v[2]; }
 void Bi4Item::set_double(const std::string& n,double v){ Bi4Value* x=upsert(values,n); x->type=BT_DOUBLE; x->d=v; }
 void Bi4Item::set_double3(const std::string& n,const double v[3]){ Bi4Value* x=upsert(values,n); x->type=BT_DOUBLE3; x->d3[0]=v[0]; x->d3[1]=v[1]; x->d3[2]=v[2]; }
 const Bi4Value* Bi4Item::find(const std::string& n)const{ for(auto& v:values)if(v.name==n)return &v; return nullptr; }

@@ -34,6 +34,9 @@ struct Bi4Item {
   void set_int(const std::string& n,int v);
   void set_uint(const std::string& n,unsigned v);
   void set_ullong(const std::string& n,uint64_t v);
+  void set_llong(const std::string& n,int64_t v);
+  void set_float(const std::string& n,float v);
+  void set_float3(const std::string& n,const float v[3]);
   void set_double(const std::string& n,double v);
   void set_double3(const std::string& n,const double v[3]);
   const Bi4Value* find(const std::string& n)const;

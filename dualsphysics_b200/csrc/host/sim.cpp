@@ -23,6 +23,8 @@
 #include <sstream>
 #include <stdexcept>
 #include <algorithm>
+#include <ctime>
+#include <cstdint>
 #include <sys/stat.h>
 
 using namespace b2s;
@@ -43,7 +45,14 @@ struct b2s_sim {
   double caseposmin[3], caseposmax[3];
   unsigned np0;
   std::vector<uint32_t> slab_cuts; uint32_t slab_maxplane;   // slab loading (b2s_sim_load_slab)
-  b2s_sim():slab_maxplane(0),ctx(NULL),timemax(0),timepart(0),timepartnext(0),part(0),nstepsbreak(0),svallsteps(false),svposdouble(false),svdata(true),np0(0){ memset(&prm,0,sizeof(prm)); }
+  std::string runcode, date; unsigned part_nstep0; double part_time0, part_dtmin, part_dtmax;   // PART header / PartInfo statistics
+  b2s_sim():slab_maxplane(0),part_nstep0(0),part_time0(0),part_dtmin(DBL_MAX),part_dtmax(0),ctx(NULL),timemax(0),timepart(0),timepartnext(0),part(0),nstepsbreak(0),svallsteps(false),svposdouble(false),svdata(true),np0(0){
+    memset(&prm,0,sizeof(prm));
+    // RunCode (8 random characters) and Date like JSph::CalcRunCode / fun::GetDateTime
+    const time_t now=time(NULL); char buf[64]; strftime(buf,sizeof(buf),"%d-%m-%Y %H:%M:%S",localtime(&now)); date=buf;
+    static const char cs[]="abcdefghijklmnopqrstuvwxyz0123456789"; unsigned seed=unsigned(now)^unsigned(uintptr_t(this)>>4);
+    for(int k=0;k<8;k++){ seed=seed*1664525u+1013904223u; runcode+=cs[(seed>>16)%36]; }
+  }
 };
 
 static std::string g_host_err;
@@ -420,10 +429,12 @@ static void save_part(b2s_sim* s){
   int r=b2s_download_particles_byid(s->ctx,&n,idp.data(),pos.data(),vel.data(),rho.data());
   if(r)throw std::runtime_error(std::string("download failed: ")+b2s_last_error(s->ctx));
   b2s_info inf; b2s_get_info(s->ctx,&inf);
+  // Item/value order and types follow the reference's files exactly (JPartDataBi4::ConfigBasic/ConfigParticles/AddPartInfo,
+  // JPartDataHead::SaveFile, JSph::AddBasicInfo; checked against reference output by tests/test_part_files.py).
   Bi4Item d("JPartDataBi4");
   const double zero3[3]={0,0,0};
-  d.set_uint("Piece",0); d.set_uint("Npiece",1); d.set_text("RunCode","00000000"); d.set_text("Date","???");
-  d.set_text("AppName","b200sph"); d.set_text("CaseName",s->casename); d.set_bool("Data2d",false); d.set_double("Data2dPosY",0);
+  d.set_uint("Piece",0); d.set_uint("Npiece",1); d.set_text("RunCode",s->runcode); d.set_text("Date",s->date);
+  d.set_text("AppName","b200sph v0.1 (DualSPHysics v5.4 case interface)"); d.set_text("CaseName",s->casename); d.set_bool("Data2d",p.simulate2d!=0); d.set_double("Data2dPosY",0);
   d.set_double3("MapPosMin",p.maprealposmin); d.set_double3("MapPosMax",p.maprealposmax);
   d.set_int("PeriMode",0); d.set_double3("PeriXinc",zero3); d.set_double3("PeriYinc",zero3); d.set_double3("PeriZinc",zero3);
   d.set_int("AxisDiv",0);
@@ -439,7 +450,19 @@ static void save_part(b2s_sim* s){
   pt->set_uint("Cpart",s->part); pt->set_double("TimeStep",inf.timestep); pt->set_uint("Npok",n); pt->set_uint("Nout",p.casenp-n);
   pt->set_uint("Step",inf.nstep); pt->set_double("RunTime",0);
   pt->set_double3("DomainMin",p.maprealposmin); pt->set_double3("DomainMax",p.maprealposmax);
+  pt->set_ullong("NpTotal",p.casenp);
   if(p.tstep==B2S_STEP_SYMPLECTIC)pt->set_double("SymplecticDtPre",inf.symplectic_dtpre);
+  // PartInfo statistics of the interval since the previous PART (JSph::AddBasicInfo, JSph.cpp:2937-2975)
+  const unsigned dsteps=inf.nstep-s->part_nstep0;
+  pt->set_double("dtmean",dsteps? (inf.timestep-s->part_time0)/dsteps: 0.0);
+  pt->set_double("dtmin",dsteps? s->part_dtmin: 0.0); pt->set_double("dtmax",dsteps? s->part_dtmax: 0.0);
+  pt->set_double("timesim",0);
+  pt->set_uint("nct",inf.nct); pt->set_uint("nctsize",inf.nct);
+  pt->set_uint("npsim",inf.np); pt->set_uint("npsize",inf.np); pt->set_uint("npnormal",inf.np); pt->set_uint("npsave",n); pt->set_uint("npnew",0);
+  pt->set_uint("noutpos",inf.npf_out_total); pt->set_uint("noutrho",0); pt->set_uint("noutmov",0);
+  pt->set_uint("npbin",inf.npbok); pt->set_uint("npbout",inf.npb-inf.npbok); pt->set_uint("npf",inf.np-inf.npb); pt->set_uint("npbper",0); pt->set_uint("npfper",0);
+  pt->set_llong("cpualloc",int64_t(cap)*(4+24+12+4));
+  s->part_nstep0=inf.nstep; s->part_time0=inf.timestep; s->part_dtmin=DBL_MAX; s->part_dtmax=0;
   std::vector<float> posf;
   pt->add_array_ext("Idp",BT_UINT,n,idp.data());
   if(s->svposdouble)pt->add_array_ext("Posd",BT_DOUBLE3,n,pos.data());
@@ -449,20 +472,30 @@ static void save_part(b2s_sim* s){
   char fn[64]; snprintf(fn,sizeof(fn),"Part_%04u.bi4",s->part);
   bi4_save(s->dirdata+fn,d,"JPartDataBi4");
   if(s->part==0){
-    // Part_Head.ibi4 (JPartDataHead): same head values + MK blocks
+    // Part_Head.ibi4 (JPartDataHead::SaveFile, JPartDataHead.cpp): head values + MkBlocks
     Bi4Item h("JPartDataHead");
-    h.set_text("AppName","b200sph"); h.set_text("CaseName",s->casename); h.set_bool("Data2d",false); h.set_double("Data2dPosY",0);
+    h.set_uint("FmtVersion",180324);
+    h.set_text("AppName","b200sph v0.1 (DualSPHysics v5.4 case interface)"); h.set_text("Date",s->date); h.set_text("RunCode",s->runcode);
+    h.set_text("CaseName",s->casename); h.set_bool("Data2d",p.simulate2d!=0); h.set_double("Data2dPosY",0);
+    h.set_uint("Npiece",1); h.set_uint("FirstPart",0);
     h.set_double3("CasePosMin",s->caseposmin); h.set_double3("CasePosMax",s->caseposmax); h.set_bool("NpDynamic",false); h.set_bool("ReuseIds",false);
     h.set_double3("MapPosMin",p.maprealposmin); h.set_double3("MapPosMax",p.maprealposmax);
-    h.set_double("Dp",s->casedp); h.set_double("H",s->caseh); h.set_double("B",s->caseb); h.set_double("Rhop0",s->caserhop0); h.set_double("Gamma",s->casegamma);
+    h.set_int("PeriMode",0); h.set_double3("PeriXinc",zero3); h.set_double3("PeriYinc",zero3); h.set_double3("PeriZinc",zero3);
+    h.set_uint("ViscoType",unsigned(p.tvisco)); h.set_float("ViscoValue",p.visco); h.set_float("ViscoBoundFactor",p.viscoboundfactor);
+    h.set_bool("Symmetry",false); h.set_bool("Splitting",false);
+    h.set_double("Dp",s->casedp); h.set_double("H",s->caseh); h.set_double("B",s->caseb); h.set_double("Gamma",s->casegamma); h.set_double("RhopZero",s->caserhop0);
     h.set_double("MassBound",s->casemassb); h.set_double("MassFluid",s->casemassf);
-    h.set_uint("MkListSize",unsigned(s->blocks.size()));
+    h.set_float3("Gravity",p.gravity);
+    h.set_ullong("CaseNp",p.casenp); h.set_ullong("CaseNfixed",p.casenfixed); h.set_ullong("CaseNmoving",p.casenmoving);
+    h.set_ullong("CaseNfloat",p.casenfloat); h.set_ullong("CaseNfluid",p.casenfluid);
+    Bi4Item* mk=h.add_item("MkBlocks");
+    mk->set_uint("Count",unsigned(s->blocks.size()));
     unsigned c=0;
     for(auto& b:s->blocks){
       char bn[32]; snprintf(bn,sizeof(bn),"MkBlock_%03u",c++);
-      Bi4Item* it=h.add_item(bn);
+      Bi4Item* it=mk->add_item(bn);
       static const char* tn[4]={"Fixed","Moving","Floating","Fluid"};
-      it->set_text("Type",tn[b.type]); it->set_uint("Mk",b.mk); it->set_uint("MkType",b.mktype); it->set_uint("Begin",b.begin); it->set_uint("Count",b.count);
+      it->set_text("Type",tn[b.type]); it->set_uint("Mk",b.mk); it->set_uint("MkType",b.mktype); it->set_uint("Count",b.count);
     }
     bi4_save(s->dirdata+"Part_Head.ibi4",h,"JPartDataHead");
   }
@@ -540,6 +573,7 @@ extern "C" int b2s_sim_run(b2s_sim* s,uint32_t nsteps_break,double* time_out,uin
       if(r){ g_host_err=b2s_last_error(s->ctx); return r; }
       r=b2s_get_info(s->ctx,&inf); if(r){ g_host_err=b2s_last_error(s->ctx); return r; }
       t=inf.timestep; nstep++;
+      s->part_dtmin=std::min(s->part_dtmin,dt); s->part_dtmax=std::max(s->part_dtmax,dt);
       if(save && t>=s->timepartnext){
         save_part(s); s->part++;
         if(s->svallsteps)s->timepartnext=t;
