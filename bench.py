@@ -196,7 +196,8 @@ def main():
         sim = dsb.Simulation(case, options=OPTIONS, device=dev)
         ctx = sim.ctx
     else:
-        ss = slab.SlabSimulation(case, options=OPTIONS, nranks=world, dist=dist, device=dev)
+        ss = slab.SlabSimulation(case, options=OPTIONS, nranks=world, dist=dist, device=dev,
+                                 recut_every=int(os.environ.get("B2S_RECUT_EVERY", "0")))
         sim = ss.ranks[0].sim
         ctx = ss.ranks[0].ctx
     ctx.set_variant(a.variant)

@@ -159,6 +159,49 @@ extern "C" int b2s_slab_config(b2s_ctx* ctx, int rank, int nranks, uint32_t cx_b
   return b2s_sync_info(ctx);
 }
 
+// ---- re-cutting (dynamic load balance): histogram of owned particles per x cell plane, new slab range -------------------
+__global__ void __launch_bounds__(S_BS) k_slab_hist(const DivState* __restrict__ ds, const typecode* __restrict__ code, const uint32_t* __restrict__ dcell,
+  uint32_t dcc, uint32_t ncx, uint32_t* hist)
+{
+  const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
+  if(p>=ds->np)return;
+  if(B2S_CODE_SPECIAL(code[p])!=B2S_CODE_NORMAL)return;
+  const uint32_t rc=dcell[p];
+  if(rc==B2S_DCEL_MAPOUT)return;
+  const uint32_t cx=B2S_DCEL_CELLX(dcc,rc);
+  // particles of a warp mostly share a few planes: aggregate equal planes before the atomic
+  const uint32_t peers=__match_any_sync(__activemask(),cx);
+  if((__ffs(peers)-1)==int(threadIdx.x&31) && cx<ncx)atomicAdd(&hist[cx],uint32_t(__popc(peers)));
+}
+extern "C" int b2s_slab_histogram(b2s_ctx* ctx, void* dev_u32_ncx){
+  if(!ctx || !ctx->slab_on || !dev_u32_ncx)return B2S_ERR_ARG;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  const uint32_t ncx=ctx->prm.domcells[0];
+  B2S_CUDA(ctx,cudaMemsetAsync(dev_u32_ncx,0,size_t(ncx)*4,ctx->stream));
+  if(ctx->np_host){
+    k_slab_hist<<<b2s_blocks(ctx->np_host,S_BS),S_BS,0,ctx->stream>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,ncx,(uint32_t*)dev_u32_ncx); B2S_LAUNCHED(ctx);
+  }
+  B2S_CUDA(ctx,cudaGetLastError());
+  return B2S_OK;
+}
+__global__ void __launch_bounds__(S_BS) k_slab_drop_ghosts(const DivState* __restrict__ ds, typecode* code){
+  const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
+  if(p<ds->np && B2S_CODE_SPECIAL(code[p])==B2S_CODE_PERIODIC)code[p]=typecode(B2S_CODE_SETNORMAL(code[p])|B2S_CODE_OUTIGNORE);
+}
+extern "C" int b2s_slab_drop_ghosts(b2s_ctx* ctx){
+  if(!ctx || !ctx->slab_on)return B2S_ERR_ARG;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  if(ctx->np_host){ k_slab_drop_ghosts<<<b2s_blocks(ctx->np_host,S_BS),S_BS,0,ctx->stream>>>(ctx->div,ctx->cur.code); B2S_LAUNCHED(ctx); }
+  ctx->bound_changed=true;
+  B2S_CUDA(ctx,cudaGetLastError());
+  return B2S_OK;
+}
+extern "C" int b2s_slab_set_range(b2s_ctx* ctx, uint32_t cx_begin, uint32_t cx_end){
+  if(!ctx || !ctx->slab_on || cx_begin>=cx_end || cx_end>ctx->prm.domcells[0])return B2S_ERR_ARG;
+  ctx->slab_cxa=cx_begin; ctx->slab_cxb=cx_end;
+  return B2S_OK;
+}
+
 extern "C" int b2s_slab_record_bytes(b2s_ctx* ctx, int kind, uint32_t* bytes){
   if(!ctx || !bytes || kind<0 || kind>1)return B2S_ERR_ARG;
   *bytes=slab_layout(ctx,kind).bytes;

@@ -91,7 +91,7 @@ ABI_SYMBOLS = [
     "b2s_compute_symplectic_corr", "b2s_compute_step", "b2s_run_steps", "b2s_add_motion_rectsinu",
     "b2s_move_linear", "b2s_set_floatings", "b2s_get_floatings", "b2s_count_pairs", "b2s_time_interaction",
     "b2s_launch_count", "b2s_get_stream", "b2s_set_interaction_variant", "b2s_slab_config",
-    "b2s_slab_record_bytes", "b2s_slab_pack", "b2s_slab_unpack", "b2s_slab_dt_buffer", "b2s_slab_forces",
+    "b2s_slab_histogram", "b2s_slab_set_range", "b2s_slab_drop_ghosts", "b2s_slab_record_bytes", "b2s_slab_pack", "b2s_slab_unpack", "b2s_slab_dt_buffer", "b2s_slab_forces",
     "b2s_slab_apply_dt", "b2s_slab_integrate", "b2s_slab_step_end",
     "b2s_sim_load", "b2s_sim_load_slab", "b2s_sim_slab_info", "b2s_sim_free", "b2s_sim_ctx", "b2s_sim_params", "b2s_sim_save_part", "b2s_sim_run",
     "b2s_host_last_error",
@@ -146,6 +146,9 @@ def load_library():
     lib.b2s_get_stream.argtypes = [vp, C.POINTER(vp)]
     lib.b2s_set_interaction_variant.argtypes = [vp, C.c_int]
     lib.b2s_slab_config.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32]
+    lib.b2s_slab_histogram.argtypes = [vp, vp]
+    lib.b2s_slab_set_range.argtypes = [vp, C.c_uint32, C.c_uint32]
+    lib.b2s_slab_drop_ghosts.argtypes = [vp]
     lib.b2s_slab_record_bytes.argtypes = [vp, C.c_int, u32p]
     lib.b2s_slab_pack.argtypes = [vp, C.c_int, vp, vp, C.c_uint32, u32p, u32p]
     lib.b2s_slab_unpack.argtypes = [vp, C.c_int, vp, C.c_uint32]
@@ -298,6 +301,15 @@ class Context:
     # ---- slab decomposition (include/b2s.h, "slab" section) ----
     def slab_config(self, rank, nranks, cx_begin, cx_end):
         self._chk(self._lib.b2s_slab_config(self._h, rank, nranks, cx_begin, cx_end))
+
+    def slab_histogram(self, dev_ptr):
+        self._chk(self._lib.b2s_slab_histogram(self._h, dev_ptr))
+
+    def slab_set_range(self, cx_begin, cx_end):
+        self._chk(self._lib.b2s_slab_set_range(self._h, cx_begin, cx_end))
+
+    def slab_drop_ghosts(self):
+        self._chk(self._lib.b2s_slab_drop_ghosts(self._h))
 
     def slab_record_bytes(self, kind):
         b = C.c_uint32(0)

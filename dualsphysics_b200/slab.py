@@ -22,7 +22,13 @@ HALO, MIGRANT = 0, 1
 
 def compute_cuts(cellx: np.ndarray, ncells_x: int, nranks: int) -> list:
     """Cut planes [c0=0, c1, ..., cN=ncells_x] balancing the particle count per slab (prefix sum over x cell planes)."""
-    hist = np.bincount(np.asarray(cellx, np.int64), minlength=ncells_x).astype(np.int64)
+    return compute_cuts_hist(np.bincount(np.asarray(cellx, np.int64), minlength=ncells_x), nranks)
+
+
+def compute_cuts_hist(hist, nranks: int) -> list:
+    """Same from the histogram of particles per x cell plane (the form the re-cut uses after an all-reduce)."""
+    hist = np.asarray(hist, np.int64)
+    ncells_x = len(hist)
     cum = np.cumsum(hist)
     total = int(cum[-1])
     cuts = [0]
@@ -171,7 +177,7 @@ class SlabSimulation:
     ``dist`` = torch.distributed (already initialised, NCCL): this process owns ONE rank.
     ``dist`` = None: all ranks are created in this process on ``device`` (LocalTransport, for tests)."""
 
-    def __init__(self, casepath, options="", nranks=1, dist=None, device=0):
+    def __init__(self, casepath, options="", nranks=1, dist=None, device=0, recut_every=0):
         import torch
         self.torch, self.dist = torch, dist
         if dist is None:
@@ -181,6 +187,8 @@ class SlabSimulation:
         self.symplectic = self.ranks[0].symplectic
         self.exchanged_bytes = 0
         self.migrated = 0
+        self.recut_every = int(recut_every)     # >0: rebalance the cuts every that many steps (dynamic load balance)
+        self.nstep = 0
         import os
         self._prof = [] if (os.environ.get("B2S_SLAB_PROFILE") and dist is not None) else None
         self.cuts = self.ranks[0].cuts
@@ -270,11 +278,63 @@ class SlabSimulation:
                 r.ctx.slab_integrate(0)
             self._mark("integrate")
         dts = [r.ctx.slab_step_end() for r in self.ranks]
+        self.nstep += 1
         self._mark("step_end")
         if final_exchange:
-            self._exchange()
+            if self.recut_every and self.nstep % self.recut_every == 0:
+                self._exchange()          # settle this step's migrants against the old cuts first
+                self.recut()
+            else:
+                self._exchange()
             self._mark("exchange_end+celldiv")
         return dts[0]
+
+    def recut(self, cuts=None):
+        """Dynamic load balance: new cut planes from the global particle histogram along x (all-reduced), then the particles
+        outside their slab's new range migrate (one neighbour hop per round, repeated until nobody has migrants left), then
+        halos + divide.  Call between steps.  ``cuts`` overrides the balanced cuts (tests)."""
+        torch = self.torch
+        ncx = int(self.ranks[0].p.domcells[0])
+        nranks = self.ranks[0].nranks
+        for r in self.ranks:                      # the halos are rebuilt at the end: the ghosts of the last exchange go
+            r.ctx.slab_drop_ghosts()
+            r.ctx.celldiv()
+        if cuts is None:
+            hists = []
+            for r in self.ranks:
+                h = torch.zeros(ncx, dtype=torch.int32, device=r.dev)
+                with r.on_stream():
+                    r.ctx.slab_histogram(h.data_ptr())
+                    if self.dist is not None:
+                        self.dist.all_reduce(h, op=self.dist.ReduceOp.SUM)
+                hists.append(h)
+            for r in self.ranks:
+                r.sync()
+            total = hists[0].cpu().numpy().astype(np.int64) if self.dist is not None else sum(h.cpu().numpy().astype(np.int64) for h in hists)
+            cuts = compute_cuts_hist(total, nranks)
+        self.cuts = [int(c) for c in cuts]
+        for r in self.ranks:
+            r.cuts = self.cuts
+            r.cxa, r.cxb = self.cuts[r.rank], self.cuts[r.rank + 1]
+            r.ctx.slab_set_range(r.cxa, r.cxb)
+        for _ in range(nranks):                    # a particle travels at most nranks-1 hops
+            if self.dist is None:
+                c = _exchange_local(self.ranks, MIGRANT)
+                moved = sum(a + b for a, b in c)
+            else:
+                c = _exchange_dist(self.ranks[0], MIGRANT, self.dist)
+                t = torch.tensor([c[0] + c[1]], dtype=torch.int64, device=self.ranks[0].dev)
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+                moved = int(t.item())
+            self.migrated += moved if self.dist is None else c[0] + c[1]
+            if moved == 0:
+                break
+            for r in self.ranks:                   # forwarded particles must be (re)flagged against the new range
+                r.ctx.celldiv()
+        else:
+            raise RuntimeError("recut: migrants left after nranks rounds")
+        self._exchange(first=True)
+        return self.cuts
 
     def host_roundtrip_begin(self):
         """After ``step(final_exchange=False)``: drop the ghosts (they were marked by the integrator) so that a download

@@ -230,6 +230,13 @@ int b2s_slab_dt_buffer(b2s_ctx* ctx, void** dev_u32x3);
  *   b2s_slab_apply_dt   = DtVariable from the (all-reduced) maxima; interstep as in b2s_interaction
  *   b2s_slab_integrate  = mode 0 ComputeVerlet, 1 ComputeSymplecticPre, 2 ComputeSymplecticCorr with the device dt
  *   b2s_slab_step_end   = SymplecticDtPre=min(dt_p,dt_c), TimeStep+=dt, Nstep++ ; returns dt (one host sync) */
+/* Re-cutting (dynamic load balance): b2s_slab_histogram counts the owned particles per x cell plane of the GLOBAL grid into
+ * dev_u32_ncx[domcells[0]] (all-reduce it with SUM, derive new cuts), b2s_slab_set_range installs the new [cx_begin,cx_end);
+ * the particles now outside leave through the normal migrant exchange (repeat it until no rank has migrants left). */
+int b2s_slab_histogram(b2s_ctx* ctx, void* dev_u32_ncx);
+int b2s_slab_set_range(b2s_ctx* ctx, uint32_t cx_begin, uint32_t cx_end);
+/* Marks the halo ghosts of the last exchange for removal by the next divide (needed when halos are rebuilt between steps). */
+int b2s_slab_drop_ghosts(b2s_ctx* ctx);
 int b2s_slab_forces(b2s_ctx* ctx, int interstep);
 int b2s_slab_apply_dt(b2s_ctx* ctx, int interstep);
 int b2s_slab_integrate(b2s_ctx* ctx, int mode);

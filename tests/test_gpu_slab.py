@@ -81,6 +81,37 @@ def test_slab_migration(options, tmp_path, built_lib):
     ss.close(); ref.close()
 
 
+def test_slab_recut(tmp_path, built_lib):
+    """Re-cutting between steps: forced cuts that move a cut by several planes (particles travel across a whole slab in
+    two hops), then balanced cuts from the all-reduced histogram; the union of the slabs must stay the particle set of the
+    single-context run and the state must agree as in the migration test."""
+    H.write_case(tmp_path, dp=0.04)
+    case = str(tmp_path / "Case")
+    options = "-symplectic -cellmode:half"
+    ref = dsb.Simulation(case, options=options)
+    ss = slab.SlabSimulation(case, options=options, nranks=3, dist=None)
+    c0 = list(ss.cuts)
+    n0 = ref.ctx.info().np
+    for s in range(30):
+        ref.ctx.compute_step(); ss.step()
+        if s == 9:    # squeeze the middle slab to one plane on the far side: everything it owned moves two slabs over
+            forced = [c0[0], c0[2] + 2, c0[2] + 3, c0[3]]
+            assert ss.recut(cuts=forced) == forced
+            assert sum(ss.owned_counts()) == n0
+        if s == 19:
+            balanced = ss.recut()
+            oc = np.array(ss.owned_counts(), np.float64)
+            assert sum(ss.owned_counts()) == n0 and oc.max() / oc.mean() < 1.5, (balanced, oc)
+    ids, pos, vr = ss.gather_byid()
+    rid = ref.ctx.array("idp"); o = np.argsort(rid, kind="stable")
+    assert np.array_equal(ids, rid[o])
+    epos = float(np.max(np.abs(pos - ref.ctx.array("pos")[o])))
+    evr = H.rel_err(vr, ref.ctx.array("velrho")[o])
+    print(f"\n[slab recut] cuts {c0} -> {ss.cuts} migrated={ss.migrated} owned={ss.owned_counts()} pos_err={epos:.3e} velrho_err={evr:.3e}")
+    assert ss.migrated > 0 and epos < 1e-6 and evr < 1e-4
+    ss.close(); ref.close()
+
+
 def test_slab_unsupported_is_loud(tmp_path, built_lib):
     H.write_case(tmp_path, dp=0.05, floating_box=(0.15, 0.25, 0.2, 0.1, 0.15, 0.1), floating_rel_density=0.5)
     with pytest.raises(dsb.B2SError):
