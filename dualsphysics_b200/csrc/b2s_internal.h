@@ -136,7 +136,7 @@ struct b2s_ctx {
   bool bound_changed;
   uint32_t verletstep;          // JSphGpu::VerletStep (host counter)
   // floatings
-  uint32_t ftcount; std::vector<b2s_floating> fts; float* ft_massp_dev; float* ft_sums_dev; float* ft_sums_h;
+  uint32_t ftcount; std::vector<b2s_floating> fts; float* ft_massp_dev; float* ft_sums_dev; float* ft_allsums_dev; float* ft_sums_h;
   void* ft_dev; // device copy of per-floating update data
   std::vector<Motion> motions;
   // slab decomposition (slab.cu)

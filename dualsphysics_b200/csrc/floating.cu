@@ -24,7 +24,7 @@ struct FtDev {
 // ---- level 1: per-block partial sums (fixed tree order -> deterministic) ------------------------------------------
 __global__ void __launch_bounds__(FT_BS) k_ft_sum_blocks(const FtDev* __restrict__ fts, uint32_t cf, const DivState* __restrict__ ds,
   const uint32_t* __restrict__ ridp, uint32_t casenfixed, const double2* __restrict__ posxy, const double* __restrict__ posz,
-  const float4* __restrict__ acear, float* __restrict__ partials)
+  const typecode* __restrict__ code, const float4* __restrict__ acear, float* __restrict__ partials)
 {
   __shared__ float sh[6][FT_BS/32];
   const b2s_floating& fo=fts[cf].f;
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(FT_BS) k_ft_sum_blocks(const FtDev* __restrict
   float v[6]={0,0,0,0,0,0};
   if(i<fo.count){
     const uint32_t p=ridp[fo.begin-casenfixed+i];
-    if(p<ds->np){
+    if(p<ds->np && B2S_CODE_ISNORMAL(code[p])){   // slab mode: halo ghosts belong to the neighbour's sum
       const float4 a=acear[p];
       const double2 xy=posxy[p];
       const float dx=float(xy.x-fo.center[0]), dy=float(xy.y-fo.center[1]), dz=float(posz[p]-fo.center[2]);
@@ -62,17 +62,19 @@ __device__ __forceinline__ void ft_constraints(int con,float* lin,float* ang){
 }
 
 // ---- level 2 + JSph::FtComputeAceVel on the device: one block per call, thread 0..5 finish the sums --------------------
-__global__ void k_ft_compute(FtDev* fts, uint32_t cf, uint32_t nblocks, const float* __restrict__ partials, const StepState* __restrict__ st,
-  int predictor, double ftpause, const __grid_constant__ DevCte c)
-{
-  __shared__ float sums[6];
+__global__ void k_ft_reduce(uint32_t cf, uint32_t nblocks, const float* __restrict__ partials, float* __restrict__ allsums){
   if(threadIdx.x<6){
     float s=0;
     for(uint32_t b=0;b<nblocks;b++)s+=partials[size_t(b)*6+threadIdx.x];
-    sums[threadIdx.x]=s;
+    allsums[size_t(cf)*6+threadIdx.x]=s;      // slab mode: all-reduced (SUM) over the ranks before k_ft_compute
   }
-  __syncthreads();
+}
+__global__ void k_ft_compute(FtDev* fts, uint32_t cf, const float* __restrict__ allsums, const StepState* __restrict__ st,
+  int predictor, double ftpause, const __grid_constant__ DevCte c)
+{
   if(threadIdx.x)return;
+  float sums[6];
+  for(int k=0;k<6;k++)sums[k]=allsums[size_t(cf)*6+k];
   FtDev& d=fts[cf];
   b2s_floating& fo=d.f;
   for(int k=0;k<6;k++)d.sums[k]=sums[k];
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(FT_BS) k_ft_update(const FtDev* __restrict__ f
   const uint32_t i=blockIdx.x*blockDim.x+threadIdx.x;
   if(i>=d.f.count || st->timestep<ftpause)return;
   const uint32_t p=ridp[d.f.begin-casenfixed+i];
-  if(p>=ds->np)return;
+  if(p>=ds->np || !B2S_CODE_ISNORMAL(code[p]))return;   // not on this rank, or a halo ghost (frozen)
   const double dt=(predictor? st->dt*.5: st->dt);
   float4 vr=velrho[p];
   double2 xy=posxy[p]; double z=posz[p];
@@ -156,16 +158,25 @@ __global__ void k_ft_commit(FtDev* fts, uint32_t ftcount, const StepState* __res
   for(int k=0;k<3;k++){ d.f.center[k]=d.ncenter[k]; d.f.fvel[k]=d.nvel[k]; d.f.fomega[k]=d.nomega[k]; }
 }
 
-int b2s_floating_impl(b2s_ctx* ctx, double, bool predictor, bool){
-  if(!ctx->ftcount)return B2S_OK;
+// phase 1: sums of this context's particles into ft_allsums[6*ftcount]; phase 2: rigid-body algebra + particle update
+static int ft_sums(b2s_ctx* ctx){
+  cudaStream_t s=ctx->stream;
+  FtDev* fts=(FtDev*)ctx->ft_dev;
+  for(uint32_t cf=0;cf<ctx->ftcount;cf++){
+    const uint32_t nb=b2s_blocks(ctx->fts[cf].count,FT_BS);
+    k_ft_sum_blocks<<<nb,FT_BS,0,s>>>(fts,cf,ctx->div,ctx->ridp,ctx->prm.casenfixed,ctx->cur.posxy,ctx->cur.posz,ctx->cur.code,ctx->acear,ctx->ft_sums_dev); B2S_LAUNCHED(ctx);
+    k_ft_reduce<<<1,32,0,s>>>(cf,nb,ctx->ft_sums_dev,ctx->ft_allsums_dev); B2S_LAUNCHED(ctx);
+  }
+  B2S_CUDA(ctx,cudaGetLastError());
+  return B2S_OK;
+}
+static int ft_apply(b2s_ctx* ctx, bool predictor){
   cudaStream_t s=ctx->stream;
   FtDev* fts=(FtDev*)ctx->ft_dev;
   const double ftpause=ctx->prm.ftpause;
   for(uint32_t cf=0;cf<ctx->ftcount;cf++){
-    const uint32_t cnt=ctx->fts[cf].count;
-    const uint32_t nb=b2s_blocks(cnt,FT_BS);
-    k_ft_sum_blocks<<<nb,FT_BS,0,s>>>(fts,cf,ctx->div,ctx->ridp,ctx->prm.casenfixed,ctx->cur.posxy,ctx->cur.posz,ctx->acear,ctx->ft_sums_dev); B2S_LAUNCHED(ctx);
-    k_ft_compute<<<1,32,0,s>>>(fts,cf,nb,ctx->ft_sums_dev,ctx->step,predictor? 1: 0,ftpause,ctx->cte); B2S_LAUNCHED(ctx);
+    const uint32_t nb=b2s_blocks(ctx->fts[cf].count,FT_BS);
+    k_ft_compute<<<1,32,0,s>>>(fts,cf,ctx->ft_allsums_dev,ctx->step,predictor? 1: 0,ftpause,ctx->cte); B2S_LAUNCHED(ctx);
     k_ft_update<<<nb,FT_BS,0,s>>>(fts,cf,ctx->div,ctx->step,predictor? 1: 0,ftpause,ctx->ridp,ctx->prm.casenfixed,ctx->cur.posxy,ctx->cur.posz,
       ctx->cur.velrho,ctx->cur.dcell,ctx->cur.code,ctx->cte); B2S_LAUNCHED(ctx);
   }
@@ -173,13 +184,35 @@ int b2s_floating_impl(b2s_ctx* ctx, double, bool predictor, bool){
   B2S_CUDA(ctx,cudaGetLastError());
   return B2S_OK;
 }
+int b2s_floating_impl(b2s_ctx* ctx, double, bool predictor, bool){
+  if(!ctx->ftcount)return B2S_OK;
+  int r=ft_sums(ctx); if(r)return r;
+  return ft_apply(ctx,predictor);
+}
+// Slab mode (include/b2s.h): the sums of every rank are all-reduced (SUM) between the two calls, every rank then does the
+// same rigid-body algebra on the same numbers and moves the floating particles it owns.
+extern "C" int b2s_slab_ft_sums(b2s_ctx* ctx, void** dev_f32, uint32_t* count){
+  if(!ctx || !dev_f32 || !count)return B2S_ERR_ARG;
+  *dev_f32=NULL; *count=0;
+  if(!ctx->ftcount)return B2S_OK;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  int r=ft_sums(ctx); if(r)return r;
+  *dev_f32=(void*)ctx->ft_allsums_dev; *count=6u*ctx->ftcount;
+  return B2S_OK;
+}
+extern "C" int b2s_slab_ft_apply(b2s_ctx* ctx, int predictor){
+  if(!ctx)return B2S_ERR_ARG;
+  if(!ctx->ftcount)return B2S_OK;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  return ft_apply(ctx,predictor!=0);
+}
 
 extern "C" int b2s_set_floatings(b2s_ctx* ctx, uint32_t ftcount, const b2s_floating* fin){
   if(!ctx || (ftcount && !fin))return B2S_ERR_ARG;
   if(ftcount>2047)return b2s_fail(ctx,B2S_ERR_ARG,"too many floating bodies");
   B2S_CUDA(ctx,cudaSetDevice(ctx->device));
-  cudaFree(ctx->ft_dev); cudaFree(ctx->ft_massp_dev); cudaFree(ctx->ft_sums_dev);
-  ctx->ft_dev=NULL; ctx->ft_massp_dev=NULL; ctx->ft_sums_dev=NULL;
+  cudaFree(ctx->ft_dev); cudaFree(ctx->ft_massp_dev); cudaFree(ctx->ft_sums_dev); cudaFree(ctx->ft_allsums_dev);
+  ctx->ft_dev=NULL; ctx->ft_massp_dev=NULL; ctx->ft_sums_dev=NULL; ctx->ft_allsums_dev=NULL;
   ctx->ftcount=ftcount; ctx->fts.assign(fin,fin+ftcount);
   if(!ftcount)return B2S_OK;
   std::vector<FtDev> h(ftcount); std::vector<float> massp(ftcount);
@@ -193,6 +226,7 @@ extern "C" int b2s_set_floatings(b2s_ctx* ctx, uint32_t ftcount, const b2s_float
   B2S_CUDA(ctx,cudaMalloc(&ctx->ft_dev,sizeof(FtDev)*ftcount));
   B2S_CUDA(ctx,cudaMalloc((void**)&ctx->ft_massp_dev,sizeof(float)*ftcount));
   B2S_CUDA(ctx,cudaMalloc((void**)&ctx->ft_sums_dev,sizeof(float)*6*(size_t(b2s_blocks(maxcount,FT_BS))+1)));
+  B2S_CUDA(ctx,cudaMalloc((void**)&ctx->ft_allsums_dev,sizeof(float)*6*size_t(ftcount)));
   B2S_CUDA(ctx,cudaMemcpy(ctx->ft_dev,h.data(),sizeof(FtDev)*ftcount,cudaMemcpyHostToDevice));
   B2S_CUDA(ctx,cudaMemcpy(ctx->ft_massp_dev,massp.data(),sizeof(float)*ftcount,cudaMemcpyHostToDevice));
   return B2S_OK;

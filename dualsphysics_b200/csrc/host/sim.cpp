@@ -256,7 +256,7 @@ static void load_case(b2s_sim* s,const std::string& options){
 
 // Balanced cut planes along x: prefix sum of the particles per x cell plane, every cut at the plane whose cumulative count
 // is nearest to r*Np/G (the same rule as dualsphysics_b200/slab.py compute_cuts; tests compare both).
-static std::vector<uint32_t> slab_compute_cuts(const std::vector<uint64_t>& hist,int nranks){
+static std::vector<uint32_t> slab_compute_cuts(const std::vector<uint64_t>& hist,int nranks,uint32_t minw){
   const uint32_t ncx=uint32_t(hist.size());
   std::vector<uint64_t> cum(ncx); uint64_t t=0; for(uint32_t i=0;i<ncx;i++){ t+=hist[i]; cum[i]=t; }
   std::vector<uint32_t> cuts; cuts.push_back(0);
@@ -265,8 +265,8 @@ static std::vector<uint32_t> slab_compute_cuts(const std::vector<uint64_t>& hist
     uint32_t i=0; while(i<ncx && double(cum[i])<target)i++;      // searchsorted(cum,target,'left')
     uint32_t c=i+1;
     if(c>=2 && c-1<ncx && fabs(double(cum[c-2])-target)<fabs(double(cum[c-1])-target))c--;
-    if(c<cuts.back()+1)c=cuts.back()+1;
-    if(c>ncx-uint32_t(nranks-r))c=ncx-uint32_t(nranks-r);
+    if(c<cuts.back()+minw)c=cuts.back()+minw;                          // a slab is at least as wide as the halo (scelldiv planes)
+    if(c>ncx-uint32_t(nranks-r)*minw)c=ncx-uint32_t(nranks-r)*minw;
     cuts.push_back(c);
   }
   cuts.push_back(ncx);
@@ -350,19 +350,25 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   s->casemassb=data->get_double("MassBound",p.massbound); s->casemassf=data->get_double("MassFluid",p.massfluid);
   int r=b2s_config_finalize(&p);
   if(r)throw std::runtime_error(std::string("configuration failed: ")+b2s_error_string(r));
+  // radius of every floating body = max distance particle-centre (JSph::InitFloatings), from the FULL particle set
+  std::vector<float> ftradius;
+  for(auto& b:s->blocks)if(b.type==2){
+    double r2max=0;
+    for(unsigned i=0;i<np;i++)if(idp[i]>=b.begin && idp[i]<b.begin+b.count){ double d2=0; for(int k=0;k<3;k++){ const double d=pos[size_t(i)*3+k]-b.center[k]; d2+=d*d; } r2max=std::max(r2max,d2); }
+    ftradius.push_back(float(sqrt(r2max)));
+  }
   // slab loading: only the particles of [cuts[rank],cuts[rank+1]) reach the device; capacity is sized for the slab
   unsigned npsel=np;
   std::vector<uint32_t> sel_idp;
   if(slab_nranks>0){
-    if(p.casenfloat)throw std::runtime_error("floating bodies are single-GPU only in this round");
     if(p.tboundary==B2S_BC_MDBC)throw std::runtime_error("mDBC is single-GPU only in this round");
     const uint32_t ncx=p.domcells[0];
-    if(uint32_t(slab_nranks)>ncx)throw std::runtime_error("more slabs than cell planes along x");
+    if(uint32_t(slab_nranks)*uint32_t(p.scelldiv)>ncx)throw std::runtime_error("more slabs than the cell planes along x allow (a slab is at least scelldiv planes wide)");
     const double sc=double(p.scell);
     std::vector<uint32_t> cx(np);
     std::vector<uint64_t> hist(ncx,0);
     for(unsigned i=0;i<np;i++){ const double d=(pos[size_t(i)*3]-p.domposmin[0])/sc; uint32_t c=(d<0? 0u: uint32_t(d)); if(c>=ncx)c=ncx-1; cx[i]=c; hist[c]++; }
-    s->slab_cuts=slab_compute_cuts(hist,slab_nranks);
+    s->slab_cuts=slab_compute_cuts(hist,slab_nranks,uint32_t(p.scelldiv));
     s->slab_maxplane=uint32_t(*std::max_element(hist.begin(),hist.end()));
     const uint32_t ca=s->slab_cuts[slab_rank], cb=s->slab_cuts[slab_rank+1];
     unsigned w=0;
@@ -377,19 +383,17 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   }
   r=b2s_create(&p,device,npsel+extra_capacity,&s->ctx);
   if(r)throw std::runtime_error(std::string("b2s_create failed: ")+b2s_error_string(r));
-  // floating bodies (JSph::InitFloatings subset, JSph.cpp:1190-1290)
+  // floating bodies (JSph::InitFloatings subset, JSph.cpp:1190-1290); the radii were taken from the full particle set above
   if(p.casenfloat){
     std::vector<b2s_floating> fts;
+    size_t kf=0;
     for(auto& b:s->blocks)if(b.type==2){
       b2s_floating f; memset(&f,0,sizeof(f));
       f.begin=b.begin; f.count=b.count; f.mass=float(b.massbody); f.massp=float(b.masspart);
       f.constraints=(b.transfree[0]?0:1)|(b.transfree[1]?0:2)|(b.transfree[2]?0:4)|(b.rotfree[0]?0:8)|(b.rotfree[1]?0:16)|(b.rotfree[2]?0:32);
       for(int k=0;k<3;k++){ f.center[k]=b.center[k]; f.fvel[k]=float(b.linvelini[k]); f.fomega[k]=float(b.angvelini[k]); }
       for(int k=0;k<9;k++)f.inertiaini[k]=float(b.inertia[k]);
-      // radius = max distance particle-centre (JSph::InitFloatings)
-      double r2max=0;
-      for(unsigned i=0;i<np;i++)if(idp[i]>=b.begin && idp[i]<b.begin+b.count){ double d2=0; for(int k=0;k<3;k++){ const double d=pos[size_t(i)*3+k]-b.center[k]; d2+=d*d; } r2max=std::max(r2max,d2); }
-      f.radius=float(sqrt(r2max));
+      f.radius=ftradius[kf++];
       fts.push_back(f);
     }
     r=b2s_set_floatings(s->ctx,unsigned(fts.size()),fts.data());

@@ -140,7 +140,7 @@ static SlabArrays slab_arrays(b2s_ctx* ctx){
 
 extern "C" int b2s_slab_config(b2s_ctx* ctx, int rank, int nranks, uint32_t cx_begin, uint32_t cx_end){
   if(!ctx || nranks<1 || rank<0 || rank>=nranks || cx_begin>=cx_end || cx_end>ctx->prm.domcells[0])return B2S_ERR_ARG;
-  if(ctx->ftcount)return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"floating bodies are single-GPU only in this round");
+  if(nranks>1 && cx_end-cx_begin<uint32_t(ctx->prm.scelldiv))return b2s_fail(ctx,B2S_ERR_ARG,"slab [%u,%u) is thinner than the halo (%d cell planes)",cx_begin,cx_end,ctx->prm.scelldiv);
   // mDBC would need the boundary ghosts' extrapolated rho AFTER the owner's mdbc pass (a second, boundary-only halo exchange)
   if(ctx->prm.tboundary==B2S_BC_MDBC)return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"mDBC is single-GPU only in this round");
   B2S_CUDA(ctx,cudaSetDevice(ctx->device));
@@ -198,6 +198,7 @@ extern "C" int b2s_slab_drop_ghosts(b2s_ctx* ctx){
 }
 extern "C" int b2s_slab_set_range(b2s_ctx* ctx, uint32_t cx_begin, uint32_t cx_end){
   if(!ctx || !ctx->slab_on || cx_begin>=cx_end || cx_end>ctx->prm.domcells[0])return B2S_ERR_ARG;
+  if(ctx->slab_nranks>1 && cx_end-cx_begin<uint32_t(ctx->prm.scelldiv))return b2s_fail(ctx,B2S_ERR_ARG,"slab [%u,%u) is thinner than the halo (%d cell planes)",cx_begin,cx_end,ctx->prm.scelldiv);
   ctx->slab_cxa=cx_begin; ctx->slab_cxb=cx_end;
   return B2S_OK;
 }

@@ -92,7 +92,7 @@ ABI_SYMBOLS = [
     "b2s_move_linear", "b2s_set_floatings", "b2s_get_floatings", "b2s_count_pairs", "b2s_time_interaction",
     "b2s_launch_count", "b2s_get_stream", "b2s_set_interaction_variant", "b2s_slab_config",
     "b2s_slab_histogram", "b2s_slab_set_range", "b2s_slab_drop_ghosts", "b2s_slab_record_bytes", "b2s_slab_pack", "b2s_slab_unpack", "b2s_slab_dt_buffer", "b2s_slab_forces",
-    "b2s_slab_apply_dt", "b2s_slab_integrate", "b2s_slab_step_end",
+    "b2s_slab_apply_dt", "b2s_slab_integrate", "b2s_slab_step_end", "b2s_slab_ft_sums", "b2s_slab_ft_apply",
     "b2s_sim_load", "b2s_sim_load_slab", "b2s_sim_slab_info", "b2s_sim_free", "b2s_sim_ctx", "b2s_sim_params", "b2s_sim_save_part", "b2s_sim_run",
     "b2s_host_last_error",
 ]
@@ -157,6 +157,8 @@ def load_library():
     lib.b2s_slab_apply_dt.argtypes = [vp, C.c_int]
     lib.b2s_slab_integrate.argtypes = [vp, C.c_int]
     lib.b2s_slab_step_end.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.b2s_slab_ft_sums.argtypes = [vp, C.POINTER(vp), u32p]
+    lib.b2s_slab_ft_apply.argtypes = [vp, C.c_int]
     lib.b2s_sim_load_slab.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     lib.b2s_sim_slab_info.argtypes = [vp, u32p, C.c_uint32, u32p]
     lib.b2s_sim_load.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_uint32, C.POINTER(vp)]
@@ -337,6 +339,14 @@ class Context:
 
     def slab_integrate(self, mode):
         self._chk(self._lib.b2s_slab_integrate(self._h, mode))
+
+    def slab_ft_sums(self):
+        p, n = C.c_void_p(), C.c_uint32(0)
+        self._chk(self._lib.b2s_slab_ft_sums(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def slab_ft_apply(self, predictor):
+        self._chk(self._lib.b2s_slab_ft_apply(self._h, int(predictor)))
 
     def slab_step_end(self):
         dt = C.c_double(0)

@@ -20,13 +20,15 @@ from . import lib as L
 HALO, MIGRANT = 0, 1
 
 
-def compute_cuts(cellx: np.ndarray, ncells_x: int, nranks: int) -> list:
+def compute_cuts(cellx: np.ndarray, ncells_x: int, nranks: int, minwidth: int = 1) -> list:
     """Cut planes [c0=0, c1, ..., cN=ncells_x] balancing the particle count per slab (prefix sum over x cell planes)."""
-    return compute_cuts_hist(np.bincount(np.asarray(cellx, np.int64), minlength=ncells_x), nranks)
+    return compute_cuts_hist(np.bincount(np.asarray(cellx, np.int64), minlength=ncells_x), nranks, minwidth)
 
 
-def compute_cuts_hist(hist, nranks: int) -> list:
-    """Same from the histogram of particles per x cell plane (the form the re-cut uses after an all-reduce)."""
+def compute_cuts_hist(hist, nranks: int, minwidth: int = 1) -> list:
+    """Same from the histogram of particles per x cell plane (the form the re-cut uses after an all-reduce).
+    ``minwidth``: planes per slab at least (the halo is scelldiv planes wide and only comes from the direct neighbours, so a
+    slab must be at least that wide)."""
     hist = np.asarray(hist, np.int64)
     ncells_x = len(hist)
     cum = np.cumsum(hist)
@@ -37,8 +39,8 @@ def compute_cuts_hist(hist, nranks: int) -> list:
         c = int(np.searchsorted(cum, target, side="left")) + 1          # first cut with cum[c-1] >= target ...
         if c >= 2 and abs(cum[c - 2] - target) < abs(cum[c - 1] - target):
             c -= 1                                                        # ... or the plane before, whichever is nearer
-        c = max(c, cuts[-1] + 1)
-        c = min(c, ncells_x - (nranks - r))
+        c = max(c, cuts[-1] + minwidth)
+        c = min(c, ncells_x - (nranks - r) * minwidth)
         cuts.append(c)
     cuts.append(ncells_x)
     return cuts
@@ -81,6 +83,7 @@ class SlabRank:
         self.send_l, self.send_r, self.recv_l, self.recv_r = mk(), mk(), mk(), mk()
         self._ext = None
         self._dt_t = None
+        self._ft_t = None
 
     def on_stream(self):
         """Context that makes the ctx's CUDA stream torch's current stream: NCCL operations issued inside are ordered with
@@ -226,6 +229,33 @@ class SlabSimulation:
             with r.on_stream():     # ordered after the interaction kernels and before k_dtvariable by the stream itself
                 self.dist.all_reduce(r.dt_tensor(), op=self.dist.ReduceOp.MAX)
 
+    def _floating(self, predictor):
+        """RunFloating across slabs: local sums -> all-reduce(SUM) -> rigid-body update on every rank."""
+        torch = self.torch
+        views = []
+        for r in self.ranks:
+            ptr, n = r.ctx.slab_ft_sums()
+            if not n:
+                return
+            if r._ft_t is None:
+                class _W:
+                    __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+                r._ft_t = torch.as_tensor(_W(), device=r.dev)
+            views.append(r._ft_t)
+        if self.dist is None:
+            for r in self.ranks:
+                r.sync()
+            tot = torch.stack(views).sum(dim=0)
+            for v in views:
+                v.copy_(tot)
+            for r in self.ranks:
+                r.sync()
+        else:
+            with self.ranks[0].on_stream():
+                self.dist.all_reduce(views[0], op=self.dist.ReduceOp.SUM)
+        for r in self.ranks:
+            r.ctx.slab_ft_apply(predictor)
+
     def _interaction(self, interstep):
         for r in self.ranks:
             r.ctx.slab_forces(interstep)
@@ -263,6 +293,7 @@ class SlabSimulation:
             self._mark("interaction_pre")
             for r in self.ranks:
                 r.ctx.slab_integrate(1)
+            self._floating(True)
             self._mark("integrate_pre")
             self._exchange()
             self._mark("exchange_mid+celldiv")
@@ -270,12 +301,14 @@ class SlabSimulation:
             self._mark("interaction_corr")
             for r in self.ranks:
                 r.ctx.slab_integrate(2)
+            self._floating(False)
             self._mark("integrate_corr")
         else:
             self._interaction(L.INTER_VERLET)
             self._mark("interaction")
             for r in self.ranks:
                 r.ctx.slab_integrate(0)
+            self._floating(False)
             self._mark("integrate")
         dts = [r.ctx.slab_step_end() for r in self.ranks]
         self.nstep += 1
@@ -311,7 +344,7 @@ class SlabSimulation:
             for r in self.ranks:
                 r.sync()
             total = hists[0].cpu().numpy().astype(np.int64) if self.dist is not None else sum(h.cpu().numpy().astype(np.int64) for h in hists)
-            cuts = compute_cuts_hist(total, nranks)
+            cuts = compute_cuts_hist(total, nranks, int(self.ranks[0].p.scelldiv))
         self.cuts = [int(c) for c in cuts]
         for r in self.ranks:
             r.cuts = self.cuts

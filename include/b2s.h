@@ -241,6 +241,12 @@ int b2s_slab_forces(b2s_ctx* ctx, int interstep);
 int b2s_slab_apply_dt(b2s_ctx* ctx, int interstep);
 int b2s_slab_integrate(b2s_ctx* ctx, int mode);
 int b2s_slab_step_end(b2s_ctx* ctx, double* dt_out);
+/* Floating bodies across slabs (RunFloating, JSphGpuSingle.cpp:827-907, cut where the ranks must talk): after
+ * b2s_slab_integrate call b2s_slab_ft_sums (force/torque sums of the floating particles THIS rank owns; returns the device
+ * buffer of 6*ftcount floats), all-reduce that buffer with SUM, then b2s_slab_ft_apply (rigid-body algebra, identical on
+ * every rank, and update of the owned floating particles).  predictor: 1 after SymplecticPre, 0 otherwise. */
+int b2s_slab_ft_sums(b2s_ctx* ctx, void** dev_f32, uint32_t* count);
+int b2s_slab_ft_apply(b2s_ctx* ctx, int predictor);
 
 #ifdef __cplusplus
 }

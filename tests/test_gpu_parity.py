@@ -22,7 +22,7 @@ from dualsphysics_b200 import b2sd
 
 pytestmark = pytest.mark.gpu
 
-FIXTURES = sorted(d for d in os.listdir(H.GOLDEN) if os.path.isdir(os.path.join(H.GOLDEN, d)))
+FIXTURES = sorted(d for d in os.listdir(H.GOLDEN) if os.path.exists(os.path.join(H.GOLDEN, d, "fixture.json")))
 TOL_PRESS, TOL_ACE, TOL_DT, TOL_POS, TOL_STATE = 3e-4, 5e-4, 2e-5, 1e-7, 2e-6
 
 

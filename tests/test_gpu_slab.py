@@ -94,8 +94,8 @@ def test_slab_recut(tmp_path, built_lib):
     n0 = ref.ctx.info().np
     for s in range(30):
         ref.ctx.compute_step(); ss.step()
-        if s == 9:    # squeeze the middle slab to one plane on the far side: everything it owned moves two slabs over
-            forced = [c0[0], c0[2] + 2, c0[2] + 3, c0[3]]
+        if s == 9:    # squeeze the middle slab to two planes on the far side: everything it owned moves two slabs over
+            forced = [c0[0], c0[2] + 2, c0[2] + 4, c0[3]]
             assert ss.recut(cuts=forced) == forced
             assert sum(ss.owned_counts()) == n0
         if s == 19:
@@ -112,7 +112,53 @@ def test_slab_recut(tmp_path, built_lib):
     ss.close(); ref.close()
 
 
-def test_slab_unsupported_is_loud(tmp_path, built_lib):
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_slab_floating_body(nranks, tmp_path, built_lib):
+    """A floating box that straddles a cut: every rank sums the force/torque of the floating particles it owns, the sums are
+    all-reduced and every rank integrates the same rigid body.  Against the single-context run: body centre 1e-8 m, linear /
+    angular velocity 1e-5 relative (the partial sums are added in a different order), particles as in the other slab tests."""
     H.write_case(tmp_path, dp=0.05, floating_box=(0.15, 0.25, 0.2, 0.1, 0.15, 0.1), floating_rel_density=0.5)
+    case = str(tmp_path / "Case")
+    ref = dsb.Simulation(case, options="-symplectic -cellmode:half")
+    ss = slab.SlabSimulation(case, options="-symplectic -cellmode:half", nranks=nranks, dist=None)
+    # put a cut through the middle of the box (x=0.2): the body must really be shared by at least two ranks
+    p = ss.ranks[0].p
+    cmid = int((0.2 - p.map_posmin[0]) / float(p.scell))
+    ncx = int(p.domcells[0])
+    ss.recut(cuts=[0, cmid, ncx] if nranks == 2 else [0, cmid, cmid + 2, ncx])   # slabs are >= 2 planes (halo width)
+    owners = 0
+    for r in ss.ranks:
+        code = r.ctx.array("code")
+        owners += int(np.any(((code & 0xe000) == 0) & ((code & 0x1800) == 0x1000)))
+    assert owners >= 2, (ss.cuts, owners)
+    for s in range(20):
+        dt_ref, dt = ref.ctx.compute_step(), ss.step()
+        assert abs(dt - dt_ref) <= 2e-5 * dt_ref, (s, dt, dt_ref)
+    f0 = ref.ctx.get_floatings(1)[0]
+    for r in ss.ranks:
+        f = r.ctx.get_floatings(1)[0]
+        assert max(abs(f.center[k] - f0.center[k]) for k in range(3)) < 1e-8
+        v0 = np.array([*f0.fvel, *f0.fomega]); v = np.array([*f.fvel, *f.fomega])
+        assert np.max(np.abs(v - v0)) < 1e-5 * max(np.max(np.abs(v0)), 1e-2), (v, v0)
+    ids, pos, vr = ss.gather_byid()
+    rid = ref.ctx.array("idp"); o = np.argsort(rid, kind="stable")
+    assert np.array_equal(ids, rid[o])
+    epos = float(np.max(np.abs(pos - ref.ctx.array("pos")[o])))
+    evr = H.rel_err(vr, ref.ctx.array("velrho")[o])
+    print(f"\n[slab floating x{nranks}] cuts={ss.cuts} owners={owners} pos_err={epos:.3e} velrho_err={evr:.3e}")
+    assert epos < 1e-7 and evr < 2e-6
+    ss.close(); ref.close()
+
+
+def test_slab_too_thin_is_loud(tmp_path, built_lib):
+    H.write_case(tmp_path, dp=0.04)
+    ss = slab.SlabSimulation(str(tmp_path / "Case"), options="-cellmode:half", nranks=2, dist=None)
+    with pytest.raises(dsb.B2SError):
+        ss.recut(cuts=[0, 1, ss.cuts[-1]])      # one plane < halo width of two planes
+    ss.close()
+
+
+def test_slab_unsupported_is_loud(tmp_path, built_lib):
+    H.write_case(tmp_path, dp=0.05, layers=4, normals=True, params={"Boundary": 2, "SlipMode": 1})
     with pytest.raises(dsb.B2SError):
         slab.SlabSimulation(str(tmp_path / "Case"), nranks=2, dist=None)

@@ -24,6 +24,13 @@ def test_compute_cuts_balances_particles():
             assert own.max() <= len(cx) / n + np.bincount(cx.astype(int)).max()
 
 
+def test_compute_cuts_min_width():
+    rng = np.random.default_rng(5)
+    cx = np.floor(rng.random(5000) ** 4 * 40)
+    cuts = slab.compute_cuts(cx, 40, 6, minwidth=2)
+    assert cuts[0] == 0 and cuts[-1] == 40 and all(b - a >= 2 for a, b in zip(cuts, cuts[1:]))
+
+
 def test_compute_cuts_degenerate():
     # fewer populated planes than ranks: every slab still gets at least one plane
     assert slab.compute_cuts(np.zeros(10), 4, 4) == [0, 1, 2, 3, 4]
