@@ -131,9 +131,11 @@ def test_golden_reference_parity(fx, variant, tmp_path, built_lib):
     sim.close()
 
 
-@pytest.mark.parametrize("dp,opts", [(0.03, {}), (0.025, {"StepAlgorithm": 1, "Kernel": 1, "DensityDT": 3})])
+@pytest.mark.parametrize("dp,opts", [(0.03, {}), (0.025, {"StepAlgorithm": 1, "Kernel": 1, "DensityDT": 3}),
+                                     (0.0085, {"DensityDT": 0})])   # BASELINE configs[0]: 01_DamBreak resolution, ~170k particles
 def test_oracle_parity_other_sizes(dp, opts, tmp_path, built_lib):
-    """Fresh cases at other sizes against the C restatement, 5 whole steps."""
+    """Fresh cases at other sizes against the C restatement, 5 whole steps.  dp=0.0085 is the resolution, tank and column of
+    examples/main/01_DamBreak (CaseDambreak_Def.xml: Wendland, Symplectic, DBC, no density diffusion), without its obstacle."""
     H.write_case(tmp_path, dp=dp, params=opts)
     case = str(tmp_path / "Case")
     sim = dsb.Simulation(case)

@@ -150,6 +150,32 @@ def test_slab_floating_body(nranks, tmp_path, built_lib):
     ss.close(); ref.close()
 
 
+def test_slab_piston_and_floating(tmp_path, built_lib):
+    """BASELINE configs[3] in miniature: piston wavemaker (mvrectsinu) + floating box, 3 slabs, against the single context."""
+    H.write_case(tmp_path, dp=0.05, piston=True, piston_ampl=0.05, piston_freq=2.0, floating_box=(0.45, 0.25, 0.2, 0.1, 0.15, 0.1), floating_rel_density=0.5)
+    case = str(tmp_path / "Case")
+    opts = "-symplectic -cellmode:half"
+    ref = dsb.Simulation(case, options=opts)
+    ss = slab.SlabSimulation(case, options=opts, nranks=3, dist=None)
+    for s in range(40):
+        dt_ref, dt = ref.ctx.compute_step(), ss.step()
+        assert abs(dt - dt_ref) <= 2e-5 * dt_ref, (s, dt, dt_ref)
+    f0 = ref.ctx.get_floatings(1)[0]
+    f = ss.ranks[0].ctx.get_floatings(1)[0]
+    assert max(abs(f.center[k] - f0.center[k]) for k in range(3)) < 1e-8
+    ids, pos, vr = ss.gather_byid()
+    rid = ref.ctx.array("idp"); o = np.argsort(rid, kind="stable")
+    assert np.array_equal(ids, rid[o])
+    epos = float(np.max(np.abs(pos - ref.ctx.array("pos")[o])))
+    evr = H.rel_err(vr, ref.ctx.array("velrho")[o])
+    # the piston must have moved (moving boundary particles are displaced identically on every rank that owns some)
+    moving = (ref.ctx.array("code")[o] & 0x1800) == 0x0800
+    assert moving.any() and np.max(np.abs(pos[moving, 0] - ref.ctx.array("pos")[o][moving, 0])) < 1e-12
+    print(f"\n[slab piston+floating] cuts={ss.cuts} pos_err={epos:.3e} velrho_err={evr:.3e}")
+    assert epos < 1e-7 and evr < 2e-6
+    ss.close(); ref.close()
+
+
 def test_slab_too_thin_is_loud(tmp_path, built_lib):
     H.write_case(tmp_path, dp=0.04)
     ss = slab.SlabSimulation(str(tmp_path / "Case"), options="-cellmode:half", nranks=2, dist=None)
