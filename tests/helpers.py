@@ -141,3 +141,28 @@ def rel_err(a, b, floor=None):
     if scale == 0:
         return float(np.max(np.abs(a - b)))
     return float(np.max(np.abs(a - b)) / scale)
+
+
+def part_observables(datadir, dp):
+    """Per PART file: time, dam front (max x of fluid below z=3dp... any fluid), column height at the left wall, kinetic
+    energy per unit mass, max |v|, floating-body centre (mean position of its particles)."""
+    head = bi4.load(os.path.join(datadir, "Part_Head.ibi4"))
+    nfixed, nmoving, nfloat = head.get("CaseNfixed"), head.get("CaseNmoving"), head.get("CaseNfloat")
+    nb = nfixed + nmoving + nfloat
+    out = []
+    k = 0
+    while os.path.exists(os.path.join(datadir, f"Part_{k:04d}.bi4")):
+        d = bi4.load_part(os.path.join(datadir, f"Part_{k:04d}.bi4"))
+        idp, pos, vel = d["Idp"], d["pos"], d["Vel"]
+        fl = idp >= nb
+        ft = (idp >= nfixed + nmoving) & (idp < nb)
+        v2 = np.sum(vel[fl].astype(np.float64) ** 2, axis=1)
+        near_wall = fl & (pos[:, 0] < 4 * dp)
+        rec = {"t": float(d["part"].get("TimeStep")), "front_x": float(pos[fl, 0].max()),
+               "height_wall": float(pos[near_wall, 2].max()) if near_wall.any() else 0.0,
+               "ke": float(0.5 * v2.sum()), "vmax": float(np.sqrt(v2.max())), "nfluid": int(fl.sum())}
+        if ft.any():
+            rec["ft_center"] = [float(x) for x in pos[ft].mean(axis=0)]
+        out.append(rec)
+        k += 1
+    return out
