@@ -212,7 +212,9 @@ extern "C" int b2s_upload_particles(b2s_ctx* ctx, uint32_t np, const uint32_t* i
     B2S_CUDA(ctx,cudaMemsetAsync(ctx->boundnor,0,size_t(ctx->cap)*16,s));
     if(boundnor){
       // normals are given for the casenbound first particles; the solver doubles them to reach the ghost node (JSph.cpp:1417)
-      const uint32_t nb=std::min(np,ctx->prm.casenbound);
+      // (the count of leading non-fluid particles, by bisection: a slab upload holds a subset of the case's boundary)
+      uint32_t nb=0;
+      { uint32_t lo=0,hi=np; while(lo<hi){ const uint32_t mid=lo+(hi-lo)/2; if(!B2S_CODE_ISFLUID(code[mid]))lo=mid+1; else hi=mid; } nb=lo; }
       B2S_CUDA(ctx,cudaStreamSynchronize(s));
       B2S_CUDA(ctx,cudaMemcpyAsync(ctx->scratch,boundnor,size_t(nb)*12,cudaMemcpyHostToDevice,s));
       k_nor3to4<<<b2s_blocks(nb,256),256,0,s>>>(nb,(const float*)ctx->scratch,ctx->boundnor); B2S_LAUNCHED(ctx);

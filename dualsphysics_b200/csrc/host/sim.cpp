@@ -360,26 +360,28 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   // slab loading: only the particles of [cuts[rank],cuts[rank+1]) reach the device; capacity is sized for the slab
   unsigned npsel=np;
   std::vector<uint32_t> sel_idp;
+  std::vector<float> sel_nor;     // BoundNor of the boundary particles that stay on this rank (slab loading)
   if(slab_nranks>0){
-    if(p.tboundary==B2S_BC_MDBC)throw std::runtime_error("mDBC is single-GPU only in this round");
     const uint32_t ncx=p.domcells[0];
-    if(uint32_t(slab_nranks)*uint32_t(p.scelldiv)>ncx)throw std::runtime_error("more slabs than the cell planes along x allow (a slab is at least scelldiv planes wide)");
+    const uint32_t halow=uint32_t(p.scelldiv)*(p.tboundary==B2S_BC_MDBC? 2u: 1u);   // halo planes (slab.cu slab_halo_planes)
+    if(uint32_t(slab_nranks)*halow>ncx)throw std::runtime_error("more slabs than the cell planes along x allow (a slab is at least as wide as the halo)");
     const double sc=double(p.scell);
     std::vector<uint32_t> cx(np);
     std::vector<uint64_t> hist(ncx,0);
     for(unsigned i=0;i<np;i++){ const double d=(pos[size_t(i)*3]-p.domposmin[0])/sc; uint32_t c=(d<0? 0u: uint32_t(d)); if(c>=ncx)c=ncx-1; cx[i]=c; hist[c]++; }
-    s->slab_cuts=slab_compute_cuts(hist,slab_nranks,uint32_t(p.scelldiv));
+    s->slab_cuts=slab_compute_cuts(hist,slab_nranks,halow);
     s->slab_maxplane=uint32_t(*std::max_element(hist.begin(),hist.end()));
     const uint32_t ca=s->slab_cuts[slab_rank], cb=s->slab_cuts[slab_rank+1];
     unsigned w=0;
     sel_idp.resize(np);
+    if(anor){ sel_nor.reserve(size_t(nbound)*3); for(unsigned i=0;i<nbound;i++)if(cx[i]>=ca && cx[i]<cb)for(int k=0;k<3;k++)sel_nor.push_back(((const float*)anor->ptr())[size_t(i)*3+k]); }
     for(unsigned i=0;i<np;i++)if(cx[i]>=ca && cx[i]<cb){
       sel_idp[w]=idp[i]; code[w]=code[i]; for(int k=0;k<3;k++)pos[size_t(w)*3+k]=pos[size_t(i)*3+k]; for(int k=0;k<4;k++)velrho[size_t(w)*4+k]=velrho[size_t(i)*4+k];
       w++;
     }
     npsel=w; idp=sel_idp.data();
     // room for: ghosts (scelldiv planes each side), migrants, and a 25% drift of the owned count before re-cutting
-    extra_capacity+=npsel/4+4u*unsigned(p.scelldiv)*s->slab_maxplane+4096u;
+    extra_capacity+=npsel/4+4u*halow*s->slab_maxplane+4096u;
   }
   r=b2s_create(&p,device,npsel+extra_capacity,&s->ctx);
   if(r)throw std::runtime_error(std::string("b2s_create failed: ")+b2s_error_string(r));
@@ -411,7 +413,8 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   if(p.tboundary==B2S_BC_MDBC){
     if(!anor)throw std::runtime_error("No normal data for mDBC in the input file.");
     if(anor->count!=nbound)throw std::runtime_error("Size of loaded BoundNor data does not match number of boundary particles.");
-    nor.assign((const float*)anor->ptr(),(const float*)anor->ptr()+size_t(nbound)*3);
+    if(slab_nranks>0)nor=sel_nor;
+    else nor.assign((const float*)anor->ptr(),(const float*)anor->ptr()+size_t(nbound)*3);
     for(auto& v:nor)v*=2.f;   // boundary->interface normals doubled to reach the ghost node (JSph.cpp:1417)
     norp=nor.data();
   }

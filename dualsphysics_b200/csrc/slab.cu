@@ -16,6 +16,11 @@
 
 #define S_BS 256
 
+// Halo width in cell planes: one kernel radius (scelldiv planes).  With mDBC the boundary ghosts must carry the density the
+// owner extrapolates at their ghost node; instead of a second exchange after the mDBC pass every rank recomputes it locally,
+// which needs the fluid within one more kernel radius of those boundary ghosts: the halo is two radii wide.
+static inline uint32_t slab_halo_planes(const b2s_ctx* ctx){ return uint32_t(ctx->prm.scelldiv)*(ctx->prm.tboundary==B2S_BC_MDBC? 2u: 1u); }
+
 void b2s_launch_scan_excl(cudaStream_t s, uint32_t* data, uint32_t n);   // celldiv.cu
 
 struct SlabLayout { uint32_t bytes, off_pre, off_m1, off_tau, off_nor; };
@@ -140,9 +145,7 @@ static SlabArrays slab_arrays(b2s_ctx* ctx){
 
 extern "C" int b2s_slab_config(b2s_ctx* ctx, int rank, int nranks, uint32_t cx_begin, uint32_t cx_end){
   if(!ctx || nranks<1 || rank<0 || rank>=nranks || cx_begin>=cx_end || cx_end>ctx->prm.domcells[0])return B2S_ERR_ARG;
-  if(nranks>1 && cx_end-cx_begin<uint32_t(ctx->prm.scelldiv))return b2s_fail(ctx,B2S_ERR_ARG,"slab [%u,%u) is thinner than the halo (%d cell planes)",cx_begin,cx_end,ctx->prm.scelldiv);
-  // mDBC would need the boundary ghosts' extrapolated rho AFTER the owner's mdbc pass (a second, boundary-only halo exchange)
-  if(ctx->prm.tboundary==B2S_BC_MDBC)return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"mDBC is single-GPU only in this round");
+  if(nranks>1 && cx_end-cx_begin<slab_halo_planes(ctx))return b2s_fail(ctx,B2S_ERR_ARG,"slab [%u,%u) is thinner than the halo (%u cell planes)",cx_begin,cx_end,slab_halo_planes(ctx));
   B2S_CUDA(ctx,cudaSetDevice(ctx->device));
   ctx->slab_on=true; ctx->slab_rank=rank; ctx->slab_nranks=nranks; ctx->slab_cxa=cx_begin; ctx->slab_cxb=cx_end;
   const size_t nb=b2s_blocks(ctx->cap,S_BS);
@@ -198,7 +201,7 @@ extern "C" int b2s_slab_drop_ghosts(b2s_ctx* ctx){
 }
 extern "C" int b2s_slab_set_range(b2s_ctx* ctx, uint32_t cx_begin, uint32_t cx_end){
   if(!ctx || !ctx->slab_on || cx_begin>=cx_end || cx_end>ctx->prm.domcells[0])return B2S_ERR_ARG;
-  if(ctx->slab_nranks>1 && cx_end-cx_begin<uint32_t(ctx->prm.scelldiv))return b2s_fail(ctx,B2S_ERR_ARG,"slab [%u,%u) is thinner than the halo (%d cell planes)",cx_begin,cx_end,ctx->prm.scelldiv);
+  if(ctx->slab_nranks>1 && cx_end-cx_begin<slab_halo_planes(ctx))return b2s_fail(ctx,B2S_ERR_ARG,"slab [%u,%u) is thinner than the halo (%u cell planes)",cx_begin,cx_end,slab_halo_planes(ctx));
   ctx->slab_cxa=cx_begin; ctx->slab_cxb=cx_end;
   return B2S_OK;
 }
@@ -219,7 +222,7 @@ extern "C" int b2s_slab_pack(b2s_ctx* ctx, int kind, void* dev_left, void* dev_r
   const uint32_t nb=b2s_blocks(n,S_BS);
   const int hl=(ctx->slab_rank>0), hr=(ctx->slab_rank<ctx->slab_nranks-1);
   B2S_CUDA(ctx,cudaMemsetAsync(ctx->slab_counts,0,size_t(2)*(nb+1)*4,s));
-  k_slab_flag<<<nb,S_BS,0,s>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,kind,hl,hr,ctx->slab_cxa,ctx->slab_cxb,uint32_t(ctx->cte.scelldiv),
+  k_slab_flag<<<nb,S_BS,0,s>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,kind,hl,hr,ctx->slab_cxa,ctx->slab_cxb,slab_halo_planes(ctx),
     ctx->slab_flags,ctx->slab_counts,nb); B2S_LAUNCHED(ctx);
   b2s_launch_scan_excl(s,ctx->slab_counts,nb+1); B2S_LAUNCHED(ctx);
   b2s_launch_scan_excl(s,ctx->slab_counts+nb+1,nb+1); B2S_LAUNCHED(ctx);

@@ -76,7 +76,8 @@ class SlabRank:
         self.cuts, maxplane = self.sim.slab_info(nranks)
         self.cxa, self.cxb = self.cuts[rank], self.cuts[rank + 1]
         # exchange buffers: scelldiv cell planes of halo per side, or the migrants of one step (far fewer)
-        self.cap_records = int(2 * self.p.scelldiv * maxplane + 4096)
+        self.halo_planes = int(self.p.scelldiv) * (2 if self.p.tboundary == L.BC_MDBC else 1)   # csrc/slab.cu slab_halo_planes
+        self.cap_records = int(2 * self.halo_planes * maxplane + 4096)
         self.symplectic = (self.p.tstep == L.STEP_SYMPLECTIC)
         maxbytes = 48 + 48 + 16 + 16 + 32     # largest record csrc/slab.cu can produce (the size varies with the step phase)
         mk = lambda: torch.empty(self.cap_records * maxbytes, dtype=torch.uint8, device=self.dev)  # noqa: E731
@@ -344,7 +345,7 @@ class SlabSimulation:
             for r in self.ranks:
                 r.sync()
             total = hists[0].cpu().numpy().astype(np.int64) if self.dist is not None else sum(h.cpu().numpy().astype(np.int64) for h in hists)
-            cuts = compute_cuts_hist(total, nranks, int(self.ranks[0].p.scelldiv))
+            cuts = compute_cuts_hist(total, nranks, self.ranks[0].halo_planes)
         self.cuts = [int(c) for c in cuts]
         for r in self.ranks:
             r.cuts = self.cuts

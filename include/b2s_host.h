@@ -19,7 +19,7 @@ int b2s_sim_load(const char* casepath, const char* dirout, const char* options, 
                  uint32_t extra_capacity, b2s_sim** out);
 /* One rank of a slab-decomposed multi-GPU run (no reference counterpart: DualSPHysics v5.4 is single-GPU).  Every rank
  * reads the same case, derives the same balanced cut planes along x from the particle histogram, uploads ONLY its slab
- * and calls b2s_slab_config.  mDBC is rejected (single-GPU only). */
+ * and calls b2s_slab_config.  With mDBC the halo is two kernel radii wide (boundary ghosts recompute their ghost-node density locally). */
 int b2s_sim_load_slab(const char* casepath, const char* options, int device, int rank, int nranks, b2s_sim** out);
 /* cuts[nranks+1] (cell planes along x) and the particle count of the densest plane (sizes the exchange buffers). */
 int b2s_sim_slab_info(b2s_sim* sim, uint32_t* cuts, uint32_t ncuts, uint32_t* max_plane_particles);
