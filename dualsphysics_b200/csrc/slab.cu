@@ -83,7 +83,7 @@ __device__ __forceinline__ void slab_write(char* rec, const SlabLayout& l, const
 }
 
 __global__ void __launch_bounds__(S_BS) k_slab_scatter(const DivState* __restrict__ ds, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ offs,
-  uint32_t nblocks, SlabLayout l, SlabArrays a, int kind, char* left, char* right, uint32_t cap)
+  uint32_t nblocks, SlabLayout l, SlabArrays a, int kind, char* left, char* right, uint32_t cap, typecode migcode)
 {
   __shared__ uint32_t wl[S_BS/32], wr[S_BS/32];
   const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(S_BS) k_slab_scatter(const DivState* __restric
   const uint32_t lm=(1u<<lane)-1u;
   if(f&1){ const uint32_t i=offs[blockIdx.x]+pl+__popc(bl&lm); if(i<cap)slab_write(left+size_t(i)*l.bytes,l,a,p); }
   if(f&2){ const uint32_t i=offs[nblocks+1+blockIdx.x]+pr+__popc(br&lm); if(i<cap)slab_write(right+size_t(i)*l.bytes,l,a,p); }
-  if(kind==1 && f)a.code[p]=typecode(B2S_CODE_SETNORMAL(a.code[p])|B2S_CODE_OUTIGNORE);   // migrated away: dropped by the next divide
+  // migrated away: dropped by the next divide (OUTIGNORE), or kept as a halo ghost of its new owner (PERIODIC; merged exchange)
+  if(kind==1 && f)a.code[p]=typecode(B2S_CODE_SETNORMAL(a.code[p])|migcode);
 }
 
 __global__ void __launch_bounds__(S_BS) k_slab_unpack(DivState* ds, const char* __restrict__ buf, uint32_t n, SlabLayout l, SlabArrays a, int kind,
@@ -150,9 +151,9 @@ extern "C" int b2s_slab_config(b2s_ctx* ctx, int rank, int nranks, uint32_t cx_b
   ctx->slab_on=true; ctx->slab_rank=rank; ctx->slab_nranks=nranks; ctx->slab_cxa=cx_begin; ctx->slab_cxb=cx_end;
   const size_t nb=b2s_blocks(ctx->cap,S_BS);
   if(!ctx->slab_counts){
-    ctx->slab_counts_len=2*(nb+1);
+    ctx->slab_counts_len=4*(nb+1);           // two sets (migrants, halos) for the merged exchange
     B2S_CUDA(ctx,cudaMalloc((void**)&ctx->slab_counts,ctx->slab_counts_len*4));
-    B2S_CUDA(ctx,cudaMalloc((void**)&ctx->slab_flags,ctx->cap));
+    B2S_CUDA(ctx,cudaMalloc((void**)&ctx->slab_flags,size_t(ctx->cap)*2));
   }
   // drop everything that does not belong to this slab and re-divide
   k_slab_select<<<b2s_blocks(ctx->np_host,S_BS),S_BS,0,ctx->stream>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,cx_begin,cx_end); B2S_LAUNCHED(ctx);
@@ -233,10 +234,56 @@ extern "C" int b2s_slab_pack(b2s_ctx* ctx, int kind, void* dev_left, void* dev_r
   if(tot[0]>cap_records || tot[1]>cap_records)return b2s_fail(ctx,B2S_ERR_NOMEM,"slab exchange buffer too small: need %u/%u records, have %u",tot[0],tot[1],cap_records);
   if((tot[0] && !dev_left) || (tot[1] && !dev_right))return B2S_ERR_ARG;
   const SlabLayout l=slab_layout(ctx,kind);
-  k_slab_scatter<<<nb,S_BS,0,s>>>(ctx->div,ctx->slab_flags,ctx->slab_counts,nb,l,slab_arrays(ctx),kind,(char*)dev_left,(char*)dev_right,cap_records); B2S_LAUNCHED(ctx);
+  k_slab_scatter<<<nb,S_BS,0,s>>>(ctx->div,ctx->slab_flags,ctx->slab_counts,nb,l,slab_arrays(ctx),kind,(char*)dev_left,(char*)dev_right,cap_records,typecode(B2S_CODE_OUTIGNORE)); B2S_LAUNCHED(ctx);
   B2S_CUDA(ctx,cudaGetLastError());
   *nleft=tot[0]; *nright=tot[1];
   return B2S_OK;
+}
+
+// Merged exchange: migrants AND halos of one interaction in one message per neighbour (one host sync, one count exchange, one
+// payload exchange instead of two each).  A particle that migrates stays on the sender as a halo ghost of its new owner (it has
+// just crossed the cut, so it lies inside the sender's halo region), hence the receiver need not send it back and the halo can be
+// selected before the migrants arrive.  Needs slabs wider than the halo (a received migrant must not fall into the far halo band).
+// Buffer per side: [counts[0|1] migrant records][counts[2|3] halo records].
+extern "C" int b2s_slab_pack_both(b2s_ctx* ctx, void* dev_left, void* dev_right, uint64_t cap_bytes, uint32_t counts[4]){
+  if(!ctx || !ctx->slab_on || !counts)return B2S_ERR_ARG;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  cudaStream_t s=ctx->stream;
+  counts[0]=counts[1]=counts[2]=counts[3]=0;
+  const uint32_t n=ctx->np_host;
+  if(!n)return B2S_OK;
+  if(ctx->slab_nranks>1 && ctx->slab_cxb-ctx->slab_cxa<=slab_halo_planes(ctx))
+    return b2s_fail(ctx,B2S_ERR_STATE,"merged exchange needs slabs wider than the halo (%u planes)",slab_halo_planes(ctx));
+  const uint32_t nb=b2s_blocks(n,S_BS);
+  const int hl=(ctx->slab_rank>0), hr=(ctx->slab_rank<ctx->slab_nranks-1);
+  uint32_t* cM=ctx->slab_counts; uint32_t* cH=ctx->slab_counts+2*(nb+1);
+  uint8_t* fM=ctx->slab_flags; uint8_t* fH=ctx->slab_flags+ctx->cap;
+  B2S_CUDA(ctx,cudaMemsetAsync(ctx->slab_counts,0,size_t(4)*(nb+1)*4,s));
+  k_slab_flag<<<nb,S_BS,0,s>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,1,hl,hr,ctx->slab_cxa,ctx->slab_cxb,slab_halo_planes(ctx),fM,cM,nb); B2S_LAUNCHED(ctx);
+  k_slab_flag<<<nb,S_BS,0,s>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,0,hl,hr,ctx->slab_cxa,ctx->slab_cxb,slab_halo_planes(ctx),fH,cH,nb); B2S_LAUNCHED(ctx);
+  b2s_launch_scan_excl(s,cM,nb+1); b2s_launch_scan_excl(s,cM+nb+1,nb+1); b2s_launch_scan_excl(s,cH,nb+1); b2s_launch_scan_excl(s,cH+nb+1,nb+1); ctx->launches+=4;
+  uint32_t tot[4]={0,0,0,0};
+  B2S_CUDA(ctx,cudaMemcpyAsync(&tot[0],cM+nb,4,cudaMemcpyDeviceToHost,s));
+  B2S_CUDA(ctx,cudaMemcpyAsync(&tot[1],cM+2*nb+1,4,cudaMemcpyDeviceToHost,s));
+  B2S_CUDA(ctx,cudaMemcpyAsync(&tot[2],cH+nb,4,cudaMemcpyDeviceToHost,s));
+  B2S_CUDA(ctx,cudaMemcpyAsync(&tot[3],cH+2*nb+1,4,cudaMemcpyDeviceToHost,s));
+  B2S_CUDA(ctx,cudaStreamSynchronize(s));
+  const SlabLayout lM=slab_layout(ctx,1), lH=slab_layout(ctx,0);
+  const uint64_t needl=uint64_t(tot[0])*lM.bytes+uint64_t(tot[2])*lH.bytes, needr=uint64_t(tot[1])*lM.bytes+uint64_t(tot[3])*lH.bytes;
+  if(needl>cap_bytes || needr>cap_bytes)return b2s_fail(ctx,B2S_ERR_NOMEM,"slab exchange buffer too small: need %llu/%llu bytes, have %llu",(unsigned long long)needl,(unsigned long long)needr,(unsigned long long)cap_bytes);
+  if((needl && !dev_left) || (needr && !dev_right))return B2S_ERR_ARG;
+  if(tot[0]||tot[1]){ k_slab_scatter<<<nb,S_BS,0,s>>>(ctx->div,fM,cM,nb,lM,slab_arrays(ctx),1,(char*)dev_left,(char*)dev_right,0xffffffffu,typecode(B2S_CODE_PERIODIC)); B2S_LAUNCHED(ctx); ctx->bound_changed=true; }
+  if(tot[2]||tot[3]){ k_slab_scatter<<<nb,S_BS,0,s>>>(ctx->div,fH,cH,nb,lH,slab_arrays(ctx),0,(char*)dev_left+size_t(tot[0])*lM.bytes,(char*)dev_right+size_t(tot[1])*lM.bytes,0xffffffffu,typecode(B2S_CODE_OUTIGNORE)); B2S_LAUNCHED(ctx); }
+  B2S_CUDA(ctx,cudaGetLastError());
+  for(int k=0;k<4;k++)counts[k]=tot[k];
+  return B2S_OK;
+}
+extern "C" int b2s_slab_unpack(b2s_ctx* ctx, int kind, const void* dev_buf, uint32_t count);
+extern "C" int b2s_slab_unpack_both(b2s_ctx* ctx, const void* dev_buf, uint32_t nmigrants, uint32_t nhalo){
+  if(!ctx || !ctx->slab_on)return B2S_ERR_ARG;
+  const uint32_t rbM=slab_layout(ctx,1).bytes;
+  int r=b2s_slab_unpack(ctx,1,dev_buf,nmigrants); if(r)return r;
+  return b2s_slab_unpack(ctx,0,(const char*)dev_buf+size_t(nmigrants)*rbM,nhalo);
 }
 
 extern "C" int b2s_slab_unpack(b2s_ctx* ctx, int kind, const void* dev_buf, uint32_t count){

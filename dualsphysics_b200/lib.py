@@ -91,7 +91,7 @@ ABI_SYMBOLS = [
     "b2s_compute_symplectic_corr", "b2s_compute_step", "b2s_run_steps", "b2s_add_motion_rectsinu",
     "b2s_move_linear", "b2s_set_floatings", "b2s_get_floatings", "b2s_count_pairs", "b2s_time_interaction",
     "b2s_launch_count", "b2s_get_stream", "b2s_set_interaction_variant", "b2s_slab_config",
-    "b2s_slab_histogram", "b2s_slab_set_range", "b2s_slab_drop_ghosts", "b2s_slab_record_bytes", "b2s_slab_pack", "b2s_slab_unpack", "b2s_slab_dt_buffer", "b2s_slab_forces",
+    "b2s_slab_histogram", "b2s_slab_set_range", "b2s_slab_drop_ghosts", "b2s_slab_record_bytes", "b2s_slab_pack", "b2s_slab_unpack", "b2s_slab_pack_both", "b2s_slab_unpack_both", "b2s_slab_dt_buffer", "b2s_slab_forces",
     "b2s_slab_apply_dt", "b2s_slab_integrate", "b2s_slab_step_end", "b2s_slab_ft_sums", "b2s_slab_ft_apply",
     "b2s_sim_load", "b2s_sim_load_slab", "b2s_sim_slab_info", "b2s_sim_free", "b2s_sim_ctx", "b2s_sim_params", "b2s_sim_save_part", "b2s_sim_run",
     "b2s_host_last_error",
@@ -152,6 +152,8 @@ def load_library():
     lib.b2s_slab_record_bytes.argtypes = [vp, C.c_int, u32p]
     lib.b2s_slab_pack.argtypes = [vp, C.c_int, vp, vp, C.c_uint32, u32p, u32p]
     lib.b2s_slab_unpack.argtypes = [vp, C.c_int, vp, C.c_uint32]
+    lib.b2s_slab_pack_both.argtypes = [vp, vp, vp, C.c_uint64, u32p]
+    lib.b2s_slab_unpack_both.argtypes = [vp, vp, C.c_uint32, C.c_uint32]
     lib.b2s_slab_dt_buffer.argtypes = [vp, C.POINTER(vp)]
     lib.b2s_slab_forces.argtypes = [vp, C.c_int]
     lib.b2s_slab_apply_dt.argtypes = [vp, C.c_int]
@@ -322,6 +324,14 @@ class Context:
         a, b = C.c_uint32(0), C.c_uint32(0)
         self._chk(self._lib.b2s_slab_pack(self._h, kind, left_ptr, right_ptr, cap_records, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def slab_pack_both(self, left_ptr, right_ptr, cap_bytes):
+        c = (C.c_uint32 * 4)()
+        self._chk(self._lib.b2s_slab_pack_both(self._h, left_ptr, right_ptr, cap_bytes, c))
+        return list(c)
+
+    def slab_unpack_both(self, ptr, nmigrants, nhalo):
+        self._chk(self._lib.b2s_slab_unpack_both(self._h, ptr, nmigrants, nhalo))
 
     def slab_unpack(self, kind, ptr, count):
         self._chk(self._lib.b2s_slab_unpack(self._h, kind, ptr, count))

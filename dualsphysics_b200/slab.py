@@ -96,6 +96,12 @@ class SlabRank:
     def pack(self, kind):
         return self.ctx.slab_pack(kind, self.send_l.data_ptr(), self.send_r.data_ptr(), self.cap_records)
 
+    def pack_both(self):
+        return self.ctx.slab_pack_both(self.send_l.data_ptr(), self.send_r.data_ptr(), self.send_l.numel())
+
+    def unpack_both(self, buf, nmig, nhalo):
+        self.ctx.slab_unpack_both(buf.data_ptr(), nmig, nhalo)
+
     def unpack(self, kind, nl, nr):
         if nl:
             self.ctx.slab_unpack(kind, self.recv_l.data_ptr(), nl)
@@ -175,13 +181,77 @@ def _exchange_dist(rank, kind, dist):
     return (nl_s, nr_s, nl_r, nr_r)
 
 
+def _exchange_both_local(ranks):
+    """Merged migrant+halo exchange, single-process transport (device copies)."""
+    counts = [r.ctx.slab_pack_both(r.send_l.data_ptr(), r.send_r.data_ptr(), r.send_l.numel()) for r in ranks]
+    for r in ranks:
+        r.sync()
+    rbm, rbh = ranks[0].ctx.slab_record_bytes(MIGRANT), ranks[0].ctx.slab_record_bytes(HALO)
+    for i, r in enumerate(ranks):
+        if i > 0:                                   # what the left neighbour sent to its right
+            nm, nh = counts[i - 1][1], counts[i - 1][3]
+            nb = nm * rbm + nh * rbh
+            if nb:
+                r.recv_l[:nb].copy_(ranks[i - 1].send_r[:nb]); r.sync()
+                r.ctx.slab_unpack_both(r.recv_l.data_ptr(), nm, nh)
+        if i < len(ranks) - 1:
+            nm, nh = counts[i + 1][0], counts[i + 1][2]
+            nb = nm * rbm + nh * rbh
+            if nb:
+                r.recv_r[:nb].copy_(ranks[i + 1].send_l[:nb]); r.sync()
+                r.ctx.slab_unpack_both(r.recv_r.data_ptr(), nm, nh)
+    return counts, rbm, rbh
+
+
+def _exchange_both_dist(rank, dist):
+    """Merged migrant+halo exchange over torch.distributed: ONE count exchange and ONE payload exchange per interaction,
+    everything on the ctx's stream; the host waits twice (packed counts, neighbours' counts)."""
+    torch = rank.torch
+    me, n = rank.rank, rank.nranks
+    with rank.on_stream():
+        c = rank.pack_both()
+        rbm, rbh = rank.ctx.slab_record_bytes(MIGRANT), rank.ctx.slab_record_bytes(HALO)
+        cnt_send = torch.tensor([c[0], c[2], c[1], c[3]], dtype=torch.int64, device=rank.dev)   # (mig,halo) left, (mig,halo) right
+        cnt_recv = torch.zeros(4, dtype=torch.int64, device=rank.dev)
+        ops = []
+        if me > 0:
+            ops += [dist.P2POp(dist.isend, cnt_send[0:2], me - 1), dist.P2POp(dist.irecv, cnt_recv[0:2], me - 1)]
+        if me < n - 1:
+            ops += [dist.P2POp(dist.isend, cnt_send[2:4], me + 1), dist.P2POp(dist.irecv, cnt_recv[2:4], me + 1)]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        ml, hl, mr, hr = (int(v) for v in cnt_recv.tolist())
+        sl, sr = c[0] * rbm + c[2] * rbh, c[1] * rbm + c[3] * rbh
+        rl, rr = ml * rbm + hl * rbh, mr * rbm + hr * rbh
+        ops = []
+        if me > 0:
+            if sl:
+                ops.append(dist.P2POp(dist.isend, rank.send_l[:sl], me - 1))
+            if rl:
+                ops.append(dist.P2POp(dist.irecv, rank.recv_l[:rl], me - 1))
+        if me < n - 1:
+            if sr:
+                ops.append(dist.P2POp(dist.isend, rank.send_r[:sr], me + 1))
+            if rr:
+                ops.append(dist.P2POp(dist.irecv, rank.recv_r[:rr], me + 1))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if rl:
+            rank.unpack_both(rank.recv_l, ml, hl)
+        if rr:
+            rank.unpack_both(rank.recv_r, mr, hr)
+    return c, rbm, rbh
+
+
 class SlabSimulation:
     """Drives N slabs through ComputeStep_Sym / ComputeStep_Ver (JSphGpuSingle.cpp:761-819) with the exchanges in between.
 
     ``dist`` = torch.distributed (already initialised, NCCL): this process owns ONE rank.
     ``dist`` = None: all ranks are created in this process on ``device`` (LocalTransport, for tests)."""
 
-    def __init__(self, casepath, options="", nranks=1, dist=None, device=0, recut_every=0):
+    def __init__(self, casepath, options="", nranks=1, dist=None, device=0, recut_every=0, merged=True):
         import torch
         self.torch, self.dist = torch, dist
         if dist is None:
@@ -191,6 +261,7 @@ class SlabSimulation:
         self.symplectic = self.ranks[0].symplectic
         self.exchanged_bytes = 0
         self.migrated = 0
+        self.merged = bool(merged)              # migrants and halos in one message per neighbour (csrc/slab.cu pack_both)
         self.recut_every = int(recut_every)     # >0: rebalance the cuts every that many steps (dynamic load balance)
         self.nstep = 0
         import os
@@ -199,7 +270,24 @@ class SlabSimulation:
         self._exchange(first=True)
 
     # migrants then halos, then the cell divide (RunCellDivide with the ghosts in place)
+    def _merged_ok(self):
+        """The merged exchange needs every slab wider than the halo (cuts are the same on all ranks)."""
+        hw = self.ranks[0].halo_planes
+        return self.merged and all(b - a > hw for a, b in zip(self.cuts, self.cuts[1:]))
+
     def _exchange(self, first=False):
+        if not first and self._merged_ok():
+            if self.dist is None:
+                cs, rbm, rbh = _exchange_both_local(self.ranks)
+            else:
+                c, rbm, rbh = _exchange_both_dist(self.ranks[0], self.dist)
+                cs = [c]
+            for c in cs:
+                self.exchanged_bytes += (c[0] + c[1]) * rbm + (c[2] + c[3]) * rbh
+                self.migrated += c[0] + c[1]
+            for r in self.ranks:
+                r.ctx.celldiv()
+            return
         for kind in ((HALO,) if first else (MIGRANT, HALO)):
             if self.dist is None:
                 c = _exchange_local(self.ranks, kind)

@@ -221,6 +221,11 @@ int b2s_slab_record_bytes(b2s_ctx* ctx, int kind, uint32_t* bytes);
 int b2s_slab_pack(b2s_ctx* ctx, int kind, void* dev_left, void* dev_right, uint32_t cap_records,
                   uint32_t* nleft, uint32_t* nright);
 int b2s_slab_unpack(b2s_ctx* ctx, int kind, const void* dev_buf, uint32_t count);
+/* Merged exchange of one interaction: migrants and halos in ONE message per neighbour.  counts = {migrants left, migrants right,
+ * halo left, halo right}; each buffer holds the migrant records followed by the halo records.  Migrated particles stay on the
+ * sender as halo ghosts of their new owner.  Needs slabs wider than the halo. */
+int b2s_slab_pack_both(b2s_ctx* ctx, void* dev_left, void* dev_right, uint64_t cap_bytes, uint32_t counts[4]);
+int b2s_slab_unpack_both(b2s_ctx* ctx, const void* dev_buf, uint32_t nmigrants, uint32_t nhalo);
 /* Device address of the three dt maxima {velmax^2, acemax^2, viscdtmax} stored as order-preserving uint32 bit
  * patterns (non-negative floats): all-reduce them with MAX (ncclMax on int32) between b2s_slab_forces and
  * b2s_slab_apply_dt so that every rank computes the same DtVariable (JSphGpu.cpp:1103-1147). */
