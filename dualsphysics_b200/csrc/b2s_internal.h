@@ -42,6 +42,10 @@ typedef uint16_t typecode;
 #define B2S_DCEL_CELL(dcc,cx,cy,cz) (((cx)<<(((dcc)>>10)&31))|((cy)<<(((dcc)>>15)&31))|(cz))
 
 #define B2S_ALMOSTZERO 1e-18f      // DualSphDef.h:114
+// boundary particle modes of mDBC2 (DualSphDef.h:473-475)
+#define B2S_BMODE_DBC 0
+#define B2S_BMODE_MDBC2 1
+#define B2S_BMODE_MDBC2OFF 2
 
 // ---- constants passed by value to every kernel (replaces __constant__ CTE, JSphGpu_ker.cu:39) ----
 struct DevCte {
@@ -60,6 +64,8 @@ struct DevCte {
   uint32_t domcellcode, domcells[3];
   int32_t  scelldiv, tkernel, tvisco, tdensity, tboundary, tstep, use_floating, dt_allparticles, refsem, simulate2d;
   int32_t  gamma_is7;
+  int32_t  mdbc2;                  // SlipMode>=2: boundary neighbours use boundmode/tangenvel (JSphCpu.cpp:851-853,990-995)
+  float dp2;                       // float(Dp*Dp): scaled condition number of mDBC2
 };
 
 // ---- device-resident state of the last cell divide (JCellDivGpu members, JCellDivGpu.h:86-138) ----
@@ -121,6 +127,7 @@ struct b2s_ctx {
   float* spstau; float* spstau_alt; float* spstau_new;   // 6 floats per particle
   // mDBC
   float4* boundnor; float4* boundnor_alt;                 // xyz normal, w unused
+  uint8_t* boundmode; float4* tangenvel;                  // mDBC2 (SlipMode 2/3): per interaction, in the current sorted order
   // interaction inputs/outputs
   float4* posp;      // (x,y,z) relative to own cell origin, w = pressure
   uint4*  posh;      // FP16 copy of posp.xyz in cell units, two particles per 16 B: (x0,x1)(y0,y1)(z0,z1)(-) -- pre-filter of forces_pair2.cu

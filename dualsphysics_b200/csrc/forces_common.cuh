@@ -15,6 +15,7 @@ struct ForcesArgs {
   const float* tau; float* tau_new;   // 6 floats/particle (xx,xy,xz,yy,yz,zz) or NULL
   const float* ftomassp;
   float4* acear;
+  const uint8_t* boundmode; const float4* tangenvel;   // mDBC2 (SlipMode 2/3), else NULL
 };
 
 __device__ __forceinline__ float b2s_rcp(float x){ float r; asm("rcp.approx.ftz.f32 %0, %1;":"=f"(r):"f"(x)); return r; }
@@ -69,11 +70,14 @@ template<int TKER,int TVISCO,int TDENS,bool FLOATING,bool BOUNDP2>
 __device__ __forceinline__ void pair_fluid(const DevCte& c, float drx,float dry,float drz,float rr2,
   const float4 velrhop1,float pressp1,bool ftp1,const float* taup1,
   const float4 velrhop2,float pressp2,typecode codep2,const float* __restrict__ taug,uint32_t p2,
-  const float* __restrict__ ftomassp,float visco,PairAcc& a)
+  const float* __restrict__ ftomassp,float visco,PairAcc& a,const uint8_t* __restrict__ boundmode=nullptr,const float4* __restrict__ tangenvel=nullptr)
 {
   const float fac=kernel_fac<TKER>(rr2,c);
   const float frx=FMUL(fac,drx), fry=FMUL(fac,dry), frz=FMUL(fac,drz);
   float massp2=(BOUNDP2? c.massb: c.massf);
+  //-mDBC2: a boundary particle whose ghost node is not submerged has no mass (JSphCpu.cpp:851-853).
+  const bool m2=(BOUNDP2 && c.mdbc2 && boundmode!=nullptr);
+  if(m2 && boundmode[p2]==B2S_BMODE_MDBC2OFF)massp2=0.f;
   bool ftp2=false;
   if(FLOATING){
     ftp2=B2S_CODE_ISFLOATING(codep2);
@@ -116,6 +120,9 @@ __device__ __forceinline__ void pair_fluid(const DevCte& c, float drx,float dry,
   }
   //-Viscosity.
   {
+    //-mDBC2: the viscous terms see the tangential velocity of the boundary particle (JSphCpu.cpp:990-995).
+    float dvx=FSUB(velrhop1.x,velrhop2.x), dvy=FSUB(velrhop1.y,velrhop2.y), dvz=FSUB(velrhop1.z,velrhop2.z);
+    if(m2){ const float4 tv=tangenvel[p2]; dvx=FSUB(velrhop1.x,tv.x); dvy=FSUB(velrhop1.y,tv.y); dvz=FSUB(velrhop1.z,tv.z); }
     const float dot=b2s_dot3(drx,dry,drz,dvx,dvy,dvz);
     const float dot_rr2=FMUL(dot,ovrr2eta);
     a.visc=fmaxf(dot_rr2,a.visc);

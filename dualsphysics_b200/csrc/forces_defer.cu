@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(D_BS,D_MINB) k_forces_fluid_defer(ForcesArgs g
           const typecode cod2=(FLOATING? g.code[p2]: typecode(0));
           pair_fluid<TKER,TVISCO,TDENS,FLOATING,false>(c,drx,dry,drz,rr2,velrhop1,pressp1,ftp1,taup1,__ldg(g.velrho+p2),pp2.w,cod2,g.tau,p2,g.ftomassp,c.visco_f,af);
         }
-        else pair_fluid<TKER,TVISCO,TDENS,FLOATING,true>(c,drx,dry,drz,rr2,velrhop1,pressp1,ftp1,taup1,__ldg(g.velrho+p2),pp2.w,typecode(0),g.tau,p2,g.ftomassp,c.visco_b,ab);
+        else pair_fluid<TKER,TVISCO,TDENS,FLOATING,true>(c,drx,dry,drz,rr2,velrhop1,pressp1,ftp1,taup1,__ldg(g.velrho+p2),pp2.w,typecode(0),g.tau,p2,g.ftomassp,c.visco_b,ab,g.boundmode,g.tangenvel);
       }
     };
     #pragma unroll 1

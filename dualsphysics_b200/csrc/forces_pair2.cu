@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(P2_BS,P2_MINB) k_forces_fluid_pair2(ForcesArgs
 
 // ------------------------------------------------------------------------------------------------
 bool b2s_forces_pair2_supported(const DevCte& c){
-  return c.tkernel==B2S_KERNEL_WENDLAND && c.tvisco==B2S_VISCO_ARTIFICIAL && !c.use_floating && (2*c.scelldiv+1)<=5;
+  return c.tkernel==B2S_KERNEL_WENDLAND && c.tvisco==B2S_VISCO_ARTIFICIAL && !c.use_floating && !c.mdbc2 && (2*c.scelldiv+1)<=5;
 }
 
 int b2s_forces_pair2_launch(b2s_ctx* ctx, const ForcesArgs& g){

@@ -24,6 +24,7 @@ struct IntegArgs {
   const float4* velrho_aux;   // verlet: velrho(n-1) (or == velrho on Euler steps); symcorr: predicted velrho (rho*)
   const float4* acear;
   int euler;                  // verlet only
+  const uint8_t* boundmode;   // mDBC2 only (else NULL): boundary particles with mode>=BMODE_MDBC2 keep their velrho
 };
 
 // KerUpdatePos / JSphCpu::UpdatePos (JSphCpu.cpp:1458-1510) without periodic boundaries.
@@ -63,8 +64,10 @@ __global__ void __launch_bounds__(I_BS) k_sym_pre(IntegArgs a, const __grid_cons
   const double2 xy=a.posxy_r[p]; const double z=a.posz_r[p];
   if(p<a.ds->npb){
     float4 vr=pre;
-    vr.w=float(double(vr.w)+dt05*double(acear.w));
-    vr.w=(vr.w<c.rhopzero? c.rhopzero: vr.w);
+    if(!a.boundmode || a.boundmode[p]<B2S_BMODE_MDBC2){   // DBC / mDBC vel0 (JSphCpu.cpp:1717)
+      vr.w=float(double(vr.w)+dt05*double(acear.w));
+      vr.w=(vr.w<c.rhopzero? c.rhopzero: vr.w);
+    }
     a.velrho_w[p]=vr; a.posxy_w[p]=xy; a.posz_w[p]=z;
     return;
   }
@@ -104,7 +107,8 @@ __global__ void __launch_bounds__(I_BS) k_sym_corr(IntegArgs a, const __grid_con
   const double epsilon_rdot=(-double(acear.w)/double(rhopred))*dt;
   const float rhonew=float(double(pre.w)*(2.-epsilon_rdot)/(2.+epsilon_rdot));
   if(p<a.ds->npb){
-    a.velrho_w[p]=make_float4(0.f,0.f,0.f,(rhonew<c.rhopzero? c.rhopzero: rhonew));
+    if(a.boundmode && a.boundmode[p]>=B2S_BMODE_MDBC2)a.velrho_w[p]=pre;   // mDBC2: velrho of the start of the step (JSphCpu.cpp:1869-1875)
+    else a.velrho_w[p]=make_float4(0.f,0.f,0.f,(rhonew<c.rhopzero? c.rhopzero: rhonew));
     return;   // boundary positions: unchanged (pos already equals pospre)
   }
   const typecode rcode=a.code[p];
@@ -146,7 +150,8 @@ __global__ void __launch_bounds__(I_BS) k_verlet(IntegArgs a, const __grid_const
   const float4 acear=a.acear[p];
   const float rhonew=float(double(v2.w)+dt2*double(acear.w));
   if(p<a.ds->npb){
-    a.velrho_w[p]=make_float4(0.f,0.f,0.f,(rhonew<c.rhopzero? c.rhopzero: rhonew));
+    if(a.boundmode && a.boundmode[p]>=B2S_BMODE_MDBC2)a.velrho_w[p]=v2;    // mDBC2: ComputeVelrhoBound keeps velrhoold (JSphCpu.cpp:1616)
+    else a.velrho_w[p]=make_float4(0.f,0.f,0.f,(rhonew<c.rhopzero? c.rhopzero: rhonew));
     return;
   }
   const typecode rcode=a.code[p];
@@ -181,6 +186,7 @@ int b2s_integrate_impl(b2s_ctx* ctx, int mode, double dt, bool dt_from_device){
   if(!n)return B2S_OK;
   IntegArgs a; memset(&a,0,sizeof(a));
   a.ds=ctx->div; a.st=ctx->step; a.code=ctx->cur.code; a.dcell=ctx->cur.dcell; a.acear=ctx->acear;
+  a.boundmode=(ctx->prm.slipmode>=B2S_SLIP_NOSLIP? ctx->boundmode: NULL);
   const unsigned g=b2s_blocks(n,I_BS);
   if(mode==1){
     if(ctx->pre_active)return b2s_fail(ctx,B2S_ERR_STATE,"symplectic predictor called twice");

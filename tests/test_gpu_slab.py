@@ -184,13 +184,14 @@ def test_slab_too_thin_is_loud(tmp_path, built_lib):
     ss.close()
 
 
+@pytest.mark.parametrize("slipmode", [1, 2])
 @pytest.mark.parametrize("nranks", [2, 3])
-def test_slab_mdbc_lamsps(nranks, tmp_path, built_lib):
+def test_slab_mdbc_lamsps(nranks, slipmode, tmp_path, built_lib):
     """BASELINE configs[2] in miniature: mDBC boundaries + laminar+SPS viscosity over slabs.  The halo is two kernel radii wide
     so that every rank can recompute the ghost-node density of its boundary ghosts; those sums visit the same fluid particles
     in another order than on the owner, so the result equals the single-context run to rounding (not bit for bit)."""
     H.write_case(tmp_path, dp=0.04, layers=4, normals=True,
-                 params={"Boundary": 2, "SlipMode": 1, "ViscoTreatment": 2, "Visco": 1e-6, "DensityDT": 3})
+                 params={"Boundary": 2, "SlipMode": slipmode, "ViscoTreatment": 2, "Visco": 1e-6, "DensityDT": 3})
     case = str(tmp_path / "Case")
     opts = "-cellmode:half"
     ref = dsb.Simulation(case, options=opts)
@@ -204,6 +205,6 @@ def test_slab_mdbc_lamsps(nranks, tmp_path, built_lib):
     assert np.array_equal(ids, rid[o])
     epos = float(np.max(np.abs(pos - ref.ctx.array("pos")[o])))
     evr = H.rel_err(vr, ref.ctx.array("velrho")[o])
-    print(f"\n[slab mdbc+lamsps x{nranks}] cuts={ss.cuts} owned={ss.owned_counts()} pos_err={epos:.3e} velrho_err={evr:.3e}")
+    print(f"\n[slab mdbc(slip {slipmode})+lamsps x{nranks}] cuts={ss.cuts} owned={ss.owned_counts()} pos_err={epos:.3e} velrho_err={evr:.3e}")
     assert epos < 1e-7 and evr < 1e-5      # the mDBC tolerance of the golden-fixture tests (ill-conditioned 4x4 inverse)
     ss.close(); ref.close()
