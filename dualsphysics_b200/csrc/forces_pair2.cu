@@ -27,6 +27,9 @@
 #define P2_MASK 2            // 1: hits of a row chunk are collected in a bit mask (FP32 test), then evaluated two at a time;
                              // 2: same with the FP16 pre-filter on posh; 0: two consecutive candidates per iteration
 #endif
+#ifndef P2_PIPE
+#define P2_PIPE 0            // 1: body rounds software-pipelined two deep (measured slower: 126 registers or heavy spills, profiles/r01_pair2_tuning.txt)
+#endif
 #ifndef P2_EARLYV
 #define P2_EARLYV 0          // 1: load velrho of both candidates together with posp (no dependent load inside the body)
 #endif
@@ -154,19 +157,34 @@ __global__ void __launch_bounds__(P2_BS,P2_MINB) k_forces_fluid_pair2(ForcesArgs
   #pragma unroll 1
   for(int pass=1;pass>=0;pass--){
     const uint32_t* beg=(pass==0? g.beg+ds->box_fluid: g.beg);   // pass 1: boundary neighbours (first), pass 0: fluid neighbours
-    #pragma unroll 1
-    for(int z=r.cz-d;z<=r.cz+d;z++){
-      const float sz=FADD(pp1.z,c.scell*float(r.cz-z));
-      #pragma unroll 1
-      for(int y=r.cy-d;y<=r.cy+d;y++){
-        const float sy=FADD(pp1.y,c.scell*float(r.cy-y));
-        uint32_t pbeg=0,pend=0,pmid=0;
-        int xa,xb;
-        if(z>=r.zini && z<r.zfin && y>=r.yini && y<r.yfin && row_trim(c,r,xin,sy,sz,xa,xb)){
-          const uint32_t* brow=beg+(y*ncx+z*nsheet);
-          pbeg=brow[xa]; pend=brow[xb];
-          pmid=(oneblk || xmid0<=xa? pbeg: (xmid0>=xb? pend: brow[xmid0]));
+    // Rows (z,y) of the neighbour window, software-pipelined: the begin-table loads of row i+1 are issued before row i is
+    // processed, so their latency (three dependent loads after the trim) hides behind the pair work of the current row.
+    struct Row { uint32_t pbeg,pend,pmid; float sy,sz; };
+    auto setup_row=[&](int z,int y)->Row{
+      Row w; w.pbeg=w.pend=w.pmid=0;
+      w.sz=FADD(pp1.z,c.scell*float(r.cz-z)); w.sy=FADD(pp1.y,c.scell*float(r.cy-y));
+      int xa,xb;
+      if(z>=r.zini && z<r.zfin && y>=r.yini && y<r.yfin){
+        const uint32_t* brow=beg+(y*ncx+z*nsheet);
+        // boundary pass: most fluid particles have no boundary particle anywhere in the row -> two loads settle it, no trim
+        if((pass==0 || brow[r.xini]!=brow[r.xfin]) && row_trim(c,r,xin,w.sy,w.sz,xa,xb)){
+          w.pbeg=brow[xa]; w.pend=brow[xb];
+          w.pmid=(oneblk || xmid0<=xa? w.pbeg: (xmid0>=xb? w.pend: brow[xmid0]));
         }
+      }
+      return w;
+    };
+    const int nrows=(2*d+1)*(2*d+1);
+    int zn=r.cz-d, yn=r.cy-d;
+    Row nextrow=setup_row(zn,yn);
+    #pragma unroll 1
+    for(int irow=0;irow<nrows;irow++){
+      {
+        const Row w=nextrow;
+        if(++yn>r.cy+d){ yn=r.cy-d; zn++; }
+        if(irow+1<nrows)nextrow=setup_row(zn,yn);
+        const uint32_t pbeg=w.pbeg, pend=w.pend, pmid=w.pmid;
+        const float sy=w.sy, sz=w.sz;
         const uint32_t lenmax=__reduce_max_sync(0xffffffffu,pend-pbeg);
 #if P2_MASK==2
         //-Two phases per chunk of 16 candidate PAIRS (32 particles, aligned to even indices):
@@ -192,6 +210,44 @@ __global__ void __launch_bounds__(P2_BS,P2_MINB) k_forces_fluid_pair2(ForcesArgs
           //-Bits of particles outside [pbeg,pend) (first/last pair of the row) are cleared.
           if(pb0<pbeg)mask&=~1u;
           { const uint32_t v=(pend>pb0? pend-pb0: 0u); if(v<32u)mask&=((1u<<v)-1u); }
+#if P2_PIPE
+          //-Rounds, software-pipelined two deep: the gathers (posp, velrho of both hits) of round i+1 are in flight while
+          // round i is evaluated.  Two register sets A/B alternate (loop unrolled by two), no register copies.
+          struct Hit { uint32_t p2a,p2b; bool ok,two; float4 pa,pb,va,vb; };
+          auto fetch=[&](Hit& h){
+            h.ok=(mask!=0u);
+            if(h.ok){
+              const uint32_t ka=__ffs(mask)-1u; mask&=mask-1u;
+              h.two=(mask!=0u);
+              const uint32_t kb=(h.two? __ffs(mask)-1u: ka); mask&=mask-1u;
+              h.p2a=pb0+ka; h.p2b=pb0+kb;
+              h.pa=__ldg(g.posp+h.p2a); h.pb=__ldg(g.posp+h.p2b); h.va=__ldg(g.velrho+h.p2a); h.vb=__ldg(g.velrho+h.p2b);
+            }
+          };
+          auto eval=[&](const Hit& h){
+            if(h.ok){
+              const f2 drx=pk(FSUB(h.p2a>=pmid? sxB: sxA,h.pa.x),FSUB(h.p2b>=pmid? sxB: sxA,h.pb.x));
+              const f2 dry=pk(FSUB(sy,h.pa.y),FSUB(sy,h.pb.y)), drz=pk(FSUB(sz,h.pa.z),FSUB(sz,h.pb.z));
+              const f2 rr2=fma2(drz,drz,fma2(dry,dry,mul2(drx,drx)));   // b2s_rr2 order
+              const float ra=lo(rr2), rb=hi(rr2);
+              const bool ha=(ra<=c.kernelsize2 && ra>=B2S_ALMOSTZERO), hb=(h.two && rb<=c.kernelsize2 && rb>=B2S_ALMOSTZERO);
+              if(ha||hb){
+                if(pass==0)pair2_body<TDENS,false>(c,drx,dry,drz,rr2,ha,hb,velrhop1,pressp1,h.va,h.vb,h.pa.w,h.pb.w,c.visco_f,acc);
+                else       pair2_body<TDENS,true >(c,drx,dry,drz,rr2,ha,hb,velrhop1,pressp1,h.va,h.vb,h.pa.w,h.pb.w,c.visco_b,acc);
+              }
+            }
+          };
+          const uint32_t rounds=(__reduce_max_sync(0xffffffffu,uint32_t(__popc(mask)))+1u)>>1;
+          Hit A,B;
+          if(rounds)fetch(A);
+          #pragma unroll 1
+          for(uint32_t it=0;it<rounds;it+=2){
+            fetch(B); eval(A);
+            if(it+2<rounds)fetch(A);
+            eval(B);
+          }
+        }
+#else
           #pragma unroll 1
           for(uint32_t it=(__reduce_max_sync(0xffffffffu,uint32_t(__popc(mask)))+1u)>>1;it;it--){
             if(mask){
@@ -213,6 +269,7 @@ __global__ void __launch_bounds__(P2_BS,P2_MINB) k_forces_fluid_pair2(ForcesArgs
             }
           }
         }
+#endif
 #elif P2_MASK==1
         //-Two phases per chunk of up to 32 candidates: (1) check every candidate and record the hits in a per-lane bit mask,
         // (2) evaluate the hits two at a time.  Phase 2 only iterates as long as the lane with most hits needs, so the packed
