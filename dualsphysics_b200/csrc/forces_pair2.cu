@@ -21,7 +21,7 @@
 #define P2_BS 128
 #endif
 #ifndef P2_MINB
-#define P2_MINB 6            // resident blocks per SM the register allocation aims at
+#define P2_MINB 7            // resident blocks per SM the register allocation aims at
 #endif
 #ifndef P2_MASK
 #define P2_MASK 2            // 1: hits of a row chunk are collected in a bit mask (FP32 test), then evaluated two at a time;

@@ -158,7 +158,14 @@ def part_observables(datadir, dp):
         ft = (idp >= nfixed + nmoving) & (idp < nb)
         v2 = np.sum(vel[fl].astype(np.float64) ** 2, axis=1)
         near_wall = fl & (pos[:, 0] < 4 * dp)
-        rec = {"t": float(d["part"].get("TimeStep")), "front_x": float(pos[fl, 0].max()),
+        # pressure "gauge": mean Tait pressure of the fluid in the bottom corner of the end wall (x > L-6dp, z < 6dp)
+        rho = d["Rhop"].astype(np.float64)
+        rho0, gamma, cteb = float(d["head"].get("Rhop0")), float(d["head"].get("Gamma")), float(d["head"].get("B"))
+        xwall = float(pos[~fl & (idp < nfixed), 0].max())
+        corner = fl & (pos[:, 0] > xwall - 6 * dp) & (pos[:, 2] < 6 * dp)
+        press_corner = float(np.mean(cteb * ((rho[corner] / rho0) ** gamma - 1.0))) if corner.any() else 0.0
+        rec = {"t": float(d["part"].get("TimeStep")), "front_x": float(pos[fl, 0].max()), "press_corner": press_corner,
+               "ncorner": int(corner.sum()),
                "height_wall": float(pos[near_wall, 2].max()) if near_wall.any() else 0.0,
                "ke": float(0.5 * v2.sum()), "vmax": float(np.sqrt(v2.max())), "nfluid": int(fl.sum())}
         if ft.any():

@@ -11,6 +11,8 @@ measured on B200 over 4213 steps in brackets:
   kinetic energy          1 % of the run's maximum [0.05 %]
   max |v|                 10 % (single particle)   [2.7 %]
   floating-body centre    0.25 dp per axis; the box travels 0.42 m = 21 dp   [0.007 dp]
+  pressure gauge          mean Tait pressure of the fluid in the bottom corner of the end wall (6 dp x 6 dp, ~440 particles):
+                          5 % of its maximum over the run   [1.6 %]
   no particle lost        fluid count identical
 """
 import json
@@ -37,15 +39,19 @@ def test_longrun_observables_match_reference(tmp_path, built_lib):
     assert len(obs) == len(ref)
     dp = fx["spec"]["dp"]
     kemax = max(o["ke"] for o in ref)
-    worst = {"front": 0.0, "height": 0.0, "ke": 0.0, "vmax": 0.0, "ft": 0.0}
+    pmax = max(abs(o["press_corner"]) for o in ref)
+    worst = {"front": 0.0, "height": 0.0, "ke": 0.0, "vmax": 0.0, "ft": 0.0, "press": 0.0}
     for o, g in zip(obs, ref):
         assert abs(o["t"] - g["t"]) < 2e-3, (o["t"], g["t"])          # PARTs are written at the first step past k*TimeOut
         assert o["nfluid"] == g["nfluid"]
         worst["front"] = max(worst["front"], abs(o["front_x"] - g["front_x"]) / dp)
         worst["height"] = max(worst["height"], abs(o["height_wall"] - g["height_wall"]) / dp)
         worst["ke"] = max(worst["ke"], abs(o["ke"] - g["ke"]) / kemax)
+        worst["press"] = max(worst["press"], abs(o["press_corner"] - g["press_corner"]) / pmax)
+        assert o["ncorner"] == g["ncorner"] or abs(o["ncorner"] - g["ncorner"]) <= 2
         worst["vmax"] = max(worst["vmax"], abs(o["vmax"] - g["vmax"]) / max(g["vmax"], 0.5))
         worst["ft"] = max(worst["ft"], float(np.max(np.abs(np.array(o["ft_center"]) - np.array(g["ft_center"])))) / dp)
     print("\n[longrun] worst deviations: " + json.dumps(worst) + f"  (front, height, ft in dp; ke of max; vmax relative); box moved "
           f"{ref[-1]['ft_center'][0] - ref[0]['ft_center'][0]:.3f} m; {r.stdout.strip().splitlines()[-3]}")
     assert worst["front"] < 0.25 and worst["height"] < 0.25 and worst["ke"] < 0.01 and worst["vmax"] < 0.10 and worst["ft"] < 0.25
+    assert worst["press"] < 0.05
