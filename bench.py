@@ -29,9 +29,9 @@ METRIC = "particle-steps/sec (whole box) at 1/2/4/8 B200; interaction-kernel roo
 UNIT = "particle-steps/s"
 OPTIONS = "-symplectic -wendland -viscoart:0.1 -ddt:2 -ddtvalue:0.1 -dbc -cellmode:half" + os.environ.get("B2S_BENCH_EXTRA_OPTS", "")
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the fluid interaction kernel at the 10M-particle
-# workload, from the `ncu --set full` capture summarised in profiles/r01_ncu_forces_pair2_10M.txt (451.1 MB + 139.3 MB);
+# workload, from the `ncu --set full` capture summarised in profiles/r01_ncu_forces_pair2_10M.txt (451.0 MB + 138.9 MB);
 # scaled by the fluid count when the bench runs another size
-NCU_TRAFFIC_BYTES, NCU_TRAFFIC_NPF = 590437888, 9281220
+NCU_TRAFFIC_BYTES, NCU_TRAFFIC_NPF = 589891072, 9281220
 NP_TARGET = int(os.environ.get("B2S_BENCH_NP", "10000000"))
 CPU_SAMPLE_NP = int(os.environ.get("B2S_BENCH_CPU_NP", "1000000"))
 # flop model of SURVEY 8(d): per checked pair 16 flop, per real pair (r<2h) 90 flop
@@ -222,13 +222,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler starts here: the warm-up is the same workload and nvidia-smi needs ~100 ms per sample)
+    sampler = ClockSampler(dev) if rank == 0 else None
     run(warmup)
     # ---- timed steps: CUDA events on the stream the kernels are launched on (the ctx stream), bracketed by
     #      barrier + synchronize; max over ranks.  Wall clock is taken too and must agree.
     kstream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", dev))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(dev) if rank == 0 else None
     ctx.launch_count(reset=True)
     if ss is not None:
         ss.exchanged_bytes = 0
