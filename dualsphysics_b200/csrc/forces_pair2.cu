@@ -210,7 +210,45 @@ __global__ void __launch_bounds__(P2_BS,P2_MINB) k_forces_fluid_pair2(ForcesArgs
           //-Bits of particles outside [pbeg,pend) (first/last pair of the row) are cleared.
           if(pb0<pbeg)mask&=~1u;
           { const uint32_t v=(pend>pb0? pend-pb0: 0u); if(v<32u)mask&=((1u<<v)-1u); }
-#if P2_PIPE
+#if P2_PIPE==2
+          //-Rounds with the position gathers one round ahead: the hit indices and posp of round i+1 are fetched before round i
+          // is evaluated (8 registers of look-ahead instead of 16: velrho is loaded inside the round, behind the dr/rr2 work).
+          struct Hit { uint32_t p2a,p2b; bool ok,two; float4 pa,pb; };
+          auto fetch=[&](Hit& h){
+            h.ok=(mask!=0u);
+            if(h.ok){
+              const uint32_t ka=__ffs(mask)-1u; mask&=mask-1u;
+              h.two=(mask!=0u);
+              const uint32_t kb=(h.two? __ffs(mask)-1u: ka); mask&=mask-1u;
+              h.p2a=pb0+ka; h.p2b=pb0+kb;
+              h.pa=__ldg(g.posp+h.p2a); h.pb=__ldg(g.posp+h.p2b);
+            }
+          };
+          auto eval=[&](const Hit& h){
+            if(h.ok){
+              const float4 va=__ldg(g.velrho+h.p2a), vb=__ldg(g.velrho+h.p2b);
+              const f2 drx=pk(FSUB(h.p2a>=pmid? sxB: sxA,h.pa.x),FSUB(h.p2b>=pmid? sxB: sxA,h.pb.x));
+              const f2 dry=pk(FSUB(sy,h.pa.y),FSUB(sy,h.pb.y)), drz=pk(FSUB(sz,h.pa.z),FSUB(sz,h.pb.z));
+              const f2 rr2=fma2(drz,drz,fma2(dry,dry,mul2(drx,drx)));   // b2s_rr2 order
+              const float ra=lo(rr2), rb=hi(rr2);
+              const bool ha=(ra<=c.kernelsize2 && ra>=B2S_ALMOSTZERO), hb=(h.two && rb<=c.kernelsize2 && rb>=B2S_ALMOSTZERO);
+              if(ha||hb){
+                if(pass==0)pair2_body<TDENS,false>(c,drx,dry,drz,rr2,ha,hb,velrhop1,pressp1,va,vb,h.pa.w,h.pb.w,c.visco_f,acc);
+                else       pair2_body<TDENS,true >(c,drx,dry,drz,rr2,ha,hb,velrhop1,pressp1,va,vb,h.pa.w,h.pb.w,c.visco_b,acc);
+              }
+            }
+          };
+          const uint32_t rounds=(__reduce_max_sync(0xffffffffu,uint32_t(__popc(mask)))+1u)>>1;
+          Hit A,B;
+          if(rounds)fetch(A);
+          #pragma unroll 1
+          for(uint32_t it=0;it<rounds;it+=2){
+            fetch(B); eval(A);
+            if(it+2<rounds)fetch(A);
+            eval(B);
+          }
+        }
+#elif P2_PIPE==1
           //-Rounds, software-pipelined two deep: the gathers (posp, velrho of both hits) of round i+1 are in flight while
           // round i is evaluated.  Two register sets A/B alternate (loop unrolled by two), no register copies.
           struct Hit { uint32_t p2a,p2b; bool ok,two; float4 pa,pb,va,vb; };
