@@ -149,6 +149,8 @@ struct b2s_ctx {
   // slab decomposition (slab.cu)
   bool slab_on; int slab_rank, slab_nranks; uint32_t slab_cxa, slab_cxb; uint32_t* slab_counts; uint8_t* slab_flags; size_t slab_counts_len;
   bool defer_attr_set;   // forces_defer.cu: dynamic shared memory opt-in done
+  // gauges (gauges.cu): device list + results of the last evaluation (device and pinned host)
+  std::vector<int> gauge_types; std::vector<unsigned char> gauges_host; void* gauges_dev; float* gauge_res_dev; float* gauge_res_h; float* gauge_mass_dev; uint32_t gauge_points;
   // scratch for byid download
   void* scratch; size_t scratch_bytes;
 };
@@ -178,6 +180,29 @@ __device__ __forceinline__ float b2s_press(float rho, const DevCte& c){
 }
 #endif
 
+#ifdef __CUDACC__
+// fsph::GetKernel_WabFac (FunSphKernel.h:71-85 cubic, :235-245 Wendland)
+__device__ __forceinline__ float wab_fac(int tkernel,float rr2,const DevCte& c,float& fac){
+  const float rad=sqrtf(rr2);
+  const float qq=rad/c.kernelh;
+  if(tkernel==B2S_KERNEL_WENDLAND){
+    const float wqq1=1.f-0.5f*qq;
+    const float wqq2=wqq1*wqq1;
+    fac=c.bwenh*wqq2*wqq1;
+    const float wqq=qq+qq+1.f;
+    return c.awen*wqq*wqq2*wqq2;
+  }
+  if(rad>c.kernelh){
+    const float wqq1=2.0f-qq; const float wqq2=wqq1*wqq1;
+    fac=(c.cub_c2*wqq2/rad);
+    return c.cub_a24*(wqq2*wqq1);
+  }
+  const float wqq2=qq*qq;
+  fac=((c.cub_c1*qq+c.cub_d1*wqq2)/rad);
+  return c.cub_a2*(1.0f+(0.75f*qq-1.5f)*wqq2);
+}
+#endif
+
 // implemented in the .cu files
 int b2s_celldiv_impl(b2s_ctx* ctx);
 int b2s_forces_impl(b2s_ctx* ctx, int interstep);
@@ -186,3 +211,4 @@ int b2s_mdbc_impl(b2s_ctx* ctx);
 int b2s_floating_impl(b2s_ctx* ctx, double dt, bool predictor, bool dt_from_device);
 int b2s_motion_impl(b2s_ctx* ctx, double timestep, double dt);
 int b2s_sync_info(b2s_ctx* ctx);
+int b2s_gauges_run(b2s_ctx* ctx, int stepdt_ahead);   // gauges.cu: evaluates every gauge on the current particle state

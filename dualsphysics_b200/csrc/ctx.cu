@@ -74,6 +74,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   ctx->verletstep=0;
   ctx->slab_on=false; ctx->slab_rank=0; ctx->slab_nranks=1; ctx->slab_cxa=0; ctx->slab_cxb=0; ctx->slab_counts=NULL; ctx->slab_flags=NULL; ctx->slab_counts_len=0;
   ctx->defer_attr_set=false; ctx->boundmode=NULL; ctx->tangenvel=NULL;
+  ctx->gauges_dev=NULL; ctx->gauge_res_dev=NULL; ctx->gauge_res_h=NULL; ctx->gauge_mass_dev=NULL; ctx->gauge_points=0;
   ctx->ft_massp_dev=NULL; ctx->ft_sums_dev=NULL; ctx->ft_allsums_dev=NULL; ctx->ft_sums_h=NULL; ctx->ft_dev=NULL; ctx->scratch=NULL; ctx->scratch_bytes=0;
   ctx->pospre_xy=ctx->pospre_xy_alt=NULL; ctx->pospre_z=ctx->pospre_z_alt=NULL; ctx->velrhopre=ctx->velrhopre_alt=NULL;
   ctx->velrhom1=ctx->velrhom1_alt=NULL; ctx->spstau=ctx->spstau_alt=ctx->spstau_new=NULL; ctx->boundnor=ctx->boundnor_alt=NULL;
@@ -128,6 +129,7 @@ extern "C" int b2s_destroy(b2s_ctx* ctx){
   cudaFree(ctx->cellpart); cudaFree(ctx->sortpart); cudaFree(ctx->cellpart_alt); cudaFree(ctx->sortpart_alt);
   cudaFree(ctx->begincell); cudaFree(ctx->radix_counts); cudaFree(ctx->ridp);
   cudaFree(ctx->div); cudaFree(ctx->step);
+  cudaFree(ctx->gauges_dev); cudaFree(ctx->gauge_res_dev); cudaFree(ctx->gauge_mass_dev); if(ctx->gauge_res_h)cudaFreeHost(ctx->gauge_res_h);
   cudaFree(ctx->boundmode); cudaFree(ctx->tangenvel); cudaFree(ctx->slab_counts); cudaFree(ctx->slab_flags);
   cudaFree(ctx->ft_massp_dev); cudaFree(ctx->ft_sums_dev); cudaFree(ctx->ft_allsums_dev); cudaFree(ctx->ft_dev); cudaFree(ctx->scratch);
   if(ctx->ft_sums_h)cudaFreeHost(ctx->ft_sums_h);
@@ -462,6 +464,8 @@ static int enqueue_step(b2s_ctx* ctx){
     if(ctx->ftcount){ r=b2s_floating_impl(ctx,0,false,true); if(r)return r; }
   }
   // Run-loop tail (JSphGpuSingle.cpp:1003-1008): RunMotion, RunCellDivide, TimeStep+=dt
+  // RunGaugeSystem(TimeStep+stepdt) (JSphCpuSingle.cpp:1192): new particle state, cell table of the last divide
+  r=b2s_gauges_run(ctx,1); if(r)return r;
   if(!ctx->motions.empty()){ r=b2s_motion_impl(ctx,0,0); if(r)return r; }
   k_step_end<<<1,1,0,ctx->stream>>>(ctx->step,q.tstep==B2S_STEP_SYMPLECTIC? 1: 0); B2S_LAUNCHED(ctx);
   r=b2s_celldiv_impl(ctx); if(r)return r;

@@ -1,0 +1,166 @@
+// gauges.cu -- measurement gauges evaluated on the device every step: velocity at a point and surface water level along a line.
+//
+// Replaces JGaugeVelocity::CalculeCpuT / JGaugeSwl::CalculeCpuT (src/source/JDsGaugeItem.cpp:427-478, 728-790; GPU versions
+// JDsGauge_ker.cu:50-310) as driven by JSphCpuSingle::RunGaugeSystem (JSphCpuSingle.cpp:1118-1125), which the reference calls
+// right after ComputeStep and BEFORE the end-of-step cell divide: the particles already carry the new positions while the cell
+// table is the one of the last divide.  The same state is used here (double positions, current begin table).
+//   velocity: sum over fluid neighbours of W(r) m/rho * v (no kernel correction)
+//   SWL     : mass(pt)=sum W(r) m/rho * m at PointNp+1 points from point0 towards point2; the surface is where the mass
+//             falls below MassLimit, linearly interpolated between the two points around the crossing.
+// Timing (computedt/outputdt) is the host's business (csrc/host/sim.cpp): the device evaluates all gauges after every step
+// (a few microseconds) so that no host round trip is needed to know the time first.
+#include "b2s_internal.h"
+#include <float.h>
+
+#define G_BS 128
+enum { GAUGE_VEL=1, GAUGE_SWL=2 };
+struct GaugeDev { int type; uint32_t np, first; float masslimit; double p0[3], dir[3]; };
+
+// fluid neighbours of a point: returns sum W m/rho (and the velocity sums)
+__device__ void gauge_point(const DivState* ds,const uint32_t* begt,const double2* posxy,const double* posz,const typecode* code,
+  const float4* velrho,const DevCte& c,double px,double py,double pz,double& sumwab,double& svx,double& svy,double& svz)
+{
+  sumwab=svx=svy=svz=0;
+  // nsearch::Init (JCellSearch_inline.h): cell of the point relative to the cell domain, window clipped to the domain
+  const int cx=int((px-c.domposmin[0])/c.scell_d)-int(ds->cellmin[0]);
+  const int cy=int((py-c.domposmin[1])/c.scell_d)-int(ds->cellmin[1]);
+  const int cz=int((pz-c.domposmin[2])/c.scell_d)-int(ds->cellmin[2]);
+  const int d=c.scelldiv, ncx=int(ds->ncx), ncy=int(ds->ncy), ncz=int(ds->ncz), nsheet=int(ds->nsheet);
+  const int xini=cx-min(cx,d), xfin=cx+min(ncx-cx-1,d)+1;
+  const int yini=cy-min(cy,d), yfin=cy+min(ncy-cy-1,d)+1;
+  const int zini=cz-min(cz,d), zfin=cz+min(ncz-cz-1,d)+1;
+  if(xini<0 || yini<0 || zini<0 || xfin<=xini)return;
+  const uint32_t* beg=begt+ds->box_fluid;
+  for(int z=zini;z<zfin;z++)for(int y=yini;y<yfin;y++){
+    const uint32_t pini=beg[y*ncx+z*nsheet+xini], pfin=beg[y*ncx+z*nsheet+xfin];
+    for(uint32_t p2=pini;p2<pfin;p2++){
+      const double2 xy=posxy[p2];
+      const float drx=float(px-xy.x), dry=float(py-xy.y), drz=float(pz-posz[p2]);
+      const float rr2=drx*drx+dry*dry+drz*drz;
+      if(rr2<=c.kernelsize2 && rr2>=B2S_ALMOSTZERO && B2S_CODE_ISFLUID(code[p2])){
+        float fac;
+        float wab=wab_fac(c.tkernel,rr2,c,fac);
+        const float4 v=velrho[p2];
+        wab*=c.massf/v.w;
+        sumwab+=wab; svx+=wab*v.x; svy+=wab*v.y; svz+=wab*v.z;
+      }
+    }
+  }
+}
+
+// one thread per measurement point (velocity gauges have one, SWL gauges PointNp+1)
+__global__ void __launch_bounds__(G_BS) k_gauge_points(const GaugeDev* __restrict__ gs, uint32_t ng, uint32_t npoints, const DivState* ds,
+  const uint32_t* __restrict__ begt, const double2* __restrict__ posxy, const double* __restrict__ posz, const typecode* __restrict__ code,
+  const float4* __restrict__ velrho, float* mass, float* res, const __grid_constant__ DevCte c)
+{
+  const uint32_t i=blockIdx.x*blockDim.x+threadIdx.x;
+  if(i>=npoints)return;
+  uint32_t cg=0;
+  while(cg+1<ng && gs[cg+1].first<=i)cg++;
+  const GaugeDev& gd=gs[cg];
+  const uint32_t cp=i-gd.first;
+  const double px=gd.p0[0]+gd.dir[0]*double(cp), py=gd.p0[1]+gd.dir[1]*double(cp), pz=gd.p0[2]+gd.dir[2]*double(cp);
+  double sw,vx,vy,vz;
+  gauge_point(ds,begt,posxy,posz,code,velrho,c,px,py,pz,sw,vx,vy,vz);
+  if(gd.type==GAUGE_VEL){ res[cg*4]=float(vx); res[cg*4+1]=float(vy); res[cg*4+2]=float(vz); res[cg*4+3]=0.f; }
+  else mass[i]=float(sw*double(c.massf));
+}
+// SWL: the sequential search of JGaugeSwl::CalculeCpuT (JDsGaugeItem.cpp:770-782), one thread per gauge
+__global__ void k_gauge_swl(const GaugeDev* __restrict__ gs, uint32_t ng, const float* __restrict__ mass, float* res){
+  const uint32_t cg=blockIdx.x*blockDim.x+threadIdx.x;
+  if(cg>=ng || gs[cg].type!=GAUGE_SWL)return;
+  const GaugeDev& gd=gs[cg];
+  const uint32_t pointnp=gd.np-1;
+  double sx=DBL_MAX,sy=0,sz=0;
+  float mpre=0;
+  double px=gd.p0[0],py=gd.p0[1],pz=gd.p0[2];
+  for(uint32_t cp=0;cp<=pointnp;cp++){
+    const float m=mass[gd.first+cp];
+    if(m>gd.masslimit)mpre=m;
+    if(m<gd.masslimit && mpre){
+      const float fxm1=(gd.masslimit-mpre)/(m-mpre)-1;
+      sx=px+gd.dir[0]*double(fxm1); sy=py+gd.dir[1]*double(fxm1); sz=pz+gd.dir[2]*double(fxm1);
+      break;
+    }
+    px+=gd.dir[0]; py+=gd.dir[1]; pz+=gd.dir[2];
+  }
+  if(sx==DBL_MAX){ const double k=(mpre? double(pointnp): 0.0); sx=gd.p0[0]+gd.dir[0]*k; sy=gd.p0[1]+gd.dir[1]*k; sz=gd.p0[2]+gd.dir[2]*k; }
+  res[cg*4]=float(sx); res[cg*4+1]=float(sy); res[cg*4+2]=float(sz); res[cg*4+3]=0.f;
+}
+
+static int gauges_upload(b2s_ctx* ctx, const std::vector<GaugeDev>& h){
+  cudaFree(ctx->gauges_dev); cudaFree(ctx->gauge_res_dev); cudaFree(ctx->gauge_mass_dev); if(ctx->gauge_res_h)cudaFreeHost(ctx->gauge_res_h);
+  ctx->gauges_dev=NULL; ctx->gauge_res_dev=NULL; ctx->gauge_mass_dev=NULL; ctx->gauge_res_h=NULL;
+  const size_t ng=h.size();
+  B2S_CUDA(ctx,cudaMalloc(&ctx->gauges_dev,sizeof(GaugeDev)*ng));
+  B2S_CUDA(ctx,cudaMalloc((void**)&ctx->gauge_res_dev,sizeof(float)*4*ng));
+  B2S_CUDA(ctx,cudaMalloc((void**)&ctx->gauge_mass_dev,sizeof(float)*std::max<size_t>(ctx->gauge_points,1)));
+  B2S_CUDA(ctx,cudaMallocHost((void**)&ctx->gauge_res_h,sizeof(float)*4*ng));
+  B2S_CUDA(ctx,cudaMemcpy(ctx->gauges_dev,h.data(),sizeof(GaugeDev)*ng,cudaMemcpyHostToDevice));
+  B2S_CUDA(ctx,cudaMemset(ctx->gauge_res_dev,0,sizeof(float)*4*ng));
+  return B2S_OK;
+}
+// the host copy of the gauge list lives in the ctx as raw bytes (GaugeDev is private to this file)
+static std::vector<GaugeDev> host_list(b2s_ctx* ctx){
+  std::vector<GaugeDev> h(ctx->gauges_host.size()/sizeof(GaugeDev));
+  if(!h.empty())memcpy(h.data(),ctx->gauges_host.data(),ctx->gauges_host.size());
+  return h;
+}
+static void host_store(b2s_ctx* ctx,const std::vector<GaugeDev>& h){
+  ctx->gauges_host.resize(h.size()*sizeof(GaugeDev));
+  if(!h.empty())memcpy(ctx->gauges_host.data(),h.data(),ctx->gauges_host.size());
+}
+
+extern "C" int b2s_gauge_add_velocity(b2s_ctx* ctx, const double point[3], int* id){
+  if(!ctx || !point)return B2S_ERR_ARG;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  std::vector<GaugeDev> h=host_list(ctx);
+  GaugeDev g; memset(&g,0,sizeof(g)); g.type=GAUGE_VEL; g.np=1; g.first=ctx->gauge_points;
+  for(int k=0;k<3;k++)g.p0[k]=point[k];
+  h.push_back(g); ctx->gauge_types.push_back(GAUGE_VEL); ctx->gauge_points+=1;
+  host_store(ctx,h);
+  if(id)*id=int(h.size())-1;
+  return gauges_upload(ctx,h);
+}
+extern "C" int b2s_gauge_add_swl(b2s_ctx* ctx, const double point0[3], const double point2[3], double pointdp, float masslimit, int* id){
+  if(!ctx || !point0 || !point2 || pointdp<=0 || masslimit<=0)return B2S_ERR_ARG;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  std::vector<GaugeDev> h=host_list(ctx);
+  // JGaugeSwl::SetPoints (JDsGaugeItem.cpp:614-633)
+  double dv[3]={point2[0]-point0[0],point2[1]-point0[1],point2[2]-point0[2]};
+  const double dis=sqrt(dv[0]*dv[0]+dv[1]*dv[1]+dv[2]*dv[2]);
+  if(!(dis>0))return b2s_fail(ctx,B2S_ERR_ARG,"swl gauge: point0 and point2 coincide");
+  unsigned pointnp=unsigned(dis/pointdp);
+  if(dis-(pointdp*pointnp)>=pointdp*0.1)pointnp++;
+  if(pointnp<1)pointnp++;
+  const double dp=dis/pointnp;
+  GaugeDev g; memset(&g,0,sizeof(g)); g.type=GAUGE_SWL; g.np=pointnp+1; g.first=ctx->gauge_points; g.masslimit=masslimit;
+  for(int k=0;k<3;k++){ g.p0[k]=point0[k]; g.dir[k]=dv[k]/dis*dp; }
+  h.push_back(g); ctx->gauge_types.push_back(GAUGE_SWL); ctx->gauge_points+=g.np;
+  host_store(ctx,h);
+  if(id)*id=int(h.size())-1;
+  return gauges_upload(ctx,h);
+}
+int b2s_gauges_run(b2s_ctx* ctx, int){
+  const uint32_t ng=uint32_t(ctx->gauge_types.size());
+  if(!ng)return B2S_OK;
+  cudaStream_t s=ctx->stream;
+  k_gauge_points<<<b2s_blocks(ctx->gauge_points,G_BS),G_BS,0,s>>>((const GaugeDev*)ctx->gauges_dev,ng,ctx->gauge_points,ctx->div,(const uint32_t*)ctx->begincell,
+    ctx->cur.posxy,ctx->cur.posz,ctx->cur.code,ctx->cur.velrho,ctx->gauge_mass_dev,ctx->gauge_res_dev,ctx->cte); B2S_LAUNCHED(ctx);
+  k_gauge_swl<<<b2s_blocks(ng,32),32,0,s>>>((const GaugeDev*)ctx->gauges_dev,ng,ctx->gauge_mass_dev,ctx->gauge_res_dev); B2S_LAUNCHED(ctx);
+  B2S_CUDA(ctx,cudaMemcpyAsync(ctx->gauge_res_h,ctx->gauge_res_dev,sizeof(float)*4*ng,cudaMemcpyDeviceToHost,s));
+  B2S_CUDA(ctx,cudaGetLastError());
+  return B2S_OK;
+}
+extern "C" int b2s_gauges_compute(b2s_ctx* ctx){
+  if(!ctx)return B2S_ERR_ARG;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  int r=b2s_gauges_run(ctx,0); if(r)return r;
+  B2S_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  return B2S_OK;
+}
+extern "C" int b2s_gauge_result(b2s_ctx* ctx, int id, float out[3]){
+  if(!ctx || !out || id<0 || size_t(id)>=ctx->gauge_types.size() || !ctx->gauge_res_h)return B2S_ERR_ARG;
+  for(int k=0;k<3;k++)out[k]=ctx->gauge_res_h[id*4+k];
+  return B2S_OK;
+}

@@ -33,12 +33,22 @@ struct PartBlock { int type; unsigned mktype, mk, begin, count; // type: 0 fixed
   double massbody, masspart, center[3], inertia[9], linvelini[3], angvelini[3]; int transfree[3], rotfree[3]; unsigned refmotion; };
 struct MotionCfg { unsigned ref; double freq[3], ampl[3], phase[3], tstart, tend; };
 
+// One gauge of <special><gauges> (JGaugeSystem::ReadXml, JDsGaugeSystem.cpp:244-330) with the timing state of JGaugeItem
+struct GaugeCfg {
+  std::string name; int type;            // 1 velocity, 2 swl
+  double point[3], point0[3], point2[3], pointdp; float masslimit;
+  double computedt, computestart, computeend, outputdt, outputstart, outputend; bool output;
+  double computenext, outputnext; int id; bool headdone;
+  GaugeCfg():type(0),pointdp(0),masslimit(0),computedt(0),computestart(0),computeend(0),outputdt(0),outputstart(0),outputend(0),output(false),computenext(0),outputnext(0),id(-1),headdone(false){}
+};
+
 struct b2s_sim {
   std::string casepath, casename, dirout, dirdata, err;
   b2s_params prm;
   b2s_ctx* ctx;
   std::vector<PartBlock> blocks;
   std::vector<MotionCfg> motions;
+  std::vector<GaugeCfg> gauges;
   // run control (JSph members)
   double timemax, timepart, timepartnext; unsigned part, nstepsbreak; bool svallsteps, svposdouble, svdata;
   double casedp, caseh, caseb, caserhop0, casegamma, casemassb, casemassf;
@@ -231,6 +241,52 @@ static void load_case(b2s_sim* s,const std::string& options){
   p.casenfixed=cnt[0]; p.casenmoving=cnt[1]; p.casenfloat=cnt[2]; p.casenfluid=cnt[3]; p.casenp=cnt[0]+cnt[1]+cnt[2]+cnt[3];
   { const unsigned np=unsigned(strtoul(pa->attr("np","0").c_str(),NULL,10)), nb=unsigned(strtoul(pa->attr("nb","0").c_str(),NULL,10)), nbf=unsigned(strtoul(pa->attr("nbf","0").c_str(),NULL,10));
     if(np!=p.casenp || nb!=p.casenp-p.casenfluid || nbf!=p.casenfixed)throw std::runtime_error("The amount of particles does not match the header."); }
+  // -- gauges (JGaugeSystem::LoadXml "case.execution.special.gauges"): velocity and swl
+  if(const XmlNode* sp=exe->child("special")){
+    if(const XmlNode* gs=sp->child("gauges")){
+      struct Def { double cdt,cs,ce,odt,os,oe; bool out; } def={-1,0,-1,-1,0,-1,false};   // <0: TimeOut / TimeMax, resolved after the command-line options
+      auto common=[&](const XmlNode* e,Def d)->Def{
+        if(!e)return d;
+        if(const XmlNode* c=e->child("computedt"))d.cdt=todouble(c->attr("value","0"));
+        if(const XmlNode* c=e->child("computetime")){ if(c->has("start"))d.cs=todouble(c->attr("start")); if(c->has("end"))d.ce=todouble(c->attr("end")); }
+        if(const XmlNode* c=e->child("output")){ const std::string v=lower(c->attr("value","false")); d.out=(v=="true"||v=="1"); }
+        if(const XmlNode* c=e->child("outputdt"))d.odt=todouble(c->attr("value","0"));
+        if(const XmlNode* c=e->child("outputtime")){ if(c->has("start"))d.os=todouble(c->attr("start")); if(c->has("end"))d.oe=todouble(c->attr("end")); }
+        return d;
+      };
+      def=common(gs->child("default"),def);
+      for(auto& cu:gs->children){
+        const XmlNode* c=cu.get();
+        if(c->name.empty() || c->name[0]=='_' || c->name=="default")continue;
+        const std::string act=lower(c->attr("active","true"));
+        if(act=="false"||act=="0")continue;
+        GaugeCfg g; g.name=c->attr("name");
+        if(g.name.empty())throw std::runtime_error("gauge without name");
+        for(auto& o:s->gauges)if(o.name==g.name)throw std::runtime_error("The gauge name '"+g.name+"' already exists.");
+        const Def d=common(c,def);
+        g.computedt=d.cdt; g.computestart=d.cs; g.computeend=d.ce; g.outputdt=d.odt; g.outputstart=d.os; g.outputend=d.oe; g.output=d.out;
+        if(c->name=="velocity"){
+          g.type=1;
+          if(!read_xyz(c->child("point"),g.point))throw std::runtime_error("gauge velocity: <point> missing");
+        }
+        else if(c->name=="swl"){
+          g.type=2;
+          if(!read_xyz(c->child("point0"),g.point0)||!read_xyz(c->child("point2"),g.point2))throw std::runtime_error("gauge swl: point0/point2 missing");
+          const XmlNode* pd=c->child("pointdp");
+          if(pd && pd->has("coefdp"))g.pointdp=p.dp*atof(pd->attr("coefdp").c_str());
+          else if(pd)g.pointdp=double(float(atof(pd->attr("value","0").c_str())));
+          if(g.pointdp<=0)throw std::runtime_error("gauge swl: the pointdp is invalid");
+          const XmlNode* ml=c->child("masslimit");
+          if(ml && ml->has("value"))g.masslimit=float(atof(ml->attr("value").c_str()));
+          else if(ml && ml->has("coef"))g.masslimit=p.massfluid*float(atof(ml->attr("coef").c_str()));
+          else g.masslimit=p.massfluid*(p.simulate2d? 0.4f: 0.5f);
+          if(g.masslimit<=0)throw std::runtime_error("gauge swl: the masslimit is invalid");
+        }
+        else throw std::runtime_error("gauge <"+c->name+"> is not supported by this build (velocity, swl)");
+        s->gauges.push_back(g);
+      }
+    }
+  }
   // -- motion (JMotion::ReadXml subset: objreal + mvrectsinu)
   if(const XmlNode* mo=exe->child("motion")){
     for(const XmlNode* o:mo->childs("objreal")){
@@ -410,6 +466,13 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
     r=b2s_add_motion_rectsinu(s->ctx,blk->begin,blk->count,m.freq,m.ampl,m.phase,m.tstart,m.tend);
     if(r)throw std::runtime_error(std::string("b2s_add_motion_rectsinu failed: ")+b2s_last_error(s->ctx));
   }
+  for(auto& g:s->gauges){
+    if(g.computedt<0)g.computedt=s->timepart;  if(g.computeend<0)g.computeend=s->timemax;     // JGaugeSystem::ResetCfgDefault
+    if(g.outputdt<0)g.outputdt=s->timepart;    if(g.outputend<0)g.outputend=s->timemax;
+    if(g.type==1)r=b2s_gauge_add_velocity(s->ctx,g.point,&g.id);
+    else r=b2s_gauge_add_swl(s->ctx,g.point0,g.point2,g.pointdp,g.masslimit,&g.id);
+    if(r)throw std::runtime_error(std::string("gauge '")+g.name+"' failed: "+b2s_last_error(s->ctx));
+  }
   std::vector<float> nor;
   const float* norp=NULL;
   if(p.tboundary==B2S_BC_MDBC){
@@ -510,6 +573,29 @@ static void save_part(b2s_sim* s){
   }
 }
 
+// ---- gauges: JGaugeItem::Update/SetTimeStep/Output/StoreResult + SaveResults (JDsGaugeItem.h:274-275, .cpp:239-249,360-403,654-700)
+static void gauges_record(b2s_sim* s,double t){
+  for(auto& g:s->gauges){
+    if(!(t>=g.computenext && g.computestart<=t && t<=g.computeend))continue;
+    if(g.computedt){ const unsigned nt=unsigned(t/g.computedt); g.computenext=g.computedt*nt; if(g.computenext<=t)g.computenext=g.computedt*(nt+1); }
+    float res[3]={0,0,0};
+    if(b2s_gauge_result(s->ctx,g.id,res))throw std::runtime_error("gauge result not available");
+    if(!(g.output && t>=g.outputnext && g.outputstart<=t && t<=g.outputend) || s->dirout.empty())continue;
+    const std::string fn=s->dirout+(g.type==1? "GaugesVel_": "GaugesSWL_")+g.name+".csv";
+    FILE* f=fopen(fn.c_str(),g.headdone? "a": "w");
+    if(!f)throw std::runtime_error("cannot write "+fn);
+    if(!g.headdone){
+      fputs(g.type==1? "time [s];velx [m/s];vely [m/s];velz [m/s];posx [m];posy [m];posz [m]\n"
+                     : "time [s];swlx [m];swly [m];swlz [m];pos0x [m];pos0y [m];pos0z [m];pos2x [m];pos2y [m];pos2z [m]\n",f);
+      g.headdone=true;
+    }
+    if(g.type==1)fprintf(f,"%f;%g;%g;%g;%g;%g;%g\n",t,res[0],res[1],res[2],float(g.point[0]),float(g.point[1]),float(g.point[2]));
+    else fprintf(f,"%f;%g;%g;%g;%g;%g;%g;%g;%g;%g\n",t,res[0],res[1],res[2],float(g.point0[0]),float(g.point0[1]),float(g.point0[2]),float(g.point2[0]),float(g.point2[1]),float(g.point2[2]));
+    fclose(f);
+    if(g.outputdt){ const unsigned nt=unsigned(t/g.outputdt); g.outputnext=g.outputdt*nt; if(g.outputnext<=t)g.outputnext=g.outputdt*(nt+1); }
+  }
+}
+
 // ---- C entry points ---------------------------------------------------------------------------------------
 extern "C" const char* b2s_host_last_error(void){ return g_host_err.c_str(); }
 
@@ -573,6 +659,10 @@ extern "C" int b2s_sim_run(b2s_sim* s,uint32_t nsteps_break,double* time_out,uin
   const bool save=(s->svdata && !s->dirdata.empty());
   try{
     b2s_info inf; int r=b2s_get_info(s->ctx,&inf); if(r){ g_host_err=b2s_last_error(s->ctx); return r; }
+    if(!s->gauges.empty() && inf.nstep==0){   // initial measurement (JSphCpuSingle.cpp:1110-1111)
+      r=b2s_gauges_compute(s->ctx); if(r){ g_host_err=b2s_last_error(s->ctx); return r; }
+      gauges_record(s,inf.timestep);
+    }
     if(save && s->part==0){ save_part(s); s->part++; s->timepartnext=(s->svallsteps? inf.timestep: s->timepart); }
     unsigned nstep=0;
     double t=inf.timestep;
@@ -583,6 +673,7 @@ extern "C" int b2s_sim_run(b2s_sim* s,uint32_t nsteps_break,double* time_out,uin
       r=b2s_get_info(s->ctx,&inf); if(r){ g_host_err=b2s_last_error(s->ctx); return r; }
       t=inf.timestep; nstep++;
       s->part_dtmin=std::min(s->part_dtmin,dt); s->part_dtmax=std::max(s->part_dtmax,dt);
+      if(!s->gauges.empty())gauges_record(s,t);
       if(save && t>=s->timepartnext){
         save_part(s); s->part++;
         if(s->svallsteps)s->timepartnext=t;

@@ -14,26 +14,6 @@
 
 __device__ __forceinline__ float m_rcp(float x){ float r; asm("rcp.approx.ftz.f32 %0, %1;":"=f"(r):"f"(x)); return r; }
 
-// fsph::GetKernel_WabFac (FunSphKernel.h:71-85 cubic, :235-245 Wendland)
-__device__ __forceinline__ float wab_fac(int tkernel,float rr2,const DevCte& c,float& fac){
-  const float rad=sqrtf(rr2);
-  const float qq=rad/c.kernelh;
-  if(tkernel==B2S_KERNEL_WENDLAND){
-    const float wqq1=1.f-0.5f*qq;
-    const float wqq2=wqq1*wqq1;
-    fac=c.bwenh*wqq2*wqq1;
-    const float wqq=qq+qq+1.f;
-    return c.awen*wqq*wqq2*wqq2;
-  }
-  if(rad>c.kernelh){
-    const float wqq1=2.0f-qq; const float wqq2=wqq1*wqq1;
-    fac=(c.cub_c2*wqq2/rad);
-    return c.cub_a24*(wqq2*wqq1);
-  }
-  const float wqq2=qq*qq;
-  fac=((c.cub_c1*qq+c.cub_d1*wqq2)/rad);
-  return c.cub_a2*(1.0f+(0.75f*qq-1.5f)*wqq2);
-}
 
 __global__ void __launch_bounds__(M_BS) k_mdbc_vel0(const DivState* __restrict__ ds, const uint32_t* __restrict__ begt,
   const double2* __restrict__ posxy, const double* __restrict__ posz, const typecode* __restrict__ code, const float4* __restrict__ boundnor,

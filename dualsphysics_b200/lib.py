@@ -90,6 +90,7 @@ ABI_SYMBOLS = [
     "b2s_get_info", "b2s_celldiv", "b2s_interaction", "b2s_compute_verlet", "b2s_compute_symplectic_pre",
     "b2s_compute_symplectic_corr", "b2s_compute_step", "b2s_run_steps", "b2s_add_motion_rectsinu",
     "b2s_move_linear", "b2s_set_floatings", "b2s_get_floatings", "b2s_count_pairs", "b2s_time_interaction",
+    "b2s_gauge_add_velocity", "b2s_gauge_add_swl", "b2s_gauges_compute", "b2s_gauge_result",
     "b2s_launch_count", "b2s_get_stream", "b2s_set_interaction_variant", "b2s_slab_config",
     "b2s_slab_histogram", "b2s_slab_set_range", "b2s_slab_drop_ghosts", "b2s_slab_record_bytes", "b2s_slab_pack", "b2s_slab_unpack", "b2s_slab_pack_both", "b2s_slab_unpack_both", "b2s_slab_dt_buffer", "b2s_slab_forces",
     "b2s_slab_apply_dt", "b2s_slab_integrate", "b2s_slab_step_end", "b2s_slab_ft_sums", "b2s_slab_ft_apply",
@@ -145,6 +146,10 @@ def load_library():
     lib.b2s_launch_count.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
     lib.b2s_get_stream.argtypes = [vp, C.POINTER(vp)]
     lib.b2s_set_interaction_variant.argtypes = [vp, C.c_int]
+    lib.b2s_gauge_add_velocity.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    lib.b2s_gauge_add_swl.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_float, C.POINTER(C.c_int)]
+    lib.b2s_gauges_compute.argtypes = [vp]
+    lib.b2s_gauge_result.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     lib.b2s_slab_config.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32]
     lib.b2s_slab_histogram.argtypes = [vp, vp]
     lib.b2s_slab_set_range.argtypes = [vp, C.c_uint32, C.c_uint32]
@@ -367,6 +372,25 @@ class Context:
         p = C.c_void_p()
         self._chk(self._lib.b2s_get_stream(self._h, C.byref(p)))
         return p.value
+
+    # ---- gauges
+    def gauge_add_velocity(self, point):
+        gid = C.c_int(0)
+        self._chk(self._lib.b2s_gauge_add_velocity(self._h, (C.c_double * 3)(*point), C.byref(gid)))
+        return gid.value
+
+    def gauge_add_swl(self, point0, point2, pointdp, masslimit):
+        gid = C.c_int(0)
+        self._chk(self._lib.b2s_gauge_add_swl(self._h, (C.c_double * 3)(*point0), (C.c_double * 3)(*point2), pointdp, masslimit, C.byref(gid)))
+        return gid.value
+
+    def gauges_compute(self):
+        self._chk(self._lib.b2s_gauges_compute(self._h))
+
+    def gauge_result(self, gid):
+        out = (C.c_float * 3)()
+        self._chk(self._lib.b2s_gauge_result(self._h, gid, out))
+        return [out[0], out[1], out[2]]
 
     def set_floatings(self, fts):
         arr = (Floating * len(fts))(*fts)

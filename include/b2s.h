@@ -190,6 +190,15 @@ int b2s_move_linear(b2s_ctx* ctx, uint32_t idbegin, uint32_t count, const double
 int b2s_set_floatings(b2s_ctx* ctx, uint32_t ftcount, const b2s_floating* fts);
 int b2s_get_floatings(b2s_ctx* ctx, uint32_t ftcount, b2s_floating* fts);
 
+/* ---- gauges: JGaugeVelocity / JGaugeSwl (JDsGaugeItem.cpp:427-478,728-790), evaluated on the device after every step at the
+ * point of the step where the reference calls RunGaugeSystem (JSphCpuSingle.cpp:1192).  The timing rules (computedt/outputdt)
+ * and the Gauges*.csv files are the host driver's (b2s_host.h); b2s_gauge_result returns the last evaluation:
+ * velocity (vx,vy,vz) or the surface point (x,y,z).  b2s_gauges_compute evaluates them now (initial measurement at t=0). */
+int b2s_gauge_add_velocity(b2s_ctx* ctx, const double point[3], int* id);
+int b2s_gauge_add_swl(b2s_ctx* ctx, const double point0[3], const double point2[3], double pointdp, float masslimit, int* id);
+int b2s_gauges_compute(b2s_ctx* ctx);
+int b2s_gauge_result(b2s_ctx* ctx, int id, float out[3]);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Counts candidate / real (r<2h) pairs of the current neighbour list (what JDsPips reports,
  * JDsPips.cpp:116-142) for the flop model. */
