@@ -247,6 +247,15 @@ extern "C" int b2s_upload_particles(b2s_ctx* ctx, uint32_t np, const uint32_t* i
   return b2s_sync_info(ctx);
 }
 
+__global__ void k_set_time(StepState* st, double timestep, double dtpre){ st->timestep=timestep; if(dtpre>0){ st->symplectic_dtpre=dtpre; st->dt=dtpre; } }
+// Restart: simulated time and (Symplectic) the dt of the next step, as stored in the PART the run continues from.
+extern "C" int b2s_set_time(b2s_ctx* ctx, double timestep, double symplectic_dtpre){
+  if(!ctx || !(timestep>=0))return B2S_ERR_ARG;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  k_set_time<<<1,1,0,ctx->stream>>>(ctx->step,timestep,symplectic_dtpre); B2S_LAUNCHED(ctx);
+  return b2s_sync_info(ctx);
+}
+
 extern "C" int b2s_download_particles(b2s_ctx* ctx, uint32_t* np_out, uint32_t* idp, uint16_t* code, double* pos, float* velrho){
   if(!ctx)return B2S_ERR_ARG;
   int r=b2s_sync_info(ctx); if(r)return r;

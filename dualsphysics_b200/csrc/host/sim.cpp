@@ -49,6 +49,7 @@ struct b2s_sim {
   std::vector<PartBlock> blocks;
   std::vector<MotionCfg> motions;
   std::vector<GaugeCfg> gauges;
+  bool initial_saved, head_saved; unsigned partbegin, partbeginfirst; std::string partbegindir; double partbegintime, partbegindtpre;   // restart (-partbegin)
   // run control (JSph members)
   double timemax, timepart, timepartnext; unsigned part, nstepsbreak; bool svallsteps, svposdouble, svdata;
   double casedp, caseh, caseb, caserhop0, casegamma, casemassb, casemassf;
@@ -56,7 +57,7 @@ struct b2s_sim {
   unsigned np0;
   std::vector<uint32_t> slab_cuts; uint32_t slab_maxplane;   // slab loading (b2s_sim_load_slab)
   std::string runcode, date; unsigned part_nstep0; double part_time0, part_dtmin, part_dtmax;   // PART header / PartInfo statistics
-  b2s_sim():slab_maxplane(0),part_nstep0(0),part_time0(0),part_dtmin(DBL_MAX),part_dtmax(0),ctx(NULL),timemax(0),timepart(0),timepartnext(0),part(0),nstepsbreak(0),svallsteps(false),svposdouble(false),svdata(true),np0(0){
+  b2s_sim():initial_saved(false),head_saved(false),partbegin(0),partbeginfirst(0),partbegintime(0),partbegindtpre(0),slab_maxplane(0),part_nstep0(0),part_time0(0),part_dtmin(DBL_MAX),part_dtmax(0),ctx(NULL),timemax(0),timepart(0),timepartnext(0),part(0),nstepsbreak(0),svallsteps(false),svposdouble(false),svdata(true),np0(0){
     memset(&prm,0,sizeof(prm));
     // RunCode (8 random characters) and Date like JSph::CalcRunCode / fun::GetDateTime
     const time_t now=time(NULL); char buf[64]; strftime(buf,sizeof(buf),"%d-%m-%Y %H:%M:%S",localtime(&now)); date=buf;
@@ -181,6 +182,11 @@ static void load_case(b2s_sim* s,const std::string& options){
       else if(w=="TMAX")s->timemax=atof(a.c_str());
       else if(w=="TOUT")s->timepart=atof(a.c_str());
       else if(w=="NSTEPS")s->nstepsbreak=unsigned(atoi(a.c_str()));
+      else if(w=="PARTBEGIN"){   // -partbegin:begin[:first] dir  (JSphCfgRun.cpp:462-470): restart from dir/Part_<begin>.bi4
+        s->partbegin=unsigned(atoi(a2(0).c_str())); s->partbeginfirst=(a2(1).empty()? s->partbegin: unsigned(atoi(a2(1).c_str())));
+        if(!(ss>>s->partbegindir) || s->partbegindir[0]=='-')throw std::runtime_error("-partbegin needs the directory of the PART files as next argument");
+        if(!s->partbegin)throw std::runtime_error("-partbegin:0 is not a restart");
+      }
       else if(w=="SVSTEPS")s->svallsteps=(a.empty()||atoi(a.c_str())!=0);
       else if(w=="SAVEPOSDOUBLE")s->svposdouble=(a.empty()||atoi(a.c_str())!=0);
       else if(w=="SV"){ s->svdata=(lower(a).find("none")==std::string::npos); }
@@ -341,7 +347,7 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
      || data->get_uint("CaseNfloat")!=p.casenfloat || data->get_uint("CaseNfluid")!=p.casenfluid)
     throw std::runtime_error("Particle number does not match the configuration of the case.");
   if(data->get_bool("Data2d"))throw std::runtime_error("Data file does not match the dimension of the case (2D/3D).");
-  const unsigned np=unsigned(part->get_uint("Npok"));
+  unsigned np=unsigned(part->get_uint("Npok"));
   const Bi4Array* aid=part->array("Idp"); const Bi4Array* apd=part->array("Posd"); const Bi4Array* apf=part->array("Pos");
   const Bi4Array* avel=part->array("Vel"); const Bi4Array* arho=part->array("Rhop"); const Bi4Array* anor=part->array("BoundNor");
   if(!aid)throw std::runtime_error("Only Idp (32 bits) is valid at the moment.");
@@ -354,11 +360,46 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   const float* vel=(const float*)avel->ptr(); const float* rho=(const float*)arho->ptr();
   std::vector<float> velrho(size_t(np)*4);
   for(unsigned i=0;i<np;i++){ velrho[size_t(i)*4]=vel[size_t(i)*3]; velrho[size_t(i)*4+1]=vel[size_t(i)*3+1]; velrho[size_t(i)*4+2]=vel[size_t(i)*3+2]; velrho[size_t(i)*4+3]=rho[i]; }
+  // Restart (JPartsLoad4::LoadParticles with partbegin, JPartsLoad4.cpp:181-224): particle data of dir/Part_<begin>.bi4 replace the
+  // initial state; the case definition (counts, constants, mk blocks) still comes from Case.xml/Case.bi4.
+  std::unique_ptr<Bi4Item> pdata;
+  std::vector<uint32_t> pb_idp; unsigned np_case=np;
+  if(s->partbegin){
+    if(p.casenfloat)throw std::runtime_error("restart with floating bodies is not supported by this build (needs PartFloat.fbi4)");
+    if(p.tboundary==B2S_BC_MDBC)throw std::runtime_error("restart with mDBC is not supported by this build (needs the normals extra data)");
+    std::string dir=s->partbegindir; if(!dir.empty() && dir[dir.size()-1]!='/')dir+='/';
+    char fn[64]; snprintf(fn,sizeof(fn),"Part_%04u.bi4",s->partbegin);
+    pdata=bi4_load(dir+fn);
+    char pn[32]; snprintf(pn,sizeof(pn),"PART_%04u",s->partbegin);
+    const Bi4Item* pp=pdata->item(pn);
+    if(!pp)throw std::runtime_error(std::string("restart: item ")+pn+" not found in "+dir+fn);
+    if(pdata->get_uint("CaseNp")!=p.casenp || pdata->get_uint("CaseNfluid")!=p.casenfluid)throw std::runtime_error("restart: the PART file does not belong to this case (particle counts differ)");
+    const unsigned npp=unsigned(pp->get_uint("Npok"));
+    const Bi4Array* qid=pp->array("Idp"); const Bi4Array* qpd=pp->array("Posd"); const Bi4Array* qpf=pp->array("Pos");
+    const Bi4Array* qv=pp->array("Vel"); const Bi4Array* qr=pp->array("Rhop");
+    if(!qid||(!qpd&&!qpf)||!qv||!qr||qid->count!=npp)throw std::runtime_error("restart: particle arrays missing in the PART file");
+    // particles by id (boundary first, as the solver needs them)
+    std::vector<unsigned> order(npp); for(unsigned i=0;i<npp;i++)order[i]=i;
+    const uint32_t* rid=(const uint32_t*)qid->ptr();
+    std::sort(order.begin(),order.end(),[&](unsigned a,unsigned b){ return rid[a]<rid[b]; });
+    pb_idp.resize(npp); pos.resize(size_t(npp)*3); velrho.resize(size_t(npp)*4);
+    const float* rv=(const float*)qv->ptr(); const float* rr=(const float*)qr->ptr();
+    for(unsigned k=0;k<npp;k++){
+      const unsigned i=order[k];
+      pb_idp[k]=rid[i];
+      for(int c=0;c<3;c++)pos[size_t(k)*3+c]=(qpd? ((const double*)qpd->ptr())[size_t(i)*3+c]: double(((const float*)qpf->ptr())[size_t(i)*3+c]));
+      for(int c=0;c<3;c++)velrho[size_t(k)*4+c]=rv[size_t(i)*3+c];
+      velrho[size_t(k)*4+3]=rr[i];
+    }
+    s->partbegintime=pp->get_double("TimeStep",0); s->partbegindtpre=pp->get_double("SymplecticDtPre",0);
+    np=npp; idp=pb_idp.data();
+  }
+  (void)np_case;
   // CheckSortParticles: boundary ids occupy the first slots (JPartsLoad4.cpp:131-140)
   const unsigned nbound=p.casenfixed+p.casenmoving+p.casenfloat;
   { unsigned lastbound=0; for(unsigned i=0;i<np;i++)if(idp[i]<nbound && i>lastbound)lastbound=i; if(nbound && lastbound+1!=nbound)throw std::runtime_error("Order of boundary (fixed, moving and floating) particles is invalid."); }
   // CheckRhoLimits (JSph.cpp:2136-2145)
-  for(unsigned i=0;i<np;i++)if(idp[i]>=nbound && (rho[i]<p.rhopoutmin || rho[i]>p.rhopoutmax))throw std::runtime_error("Initial fluid density is out of limits.");
+  for(unsigned i=0;i<np;i++)if(idp[i]>=nbound && (velrho[size_t(i)*4+3]<p.rhopoutmin || velrho[size_t(i)*4+3]>p.rhopoutmax))throw std::runtime_error("Initial fluid density is out of limits.");
   // particle codes (JSphMk)
   std::vector<uint16_t> code(np);
   {
@@ -486,6 +527,11 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   r=b2s_upload_particles(s->ctx,npsel,idp,code.data(),pos.data(),velrho.data(),norp);
   if(r)throw std::runtime_error(std::string("b2s_upload_particles failed: ")+b2s_last_error(s->ctx));
   s->np0=np;
+  if(s->partbegin){   // TimeStepIni / SymplecticDtPre / PartIni of the restart (JSph.cpp:2214-2225)
+    r=b2s_set_time(s->ctx,(s->partbeginfirst? s->partbegintime: 0.0),s->partbegindtpre);
+    if(r)throw std::runtime_error(std::string("b2s_set_time failed: ")+b2s_last_error(s->ctx));
+    s->part=s->partbeginfirst;
+  }
   if(slab_nranks>0){
     r=b2s_slab_config(s->ctx,slab_rank,slab_nranks,s->slab_cuts[slab_rank],s->slab_cuts[slab_rank+1]);
     if(r)throw std::runtime_error(std::string("b2s_slab_config failed: ")+b2s_last_error(s->ctx));
@@ -543,7 +589,8 @@ static void save_part(b2s_sim* s){
   pt->add_array_ext("Rhop",BT_FLOAT,n,rho.data());
   char fn[64]; snprintf(fn,sizeof(fn),"Part_%04u.bi4",s->part);
   bi4_save(s->dirdata+fn,d,"JPartDataBi4");
-  if(s->part==0){
+  if(!s->head_saved){
+    s->head_saved=true;
     // Part_Head.ibi4 (JPartDataHead::SaveFile, JPartDataHead.cpp): head values + MkBlocks
     Bi4Item h("JPartDataHead");
     h.set_uint("FmtVersion",180324);
@@ -663,7 +710,12 @@ extern "C" int b2s_sim_run(b2s_sim* s,uint32_t nsteps_break,double* time_out,uin
       r=b2s_gauges_compute(s->ctx); if(r){ g_host_err=b2s_last_error(s->ctx); return r; }
       gauges_record(s,inf.timestep);
     }
-    if(save && s->part==0){ save_part(s); s->part++; s->timepartnext=(s->svallsteps? inf.timestep: s->timepart); }
+    if(save && !s->initial_saved){   // the initial PART (PartIni: 0, or the first PART number of a restart)
+      save_part(s); s->part++; s->initial_saved=true;
+      const double t0=inf.timestep;
+      if(s->svallsteps)s->timepartnext=t0;
+      else{ unsigned ct=unsigned(t0/s->timepart); double tn=s->timepart*ct; for(;tn<=t0;ct++)tn=s->timepart*ct; s->timepartnext=tn; }
+    }
     unsigned nstep=0;
     double t=inf.timestep;
     while(t<s->timemax){

@@ -151,6 +151,9 @@ int b2s_download_particles_byid(b2s_ctx* ctx, uint32_t* np_out, uint32_t* idp, d
  * fails with B2S_ERR_ARG if capacity_bytes is too small. */
 int b2s_get_array(b2s_ctx* ctx, const char* name, void* dst, size_t capacity_bytes, size_t* count_out);
 int b2s_get_info(b2s_ctx* ctx, b2s_info* out);
+/* Restart support (JSph.cpp:2214-2225, -partbegin): sets the simulated time and, if >0, SymplecticDtPre (the dt the next
+ * Symplectic step starts with).  Call after b2s_upload_particles. */
+int b2s_set_time(b2s_ctx* ctx, double timestep, double symplectic_dtpre);
 
 /* ---- neighbour list: JSphGpuSingle::RunCellDivide (JSphGpuSingle.cpp:372-498) ------------ */
 /* = cudiv::LimitsCell + PreSortFull/Fluid + Sort + CalcBeginEndCell + SortDataParticles +
