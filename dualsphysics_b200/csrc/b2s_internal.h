@@ -66,6 +66,7 @@ struct DevCte {
   int32_t  gamma_is7;
   int32_t  mdbc2;                  // SlipMode>=2: boundary neighbours use boundmode/tangenvel (JSphCpu.cpp:851-853,990-995)
   float dp2;                       // float(Dp*Dp): scaled condition number of mDBC2
+  int32_t  shiftmode; float shiftcoef, shifttfs, shiftmaxdist;   // standard shifting (JSphShifting)
 };
 
 // ---- device-resident state of the last cell divide (JCellDivGpu members, JCellDivGpu.h:86-138) ----
@@ -127,6 +128,7 @@ struct b2s_ctx {
   float* spstau; float* spstau_alt; float* spstau_new;   // 6 floats per particle
   // mDBC
   float4* boundnor; float4* boundnor_alt;                 // xyz normal, w unused
+  float4* shiftpos;                                       // standard shifting: displacement of the current sub-step (fluid particles)
   uint8_t* boundmode; float4* tangenvel;                  // mDBC2 (SlipMode 2/3): per interaction, in the current sorted order
   // interaction inputs/outputs
   float4* posp;      // (x,y,z) relative to own cell origin, w = pressure
@@ -208,6 +210,7 @@ int b2s_celldiv_impl(b2s_ctx* ctx);
 int b2s_forces_impl(b2s_ctx* ctx, int interstep);
 int b2s_integrate_impl(b2s_ctx* ctx, int mode, double dt, bool dt_from_device);   // mode: 0 verlet,1 sympre,2 symcorr
 int b2s_mdbc_impl(b2s_ctx* ctx);
+int b2s_shifting_impl(b2s_ctx* ctx);   // shifting.cu: RunShifting with StepState.dt, called by b2s_integrate_impl (corrector / Verlet)
 int b2s_floating_impl(b2s_ctx* ctx, double dt, bool predictor, bool dt_from_device);
 int b2s_motion_impl(b2s_ctx* ctx, double timestep, double dt);
 int b2s_sync_info(b2s_ctx* ctx);

@@ -41,6 +41,7 @@ static void make_devcte(const b2s_params& p, DevCte& c){
   c.domcellcode=p.domcellcode; c.scelldiv=p.scelldiv; c.tkernel=p.tkernel; c.tvisco=p.tvisco; c.tdensity=p.tdensity;
   c.tboundary=p.tboundary; c.tstep=p.tstep; c.use_floating=p.use_floating; c.dt_allparticles=p.dt_allparticles;
   c.refsem=p.refsem; c.simulate2d=p.simulate2d;
+  c.shiftmode=p.shiftmode; c.shiftcoef=p.shiftcoef; c.shifttfs=p.shifttfs; c.shiftmaxdist=float(p.dp*0.1);
   c.mdbc2=(p.tboundary==B2S_BC_MDBC && p.slipmode>=B2S_SLIP_NOSLIP)? 1: 0; c.dp2=float(p.dp*p.dp);
   c.gamma_is7=(p.gamma==7.0f? 1: 0);
 }
@@ -73,7 +74,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   ctx->launches=0; ctx->variant=0; ctx->pre_active=false; ctx->bound_changed=true; ctx->ftcount=0;
   ctx->verletstep=0;
   ctx->slab_on=false; ctx->slab_rank=0; ctx->slab_nranks=1; ctx->slab_cxa=0; ctx->slab_cxb=0; ctx->slab_counts=NULL; ctx->slab_flags=NULL; ctx->slab_counts_len=0;
-  ctx->defer_attr_set=false; ctx->boundmode=NULL; ctx->tangenvel=NULL;
+  ctx->defer_attr_set=false; ctx->boundmode=NULL; ctx->tangenvel=NULL; ctx->shiftpos=NULL;
   ctx->gauges_dev=NULL; ctx->gauge_res_dev=NULL; ctx->gauge_res_h=NULL; ctx->gauge_mass_dev=NULL; ctx->gauge_points=0;
   ctx->ft_massp_dev=NULL; ctx->ft_sums_dev=NULL; ctx->ft_allsums_dev=NULL; ctx->ft_sums_h=NULL; ctx->ft_dev=NULL; ctx->scratch=NULL; ctx->scratch_bytes=0;
   ctx->pospre_xy=ctx->pospre_xy_alt=NULL; ctx->pospre_z=ctx->pospre_z_alt=NULL; ctx->velrhopre=ctx->velrhopre_alt=NULL;
@@ -96,6 +97,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
     TRY(dalloc(ctx->spstau,cap*6)); TRY(dalloc(ctx->spstau_alt,cap*6)); TRY(dalloc(ctx->spstau_new,cap*6));
     if(e==cudaSuccess){ cudaMemset(ctx->spstau,0,cap*24); cudaMemset(ctx->spstau_alt,0,cap*24); cudaMemset(ctx->spstau_new,0,cap*24); }
   }
+  if(q.shiftmode){ TRY(dalloc(ctx->shiftpos,cap)); if(e==cudaSuccess)cudaMemset(ctx->shiftpos,0,size_t(cap)*16); }
   if(q.tboundary==B2S_BC_MDBC && q.slipmode>=B2S_SLIP_NOSLIP){ TRY(dalloc(ctx->boundmode,cap)); TRY(dalloc(ctx->tangenvel,cap)); if(e==cudaSuccess){ cudaMemset(ctx->boundmode,0,cap); cudaMemset(ctx->tangenvel,0,size_t(cap)*16); } }
   if(q.tboundary==B2S_BC_MDBC){ TRY(dalloc(ctx->boundnor,cap)); TRY(dalloc(ctx->boundnor_alt,cap)); if(e==cudaSuccess){ cudaMemset(ctx->boundnor,0,cap*16); cudaMemset(ctx->boundnor_alt,0,cap*16);} }
   TRY(dalloc(ctx->posp,cap)); TRY(dalloc(ctx->acear,cap)); TRY(dalloc(ctx->posh,size_t(cap)/2+2));
@@ -130,7 +132,7 @@ extern "C" int b2s_destroy(b2s_ctx* ctx){
   cudaFree(ctx->begincell); cudaFree(ctx->radix_counts); cudaFree(ctx->ridp);
   cudaFree(ctx->div); cudaFree(ctx->step);
   cudaFree(ctx->gauges_dev); cudaFree(ctx->gauge_res_dev); cudaFree(ctx->gauge_mass_dev); if(ctx->gauge_res_h)cudaFreeHost(ctx->gauge_res_h);
-  cudaFree(ctx->boundmode); cudaFree(ctx->tangenvel); cudaFree(ctx->slab_counts); cudaFree(ctx->slab_flags);
+  cudaFree(ctx->shiftpos); cudaFree(ctx->boundmode); cudaFree(ctx->tangenvel); cudaFree(ctx->slab_counts); cudaFree(ctx->slab_flags);
   cudaFree(ctx->ft_massp_dev); cudaFree(ctx->ft_sums_dev); cudaFree(ctx->ft_allsums_dev); cudaFree(ctx->ft_dev); cudaFree(ctx->scratch);
   if(ctx->ft_sums_h)cudaFreeHost(ctx->ft_sums_h);
   if(ctx->div_h)cudaFreeHost(ctx->div_h);

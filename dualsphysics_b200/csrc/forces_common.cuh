@@ -204,8 +204,9 @@ __device__ __forceinline__ void finalize_store(const ForcesArgs& g,const DevCte&
   float4 res;
   res.x=af.ax+ab.ax; res.y=af.ay+ab.ay; res.z=af.az+ab.az; res.w=af.ar+ab.ar;
   if(TDENS!=B2S_DDT_NONE){
-    const bool sf=(af.ar!=0.f || af.ax!=0.f || af.ay!=0.f || af.az!=0.f || af.visc!=0.f);
-    const bool sb=(ab.ar!=0.f || ab.ax!=0.f || ab.ay!=0.f || ab.az!=0.f || ab.visc!=0.f);
+    // with shifting the reference stores unconditionally: `if(shift||arp1||acep1.x||...)` (JSphCpu.cpp:1084)
+    const bool sf=(c.shiftmode!=0 || af.ar!=0.f || af.ax!=0.f || af.ay!=0.f || af.az!=0.f || af.visc!=0.f);
+    const bool sb=(c.shiftmode!=0 || ab.ar!=0.f || ab.ax!=0.f || ab.ay!=0.f || ab.az!=0.f || ab.visc!=0.f);
     const bool dmax=((sf && af.delta==FLT_MAX) || (sb && ab.delta==FLT_MAX));
     if(!dmax)res.w+=((sf? af.delta: 0.f)+(sb? ab.delta: 0.f));
   }

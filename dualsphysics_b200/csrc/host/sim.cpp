@@ -141,7 +141,12 @@ static void load_case(b2s_sim* s,const std::string& options){
   p.slipmode=0;
   if(p.tboundary==B2S_BC_MDBC)p.slipmode=ep.inum("SlipMode",1);
   { const int tddt=ep.inum("DensityDT",0); if(tddt<0||tddt>3)throw std::runtime_error("Density Diffusion Term mode is not valid."); p.tdensity=tddt; p.ddtvalue=float(ep.num("DensityDTvalue",0.1)); }
-  if(ep.inum("Shifting",0)!=0)throw std::runtime_error("Shifting is not supported by this build (out of the hot-path scope)");
+  { // standard shifting (JSph.cpp:744-758); zones (<special><shifting>) and the advanced mode 4 are rejected below
+    const int sm=ep.inum("Shifting",0);
+    if(sm<0||sm>4)throw std::runtime_error("Shifting mode in <execution><parameters> is not valid.");
+    if(sm==4)throw std::runtime_error("advanced shifting (Shifting=4) is not supported by this build");
+    p.shiftmode=sm; p.shiftcoef=float(ep.num("ShiftCoef",-2)); p.shifttfs=float(ep.num("ShiftTFS",0));
+  }
   p.ftpause=ep.num("FtPause",0);
   s->timemax=ep.num("TimeMax",0); s->timepart=ep.num("TimeOut",0);
   p.dtini=std::max(0.0,ep.num("DtIni",0)); p.dtmin=std::max(0.0,ep.num("DtMin",0)); p.coefdtmin=double(float(ep.num("CoefDtMin",0.05)));
@@ -177,6 +182,12 @@ static void load_case(b2s_sim* s,const std::string& options){
       else if(w=="MDBC_FREESLIP"){ opt_boundary=2; opt_slip=3; }
       else if(w=="CELLMODE"){ const std::string u=upper(a); if(u=="HALF"||u=="H")cellmode_half=1; else if(u=="FULL"||u=="2H")cellmode_half=0; else throw std::runtime_error("invalid cellmode"); }
       else if(w=="RHOPOUT"){ p.rhopoutmin=float(atof(a2(0).c_str())); p.rhopoutmax=float(atof(a2(1).c_str())); }
+      else if(w=="SHIFTING"){   // -shifting:<mode> with default parameters (JSphCfgRun.cpp:423-436, JSph.cpp:939-953)
+        const std::string u=upper(a);
+        if(u=="NONE")p.shiftmode=B2S_SHIFT_NONE; else if(u=="NOBOUND")p.shiftmode=B2S_SHIFT_NOBOUND; else if(u=="NOFIXED")p.shiftmode=B2S_SHIFT_NOFIXED; else if(u=="FULL")p.shiftmode=B2S_SHIFT_FULL;
+        else throw std::runtime_error("shifting mode '"+a+"' is not supported by this build (none, nobound, nofixed, full)");
+        p.shiftcoef=-2.f; p.shifttfs=0.f;
+      }
       else if(w=="CFL")p.cflnumber=atof(a.c_str());
       else if(w=="FTPAUSE")p.ftpause=atof(a.c_str());
       else if(w=="TMAX")s->timemax=atof(a.c_str());
@@ -249,6 +260,7 @@ static void load_case(b2s_sim* s,const std::string& options){
     if(np!=p.casenp || nb!=p.casenp-p.casenfluid || nbf!=p.casenfixed)throw std::runtime_error("The amount of particles does not match the header."); }
   // -- gauges (JGaugeSystem::LoadXml "case.execution.special.gauges"): velocity and swl
   if(const XmlNode* sp=exe->child("special")){
+    if(sp->child("shifting"))throw std::runtime_error("<special><shifting> (shifting zones) is not supported by this build; use the Shifting parameters");
     if(const XmlNode* gs=sp->child("gauges")){
       struct Def { double cdt,cs,ce,odt,os,oe; bool out; } def={-1,0,-1,-1,0,-1,false};   // <0: TimeOut / TimeMax, resolved after the command-line options
       auto common=[&](const XmlNode* e,Def d)->Def{

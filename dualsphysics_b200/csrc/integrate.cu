@@ -24,6 +24,7 @@ struct IntegArgs {
   const float4* velrho_aux;   // verlet: velrho(n-1) (or == velrho on Euler steps); symcorr: predicted velrho (rho*)
   const float4* acear;
   int euler;                  // verlet only
+  const float4* shiftpos;     // standard shifting (else NULL): displacement added to the fluid particles' move
   const uint8_t* boundmode;   // mDBC2 only (else NULL): boundary particles with mode>=BMODE_MDBC2 keep their velrho
 };
 
@@ -118,9 +119,10 @@ __global__ void __launch_bounds__(I_BS) k_sym_corr(IntegArgs a, const __grid_con
     vn.y=float(double(pre.y)+(double(acear.y)+double(c.gravity[1]))*dt);
     vn.z=float(double(pre.z)+(double(acear.z)+double(c.gravity[2]))*dt);
     vn.w=rhonew;
-    const double dx=(double(pre.x)+double(vn.x))*dt05;
-    const double dy=(double(pre.y)+double(vn.y))*dt05;
-    const double dz=(double(pre.z)+double(vn.z))*dt05;
+    double dx=(double(pre.x)+double(vn.x))*dt05;
+    double dy=(double(pre.y)+double(vn.y))*dt05;
+    double dz=(double(pre.z)+double(vn.z))*dt05;
+    if(a.shiftpos){ const float4 sh=a.shiftpos[p]; dx+=double(sh.x); dy+=double(sh.y); dz+=double(sh.z); }   // JSphCpu.cpp:1936-1940
     const bool outrho=(rhonew<c.rhopoutmin || rhonew>c.rhopoutmax);
     a.velrho_w[p]=vn;
     const double2 xy=a.posxy_r[p]; const double z=a.posz_r[p];
@@ -158,7 +160,8 @@ __global__ void __launch_bounds__(I_BS) k_verlet(IntegArgs a, const __grid_const
   if(!c.use_floating || B2S_CODE_ISFLUID(rcode)){
     const double dt205=0.5*dt*dt;
     const double agx=double(acear.x)+double(c.gravity[0]), agy=double(acear.y)+double(c.gravity[1]), agz=double(acear.z)+double(c.gravity[2]);
-    const double dx=double(v1.x)*dt+agx*dt205, dy=double(v1.y)*dt+agy*dt205, dz=double(v1.z)*dt+agz*dt205;
+    double dx=double(v1.x)*dt+agx*dt205, dy=double(v1.y)*dt+agy*dt205, dz=double(v1.z)*dt+agz*dt205;
+    if(a.shiftpos){ const float4 sh=a.shiftpos[p]; dx+=double(sh.x); dy+=double(sh.y); dz+=double(sh.z); }   // JSphCpu.cpp:1543-1547
     const bool outrho=(rhonew<c.rhopoutmin || rhonew>c.rhopoutmax);
     float4 vn;
     vn.x=float(double(v2.x)+agx*dt2); vn.y=float(double(v2.y)+agy*dt2); vn.z=float(double(v2.z)+agz*dt2); vn.w=rhonew;
@@ -187,7 +190,10 @@ int b2s_integrate_impl(b2s_ctx* ctx, int mode, double dt, bool dt_from_device){
   IntegArgs a; memset(&a,0,sizeof(a));
   a.ds=ctx->div; a.st=ctx->step; a.code=ctx->cur.code; a.dcell=ctx->cur.dcell; a.acear=ctx->acear;
   a.boundmode=(ctx->prm.slipmode>=B2S_SLIP_NOSLIP? ctx->boundmode: NULL);
+  a.shiftpos=(ctx->prm.shiftmode? ctx->shiftpos: NULL);
   const unsigned g=b2s_blocks(n,I_BS);
+  // RunShifting(dt) before the corrector / the Verlet update (JSphCpuSingle.cpp:881,924); the predictor does not use it (JSphCpu.cpp:1689).
+  if(a.shiftpos && mode!=1){ const int r=b2s_shifting_impl(ctx); if(r)return r; }
   if(mode==1){
     if(ctx->pre_active)return b2s_fail(ctx,B2S_ERR_STATE,"symplectic predictor called twice");
     // new state -> alt buffers; old state becomes PRE; old PRE buffers become the scratch.

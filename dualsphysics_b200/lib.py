@@ -35,7 +35,7 @@ class Params(C.Structure):
         ("tdensity", C.c_int32), ("tboundary", C.c_int32), ("slipmode", C.c_int32),
         ("verletsteps", C.c_int32), ("cellmode_half", C.c_int32), ("dt_allparticles", C.c_int32),
         ("mdbc_corrector", C.c_int32), ("refsem", C.c_int32), ("use_floating", C.c_int32),
-        ("reserved_i", C.c_int32 * 3),
+        ("shiftmode", C.c_int32), ("shiftcoef", C.c_float), ("shifttfs", C.c_float),
         ("kernelh", C.c_float), ("cteb", C.c_float), ("gamma", C.c_float), ("rhopzero", C.c_float),
         ("massfluid", C.c_float), ("massbound", C.c_float),
         ("visco", C.c_float), ("viscoboundfactor", C.c_float), ("ddtvalue", C.c_float),

@@ -46,6 +46,7 @@ enum { B2S_VISCO_ARTIFICIAL = 1, B2S_VISCO_LAMINARSPS = 2, B2S_VISCO_LAMINAR = 3
 enum { B2S_DDT_NONE = 0, B2S_DDT_MOLTENI = 1, B2S_DDT_FOURTAKAS = 2, B2S_DDT_FOURTAKASFULL = 3 }; /* TpDensity */
 enum { B2S_BC_DBC = 1, B2S_BC_MDBC = 2 };                                  /* TpBoundary */
 enum { B2S_SLIP_VEL0 = 1, B2S_SLIP_NOSLIP = 2, B2S_SLIP_FREESLIP = 3 };    /* TpSlipMode */
+enum { B2S_SHIFT_NONE = 0, B2S_SHIFT_NOBOUND = 1, B2S_SHIFT_NOFIXED = 2, B2S_SHIFT_FULL = 3 };  /* TpShifting (DualSphDef.h) */
 enum { B2S_INTER_VERLET = 1, B2S_INTER_SYMPREDICTOR = 2, B2S_INTER_SYMCORRECTOR = 3 }; /* TpInterStep */
 /* Which reference build a semantic detail follows where CPU and GPU differ
  * (DDT2 near DBC boundaries, JSphCpu.cpp:1318-1340 vs JSphGpu_ker.cu:939-946). */
@@ -64,7 +65,8 @@ typedef struct b2s_params {
   int32_t  mdbc_corrector;
   int32_t  refsem;             /* B2S_REFSEM_* */
   int32_t  use_floating;       /* casenfloat>0 */
-  int32_t  reserved_i[3];
+  int32_t  shiftmode;          /* TpShifting: 0 none, 1 NoBound, 2 NoFixed, 3 Full (JSph.cpp:744-758) */
+  float    shiftcoef, shifttfs; /* ShiftCoef (default -2), ShiftTFS (0: no free-surface threshold) */
   float    kernelh, cteb, gamma, rhopzero, massfluid, massbound;
   float    visco, viscoboundfactor, ddtvalue;
   float    rhopoutmin, rhopoutmax;

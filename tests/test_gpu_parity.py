@@ -185,7 +185,7 @@ def test_celldiv_properties_large(tmp_path, built_lib):
 def test_errors_are_loud(tmp_path, built_lib):
     H.write_case(tmp_path, dp=0.05)
     with pytest.raises(dsb.B2SError):
-        dsb.Simulation(str(tmp_path / "Case"), options="-shifting:full")      # unsupported option: error, not ignored
+        dsb.Simulation(str(tmp_path / "Case"), options="-shifting:fulladv")      # unsupported option: error, not ignored
     sim = dsb.Simulation(str(tmp_path / "Case"))
     with pytest.raises(dsb.B2SError):
         sim.ctx.compute_symplectic_corr(1e-4)                                 # corrector without predictor
