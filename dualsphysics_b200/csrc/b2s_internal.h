@@ -153,6 +153,8 @@ struct b2s_ctx {
   bool defer_attr_set;   // forces_defer.cu: dynamic shared memory opt-in done
   // gauges (gauges.cu): device list + results of the last evaluation (device and pinned host)
   std::vector<int> gauge_types; std::vector<unsigned char> gauges_host; void* gauges_dev; float* gauge_res_dev; float* gauge_res_h; float* gauge_mass_dev; uint32_t gauge_points;
+  // damping zones (damping.cu): DampOp records, host list + device copy
+  std::vector<unsigned char> damp_host; void* damp_dev; bool damp_dirty;
   // scratch for byid download
   void* scratch; size_t scratch_bytes;
 };
@@ -211,6 +213,7 @@ int b2s_forces_impl(b2s_ctx* ctx, int interstep);
 int b2s_integrate_impl(b2s_ctx* ctx, int mode, double dt, bool dt_from_device);   // mode: 0 verlet,1 sympre,2 symcorr
 int b2s_mdbc_impl(b2s_ctx* ctx);
 int b2s_shifting_impl(b2s_ctx* ctx);   // shifting.cu: RunShifting with StepState.dt, called by b2s_integrate_impl (corrector / Verlet)
+int b2s_damping_impl(b2s_ctx* ctx);    // damping.cu: RunDamping with StepState.dt
 int b2s_floating_impl(b2s_ctx* ctx, double dt, bool predictor, bool dt_from_device);
 int b2s_motion_impl(b2s_ctx* ctx, double timestep, double dt);
 int b2s_sync_info(b2s_ctx* ctx);

@@ -74,7 +74,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   ctx->launches=0; ctx->variant=0; ctx->pre_active=false; ctx->bound_changed=true; ctx->ftcount=0;
   ctx->verletstep=0;
   ctx->slab_on=false; ctx->slab_rank=0; ctx->slab_nranks=1; ctx->slab_cxa=0; ctx->slab_cxb=0; ctx->slab_counts=NULL; ctx->slab_flags=NULL; ctx->slab_counts_len=0;
-  ctx->defer_attr_set=false; ctx->boundmode=NULL; ctx->tangenvel=NULL; ctx->shiftpos=NULL;
+  ctx->defer_attr_set=false; ctx->boundmode=NULL; ctx->tangenvel=NULL; ctx->shiftpos=NULL; ctx->damp_dev=NULL; ctx->damp_dirty=false;
   ctx->gauges_dev=NULL; ctx->gauge_res_dev=NULL; ctx->gauge_res_h=NULL; ctx->gauge_mass_dev=NULL; ctx->gauge_points=0;
   ctx->ft_massp_dev=NULL; ctx->ft_sums_dev=NULL; ctx->ft_allsums_dev=NULL; ctx->ft_sums_h=NULL; ctx->ft_dev=NULL; ctx->scratch=NULL; ctx->scratch_bytes=0;
   ctx->pospre_xy=ctx->pospre_xy_alt=NULL; ctx->pospre_z=ctx->pospre_z_alt=NULL; ctx->velrhopre=ctx->velrhopre_alt=NULL;
@@ -132,7 +132,7 @@ extern "C" int b2s_destroy(b2s_ctx* ctx){
   cudaFree(ctx->begincell); cudaFree(ctx->radix_counts); cudaFree(ctx->ridp);
   cudaFree(ctx->div); cudaFree(ctx->step);
   cudaFree(ctx->gauges_dev); cudaFree(ctx->gauge_res_dev); cudaFree(ctx->gauge_mass_dev); if(ctx->gauge_res_h)cudaFreeHost(ctx->gauge_res_h);
-  cudaFree(ctx->shiftpos); cudaFree(ctx->boundmode); cudaFree(ctx->tangenvel); cudaFree(ctx->slab_counts); cudaFree(ctx->slab_flags);
+  cudaFree(ctx->damp_dev); cudaFree(ctx->shiftpos); cudaFree(ctx->boundmode); cudaFree(ctx->tangenvel); cudaFree(ctx->slab_counts); cudaFree(ctx->slab_flags);
   cudaFree(ctx->ft_massp_dev); cudaFree(ctx->ft_sums_dev); cudaFree(ctx->ft_allsums_dev); cudaFree(ctx->ft_dev); cudaFree(ctx->scratch);
   if(ctx->ft_sums_h)cudaFreeHost(ctx->ft_sums_h);
   if(ctx->div_h)cudaFreeHost(ctx->div_h);
@@ -474,6 +474,7 @@ static int enqueue_step(b2s_ctx* ctx){
     r=b2s_integrate_impl(ctx,0,0,true); if(r)return r;
     if(ctx->ftcount){ r=b2s_floating_impl(ctx,0,false,true); if(r)return r; }
   }
+  r=b2s_damping_impl(ctx); if(r)return r;                           // RunDamping(dt), JSphCpuSingle.cpp:885,928
   // Run-loop tail (JSphGpuSingle.cpp:1003-1008): RunMotion, RunCellDivide, TimeStep+=dt
   // RunGaugeSystem(TimeStep+stepdt) (JSphCpuSingle.cpp:1192): new particle state, cell table of the last divide
   r=b2s_gauges_run(ctx,1); if(r)return r;
@@ -545,6 +546,7 @@ extern "C" int b2s_slab_integrate(b2s_ctx* ctx, int mode){
 extern "C" int b2s_slab_step_end(b2s_ctx* ctx, double* dt_out){
   if(!ctx)return B2S_ERR_ARG;
   B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  { int r=b2s_damping_impl(ctx); if(r)return r; }
   if(!ctx->motions.empty()){ int r=b2s_motion_impl(ctx,0,0); if(r)return r; }
   k_step_end<<<1,1,0,ctx->stream>>>(ctx->step,ctx->prm.tstep==B2S_STEP_SYMPLECTIC? 1: 0); B2S_LAUNCHED(ctx);
   int r=b2s_sync_info(ctx);

@@ -42,6 +42,14 @@ struct GaugeCfg {
   GaugeCfg():type(0),pointdp(0),masslimit(0),computedt(0),computestart(0),computeend(0),outputdt(0),outputstart(0),outputend(0),output(false),computenext(0),outputnext(0),id(-1),headdone(false){}
 };
 
+// One zone of <special><damping> (JDsDamping::ReadXml, JDsDamping.cpp:664-681)
+struct DampCfg {
+  int type;   // 0 dampingzone, 1 dampingbox
+  float over, redumax, factor[3];
+  double a[3], b[3], c[3], d[3];   // plane: limitmin, limitmax;  box: limitmin ini/end, limitmax ini/end
+  bool usedomain; double domain[10]; unsigned directions;
+};
+
 struct b2s_sim {
   std::string casepath, casename, dirout, dirdata, err;
   b2s_params prm;
@@ -49,6 +57,7 @@ struct b2s_sim {
   std::vector<PartBlock> blocks;
   std::vector<MotionCfg> motions;
   std::vector<GaugeCfg> gauges;
+  std::vector<DampCfg> dampings;
   bool initial_saved, head_saved; unsigned partbegin, partbeginfirst; std::string partbegindir; double partbegintime, partbegindtpre;   // restart (-partbegin)
   // run control (JSph members)
   double timemax, timepart, timepartnext; unsigned part, nstepsbreak; bool svallsteps, svposdouble, svdata;
@@ -261,6 +270,55 @@ static void load_case(b2s_sim* s,const std::string& options){
   // -- gauges (JGaugeSystem::LoadXml "case.execution.special.gauges"): velocity and swl
   if(const XmlNode* sp=exe->child("special")){
     if(sp->child("shifting"))throw std::runtime_error("<special><shifting> (shifting zones) is not supported by this build; use the Shifting parameters");
+    if(const XmlNode* ds=sp->child("damping")){
+      const std::string dact=lower(ds->attr("active","true"));
+      if(!(dact=="false"||dact=="0"))for(auto& cu:ds->children){
+        const XmlNode* c=cu.get();
+        if(c->name.empty() || c->name[0]=='_')continue;
+        const std::string act=lower(c->attr("active","true"));
+        if(act=="false"||act=="0")continue;
+        DampCfg d; memset(&d,0,sizeof(d));
+        auto fval=[&](const char* n,const char* a,bool opt,double def){ const XmlNode* e=c->child(n); if(!e||!e->has(a)){ if(opt)return def; throw std::runtime_error("damping: <"+std::string(n)+" "+a+"> missing"); } return todouble(e->attr(a)); };
+        d.over=float(fval("overlimit","value",false,0)); d.redumax=float(fval("redumax","value",true,10));
+        d.factor[0]=float(fval("factorxyz","x",true,1)); d.factor[1]=float(fval("factorxyz","y",true,1)); d.factor[2]=float(fval("factorxyz","z",true,1));
+        if(c->name=="dampingzone"){
+          d.type=0;
+          if(!read_xyz(c->child("limitmin"),d.a)||!read_xyz(c->child("limitmax"),d.b))throw std::runtime_error("dampingzone: limitmin/limitmax missing");
+          if(const XmlNode* dom=c->child("domain")){
+            d.usedomain=true;
+            if(!dom->has("zmin")||!dom->has("zmax"))throw std::runtime_error("dampingzone: <domain zmin zmax> missing");
+            d.domain[0]=todouble(dom->attr("zmin")); d.domain[1]=todouble(dom->attr("zmax"));
+            const char* pn[4]={"point1","point2","point3","point4"};
+            for(int k=0;k<4;k++){ const XmlNode* q=dom->child(pn[k]); if(!q||!q->has("x")||!q->has("y"))throw std::runtime_error("dampingzone: <domain> point missing"); d.domain[2+2*k]=todouble(q->attr("x")); d.domain[3+2*k]=todouble(q->attr("y")); }
+          }
+        }
+        else if(c->name=="dampingbox"){
+          d.type=1;
+          const XmlNode* emin=c->child("limitmin"); const XmlNode* emax=c->child("limitmax");
+          if(!emin||!emax||!read_xyz(emin->child("pointini"),d.a)||!read_xyz(emin->child("pointend"),d.b)||!read_xyz(emax->child("pointini"),d.c)||!read_xyz(emax->child("pointend"),d.d))
+            throw std::runtime_error("dampingbox: limitmin/limitmax pointini/pointend missing");
+          // directions (JDsDampingOp_Box::ReadXmlDirections, JDsDamping.cpp:313-340): list of [+-]name, default all
+          d.directions=B2S_DAMPDIR_ALL;
+          std::string dirs=(c->child("directions")? lower(c->child("directions")->attr("value","")): "");
+          for(auto& ch:dirs)if(ch==',')ch=' ';
+          std::stringstream ss(dirs); std::string v; bool any=false;
+          while(ss>>v){
+            if(!any){ d.directions=0; any=true; }
+            bool add=true;
+            if(v[0]=='+')v=v.substr(1);
+            if(!v.empty() && v[0]=='-'){ v=v.substr(1); add=false; }
+            unsigned bd=0;
+            if(v=="top")bd=B2S_DAMPDIR_TOP; else if(v=="bottom")bd=B2S_DAMPDIR_BOTTOM; else if(v=="left")bd=B2S_DAMPDIR_LEFT; else if(v=="right")bd=B2S_DAMPDIR_RIGHT;
+            else if(v=="front")bd=B2S_DAMPDIR_FRONT; else if(v=="back")bd=B2S_DAMPDIR_BACK; else if(v=="all")bd=B2S_DAMPDIR_ALL;
+            else throw std::runtime_error("dampingbox: <directions>: some value is invalid");
+            if(add)d.directions|=bd; else d.directions&=(B2S_DAMPDIR_ALL^bd);
+          }
+          if(!d.directions)throw std::runtime_error("dampingbox: at least one direction must be configured");
+        }
+        else throw std::runtime_error("damping <"+c->name+"> is not supported by this build (dampingzone, dampingbox)");
+        s->dampings.push_back(d);
+      }
+    }
     if(const XmlNode* gs=sp->child("gauges")){
       struct Def { double cdt,cs,ce,odt,os,oe; bool out; } def={-1,0,-1,-1,0,-1,false};   // <0: TimeOut / TimeMax, resolved after the command-line options
       auto common=[&](const XmlNode* e,Def d)->Def{
@@ -518,6 +576,11 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
     if(!blk)continue;
     r=b2s_add_motion_rectsinu(s->ctx,blk->begin,blk->count,m.freq,m.ampl,m.phase,m.tstart,m.tend);
     if(r)throw std::runtime_error(std::string("b2s_add_motion_rectsinu failed: ")+b2s_last_error(s->ctx));
+  }
+  for(auto& d:s->dampings){
+    if(d.type==0)r=b2s_add_damping_plane(s->ctx,d.a,d.b,d.over,d.redumax,d.factor,d.usedomain? d.domain: NULL);
+    else r=b2s_add_damping_box(s->ctx,d.a,d.b,d.c,d.d,d.over,d.redumax,d.factor,d.directions);
+    if(r)throw std::runtime_error(std::string("damping zone failed: ")+b2s_last_error(s->ctx));
   }
   for(auto& g:s->gauges){
     if(g.computedt<0)g.computedt=s->timepart;  if(g.computeend<0)g.computeend=s->timemax;     // JGaugeSystem::ResetCfgDefault

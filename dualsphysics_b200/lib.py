@@ -139,6 +139,9 @@ def load_library():
     lib.b2s_run_steps.argtypes = [vp, C.c_uint32, C.POINTER(C.c_double)]
     lib.b2s_add_motion_rectsinu.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                             C.POINTER(C.c_double), C.c_double, C.c_double]
+    dp_, fp_ = C.POINTER(C.c_double), C.POINTER(C.c_float)
+    lib.b2s_add_damping_plane.argtypes = [vp, dp_, dp_, C.c_float, C.c_float, fp_, dp_]
+    lib.b2s_add_damping_box.argtypes = [vp, dp_, dp_, dp_, dp_, C.c_float, C.c_float, fp_, C.c_uint32]
     lib.b2s_move_linear.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     lib.b2s_set_floatings.argtypes = [vp, C.c_uint32, C.POINTER(Floating)]
     lib.b2s_get_floatings.argtypes = [vp, C.c_uint32, C.POINTER(Floating)]
@@ -392,6 +395,17 @@ class Context:
         out = (C.c_float * 3)()
         self._chk(self._lib.b2s_gauge_result(self._h, gid, out))
         return [out[0], out[1], out[2]]
+
+    def add_damping_plane(self, limitmin, limitmax, overlimit, redumax=10.0, factorxyz=(1, 1, 1), domain=None):
+        dom = (C.c_double * 10)(*domain) if domain is not None else None
+        self._chk(self._lib.b2s_add_damping_plane(self._h, (C.c_double * 3)(*limitmin), (C.c_double * 3)(*limitmax),
+                                                  overlimit, redumax, (C.c_float * 3)(*factorxyz), dom))
+
+    def add_damping_box(self, limitmin_ini, limitmin_end, limitmax_ini, limitmax_end, overlimit, redumax=10.0,
+                        factorxyz=(1, 1, 1), directions=63):
+        d3 = C.c_double * 3
+        self._chk(self._lib.b2s_add_damping_box(self._h, d3(*limitmin_ini), d3(*limitmin_end), d3(*limitmax_ini), d3(*limitmax_end),
+                                                overlimit, redumax, (C.c_float * 3)(*factorxyz), directions))
 
     def set_floatings(self, fts):
         arr = (Floating * len(fts))(*fts)

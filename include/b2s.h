@@ -190,6 +190,19 @@ int b2s_add_motion_rectsinu(b2s_ctx* ctx, uint32_t idbegin, uint32_t count, cons
 /* Direct form: displace a block now (MOTT_Linear data: JDsMotionDef.h). */
 int b2s_move_linear(b2s_ctx* ctx, uint32_t idbegin, uint32_t count, const double mvpos[3], const float mvvel[3]);
 
+/* ---- damping zones: JDsDamping (JDsDamping.cpp:96-131,185-233 plane; :345-391,446-492 box), JSphCpu::RunDamping
+ * (JSphCpu.cpp:2312-2316).  Registered zones are applied to the fluid particles once per step, after the integrator and the
+ * floating-body update (JSphCpuSingle.cpp:885,928), in registration order.
+ * plane: <dampingzone> limitmin -> limitmax gives the direction and the ramp length, overlimit extends it; domain = NULL or
+ * 10 doubles {zmin, zmax, x1,y1, x2,y2, x3,y3, x4,y4} (<domain>).  box: <dampingbox> with the four corner points and the
+ * active directions (B2S_DAMPDIR_* mask). */
+enum { B2S_DAMPDIR_TOP = 1, B2S_DAMPDIR_BOTTOM = 2, B2S_DAMPDIR_LEFT = 4, B2S_DAMPDIR_RIGHT = 8, B2S_DAMPDIR_FRONT = 16,
+       B2S_DAMPDIR_BACK = 32, B2S_DAMPDIR_ALL = 63 };   /* JDsDampingOp_Box::TpDirections (JDsDamping.h:171-181) */
+int b2s_add_damping_plane(b2s_ctx* ctx, const double limitmin[3], const double limitmax[3], float overlimit, float redumax,
+                          const float factorxyz[3], const double* domain);
+int b2s_add_damping_box(b2s_ctx* ctx, const double limitmin_ini[3], const double limitmin_end[3], const double limitmax_ini[3],
+                        const double limitmax_end[3], float overlimit, float redumax, const float factorxyz[3], uint32_t directions);
+
 /* ---- floating bodies: FtPartsSumAce / FtComputeAceVel / FtPartsUpdate ---------------------- */
 /* (JSphGpu_ker.cu:1938-2101, JSph.cpp:2565-2704, JSphGpuSingle.cpp:827-907). */
 int b2s_set_floatings(b2s_ctx* ctx, uint32_t ftcount, const b2s_floating* fts);
