@@ -46,6 +46,9 @@ class DamBreakSpec:
     coefh: float = 1.0
     cfl: float = 0.2
     hydrostatic: bool = True                # rhopgradient=2 (water column)
+    open_axes: str = ""                     # "y", "xy": no tank walls across these axes (periodic cases); the lattice then
+                                            # covers [0, n-1] along them so that the period is n*dp
+    fluid_vel: tuple = (0.0, 0.0, 0.0)      # initial velocity of the fluid particles
     params: dict = field(default_factory=dict)   # overrides for <parameters>
     special_xml: str = ""                   # raw xml placed inside <special>
 
@@ -77,15 +80,16 @@ def build_particles(spec: DamBreakSpec) -> dict:
     nl = max(1, int(spec.layers))
     # -- boundary shell: lattice box [-(nl-1) .. n+(nl-1)] minus the interior, open top
     lo = -(nl - 1)
-    full = _lattice(lo, nx + nl - 1, lo, ny + nl - 1, lo, nz)
+    ox, oy = "x" in spec.open_axes, "y" in spec.open_axes
+    full = _lattice(0 if ox else lo, nx - 1 if ox else nx + nl - 1, 0 if oy else lo, ny - 1 if oy else ny + nl - 1, lo, nz)
     i, j, k = full[:, 0], full[:, 1], full[:, 2]
-    interior = (i >= 1) & (i <= nx - 1) & (j >= 1) & (j <= ny - 1) & (k >= 1)
+    interior = (ox | ((i >= 1) & (i <= nx - 1))) & (oy | ((j >= 1) & (j <= ny - 1))) & (k >= 1)
     fixed = full[~interior]
     # -- fluid column
     fx = min(nx - 1, int(math.floor(spec.fluid[0] / dp + 1e-9)))
     fy = min(ny - 1, int(math.floor(spec.fluid[1] / dp + 1e-9)))
     fz = min(nz - 1, int(math.floor(spec.fluid[2] / dp + 1e-9)))
-    fluid = _lattice(1, fx, 1, fy, 1, fz)
+    fluid = _lattice(0 if ox else 1, fx, 0 if oy else 1, fy, 1, fz)
     moving = np.zeros((0, 3), dtype=np.int64)
     floating = np.zeros((0, 3), dtype=np.int64)
     if spec.piston:
@@ -146,6 +150,7 @@ def write_case(dirpath: str, name: str, spec: DamBreakSpec) -> dict:
     nbound = nfixed + nmoving + nfloat
     pos = ijk.astype(np.float64) * dp
     vel = np.zeros((n, 3), dtype=np.float32)
+    vel[nbound:] = np.asarray(spec.fluid_vel, dtype=np.float32)
     rhop = np.full(n, spec.rhop0, dtype=np.float32)
     if spec.hydrostatic:
         # rhopgradient=2: rho = rho0*(1+rho0*g*(hswl-z)/B)^(1/gamma), fluid only, column top = hswl

@@ -67,6 +67,8 @@ struct DevCte {
   int32_t  mdbc2;                  // SlipMode>=2: boundary neighbours use boundmode/tangenvel (JSphCpu.cpp:851-853,990-995)
   float dp2;                       // float(Dp*Dp): scaled condition number of mDBC2
   int32_t  shiftmode; float shiftcoef, shifttfs, shiftmaxdist;   // standard shifting (JSphShifting)
+  int32_t  periactive;             // periodic axes: bit0 X, bit1 Y, bit2 Z (JSph::PeriActive)
+  double   perinc[3][3];           // PeriXinc, PeriYinc, PeriZinc (JSph.cpp:2186-2188)
 };
 
 // ---- device-resident state of the last cell divide (JCellDivGpu members, JCellDivGpu.h:86-138) ----
@@ -82,6 +84,7 @@ struct DivState {
   uint32_t npf_out_total;
   uint32_t error;          // !=0: boundary particle excluded etc.
   uint32_t slab_nbound_tmp; // boundary-type particles appended by the last slab unpack
+  uint32_t peri_np0, peri_npb0, peri_nbper, peri_nfper;   // RunPeriodic bookkeeping (periodic.cu): Np/Npb at entry, NpbPer, NpfPer
 };
 
 // ---- device-resident step scalars (dt maxima as ordered uints for atomicMax) ----
@@ -173,6 +176,36 @@ static inline unsigned b2s_blocks(size_t n, unsigned bs){ return (unsigned)((n+b
 #define B2S_XBLK 2
 #ifdef __CUDACC__
 __device__ __forceinline__ float b2s_offx(const DevCte& c,int cx1_abs,int cx2_abs){ return c.scell_blk*float((cx1_abs>>B2S_XBLK)-(cx2_abs>>B2S_XBLK)); }
+// The position/cell part of JSphCpu::UpdatePos (JSphCpu.cpp:1471-1515) after the displacement has been applied: checks the real
+// map limits, wraps the position around periodic axes, computes the cell.  Returns true when the particle is out of the map.
+__device__ __forceinline__ bool b2s_pos_to_cell(const DevCte& c,double& rx,double& ry,double& rz,uint32_t& cell){
+  double dx=rx-c.maprealposmin[0], dy=ry-c.maprealposmin[1], dz=rz-c.maprealposmin[2];
+  bool out=(dx!=dx || dy!=dy || dz!=dz || dx<0 || dy<0 || dz<0 || dx>=c.maprealsize[0] || dy>=c.maprealsize[1] || dz>=c.maprealsize[2]);
+  if(c.periactive && out){
+    const bool px=(c.periactive&1)!=0, py=(c.periactive&2)!=0, pz=(c.periactive&4)!=0;
+    if(px){
+      if(dx<0)                { dx-=c.perinc[0][0]; dy-=c.perinc[0][1]; dz-=c.perinc[0][2]; }
+      if(dx>=c.maprealsize[0]){ dx+=c.perinc[0][0]; dy+=c.perinc[0][1]; dz+=c.perinc[0][2]; }
+    }
+    if(py){
+      if(dy<0)                { dx-=c.perinc[1][0]; dy-=c.perinc[1][1]; dz-=c.perinc[1][2]; }
+      if(dy>=c.maprealsize[1]){ dx+=c.perinc[1][0]; dy+=c.perinc[1][1]; dz+=c.perinc[1][2]; }
+    }
+    if(pz){
+      if(dz<0)                { dx-=c.perinc[2][0]; dy-=c.perinc[2][1]; dz-=c.perinc[2][2]; }
+      if(dz>=c.maprealsize[2]){ dx+=c.perinc[2][0]; dy+=c.perinc[2][1]; dz+=c.perinc[2][2]; }
+    }
+    const bool outx=!px && (dx<0 || dx>=c.maprealsize[0]);
+    const bool outy=!py && (dy<0 || dy>=c.maprealsize[1]);
+    const bool outz=!pz && (dz<0 || dz>=c.maprealsize[2]);
+    out=(outx||outy||outz);
+    rx=dx+c.maprealposmin[0]; ry=dy+c.maprealposmin[1]; rz=dz+c.maprealposmin[2];
+  }
+  if(out){ cell=B2S_DCEL_MAPOUT; return true; }
+  if(c.periactive){ dx=rx-c.domposmin[0]; dy=ry-c.domposmin[1]; dz=rz-c.domposmin[2]; }
+  cell=B2S_DCEL_CELL(c.domcellcode,uint32_t(dx/c.scell_d),uint32_t(dy/c.scell_d),uint32_t(dz/c.scell_d));
+  return false;
+}
 __device__ __forceinline__ float b2s_press(float rho, const DevCte& c){
   // Tait EOS as the CPU path evaluates it (FunSphEos.h:37-39): cteb*(powf(rho/rho0,gamma)-1).
   // gamma==7: exact product chain in double, rounded once (== correctly rounded powf to <1ulp).
@@ -213,6 +246,7 @@ int b2s_forces_impl(b2s_ctx* ctx, int interstep);
 int b2s_integrate_impl(b2s_ctx* ctx, int mode, double dt, bool dt_from_device);   // mode: 0 verlet,1 sympre,2 symcorr
 int b2s_mdbc_impl(b2s_ctx* ctx);
 int b2s_shifting_impl(b2s_ctx* ctx);   // shifting.cu: RunShifting with StepState.dt, called by b2s_integrate_impl (corrector / Verlet)
+int b2s_periodic_impl(b2s_ctx* ctx);   // periodic.cu: RunPeriodic (duplicates behind the current particles; no-op without periodic axes)
 int b2s_damping_impl(b2s_ctx* ctx);    // damping.cu: RunDamping with StepState.dt
 int b2s_floating_impl(b2s_ctx* ctx, double dt, bool predictor, bool dt_from_device);
 int b2s_motion_impl(b2s_ctx* ctx, double timestep, double dt);

@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(DIV_BS) k_reorder(const DivState* __restrict__
         h[0]=__float2half_rn(pp.x*ovs); h[2]=__float2half_rn(pp.y*ovs); h[4]=__float2half_rn(pp.z*ovs);
       }
       if((p>=ds->npb || cte.dt_allparticles) && B2S_CODE_ISNORMAL(cod))v2=vr.x*vr.x+vr.y*vr.y+vr.z*vr.z;   // ghosts (slab halos) excluded
-      if(a.ridp && id>=a.casenfixed && id<a.casenbound)a.ridp[id-a.casenfixed]=p;
+      if(a.ridp && id>=a.casenfixed && id<a.casenbound && B2S_CODE_ISNORMAL(cod))a.ridp[id-a.casenfixed]=p;   // never a duplicate (CalcRidp with PeriActive, JSphCpu.cpp)
     }
   }
   // block max -> one atomic per warp (values >=0 so uint order == float order)
@@ -384,11 +384,12 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   const DevCte& c=ctx->cte;
   if(nptot==0)return B2S_OK;
   // 1. limits
-  k_limits_reset<<<1,32,0,s>>>(ctx->div,(ctx->bound_changed || ctx->slab_on)? 1: 0); B2S_LAUNCHED(ctx);
+  const bool mixed=(ctx->slab_on || c.periactive);   // ghosts / periodic duplicates are appended behind the owned particles: limits by type
+  k_limits_reset<<<1,32,0,s>>>(ctx->div,(ctx->bound_changed || mixed)? 1: 0); B2S_LAUNCHED(ctx);
   const unsigned gl=min(b2s_blocks(nptot,DIV_BS),148u*8u);
-  if(ctx->slab_on){ k_limits_bytype<<<gl,DIV_BS,0,s>>>(ctx->div,ctx->cur.dcell,ctx->cur.code,c.domcellcode); B2S_LAUNCHED(ctx); }
+  if(mixed){ k_limits_bytype<<<gl,DIV_BS,0,s>>>(ctx->div,ctx->cur.dcell,ctx->cur.code,c.domcellcode); B2S_LAUNCHED(ctx); }
   else if(ctx->bound_changed && npb){ k_limits<<<gl,DIV_BS,0,s>>>(npb,0,ctx->cur.dcell,ctx->cur.code,c.domcellcode,ctx->div->blim); B2S_LAUNCHED(ctx); }
-  if(!ctx->slab_on && nptot>npb){ k_limits<<<gl,DIV_BS,0,s>>>(nptot-npb,npb,ctx->cur.dcell,ctx->cur.code,c.domcellcode,ctx->div->flim); B2S_LAUNCHED(ctx); }
+  if(!mixed && nptot>npb){ k_limits<<<gl,DIV_BS,0,s>>>(nptot-npb,npb,ctx->cur.dcell,ctx->cur.code,c.domcellcode,ctx->div->flim); B2S_LAUNCHED(ctx); }
   k_divstate<<<1,32,0,s>>>(ctx->div,c.domcells[0],c.domcells[1],c.domcells[2],(uint32_t)c.scelldiv); B2S_LAUNCHED(ctx);
   // 2. keys
   k_presort<<<b2s_blocks(nptot,DIV_BS),DIV_BS,0,s>>>(ctx->div,ctx->cur.dcell,ctx->cur.code,c.domcellcode,ctx->cellpart,ctx->sortpart); B2S_LAUNCHED(ctx);

@@ -75,12 +75,16 @@ extern "C" int b2s_config_finalize(b2s_params* p){
   if(p->coefdtmin<=0)p->coefdtmin=0.05f;     // default CoefDtMin (JSph.cpp:800), stored through float
   if(!p->dtini)p->dtini=double(p->kernelh)/p->cs0;
   if(!p->dtmin)p->dtmin=(double(p->kernelh)/p->cs0)*double(float(p->coefdtmin));
-  // ---- map (no periodic boundaries: Map_Pos == MapRealPos)
+  // ---- map: Map_Pos == MapRealPos, widened by KernelSize on periodic axes for the duplicates (JSph.cpp:2184-2195)
+  if(p->periactive<0 || p->periactive>7)return B2S_ERR_ARG;
   for(int k=0;k<3;k++){
-    p->map_posmin[k]=p->maprealposmin[k]; p->map_posmax[k]=p->maprealposmax[k];
-    p->map_size[k]=p->map_posmax[k]-p->map_posmin[k];
+    const bool peri=((p->periactive>>k)&1)!=0;
     p->maprealsize[k]=p->maprealposmax[k]-p->maprealposmin[k];
+    p->map_posmin[k]=p->maprealposmin[k]-(peri? double(p->kernelsize): 0.0); p->map_posmax[k]=p->maprealposmax[k]+(peri? double(p->kernelsize): 0.0);
+    p->map_size[k]=p->map_posmax[k]-p->map_posmin[k];
     if(!(p->map_size[k]>0))return B2S_ERR_ARG;
+    double* inc=(k==0? p->perixinc: (k==1? p->periyinc: p->perizinc));
+    if(peri)inc[k]=-p->maprealsize[k]; else inc[0]=inc[1]=inc[2]=0;
   }
   // ---- ConfigCellDivision
   p->scelldiv=(p->cellmode_half? 2: 1);

@@ -44,6 +44,8 @@ static void make_devcte(const b2s_params& p, DevCte& c){
   c.shiftmode=p.shiftmode; c.shiftcoef=p.shiftcoef; c.shifttfs=p.shifttfs; c.shiftmaxdist=float(p.dp*0.1);
   c.mdbc2=(p.tboundary==B2S_BC_MDBC && p.slipmode>=B2S_SLIP_NOSLIP)? 1: 0; c.dp2=float(p.dp*p.dp);
   c.gamma_is7=(p.gamma==7.0f? 1: 0);
+  c.periactive=p.periactive;
+  for(int k=0;k<3;k++){ c.perinc[0][k]=p.perixinc[k]; c.perinc[1][k]=p.periyinc[k]; c.perinc[2][k]=p.perizinc[k]; }
 }
 
 template<class T> static cudaError_t dalloc(T*& ptr, size_t n){ ptr=NULL; return cudaMalloc((void**)&ptr, std::max<size_t>(n,1)*sizeof(T)); }
@@ -62,6 +64,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   int ndev=0;
   if(cudaGetDeviceCount(&ndev)!=cudaSuccess || ndev<=0)return B2S_ERR_NODEVICE;
   if(device>=ndev)return B2S_ERR_ARG;
+  if(p->periactive && (p->casenfloat || p->tboundary==B2S_BC_MDBC))return B2S_ERR_UNSUPPORTED;   // periodic + floating bodies / mDBC: not built
   b2s_ctx* ctx=new b2s_ctx();
   ctx->prm=*p;
   if(ctx->prm.domcellcode==0){ int r=b2s_config_finalize(&ctx->prm); if(r){ delete ctx; return r; } }
@@ -154,6 +157,7 @@ int b2s_sync_info(b2s_ctx* ctx){
   B2S_CUDA(ctx,cudaMemcpyAsync(ctx->step_h,ctx->step,sizeof(StepState),cudaMemcpyDeviceToHost,ctx->stream));
   B2S_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
   ctx->np_host=ctx->div_h->np; ctx->npb_host=ctx->div_h->npb; ctx->npbok_host=ctx->div_h->npbok;
+  if(ctx->div_h->error==2u)return b2s_fail(ctx,B2S_ERR_NOMEM,"particle capacity %u exceeded by the periodic duplicates",ctx->cap);
   if(ctx->div_h->error)return b2s_fail(ctx,B2S_ERR_BOUNDOUT,"boundary particles were excluded from the domain (%u)",ctx->div_h->npb_out);
   if(ctx->step_h->error)return b2s_fail(ctx,ctx->step_h->error,"%s (acemax=%g velmax=%g viscdtmax=%g nstep=%u)",b2s_error_string(ctx->step_h->error),ctx->step_h->acemax,ctx->step_h->velmax,(double)ctx->step_h->viscdtmax,ctx->step_h->nstep);
   return B2S_OK;
@@ -245,6 +249,7 @@ extern "C" int b2s_upload_particles(b2s_ctx* ctx, uint32_t np, const uint32_t* i
   ctx->np_host=np; ctx->npb_host=npb; ctx->npbok_host=npb;
   ctx->pre_active=false; ctx->bound_changed=true; ctx->verletstep=0;
   if(ctx->velrhom1)B2S_CUDA(ctx,cudaMemcpyAsync(ctx->velrhom1,ctx->cur.velrho,size_t(np)*16,cudaMemcpyDeviceToDevice,s));  // InitRunGpu: VelrhoM1=Velrho
+  r=b2s_periodic_impl(ctx); if(r)return r;
   r=b2s_celldiv_impl(ctx); if(r)return r;
   return b2s_sync_info(ctx);
 }
@@ -277,13 +282,13 @@ extern "C" int b2s_download_particles(b2s_ctx* ctx, uint32_t* np_out, uint32_t* 
 }
 
 // scatter by id: out[idp]=value, compacted afterwards on the host side (ids are dense while no particle is out).
-__global__ void k_scatter_byid(uint32_t n, const uint32_t* __restrict__ idp, const double2* __restrict__ posxy, const double* __restrict__ posz,
+__global__ void k_scatter_byid(uint32_t n, const uint32_t* __restrict__ idp, const typecode* __restrict__ code, const double2* __restrict__ posxy, const double* __restrict__ posz,
   const float4* __restrict__ velrho, uint32_t idmax, double* pos3, float* vel3, float* rhop, uint32_t* present)
 {
   const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
   if(p>=n)return;
   const uint32_t id=idp[p];
-  if(id>=idmax)return;
+  if(id>=idmax || !B2S_CODE_ISNORMAL(code[p]))return;   // periodic duplicates and slab ghosts share the id of their original
   const double2 xy=posxy[p]; const float4 v=velrho[p];
   pos3[size_t(id)*3]=xy.x; pos3[size_t(id)*3+1]=xy.y; pos3[size_t(id)*3+2]=posz[p];
   vel3[size_t(id)*3]=v.x; vel3[size_t(id)*3+1]=v.y; vel3[size_t(id)*3+2]=v.z; rhop[id]=v.w; present[id]=1u;
@@ -299,7 +304,7 @@ extern "C" int b2s_download_particles_byid(b2s_ctx* ctx, uint32_t* np_out, uint3
   char* base=(char*)ctx->scratch;
   double* dpos=(double*)base; float* dvel=(float*)(base+size_t(idmax)*24); float* drho=(float*)(base+size_t(idmax)*36); uint32_t* dpres=(uint32_t*)(base+size_t(idmax)*40);
   B2S_CUDA(ctx,cudaMemsetAsync(dpres,0,size_t(idmax)*4,s));
-  k_scatter_byid<<<b2s_blocks(np,256),256,0,s>>>(np,ctx->cur.idp,ctx->cur.posxy,ctx->cur.posz,ctx->cur.velrho,idmax,dpos,dvel,drho,dpres); B2S_LAUNCHED(ctx);
+  k_scatter_byid<<<b2s_blocks(np,256),256,0,s>>>(np,ctx->cur.idp,ctx->cur.code,ctx->cur.posxy,ctx->cur.posz,ctx->cur.velrho,idmax,dpos,dvel,drho,dpres); B2S_LAUNCHED(ctx);
   std::vector<uint32_t> pres(idmax);
   std::vector<double> hpos(size_t(idmax)*3); std::vector<float> hvel(size_t(idmax)*3), hrho(idmax);
   B2S_CUDA(ctx,cudaMemcpyAsync(pres.data(),dpres,size_t(idmax)*4,cudaMemcpyDeviceToHost,s));
@@ -428,7 +433,8 @@ extern "C" int b2s_get_info(b2s_ctx* ctx, b2s_info* o){
 extern "C" int b2s_celldiv(b2s_ctx* ctx){
   if(!ctx)return B2S_ERR_ARG;
   B2S_CUDA(ctx,cudaSetDevice(ctx->device));
-  int r=b2s_celldiv_impl(ctx); if(r)return r;
+  int r=b2s_periodic_impl(ctx); if(r)return r;
+  r=b2s_celldiv_impl(ctx); if(r)return r;
   return b2s_sync_info(ctx);
 }
 extern "C" int b2s_interaction(b2s_ctx* ctx, int interstep){
@@ -449,6 +455,15 @@ __global__ void k_step_end(StepState* st, int symplectic){
   st->nstep++;
 }
 
+// RunCellDivide(true): periodic duplicates, then the divide.  Periodic runs refresh the host mirrors here (the number of
+// duplicates decides the launch bounds); all other runs keep the one synchronisation per step.
+static int divide_full(b2s_ctx* ctx){
+  int r=b2s_periodic_impl(ctx); if(r)return r;
+  r=b2s_celldiv_impl(ctx); if(r)return r;
+  if(ctx->cte.periactive)r=b2s_sync_info(ctx);
+  return r;
+}
+
 static int enqueue_step(b2s_ctx* ctx){
   int r;
   const b2s_params& q=ctx->prm;
@@ -460,7 +475,7 @@ static int enqueue_step(b2s_ctx* ctx){
     r=b2s_forces_impl(ctx,B2S_INTER_SYMPREDICTOR); if(r)return r;  // -> dt_p
     r=b2s_integrate_impl(ctx,1,0,true); if(r)return r;
     if(ctx->ftcount){ r=b2s_floating_impl(ctx,0,true,true); if(r)return r; }
-    r=b2s_celldiv_impl(ctx); if(r)return r;
+    r=divide_full(ctx); if(r)return r;
     if(mdbc && q.mdbc_corrector){ r=b2s_mdbc_impl(ctx); if(r)return r; }
     r=b2s_forces_impl(ctx,B2S_INTER_SYMCORRECTOR); if(r)return r;  // -> dt_c
     r=b2s_integrate_impl(ctx,2,0,true); if(r)return r;
@@ -480,7 +495,7 @@ static int enqueue_step(b2s_ctx* ctx){
   r=b2s_gauges_run(ctx,1); if(r)return r;
   if(!ctx->motions.empty()){ r=b2s_motion_impl(ctx,0,0); if(r)return r; }
   k_step_end<<<1,1,0,ctx->stream>>>(ctx->step,q.tstep==B2S_STEP_SYMPLECTIC? 1: 0); B2S_LAUNCHED(ctx);
-  r=b2s_celldiv_impl(ctx); if(r)return r;
+  r=divide_full(ctx); if(r)return r;
   return B2S_OK;
 }
 

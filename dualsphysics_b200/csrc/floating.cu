@@ -136,14 +136,14 @@ __global__ void __launch_bounds__(FT_BS) k_ft_update(const FtDev* __restrict__ f
   // JSphCpu::UpdatePos with outrho=false (JSphCpu.cpp:1458-1510)
   const bool outmov=(fabsf(float(mx))>c.movlimit || fabsf(float(my))>c.movlimit || fabsf(float(mz))>c.movlimit);
   xy.x+=mx; xy.y+=my; z+=mz;
-  const double dx=xy.x-c.maprealposmin[0], dy=xy.y-c.maprealposmin[1], dz=z-c.maprealposmin[2];
-  const bool out=(dx!=dx || dy!=dy || dz!=dz || dx<0 || dy<0 || dz<0 || dx>=c.maprealsize[0] || dy>=c.maprealsize[1] || dz>=c.maprealsize[2]);
+  uint32_t cell;
+  const bool out=b2s_pos_to_cell(c,xy.x,xy.y,z,cell);
   posxy[p]=xy; posz[p]=z;
   if(outmov || out){
     code[p]=typecode(B2S_CODE_SETNORMAL(code[p])|(out? B2S_CODE_OUTPOS: B2S_CODE_OUTMOV));
     dcell[p]=B2S_DCEL_MAPOUT;
   }
-  else dcell[p]=B2S_DCEL_CELL(c.domcellcode,uint32_t(dx/c.scell_d),uint32_t(dy/c.scell_d),uint32_t(dz/c.scell_d));
+  else dcell[p]=cell;
   const float rx=float(xy.x-d.ncenter[0]), ry=float(xy.y-d.ncenter[1]), rz=float(z-d.ncenter[2]);
   vr.x=d.nvel[0]+(d.nomega[1]*rz-d.nomega[2]*ry);
   vr.y=d.nvel[1]+(d.nomega[2]*rx-d.nomega[0]*rz);

@@ -163,8 +163,20 @@ static void load_case(b2s_sim* s,const std::string& options){
   if(ep.num("DtFixed",0)!=0)throw std::runtime_error("DtFixed is not supported by this build");
   p.rhopoutmin=float(ep.num("RhopOutMin",700)); p.rhopoutmax=float(ep.num("RhopOutMax",1300));
   s->svposdouble=(ep.inum("SavePosDouble",0)!=0);
-  for(const char* k:{"XPeriodicIncY","XPeriodicIncZ","YPeriodicIncX","YPeriodicIncZ","ZPeriodicIncX","ZPeriodicIncY","XYPeriodic","XZPeriodic","YZPeriodic"})
-    if(ep.exists(k))throw std::runtime_error("periodic boundaries are not supported by this build (SURVEY 8f 'next' row)");
+  { // periodic boundaries (JSph.cpp:815-827)
+    bool px=false,py=false,pz=false;
+    for(int k=0;k<3;k++)p.perixinc[k]=p.periyinc[k]=p.perizinc[k]=0;
+    if(ep.exists("XPeriodicIncY")){ p.perixinc[1]=ep.num("XPeriodicIncY",0); px=true; }
+    if(ep.exists("XPeriodicIncZ")){ p.perixinc[2]=ep.num("XPeriodicIncZ",0); px=true; }
+    if(ep.exists("YPeriodicIncX")){ p.periyinc[0]=ep.num("YPeriodicIncX",0); py=true; }
+    if(ep.exists("YPeriodicIncZ")){ p.periyinc[2]=ep.num("YPeriodicIncZ",0); py=true; }
+    if(ep.exists("ZPeriodicIncX")){ p.perizinc[0]=ep.num("ZPeriodicIncX",0); pz=true; }
+    if(ep.exists("ZPeriodicIncY")){ p.perizinc[1]=ep.num("ZPeriodicIncY",0); pz=true; }
+    if(ep.exists("XYPeriodic")){ px=true;  py=true;  pz=false; for(int k=0;k<3;k++)p.perixinc[k]=p.periyinc[k]=p.perizinc[k]=0; }
+    if(ep.exists("XZPeriodic")){ px=true;  py=false; pz=true;  for(int k=0;k<3;k++)p.perixinc[k]=p.periyinc[k]=p.perizinc[k]=0; }
+    if(ep.exists("YZPeriodic")){ px=false; py=true;  pz=true;  for(int k=0;k<3;k++)p.perixinc[k]=p.periyinc[k]=p.perizinc[k]=0; }
+    p.periactive=(px? 1: 0)|(py? 2: 0)|(pz? 4: 0);
+  }
   // -- command-line style overrides (JSphCfgRun::LoadArgv + JSph::LoadConfigCommands)
   int cellmode_half=0; int opt_boundary=-1, opt_slip=1;
   {
@@ -490,9 +502,9 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   if(data->get_double3("MapPosMin",mpmin) && data->get_double3("MapPosMax",mpmax))mapsize=!(mpmin[0]==mpmax[0]&&mpmin[1]==mpmax[1]&&mpmin[2]==mpmax[2]);
   if(mapsize){ for(int k=0;k<3;k++){ p.maprealposmin[k]=mpmin[k]; p.maprealposmax[k]=mpmax[k]; } }
   else{
-    const double border=double(p.kernelh)*0.05;   // BORDER_MAP (DualSphDef.h:112)
+    const double border=double(p.kernelh)*0.05;   // BORDER_MAP (DualSphDef.h:112); periodic axes: dp/2 (JPartsLoad4.cpp:389-399)
     double dmin[3],dmax[3],rmin[3],rmax[3];
-    for(int k=0;k<3;k++){ rmin[k]=cmin[k]-border; rmax[k]=cmax[k]+border; dmin[k]=rmin[k]; dmax[k]=rmax[k]; }
+    for(int k=0;k<3;k++){ const double b=(((p.periactive>>k)&1)? p.dp/2.: border); rmin[k]=cmin[k]-b; rmax[k]=cmax[k]+b; dmin[k]=rmin[k]; dmax[k]=rmax[k]; }
     // re-read <simulationdomain> to apply default+-value / default+-% / fixed
     std::unique_ptr<XmlNode> root=xml_load(s->casepath+".xml");
     const XmlNode* sd=root->path("execution.parameters.simulationdomain");
@@ -511,6 +523,7 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
       if(hasfixmin[k])a=fixmin[k];
       if(hasfixmax[k])b=fixmax[k];
       if(a>rmin[k] || b<rmax[k])throw std::runtime_error("Domain limits are not valid.");
+      if((p.periactive>>k)&1){ a=rmin[k]; b=rmax[k]; }   // periodic axes keep the particle limits (JSph.cpp:1472-1475)
       p.maprealposmin[k]=a; p.maprealposmax[k]=b;
     }
   }
@@ -551,6 +564,15 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
     npsel=w; idp=sel_idp.data();
     // room for: ghosts (scelldiv planes each side), migrants, and a 25% drift of the owned count before re-cutting
     extra_capacity+=npsel/4+4u*halow*s->slab_maxplane+4096u;
+  }
+  if(p.periactive){
+    if(p.casenfloat)throw std::runtime_error("periodic boundaries with floating bodies are not supported by this build");
+    if(p.tboundary==B2S_BC_MDBC)throw std::runtime_error("periodic boundaries with mDBC are not supported by this build");
+    if(slab_nranks>1)throw std::runtime_error("periodic boundaries with slab decomposition are not supported by this build");
+    // duplicates: the particles within KernelSize of a periodic face, both faces, plus corner copies -> generous slack
+    double frac=0;
+    for(int k=0;k<3;k++)if((p.periactive>>k)&1)frac+=2.5*double(p.kernelsize)/std::max(p.maprealsize[k],double(p.kernelsize));
+    extra_capacity+=unsigned(std::min(3.0,frac)*npsel)+4096u;
   }
   r=b2s_create(&p,device,npsel+extra_capacity,&s->ctx);
   if(r)throw std::runtime_error(std::string("b2s_create failed: ")+b2s_error_string(r));

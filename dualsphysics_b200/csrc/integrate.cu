@@ -28,14 +28,14 @@ struct IntegArgs {
   const uint8_t* boundmode;   // mDBC2 only (else NULL): boundary particles with mode>=BMODE_MDBC2 keep their velrho
 };
 
-// KerUpdatePos / JSphCpu::UpdatePos (JSphCpu.cpp:1458-1510) without periodic boundaries.
+// KerUpdatePos / JSphCpu::UpdatePos (JSphCpu.cpp:1458-1516), periodic wrap included (b2s_pos_to_cell).
 __device__ __forceinline__ void update_pos(const DevCte& c, double rx,double ry,double rz, double movx,double movy,double movz,
   bool outrho, typecode rcode, uint32_t p, double2* posxy, double* posz, uint32_t* dcell, typecode* code)
 {
   const bool outmov=(fabsf(float(movx))>c.movlimit || fabsf(float(movy))>c.movlimit || fabsf(float(movz))>c.movlimit);
   rx+=movx; ry+=movy; rz+=movz;
-  const double dx=rx-c.maprealposmin[0], dy=ry-c.maprealposmin[1], dz=rz-c.maprealposmin[2];
-  const bool out=(dx!=dx || dy!=dy || dz!=dz || dx<0 || dy<0 || dz<0 || dx>=c.maprealsize[0] || dy>=c.maprealsize[1] || dz>=c.maprealsize[2]);
+  uint32_t cell;
+  const bool out=b2s_pos_to_cell(c,rx,ry,rz,cell);
   posxy[p]=make_double2(rx,ry); posz[p]=rz;
   if(outrho || outmov || out){
     if(out)rcode=typecode(B2S_CODE_SETNORMAL(rcode)|B2S_CODE_OUTPOS);
@@ -44,10 +44,7 @@ __device__ __forceinline__ void update_pos(const DevCte& c, double rx,double ry,
     code[p]=rcode;
     dcell[p]=B2S_DCEL_MAPOUT;
   }
-  else{
-    const uint32_t cx=uint32_t(dx/c.scell_d), cy=uint32_t(dy/c.scell_d), cz=uint32_t(dz/c.scell_d);
-    dcell[p]=B2S_DCEL_CELL(c.domcellcode,cx,cy,cz);
-  }
+  else dcell[p]=cell;
 }
 
 // ---- Symplectic predictor ---------------------------------------------------------------------

@@ -28,11 +28,11 @@ __global__ void k_move_rectsinu(MotionDev m, const StepState* __restrict__ st, c
   // KerMoveLinBound: pos+=mvpos (double), cell recomputed, vel=mvvel, rho kept.
   double2 xy=posxy[p]; double z=posz[p];
   xy.x+=mv[0]; xy.y+=mv[1]; z+=mv[2];
+  uint32_t cell;
+  const bool out=b2s_pos_to_cell(c,xy.x,xy.y,z,cell);
   posxy[p]=xy; posz[p]=z;
-  const double dx=xy.x-c.maprealposmin[0], dy=xy.y-c.maprealposmin[1], dz=z-c.maprealposmin[2];
-  const bool out=(dx!=dx || dy!=dy || dz!=dz || dx<0 || dy<0 || dz<0 || dx>=c.maprealsize[0] || dy>=c.maprealsize[1] || dz>=c.maprealsize[2]);
-  if(out){ code[p]=typecode(B2S_CODE_SETNORMAL(code[p])|B2S_CODE_OUTPOS); dcell[p]=B2S_DCEL_MAPOUT; }
-  else dcell[p]=B2S_DCEL_CELL(c.domcellcode,uint32_t(dx/c.scell_d),uint32_t(dy/c.scell_d),uint32_t(dz/c.scell_d));
+  if(out)code[p]=typecode(B2S_CODE_SETNORMAL(code[p])|B2S_CODE_OUTPOS);
+  dcell[p]=cell;
   float4 v=velrho[p]; v.x=vx; v.y=vy; v.z=vz; velrho[p]=v;
 }
 
@@ -70,11 +70,11 @@ __global__ void k_move_linear(uint32_t idbegin,uint32_t count,double mx,double m
   if(p>=ds->np)return;
   double2 xy=posxy[p]; double z=posz[p];
   xy.x+=mx; xy.y+=my; z+=mz;
+  uint32_t cell;
+  const bool out=b2s_pos_to_cell(c,xy.x,xy.y,z,cell);
   posxy[p]=xy; posz[p]=z;
-  const double dx=xy.x-c.maprealposmin[0], dy=xy.y-c.maprealposmin[1], dz=z-c.maprealposmin[2];
-  const bool out=(dx!=dx || dy!=dy || dz!=dz || dx<0 || dy<0 || dz<0 || dx>=c.maprealsize[0] || dy>=c.maprealsize[1] || dz>=c.maprealsize[2]);
-  if(out){ code[p]=typecode(B2S_CODE_SETNORMAL(code[p])|B2S_CODE_OUTPOS); dcell[p]=B2S_DCEL_MAPOUT; }
-  else dcell[p]=B2S_DCEL_CELL(c.domcellcode,uint32_t(dx/c.scell_d),uint32_t(dy/c.scell_d),uint32_t(dz/c.scell_d));
+  if(out)code[p]=typecode(B2S_CODE_SETNORMAL(code[p])|B2S_CODE_OUTPOS);
+  dcell[p]=cell;
   float4 v=velrho[p]; v.x=vx; v.y=vy; v.z=vz; velrho[p]=v;
 }
 

@@ -45,6 +45,7 @@ class Params(C.Structure):
         ("maprealposmin", C.c_double * 3), ("maprealposmax", C.c_double * 3),
         ("casenp", C.c_uint32), ("casenfixed", C.c_uint32), ("casenmoving", C.c_uint32),
         ("casenfloat", C.c_uint32), ("casenfluid", C.c_uint32),
+        ("periactive", C.c_int32), ("perixinc", C.c_double * 3), ("periyinc", C.c_double * 3), ("perizinc", C.c_double * 3),
         # derived
         ("kernelsize", C.c_float), ("kernelsize2", C.c_float), ("awen", C.c_float), ("bwenh", C.c_float),
         ("cubic_a1", C.c_float), ("cubic_a2", C.c_float), ("cubic_aa", C.c_float), ("cubic_a24", C.c_float),
@@ -252,7 +253,8 @@ class Context:
             p = self.params
             n = p.casenmoving + p.casenfloat
         else:
-            n = max(inf.np + inf.npf_out_last + inf.npb_out_last + 16, 1)
+            # cellpart/sortpart cover the particles that ENTERED the divide: + excluded ones and the previous periodic duplicates / ghosts
+            n = max(2 * inf.np + inf.npf_out_last + inf.npb_out_last + 16, 1)
         buf = np.empty((n, k) if k > 1 else (n,), dtype=dt)
         cnt = C.c_size_t(0)
         self._chk(self._lib.b2s_get_array(self._h, name.encode(), buf.ctypes.data, buf.nbytes, C.byref(cnt)))

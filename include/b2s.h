@@ -74,12 +74,18 @@ typedef struct b2s_params {
   double   dp, cflnumber, dtini, dtmin, coefdtmin, ftpause;
   double   maprealposmin[3], maprealposmax[3];   /* after ResizeMapLimits (JSph.cpp:1445-1476) */
   uint32_t casenp, casenfixed, casenmoving, casenfloat, casenfluid;
+  /* periodic boundaries (JSph.cpp:815-827): bit0 X, bit1 Y, bit2 Z; periNinc = displacement applied to a particle that
+   * leaves through the upper face of axis N.  Primary input: the off-axis components (XPeriodicIncY ...); the component
+   * along the axis itself is set by b2s_config_finalize to -MapRealSize (JSph.cpp:2186-2188).  maprealposmin/max of a
+   * periodic axis = case limits -+ dp/2 (JPartsLoad4::CalculeLimitsPos, JPartsLoad4.cpp:389-399). */
+  int32_t  periactive;
+  double   perixinc[3], periyinc[3], perizinc[3];
   /* ---- derived values (b2s_config_finalize) ---- */
   float    kernelsize, kernelsize2, awen, bwenh;            /* FunSphKernel.h:198-209 */
   float    cubic_a1, cubic_a2, cubic_aa, cubic_a24, cubic_c1, cubic_d1, cubic_c2, cubic_od_wdeltap; /* :45-85 */
   float    eta2, ddtkh, ddtgz, spssmag, spsblin, scell, movlimit, ovrhopzero;
   double   cs0;
-  double   map_posmin[3], map_posmax[3], map_size[3];       /* == maprealpos without periodic */
+  double   map_posmin[3], map_posmax[3], map_size[3];       /* == maprealpos; widened by KernelSize on periodic axes (JSph.cpp:2191-2195) */
   double   maprealsize[3];
   uint32_t map_cells[3];                                     /* ceil(map_size/scell) */
   uint32_t domcells[3];                                      /* single domain: == map_cells */
