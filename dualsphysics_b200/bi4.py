@@ -251,6 +251,21 @@ def load(path: str) -> Item:
     return _Reader(buf[64:], si64).item()
 
 
+def load_list(path: str) -> list:
+    """Read a list file (JBinaryData::SaveFileListApp / LoadFileListApp, JBinaryData.cpp:1736-1810): the head item followed
+    by the items appended to it, one per saved PART (PartFloatInfo.ibi4, PartOut_000.obi4, PartMotionRef.ibi4, PartInfo.ibi4)."""
+    with open(path, "rb") as f:
+        buf = f.read()
+    if len(buf) < 64 or not buf.startswith(b"#FileJBD "):
+        raise ValueError(f"{path}: not a JBinaryData file")
+    si64 = buf[61] != 0
+    rd = _Reader(buf[64:], si64)
+    out = []
+    while rd.p < len(rd.b):
+        out.append(rd.item())
+    return out
+
+
 # ---------------------------------------------------------------------------
 # JPartDataBi4 helpers (JPartDataBi4.cpp:190-390)
 # ---------------------------------------------------------------------------

@@ -156,6 +156,9 @@ struct b2s_ctx {
   bool defer_attr_set;   // forces_defer.cu: dynamic shared memory opt-in done
   // gauges (gauges.cu): device list + results of the last evaluation (device and pinned host)
   std::vector<int> gauge_types; std::vector<unsigned char> gauges_host; void* gauges_dev; float* gauge_res_dev; float* gauge_res_h; float* gauge_mass_dev; uint32_t gauge_points;
+  // excluded particles (JSphGpuSingle::RunCellDivide -> AddParticlesOut -> PartsOut, JSphGpuSingle.cpp:455-470): 48-byte
+  // records appended on the device by every divide, drained by b2s_out_fetch (PartOut_000.obi4); NULL = not collected
+  void* out_dev; uint32_t* out_count_dev; uint32_t out_cap;
   // damping zones (damping.cu): DampOp records, host list + device copy
   std::vector<unsigned char> damp_host; void* damp_dev; bool damp_dirty;
   // scratch for byid download

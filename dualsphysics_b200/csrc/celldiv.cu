@@ -370,6 +370,24 @@ __global__ void __launch_bounds__(DIV_BS) k_reorder(const DivState* __restrict__
   if((threadIdx.x&31)==0 && v2>0.f)atomicMax(&st->velmax2_bits,__float_as_uint(v2));
 }
 
+// Excluded fluid particles of this divide: after the sort they sit right behind the valid ones, [np+npb_out, +npf_out).
+// Record: u32 idp | u32 motive (1 position, 2 density, 3 displacement: JPartOutBi4Save) | f64 pos[3] | f32 vel[3] | f32 rho.
+struct OutRec { uint32_t idp, motive; double pos[3]; float vel[3]; float rho; };
+__global__ void __launch_bounds__(DIV_BS) k_collect_out(const DivState* __restrict__ ds, PartSet a, OutRec* out, uint32_t* count, uint32_t cap){
+  const uint32_t n=ds->npf_out, p0=ds->np+ds->npb_out;
+  for(uint32_t i=blockIdx.x*blockDim.x+threadIdx.x; i<n; i+=gridDim.x*blockDim.x){
+    const uint32_t p=p0+i;
+    const uint32_t k=atomicAdd(count,1u);
+    if(k>=cap)continue;   // overflow: the count keeps growing and b2s_out_fetch reports it
+    const typecode c=a.code[p];
+    const uint32_t sp=B2S_CODE_SPECIAL(c);
+    OutRec r; r.idp=a.idp[p]; r.motive=(sp==B2S_CODE_OUTRHO? 2u: (sp==B2S_CODE_OUTMOV? 3u: 1u));
+    const double2 xy=a.posxy[p]; r.pos[0]=xy.x; r.pos[1]=xy.y; r.pos[2]=a.posz[p];
+    const float4 v=a.velrho[p]; r.vel[0]=v.x; r.vel[1]=v.y; r.vel[2]=v.z; r.rho=v.w;
+    out[k]=r;
+  }
+}
+
 __global__ void k_reset_step_maxima(StepState* st){
   st->velmax2_bits=0; st->acemax2_bits=0; st->viscdtmax_bits=0;
 }
@@ -427,6 +445,7 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   if(a.ridp)B2S_CUDA(ctx,cudaMemsetAsync(ctx->ridp,0xff,size_t(ctx->prm.casenmoving+ctx->prm.casenfloat)*4,s));
   k_reorder<<<b2s_blocks(nptot,DIV_BS),DIV_BS,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte); B2S_LAUNCHED(ctx);
   { PartSet t=ctx->cur; ctx->cur=ctx->alt; ctx->alt=t; }
+  if(ctx->out_dev){ k_collect_out<<<32,DIV_BS,0,s>>>(ctx->div,ctx->cur,(OutRec*)ctx->out_dev,ctx->out_count_dev,ctx->out_cap); B2S_LAUNCHED(ctx); }
   if(ctx->pre_active){
     std::swap(ctx->pospre_xy,ctx->pospre_xy_alt); std::swap(ctx->pospre_z,ctx->pospre_z_alt); std::swap(ctx->velrhopre,ctx->velrhopre_alt);
   }
@@ -435,6 +454,44 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   if(ctx->boundnor)std::swap(ctx->boundnor,ctx->boundnor_alt);
   ctx->bound_changed=false;
   B2S_CUDA(ctx,cudaGetLastError());
+  return B2S_OK;
+}
+
+// ---- excluded particles: enable the collection / drain it ----------------------------------------------------
+extern "C" int b2s_out_enable(b2s_ctx* ctx, uint32_t capacity){
+  if(!ctx || !capacity)return B2S_ERR_ARG;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  if(ctx->out_dev){ cudaFree(ctx->out_dev); cudaFree(ctx->out_count_dev); ctx->out_dev=NULL; ctx->out_count_dev=NULL; }
+  B2S_CUDA(ctx,cudaMalloc(&ctx->out_dev,size_t(capacity)*sizeof(OutRec)));
+  B2S_CUDA(ctx,cudaMalloc((void**)&ctx->out_count_dev,4));
+  B2S_CUDA(ctx,cudaMemsetAsync(ctx->out_count_dev,0,4,ctx->stream));
+  ctx->out_cap=capacity;
+  return B2S_OK;
+}
+extern "C" int b2s_out_fetch(b2s_ctx* ctx, uint32_t maxcount, uint32_t* count_out, uint32_t* idp, double* pos, float* vel, float* rhop, uint8_t* motive){
+  if(!ctx || !count_out)return B2S_ERR_ARG;
+  *count_out=0;
+  if(!ctx->out_dev)return b2s_fail(ctx,B2S_ERR_STATE,"excluded particles are not collected (b2s_out_enable)");
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  uint32_t n=0;
+  B2S_CUDA(ctx,cudaMemcpyAsync(&n,ctx->out_count_dev,4,cudaMemcpyDeviceToHost,ctx->stream));
+  B2S_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  if(n>ctx->out_cap)return b2s_fail(ctx,B2S_ERR_NOMEM,"%u particles were excluded since the last fetch but the buffer holds %u",n,ctx->out_cap);
+  if(n>maxcount)return b2s_fail(ctx,B2S_ERR_ARG,"b2s_out_fetch: %u records pending, room for %u",n,maxcount);
+  if(n){
+    std::vector<OutRec> h(n);
+    B2S_CUDA(ctx,cudaMemcpyAsync(h.data(),ctx->out_dev,size_t(n)*sizeof(OutRec),cudaMemcpyDeviceToHost,ctx->stream));
+    B2S_CUDA(ctx,cudaMemsetAsync(ctx->out_count_dev,0,4,ctx->stream));
+    B2S_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+    for(uint32_t i=0;i<n;i++){
+      if(idp)idp[i]=h[i].idp;
+      if(pos){ pos[size_t(i)*3]=h[i].pos[0]; pos[size_t(i)*3+1]=h[i].pos[1]; pos[size_t(i)*3+2]=h[i].pos[2]; }
+      if(vel){ vel[size_t(i)*3]=h[i].vel[0]; vel[size_t(i)*3+1]=h[i].vel[1]; vel[size_t(i)*3+2]=h[i].vel[2]; }
+      if(rhop)rhop[i]=h[i].rho;
+      if(motive)motive[i]=uint8_t(h[i].motive);
+    }
+  }
+  *count_out=n;
   return B2S_OK;
 }
 

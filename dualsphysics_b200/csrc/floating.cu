@@ -101,6 +101,7 @@ __global__ void k_ft_compute(FtDev* fts, uint32_t cf, const float* __restrict__ 
     }
     for(int i=0;i<3;i++)aceang[i]=fang[0]*inv[i][0]+fang[1]*inv[i][1]+fang[2]*inv[i][2];
   }
+  if(!predictor)for(int k=0;k<3;k++){ fo.fluforcelin[k]=flin[k]; fo.fluforceang[k]=fang[k]; fo.preacelin[k]=acelin[k]; fo.preaceang[k]=aceang[k]; }   // saveftvalues (JSph.cpp:2613-2620)
   float fvel[3],fomega[3];
   for(int k=0;k<3;k++){
     d.ncenter[k]=fo.center[k]+dt*fo.fvel[k];

@@ -201,4 +201,44 @@ std::unique_ptr<Bi4Item> bi4_load(const std::string& file){
   return r.item();
 }
 
+std::vector<std::unique_ptr<Bi4Item>> bi4_load_list(const std::string& file){
+  std::ifstream f(file.c_str(),std::ios::binary);
+  if(!f)throw std::runtime_error("bi4: cannot open "+file);
+  f.seekg(0,std::ios::end); const size_t n=size_t(f.tellg()); f.seekg(0,std::ios::beg);
+  if(n<64)throw std::runtime_error("bi4: file too small "+file);
+  char head[64]; f.read(head,64);
+  if(strncmp(head,"#FileJBD ",9)!=0)throw std::runtime_error("bi4: not a JBinaryData file "+file);
+  const bool si64=(head[61]!=0);
+  std::vector<char> buf(n-64);
+  f.read(buf.data(),n-64);
+  if(!f)throw std::runtime_error("bi4: read failure "+file);
+  Rd r(buf,si64);
+  std::vector<std::unique_ptr<Bi4Item>> out;
+  while(r.p<buf.size())out.push_back(r.item());
+  return out;
+}
+
+void bi4_save_listapp(const std::string& file,const std::string& filecode,const Bi4Item& head,const Bi4Item* item,bool truncate){
+  bool exists=false;
+  if(!truncate){ FILE* t=fopen(file.c_str(),"rb"); if(t){ fseek(t,0,SEEK_END); exists=(ftell(t)>=64); fclose(t); } }
+  FILE* f=fopen(file.c_str(),exists? "ab": "wb");
+  if(!f)throw std::runtime_error("bi4: cannot write "+file);
+  if(!exists){
+    char hd[64]; memset(hd,0,64);
+    std::string titu="#FileJBD "+filecode;
+    for(size_t c=0;c<58;c++)hd[c]=(c<titu.size()? titu[c]: ' ');
+    hd[58]='\n';
+    fwrite(hd,1,64,f);
+    write_item(f,head,false);
+  }
+  if(item)write_item(f,*item,false);
+  if(fclose(f)!=0)throw std::runtime_error("bi4: write failure "+file);
+}
+
+void bi4_add_array_owned(Bi4Item& it,const std::string& n,int type,uint64_t count,const void* p){
+  it.arrays.emplace_back(); Bi4Array& a=it.arrays.back(); a.name=n; a.type=type; a.count=count;
+  const size_t bytes=size_t(count)*bi4_type_size(type);
+  a.data.assign((const char*)p,(const char*)p+bytes);
+}
+
 } // namespace b2s

@@ -53,5 +53,11 @@ struct Bi4Item {
 // throw std::runtime_error on failure
 std::unique_ptr<Bi4Item> bi4_load(const std::string& file);
 void bi4_save(const std::string& file,const Bi4Item& root,const std::string& filecode);
+// List files (JBinaryData::SaveFileListApp, JBinaryData.cpp:1736-1758): `head` is written when the file is created,
+// `item` (may be NULL: head only) is appended behind whatever the file already holds.
+void bi4_save_listapp(const std::string& file,const std::string& filecode,const Bi4Item& head,const Bi4Item* item,bool truncate);
+// All top-level items of a list file: [0] = head, then the appended items.
+std::vector<std::unique_ptr<Bi4Item>> bi4_load_list(const std::string& file);
+void bi4_add_array_owned(Bi4Item& it,const std::string& n,int type,uint64_t count,const void* p);   // copies the data
 
 } // namespace b2s

@@ -447,7 +447,6 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   std::unique_ptr<Bi4Item> pdata;
   std::vector<uint32_t> pb_idp; unsigned np_case=np;
   if(s->partbegin){
-    if(p.casenfloat)throw std::runtime_error("restart with floating bodies is not supported by this build (needs PartFloat.fbi4)");
     if(p.tboundary==B2S_BC_MDBC)throw std::runtime_error("restart with mDBC is not supported by this build (needs the normals extra data)");
     std::string dir=s->partbegindir; if(!dir.empty() && dir[dir.size()-1]!='/')dir+='/';
     char fn[64]; snprintf(fn,sizeof(fn),"Part_%04u.bi4",s->partbegin);
@@ -589,6 +588,28 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
       f.radius=ftradius[kf++];
       fts.push_back(f);
     }
+    if(s->partbegin){
+      // JSph::InitFloatingsRestart (JSph.cpp:2373-2391): centre, linear and angular velocity of PART <begin> and the radius of
+      // the head replace the initial values; the constant data must match (JPartFloatInfoBi4Load::CheckHeadData)
+      std::string dir=s->partbegindir; if(!dir.empty() && dir[dir.size()-1]!='/')dir+='/';
+      const std::string ffile=dir+"PartFloatInfo.ibi4";
+      std::vector<std::unique_ptr<Bi4Item>> fl=bi4_load_list(ffile);
+      if(fl.empty() || fl[0]->get_uint("FtCount")!=fts.size())throw std::runtime_error("restart: "+ffile+" does not hold the floating bodies of this case");
+      const Bi4Array* hb=fl[0]->array("Beginp"); const Bi4Array* hc=fl[0]->array("Countp"); const Bi4Array* hm=fl[0]->array("Mass"); const Bi4Array* hp=fl[0]->array("Massp"); const Bi4Array* hr=fl[0]->array("Radius");
+      if(!hb||!hc||!hm||!hp||!hr||hb->count!=fts.size())throw std::runtime_error("restart: head arrays missing in "+ffile);
+      const Bi4Item* it=NULL;
+      for(size_t k=1;k<fl.size();k++)if(fl[k]->find("Cpart") && fl[k]->get_uint("Cpart")==s->partbegin)it=fl[k].get();
+      if(!it)throw std::runtime_error("restart: PART not found in "+ffile);
+      const Bi4Array* ac=it->array("center"); const Bi4Array* av=it->array("fvel"); const Bi4Array* ao=it->array("fomega");
+      if(!ac||!av||!ao||ac->count!=fts.size())throw std::runtime_error("restart: floating data missing in "+ffile);
+      for(size_t cf=0;cf<fts.size();cf++){
+        b2s_floating& f=fts[cf];
+        if(((const uint32_t*)hb->ptr())[cf]!=f.begin || ((const uint32_t*)hc->ptr())[cf]!=f.count || ((const float*)hm->ptr())[cf]!=f.mass || ((const float*)hp->ptr())[cf]!=f.massp)
+          throw std::runtime_error("restart: the constant data of the floating bodies in "+ffile+" do not match the case");
+        for(int k=0;k<3;k++){ f.center[k]=((const double*)ac->ptr())[cf*3+k]; f.fvel[k]=((const float*)av->ptr())[cf*3+k]; f.fomega[k]=((const float*)ao->ptr())[cf*3+k]; }
+        if(((const float*)hr->ptr())[cf]>0)f.radius=((const float*)hr->ptr())[cf];   // files of the reference hold 0 here
+      }
+    }
     r=b2s_set_floatings(s->ctx,unsigned(fts.size()),fts.data());
     if(r)throw std::runtime_error(std::string("b2s_set_floatings failed: ")+b2s_last_error(s->ctx));
   }
@@ -624,6 +645,10 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   r=b2s_upload_particles(s->ctx,npsel,idp,code.data(),pos.data(),velrho.data(),norp);
   if(r)throw std::runtime_error(std::string("b2s_upload_particles failed: ")+b2s_last_error(s->ctx));
   s->np0=np;
+  if(!s->dirdata.empty() && slab_nranks<=0){   // excluded particles -> PartOut_000.obi4
+    r=b2s_out_enable(s->ctx,std::max(p.casenfluid,1024u));
+    if(r)throw std::runtime_error(std::string("b2s_out_enable failed: ")+b2s_last_error(s->ctx));
+  }
   if(s->partbegin){   // TimeStepIni / SymplecticDtPre / PartIni of the restart (JSph.cpp:2214-2225)
     r=b2s_set_time(s->ctx,(s->partbeginfirst? s->partbegintime: 0.0),s->partbegindtpre);
     if(r)throw std::runtime_error(std::string("b2s_set_time failed: ")+b2s_last_error(s->ctx));
@@ -662,7 +687,17 @@ static void save_part(b2s_sim* s){
   d.set_bool("Symmetry",false); d.set_bool("Splitting",false);
   char nm[32]; snprintf(nm,sizeof(nm),"PART_%04u",s->part);
   Bi4Item* pt=d.add_item(nm);
-  pt->set_uint("Cpart",s->part); pt->set_double("TimeStep",inf.timestep); pt->set_uint("Npok",n); pt->set_uint("Nout",p.casenp-n);
+  // particles excluded since the previous PART (JSph::AddParticlesOut / PartsOut): drained from the device buffer
+  uint32_t nout=0; unsigned nmot[4]={0,0,0,0};
+  std::vector<uint32_t> oid; std::vector<double> opos; std::vector<float> ovel, orho; std::vector<uint8_t> omot;
+  {
+    const uint32_t ocap=std::max(p.casenfluid,1024u);
+    oid.resize(ocap); opos.resize(size_t(ocap)*3); ovel.resize(size_t(ocap)*3); orho.resize(ocap); omot.resize(ocap);
+    r=b2s_out_fetch(s->ctx,ocap,&nout,oid.data(),opos.data(),ovel.data(),orho.data(),omot.data());
+    if(r)throw std::runtime_error(std::string("b2s_out_fetch failed: ")+b2s_last_error(s->ctx));
+    for(uint32_t i=0;i<nout;i++)nmot[omot[i]&3]++;
+  }
+  pt->set_uint("Cpart",s->part); pt->set_double("TimeStep",inf.timestep); pt->set_uint("Npok",n); pt->set_uint("Nout",nout);
   pt->set_uint("Step",inf.nstep); pt->set_double("RunTime",0);
   pt->set_double3("DomainMin",p.maprealposmin); pt->set_double3("DomainMax",p.maprealposmax);
   pt->set_ullong("NpTotal",p.casenp);
@@ -674,7 +709,7 @@ static void save_part(b2s_sim* s){
   pt->set_double("timesim",0);
   pt->set_uint("nct",inf.nct); pt->set_uint("nctsize",inf.nct);
   pt->set_uint("npsim",inf.np); pt->set_uint("npsize",inf.np); pt->set_uint("npnormal",inf.np); pt->set_uint("npsave",n); pt->set_uint("npnew",0);
-  pt->set_uint("noutpos",inf.npf_out_total); pt->set_uint("noutrho",0); pt->set_uint("noutmov",0);
+  pt->set_uint("noutpos",nmot[1]); pt->set_uint("noutrho",nmot[2]); pt->set_uint("noutmov",nmot[3]);
   pt->set_uint("npbin",inf.npbok); pt->set_uint("npbout",inf.npb-inf.npbok); pt->set_uint("npf",inf.np-inf.npb); pt->set_uint("npbper",0); pt->set_uint("npfper",0);
   pt->set_llong("cpualloc",int64_t(cap)*(4+24+12+4));
   s->part_nstep0=inf.nstep; s->part_time0=inf.timestep; s->part_dtmin=DBL_MAX; s->part_dtmax=0;
@@ -686,6 +721,61 @@ static void save_part(b2s_sim* s){
   pt->add_array_ext("Rhop",BT_FLOAT,n,rho.data());
   char fn[64]; snprintf(fn,sizeof(fn),"Part_%04u.bi4",s->part);
   bi4_save(s->dirdata+fn,d,"JPartDataBi4");
+  const bool firstsave=!s->head_saved;
+  const bool fresh=(firstsave && !s->partbeginfirst);   // a restart that continues the numbering appends to the list files
+  { // PartInfo.ibi4 (JPartDataBi4::SaveFileInfo, JPartDataBi4.cpp): the head values + one item of values per PART
+    Bi4Item hd("JPartDataBi4"); hd.values=d.values;
+    Bi4Item pi(nm); pi.hide=true; pi.values=pt->values;
+    bi4_save_listapp(s->dirdata+"PartInfo.ibi4","JPartDataBi4_Info",hd,&pi,fresh);
+  }
+  { // PartOut_000.obi4 (JPartOutBi4Save::ConfigBasic/ConfigParticles/ConfigLimits/SavePartOut, JPartOutBi4Save.cpp:119-232)
+    Bi4Item hd("JPartOutBi4");
+    hd.set_uint("Piece",0); hd.set_uint("Npiece",1); hd.set_text("RunCode",s->runcode); hd.set_text("Date",s->date);
+    hd.set_text("AppName","b200sph v0.1 (DualSPHysics v5.4 case interface)"); hd.set_bool("Data2d",p.simulate2d!=0);
+    hd.set_uint("FmtVersion",180320); hd.set_uint("Block",0);
+    hd.set_double3("MapPosMin",p.maprealposmin); hd.set_double3("MapPosMax",p.maprealposmax);
+    hd.set_float("RhopMin",p.rhopoutmin); hd.set_float("RhopMax",p.rhopoutmax);
+    hd.set_ullong("CaseNp",p.casenp); hd.set_ullong("CaseNfixed",p.casenfixed); hd.set_ullong("CaseNmoving",p.casenmoving);
+    hd.set_ullong("CaseNfloat",p.casenfloat); hd.set_ullong("CaseNfluid",p.casenfluid);
+    Bi4Item po(nm); po.hide=true;
+    po.set_uint("Cpart",s->part); po.set_double("TimeStep",inf.timestep); po.set_uint("Nout",nout);
+    std::vector<float> oposf;
+    po.add_array_ext("Idp",BT_UINT,nout,oid.data());
+    if(s->svposdouble)po.add_array_ext("Posd",BT_DOUBLE3,nout,opos.data());
+    else{ oposf.resize(size_t(nout)*3); for(size_t i=0;i<size_t(nout)*3;i++)oposf[i]=float(opos[i]); po.add_array_ext("Pos",BT_FLOAT3,nout,oposf.data()); }
+    po.add_array_ext("Vel",BT_FLOAT3,nout,ovel.data()); po.add_array_ext("Rhop",BT_FLOAT,nout,orho.data()); po.add_array_ext("Motive",BT_UCHAR,nout,omot.data());
+    if(firstsave || nout)bi4_save_listapp(s->dirdata+"PartOut_000.obi4","JPartOutBi4",hd,(nout? &po: NULL),fresh);
+  }
+  if(p.casenfloat){ // PartFloatInfo.ibi4 (JPartFloatInfoBi4Save::Config/MakeBdPartSingle/SaveBdPart, JPartFloatInfoBi4.cpp:464-602)
+    std::vector<const PartBlock*> fb; for(auto& b:s->blocks)if(b.type==2)fb.push_back(&b);
+    const unsigned ftc=unsigned(fb.size());
+    std::vector<b2s_floating> fts(ftc);
+    r=b2s_get_floatings(s->ctx,ftc,fts.data());
+    if(r)throw std::runtime_error(std::string("b2s_get_floatings failed: ")+b2s_last_error(s->ctx));
+    unsigned mkboundfirst=0; for(auto& b:s->blocks)if(b.type!=3){ mkboundfirst=b.mk-b.mktype; break; }
+    Bi4Item hd("JPartFloatInfoBi4");
+    hd.set_text("AppName","b200sph v0.1 (DualSPHysics v5.4 case interface)"); hd.set_uint("FormatVer",230729); hd.set_bool("MainFile",true);
+    hd.set_double("TimeOut",s->timepart);
+    { Bi4Value v; v.name="MkBoundFirst"; v.type=BT_USHORT; v.i=0; v.u=mkboundfirst; v.d=0; v.d3[0]=v.d3[1]=v.d3[2]=0; hd.values.push_back(v); }
+    hd.set_uint("FtCount",ftc); hd.set_uint("FptCount",0);
+    std::vector<uint16_t> mkb(ftc); std::vector<uint32_t> beg(ftc),cnt(ftc); std::vector<float> mass(ftc),massp(ftc),radi(ftc);
+    std::vector<double> cen(size_t(ftc)*3); std::vector<float> f3[10]; for(auto& v:f3)v.assign(size_t(ftc)*3,0.f);
+    for(unsigned cf=0;cf<ftc;cf++){
+      mkb[cf]=uint16_t(fb[cf]->mktype); beg[cf]=fts[cf].begin; cnt[cf]=fts[cf].count; mass[cf]=fts[cf].mass; massp[cf]=fts[cf].massp; radi[cf]=fts[cf].radius;
+      for(int k=0;k<3;k++){
+        cen[cf*3+k]=fts[cf].center[k]; f3[0][cf*3+k]=fts[cf].fvel[k]; f3[1][cf*3+k]=fts[cf].fomega[k]; f3[2][cf*3+k]=fts[cf].facelin[k]; f3[3][cf*3+k]=fts[cf].faceang[k];
+        f3[6][cf*3+k]=fts[cf].fluforcelin[k]; f3[7][cf*3+k]=fts[cf].fluforceang[k]; f3[8][cf*3+k]=fts[cf].preacelin[k]; f3[9][cf*3+k]=fts[cf].preaceang[k];
+      }
+    }
+    hd.add_array_ext("MkBound",BT_USHORT,ftc,mkb.data()); hd.add_array_ext("Beginp",BT_UINT,ftc,beg.data()); hd.add_array_ext("Countp",BT_UINT,ftc,cnt.data());
+    hd.add_array_ext("Mass",BT_FLOAT,ftc,mass.data()); hd.add_array_ext("Massp",BT_FLOAT,ftc,massp.data()); hd.add_array_ext("Radius",BT_FLOAT,ftc,radi.data());
+    Bi4Item pf(nm); pf.hide=true;
+    pf.set_uint("Cpart",s->part); pf.set_double("TimeStep",inf.timestep); pf.set_uint("Step",inf.nstep);
+    pf.add_array_ext("center",BT_DOUBLE3,ftc,cen.data());
+    static const char* fn3[10]={"fvel","fomega","facelin","faceang","extforcelin","extforceang","fluforcelin","fluforceang","preacelin","preaceang"};
+    for(int a=0;a<10;a++)pf.add_array_ext(fn3[a],BT_FLOAT3,ftc,f3[a].data());
+    bi4_save_listapp(s->dirdata+"PartFloatInfo.ibi4","JPartFloatInfoBi4",hd,&pf,fresh);
+  }
   if(!s->head_saved){
     s->head_saved=true;
     // Part_Head.ibi4 (JPartDataHead::SaveFile, JPartDataHead.cpp): head values + MkBlocks

@@ -68,6 +68,7 @@ class Floating(C.Structure):
         ("radius", C.c_float), ("constraints", C.c_int32), ("center", C.c_double * 3),
         ("angles", C.c_float * 3), ("fvel", C.c_float * 3), ("fomega", C.c_float * 3),
         ("facelin", C.c_float * 3), ("faceang", C.c_float * 3), ("inertiaini", C.c_float * 9),
+        ("fluforcelin", C.c_float * 3), ("fluforceang", C.c_float * 3), ("preacelin", C.c_float * 3), ("preaceang", C.c_float * 3),
     ]
 
 
@@ -89,7 +90,7 @@ ABI_SYMBOLS = [
     "b2s_config_finalize", "b2s_error_string", "b2s_create", "b2s_destroy", "b2s_last_error", "b2s_get_params",
     "b2s_upload_particles", "b2s_download_particles", "b2s_download_particles_byid", "b2s_get_array",
     "b2s_get_info", "b2s_set_time", "b2s_celldiv", "b2s_interaction", "b2s_compute_verlet", "b2s_compute_symplectic_pre",
-    "b2s_compute_symplectic_corr", "b2s_compute_step", "b2s_run_steps", "b2s_add_motion_rectsinu", "b2s_add_damping_plane", "b2s_add_damping_box",
+    "b2s_compute_symplectic_corr", "b2s_compute_step", "b2s_run_steps", "b2s_add_motion_rectsinu", "b2s_add_damping_plane", "b2s_add_damping_box", "b2s_out_enable", "b2s_out_fetch",
     "b2s_move_linear", "b2s_set_floatings", "b2s_get_floatings", "b2s_count_pairs", "b2s_time_interaction",
     "b2s_gauge_add_velocity", "b2s_gauge_add_swl", "b2s_gauges_compute", "b2s_gauge_result",
     "b2s_launch_count", "b2s_get_stream", "b2s_set_interaction_variant", "b2s_slab_config",
@@ -143,6 +144,8 @@ def load_library():
     dp_, fp_ = C.POINTER(C.c_double), C.POINTER(C.c_float)
     lib.b2s_add_damping_plane.argtypes = [vp, dp_, dp_, C.c_float, C.c_float, fp_, dp_]
     lib.b2s_add_damping_box.argtypes = [vp, dp_, dp_, dp_, dp_, C.c_float, C.c_float, fp_, C.c_uint32]
+    lib.b2s_out_enable.argtypes = [vp, C.c_uint32]
+    lib.b2s_out_fetch.argtypes = [vp, C.c_uint32, u32p, vp, vp, vp, vp, vp]
     lib.b2s_move_linear.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     lib.b2s_set_floatings.argtypes = [vp, C.c_uint32, C.POINTER(Floating)]
     lib.b2s_get_floatings.argtypes = [vp, C.c_uint32, C.POINTER(Floating)]
@@ -408,6 +411,18 @@ class Context:
         d3 = C.c_double * 3
         self._chk(self._lib.b2s_add_damping_box(self._h, d3(*limitmin_ini), d3(*limitmin_end), d3(*limitmax_ini), d3(*limitmax_end),
                                                 overlimit, redumax, (C.c_float * 3)(*factorxyz), directions))
+
+    def out_enable(self, capacity: int):
+        self._chk(self._lib.b2s_out_enable(self._h, capacity))
+
+    def out_fetch(self, maxcount: int = 1 << 20):
+        idp = np.empty(maxcount, np.uint32); pos = np.empty((maxcount, 3), np.float64); vel = np.empty((maxcount, 3), np.float32)
+        rho = np.empty(maxcount, np.float32); mot = np.empty(maxcount, np.uint8)
+        cnt = C.c_uint32(0)
+        self._chk(self._lib.b2s_out_fetch(self._h, maxcount, C.byref(cnt), idp.ctypes.data, pos.ctypes.data, vel.ctypes.data,
+                                          rho.ctypes.data, mot.ctypes.data))
+        c = cnt.value
+        return idp[:c], pos[:c], vel[:c], rho[:c], mot[:c]
 
     def set_floatings(self, fts):
         arr = (Floating * len(fts))(*fts)

@@ -106,6 +106,9 @@ typedef struct b2s_floating {
   float    fvel[3], fomega[3];
   float    facelin[3], faceang[3];
   float    inertiaini[9];       /* row-major 3x3 */
+  /* values of the last corrector / Verlet update, for PartFloatInfo.ibi4 (JSph.cpp:2613-2620): force and torque of the
+   * fluid on the body (N, N*m) and the accelerations before the motion constraints (gravity included) */
+  float    fluforcelin[3], fluforceang[3], preacelin[3], preaceang[3];
 } b2s_floating;
 
 /* Run-time counters and maxima, one coherent snapshot (replaces the blocking scalar
@@ -195,6 +198,12 @@ int b2s_add_motion_rectsinu(b2s_ctx* ctx, uint32_t idbegin, uint32_t count, cons
                             const double ampl[3], const double phase[3], double tstart, double tend);
 /* Direct form: displace a block now (MOTT_Linear data: JDsMotionDef.h). */
 int b2s_move_linear(b2s_ctx* ctx, uint32_t idbegin, uint32_t count, const double mvpos[3], const float mvvel[3]);
+
+/* ---- excluded particles: JSphGpuSingle::RunCellDivide -> ParticlesDataDown(...) -> AddParticlesOut (JSphGpuSingle.cpp:455-470,
+ * JSph.cpp:2981-3040): after b2s_out_enable every cell divide appends the fluid particles it excludes (id, position, velocity,
+ * density, motive 1 position / 2 density / 3 displacement) to a device buffer; b2s_out_fetch drains it (PartOut_000.obi4). */
+int b2s_out_enable(b2s_ctx* ctx, uint32_t capacity);
+int b2s_out_fetch(b2s_ctx* ctx, uint32_t maxcount, uint32_t* count_out, uint32_t* idp, double* pos, float* vel, float* rhop, uint8_t* motive);
 
 /* ---- damping zones: JDsDamping (JDsDamping.cpp:96-131,185-233 plane; :345-391,446-492 box), JSphCpu::RunDamping
  * (JSphCpu.cpp:2312-2316).  Registered zones are applied to the fluid particles once per step, after the integrator and the

@@ -86,3 +86,87 @@ def test_restart_from_part(tmp_path, built_lib):
     # a restart needs its directory argument, and PART files of another case are refused
     r = subprocess.run([CLI, case, str(b), "-symplectic", "-partbegin:1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "partbegin" in (r.stdout + r.stderr)
+
+
+REF_FLOAT = os.path.join(H.GOLDEN, "ref_part_float")
+FLOAT_SPEC = dict(dp=0.05, floating_box=(0.15, 0.25, 0.2, 0.1, 0.15, 0.1), floating_rel_density=0.5, piston=True,
+                  params={"TimeMax": 0.02, "TimeOut": 0.005, "RhopOutMin": 999.5})   # == tools/make_ref_part_float.py
+
+
+def _list_structure(items):
+    return [(it.name, it.hide, tuple((n, t) for n, t, _ in it.values), tuple((n, t) for n, t, _ in it.arrays)) for it in items]
+
+
+def test_reader_understands_reference_list_files():
+    """load_list against the reference's own PartInfo / PartOut / PartFloatInfo files (no GPU needed)."""
+    info = bi4.load_list(os.path.join(REF_FLOAT, "PartInfo.ibi4"))
+    assert info[0].name == "JPartDataBi4" and [it.name for it in info[1:]] == [f"PART_{k:04d}" for k in range(5)]
+    out = bi4.load_list(os.path.join(REF_FLOAT, "PartOut_000.obi4"))
+    assert out[0].name == "JPartOutBi4" and all(it.get("Nout") == len(it.array("Idp")) for it in out[1:])
+    ft = bi4.load_list(os.path.join(REF_FLOAT, "PartFloatInfo.ibi4"))
+    assert ft[0].get("FtCount") == 1 and len(ft) == 6 and ft[1].array("center").shape == (1, 3)
+
+
+@pytest.mark.gpu
+def test_driver_writes_reference_compatible_list_files(tmp_path, built_lib):
+    """PartInfo.ibi4, PartOut_000.obi4 and PartFloatInfo.ibi4 against the files the reference wrote for the same
+    case: same heads and items (names, value/array names and types), same excluded particles, same floating-body history."""
+    H.write_case(tmp_path, **FLOAT_SPEC)
+    out = tmp_path / "out"
+    r = subprocess.run([CLI, str(tmp_path / "Case"), str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "Finished execution (code=0)" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    for name in ("PartInfo.ibi4", "PartOut_000.obi4", "PartFloatInfo.ibi4"):
+        ours, ref = bi4.load_list(str(out / "data" / name)), bi4.load_list(os.path.join(REF_FLOAT, name))
+        so, sr = _list_structure(ours), _list_structure(ref)
+        assert so == sr, f"{name}: structure differs\nours={so}\nref ={sr}"
+    # excluded particles: the same ids per PART (density threshold; at most a few borderline particles may change PART)
+    oo, rr = bi4.load_list(str(out / "data" / "PartOut_000.obi4")), bi4.load_list(os.path.join(REF_FLOAT, "PartOut_000.obi4"))
+    alo, alr = set(), set()
+    for a, b in zip(oo[1:], rr[1:]):
+        assert a.get("Cpart") == b.get("Cpart") and abs(a.get("TimeStep") - b.get("TimeStep")) < 1e-6
+        alo |= set(a.array("Idp").tolist()); alr |= set(b.array("Idp").tolist())
+        assert set(np.unique(a.array("Motive")).tolist()) <= {1, 2, 3}
+    assert len(alo ^ alr) <= 3, sorted(alo ^ alr)
+    first_o, first_r = dict(zip(oo[1].array("Idp").tolist(), oo[1].array("Rhop"))), dict(zip(rr[1].array("Idp").tolist(), rr[1].array("Rhop")))
+    common = sorted(set(first_o) & set(first_r))
+    assert len(common) >= 0.9 * len(first_r) and max(abs(first_o[i] - first_r[i]) for i in common) < 2e-3   # rho ~1000: 2e-6 relative
+    # PART info: counts of the interval
+    io, ir = bi4.load_list(str(out / "data" / "PartInfo.ibi4")), bi4.load_list(os.path.join(REF_FLOAT, "PartInfo.ibi4"))
+    for a, b in zip(io[1:], ir[1:]):
+        assert a.get("Step") == b.get("Step") and abs(a.get("Nout") - b.get("Nout")) <= 3 and abs(a.get("noutrho") - b.get("noutrho")) <= 3
+        assert abs(a.get("Npok") - b.get("Npok")) <= 3
+    # floating body history
+    fo, fr = bi4.load_list(str(out / "data" / "PartFloatInfo.ibi4")), bi4.load_list(os.path.join(REF_FLOAT, "PartFloatInfo.ibi4"))
+    for name in ("MkBound", "Beginp", "Countp", "Mass", "Massp"):
+        assert np.array_equal(fo[0].array(name), fr[0].array(name)), name
+    # (the reference writes Radius=0 in the head: it configures the file before it computes the radius; ours holds the value)
+    assert float(fo[0].array("Radius")[0]) > 0
+    for a, b in zip(fo[1:], fr[1:]):
+        assert a.get("Step") == b.get("Step")
+        assert np.max(np.abs(a.array("center") - b.array("center"))) < 1e-7
+        for name, tol in (("fvel", 1e-3), ("fomega", 1e-3), ("facelin", 5e-3), ("fluforcelin", 5e-3), ("fluforceang", 5e-3), ("preacelin", 5e-3)):
+            ref = b.array(name).astype(np.float64)
+            assert np.max(np.abs(a.array(name) - ref)) <= tol * max(np.max(np.abs(ref)), 1e-6), (name, a.get("Cpart"), a.array(name), ref)
+
+
+@pytest.mark.gpu
+def test_restart_with_floating_body(tmp_path, built_lib):
+    """JSph::InitFloatingsRestart (JSph.cpp:2373-2391): the restart takes centre, velocities and radius of the body from
+    PartFloatInfo.ibi4.  Like the reference it restarts with zero accumulated angles, so the inertia tensor is the initial one:
+    the body has turned by ~1e-3 rad at the restart, which bounds the difference to the uninterrupted run."""
+    spec = dict(FLOAT_SPEC); spec["params"] = {"TimeMax": 0.02, "TimeOut": 0.005}
+    H.write_case(tmp_path, **spec)
+    case = str(tmp_path / "Case")
+    a, b = tmp_path / "runA", tmp_path / "runB"
+    r = subprocess.run([CLI, case, str(a)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    r = subprocess.run([CLI, case, str(b), "-partbegin:2", str(a / "data")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    for k in (3, 4):
+        pa, pb = bi4.load_part(str(a / "data" / f"Part_{k:04d}.bi4")), bi4.load_part(str(b / "data" / f"Part_{k:04d}.bi4"))
+        assert np.array_equal(pa["Idp"], pb["Idp"])
+        assert np.max(np.abs(pa["pos"] - pb["pos"])) < 1e-6, k
+    fa, fb = bi4.load_list(str(a / "data" / "PartFloatInfo.ibi4")), bi4.load_list(str(b / "data" / "PartFloatInfo.ibi4"))
+    ca = {it.get("Cpart"): it.array("center") for it in fa[1:]}
+    cb = {it.get("Cpart"): it.array("center") for it in fb[1:]}
+    assert set(cb) == {2, 3, 4} and all(np.max(np.abs(ca[k] - cb[k])) < 1e-6 for k in cb)
