@@ -13,8 +13,9 @@
 #include <float.h>
 
 #define G_BS 128
-enum { GAUGE_VEL=1, GAUGE_SWL=2 };
-struct GaugeDev { int type; uint32_t np, first; float masslimit; double p0[3], dir[3]; };
+enum { GAUGE_VEL=1, GAUGE_SWL=2, GAUGE_FORCE=3 };
+struct GaugeDev { int type; uint32_t np, first; float masslimit; double p0[3], dir[3];
+  uint32_t fcode, fidbegin, fcount, foff; };   // force gauge: type+value bits of the block, its id range, offset in the partace buffer
 
 // fluid neighbours of a point: returns sum W m/rho (and the velocity sums)
 __device__ void gauge_point(const DivState* ds,const uint32_t* begt,const double2* posxy,const double* posz,const typecode* code,
@@ -88,6 +89,63 @@ __global__ void k_gauge_swl(const GaugeDev* __restrict__ gs, uint32_t ng, const 
   res[cg*4]=float(sx); res[cg*4+1]=float(sy); res[cg*4+2]=float(sz); res[cg*4+3]=0.f;
 }
 
+// ---- force gauge: JGaugeForce::CalculeCpuT (JDsGaugeItem.cpp:1847-1908; GPU JDsGauge_ker.cu:497-587) ----------------------
+// Pressure force of the fluid on the boundary particles of one mk block: for every particle of the block the momentum-equation
+// sum over its fluid neighbours (no viscous part, Wendland gradient also for cubic runs like the reference), stored by id,
+// then one ordered sum times MassBound.  One thread per boundary particle, then one block per gauge.
+__global__ void __launch_bounds__(G_BS) k_gauge_force_ace(GaugeDev gd, const DivState* ds, const uint32_t* __restrict__ begt, const double2* __restrict__ posxy,
+  const double* __restrict__ posz, const typecode* __restrict__ code, const uint32_t* __restrict__ idp, const float4* __restrict__ velrho,
+  float* partace, const __grid_constant__ DevCte c)
+{
+  const uint32_t p1=blockIdx.x*blockDim.x+threadIdx.x;
+  if(p1>=ds->npbok)return;
+  const typecode cod=code[p1];
+  if(uint32_t(cod&(B2S_CODE_MASKTYPE|B2S_CODE_MASKVALUE))!=gd.fcode || !B2S_CODE_ISNORMAL(cod))return;   // periodic copies are ignored
+  const uint32_t id=idp[p1];
+  if(id<gd.fidbegin || id>=gd.fidbegin+gd.fcount)return;
+  const double2 xy1=posxy[p1]; const double z1=posz[p1];
+  const float4 v1=velrho[p1];
+  const float press1=b2s_press(v1.w,c);
+  float ax=0,ay=0,az=0;
+  const int cx=int((xy1.x-c.domposmin[0])/c.scell_d)-int(ds->cellmin[0]);
+  const int cy=int((xy1.y-c.domposmin[1])/c.scell_d)-int(ds->cellmin[1]);
+  const int cz=int((z1   -c.domposmin[2])/c.scell_d)-int(ds->cellmin[2]);
+  const int d=c.scelldiv, ncx=int(ds->ncx), ncy=int(ds->ncy), ncz=int(ds->ncz), nsheet=int(ds->nsheet);
+  const int xini=cx-min(cx,d), xfin=cx+min(ncx-cx-1,d)+1;
+  const int yini=cy-min(cy,d), yfin=cy+min(ncy-cy-1,d)+1;
+  const int zini=cz-min(cz,d), zfin=cz+min(ncz-cz-1,d)+1;
+  if(!(xini<0 || yini<0 || zini<0 || xfin<=xini)){
+    const uint32_t* beg=begt+ds->box_fluid;
+    for(int z=zini;z<zfin;z++)for(int y=yini;y<yfin;y++){
+      const uint32_t pini=beg[y*ncx+z*nsheet+xini], pfin=beg[y*ncx+z*nsheet+xfin];
+      for(uint32_t p2=pini;p2<pfin;p2++){
+        const double2 xy=posxy[p2];
+        const float drx=float(xy1.x-xy.x), dry=float(xy1.y-xy.y), drz=float(z1-posz[p2]);
+        const float rr2=drx*drx+dry*dry+drz*drz;
+        if(rr2<=c.kernelsize2 && rr2>=B2S_ALMOSTZERO && B2S_CODE_ISFLUID(code[p2])){
+          float fac; wab_fac(B2S_KERNEL_WENDLAND,rr2,c,fac);
+          const float4 v2=velrho[p2];
+          const float press2=b2s_press(v2.w,c);
+          const float prs=(press1+press2)/(v1.w*v2.w);
+          const float p_vpm1=-prs*c.massf;
+          ax+=p_vpm1*(fac*drx); ay+=p_vpm1*(fac*dry); az+=p_vpm1*(fac*drz);
+        }
+      }
+    }
+  }
+  float* o=partace+size_t(gd.foff+(id-gd.fidbegin))*3;
+  o[0]=ax; o[1]=ay; o[2]=az;
+}
+__global__ void __launch_bounds__(256) k_gauge_force_sum(GaugeDev gd, int cg, const float* __restrict__ partace, float* res, float massbound){
+  __shared__ double sh[3][256];
+  double s[3]={0,0,0};
+  for(uint32_t i=threadIdx.x;i<gd.fcount;i+=256){ const float* a=partace+size_t(gd.foff+i)*3; s[0]+=a[0]; s[1]+=a[1]; s[2]+=a[2]; }
+  for(int k=0;k<3;k++)sh[k][threadIdx.x]=s[k];
+  __syncthreads();
+  for(int o=128;o;o>>=1){ if(int(threadIdx.x)<o)for(int k=0;k<3;k++)sh[k][threadIdx.x]+=sh[k][threadIdx.x+o]; __syncthreads(); }
+  if(threadIdx.x<3)res[cg*4+threadIdx.x]=float(sh[threadIdx.x][0])*massbound;
+}
+
 static int gauges_upload(b2s_ctx* ctx, const std::vector<GaugeDev>& h){
   cudaFree(ctx->gauges_dev); cudaFree(ctx->gauge_res_dev); cudaFree(ctx->gauge_mass_dev); if(ctx->gauge_res_h)cudaFreeHost(ctx->gauge_res_h);
   ctx->gauges_dev=NULL; ctx->gauge_res_dev=NULL; ctx->gauge_mass_dev=NULL; ctx->gauge_res_h=NULL;
@@ -122,6 +180,24 @@ extern "C" int b2s_gauge_add_velocity(b2s_ctx* ctx, const double point[3], int* 
   if(id)*id=int(h.size())-1;
   return gauges_upload(ctx,h);
 }
+// Force gauge on the boundary block with ids [idbegin,idbegin+count) whose particles carry `typevalue` in the type+value bits
+// of their code (fixed or moving; JGaugeSystem::AddGaugeForce, JDsGaugeSystem.cpp:472-495).
+extern "C" int b2s_gauge_add_force(b2s_ctx* ctx, uint32_t idbegin, uint32_t count, uint32_t typevalue, int* id){
+  if(!ctx || !count)return B2S_ERR_ARG;
+  if((typevalue&B2S_CODE_MASKTYPE)>=B2S_CODE_TYPE_FLOATING || idbegin+count>ctx->prm.casenpb)
+    return b2s_fail(ctx,B2S_ERR_ARG,"force gauge: only fixed or moving boundary blocks are allowed");
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  std::vector<GaugeDev> h=host_list(ctx);
+  GaugeDev g; memset(&g,0,sizeof(g)); g.type=GAUGE_FORCE; g.np=0; g.first=ctx->gauge_points;
+  g.fcode=typevalue&(B2S_CODE_MASKTYPE|B2S_CODE_MASKVALUE); g.fidbegin=idbegin; g.fcount=count; g.foff=ctx->gauge_force_n;
+  ctx->gauge_force_n+=count;
+  cudaFree(ctx->gauge_force_dev); ctx->gauge_force_dev=NULL;
+  B2S_CUDA(ctx,cudaMalloc((void**)&ctx->gauge_force_dev,size_t(ctx->gauge_force_n)*12));
+  h.push_back(g); ctx->gauge_types.push_back(GAUGE_FORCE);
+  host_store(ctx,h);
+  if(id)*id=int(h.size())-1;
+  return gauges_upload(ctx,h);
+}
 extern "C" int b2s_gauge_add_swl(b2s_ctx* ctx, const double point0[3], const double point2[3], double pointdp, float masslimit, int* id){
   if(!ctx || !point0 || !point2 || pointdp<=0 || masslimit<=0)return B2S_ERR_ARG;
   B2S_CUDA(ctx,cudaSetDevice(ctx->device));
@@ -145,7 +221,16 @@ int b2s_gauges_run(b2s_ctx* ctx, int){
   const uint32_t ng=uint32_t(ctx->gauge_types.size());
   if(!ng)return B2S_OK;
   cudaStream_t s=ctx->stream;
-  k_gauge_points<<<b2s_blocks(ctx->gauge_points,G_BS),G_BS,0,s>>>((const GaugeDev*)ctx->gauges_dev,ng,ctx->gauge_points,ctx->div,(const uint32_t*)ctx->begincell,
+  if(ctx->gauge_force_n){
+    B2S_CUDA(ctx,cudaMemsetAsync(ctx->gauge_force_dev,0,size_t(ctx->gauge_force_n)*12,s));
+    const std::vector<GaugeDev> h=host_list(ctx);
+    for(uint32_t cg=0;cg<ng;cg++)if(h[cg].type==GAUGE_FORCE && ctx->npbok_host){
+      k_gauge_force_ace<<<b2s_blocks(ctx->npbok_host,G_BS),G_BS,0,s>>>(h[cg],ctx->div,(const uint32_t*)ctx->begincell,ctx->cur.posxy,ctx->cur.posz,
+        ctx->cur.code,ctx->cur.idp,ctx->cur.velrho,ctx->gauge_force_dev,ctx->cte); B2S_LAUNCHED(ctx);
+      k_gauge_force_sum<<<1,256,0,s>>>(h[cg],int(cg),ctx->gauge_force_dev,ctx->gauge_res_dev,ctx->cte.massb); B2S_LAUNCHED(ctx);
+    }
+  }
+  if(ctx->gauge_points)k_gauge_points<<<b2s_blocks(ctx->gauge_points,G_BS),G_BS,0,s>>>((const GaugeDev*)ctx->gauges_dev,ng,ctx->gauge_points,ctx->div,(const uint32_t*)ctx->begincell,
     ctx->cur.posxy,ctx->cur.posz,ctx->cur.code,ctx->cur.velrho,ctx->gauge_mass_dev,ctx->gauge_res_dev,ctx->cte); B2S_LAUNCHED(ctx);
   k_gauge_swl<<<b2s_blocks(ng,32),32,0,s>>>((const GaugeDev*)ctx->gauges_dev,ng,ctx->gauge_mass_dev,ctx->gauge_res_dev); B2S_LAUNCHED(ctx);
   B2S_CUDA(ctx,cudaMemcpyAsync(ctx->gauge_res_h,ctx->gauge_res_dev,sizeof(float)*4*ng,cudaMemcpyDeviceToHost,s));

@@ -35,7 +35,8 @@ struct MotionCfg { unsigned ref; double freq[3], ampl[3], phase[3], tstart, tend
 
 // One gauge of <special><gauges> (JGaugeSystem::ReadXml, JDsGaugeSystem.cpp:244-330) with the timing state of JGaugeItem
 struct GaugeCfg {
-  std::string name; int type;            // 1 velocity, 2 swl
+  std::string name; int type;            // 1 velocity, 2 swl, 3 force
+  unsigned mkbound;                      // force: target block
   double point[3], point0[3], point2[3], pointdp; float masslimit;
   double computedt, computestart, computeend, outputdt, outputstart, outputend; bool output;
   double computenext, outputnext; int id; bool headdone;
@@ -370,7 +371,13 @@ static void load_case(b2s_sim* s,const std::string& options){
           else g.masslimit=p.massfluid*(p.simulate2d? 0.4f: 0.5f);
           if(g.masslimit<=0)throw std::runtime_error("gauge swl: the masslimit is invalid");
         }
-        else throw std::runtime_error("gauge <"+c->name+"> is not supported by this build (velocity, swl)");
+        else if(c->name=="force"){
+          g.type=3;
+          const XmlNode* tg=c->child("target");
+          if(!tg || !tg->has("mkbound"))throw std::runtime_error("gauge force: <target mkbound> missing");
+          g.mkbound=unsigned(atoi(tg->attr("mkbound").c_str()));
+        }
+        else throw std::runtime_error("gauge <"+c->name+"> is not supported by this build (velocity, swl, force)");
         s->gauges.push_back(g);
       }
     }
@@ -629,6 +636,15 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
     if(g.computedt<0)g.computedt=s->timepart;  if(g.computeend<0)g.computeend=s->timemax;     // JGaugeSystem::ResetCfgDefault
     if(g.outputdt<0)g.outputdt=s->timepart;    if(g.outputend<0)g.outputend=s->timemax;
     if(g.type==1)r=b2s_gauge_add_velocity(s->ctx,g.point,&g.id);
+    else if(g.type==3){
+      // block of the target mkbound and the code its particles carry (same numbering as the code array built above)
+      const PartBlock* blk=NULL; unsigned idx[4]={0,0,0,0}, bidx=0;
+      for(auto& b:s->blocks){ if(b.type!=3 && b.mktype==g.mkbound && !blk){ blk=&b; bidx=idx[b.type]; } idx[b.type]++; }
+      if(!blk)throw std::runtime_error("gauge force '"+g.name+"': mkbound is unknown");
+      if(blk->type!=0 && blk->type!=1)throw std::runtime_error("gauge force '"+g.name+"': only fixed or moving particles are allowed");
+      const uint32_t tcode[4]={0x0000,0x0800,0x1000,0x1800};
+      r=b2s_gauge_add_force(s->ctx,blk->begin,blk->count,tcode[blk->type]|bidx,&g.id);
+    }
     else r=b2s_gauge_add_swl(s->ctx,g.point0,g.point2,g.pointdp,g.masslimit,&g.id);
     if(r)throw std::runtime_error(std::string("gauge '")+g.name+"' failed: "+b2s_last_error(s->ctx));
   }
@@ -815,15 +831,17 @@ static void gauges_record(b2s_sim* s,double t){
     float res[3]={0,0,0};
     if(b2s_gauge_result(s->ctx,g.id,res))throw std::runtime_error("gauge result not available");
     if(!(g.output && t>=g.outputnext && g.outputstart<=t && t<=g.outputend) || s->dirout.empty())continue;
-    const std::string fn=s->dirout+(g.type==1? "GaugesVel_": "GaugesSWL_")+g.name+".csv";
+    const std::string fn=s->dirout+(g.type==1? "GaugesVel_": (g.type==3? "GaugesForce_": "GaugesSWL_"))+g.name+".csv";
     FILE* f=fopen(fn.c_str(),g.headdone? "a": "w");
     if(!f)throw std::runtime_error("cannot write "+fn);
     if(!g.headdone){
       fputs(g.type==1? "time [s];velx [m/s];vely [m/s];velz [m/s];posx [m];posy [m];posz [m]\n"
+            : g.type==3? "time [s];force [N];forcex [N];forcey [N];forcez [N]\n"
                      : "time [s];swlx [m];swly [m];swlz [m];pos0x [m];pos0y [m];pos0z [m];pos2x [m];pos2y [m];pos2z [m]\n",f);
       g.headdone=true;
     }
     if(g.type==1)fprintf(f,"%f;%g;%g;%g;%g;%g;%g\n",t,res[0],res[1],res[2],float(g.point[0]),float(g.point[1]),float(g.point[2]));
+    else if(g.type==3)fprintf(f,"%f;%g;%g;%g;%g\n",t,sqrtf(res[0]*res[0]+res[1]*res[1]+res[2]*res[2]),res[0],res[1],res[2]);
     else fprintf(f,"%f;%g;%g;%g;%g;%g;%g;%g;%g;%g\n",t,res[0],res[1],res[2],float(g.point0[0]),float(g.point0[1]),float(g.point0[2]),float(g.point2[0]),float(g.point2[1]),float(g.point2[2]));
     fclose(f);
     if(g.outputdt){ const unsigned nt=unsigned(t/g.outputdt); g.outputnext=g.outputdt*nt; if(g.outputnext<=t)g.outputnext=g.outputdt*(nt+1); }

@@ -229,6 +229,10 @@ int b2s_get_floatings(b2s_ctx* ctx, uint32_t ftcount, b2s_floating* fts);
  * velocity (vx,vy,vz) or the surface point (x,y,z).  b2s_gauges_compute evaluates them now (initial measurement at t=0). */
 int b2s_gauge_add_velocity(b2s_ctx* ctx, const double point[3], int* id);
 int b2s_gauge_add_swl(b2s_ctx* ctx, const double point0[3], const double point2[3], double pointdp, float masslimit, int* id);
+/* Force gauge (JGaugeForce, JDsGaugeItem.cpp:1847-1908; JGaugeSystem::AddGaugeForce, JDsGaugeSystem.cpp:472-495): pressure force
+ * of the fluid on the fixed or moving boundary block with ids [idbegin,idbegin+count) whose particles carry `typevalue` in the
+ * type+value bits of their code; result = (fx,fy,fz) in N. */
+int b2s_gauge_add_force(b2s_ctx* ctx, uint32_t idbegin, uint32_t count, uint32_t typevalue, int* id);
 int b2s_gauges_compute(b2s_ctx* ctx);
 int b2s_gauge_result(b2s_ctx* ctx, int id, float out[3]);
 

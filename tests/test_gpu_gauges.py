@@ -44,3 +44,28 @@ def test_gauges_match_reference(tmp_path, built_lib):
             assert err < 1e-5, (name, err)
         rep[name] = {"rows": int(o.shape[0]), "max_abs_err": err}
     print("\n[gauges] " + json.dumps(rep))
+
+
+REF_FORCE = os.path.join(H.GOLDEN, "gauges_force_ref")
+
+
+def test_force_gauges_match_reference(tmp_path, built_lib):
+    """Force gauges (JGaugeForce) on the fixed tank and on the moving piston against the CSV files the reference wrote
+    (tools/make_gauges_force_fixture.py): same rows and times, force within 2e-3 of max|F| (pressure sums inherit the Tait EOS
+    amplification of one ulp of rho)."""
+    fx = json.load(open(os.path.join(REF_FORCE, "fixture_gauges.json")))
+    H.write_case(tmp_path, **fx["spec"])
+    out = tmp_path / "out"
+    r = subprocess.run([CLI, str(tmp_path / "Case"), str(out)] + fx["options"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "Finished execution (code=0)" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    rep = {}
+    for name in ("GaugesForce_Tank.csv", "GaugesForce_Piston.csv"):
+        ho, o = _csv(str(out / name))
+        hg, g = _csv(os.path.join(REF_FORCE, name))
+        assert ho == hg, (name, ho, hg)
+        assert o.shape == g.shape, (name, o.shape, g.shape)
+        assert np.all(np.abs(o[:, 0] - g[:, 0]) <= 2e-5 * np.maximum(g[:, 0], 1e-3) + 1e-6), name
+        err = float(np.max(np.abs(o[:, 1:] - g[:, 1:]))) / float(np.max(np.abs(g[:, 1:])))
+        assert err < 2e-3, (name, err)
+        rep[name] = {"rows": int(o.shape[0]), "rel_err": err}
+    print("\n[force gauges] " + json.dumps(rep))
