@@ -55,3 +55,48 @@ def test_longrun_observables_match_reference(tmp_path, built_lib):
           f"{ref[-1]['ft_center'][0] - ref[0]['ft_center'][0]:.3f} m; {r.stdout.strip().splitlines()[-3]}")
     assert worst["front"] < 0.25 and worst["height"] < 0.25 and worst["ke"] < 0.01 and worst["vmax"] < 0.10 and worst["ft"] < 0.25
     assert worst["press"] < 0.05
+
+
+def _csv(path):
+    lines = open(path).read().strip().splitlines()
+    return lines[0], np.array([[float(x) for x in ln.split(";")] for ln in lines[1:]])
+
+
+def test_wavetank_longrun_matches_reference(tmp_path, built_lib):
+    """1 s wave tank (3450 steps, 26k particles): piston wavemaker + floating box + standard shifting (NoFixed, threshold 1.5)
+    + damping zone + SWL / velocity / force gauges, i.e. the rows next to the hot path working together, against the files the
+    reference CPU build wrote for the same case (tests/golden/wavetank_ref/, tools/make_wavetank_fixture.py; 197 s on 8 threads).
+    Stated tolerances over the whole run: free surface 0.25 dp at both gauges, velocity 5 % and piston force 5 % of their maxima,
+    floating-body centre 0.25 dp per axis and its velocity 5 % of the maximum, at every one of the reference's output times.
+    Measured on B200 (10 s for the run): surface 0.0012 / 0.0003 dp, velocity 0.17 %, piston force 0.01 %, body centre 0.0002 dp,
+    body velocity 0.006 %."""
+    from dualsphysics_b200 import bi4
+    ref = os.path.join(H.GOLDEN, "wavetank_ref")
+    fx = json.load(open(os.path.join(ref, "fixture_wavetank.json")))
+    H.write_case(tmp_path, **fx["spec"])
+    out = tmp_path / "out"
+    r = subprocess.run([CLI, str(tmp_path / "Case"), str(out)] + fx["options"], capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0 and "Finished execution (code=0)" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    dp = fx["spec"]["dp"]
+    rep = {}
+    for name in ("GaugesSWL_Near.csv", "GaugesSWL_Far.csv", "GaugesVel_Mid.csv", "GaugesForce_Piston.csv"):
+        ho, o = _csv(str(out / name))
+        hg, g = _csv(os.path.join(ref, name))
+        assert ho == hg and o.shape == g.shape, (name, o.shape, g.shape)
+        assert np.max(np.abs(o[:, 0] - g[:, 0])) < 1e-3, name     # output times: the dt histories drift by ~3e-4 s over the 1 s run
+        if "SWL" in name:
+            err = float(np.max(np.abs(o[:, 3] - g[:, 3]))) / dp
+            assert err < 0.25, (name, err)
+        else:
+            err = float(np.max(np.abs(o[:, 1:4] - g[:, 1:4]))) / float(np.max(np.abs(g[:, 1:4])))
+            assert err < 0.05, (name, err)
+        rep[name] = err
+    fo, fr = bi4.load_list(str(out / "data" / "PartFloatInfo.ibi4")), bi4.load_list(os.path.join(ref, "PartFloatInfo.ibi4"))
+    assert len(fo) == len(fr)
+    vmax = max(float(np.max(np.abs(b.array("fvel")))) for b in fr[1:])
+    ec = max(float(np.max(np.abs(a.array("center") - b.array("center")))) for a, b in zip(fo[1:], fr[1:])) / dp
+    ev = max(float(np.max(np.abs(a.array("fvel") - b.array("fvel")))) for a, b in zip(fo[1:], fr[1:])) / vmax
+    assert all(a.get("Step") == b.get("Step") for a, b in zip(fo[1:], fr[1:]))
+    assert ec < 0.25 and ev < 0.05, (ec, ev)
+    rep["float_centre_dp"], rep["float_vel_rel"] = ec, ev
+    print("\n[wavetank] " + json.dumps(rep))
