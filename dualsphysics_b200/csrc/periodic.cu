@@ -33,10 +33,15 @@ __global__ void __launch_bounds__(P_BS) k_peri_ignore(const DivState* __restrict
 }
 __global__ void k_peri_begin(DivState* ds){ ds->peri_np0=ds->np; ds->peri_npb0=ds->npb; ds->peri_nbper=0; ds->peri_nfper=0; }
 
+// Source range of a pass.  cblock 1 = the particles present at entry, selected by TYPE (boundary / fluid+floating) rather than by
+// the index ranges [0,Npb) / [Npb,Np) of the reference: identical for a single domain, and still right in slab mode where halo
+// ghosts and migrants of both types sit behind the owned particles.  cblock 0 = the duplicates of this type made so far
+// (contiguous: all boundary duplicates are created before the first fluid one).
 __device__ __forceinline__ void peri_range(const DivState* ds,int ctype,int cblock,uint32_t& pini,uint32_t& num){
-  if(cblock){ pini=(ctype? ds->peri_npb0: 0u); num=(ctype? ds->peri_np0-ds->peri_npb0: ds->peri_npb0); }
+  if(cblock){ pini=0u; num=ds->peri_np0; }
   else{ num=(ctype? ds->peri_nfper: ds->peri_nbper); pini=ds->np-num; }
 }
+__device__ __forceinline__ bool peri_type_ok(typecode c,int ctype){ return (B2S_CODE_TYPE(c)<B2S_CODE_TYPE_FLOATING)==(ctype==0); }
 
 // PeriodicMakeList: bit0 = copy at +inc lies inside the map, bit1 = copy at -inc does.
 __global__ void __launch_bounds__(P_BS) k_peri_flag(const DivState* __restrict__ ds,int ctype,int cblock,double ix,double iy,double iz,
@@ -51,7 +56,8 @@ __global__ void __launch_bounds__(P_BS) k_peri_flag(const DivState* __restrict__
   uint32_t f=0;
   if(i<num){
     const uint32_t p=pini+i;
-    if(B2S_CODE_SPECIAL(code[p])<=B2S_CODE_PERIODIC){
+    const typecode cod=code[p];
+    if(B2S_CODE_SPECIAL(cod)<=B2S_CODE_PERIODIC && peri_type_ok(cod,ctype)){
       const double2 xy=posxy[p]; const double z=posz[p];
       double x2=xy.x+ix, y2=xy.y+iy, z2=z+iz;
       if(mnx<=x2 && mny<=y2 && mnz<=z2 && x2<mxx && y2<mxy && z2<mxz)f|=1;
@@ -125,7 +131,9 @@ int b2s_periodic_impl(b2s_ctx* ctx){
     B2S_CUDA(ctx,cudaMalloc((void**)&ctx->slab_counts,ctx->slab_counts_len*4));
     B2S_CUDA(ctx,cudaMalloc((void**)&ctx->slab_flags,size_t(ctx->cap)*2));
   }
-  k_peri_ignore<<<b2s_blocks(np0,P_BS),P_BS,0,s>>>(ctx->div,ctx->cur.code); B2S_LAUNCHED(ctx);
+  // slab mode: the CODE_PERIODIC particles present now are the halo ghosts just received (the old duplicates were marked by the
+  // integrators, or by b2s_slab_config / b2s_slab_drop_ghosts): they must survive, and they are duplicated like owned particles
+  if(!ctx->slab_on){ k_peri_ignore<<<b2s_blocks(np0,P_BS),P_BS,0,s>>>(ctx->div,ctx->cur.code); B2S_LAUNCHED(ctx); }
   k_peri_begin<<<1,1,0,s>>>(ctx->div); B2S_LAUNCHED(ctx);
   PeriArrays a;
   a.idp=ctx->cur.idp; a.code=ctx->cur.code; a.dcell=ctx->cur.dcell; a.posxy=ctx->cur.posxy; a.posz=ctx->cur.posz; a.velrho=ctx->cur.velrho;
@@ -136,7 +144,7 @@ int b2s_periodic_impl(b2s_ctx* ctx){
   for(int ctype=0;ctype<2;ctype++)for(int ax=0;ax<3;ax++)if((c.periactive>>ax)&1){
     const double* inc=c.perinc[ax];
     for(int cblock=0;cblock<2;cblock++){
-      const uint32_t num=(cblock? (ctype? np0-npb0: npb0): nper[ctype]);
+      const uint32_t num=(cblock? np0: nper[ctype]);
       if(!num)continue;
       const uint32_t nb=b2s_blocks(num,P_BS);
       k_peri_flag<<<nb,P_BS,0,s>>>(ctx->div,ctype,cblock,inc[0],inc[1],inc[2],q.map_posmin[0],q.map_posmin[1],q.map_posmin[2],

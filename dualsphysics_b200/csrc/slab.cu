@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(S_BS) k_slab_select(const DivState* __restrict
   const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
   if(p>=ds->np)return;
   const typecode c=code[p];
+  if(B2S_CODE_SPECIAL(c)==B2S_CODE_PERIODIC){ code[p]=typecode(B2S_CODE_SETNORMAL(c)|B2S_CODE_OUTIGNORE); return; }   // periodic duplicates of the upload's divide
   if(B2S_CODE_SPECIAL(c)!=B2S_CODE_NORMAL)return;
   const uint32_t cx=B2S_DCEL_CELLX(dcc,dcell[p]);
   if(cx<cxa || cx>=cxb)code[p]=typecode(B2S_CODE_SETNORMAL(c)|B2S_CODE_OUTIGNORE);
@@ -147,7 +148,7 @@ static SlabArrays slab_arrays(b2s_ctx* ctx){
 extern "C" int b2s_slab_config(b2s_ctx* ctx, int rank, int nranks, uint32_t cx_begin, uint32_t cx_end){
   if(!ctx || nranks<1 || rank<0 || rank>=nranks || cx_begin>=cx_end || cx_end>ctx->prm.domcells[0])return B2S_ERR_ARG;
   if(nranks>1 && cx_end-cx_begin<slab_halo_planes(ctx))return b2s_fail(ctx,B2S_ERR_ARG,"slab [%u,%u) is thinner than the halo (%u cell planes)",cx_begin,cx_end,slab_halo_planes(ctx));
-  if(ctx->cte.periactive)return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"periodic boundaries with slab decomposition are not supported");
+  if(ctx->cte.periactive&1)return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"periodic boundaries along x (the slab axis) are not supported with slab decomposition");
   B2S_CUDA(ctx,cudaSetDevice(ctx->device));
   ctx->slab_on=true; ctx->slab_rank=rank; ctx->slab_nranks=nranks; ctx->slab_cxa=cx_begin; ctx->slab_cxb=cx_end;
   const size_t nb=b2s_blocks(ctx->cap,S_BS);

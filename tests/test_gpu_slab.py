@@ -208,3 +208,29 @@ def test_slab_mdbc_lamsps(nranks, slipmode, tmp_path, built_lib):
     print(f"\n[slab mdbc(slip {slipmode})+lamsps x{nranks}] cuts={ss.cuts} owned={ss.owned_counts()} pos_err={epos:.3e} velrho_err={evr:.3e}")
     assert epos < 1e-7 and evr < 1e-5      # the mDBC tolerance of the golden-fixture tests (ill-conditioned 4x4 inverse)
     ss.close(); ref.close()
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_slab_periodic_y(nranks, tmp_path, built_lib):
+    """Periodic boundaries across the slab axis' normal (Y periodic, slabs along x): every rank duplicates its owned particles AND
+    the halo ghosts it received next to the periodic faces (corner coverage), so the slabs reproduce the single-context run.
+    The fluid moves at 3 m/s along y, so particles wrap around during the 30 steps."""
+    H.write_case(tmp_path, dp=0.03, open_axes="y", fluid_vel=(0.0, 3.0, 0.0), params={"YPeriodicIncZ": 0})
+    case = str(tmp_path / "Case")
+    ref = dsb.Simulation(case)
+    ss = slab.SlabSimulation(case, nranks=nranks, dist=None)
+    for s in range(30):
+        dt_ref = ref.ctx.compute_step()
+        dt = ss.step()
+        assert abs(dt - dt_ref) <= 2e-5 * dt_ref, (s, dt, dt_ref)
+    ids, pos, vr = ss.gather_byid()
+    own = (ref.ctx.array("code") & 0xe000) == 0          # without the periodic duplicates
+    rid = ref.ctx.array("idp")[own]; o = np.argsort(rid, kind="stable")
+    rpos, rvr = ref.ctx.array("pos")[own][o], ref.ctx.array("velrho")[own][o]
+    assert np.array_equal(ids, rid[o]), "particle set differs from the single-context run"
+    epos, evr = float(np.max(np.abs(pos - rpos))), H.rel_err(vr, rvr)
+    y0 = ref.params.maprealposmin[1]; ly = ref.params.maprealposmax[1] - y0
+    assert np.all((rpos[:, 1] >= y0) & (rpos[:, 1] < y0 + ly)), "particles left the periodic range"
+    print(f"\n[slab periodic-y x{nranks}] cuts={ss.cuts} pos_err={epos:.3e} velrho_err={evr:.3e}")
+    assert epos < 1e-7 and evr < 2e-6
+    ss.close(); ref.close()
