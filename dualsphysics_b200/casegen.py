@@ -122,6 +122,9 @@ def _normals(spec: DamBreakSpec, ijk: np.ndarray, nx: int, ny: int, nz: int) -> 
     p = ijk.astype(np.float64) * dp
     lo = np.array([0.5 * dp, 0.5 * dp, 0.5 * dp])
     hi = np.array([(nx - 0.5) * dp, (ny - 0.5) * dp, np.inf])
+    for k, ax in enumerate("xy"):           # no wall across an open (periodic) axis
+        if ax in spec.open_axes:
+            lo[k], hi[k] = -np.inf, np.inf
     q = np.minimum(np.maximum(p, lo), hi)
     return (q - p).astype(np.float32)
 

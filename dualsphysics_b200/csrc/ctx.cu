@@ -64,7 +64,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   int ndev=0;
   if(cudaGetDeviceCount(&ndev)!=cudaSuccess || ndev<=0)return B2S_ERR_NODEVICE;
   if(device>=ndev)return B2S_ERR_ARG;
-  if(p->periactive && (p->casenfloat || p->tboundary==B2S_BC_MDBC))return B2S_ERR_UNSUPPORTED;   // periodic + floating bodies / mDBC: not built
+  if(p->periactive && p->casenfloat)return B2S_ERR_UNSUPPORTED;   // periodic + floating bodies: not built
   b2s_ctx* ctx=new b2s_ctx();
   ctx->prm=*p;
   if(ctx->prm.domcellcode==0){ int r=b2s_config_finalize(&ctx->prm); if(r){ delete ctx; return r; } }

@@ -573,7 +573,7 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   }
   if(p.periactive){
     if(p.casenfloat)throw std::runtime_error("periodic boundaries with floating bodies are not supported by this build");
-    if(p.tboundary==B2S_BC_MDBC)throw std::runtime_error("periodic boundaries with mDBC are not supported by this build");
+    if(p.tboundary==B2S_BC_MDBC && slab_nranks>1)throw std::runtime_error("periodic boundaries with mDBC and slab decomposition are not supported by this build");
     if(slab_nranks>1 && (p.periactive&1))throw std::runtime_error("periodic boundaries along x (the slab axis) with slab decomposition are not supported by this build");
     // duplicates: the particles within KernelSize of a periodic face, both faces, plus corner copies -> generous slack
     double frac=0;

@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(M_BS) k_mdbc_vel0(const DivState* __restrict__
   float rhofinal=FLT_MAX;
   //-Ghost node position (double, like the reference) and its cell.
   const double2 xy=posxy[p1];
-  const double gx=xy.x+double(nor.x), gy=xy.y+double(nor.y), gz=posz[p1]+double(nor.z);
+  double gx=xy.x+double(nor.x), gy=xy.y+double(nor.y), gz=posz[p1]+double(nor.z);
+  if(c.periactive){ uint32_t gcell; b2s_pos_to_cell(c,gx,gy,gz,gcell); }   // UpdatePeriodicPos of the ghost node (JSphCpu_mdbc.cpp:50,267)
   const int gcx=int((gx-c.domposmin[0])/c.scell_d), gcy=int((gy-c.domposmin[1])/c.scell_d), gcz=int((gz-c.domposmin[2])/c.scell_d);
   const int cx=gcx-int(ds->cellmin[0]), cy=gcy-int(ds->cellmin[1]), cz=gcz-int(ds->cellmin[2]);
   const int d=c.scelldiv, ncx=int(ds->ncx), ncy=int(ds->ncy), ncz=int(ds->ncz), nsheet=int(ds->nsheet);
@@ -127,7 +128,8 @@ __global__ void __launch_bounds__(M_BS) k_mdbc2(const DivState* __restrict__ ds,
   const float4 nor=boundnor[p1];
   if(nor.x==0.f && nor.y==0.f && nor.z==0.f)return;
   const double2 xy=posxy[p1];
-  const double gx=xy.x+double(nor.x), gy=xy.y+double(nor.y), gz=posz[p1]+double(nor.z);
+  double gx=xy.x+double(nor.x), gy=xy.y+double(nor.y), gz=posz[p1]+double(nor.z);
+  if(c.periactive){ uint32_t gcell; b2s_pos_to_cell(c,gx,gy,gz,gcell); }   // UpdatePeriodicPos of the ghost node (JSphCpu_mdbc.cpp:50,267)
   const int gcx=int((gx-c.domposmin[0])/c.scell_d), gcy=int((gy-c.domposmin[1])/c.scell_d), gcz=int((gz-c.domposmin[2])/c.scell_d);
   const int cx=gcx-int(ds->cellmin[0]), cy=gcy-int(ds->cellmin[1]), cz=gcz-int(ds->cellmin[2]);
   const int d=c.scelldiv, ncx=int(ds->ncx), ncy=int(ds->ncy), ncz=int(ds->ncz), nsheet=int(ds->nsheet);

@@ -149,6 +149,7 @@ extern "C" int b2s_slab_config(b2s_ctx* ctx, int rank, int nranks, uint32_t cx_b
   if(!ctx || nranks<1 || rank<0 || rank>=nranks || cx_begin>=cx_end || cx_end>ctx->prm.domcells[0])return B2S_ERR_ARG;
   if(nranks>1 && cx_end-cx_begin<slab_halo_planes(ctx))return b2s_fail(ctx,B2S_ERR_ARG,"slab [%u,%u) is thinner than the halo (%u cell planes)",cx_begin,cx_end,slab_halo_planes(ctx));
   if(ctx->cte.periactive&1)return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"periodic boundaries along x (the slab axis) are not supported with slab decomposition");
+  if(ctx->cte.periactive && ctx->prm.tboundary==B2S_BC_MDBC && nranks>1)return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"periodic boundaries with mDBC are not supported with slab decomposition");
   B2S_CUDA(ctx,cudaSetDevice(ctx->device));
   ctx->slab_on=true; ctx->slab_rank=rank; ctx->slab_nranks=nranks; ctx->slab_cxa=cx_begin; ctx->slab_cxb=cx_end;
   const size_t nb=b2s_blocks(ctx->cap,S_BS);
