@@ -575,9 +575,10 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
     if(p.casenfloat)throw std::runtime_error("periodic boundaries with floating bodies are not supported by this build");
     if(p.tboundary==B2S_BC_MDBC && slab_nranks>1)throw std::runtime_error("periodic boundaries with mDBC and slab decomposition are not supported by this build");
     if(slab_nranks>1 && (p.periactive&1))throw std::runtime_error("periodic boundaries along x (the slab axis) with slab decomposition are not supported by this build");
-    // duplicates: the particles within KernelSize of a periodic face, both faces, plus corner copies -> generous slack
+    // duplicates: the particles within KernelSize of a periodic face, both faces (2*ks/size of the particles per axis), and
+    // during a divide the previous set is still in the arrays next to the new one (x2), plus corner copies -> 5*ks/size per axis
     double frac=0;
-    for(int k=0;k<3;k++)if((p.periactive>>k)&1)frac+=2.5*double(p.kernelsize)/std::max(p.maprealsize[k],double(p.kernelsize));
+    for(int k=0;k<3;k++)if((p.periactive>>k)&1)frac+=5.0*double(p.kernelsize)/std::max(p.maprealsize[k],double(p.kernelsize));
     extra_capacity+=unsigned(std::min(3.0,frac)*npsel)+4096u;
   }
   r=b2s_create(&p,device,npsel+extra_capacity,&s->ctx);
