@@ -13,7 +13,7 @@
 #include <float.h>
 
 #define G_BS 128
-enum { GAUGE_VEL=1, GAUGE_SWL=2, GAUGE_FORCE=3 };
+enum { GAUGE_VEL=1, GAUGE_SWL=2, GAUGE_FORCE=3, GAUGE_MAXZ=4 };
 struct GaugeDev { int type; uint32_t np, first; float masslimit; double p0[3], dir[3];
   uint32_t fcode, fidbegin, fcount, foff; };   // force gauge: type+value bits of the block, its id range, offset in the partace buffer
 
@@ -146,6 +146,48 @@ __global__ void __launch_bounds__(256) k_gauge_force_sum(GaugeDev gd, int cg, co
   if(threadIdx.x<3)res[cg*4+threadIdx.x]=float(sh[threadIdx.x][0])*massbound;
 }
 
+// ---- maxz gauge: JGaugeMaxZ::CalculeCpu (JDsGaugeItem.cpp:1023-1091; GPU JDsGauge_ker.cu:312-420) ------------------------
+// Highest fluid particle within the horizontal distance DistLimit of the vertical line point0 .. point0+Height.  The reference
+// walks the cell slabs from the top and stops at the first slab that holds such a particle; the maximum over all slabs of the
+// window is the same number.  One block per gauge: threads stride over the (y,z) cell rows, then a block maximum.
+// GaugeDev use: p0 = point0, dir[0] = Height, masslimit = DistLimit.
+__global__ void __launch_bounds__(G_BS) k_gauge_maxz(GaugeDev gd, int cg, const DivState* ds, const uint32_t* __restrict__ begt, const double2* __restrict__ posxy,
+  const double* __restrict__ posz, const typecode* __restrict__ code, float* res, const __grid_constant__ DevCte c)
+{
+  __shared__ float sh[G_BS];
+  const float distlimit=gd.masslimit, maxdist2=distlimit*distlimit;
+  const int cx=int((gd.p0[0]-c.domposmin[0])/c.scell_d)-int(ds->cellmin[0]);
+  const int cy=int((gd.p0[1]-c.domposmin[1])/c.scell_d)-int(ds->cellmin[1]);
+  const int cz=int((gd.p0[2]-c.domposmin[2])/c.scell_d)-int(ds->cellmin[2]);
+  const int cz2=int((gd.p0[2]+gd.dir[0]-c.domposmin[2])/c.scell_d)-int(ds->cellmin[2]);
+  const int ncel=int(ceil(double(distlimit)/c.scell_d));   // Scell is the float cell size promoted to double in the reference too
+  const int ncx=int(ds->ncx), ncy=int(ds->ncy), ncz=int(ds->ncz), nsheet=int(ds->nsheet);
+  const int xini=max(cx-ncel,0), xfin=min(cx+ncel+1,ncx);
+  const int yini=max(cy-ncel,0), yfin=min(cy+ncel+1,ncy);
+  const int zini=max(cz-ncel,0), zfin=min(cz2+ncel+1,ncz);
+  float zmax=-FLT_MAX;
+  if(xini<xfin && yini<yfin && zini<zfin){
+    const uint32_t* beg=begt+ds->box_fluid;
+    const int ny=yfin-yini, nrows=ny*(zfin-zini);
+    for(int r=int(threadIdx.x);r<nrows;r+=G_BS){
+      const int y=yini+r%ny, z=zini+r/ny;
+      const uint32_t pini=beg[y*ncx+z*nsheet+xini], pfin=beg[y*ncx+z*nsheet+xfin];
+      for(uint32_t p2=pini;p2<pfin;p2++){
+        const double pz=posz[p2];
+        if(pz>double(zmax)){
+          const double2 xy=posxy[p2];
+          const float drx=float(gd.p0[0]-xy.x), dry=float(gd.p0[1]-xy.y);
+          if(drx*drx+dry*dry<=maxdist2 && B2S_CODE_ISFLUID(code[p2]))zmax=float(pz);
+        }
+      }
+    }
+  }
+  sh[threadIdx.x]=zmax;
+  __syncthreads();
+  for(int o=G_BS/2;o;o>>=1){ if(int(threadIdx.x)<o)sh[threadIdx.x]=fmaxf(sh[threadIdx.x],sh[threadIdx.x+o]); __syncthreads(); }
+  if(threadIdx.x==0){ res[cg*4]=fmaxf(sh[0],float(c.domposmin[2])); res[cg*4+1]=0.f; res[cg*4+2]=0.f; res[cg*4+3]=0.f; }
+}
+
 static int gauges_upload(b2s_ctx* ctx, const std::vector<GaugeDev>& h){
   cudaFree(ctx->gauges_dev); cudaFree(ctx->gauge_res_dev); cudaFree(ctx->gauge_mass_dev); if(ctx->gauge_res_h)cudaFreeHost(ctx->gauge_res_h);
   ctx->gauges_dev=NULL; ctx->gauge_res_dev=NULL; ctx->gauge_mass_dev=NULL; ctx->gauge_res_h=NULL;
@@ -198,6 +240,19 @@ extern "C" int b2s_gauge_add_force(b2s_ctx* ctx, uint32_t idbegin, uint32_t coun
   if(id)*id=int(h.size())-1;
   return gauges_upload(ctx,h);
 }
+// MaxZ gauge (JGaugeSystem::AddGaugeMaxZ): result[0] = zmax.
+extern "C" int b2s_gauge_add_maxz(b2s_ctx* ctx, const double point0[3], double height, float distlimit, int* id){
+  if(!ctx || !point0 || !(distlimit>0))return B2S_ERR_ARG;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  std::vector<GaugeDev> h=host_list(ctx);
+  GaugeDev g; memset(&g,0,sizeof(g)); g.type=GAUGE_MAXZ; g.np=0; g.first=ctx->gauge_points; g.masslimit=distlimit;
+  for(int k=0;k<3;k++)g.p0[k]=point0[k];
+  g.dir[0]=height;
+  h.push_back(g); ctx->gauge_types.push_back(GAUGE_MAXZ);
+  host_store(ctx,h);
+  if(id)*id=int(h.size())-1;
+  return gauges_upload(ctx,h);
+}
 extern "C" int b2s_gauge_add_swl(b2s_ctx* ctx, const double point0[3], const double point2[3], double pointdp, float masslimit, int* id){
   if(!ctx || !point0 || !point2 || pointdp<=0 || masslimit<=0)return B2S_ERR_ARG;
   B2S_CUDA(ctx,cudaSetDevice(ctx->device));
@@ -221,6 +276,12 @@ int b2s_gauges_run(b2s_ctx* ctx, int){
   const uint32_t ng=uint32_t(ctx->gauge_types.size());
   if(!ng)return B2S_OK;
   cudaStream_t s=ctx->stream;
+  {
+    const std::vector<GaugeDev> h=host_list(ctx);
+    for(uint32_t cg=0;cg<ng;cg++)if(h[cg].type==GAUGE_MAXZ){
+      k_gauge_maxz<<<1,G_BS,0,s>>>(h[cg],int(cg),ctx->div,(const uint32_t*)ctx->begincell,ctx->cur.posxy,ctx->cur.posz,ctx->cur.code,ctx->gauge_res_dev,ctx->cte); B2S_LAUNCHED(ctx);
+    }
+  }
   if(ctx->gauge_force_n){
     B2S_CUDA(ctx,cudaMemsetAsync(ctx->gauge_force_dev,0,size_t(ctx->gauge_force_n)*12,s));
     const std::vector<GaugeDev> h=host_list(ctx);

@@ -35,7 +35,8 @@ struct MotionCfg { unsigned ref; double freq[3], ampl[3], phase[3], tstart, tend
 
 // One gauge of <special><gauges> (JGaugeSystem::ReadXml, JDsGaugeSystem.cpp:244-330) with the timing state of JGaugeItem
 struct GaugeCfg {
-  std::string name; int type;            // 1 velocity, 2 swl, 3 force
+  std::string name; int type;            // 1 velocity, 2 swl, 3 force, 4 maxz
+  double height; float distlimit;        // maxz
   unsigned mkbound;                      // force: target block
   double point[3], point0[3], point2[3], pointdp; float masslimit;
   double computedt, computestart, computeend, outputdt, outputstart, outputend; bool output;
@@ -377,7 +378,20 @@ static void load_case(b2s_sim* s,const std::string& options){
           if(!tg || !tg->has("mkbound"))throw std::runtime_error("gauge force: <target mkbound> missing");
           g.mkbound=unsigned(atoi(tg->attr("mkbound").c_str()));
         }
-        else throw std::runtime_error("gauge <"+c->name+"> is not supported by this build (velocity, swl, force)");
+        else if(c->name=="maxz"){
+          g.type=4;
+          if(!read_xyz(c->child("point0"),g.point0))throw std::runtime_error("gauge maxz: <point0> missing");
+          const XmlNode* hh=c->child("height");
+          if(!hh || !hh->has("value"))throw std::runtime_error("gauge maxz: <height value> missing");
+          g.height=double(float(atof(hh->attr("value").c_str())));
+          const XmlNode* dl=c->child("distlimit");
+          g.distlimit=0;
+          if(dl && dl->has("value"))g.distlimit=float(atof(dl->attr("value").c_str()));
+          else if(dl && dl->has("coefdp"))g.distlimit=float(p.dp*double(float(atof(dl->attr("coefdp").c_str()))));
+          else if(dl && dl->has("coefh"))g.distlimit=float(double(p.kernelh)*double(float(atof(dl->attr("coefh").c_str()))));
+          if(g.distlimit<=0)throw std::runtime_error("gauge maxz: the distlimit is invalid");
+        }
+        else throw std::runtime_error("gauge <"+c->name+"> is not supported by this build (velocity, swl, maxz, force)");
         s->gauges.push_back(g);
       }
     }
@@ -637,6 +651,7 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
     if(g.computedt<0)g.computedt=s->timepart;  if(g.computeend<0)g.computeend=s->timemax;     // JGaugeSystem::ResetCfgDefault
     if(g.outputdt<0)g.outputdt=s->timepart;    if(g.outputend<0)g.outputend=s->timemax;
     if(g.type==1)r=b2s_gauge_add_velocity(s->ctx,g.point,&g.id);
+    else if(g.type==4)r=b2s_gauge_add_maxz(s->ctx,g.point0,g.height,g.distlimit,&g.id);
     else if(g.type==3){
       // block of the target mkbound and the code its particles carry (same numbering as the code array built above)
       const PartBlock* blk=NULL; unsigned idx[4]={0,0,0,0}, bidx=0;
@@ -832,16 +847,18 @@ static void gauges_record(b2s_sim* s,double t){
     float res[3]={0,0,0};
     if(b2s_gauge_result(s->ctx,g.id,res))throw std::runtime_error("gauge result not available");
     if(!(g.output && t>=g.outputnext && g.outputstart<=t && t<=g.outputend) || s->dirout.empty())continue;
-    const std::string fn=s->dirout+(g.type==1? "GaugesVel_": (g.type==3? "GaugesForce_": "GaugesSWL_"))+g.name+".csv";
+    const std::string fn=s->dirout+(g.type==1? "GaugesVel_": (g.type==3? "GaugesForce_": (g.type==4? "GaugesMaxZ_": "GaugesSWL_")))+g.name+".csv";
     FILE* f=fopen(fn.c_str(),g.headdone? "a": "w");
     if(!f)throw std::runtime_error("cannot write "+fn);
     if(!g.headdone){
       fputs(g.type==1? "time [s];velx [m/s];vely [m/s];velz [m/s];posx [m];posy [m];posz [m]\n"
             : g.type==3? "time [s];force [N];forcex [N];forcey [N];forcez [N]\n"
+            : g.type==4? "time [s];zmax [m];posx [m];posy [m];posz [m]\n"
                      : "time [s];swlx [m];swly [m];swlz [m];pos0x [m];pos0y [m];pos0z [m];pos2x [m];pos2y [m];pos2z [m]\n",f);
       g.headdone=true;
     }
     if(g.type==1)fprintf(f,"%f;%g;%g;%g;%g;%g;%g\n",t,res[0],res[1],res[2],float(g.point[0]),float(g.point[1]),float(g.point[2]));
+    else if(g.type==4)fprintf(f,"%f;%g;%g;%g;%g\n",t,res[0],float(g.point0[0]),float(g.point0[1]),float(g.point0[2]));
     else if(g.type==3)fprintf(f,"%f;%g;%g;%g;%g\n",t,sqrtf(res[0]*res[0]+res[1]*res[1]+res[2]*res[2]),res[0],res[1],res[2]);
     else fprintf(f,"%f;%g;%g;%g;%g;%g;%g;%g;%g;%g\n",t,res[0],res[1],res[2],float(g.point0[0]),float(g.point0[1]),float(g.point0[2]),float(g.point2[0]),float(g.point2[1]),float(g.point2[2]));
     fclose(f);

@@ -90,7 +90,7 @@ ABI_SYMBOLS = [
     "b2s_config_finalize", "b2s_error_string", "b2s_create", "b2s_destroy", "b2s_last_error", "b2s_get_params",
     "b2s_upload_particles", "b2s_download_particles", "b2s_download_particles_byid", "b2s_get_array",
     "b2s_get_info", "b2s_set_time", "b2s_celldiv", "b2s_interaction", "b2s_compute_verlet", "b2s_compute_symplectic_pre",
-    "b2s_compute_symplectic_corr", "b2s_compute_step", "b2s_run_steps", "b2s_add_motion_rectsinu", "b2s_add_damping_plane", "b2s_add_damping_box", "b2s_out_enable", "b2s_out_fetch", "b2s_gauge_add_force",
+    "b2s_compute_symplectic_corr", "b2s_compute_step", "b2s_run_steps", "b2s_add_motion_rectsinu", "b2s_add_damping_plane", "b2s_add_damping_box", "b2s_out_enable", "b2s_out_fetch", "b2s_gauge_add_force", "b2s_gauge_add_maxz",
     "b2s_move_linear", "b2s_set_floatings", "b2s_get_floatings", "b2s_count_pairs", "b2s_time_interaction",
     "b2s_gauge_add_velocity", "b2s_gauge_add_swl", "b2s_gauges_compute", "b2s_gauge_result",
     "b2s_launch_count", "b2s_get_stream", "b2s_set_interaction_variant", "b2s_slab_config",
@@ -157,6 +157,7 @@ def load_library():
     lib.b2s_gauge_add_velocity.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.b2s_gauge_add_swl.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_float, C.POINTER(C.c_int)]
     lib.b2s_gauge_add_force.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int)]
+    lib.b2s_gauge_add_maxz.argtypes = [vp, C.POINTER(C.c_double), C.c_double, C.c_float, C.POINTER(C.c_int)]
     lib.b2s_gauges_compute.argtypes = [vp]
     lib.b2s_gauge_result.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     lib.b2s_slab_config.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32]

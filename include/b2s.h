@@ -233,6 +233,9 @@ int b2s_gauge_add_swl(b2s_ctx* ctx, const double point0[3], const double point2[
  * of the fluid on the fixed or moving boundary block with ids [idbegin,idbegin+count) whose particles carry `typevalue` in the
  * type+value bits of their code; result = (fx,fy,fz) in N. */
 int b2s_gauge_add_force(b2s_ctx* ctx, uint32_t idbegin, uint32_t count, uint32_t typevalue, int* id);
+/* MaxZ gauge (JGaugeMaxZ, JDsGaugeItem.cpp:1023-1091): highest fluid particle within the horizontal distance distlimit of the
+ * vertical line point0 .. point0+height; result[0] = zmax (never below the domain's z minimum). */
+int b2s_gauge_add_maxz(b2s_ctx* ctx, const double point0[3], double height, float distlimit, int* id);
 int b2s_gauges_compute(b2s_ctx* ctx);
 int b2s_gauge_result(b2s_ctx* ctx, int id, float out[3]);
 

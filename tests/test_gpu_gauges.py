@@ -68,4 +68,10 @@ def test_force_gauges_match_reference(tmp_path, built_lib):
         err = float(np.max(np.abs(o[:, 1:] - g[:, 1:]))) / float(np.max(np.abs(g[:, 1:])))
         assert err < 2e-3, (name, err)
         rep[name] = {"rows": int(o.shape[0]), "rel_err": err}
+    # maxz gauge of the same run: highest fluid particle near a vertical line (1e-6 m: float z of a particle position)
+    ho, o = _csv(str(out / "GaugesMaxZ_Col.csv"))
+    hg, g = _csv(os.path.join(REF_FORCE, "GaugesMaxZ_Col.csv"))
+    assert ho == hg and o.shape == g.shape
+    assert np.array_equal(o[:, 2:], g[:, 2:]) and float(np.max(np.abs(o[:, 1] - g[:, 1]))) < 1e-6
+    rep["GaugesMaxZ_Col.csv"] = {"rows": int(o.shape[0]), "max_abs_err": float(np.max(np.abs(o[:, 1] - g[:, 1])))}
     print("\n[force gauges] " + json.dumps(rep))
