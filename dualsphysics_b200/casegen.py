@@ -37,6 +37,7 @@ class DamBreakSpec:
     piston: bool = False                    # moving plate (mkbound=1) near x=0 driven by mvrectsinu
     piston_ampl: float = 0.02
     piston_freq: float = 1.0
+    motion_xml: str = ""                    # replaces the default mvrectsinu of the piston: raw xml inside <objreal ref="0">
     floating_box: tuple | None = None       # (x0,y0,z0,sx,sy,sz) box of floating particles, relative density
     floating_rel_density: float = 0.5
     gravity: tuple = (0.0, 0.0, -9.81)
@@ -251,12 +252,15 @@ def write_case(dirpath: str, name: str, spec: DamBreakSpec) -> dict:
     if nmoving:
         x.append('    <motion>')
         x.append('      <objreal ref="0">')
-        x.append('        <begin mov="1" start="0" />')
-        x.append('        <mvrectsinu id="1" duration="1000" anglesunits="radians">')
-        x.append(f'          <freq x="{spec.piston_freq!r}" y="0" z="0" />')
-        x.append(f'          <ampl x="{spec.piston_ampl!r}" y="0" z="0" />')
-        x.append('          <phase x="0" y="0" z="0" />')
-        x.append('        </mvrectsinu>')
+        if spec.motion_xml:
+            x.append(spec.motion_xml)
+        else:
+            x.append('        <begin mov="1" start="0" />')
+            x.append('        <mvrectsinu id="1" duration="1000" anglesunits="radians">')
+            x.append(f'          <freq x="{spec.piston_freq!r}" y="0" z="0" />')
+            x.append(f'          <ampl x="{spec.piston_ampl!r}" y="0" z="0" />')
+            x.append('          <phase x="0" y="0" z="0" />')
+            x.append('        </mvrectsinu>')
         x.append('      </objreal>')
         x.append('    </motion>')
     x.append('  </execution>')

@@ -104,9 +104,11 @@ struct PartSet {
   double2* posxy; double* posz; float4* velrho;
 };
 
+// One movement of a moving block (JMotionMov*, JMotionMov.h): type = B2S_MOV_*; v1,v2,v3 by type (b2s.h b2s_motion); active in
+// [tstart,tend).  Movements of one block are kept together and in time order (b2s_motion_impl applies them in that order).
 struct Motion {
-  uint32_t idbegin, count;
-  double freq[3], ampl[3], phase[3], tstart, tend;
+  uint32_t idbegin, count; int32_t type, pad;
+  double v1[3], v2[3], v3[3], p1[3], p2[3], tstart, tend;
 };
 
 struct b2s_ctx {
@@ -150,7 +152,7 @@ struct b2s_ctx {
   // floatings
   uint32_t ftcount; std::vector<b2s_floating> fts; float* ft_massp_dev; float* ft_sums_dev; float* ft_allsums_dev; float* ft_sums_h;
   void* ft_dev; // device copy of per-floating update data
-  std::vector<Motion> motions;
+  std::vector<Motion> motions; void* motion_dev; bool motion_dirty;
   // slab decomposition (slab.cu)
   bool slab_on; int slab_rank, slab_nranks; uint32_t slab_cxa, slab_cxb; uint32_t* slab_counts; uint8_t* slab_flags; size_t slab_counts_len;
   bool defer_attr_set;   // forces_defer.cu: dynamic shared memory opt-in done

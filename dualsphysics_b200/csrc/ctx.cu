@@ -77,7 +77,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   ctx->launches=0; ctx->variant=0; ctx->pre_active=false; ctx->bound_changed=true; ctx->ftcount=0;
   ctx->verletstep=0;
   ctx->slab_on=false; ctx->slab_rank=0; ctx->slab_nranks=1; ctx->slab_cxa=0; ctx->slab_cxb=0; ctx->slab_counts=NULL; ctx->slab_flags=NULL; ctx->slab_counts_len=0;
-  ctx->defer_attr_set=false; ctx->boundmode=NULL; ctx->tangenvel=NULL; ctx->shiftpos=NULL; ctx->damp_dev=NULL; ctx->damp_dirty=false; ctx->out_dev=NULL; ctx->out_count_dev=NULL; ctx->out_cap=0;
+  ctx->defer_attr_set=false; ctx->boundmode=NULL; ctx->tangenvel=NULL; ctx->shiftpos=NULL; ctx->damp_dev=NULL; ctx->damp_dirty=false; ctx->out_dev=NULL; ctx->out_count_dev=NULL; ctx->out_cap=0; ctx->motion_dev=NULL; ctx->motion_dirty=false;
   ctx->gauges_dev=NULL; ctx->gauge_res_dev=NULL; ctx->gauge_res_h=NULL; ctx->gauge_mass_dev=NULL; ctx->gauge_points=0; ctx->gauge_force_dev=NULL; ctx->gauge_force_n=0;
   ctx->ft_massp_dev=NULL; ctx->ft_sums_dev=NULL; ctx->ft_allsums_dev=NULL; ctx->ft_sums_h=NULL; ctx->ft_dev=NULL; ctx->scratch=NULL; ctx->scratch_bytes=0;
   ctx->pospre_xy=ctx->pospre_xy_alt=NULL; ctx->pospre_z=ctx->pospre_z_alt=NULL; ctx->velrhopre=ctx->velrhopre_alt=NULL;
@@ -135,7 +135,7 @@ extern "C" int b2s_destroy(b2s_ctx* ctx){
   cudaFree(ctx->begincell); cudaFree(ctx->radix_counts); cudaFree(ctx->ridp);
   cudaFree(ctx->div); cudaFree(ctx->step);
   cudaFree(ctx->gauges_dev); cudaFree(ctx->gauge_res_dev); cudaFree(ctx->gauge_mass_dev); cudaFree(ctx->gauge_force_dev); if(ctx->gauge_res_h)cudaFreeHost(ctx->gauge_res_h);
-  cudaFree(ctx->out_dev); cudaFree(ctx->out_count_dev); cudaFree(ctx->damp_dev); cudaFree(ctx->shiftpos); cudaFree(ctx->boundmode); cudaFree(ctx->tangenvel); cudaFree(ctx->slab_counts); cudaFree(ctx->slab_flags);
+  cudaFree(ctx->motion_dev); cudaFree(ctx->out_dev); cudaFree(ctx->out_count_dev); cudaFree(ctx->damp_dev); cudaFree(ctx->shiftpos); cudaFree(ctx->boundmode); cudaFree(ctx->tangenvel); cudaFree(ctx->slab_counts); cudaFree(ctx->slab_flags);
   cudaFree(ctx->ft_massp_dev); cudaFree(ctx->ft_sums_dev); cudaFree(ctx->ft_allsums_dev); cudaFree(ctx->ft_dev); cudaFree(ctx->scratch);
   if(ctx->ft_sums_h)cudaFreeHost(ctx->ft_sums_h);
   if(ctx->div_h)cudaFreeHost(ctx->div_h);

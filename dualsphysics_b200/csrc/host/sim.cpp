@@ -31,7 +31,7 @@ using namespace b2s;
 
 struct PartBlock { int type; unsigned mktype, mk, begin, count; // type: 0 fixed,1 moving,2 floating,3 fluid
   double massbody, masspart, center[3], inertia[9], linvelini[3], angvelini[3]; int transfree[3], rotfree[3]; unsigned refmotion; };
-struct MotionCfg { unsigned ref; double freq[3], ampl[3], phase[3], tstart, tend; };
+struct MotionCfg { unsigned ref; b2s_motion m; };   // one movement of the flattened chain of a moving block (idbegin/count filled at upload)
 
 // One gauge of <special><gauges> (JGaugeSystem::ReadXml, JDsGaugeSystem.cpp:244-330) with the timing state of JGaugeItem
 struct GaugeCfg {
@@ -396,26 +396,66 @@ static void load_case(b2s_sim* s,const std::string& options){
       }
     }
   }
-  // -- motion (JMotion::ReadXml subset: objreal + mvrectsinu)
+  // -- motion (JMotion::ReadXml, JMotion.cpp:692-903): <objreal ref> with wait / mvrect / mvrectace / mvrot / mvrotace / mvrectsinu /
+  //    mvrotsinu, chained through next=; every <begin mov start [finish]> starts a chain that is flattened here into time windows
   if(const XmlNode* mo=exe->child("motion")){
     for(const XmlNode* o:mo->childs("objreal")){
       const unsigned ref=unsigned(atoi(o->attr("ref","0").c_str()));
-      std::vector<std::pair<int,double>> begins;   // (mov id, start)
-      for(const XmlNode* b:o->childs("begin"))begins.emplace_back(atoi(b->attr("mov","0").c_str()),todouble(b->attr("start","0")));
+      if(!o->childs("obj").empty() || !o->childs("objreal").empty())throw std::runtime_error("motion: nested objects are not supported by this build");
+      struct MovDef { int id,next; double duration; b2s_motion m; };
+      std::vector<MovDef> defs;
+      struct Begin { int mov; double start,finish; };
+      std::vector<Begin> begins;
       for(auto& c:o->children){
-        if(c->name=="begin"||c->name[0]=='_')continue;
-        if(c->name!="mvrectsinu")throw std::runtime_error("motion <"+c->name+"> is not supported by this build (only mvrectsinu)");
-        MotionCfg m; memset(&m,0,sizeof(m)); m.ref=ref;
-        const int id=atoi(c->attr("id","0").c_str());
-        const double duration=todouble(c->attr("duration","0"));
-        if(atoi(c->attr("next","0").c_str())!=0)throw std::runtime_error("motion chains (next=) are not supported by this build");
-        if(!read_xyz(c->child("freq"),m.freq)||!read_xyz(c->child("ampl"),m.ampl))throw std::runtime_error("mvrectsinu: freq/ampl missing");
-        if(c->child("phase"))read_xyz(c->child("phase"),m.phase);
-        const bool deg=(c->attr("anglesunits","degrees")=="degrees");
-        if(deg)for(int k=0;k<3;k++)m.phase[k]*=M_PI/180.0;
-        bool started=false;
-        for(auto& b:begins)if(b.first==id){ m.tstart=b.second; m.tend=b.second+duration; started=true; }
-        if(started)s->motions.push_back(m);
+        if(c->name.empty() || c->name[0]=='_')continue;
+        if(c->name=="begin"){ begins.push_back({atoi(c->attr("mov","0").c_str()),todouble(c->attr("start","0")),(c->has("finish")? todouble(c->attr("finish")): -1.0)}); continue; }
+        MovDef d; memset(&d.m,0,sizeof(d.m));
+        d.id=atoi(c->attr("id","0").c_str()); d.next=atoi(c->attr("next","0").c_str()); d.duration=todouble(c->attr("duration","0"));
+        const std::string units=c->attr("anglesunits","degrees");
+        if(units!="degrees" && units!="radians")throw std::runtime_error("motion: anglesunits must be degrees or radians");
+        const bool deg=(units=="degrees");
+        const double todeg=(deg? 1.0: 180.0/M_PI), torad=(deg? M_PI/180.0: 1.0);
+        auto ang=[&](const char* n,const char* at,bool req,double def){ const XmlNode* e=c->child(n); if(!e||!e->has(at)){ if(req)throw std::runtime_error("motion <"+c->name+">: <"+n+" "+at+"> missing"); return def; } return todouble(e->attr(at)); };
+        auto axis=[&](){ if(!read_xyz(c->child("axisp1"),d.m.axisp1)||!read_xyz(c->child("axisp2"),d.m.axisp2))throw std::runtime_error("motion <"+c->name+">: axisp1/axisp2 missing"); };
+        if(c->name=="wait")d.m.type=B2S_MOV_WAIT;
+        else if(c->name=="mvrect"){ d.m.type=B2S_MOV_RECT; if(!read_xyz(c->child("vel"),d.m.v1))throw std::runtime_error("mvrect: <vel> missing"); }
+        else if(c->name=="mvrectace"){
+          d.m.type=B2S_MOV_RECTACE;
+          if(!read_xyz(c->child("ace"),d.m.v2))throw std::runtime_error("mvrectace: <ace> missing");
+          if(!read_xyz(c->child("velini"),d.m.v1))throw std::runtime_error("mvrectace without <velini> (velocity of the previous movement) is not supported by this build");
+        }
+        else if(c->name=="mvrot"){ d.m.type=B2S_MOV_ROT; axis(); d.m.v1[0]=ang("vel","ang",true,0)*todeg; }
+        else if(c->name=="mvrotace"){
+          d.m.type=B2S_MOV_ROTACE; axis(); d.m.v2[0]=ang("ace","ang",true,0)*todeg;
+          if(!c->child("velini"))throw std::runtime_error("mvrotace without <velini> (velocity of the previous movement) is not supported by this build");
+          d.m.v1[0]=ang("velini","ang",true,0)*todeg;
+        }
+        else if(c->name=="mvrectsinu"){
+          d.m.type=B2S_MOV_RECTSINU;
+          if(!read_xyz(c->child("freq"),d.m.v1)||!read_xyz(c->child("ampl"),d.m.v2))throw std::runtime_error("mvrectsinu: freq/ampl missing");
+          if(c->child("phase"))read_xyz(c->child("phase"),d.m.v3);
+          for(int k=0;k<3;k++)d.m.v3[k]*=torad;
+        }
+        else if(c->name=="mvrotsinu"){
+          d.m.type=B2S_MOV_ROTSINU; axis();
+          d.m.v1[0]=ang("freq","v",true,0); d.m.v2[0]=ang("ampl","v",true,0)*todeg; d.m.v3[0]=ang("phase","v",false,0)*torad;
+        }
+        else throw std::runtime_error("motion <"+c->name+"> is not supported by this build (wait, mvrect, mvrectace, mvrot, mvrotace, mvrectsinu, mvrotsinu)");
+        defs.push_back(d);
+      }
+      const double tlimit=(s->timemax>0? s->timemax: 1e30);
+      for(auto& b:begins){
+        double t=b.start; int id=b.mov; size_t guard=0;
+        while(id && t<=tlimit && guard++<20000){
+          const MovDef* d=NULL; for(auto& q:defs)if(q.id==id)d=&q;
+          if(!d)throw std::runtime_error("motion: movement id not found in the object");
+          if(!(d->duration>0))break;
+          MotionCfg m; m.ref=ref; m.m=d->m; m.m.tstart=t; m.m.tend=t+d->duration;
+          if(b.finish>=0 && m.m.tend>b.finish)m.m.tend=b.finish;
+          if(m.m.tend>m.m.tstart)s->motions.push_back(m);
+          if(b.finish>=0 && t+d->duration>=b.finish)break;
+          t+=d->duration; id=d->next;
+        }
       }
     }
   }
@@ -639,8 +679,9 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
     const PartBlock* blk=NULL;
     for(auto& b:s->blocks)if(b.type==1 && b.refmotion==m.ref)blk=&b;
     if(!blk)continue;
-    r=b2s_add_motion_rectsinu(s->ctx,blk->begin,blk->count,m.freq,m.ampl,m.phase,m.tstart,m.tend);
-    if(r)throw std::runtime_error(std::string("b2s_add_motion_rectsinu failed: ")+b2s_last_error(s->ctx));
+    m.m.idbegin=blk->begin; m.m.count=blk->count;
+    r=b2s_add_motion(s->ctx,&m.m);
+    if(r)throw std::runtime_error(std::string("b2s_add_motion failed: ")+b2s_last_error(s->ctx));
   }
   for(auto& d:s->dampings){
     if(d.type==0)r=b2s_add_damping_plane(s->ctx,d.a,d.b,d.over,d.redumax,d.factor,d.usedomain? d.domain: NULL);

@@ -72,6 +72,15 @@ class Floating(C.Structure):
     ]
 
 
+class MotionRec(C.Structure):
+    _fields_ = [
+        ("idbegin", C.c_uint32), ("count", C.c_uint32), ("type", C.c_int32), ("pad", C.c_int32),
+        ("tstart", C.c_double), ("tend", C.c_double),
+        ("v1", C.c_double * 3), ("v2", C.c_double * 3), ("v3", C.c_double * 3),
+        ("axisp1", C.c_double * 3), ("axisp2", C.c_double * 3),
+    ]
+
+
 class Info(C.Structure):
     _fields_ = [
         ("np", C.c_uint32), ("npb", C.c_uint32), ("npbok", C.c_uint32), ("npf_out_total", C.c_uint32),
@@ -90,7 +99,7 @@ ABI_SYMBOLS = [
     "b2s_config_finalize", "b2s_error_string", "b2s_create", "b2s_destroy", "b2s_last_error", "b2s_get_params",
     "b2s_upload_particles", "b2s_download_particles", "b2s_download_particles_byid", "b2s_get_array",
     "b2s_get_info", "b2s_set_time", "b2s_celldiv", "b2s_interaction", "b2s_compute_verlet", "b2s_compute_symplectic_pre",
-    "b2s_compute_symplectic_corr", "b2s_compute_step", "b2s_run_steps", "b2s_add_motion_rectsinu", "b2s_add_damping_plane", "b2s_add_damping_box", "b2s_out_enable", "b2s_out_fetch", "b2s_gauge_add_force", "b2s_gauge_add_maxz",
+    "b2s_compute_symplectic_corr", "b2s_compute_step", "b2s_run_steps", "b2s_add_motion_rectsinu", "b2s_add_motion", "b2s_add_damping_plane", "b2s_add_damping_box", "b2s_out_enable", "b2s_out_fetch", "b2s_gauge_add_force", "b2s_gauge_add_maxz",
     "b2s_move_linear", "b2s_set_floatings", "b2s_get_floatings", "b2s_count_pairs", "b2s_time_interaction",
     "b2s_gauge_add_velocity", "b2s_gauge_add_swl", "b2s_gauges_compute", "b2s_gauge_result",
     "b2s_launch_count", "b2s_get_stream", "b2s_set_interaction_variant", "b2s_slab_config",
@@ -146,6 +155,7 @@ def load_library():
     lib.b2s_add_damping_box.argtypes = [vp, dp_, dp_, dp_, dp_, C.c_float, C.c_float, fp_, C.c_uint32]
     lib.b2s_out_enable.argtypes = [vp, C.c_uint32]
     lib.b2s_out_fetch.argtypes = [vp, C.c_uint32, u32p, vp, vp, vp, vp, vp]
+    lib.b2s_add_motion.argtypes = [vp, C.POINTER(MotionRec)]
     lib.b2s_move_linear.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     lib.b2s_set_floatings.argtypes = [vp, C.c_uint32, C.POINTER(Floating)]
     lib.b2s_get_floatings.argtypes = [vp, C.c_uint32, C.POINTER(Floating)]

@@ -196,6 +196,27 @@ int b2s_run_steps(b2s_ctx* ctx, uint32_t nsteps, double* time_out);
  * pos(t)=ampl*sin(2*pi*freq*t+phase) per axis; applied every step with the step's dt. */
 int b2s_add_motion_rectsinu(b2s_ctx* ctx, uint32_t idbegin, uint32_t count, const double freq[3],
                             const double ampl[3], const double phase[3], double tstart, double tend);
+/* General form: one movement of JMotion (JMotionMov.h:106-276, evaluated like JMotionObj::ProcesTime, JMotionObj.cpp:470-600)
+ * for the moving block [idbegin,idbegin+count), active in [tstart,tend).  Movements of one block are applied in the order they
+ * were added; linear results go through cusph::MoveLinBound, results with a rotation through cusph::MoveMatBound
+ * (JSphGpu_ker.cu:1671-1759).  Angles in degrees (as the reference stores them), phases in radians.
+ *   type            v1                 v2               v3
+ *   RECTSINU        freq (Hz)          ampl (m)         phase (rad)
+ *   RECT            vel (m/s)
+ *   RECTACE         velini (m/s)       ace (m/s^2)
+ *   ROT             v1[0]=velang (deg/s)                                  axisp1, axisp2
+ *   ROTACE          v1[0]=velini       v2[0]=aceang (deg/s^2)             axisp1, axisp2
+ *   ROTSINU         v1[0]=freq (Hz)    v2[0]=ampl (deg) v3[0]=phase (rad) axisp1, axisp2
+ *   WAIT            (nothing moves) */
+enum { B2S_MOV_RECTSINU = 0, B2S_MOV_RECT = 1, B2S_MOV_RECTACE = 2, B2S_MOV_ROT = 3, B2S_MOV_ROTACE = 4, B2S_MOV_ROTSINU = 5, B2S_MOV_WAIT = 6 };
+typedef struct b2s_motion {
+  uint32_t idbegin, count;
+  int32_t  type, pad;
+  double   tstart, tend;
+  double   v1[3], v2[3], v3[3];
+  double   axisp1[3], axisp2[3];
+} b2s_motion;
+int b2s_add_motion(b2s_ctx* ctx, const b2s_motion* m);
 /* Direct form: displace a block now (MOTT_Linear data: JDsMotionDef.h). */
 int b2s_move_linear(b2s_ctx* ctx, uint32_t idbegin, uint32_t count, const double mvpos[3], const float mvvel[3]);
 
