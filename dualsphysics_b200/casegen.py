@@ -167,6 +167,9 @@ def write_case(dirpath: str, name: str, spec: DamBreakSpec) -> dict:
     if spec.normals:
         boundnor = np.zeros((nbound, 3), dtype=np.float32)
         boundnor[:nfixed] = _normals(spec, parts["fixed"], parts["nx"], parts["ny"], parts["nz"])
+        if nmoving:
+            # piston plate (lattice planes i=2,3, fluid from i=5): interface dp/2 in front of the plane i=3
+            boundnor[nfixed:nfixed + nmoving, 0] = (3.5 * dp - pos[nfixed:nfixed + nmoving, 0]).astype(np.float32)
 
     posmin, posmax = pos.min(axis=0), pos.max(axis=0)
     root = bi4.make_case_item(name, np_total=n, nfixed=nfixed, nmoving=nmoving, nfloat=nfloat,

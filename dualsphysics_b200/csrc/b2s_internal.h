@@ -133,6 +133,7 @@ struct b2s_ctx {
   float* spstau; float* spstau_alt; float* spstau_new;   // 6 floats per particle
   // mDBC
   float4* boundnor; float4* boundnor_alt;                 // xyz normal, w unused
+  float4* motionace; float4* motionace_alt;               // mDBC2 with moving boundaries: acceleration of the imposed motion (MotionAce, JSphCpu_mdbc.cpp:472-490)
   float4* shiftpos;                                       // standard shifting: displacement of the current sub-step (fluid particles)
   uint8_t* boundmode; float4* tangenvel;                  // mDBC2 (SlipMode 2/3): per interaction, in the current sorted order
   // interaction inputs/outputs

@@ -319,6 +319,7 @@ struct ReorderArgs {
   const float4* m1_s; float4* m1_d;
   const float* tau_s; float* tau_d;
   const float4* nor_s; float4* nor_d;
+  const float4* mace_s; float4* mace_d;
   float4* posp; uint4* posh; uint32_t* ridp;
   uint32_t casenfixed, casenbound;
 };
@@ -346,6 +347,7 @@ __global__ void __launch_bounds__(DIV_BS) k_reorder(const DivState* __restrict__
       td[0]=ts[0]; td[1]=ts[1]; td[2]=ts[2];
     }
     if(a.nor_s)a.nor_d[p]=a.nor_s[s];
+    if(a.mace_s)a.mace_d[p]=a.mace_s[s];
     if(p<ds->np){
       // position relative to the origin of the particle's own cell (x: of its block of cells) (PosCell idea, JSphGpuSimple_ker.cu:46-57)
       const uint32_t cx=B2S_DCEL_CELLX(cte.domcellcode,dc), cy=B2S_DCEL_CELLY(cte.domcellcode,dc), cz=B2S_DCEL_CELLZ(cte.domcellcode,dc);
@@ -439,6 +441,7 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   if(ctx->velrhom1){ a.m1_s=ctx->velrhom1; a.m1_d=ctx->velrhom1_alt; }
   if(ctx->spstau){ a.tau_s=ctx->spstau; a.tau_d=ctx->spstau_alt; }
   if(ctx->boundnor){ a.nor_s=ctx->boundnor; a.nor_d=ctx->boundnor_alt; }
+  if(ctx->motionace){ a.mace_s=ctx->motionace; a.mace_d=ctx->motionace_alt; }
   a.posp=ctx->posp; a.posh=ctx->posh;
   a.ridp=(ctx->prm.casenmoving+ctx->prm.casenfloat? ctx->ridp: NULL);
   a.casenfixed=ctx->prm.casenfixed; a.casenbound=ctx->prm.casenbound;
@@ -452,6 +455,7 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   if(ctx->velrhom1)std::swap(ctx->velrhom1,ctx->velrhom1_alt);
   if(ctx->spstau)std::swap(ctx->spstau,ctx->spstau_alt);
   if(ctx->boundnor)std::swap(ctx->boundnor,ctx->boundnor_alt);
+  if(ctx->motionace)std::swap(ctx->motionace,ctx->motionace_alt);
   ctx->bound_changed=false;
   B2S_CUDA(ctx,cudaGetLastError());
   return B2S_OK;

@@ -81,7 +81,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   ctx->gauges_dev=NULL; ctx->gauge_res_dev=NULL; ctx->gauge_res_h=NULL; ctx->gauge_mass_dev=NULL; ctx->gauge_points=0; ctx->gauge_force_dev=NULL; ctx->gauge_force_n=0;
   ctx->ft_massp_dev=NULL; ctx->ft_sums_dev=NULL; ctx->ft_allsums_dev=NULL; ctx->ft_sums_h=NULL; ctx->ft_dev=NULL; ctx->scratch=NULL; ctx->scratch_bytes=0;
   ctx->pospre_xy=ctx->pospre_xy_alt=NULL; ctx->pospre_z=ctx->pospre_z_alt=NULL; ctx->velrhopre=ctx->velrhopre_alt=NULL;
-  ctx->velrhom1=ctx->velrhom1_alt=NULL; ctx->spstau=ctx->spstau_alt=ctx->spstau_new=NULL; ctx->boundnor=ctx->boundnor_alt=NULL;
+  ctx->velrhom1=ctx->velrhom1_alt=NULL; ctx->spstau=ctx->spstau_alt=ctx->spstau_new=NULL; ctx->boundnor=ctx->boundnor_alt=NULL; ctx->motionace=ctx->motionace_alt=NULL;
   const size_t cap=ctx->cap;
   const b2s_params& q=ctx->prm;
   const uint64_t nct64=uint64_t(q.domcells[0])*q.domcells[1]*q.domcells[2];
@@ -102,6 +102,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   }
   if(q.shiftmode){ TRY(dalloc(ctx->shiftpos,cap)); if(e==cudaSuccess)cudaMemset(ctx->shiftpos,0,size_t(cap)*16); }
   if(q.tboundary==B2S_BC_MDBC && q.slipmode>=B2S_SLIP_NOSLIP){ TRY(dalloc(ctx->boundmode,cap)); TRY(dalloc(ctx->tangenvel,cap)); if(e==cudaSuccess){ cudaMemset(ctx->boundmode,0,cap); cudaMemset(ctx->tangenvel,0,size_t(cap)*16); } }
+  if(q.tboundary==B2S_BC_MDBC && q.slipmode>=B2S_SLIP_NOSLIP && q.casenmoving){ TRY(dalloc(ctx->motionace,cap)); TRY(dalloc(ctx->motionace_alt,cap)); if(e==cudaSuccess){ cudaMemset(ctx->motionace,0,size_t(cap)*16); cudaMemset(ctx->motionace_alt,0,size_t(cap)*16);} }
   if(q.tboundary==B2S_BC_MDBC){ TRY(dalloc(ctx->boundnor,cap)); TRY(dalloc(ctx->boundnor_alt,cap)); if(e==cudaSuccess){ cudaMemset(ctx->boundnor,0,cap*16); cudaMemset(ctx->boundnor_alt,0,cap*16);} }
   TRY(dalloc(ctx->posp,cap)); TRY(dalloc(ctx->acear,cap)); TRY(dalloc(ctx->posh,size_t(cap)/2+2));
   TRY(dalloc(ctx->cellpart,cap)); TRY(dalloc(ctx->sortpart,cap)); TRY(dalloc(ctx->cellpart_alt,cap)); TRY(dalloc(ctx->sortpart_alt,cap));
@@ -129,7 +130,7 @@ extern "C" int b2s_destroy(b2s_ctx* ctx){
   cudaFree(ctx->pospre_xy_alt); cudaFree(ctx->pospre_z_alt); cudaFree(ctx->velrhopre_alt);
   cudaFree(ctx->velrhom1); cudaFree(ctx->velrhom1_alt);
   cudaFree(ctx->spstau); cudaFree(ctx->spstau_alt); cudaFree(ctx->spstau_new);
-  cudaFree(ctx->boundnor); cudaFree(ctx->boundnor_alt);
+  cudaFree(ctx->boundnor); cudaFree(ctx->boundnor_alt); cudaFree(ctx->motionace); cudaFree(ctx->motionace_alt);
   cudaFree(ctx->posp); cudaFree(ctx->acear); cudaFree(ctx->posh);
   cudaFree(ctx->cellpart); cudaFree(ctx->sortpart); cudaFree(ctx->cellpart_alt); cudaFree(ctx->sortpart_alt);
   cudaFree(ctx->begincell); cudaFree(ctx->radix_counts); cudaFree(ctx->ridp);
@@ -249,6 +250,7 @@ extern "C" int b2s_upload_particles(b2s_ctx* ctx, uint32_t np, const uint32_t* i
   ctx->np_host=np; ctx->npb_host=npb; ctx->npbok_host=npb;
   ctx->pre_active=false; ctx->bound_changed=true; ctx->verletstep=0;
   if(ctx->velrhom1)B2S_CUDA(ctx,cudaMemcpyAsync(ctx->velrhom1,ctx->cur.velrho,size_t(np)*16,cudaMemcpyDeviceToDevice,s));  // InitRunGpu: VelrhoM1=Velrho
+  if(ctx->motionace)B2S_CUDA(ctx,cudaMemsetAsync(ctx->motionace,0,size_t(ctx->cap)*16,s));
   r=b2s_periodic_impl(ctx); if(r)return r;
   r=b2s_celldiv_impl(ctx); if(r)return r;
   return b2s_sync_info(ctx);

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(M_BS) k_mdbc_vel0(const DivState* __restrict__
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(M_BS) k_mdbc2(const DivState* __restrict__ ds, const uint32_t* __restrict__ begt,
   const double2* __restrict__ posxy, const double* __restrict__ posz, const typecode* __restrict__ code, const float4* __restrict__ boundnor,
-  float4* posp, float4* velrho, uint8_t* boundmode, float4* tangenvel, int freeslip, const __grid_constant__ DevCte c)
+  float4* posp, float4* velrho, uint8_t* boundmode, float4* tangenvel, const float4* __restrict__ motionace, int freeslip, const __grid_constant__ DevCte c)
 {
   const uint32_t p1=blockIdx.x*blockDim.x+threadIdx.x;
   if(p1>=ds->npb)return;
@@ -218,19 +218,25 @@ __global__ void __launch_bounds__(M_BS) k_mdbc2(const DivState* __restrict__ ds,
     // pressure cloning (Mdbc2PressClone, JSphCpu_mdbc.cpp:182-207); dpos = boundary particle - ghost node = -normal
     const float pghost=float(c.cs0_d*c.cs0_d*double(rhofinal-c.rhopzero));
     const float normpos=(-nor.x)*nx+(-nor.y)*ny+(-nor.z)*nz;
-    const float normforce=c.rhopzero*(c.gravity[0]*nx+c.gravity[1]*ny+c.gravity[2]*nz);   // motion acceleration = 0 (fixed boundary)
+    // force = gravity - acceleration of the imposed motion (zero for fixed boundaries; MotionAce of the last RunMotion otherwise)
+    const float4 mace=(motionace? motionace[p1]: make_float4(0.f,0.f,0.f,0.f));
+    const float normforce=c.rhopzero*((c.gravity[0]-mace.x)*nx+(c.gravity[1]-mace.y)*ny+(c.gravity[2]-mace.z)*nz);
     const float pressfinal=pghost+normforce*normpos;
     rhofinal=c.rhopzero+float(double(pressfinal)/(c.cs0_d*c.cs0_d));
     const float gvx=float(vx/a11), gvy=float(vy/a11), gvz=float(vz/a11);
-    // no-slip: v2 = 2*v_motion - v_ghost = -v_ghost ; free-slip: v2 = v_ghost
-    const float v2x=(freeslip? gvx: 0.f+0.f-gvx), v2y=(freeslip? gvy: 0.f+0.f-gvy), v2z=(freeslip? gvz: 0.f+0.f-gvz);
+    // no-slip: v2 = 2*v_motion - v_ghost ; free-slip: v2 = v_ghost.  v_motion = the velocity the boundary particle carries
+    // (MDBC2_KEEPVEL, DualSphDef.h:471: velrho of a boundary particle is never overwritten, so it equals MotionVel)
+    const float4 vm=velrho[p1];
+    const float v2x=(freeslip? gvx: vm.x+vm.x-gvx), v2y=(freeslip? gvy: vm.y+vm.y-gvy), v2z=(freeslip? gvz: vm.z+vm.z-gvz);
     const float vdn=v2x*nx+v2y*ny+v2z*nz;
     tvx=v2x-vdn*nx; tvy=v2y-vdn*ny; tvz=v2z-vdn*nz;
   }
   else{
     boundmode[p1]=B2S_BMODE_MDBC2OFF;
     rhofinal=c.rhopzero;
-    tvx=tvy=tvz=0.f;   // tangential part of the motion velocity (0)
+    const float4 vm=velrho[p1];   // tangential part of the motion velocity
+    const float vdn=vm.x*nx+vm.y*ny+vm.z*nz;
+    tvx=vm.x-vdn*nx; tvy=vm.y-vdn*ny; tvz=vm.z-vdn*nz;
   }
   float4 vr=velrho[p1]; vr.w=rhofinal; velrho[p1]=vr;
   float4 pp=posp[p1]; pp.w=b2s_press(rhofinal,c); posp[p1]=pp;
@@ -240,10 +246,11 @@ __global__ void __launch_bounds__(M_BS) k_mdbc2(const DivState* __restrict__ ds,
 int b2s_mdbc_impl(b2s_ctx* ctx){
   if(!ctx->boundnor)return b2s_fail(ctx,B2S_ERR_STATE,"mDBC needs boundary normals");
   if(ctx->prm.slipmode>=B2S_SLIP_NOSLIP){
-    if(ctx->cte.use_floating || ctx->prm.casenmoving)return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"mDBC2 (SlipMode 2/3) is built for fixed boundaries only");
+    if(ctx->cte.use_floating)return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"mDBC2 (SlipMode 2/3) with floating bodies is not supported");
+    if(ctx->prm.casenmoving && ctx->slab_on)return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"mDBC2 (SlipMode 2/3) with moving boundaries is not supported with slab decomposition");
     if(!ctx->npb_host)return B2S_OK;
     k_mdbc2<<<b2s_blocks(ctx->npb_host,M_BS),M_BS,0,ctx->stream>>>(ctx->div,(const uint32_t*)ctx->begincell,ctx->cur.posxy,ctx->cur.posz,ctx->cur.code,
-      ctx->boundnor,ctx->posp,ctx->cur.velrho,ctx->boundmode,ctx->tangenvel,ctx->prm.slipmode==B2S_SLIP_FREESLIP? 1: 0,ctx->cte); B2S_LAUNCHED(ctx);
+      ctx->boundnor,ctx->posp,ctx->cur.velrho,ctx->boundmode,ctx->tangenvel,ctx->motionace,ctx->prm.slipmode==B2S_SLIP_FREESLIP? 1: 0,ctx->cte); B2S_LAUNCHED(ctx);
     B2S_CUDA(ctx,cudaGetLastError());
     return B2S_OK;
   }

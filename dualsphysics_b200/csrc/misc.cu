@@ -40,7 +40,7 @@ __device__ __forceinline__ void aff_rotate(Affine& a,double angdeg,const double 
 
 __global__ void k_move_block(const Motion* __restrict__ movs, uint32_t nmov, const StepState* __restrict__ st, const DivState* __restrict__ ds,
   const uint32_t* __restrict__ ridp, uint32_t casenfixed, double2* posxy, double* posz, float4* velrho, uint32_t* dcell, typecode* code,
-  float4* boundnor, const __grid_constant__ DevCte c)
+  float4* boundnor, float4* motionace, const __grid_constant__ DevCte c)
 {
   const uint32_t i=blockIdx.x*blockDim.x+threadIdx.x;
   const Motion& m0=movs[0];
@@ -65,9 +65,12 @@ __global__ void k_move_block(const Motion* __restrict__ movs, uint32_t nmov, con
       default: break;   // B2S_MOV_WAIT
     }
   }
-  if(!modif)return;   // no active movement: position and velocity stay (JSphCpu::RunMotion only touches MOTT_Linear / MOTT_Matrix objects)
   const uint32_t p=ridp[m0.idbegin-casenfixed+i];
   if(p>=ds->np)return;
+  if(!modif){   // no active movement: position and velocity stay (JSphCpu::RunMotion only touches MOTT_Linear / MOTT_Matrix objects)
+    if(motionace)motionace[p]=make_float4(0.f,0.f,0.f,0.f);   // CopyMotionVelAce still runs: the velocity did not change
+    return;
+  }
   double2 xy=posxy[p]; double z=posz[p];
   double mv[3];
   if(!a.rot){ mv[0]=a.t[0]; mv[1]=a.t[1]; mv[2]=a.t[2]; }
@@ -89,7 +92,10 @@ __global__ void k_move_block(const Motion* __restrict__ movs, uint32_t nmov, con
   posxy[p]=xy; posz[p]=z;
   if(out)code[p]=typecode(B2S_CODE_SETNORMAL(code[p])|B2S_CODE_OUTPOS);
   dcell[p]=cell;
-  float4 v=velrho[p]; v.x=vx; v.y=vy; v.z=vz; velrho[p]=v;
+  float4 v=velrho[p];
+  // CopyMotionVelAce (JSphCpu_mdbc.cpp:472-490): acceleration of the imposed motion = change of the motion velocity over the step
+  if(motionace)motionace[p]=make_float4(float((double(vx)-double(v.x))/dt),float((double(vy)-double(v.y))/dt),float((double(vz)-double(v.z))/dt),0.f);
+  v.x=vx; v.y=vy; v.z=vz; velrho[p]=v;
 }
 
 int b2s_motion_impl(b2s_ctx* ctx, double, double){
@@ -107,7 +113,7 @@ int b2s_motion_impl(b2s_ctx* ctx, double, double){
     while(e<n && ctx->motions[e].idbegin==ctx->motions[k].idbegin)e++;
     const Motion& h=ctx->motions[k];
     k_move_block<<<b2s_blocks(h.count,256),256,0,ctx->stream>>>((const Motion*)ctx->motion_dev+k,uint32_t(e-k),ctx->step,ctx->div,ctx->ridp,ctx->prm.casenfixed,
-      ctx->cur.posxy,ctx->cur.posz,ctx->cur.velrho,ctx->cur.dcell,ctx->cur.code,ctx->boundnor,ctx->cte); B2S_LAUNCHED(ctx);
+      ctx->cur.posxy,ctx->cur.posz,ctx->cur.velrho,ctx->cur.dcell,ctx->cur.code,ctx->boundnor,ctx->motionace,ctx->cte); B2S_LAUNCHED(ctx);
     k=e;
   }
   ctx->bound_changed=true;

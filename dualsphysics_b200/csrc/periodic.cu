@@ -23,7 +23,7 @@ void b2s_launch_scan_excl(cudaStream_t s, uint32_t* data, uint32_t n);   // cell
 
 struct PeriArrays {
   uint32_t* idp; typecode* code; uint32_t* dcell; double2* posxy; double* posz; float4* velrho;
-  double2* pre_xy; double* pre_z; float4* pre_v; float4* m1; float* tau; float4* nor;
+  double2* pre_xy; double* pre_z; float4* pre_v; float4* m1; float* tau; float4* nor; float4* mace;
 };
 
 // PeriodicIgnore + the bookkeeping of the head of RunPeriodic.
@@ -88,6 +88,7 @@ __device__ __forceinline__ void peri_copy(const PeriArrays& a,const DevCte& c,ui
   if(a.m1)a.m1[pnew]=a.m1[pcopy];
   if(a.tau){ const float2* s=reinterpret_cast<const float2*>(a.tau+size_t(pcopy)*6); float2* t=reinterpret_cast<float2*>(a.tau+size_t(pnew)*6); t[0]=s[0]; t[1]=s[1]; t[2]=s[2]; }
   if(a.nor)a.nor[pnew]=a.nor[pcopy];
+  if(a.mace)a.mace[pnew]=a.mace[pcopy];
 }
 
 __global__ void __launch_bounds__(P_BS) k_peri_dup(DivState* ds,int ctype,int cblock,double ix,double iy,double iz,
@@ -138,7 +139,7 @@ int b2s_periodic_impl(b2s_ctx* ctx){
   PeriArrays a;
   a.idp=ctx->cur.idp; a.code=ctx->cur.code; a.dcell=ctx->cur.dcell; a.posxy=ctx->cur.posxy; a.posz=ctx->cur.posz; a.velrho=ctx->cur.velrho;
   a.pre_xy=(ctx->pre_active? ctx->pospre_xy: NULL); a.pre_z=(ctx->pre_active? ctx->pospre_z: NULL); a.pre_v=(ctx->pre_active? ctx->velrhopre: NULL);
-  a.m1=ctx->velrhom1; a.tau=ctx->spstau; a.nor=ctx->boundnor;
+  a.m1=ctx->velrhom1; a.tau=ctx->spstau; a.nor=ctx->boundnor; a.mace=ctx->motionace;
   const b2s_params& q=ctx->prm;
   uint32_t nper[2]={0,0}, np=np0;
   for(int ctype=0;ctype<2;ctype++)for(int ax=0;ax<3;ax++)if((c.periactive>>ax)&1){
