@@ -143,6 +143,7 @@ struct b2s_ctx {
   // neighbour list
   uint32_t* cellpart; uint32_t* sortpart; uint32_t* cellpart_alt; uint32_t* sortpart_alt;
   int2* begincell;
+  bool nearbound_valid; uint8_t* nearbound;   // per cell of the cell domain: 1 = a boundary particle lies within +-scelldiv cells (interaction variant 4 skips its boundary pass otherwise)
   uint32_t* radix_counts; size_t radix_counts_len;
   uint32_t* ridp;    // index by id for moving+floating (CalcRidp)
   // device state

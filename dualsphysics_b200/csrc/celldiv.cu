@@ -288,6 +288,16 @@ __global__ void __launch_bounds__(DIV_BS) k_beginend(const DivState* __restrict_
   beg[c]=lo;
 }
 
+// Cells with a boundary particle within +-d cells (the neighbour window of the interaction): every occupied boundary cell marks
+// its window.  Lets the fluid interaction skip its whole boundary pass for the warps far from any wall (forces_pair2.cu).
+__global__ void __launch_bounds__(DIV_BS) k_nearbound_mark(const DivState* __restrict__ ds, const uint32_t* __restrict__ beg, uint8_t* __restrict__ nearb, int d){
+  const uint32_t c=blockIdx.x*blockDim.x+threadIdx.x;
+  if(c>=ds->nct || beg[c+1]==beg[c])return;
+  const int ncx=int(ds->ncx), ncy=int(ds->ncy), ncz=int(ds->ncz), nsheet=int(ds->nsheet);
+  const int cz=int(c)/nsheet, cy=(int(c)-cz*nsheet)/ncx, cx=int(c)-cz*nsheet-cy*ncx;
+  for(int z=max(cz-d,0);z<=min(cz+d,ncz-1);z++)for(int y=max(cy-d,0);y<=min(cy+d,ncy-1);y++)for(int x=max(cx-d,0);x<=min(cx+d,ncx-1);x++)nearb[x+y*ncx+z*nsheet]=1;
+}
+
 // Particle counts after the divide (JCellDivGpuSingle.cpp:218-231), one thread.
 __global__ void k_divcounts(DivState* ds, const uint32_t* __restrict__ beg){
   if(threadIdx.x||blockIdx.x)return;
@@ -430,6 +440,12 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   // 4. begin table + counts
   k_beginend<<<b2s_blocks(ctx->nctt_max,DIV_BS),DIV_BS,0,s>>>(ctx->div,ctx->cellpart,(uint32_t*)ctx->begincell); B2S_LAUNCHED(ctx);
   k_divcounts<<<1,32,0,s>>>(ctx->div,(const uint32_t*)ctx->begincell); B2S_LAUNCHED(ctx);
+  ctx->nearbound_valid=false;
+  if(ctx->variant==4 && ctx->npb_host){
+    ctx->nearbound_valid=true;
+    B2S_CUDA(ctx,cudaMemsetAsync(ctx->nearbound,0,size_t(ctx->nct_max),s));
+    k_nearbound_mark<<<b2s_blocks(ctx->nct_max,DIV_BS),DIV_BS,0,s>>>(ctx->div,(const uint32_t*)ctx->begincell,ctx->nearbound,c.scelldiv); B2S_LAUNCHED(ctx);
+  }
   // 5. fused gather
   k_reset_step_maxima<<<1,1,0,s>>>(ctx->step); B2S_LAUNCHED(ctx);
   ReorderArgs a; memset(&a,0,sizeof(a));

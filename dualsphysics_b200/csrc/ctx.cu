@@ -77,7 +77,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   ctx->launches=0; ctx->variant=0; ctx->pre_active=false; ctx->bound_changed=true; ctx->ftcount=0;
   ctx->verletstep=0;
   ctx->slab_on=false; ctx->slab_rank=0; ctx->slab_nranks=1; ctx->slab_cxa=0; ctx->slab_cxb=0; ctx->slab_counts=NULL; ctx->slab_flags=NULL; ctx->slab_counts_len=0;
-  ctx->defer_attr_set=false; ctx->boundmode=NULL; ctx->tangenvel=NULL; ctx->shiftpos=NULL; ctx->damp_dev=NULL; ctx->damp_dirty=false; ctx->out_dev=NULL; ctx->out_count_dev=NULL; ctx->out_cap=0; ctx->motion_dev=NULL; ctx->motion_dirty=false;
+  ctx->defer_attr_set=false; ctx->boundmode=NULL; ctx->tangenvel=NULL; ctx->shiftpos=NULL; ctx->damp_dev=NULL; ctx->damp_dirty=false; ctx->out_dev=NULL; ctx->out_count_dev=NULL; ctx->out_cap=0; ctx->motion_dev=NULL; ctx->motion_dirty=false; ctx->nearbound_valid=false;
   ctx->gauges_dev=NULL; ctx->gauge_res_dev=NULL; ctx->gauge_res_h=NULL; ctx->gauge_mass_dev=NULL; ctx->gauge_points=0; ctx->gauge_force_dev=NULL; ctx->gauge_force_n=0;
   ctx->ft_massp_dev=NULL; ctx->ft_sums_dev=NULL; ctx->ft_allsums_dev=NULL; ctx->ft_sums_h=NULL; ctx->ft_dev=NULL; ctx->scratch=NULL; ctx->scratch_bytes=0;
   ctx->pospre_xy=ctx->pospre_xy_alt=NULL; ctx->pospre_z=ctx->pospre_z_alt=NULL; ctx->velrhopre=ctx->velrhopre_alt=NULL;
@@ -107,6 +107,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   TRY(dalloc(ctx->posp,cap)); TRY(dalloc(ctx->acear,cap)); TRY(dalloc(ctx->posh,size_t(cap)/2+2));
   TRY(dalloc(ctx->cellpart,cap)); TRY(dalloc(ctx->sortpart,cap)); TRY(dalloc(ctx->cellpart_alt,cap)); TRY(dalloc(ctx->sortpart_alt,cap));
   { uint32_t* b=NULL; TRY(dalloc(b,size_t(ctx->nctt_max)+2)); ctx->begincell=(int2*)b; }
+  TRY(dalloc(ctx->nearbound,size_t(ctx->nct_max)+1));
   ctx->radix_counts_len=size_t(256)*((cap+4095)/4096+1);
   TRY(dalloc(ctx->radix_counts,ctx->radix_counts_len+ctx->radix_counts_len/4096+8));   // + block totals of the scan (celldiv.cu)
   TRY(dalloc(ctx->ridp,size_t(q.casenmoving)+q.casenfloat+1));
@@ -133,7 +134,7 @@ extern "C" int b2s_destroy(b2s_ctx* ctx){
   cudaFree(ctx->boundnor); cudaFree(ctx->boundnor_alt); cudaFree(ctx->motionace); cudaFree(ctx->motionace_alt);
   cudaFree(ctx->posp); cudaFree(ctx->acear); cudaFree(ctx->posh);
   cudaFree(ctx->cellpart); cudaFree(ctx->sortpart); cudaFree(ctx->cellpart_alt); cudaFree(ctx->sortpart_alt);
-  cudaFree(ctx->begincell); cudaFree(ctx->radix_counts); cudaFree(ctx->ridp);
+  cudaFree(ctx->begincell); cudaFree(ctx->nearbound); cudaFree(ctx->radix_counts); cudaFree(ctx->ridp);
   cudaFree(ctx->div); cudaFree(ctx->step);
   cudaFree(ctx->gauges_dev); cudaFree(ctx->gauge_res_dev); cudaFree(ctx->gauge_mass_dev); cudaFree(ctx->gauge_force_dev); if(ctx->gauge_res_h)cudaFreeHost(ctx->gauge_res_h);
   cudaFree(ctx->motion_dev); cudaFree(ctx->out_dev); cudaFree(ctx->out_count_dev); cudaFree(ctx->damp_dev); cudaFree(ctx->shiftpos); cudaFree(ctx->boundmode); cudaFree(ctx->tangenvel); cudaFree(ctx->slab_counts); cudaFree(ctx->slab_flags);

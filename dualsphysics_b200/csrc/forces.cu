@@ -206,7 +206,7 @@ bool b2s_forces_pair2_supported(const DevCte& c);
 int b2s_forces_fluid_only(b2s_ctx* ctx){
   ForcesArgs g;
   g.ds=ctx->div; g.st=ctx->step; g.beg=(const uint32_t*)ctx->begincell; g.dcell=ctx->cur.dcell; g.code=ctx->cur.code;
-  g.posp=ctx->posp; g.posh=ctx->posh; g.boundmode=ctx->boundmode; g.tangenvel=ctx->tangenvel; g.velrho=ctx->cur.velrho; g.tau=ctx->spstau; g.tau_new=ctx->spstau_new; g.ftomassp=ctx->ft_massp_dev; g.acear=ctx->acear;
+  g.posp=ctx->posp; g.posh=ctx->posh; g.boundmode=ctx->boundmode; g.tangenvel=ctx->tangenvel; g.nearbound=(ctx->nearbound_valid? ctx->nearbound: NULL); g.velrho=ctx->cur.velrho; g.tau=ctx->spstau; g.tau_new=ctx->spstau_new; g.ftomassp=ctx->ft_massp_dev; g.acear=ctx->acear;
   const uint32_t npf=(ctx->np_host>ctx->npb_host? ctx->np_host-ctx->npb_host: 0u);
   if(!npf)return B2S_OK;
   if(ctx->variant==3 && ctx->np_host<(1u<<26))return b2s_forces_defer_launch(ctx,g);   // queue entries hold 26-bit indices
@@ -220,7 +220,7 @@ int b2s_forces_impl(b2s_ctx* ctx, int interstep){
   cudaStream_t s=ctx->stream;
   ForcesArgs g;
   g.ds=ctx->div; g.st=ctx->step; g.beg=(const uint32_t*)ctx->begincell; g.dcell=ctx->cur.dcell; g.code=ctx->cur.code;
-  g.posp=ctx->posp; g.posh=ctx->posh; g.boundmode=ctx->boundmode; g.tangenvel=ctx->tangenvel; g.velrho=ctx->cur.velrho; g.tau=ctx->spstau; g.tau_new=ctx->spstau_new; g.ftomassp=ctx->ft_massp_dev; g.acear=ctx->acear;
+  g.posp=ctx->posp; g.posh=ctx->posh; g.boundmode=ctx->boundmode; g.tangenvel=ctx->tangenvel; g.nearbound=(ctx->nearbound_valid? ctx->nearbound: NULL); g.velrho=ctx->cur.velrho; g.tau=ctx->spstau; g.tau_new=ctx->spstau_new; g.ftomassp=ctx->ft_massp_dev; g.acear=ctx->acear;
   int r=b2s_forces_fluid_only(ctx); if(r)return r;
   if(ctx->npb_host){
     const bool ft=(ctx->cte.use_floating!=0);

@@ -16,6 +16,7 @@ struct ForcesArgs {
   const float* ftomassp;
   float4* acear;
   const uint8_t* boundmode; const float4* tangenvel;   // mDBC2 (SlipMode 2/3), else NULL
+  const uint8_t* nearbound;       // per cell: boundary within the neighbour window (celldiv.cu k_nearbound_mark), or NULL
 };
 
 __device__ __forceinline__ float b2s_rcp(float x){ float r; asm("rcp.approx.ftz.f32 %0, %1;":"=f"(r):"f"(x)); return r; }

@@ -154,8 +154,13 @@ __global__ void __launch_bounds__(P2_BS,P2_MINB) k_forces_fluid_pair2(ForcesArgs
   __shared__ float stash[6][P2_BS];
   Acc2 acc;
   acc.ax=acc.ay=acc.az=acc.ar=acc.delta=0ull; acc.visc=0.f; acc.mark=false;
+  // Whole boundary pass skipped for warps whose particles have no boundary particle in their neighbour windows (one byte per
+  // particle from the per-cell flags of the divide instead of 2 x 25 begin-table loads): most of the fluid is far from a wall.
+  const bool nearb=(g.nearbound==nullptr || (valid && g.nearbound[r.cx+r.cy*ncx+r.cz*nsheet]!=0));
+  const bool warpnearb=(__any_sync(0xffffffffu,nearb)!=0);
   #pragma unroll 1
   for(int pass=1;pass>=0;pass--){
+    if(pass==1 && !warpnearb)continue;   // (the stash below is only read when it was written: see the store after the loop)
     const uint32_t* beg=(pass==0? g.beg+ds->box_fluid: g.beg);   // pass 1: boundary neighbours (first), pass 0: fluid neighbours
     // Rows (z,y) of the neighbour window, software-pipelined: the begin-table loads of row i+1 are issued before row i is
     // processed, so their latency (three dependent loads after the trim) hides behind the pair work of the current row.
@@ -377,8 +382,10 @@ __global__ void __launch_bounds__(P2_BS,P2_MINB) k_forces_fluid_pair2(ForcesArgs
     PairAcc sf={0,0,0,0,0,0,0,0,0,0,0,0}, sb={0,0,0,0,0,0,0,0,0,0,0,0};
     sf.ax=FADD(lo(acc.ax),hi(acc.ax)); sf.ay=FADD(lo(acc.ay),hi(acc.ay)); sf.az=FADD(lo(acc.az),hi(acc.az)); sf.ar=FADD(lo(acc.ar),hi(acc.ar));
     sf.delta=(acc.mark? FLT_MAX: FADD(lo(acc.delta),hi(acc.delta))); sf.visc=acc.visc;
-    sb.ax=stash[0][threadIdx.x]; sb.ay=stash[1][threadIdx.x]; sb.az=stash[2][threadIdx.x]; sb.ar=stash[3][threadIdx.x];
-    sb.delta=stash[4][threadIdx.x]; sb.visc=stash[5][threadIdx.x];
+    if(warpnearb){
+      sb.ax=stash[0][threadIdx.x]; sb.ay=stash[1][threadIdx.x]; sb.az=stash[2][threadIdx.x]; sb.ar=stash[3][threadIdx.x];
+      sb.delta=stash[4][threadIdx.x]; sb.visc=stash[5][threadIdx.x];
+    }
     finalize_store<B2S_VISCO_ARTIFICIAL,TDENS>(g,c,p1,velrhop1,sf,sb,ace2,viscmax);
   }
   //-Fused maxima: ViscDtMax and AceMax^2 (replaces ReduMaxFloat x2 + cudaMemcpy, JSphGpu_ker.cu:75-125).
