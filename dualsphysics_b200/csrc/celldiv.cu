@@ -281,21 +281,30 @@ __global__ void __launch_bounds__(DIV_BS) k_radix_scatter(const uint32_t* __rest
 // all inside L2).  The former one-thread-per-particle form filled the runs of EMPTY boxes serially from the particle in front
 // of them, and a dam-break domain is mostly empty boxes (190 us at 10M particles for a 40 MB read).
 __global__ void __launch_bounds__(DIV_BS) k_beginend(const DivState* __restrict__ ds, const uint32_t* __restrict__ keys, uint32_t* __restrict__ beg){
-  const uint32_t c=blockIdx.x*blockDim.x+threadIdx.x;
-  if(c>=ds->nctt)return;
-  uint32_t lo=0, hi=ds->nptot;
-  while(lo<hi){ const uint32_t mid=lo+((hi-lo)>>1); if(keys[mid]<c)lo=mid+1; else hi=mid; }
-  beg[c]=lo;
+  // grid-stride: the table size is a device-side value (the cell domain of THIS divide); the host only knows the map-wide bound,
+  // which is many times larger on a slab rank
+  const uint32_t nctt=ds->nctt, n=ds->nptot;
+  for(uint32_t c=blockIdx.x*blockDim.x+threadIdx.x; c<nctt; c+=gridDim.x*blockDim.x){
+    uint32_t lo=0, hi=n;
+    while(lo<hi){ const uint32_t mid=lo+((hi-lo)>>1); if(keys[mid]<c)lo=mid+1; else hi=mid; }
+    beg[c]=lo;
+  }
 }
 
 // Cells with a boundary particle within +-d cells (the neighbour window of the interaction): every occupied boundary cell marks
 // its window.  Lets the fluid interaction skip its whole boundary pass for the warps far from any wall (forces_pair2.cu).
+__global__ void __launch_bounds__(DIV_BS) k_nearbound_clear(const DivState* __restrict__ ds, uint32_t* __restrict__ nearb4){
+  const uint32_t n4=(ds->nct+3u)>>2;
+  for(uint32_t i=blockIdx.x*blockDim.x+threadIdx.x; i<n4; i+=gridDim.x*blockDim.x)nearb4[i]=0u;
+}
 __global__ void __launch_bounds__(DIV_BS) k_nearbound_mark(const DivState* __restrict__ ds, const uint32_t* __restrict__ beg, uint8_t* __restrict__ nearb, int d){
-  const uint32_t c=blockIdx.x*blockDim.x+threadIdx.x;
-  if(c>=ds->nct || beg[c+1]==beg[c])return;
   const int ncx=int(ds->ncx), ncy=int(ds->ncy), ncz=int(ds->ncz), nsheet=int(ds->nsheet);
-  const int cz=int(c)/nsheet, cy=(int(c)-cz*nsheet)/ncx, cx=int(c)-cz*nsheet-cy*ncx;
-  for(int z=max(cz-d,0);z<=min(cz+d,ncz-1);z++)for(int y=max(cy-d,0);y<=min(cy+d,ncy-1);y++)for(int x=max(cx-d,0);x<=min(cx+d,ncx-1);x++)nearb[x+y*ncx+z*nsheet]=1;
+  const uint32_t nct=ds->nct;
+  for(uint32_t c=blockIdx.x*blockDim.x+threadIdx.x; c<nct; c+=gridDim.x*blockDim.x){
+    if(beg[c+1]==beg[c])continue;
+    const int cz=int(c)/nsheet, cy=(int(c)-cz*nsheet)/ncx, cx=int(c)-cz*nsheet-cy*ncx;
+    for(int z=max(cz-d,0);z<=min(cz+d,ncz-1);z++)for(int y=max(cy-d,0);y<=min(cy+d,ncy-1);y++)for(int x=max(cx-d,0);x<=min(cx+d,ncx-1);x++)nearb[x+y*ncx+z*nsheet]=1;
+  }
 }
 
 // Particle counts after the divide (JCellDivGpuSingle.cpp:218-231), one thread.
@@ -438,13 +447,14 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
     t=ctx->sortpart; ctx->sortpart=ctx->sortpart_alt; ctx->sortpart_alt=t;
   }
   // 4. begin table + counts
-  k_beginend<<<b2s_blocks(ctx->nctt_max,DIV_BS),DIV_BS,0,s>>>(ctx->div,ctx->cellpart,(uint32_t*)ctx->begincell); B2S_LAUNCHED(ctx);
+  k_beginend<<<min(b2s_blocks(ctx->nctt_max,DIV_BS),148u*16u),DIV_BS,0,s>>>(ctx->div,ctx->cellpart,(uint32_t*)ctx->begincell); B2S_LAUNCHED(ctx);
   k_divcounts<<<1,32,0,s>>>(ctx->div,(const uint32_t*)ctx->begincell); B2S_LAUNCHED(ctx);
   ctx->nearbound_valid=false;
   if(ctx->variant==4 && ctx->npb_host){
     ctx->nearbound_valid=true;
-    B2S_CUDA(ctx,cudaMemsetAsync(ctx->nearbound,0,size_t(ctx->nct_max),s));
-    k_nearbound_mark<<<b2s_blocks(ctx->nct_max,DIV_BS),DIV_BS,0,s>>>(ctx->div,(const uint32_t*)ctx->begincell,ctx->nearbound,c.scelldiv); B2S_LAUNCHED(ctx);
+    const unsigned gn=min(b2s_blocks(ctx->nct_max,DIV_BS),148u*16u);
+    k_nearbound_clear<<<gn,DIV_BS,0,s>>>(ctx->div,(uint32_t*)ctx->nearbound); B2S_LAUNCHED(ctx);
+    k_nearbound_mark<<<gn,DIV_BS,0,s>>>(ctx->div,(const uint32_t*)ctx->begincell,ctx->nearbound,c.scelldiv); B2S_LAUNCHED(ctx);
   }
   // 5. fused gather
   k_reset_step_maxima<<<1,1,0,s>>>(ctx->step); B2S_LAUNCHED(ctx);
