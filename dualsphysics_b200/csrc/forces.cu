@@ -28,7 +28,12 @@ __global__ void __launch_bounds__(F_BS) k_forces_fluid_gather(ForcesArgs g, cons
   const uint32_t npb=ds->npb, np=ds->np;
   const uint32_t p1=npb+blockIdx.x*blockDim.x+threadIdx.x;
   float ace2=0.f, viscmax=0.f;
-  if(p1<np && B2S_CODE_ISNORMAL(g.code[p1])){   // slab halo ghosts (CODE_PERIODIC) are neighbours only
+  const bool valid1=(p1<np && B2S_CODE_ISNORMAL(g.code[p1]));   // slab halo ghosts (CODE_PERIODIC) are neighbours only
+  // boundary pass only for warps with a boundary particle inside some neighbour window (per-cell flags of the divide)
+  bool nearb=(g.nearbound==nullptr);
+  if(valid1 && !nearb){ const CellRange q=cell_range(g.dcell[p1],c,ds); nearb=(g.nearbound[q.cx+q.cy*int(ds->ncx)+q.cz*int(ds->nsheet)]!=0); }
+  const bool warpnearb=(__any_sync(0xffffffffu,nearb)!=0);
+  if(valid1){
     const float4 pp1=g.posp[p1];
     const float4 velrhop1=g.velrho[p1];
     const float pressp1=pp1.w;
@@ -71,7 +76,7 @@ __global__ void __launch_bounds__(F_BS) k_forces_fluid_gather(ForcesArgs g, cons
       }
     }
     //-Boundary neighbours.
-    {
+    if(warpnearb){
       const uint32_t* beg=g.beg;
       for(int z=r.zini;z<r.zfin;z++)for(int y=r.yini;y<r.yfin;y++){
         const int row=y*ncx+z*nsheet;
