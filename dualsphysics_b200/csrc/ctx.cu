@@ -151,7 +151,7 @@ extern "C" const char* b2s_last_error(const b2s_ctx* ctx){ return ctx? ctx->err.
 extern "C" int b2s_get_params(const b2s_ctx* ctx, b2s_params* out){ if(!ctx||!out)return B2S_ERR_ARG; *out=ctx->prm; return B2S_OK; }
 extern "C" int b2s_get_stream(b2s_ctx* ctx, void** s){ if(!ctx||!s)return B2S_ERR_ARG; *s=(void*)ctx->stream; return B2S_OK; }
 extern "C" int b2s_launch_count(b2s_ctx* ctx, uint64_t* l, int reset){ if(!ctx)return B2S_ERR_ARG; if(l)*l=ctx->launches; if(reset)ctx->launches=0; return B2S_OK; }
-extern "C" int b2s_set_interaction_variant(b2s_ctx* ctx, int v){ if(!ctx||(v!=0&&v!=3&&v!=4))return B2S_ERR_ARG; ctx->variant=v; return B2S_OK; }
+extern "C" int b2s_set_interaction_variant(b2s_ctx* ctx, int v){ if(!ctx||(v!=0&&v!=3&&v!=4&&v!=5))return B2S_ERR_ARG; ctx->variant=v; return B2S_OK; }
 
 // Copies DivState+StepState to pinned memory, synchronises, refreshes the host mirrors and checks device flags.
 int b2s_sync_info(b2s_ctx* ctx){

@@ -215,7 +215,7 @@ int b2s_forces_fluid_only(b2s_ctx* ctx){
   const uint32_t npf=(ctx->np_host>ctx->npb_host? ctx->np_host-ctx->npb_host: 0u);
   if(!npf)return B2S_OK;
   if(ctx->variant==3 && ctx->np_host<(1u<<26))return b2s_forces_defer_launch(ctx,g);   // queue entries hold 26-bit indices
-  if(ctx->variant==4 && b2s_forces_pair2_supported(ctx->cte))return b2s_forces_pair2_launch(ctx,g);
+  if((ctx->variant==4 || ctx->variant==5) && b2s_forces_pair2_supported(ctx->cte))return b2s_forces_pair2_launch(ctx,g);
   fluid_kernel_t k=b2s_pick_fluid_gather(ctx->cte);
   k<<<b2s_blocks(npf,F_BS),F_BS,0,ctx->stream>>>(g,ctx->cte); B2S_LAUNCHED(ctx);
   return B2S_OK;

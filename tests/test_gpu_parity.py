@@ -69,7 +69,7 @@ def _check_forces(ctx, g, p, label, report, wide=False):
     assert e["acemax"] < ta and e["velmax"] < 1e-4 and e["viscdtmax"] < 1e-3, (label, e)
 
 
-@pytest.mark.parametrize("variant", [0, 3, 4])
+@pytest.mark.parametrize("variant", [0, 3, 4, 5])
 @pytest.mark.parametrize("fx", FIXTURES)
 def test_golden_reference_parity(fx, variant, tmp_path, built_lib):
     meta = json.load(open(os.path.join(H.GOLDEN, fx, "fixture.json")))
