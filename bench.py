@@ -29,9 +29,9 @@ METRIC = "particle-steps/sec (whole box) at 1/2/4/8 B200; interaction-kernel roo
 UNIT = "particle-steps/s"
 OPTIONS = "-symplectic -wendland -viscoart:0.1 -ddt:2 -ddtvalue:0.1 -dbc -cellmode:half" + os.environ.get("B2S_BENCH_EXTRA_OPTS", "")
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the fluid interaction kernel at the 10M-particle
-# workload, from the `ncu --set full` capture summarised in profiles/r01b_ncu_forces_pair2_10M.txt (449.6 MB + 139.7 MB);
+# workload, from the `ncu --set full` capture summarised in profiles/r01c_ncu_forces_pair2_v5_10M.txt (451.0 MB + 145.3 MB);
 # scaled by the fluid count when the bench runs another size
-NCU_TRAFFIC_BYTES, NCU_TRAFFIC_NPF = 589276160, 9281220
+NCU_TRAFFIC_BYTES, NCU_TRAFFIC_NPF = 596275200, 9281220
 NP_TARGET = int(os.environ.get("B2S_BENCH_NP", "10000000"))
 CPU_SAMPLE_NP = int(os.environ.get("B2S_BENCH_CPU_NP", "1000000"))
 # flop model of SURVEY 8(d): per checked pair 16 flop, per real pair (r<2h) 90 flop
@@ -369,7 +369,7 @@ def main():
         gbs_step = BYTES_STEP * np_total / (secs / a.steps) / 1e9
         roofline = {"kernel": (f"k_forces_fluid_pair2 (fluid<-fluid+bound interaction, variant {a.variant})" if a.variant in (4, 5) else "k_forces_fluid_gather (fluid<-fluid+bound interaction)"), "bound": "fp32", "achieved": tf_ach, "peak": fp32_peak,
                     "unit": "TFLOP/s", "frac": tf_ach / fp32_peak, "traffic": int(NCU_TRAFFIC_BYTES * npf / NCU_TRAFFIC_NPF),
-                    "traffic_note": "dram__bytes_read.sum+dram__bytes_write.sum per launch from profiles/r01b_ncu_forces_pair2_10M.txt (ncu --set full), scaled by fluid count; algorithmic bytes = 50 B x fluid particles",
+                    "traffic_note": "dram__bytes_read.sum+dram__bytes_write.sum per launch from profiles/r01c_ncu_forces_pair2_v5_10M.txt (ncu --set full), scaled by fluid count; algorithmic bytes = 50 B x fluid particles",
                     "peak_source": "148 SM x 128 FP32 lanes x 2 x clocks.max.sm (non-tensor FP32 issue; tensor cores do not apply to pairwise SPH)",
                     "ms_per_launch": ms_k, "pairs_checked": chk, "pairs_real": real, "flop_model": "16*checked + 90*real (SURVEY 8d)",
                     "share_of_step": 2 * ms_k / (secs / a.steps * 1e3),

@@ -273,8 +273,9 @@ int b2s_launch_count(b2s_ctx* ctx, uint64_t* launches, int reset);
 int b2s_get_stream(b2s_ctx* ctx, void** stream_out);
 /* Selects the fluid interaction kernel variant: 0 = gather (one thread per particle, reference summation order; default),
  * 3 = gather with deferred pair bodies (csrc/forces_defer.cu; experimental, used below 2^26 particles; bit-identical to 0),
- * 4 = two hits per lane in packed FP32 with FP16 pre-filter (csrc/forces_pair2.cu; fastest; Wendland + artificial viscosity
- * without floating bodies, other configurations run variant 0; equal to 0 within summation rounding).
+ * 4 = two hits per lane in packed FP32 with FP16 pre-filter (csrc/forces_pair2.cu; Wendland + artificial viscosity
+ * without floating bodies, other configurations run variant 0; equal to 0 within summation rounding),
+ * 5 = 4 with every neighbour row processed together with its point mirror (fastest; same scope and tolerance as 4).
  * Other values: B2S_ERR_ARG. */
 int b2s_set_interaction_variant(b2s_ctx* ctx, int variant);
 
