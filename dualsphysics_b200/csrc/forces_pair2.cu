@@ -126,8 +126,8 @@ __device__ __forceinline__ void pair2_body(const DevCte& c,f2 drx,f2 dry,f2 drz,
 // that sits close to one side of its cell has many hits in one of the two rows and few in the other, so the sum is much flatter
 // across the lanes of a warp than either count and fewer rounds are lost to the lane with most hits (tools/analyze_rounds.py:
 // 121 -> 103 rounds per particle).  Hits are still paired inside a row, so a round needs one set of row constants.
-template<int TDENS,int ROWMODE>
-__global__ void __launch_bounds__(P2_BS,P2_MINB) k_forces_fluid_pair2(ForcesArgs g, const __grid_constant__ DevCte c)
+template<int TDENS,int ROWMODE,int MINB>
+__global__ void __launch_bounds__(P2_BS,MINB) k_forces_fluid_pair2(ForcesArgs g, const __grid_constant__ DevCte c)
 {
   const DivState* ds=g.ds;
   const uint32_t npb=ds->npb, np=ds->np;
@@ -481,20 +481,16 @@ int b2s_forces_pair2_launch(b2s_ctx* ctx, const ForcesArgs& g){
   const DevCte& c=ctx->cte;
   const uint32_t npf=ctx->np_host-ctx->npb_host;
   const unsigned gb=b2s_blocks(npf,P2_BS);
-  if(ctx->variant==5){   // mirror-row pairing
-    switch(c.tdensity){
-      case B2S_DDT_NONE:      k_forces_fluid_pair2<B2S_DDT_NONE,1><<<gb,P2_BS,0,ctx->stream>>>(g,c); break;
-      case B2S_DDT_MOLTENI:   k_forces_fluid_pair2<B2S_DDT_MOLTENI,1><<<gb,P2_BS,0,ctx->stream>>>(g,c); break;
-      case B2S_DDT_FOURTAKAS: k_forces_fluid_pair2<B2S_DDT_FOURTAKAS,1><<<gb,P2_BS,0,ctx->stream>>>(g,c); break;
-      default:                k_forces_fluid_pair2<B2S_DDT_FOURTAKASFULL,1><<<gb,P2_BS,0,ctx->stream>>>(g,c); break;
-    }
-  }
-  else switch(c.tdensity){
-    case B2S_DDT_NONE:      k_forces_fluid_pair2<B2S_DDT_NONE,0><<<gb,P2_BS,0,ctx->stream>>>(g,c); break;
-    case B2S_DDT_MOLTENI:   k_forces_fluid_pair2<B2S_DDT_MOLTENI,0><<<gb,P2_BS,0,ctx->stream>>>(g,c); break;
-    case B2S_DDT_FOURTAKAS: k_forces_fluid_pair2<B2S_DDT_FOURTAKAS,0><<<gb,P2_BS,0,ctx->stream>>>(g,c); break;
-    default:                k_forces_fluid_pair2<B2S_DDT_FOURTAKASFULL,0><<<gb,P2_BS,0,ctx->stream>>>(g,c); break;
-  }
+  #define P2_LAUNCH(RM,MB) switch(c.tdensity){ \
+    case B2S_DDT_NONE:      k_forces_fluid_pair2<B2S_DDT_NONE,RM,MB><<<gb,P2_BS,0,ctx->stream>>>(g,c); break; \
+    case B2S_DDT_MOLTENI:   k_forces_fluid_pair2<B2S_DDT_MOLTENI,RM,MB><<<gb,P2_BS,0,ctx->stream>>>(g,c); break; \
+    case B2S_DDT_FOURTAKAS: k_forces_fluid_pair2<B2S_DDT_FOURTAKAS,RM,MB><<<gb,P2_BS,0,ctx->stream>>>(g,c); break; \
+    default:                k_forces_fluid_pair2<B2S_DDT_FOURTAKASFULL,RM,MB><<<gb,P2_BS,0,ctx->stream>>>(g,c); break; }
+  // variant 5 = mirror-row pairing.  Builds for 6 and 8 resident blocks per SM were timed too (80 registers: 11.75 ms, 64 registers
+  // with 400 bytes of spills: 11.46 ms, against 11.42 ms at 7 blocks / 72 registers; profiles/r01_pair2_tuning.txt)
+  if(ctx->variant==5){ P2_LAUNCH(1,P2_MINB) }
+  else{ P2_LAUNCH(0,P2_MINB) }
+  #undef P2_LAUNCH
   B2S_LAUNCHED(ctx);
   B2S_CUDA(ctx,cudaGetLastError());
   return B2S_OK;
