@@ -68,7 +68,7 @@ struct b2s_sim {
   unsigned np0;
   std::vector<uint32_t> slab_cuts; uint32_t slab_maxplane;   // slab loading (b2s_sim_load_slab)
   std::string runcode, date; unsigned part_nstep0; double part_time0, part_dtmin, part_dtmax;   // PART header / PartInfo statistics
-  b2s_sim():initial_saved(false),head_saved(false),partbegin(0),partbeginfirst(0),partbegintime(0),partbegindtpre(0),slab_maxplane(0),part_nstep0(0),part_time0(0),part_dtmin(DBL_MAX),part_dtmax(0),ctx(NULL),timemax(0),timepart(0),timepartnext(0),part(0),nstepsbreak(0),svallsteps(false),svposdouble(false),svdata(true),np0(0){
+  b2s_sim():ctx(NULL),initial_saved(false),head_saved(false),partbegin(0),partbeginfirst(0),partbegintime(0),partbegindtpre(0),timemax(0),timepart(0),timepartnext(0),part(0),nstepsbreak(0),svallsteps(false),svposdouble(false),svdata(true),np0(0),slab_maxplane(0),part_nstep0(0),part_time0(0),part_dtmin(DBL_MAX),part_dtmax(0){
     memset(&prm,0,sizeof(prm));
     // RunCode (8 random characters) and Date like JSph::CalcRunCode / fun::GetDateTime
     const time_t now=time(NULL); char buf[64]; strftime(buf,sizeof(buf),"%d-%m-%Y %H:%M:%S",localtime(&now)); date=buf;
@@ -250,8 +250,10 @@ static void load_case(b2s_sim* s,const std::string& options){
     if(t==1)b.refmotion=unsigned(atoi(c->attr("refmotion","0").c_str()));
     if(t==2){
       const XmlNode* e;
-      if(!(e=c->child("massbody")))throw std::runtime_error("floating: massbody missing"); b.massbody=todouble(e->attr("value"));
-      if(!(e=c->child("masspart")))throw std::runtime_error("floating: masspart missing"); b.masspart=todouble(e->attr("value"));
+      if(!(e=c->child("massbody")))throw std::runtime_error("floating: massbody missing");
+      b.massbody=todouble(e->attr("value"));
+      if(!(e=c->child("masspart")))throw std::runtime_error("floating: masspart missing");
+      b.masspart=todouble(e->attr("value"));
       if(!read_xyz(c->child("center"),b.center))throw std::runtime_error("floating: center missing");
       e=c->child("inertia"); if(!e)throw std::runtime_error("floating: inertia missing");
       if(e->has("x")&&e->has("y")&&e->has("z")){ double v[3]; read_xyz(e,v); b.inertia[0]=v[0]; b.inertia[4]=v[1]; b.inertia[8]=v[2]; }
@@ -689,8 +691,10 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
     if(r)throw std::runtime_error(std::string("damping zone failed: ")+b2s_last_error(s->ctx));
   }
   for(auto& g:s->gauges){
-    if(g.computedt<0)g.computedt=s->timepart;  if(g.computeend<0)g.computeend=s->timemax;     // JGaugeSystem::ResetCfgDefault
-    if(g.outputdt<0)g.outputdt=s->timepart;    if(g.outputend<0)g.outputend=s->timemax;
+    if(g.computedt<0)g.computedt=s->timepart;     // JGaugeSystem::ResetCfgDefault
+    if(g.computeend<0)g.computeend=s->timemax;
+    if(g.outputdt<0)g.outputdt=s->timepart;
+    if(g.outputend<0)g.outputend=s->timemax;
     if(g.type==1)r=b2s_gauge_add_velocity(s->ctx,g.point,&g.id);
     else if(g.type==4)r=b2s_gauge_add_maxz(s->ctx,g.point0,g.height,g.distlimit,&g.id);
     else if(g.type==3){
