@@ -228,7 +228,6 @@ static void load_case(b2s_sim* s,const std::string& options){
     }
   }
   if(opt_boundary>0){ p.tboundary=(opt_boundary==2? B2S_BC_MDBC: B2S_BC_DBC); p.slipmode=(opt_boundary==2? opt_slip: 0); }
-  if(p.tboundary==B2S_BC_MDBC && p.slipmode>=B2S_SLIP_NOSLIP && p.casenfloat)throw std::runtime_error("mDBC2 (SlipMode 2/3) with floating bodies is not supported by this build");
   if(p.tboundary==B2S_BC_MDBC && p.slipmode>=B2S_SLIP_NOSLIP && p.viscoboundfactor!=1.f)throw std::runtime_error("ViscoBoundFactor must be 1 with mDBC2 (JSph.cpp:1603)");
   if(p.tboundary==B2S_BC_MDBC && (p.slipmode<1 || p.slipmode>3))throw std::runtime_error("mDBC slip mode is invalid; use SlipMode=1");
   p.mdbc_corrector=(p.slipmode>=B2S_SLIP_NOSLIP)? 1: 0;   // MdbcCorrector (JSph.cpp:899)
@@ -281,6 +280,7 @@ static void load_case(b2s_sim* s,const std::string& options){
     s->blocks.push_back(b);
   }
   p.casenfixed=cnt[0]; p.casenmoving=cnt[1]; p.casenfloat=cnt[2]; p.casenfluid=cnt[3]; p.casenp=cnt[0]+cnt[1]+cnt[2]+cnt[3];
+  if(p.tboundary==B2S_BC_MDBC && p.slipmode>=B2S_SLIP_NOSLIP && p.casenfloat)throw std::runtime_error("mDBC2 (SlipMode 2/3) with floating bodies is not supported by this build");
   { const unsigned np=unsigned(strtoul(pa->attr("np","0").c_str(),NULL,10)), nb=unsigned(strtoul(pa->attr("nb","0").c_str(),NULL,10)), nbf=unsigned(strtoul(pa->attr("nbf","0").c_str(),NULL,10));
     if(np!=p.casenp || nb!=p.casenp-p.casenfluid || nbf!=p.casenfixed)throw std::runtime_error("The amount of particles does not match the header."); }
   // -- gauges (JGaugeSystem::LoadXml "case.execution.special.gauges"): velocity and swl
