@@ -36,6 +36,7 @@ class Cte(C.Structure):
         ("cs0", C.c_double), ("cflnumber", C.c_double), ("dtmin", C.c_double),
         ("domposmin", C.c_double * 3), ("maprealposmin", C.c_double * 3), ("maprealsize", C.c_double * 3),
         ("domcellcode", C.c_uint32), ("domcells", C.c_uint32 * 3),
+        ("shiftmode", C.c_int32), ("shiftcoef", C.c_float), ("shifttfs", C.c_float), ("dp", C.c_float),
     ]
 
 
@@ -92,6 +93,7 @@ def cte_from_params(p) -> Cte:
         c.domcells[k] = p.domcells[k]
     c.cs0, c.cflnumber, c.dtmin = p.cs0, p.cflnumber, p.dtmin
     c.domcellcode = p.domcellcode
+    c.shiftmode, c.shiftcoef, c.shifttfs, c.dp = p.shiftmode, p.shiftcoef, p.shifttfs, p.dp
     return c
 
 
@@ -103,7 +105,7 @@ class OracleSim:
     """Whole-step CPU oracle over numpy arrays (cell-sorted order, like the solver's state)."""
 
     def __init__(self, cte: Cte, idp, code, pos, velrho, npb: int, dtini: float, verletsteps: int = 40,
-                 ftomassp=None, boundnor=None, mdbc_corrector=False):
+                 ftomassp=None, boundnor=None, mdbc_corrector=False, damping=None):
         self.L = lib()
         self.c = cte
         self.idp = np.ascontiguousarray(idp, np.uint32).copy()
@@ -124,6 +126,8 @@ class OracleSim:
                 bn = np.asarray(boundnor, np.float32).reshape(-1, 3)
                 self.boundnor[:bn.shape[0]] = bn
         self.mdbc_corrector = mdbc_corrector
+        # damping zones: (nzones, 64) doubles in the layout of orc_damping (built by damping_zones() below)
+        self.damping = None if damping is None or len(damping) == 0 else np.ascontiguousarray(damping, np.float64).reshape(-1, 64)
         self.symplectic_dtpre = float(dtini)
         self.timestep, self.nstep, self.verletstep, self.verletsteps = 0.0, 0, 0, verletsteps
         self.div = Div()
@@ -174,6 +178,21 @@ class OracleSim:
         self.velmax, self.acemax, self.viscdtmax = vm.value, am.value, vd.value
         return self.L.orc_dtvariable(C.byref(self.c), vm.value, am.value, vd.value)
 
+    def shifting(self, dt):
+        """RunShifting(dt) (JSphCpuSingle.cpp:881,924): displacement of the coming position update, or None."""
+        if not self.c.shiftmode:
+            return None
+        sh = np.zeros((self.np_, 4), np.float32)
+        self.L.orc_shifting(C.byref(self.c), C.byref(self.div), _p(self.begincell), _p(self.dcell), _p(self.pos), _p(self.velrho),
+                            _p(self.code), None if self.ftomassp is None else _p(self.ftomassp), C.c_double(dt), _p(sh))
+        return sh
+
+    def run_damping(self, dt):
+        """RunDamping(dt) (JSphCpuSingle.cpp:885,928)."""
+        if self.damping is not None:
+            self.L.orc_damping(self.np_, self.npb, C.c_double(dt), int(self.damping.shape[0]), _p(self.damping), _p(self.pos),
+                               _p(self.code), _p(self.velrho))
+
     def step(self) -> float:
         n = self.np_
         if self.tstep == 2:
@@ -186,8 +205,11 @@ class OracleSim:
             self.celldiv()
             n = self.np_
             dt_c = self.interaction(corrector=True)
+            sh = self.shifting(dt)
             self.L.orc_symplectic_corr(C.byref(self.c), n, self.npb, C.c_double(dt), _p(self.pospre), _p(self.velrhopre),
-                                       _p(self.ar), _p(self.ace), _p(self.pos), _p(self.velrho), _p(self.dcell), _p(self.code))
+                                       _p(self.ar), _p(self.ace), _p(self.pos), _p(self.velrho), _p(self.dcell), _p(self.code),
+                                       None if sh is None else _p(sh))
+            self.run_damping(dt)
             self.pospre = self.velrhopre = None
             self.symplectic_dtpre = min(dt_p, dt_c)
             self.dt_p, self.dt_c = dt_p, dt_c
@@ -199,14 +221,83 @@ class OracleSim:
                 self.verletstep = 0
             v2 = self.velrho if euler else self.velrhom1
             new = np.zeros_like(self.velrho[:n])
+            sh = self.shifting(dt)
             self.L.orc_verlet(C.byref(self.c), n, self.npb, C.c_double(dt), 1 if euler else 0, _p(self.velrho), _p(v2),
-                              _p(self.ar), _p(self.ace), _p(self.pos), _p(self.dcell), _p(self.code), _p(new))
+                              _p(self.ar), _p(self.ace), _p(self.pos), _p(self.dcell), _p(self.code), _p(new),
+                              None if sh is None else _p(sh))
             self.velrhom1 = self.velrho[:n]
             self.velrho = new
+            self.run_damping(dt)
         self.celldiv()
         self.timestep += dt
         self.nstep += 1
         return dt
+
+
+def damping_zones(xml_damping) -> np.ndarray:
+    """<special><damping> (an ElementTree element) -> (nzones, 64) doubles for orc_damping: the derived values of
+    JDsDampingOp_Plane::ReadXml / ComputeDomPlanes and JDsDampingOp_Box::ReadXml (JDsDamping.cpp:58-131,345-391)."""
+    out = []
+    if xml_damping is None:
+        return np.zeros((0, 64))
+    f3 = lambda e: np.array([float(e.get("x")), float(e.get("y")), float(e.get("z"))])  # noqa: E731
+    for e in xml_damping:
+        if e.tag.startswith("_") or e.get("active", "true").lower() in ("false", "0"):
+            continue
+        z = np.zeros(64)
+        z[1] = np.float32(e.find("overlimit").get("value"))
+        z[2] = np.float32(e.find("redumax").get("value")) if e.find("redumax") is not None else 10.0
+        fx = e.find("factorxyz")
+        z[3:6] = [np.float32(fx.get(a, 1)) for a in "xyz"] if fx is not None else 1.0
+        if e.tag == "dampingzone":
+            lmin, lmax = f3(e.find("limitmin")), f3(e.find("limitmax"))
+            vec = lmax - lmin
+            dist = np.sqrt((vec * vec).sum())
+            u = vec / dist
+            z[6:9], z[9], z[10] = u, -(u * lmin).sum(), np.float32(dist)
+            dom = e.find("domain")
+            if dom is not None:
+                z[11], z[12], z[13] = 1, float(dom.get("zmin")), float(dom.get("zmax"))
+                vp = [np.array([float(dom.find(f"point{k}").get("x")), float(dom.find(f"point{k}").get("y"))]) for k in (1, 2, 3, 4)]
+                ang = [0.0] + [np.degrees(np.arctan2(vp[0][1] - vp[c][1], vp[0][0] - vp[c][0])) % 360.0 for c in (1, 2, 3)]
+                order = [0] + sorted((1, 2, 3), key=lambda c: ang[c])
+                vp = [vp[c] for c in order]
+                for c in range(4):
+                    a, b = vp[c], vp[(c + 1) % 4]
+                    p1, p2, p3 = np.array([a[0], a[1], 0.0]), np.array([b[0], b[1], 0.0]), np.array([b[0], b[1], 1.0])
+                    v = np.cross(p2 - p1, p3 - p1)
+                    z[14 + 4 * c:18 + 4 * c] = [v[0], v[1], v[2], -(v * p1).sum()]
+        elif e.tag == "dampingbox":
+            m1, m2 = f3(e.find("limitmin").find("pointini")), f3(e.find("limitmin").find("pointend"))
+            x1, x2 = f3(e.find("limitmax").find("pointini")), f3(e.find("limitmax").find("pointend"))
+            dirs = e.find("directions").get("value", "").replace(",", " ").lower().split() if e.find("directions") is not None else []
+            bits = {"top": 1, "bottom": 2, "left": 4, "right": 8, "front": 16, "back": 32, "all": 63}
+            d = 63
+            if dirs:
+                d = 0
+                for t in dirs:
+                    add = not t.startswith("-")
+                    t = t.lstrip("+-")
+                    d = (d | bits[t]) if add else (d & (63 ^ bits[t]))
+            o1, o2 = x1 - z[1], x2 + z[1]
+            low, high = (4, 16, 2), (8, 32, 1)      # x: left/right, y: front/back, z: bottom/top
+            for k in range(3):
+                if not d & high[k]:
+                    x2[k] = o2[k] = m2[k]
+                if not d & low[k]:
+                    x1[k] = o1[k] = m1[k]
+            b1, b2 = m1 - x1, x2 - m2
+            for k in range(3):
+                if not d & high[k] or b2[k] < 0:
+                    b2[k] = 0
+                if not d & low[k] or b1[k] < 0:
+                    b1[k] = 0
+            z[0] = 1
+            z[6:9], z[9:12], z[12:15], z[15:18], z[18:21], z[21:24], z[24:27], z[27:30] = m1, m2, x1, x2, o1, o2, b1, b2
+        else:
+            raise ValueError(f"damping <{e.tag}> is not restated")
+        out.append(z)
+    return np.array(out).reshape(-1, 64)
 
 
 def run_ref_probe(casepath: str, dirout: str, nsteps: int, options=(), dumplevel: int = 2, threads: int | None = None) -> str:

@@ -25,6 +25,7 @@ typedef uint16_t typecode;
 #define CODE_OUTPOS      0x8000u
 #define CODE_OUTRHO      0xA000u
 #define CODE_MASKTYPE    0x1800u
+#define CODE_TYPE_FIXED    0x0000u
 #define CODE_TYPE_FLOATING 0x1000u
 #define CODE_TYPE_FLUID  0x1800u
 #define CODE_MASKVALUE   0x07ffu
@@ -48,6 +49,8 @@ typedef struct orc_cte {
   double cs0, cflnumber, dtmin;
   double domposmin[3], maprealposmin[3], maprealsize[3];
   uint32_t domcellcode, domcells[3];
+  int32_t shiftmode;               /* TpShifting 0-3 (JSph.cpp:744-758) */
+  float shiftcoef, shifttfs, dp;   /* ShiftCoef, ShiftTFS, float(Dp) */
 } orc_cte;
 
 /* Result of a cell divide (JCellDivCpu members). */
@@ -280,7 +283,7 @@ static void forces_fluid_pass(const orc_cte* c, const orc_div* d, int boundp2, f
         }
       }
     }
-    if(arp1||ax||ay||az||visc){
+    if(c->shiftmode||arp1||ax||ay||az||visc){   /* `if(shift||arp1||...)`, JSphCpu.cpp:1084 */
       if(c->tdensity!=0)delta[p1]=(delta[p1]==FLT_MAX || deltap1==FLT_MAX? FLT_MAX: delta[p1]+deltap1);
       ar[p1]+=arp1;
       ace[3*p1]+=ax; ace[3*p1+1]+=ay; ace[3*p1+2]+=az;
@@ -440,7 +443,7 @@ void orc_symplectic_pre(const orc_cte* c, uint32_t np, uint32_t npb, double dt, 
 
 /* JSphCpu::ComputeSymplecticCorr (JSphCpu.cpp:1856-2022): velrho holds the predicted state on entry. */
 void orc_symplectic_corr(const orc_cte* c, uint32_t np, uint32_t npb, double dt, const double* pospre, const float* velrhopre,
-  const float* ar, const float* ace, double* pos, float* velrho, uint32_t* dcell, typecode* code)
+  const float* ar, const float* ace, double* pos, float* velrho, uint32_t* dcell, typecode* code, const float* shiftpos)
 {
   const double dt05=dt*.5;
   for(uint32_t p=0;p<np;p++){
@@ -452,7 +455,8 @@ void orc_symplectic_corr(const orc_cte* c, uint32_t np, uint32_t npb, double dt,
       const float nx=(float)((double)vp[0]+((double)ace[3*(size_t)p]  +c->gravity[0])*dt);
       const float ny=(float)((double)vp[1]+((double)ace[3*(size_t)p+1]+c->gravity[1])*dt);
       const float nz=(float)((double)vp[2]+((double)ace[3*(size_t)p+2]+c->gravity[2])*dt);
-      const double dx=((double)vp[0]+(double)nx)*dt05, dy=((double)vp[1]+(double)ny)*dt05, dz=((double)vp[2]+(double)nz)*dt05;
+      double dx=((double)vp[0]+(double)nx)*dt05, dy=((double)vp[1]+(double)ny)*dt05, dz=((double)vp[2]+(double)nz)*dt05;
+      if(shiftpos){ dx+=(double)shiftpos[4*(size_t)p]; dy+=(double)shiftpos[4*(size_t)p+1]; dz+=(double)shiftpos[4*(size_t)p+2]; }   /* JSphCpu.cpp:1936-1940 */
       const int outrho=(rhonew<c->rhopoutmin || rhonew>c->rhopoutmax);
       velrho[4*(size_t)p]=nx; velrho[4*(size_t)p+1]=ny; velrho[4*(size_t)p+2]=nz; velrho[4*(size_t)p+3]=rhonew;
       update_pos(c,pospre[3*(size_t)p],pospre[3*(size_t)p+1],pospre[3*(size_t)p+2],dx,dy,dz,outrho,p,pos,dcell,code);
@@ -466,7 +470,7 @@ void orc_symplectic_corr(const orc_cte* c, uint32_t np, uint32_t npb, double dt,
 
 /* JSphCpu::ComputeVerlet (JSphCpu.cpp:1523-1680): new values -> velrhonew; velrho1=v(n), velrho2=v(n-1) or v(n) on Euler steps. */
 void orc_verlet(const orc_cte* c, uint32_t np, uint32_t npb, double dt, int euler, const float* velrho1, const float* velrho2,
-  const float* ar, const float* ace, double* pos, uint32_t* dcell, typecode* code, float* velrhonew)
+  const float* ar, const float* ace, double* pos, uint32_t* dcell, typecode* code, float* velrhonew, const float* shiftpos)
 {
   const double dt2=(euler? dt: dt+dt), dt205=0.5*dt*dt;
   for(uint32_t p=0;p<np;p++){
@@ -476,13 +480,123 @@ void orc_verlet(const orc_cte* c, uint32_t np, uint32_t npb, double dt, int eule
     if(p<npb){ o[0]=o[1]=o[2]=0; o[3]=(rhonew<c->rhopzero? c->rhopzero: rhonew); }
     else if(!c->use_floating || CODE_TYPE(code[p])==CODE_TYPE_FLUID){
       const double agx=(double)ace[3*(size_t)p]+(double)c->gravity[0], agy=(double)ace[3*(size_t)p+1]+(double)c->gravity[1], agz=(double)ace[3*(size_t)p+2]+(double)c->gravity[2];
-      const double dx=(double)v1[0]*dt+agx*dt205, dy=(double)v1[1]*dt+agy*dt205, dz=(double)v1[2]*dt+agz*dt205;
+      double dx=(double)v1[0]*dt+agx*dt205, dy=(double)v1[1]*dt+agy*dt205, dz=(double)v1[2]*dt+agz*dt205;
+      if(shiftpos){ dx+=(double)shiftpos[4*(size_t)p]; dy+=(double)shiftpos[4*(size_t)p+1]; dz+=(double)shiftpos[4*(size_t)p+2]; }   /* JSphCpu.cpp:1543-1547 */
       const int outrho=(rhonew<c->rhopoutmin || rhonew>c->rhopoutmax);
       o[0]=(float)((double)v2[0]+agx*dt2); o[1]=(float)((double)v2[1]+agy*dt2); o[2]=(float)((double)v2[2]+agz*dt2); o[3]=rhonew;
       update_pos(c,pos[3*(size_t)p],pos[3*(size_t)p+1],pos[3*(size_t)p+2],dx,dy,dz,outrho,p,pos,dcell,code);
     }
     else{ o[0]=v1[0]; o[1]=v1[1]; o[2]=v1[2]; o[3]=(rhonew<c->rhopzero? c->rhopzero: rhonew); }
     memcpy(velrhonew+4*(size_t)p,o,16);
+  }
+}
+
+/* Standard shifting without zones: the shiftposfs sums of the pair loop (JSphCpu.cpp:767-779,848,942-950: fluid neighbours,
+ * then boundary neighbours, one running sum) followed by JSphShifting::RunCpu (JSphShifting.cpp:390-423).  shiftpos = 4 floats per
+ * particle: displacement xyz of the coming position update, w = the free-surface divergence. */
+void orc_shifting(const orc_cte* c, const orc_div* d, const uint32_t* begincell, const uint32_t* dcell, const double* pos,
+  const float* velrho, const typecode* code, const float* ftomassp, double dt, float* shiftpos)
+{
+  const double coefumagn=dt*(double)c->shiftcoef*(double)c->kernelh;
+  const double coeftfs=3.0-(double)c->shifttfs;
+  const float maxdist=(float)((double)c->dp*0.1);
+  memset(shiftpos,0,sizeof(float)*4*(size_t)d->np);
+  #pragma omp parallel for schedule(guided)
+  for(int64_t p1=(int64_t)d->npb;p1<(int64_t)d->np;p1++){
+    float sx=0,sy=0,sz=0,sw=0;
+    if(c->use_floating && CODE_TYPE(code[p1])==CODE_TYPE_FLOATING)sx=FLT_MAX;
+    const double px=pos[3*p1],py=pos[3*p1+1],pz=pos[3*p1+2];
+    const ngs_t r=ngs_init(c,d,dcell[p1]);
+    for(int boundp2=0;boundp2<2 && sx!=FLT_MAX;boundp2++){
+      const uint32_t* beg=begincell+(boundp2? 0: d->box_fluid);
+      for(int z=r.zini;z<r.zfin;z++)for(int y=r.yini;y<r.yfin;y++){
+        const uint32_t pini=beg[r.xini+y*(int)d->ncx+z*(int)d->nsheet], pfin=beg[r.xfin+y*(int)d->ncx+z*(int)d->nsheet];
+        for(uint32_t p2=pini;p2<pfin;p2++){
+          const float drx=(float)(px-pos[3*(size_t)p2]), dry=(float)(py-pos[3*(size_t)p2+1]), drz=(float)(pz-pos[3*(size_t)p2+2]);
+          const float rr2=drx*drx+dry*dry+drz*drz;
+          if(rr2<=c->kernelsize2 && rr2>=ALMOSTZERO){
+            const float fac=kernel_fac(c,rr2);
+            const float frx=fac*drx,fry=fac*dry,frz=fac*drz;
+            float massp2=(boundp2? c->massbound: c->massfluid);
+            if(c->use_floating && CODE_TYPE(code[p2])==CODE_TYPE_FLOATING){
+              massp2=ftomassp[code[p2]&CODE_MASKVALUE];
+              if(c->shiftmode==1)sx=FLT_MAX;
+            }
+            if(sx!=FLT_MAX){
+              const float massrho=massp2/velrho[4*(size_t)p2+3];
+              const int noshift=(boundp2 && (c->shiftmode==1 || (c->shiftmode==2 && CODE_TYPE(code[p2])==CODE_TYPE_FIXED)));
+              sx=(noshift? FLT_MAX: sx+massrho*frx);
+              sy+=massrho*fry; sz+=massrho*frz;
+              sw-=massrho*(drx*frx+dry*fry+drz*frz);
+            }
+          }
+        }
+      }
+    }
+    float* o=shiftpos+4*(size_t)p1;
+    if(sx!=FLT_MAX){
+      const double vx=velrho[4*p1],vy=velrho[4*p1+1],vz=velrho[4*p1+2];
+      double umagn=coefumagn*sqrt(vx*vx+vy*vy+vz*vz);
+      if(c->shifttfs){
+        if(sw<c->shifttfs)umagn=0;
+        else umagn*=((double)sw-(double)c->shifttfs)/coeftfs;
+      }
+      const float dx=(float)((double)sx*umagn), dy=(float)((double)sy*umagn), dz=(float)((double)sz*umagn);
+      o[0]=(fabsf(dx)<maxdist? dx: (dx>=0? maxdist: -maxdist));
+      o[1]=(fabsf(dy)<maxdist? dy: (dy>=0? maxdist: -maxdist));
+      o[2]=(fabsf(dz)<maxdist? dz: (dz>=0? maxdist: -maxdist));
+      o[3]=sw;
+    }
+  }
+}
+
+/* Damping zones (JDsDampingOp_Plane/_Box::ComputeDampingCpu, JDsDamping.cpp:185-233,446-492), zones applied in list order.
+ * One zone = 64 doubles: [0] type (0 plane, 1 box), [1] overlimit, [2] redumax, [3..5] factorxyz,
+ *   plane: [6..9] plane a,b,c,d, [10] dist, [11] usedomain, [12] zmin, [13] zmax, [14..29] four lateral planes;
+ *   box:   [6..8] limmin1, [9..11] limmin2, [12..14] limmax1, [15..17] limmax2, [18..20] limover1, [21..23] limover2,
+ *          [24..26] boxsize1, [27..29] boxsize2   (all already derived like JDsDampingOp_Box::ReadXml, JDsDamping.cpp:345-391). */
+void orc_damping(uint32_t np, uint32_t npb, double dt, uint32_t nzones, const double* zones, const double* pos, const typecode* code, float* velrho)
+{
+  for(uint32_t k=0;k<nzones;k++){
+    const double* z=zones+64*(size_t)k;
+    const float over=(float)z[1], redumax=(float)z[2];
+    const float fx=(float)z[3], fy=(float)z[4], fz=(float)z[5];
+    for(uint32_t p=npb;p<np;p++){
+      if((code[p]&CODE_MASKSPECIAL)!=0 || CODE_TYPE(code[p])!=CODE_TYPE_FLUID)continue;
+      const double x=pos[3*(size_t)p], y=pos[3*(size_t)p+1], zz=pos[3*(size_t)p+2];
+      double fdis;
+      if(z[0]==0){
+        const float dist=(float)z[10];
+        const double vdis=z[6]*x+z[7]*y+z[8]*zz+z[9];
+        if(!(0<vdis && vdis<=(double)(dist+over)))continue;
+        if(z[11]!=0){
+          int in=(zz>=z[12] && zz<=z[13]);
+          for(int q=0;q<4 && in;q++){ const double* pl=z+14+4*q; in=(pl[0]*x+pl[1]*y+pl[2]*zz+pl[3]<=0); }
+          if(!in)continue;
+        }
+        fdis=(vdis>=(double)dist? 1.: vdis/(double)dist);
+      }
+      else{
+        const double *m1=z+6,*m2=z+9,*x1=z+12,*x2=z+15,*o1=z+18,*o2=z+21,*b1=z+24,*b2=z+27;
+        if(!(o1[0]<=x && o1[1]<=y && o1[2]<=zz && x<=o2[0] && y<=o2[1] && zz<=o2[2]))continue;
+        if(m1[0]<=x && m1[1]<=y && m1[2]<=zz && x<=m2[0] && y<=m2[1] && zz<=m2[2])continue;
+        fdis=1.;
+        if(x1[0]<=x && x1[1]<=y && x1[2]<=zz && x<=x2[0] && y<=x2[1] && zz<=x2[2]){
+          double f; fdis=0;
+          if(b2[2]){ f=(zz-m2[2])/b2[2]; if(f>fdis)fdis=f; }
+          if(b2[1]){ f=(y-m2[1])/b2[1]; if(f>fdis)fdis=f; }
+          if(b2[0]){ f=(x-m2[0])/b2[0]; if(f>fdis)fdis=f; }
+          if(b1[2]){ f=(m1[2]-zz)/b1[2]; if(f>fdis)fdis=f; }
+          if(b1[1]){ f=(m1[1]-y)/b1[1]; if(f>fdis)fdis=f; }
+          if(b1[0]){ f=(m1[0]-x)/b1[0]; if(f>fdis)fdis=f; }
+        }
+      }
+      const double redudt=dt*(fdis*fdis)*redumax;
+      double rx=1.-redudt*fx, ry=1.-redudt*fy, rz=1.-redudt*fz;
+      if(rx<0)rx=0; if(ry<0)ry=0; if(rz<0)rz=0;
+      float* v=velrho+4*(size_t)p;
+      v[0]=(float)(rx*v[0]); v[1]=(float)(ry*v[1]); v[2]=(float)(rz*v[2]);
+    }
   }
 }
 

@@ -66,6 +66,8 @@ def params_from_case(casepath: str, options: dict | None = None):
     p.dt_allparticles = 1 if int(prm.get("DtAllParticles", 0)) == 1 else 0
     p.rhopoutmin, p.rhopoutmax = float(prm.get("RhopOutMin", 700)), float(prm.get("RhopOutMax", 1300))
     p.cellmode_half = int(prm.get("_cellmode_half", 0))
+    p.shiftmode = int(prm.get("Shifting", 0))
+    p.shiftcoef, p.shifttfs = float(prm.get("ShiftCoef", -2)), float(prm.get("ShiftTFS", 0))
     pa = exe.find("particles")
     cnt = {"fixed": 0, "moving": 0, "floating": 0, "fluid": 0}
     blocks = []
@@ -120,8 +122,10 @@ def params_from_case(casepath: str, options: dict | None = None):
             ftmassp.append(float(node.find("masspart").get("value")))
     code = codeofid[idp]
     velrho = np.concatenate([data["Vel"], data["Rhop"][:, None]], axis=1).astype(np.float32)
+    sp = exe.find("special")
     arrays = {"idp": idp, "code": code, "pos": pos, "velrho": velrho, "boundnor": data.get("BoundNor"),
-              "ftmassp": np.array(ftmassp, np.float32)}
+              "ftmassp": np.array(ftmassp, np.float32),
+              "damping": orc.damping_zones(sp.find("damping") if sp is not None else None)}
     return p, arrays
 
 
@@ -130,7 +134,8 @@ def oracle_sim_from_case(casepath: str, options: dict | None = None) -> "orc.Ora
     cte = orc.cte_from_params(p)
     return orc.OracleSim(cte, a["idp"], a["code"], a["pos"], a["velrho"], npb=p.casenpb, dtini=p.dtini,
                          verletsteps=p.verletsteps, ftomassp=a["ftmassp"] if len(a["ftmassp"]) else None,
-                         boundnor=None if a["boundnor"] is None else 2.0 * np.asarray(a["boundnor"], np.float32))
+                         boundnor=None if a["boundnor"] is None else 2.0 * np.asarray(a["boundnor"], np.float32),
+                         damping=a["damping"])
 
 
 def rel_err(a, b, floor=None):
