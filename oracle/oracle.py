@@ -37,6 +37,8 @@ class Cte(C.Structure):
         ("domposmin", C.c_double * 3), ("maprealposmin", C.c_double * 3), ("maprealsize", C.c_double * 3),
         ("domcellcode", C.c_uint32), ("domcells", C.c_uint32 * 3),
         ("shiftmode", C.c_int32), ("shiftcoef", C.c_float), ("shifttfs", C.c_float), ("dp", C.c_float),
+        ("periactive", C.c_int32), ("pad0", C.c_int32), ("perinc", (C.c_double * 3) * 3),
+        ("mapposmin", C.c_double * 3), ("mapposmax", C.c_double * 3),
     ]
 
 
@@ -94,6 +96,10 @@ def cte_from_params(p) -> Cte:
     c.cs0, c.cflnumber, c.dtmin = p.cs0, p.cflnumber, p.dtmin
     c.domcellcode = p.domcellcode
     c.shiftmode, c.shiftcoef, c.shifttfs, c.dp = p.shiftmode, p.shiftcoef, p.shifttfs, p.dp
+    c.periactive = p.periactive
+    for k in range(3):
+        c.perinc[0][k], c.perinc[1][k], c.perinc[2][k] = p.perixinc[k], p.periyinc[k], p.perizinc[k]
+        c.mapposmin[k], c.mapposmax[k] = p.map_posmin[k], p.map_posmax[k]
     return c
 
 
@@ -139,8 +145,75 @@ class OracleSim:
         self.pospre = self.velrhopre = None
         self.celldiv()
 
+    _PER_ARRAYS = ("idp", "code", "dcell", "pos", "velrho", "velrhom1", "tau", "pospre", "velrhopre", "boundnor")
+
+    def periodic(self):
+        """JSphCpuSingle::RunPeriodic (JSphCpuSingle.cpp:416-504) with PeriodicMakeList / PeriodicDuplicate* (:210-372): the old
+        duplicates are marked to be ignored, new ones are appended behind the particles -- boundary then fluid; per type the axes
+        X, Y, Z; per axis first from the duplicates of this type made so far, then from the original particles; per particle the
+        +inc copy before the -inc copy.  That order decides the particle order inside the cells after the stable sort."""
+        c = self.c
+        n0, npb0 = self.np_, self.npb
+        for name in self._PER_ARRAYS:
+            a = getattr(self, name)
+            if a is not None:
+                setattr(self, name, a[:n0])
+        per = (self.code & 0xe000) == 0x2000
+        self.code[per] = (self.code[per] & 0x1fff) | 0x4000          # PeriodicIgnore
+        mapmin = np.array([c.mapposmin[k] for k in range(3)]); mapmax = np.array([c.mapposmax[k] for k in range(3)])
+        dommin = np.array([c.domposmin[k] for k in range(3)]); domcells = np.array([c.domcells[k] for k in range(3)], np.int64)
+        scell = np.float64(np.float32(c.scell))
+        dcc = int(c.domcellcode)
+        shx, shy = (dcc >> 10) & 31, (dcc >> 15) & 31
+        nper = [0, 0]
+        for ctype in (0, 1):
+            for ax in range(3):
+                if not (c.periactive >> ax) & 1:
+                    continue
+                inc = np.array([c.perinc[ax][k] for k in range(3)])
+                for cblock in (0, 1):
+                    ntot = self.idp.shape[0]
+                    idx = (np.arange(0, npb0) if ctype == 0 else np.arange(npb0, n0)) if cblock else np.arange(ntot - nper[ctype], ntot)
+                    if idx.size == 0:
+                        continue
+                    idx = idx[(self.code[idx] & 0xe000) <= 0x2000]
+                    ps = self.pos[idx]
+                    plus = np.all((mapmin <= ps + inc) & (ps + inc < mapmax), axis=1)
+                    minus = np.all((mapmin <= ps - inc) & (ps - inc < mapmax), axis=1)
+                    src = np.concatenate([idx[plus], idx[minus]])
+                    sign = np.concatenate([np.ones(int(plus.sum())), -np.ones(int(minus.sum()))])
+                    order = np.lexsort((-sign, src))                   # by particle, + before -
+                    src, sign = src[order], sign[order]
+                    if src.size == 0:
+                        continue
+                    newpos = self.pos[src] + sign[:, None] * inc
+                    cell = ((newpos - dommin) / scell).astype(np.uint32).astype(np.int64)   # unsigned((ps-DomPosMin)/Scell)
+                    cell = np.minimum(cell, domcells)                                     # PeriodicDuplicatePos: clamped to cellmax=DomCells
+                    newdcell = ((cell[:, 0] << shx) | (cell[:, 1] << shy) | cell[:, 2]).astype(np.uint32)
+                    for name in self._PER_ARRAYS:
+                        a = getattr(self, name)
+                        if a is None:
+                            continue
+                        if name == "pos":
+                            add = newpos
+                        elif name == "dcell":
+                            add = newdcell
+                        elif name == "code":
+                            add = ((a[src] & 0x1fff) | 0x2000).astype(np.uint16)
+                        else:
+                            add = a[src]
+                        setattr(self, name, np.ascontiguousarray(np.concatenate([a, add.astype(a.dtype)])))
+                    nper[ctype] += int(src.size)
+        self.np_ = int(self.idp.shape[0])
+        self.npb = npb0 + nper[0]      # bound-type particles entering the divide (the sort groups them by type)
+        if self.cellpart.shape[0] < self.np_:
+            self.cellpart = np.zeros(self.np_ + 1024, np.uint32)
+            self.sortpart = np.zeros(self.np_ + 1024, np.uint32)
+
     # RunCellDivide (JSphCpuSingle.cpp:497-586)
     def celldiv(self):
+        if self.c.periactive:
+            self.periodic()
         n = self.np_
         r = self.L.orc_celldiv(C.byref(self.c), n, self.npb, _p(self.dcell), _p(self.code), _p(self.cellpart),
                                _p(self.sortpart), _p(self.begincell), C.byref(self.div))
@@ -149,7 +222,7 @@ class OracleSim:
         for name in ("idp", "code", "dcell", "pos", "velrho", "velrhom1", "tau", "pospre", "velrhopre", "boundnor"):
             a = getattr(self, name)
             if a is not None:
-                setattr(self, name, np.ascontiguousarray(a[:n][sp]))
+                setattr(self, name, np.ascontiguousarray(a[:n][sp][:int(self.div.np)]))   # excluded / ignored particles sort to the end: dropped
         self.npf_out_total += int(self.div.npf_out)
         self.np_, self.npb = int(self.div.np), int(self.div.npb)
         if self.div.npb_out:

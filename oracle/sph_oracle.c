@@ -51,6 +51,9 @@ typedef struct orc_cte {
   uint32_t domcellcode, domcells[3];
   int32_t shiftmode;               /* TpShifting 0-3 (JSph.cpp:744-758) */
   float shiftcoef, shifttfs, dp;   /* ShiftCoef, ShiftTFS, float(Dp) */
+  int32_t periactive, pad0;        /* periodic axes: bit0 X, bit1 Y, bit2 Z (JSph::PeriActive) */
+  double perinc[3][3];             /* PeriXinc, PeriYinc, PeriZinc (JSph.cpp:2186-2188) */
+  double mapposmin[3], mapposmax[3]; /* Map_PosMin/Max: the real map widened by KernelSize on periodic axes (JSph.cpp:2191-2195) */
 } orc_cte;
 
 /* Result of a cell divide (JCellDivCpu members). */
@@ -62,11 +65,13 @@ typedef struct orc_div {
 
 /* ------------------------------------------------------------------------------------------------ */
 /* JCellDivCpu::LimitsCellBound / LimitsCellFluid (JCellDivCpu.cpp:269-352)                          */
-static void limits_cell(uint32_t n, uint32_t pini, const uint32_t* dcell, const typecode* code, uint32_t dcc,
+static void limits_cell(uint32_t n, int boundtype, const uint32_t* dcell, const typecode* code, uint32_t dcc,
                         uint32_t cmin[3], uint32_t cmax[3]){
+  /* by particle TYPE over all n particles: equals the index ranges [0,npb) / [npb,np) of a plain run and also covers the
+   * periodic duplicates appended behind them (CalcCellDomainBound/Fluid with the npb2/npf2 blocks, JCellDivCpuSingle.cpp:47-78) */
   cmin[0]=cmin[1]=cmin[2]=UINT32_MAX; cmax[0]=cmax[1]=cmax[2]=0;
-  for(uint32_t p=pini;p<pini+n;p++){
-    if(CODE_SPECIAL(code[p])<CODE_OUTIGNORE){
+  for(uint32_t p=0;p<n;p++){
+    if(CODE_SPECIAL(code[p])<CODE_OUTIGNORE && (CODE_TYPE(code[p])<CODE_TYPE_FLOATING)==(boundtype!=0)){
       const uint32_t rc=dcell[p];
       const uint32_t c[3]={DCEL_CELLX(dcc,rc),DCEL_CELLY(dcc,rc),DCEL_CELLZ(dcc,rc)};
       for(int k=0;k<3;k++){ if(cmin[k]>c[k])cmin[k]=c[k]; if(cmax[k]<c[k])cmax[k]=c[k]; }
@@ -80,9 +85,9 @@ static void limits_cell(uint32_t n, uint32_t pini, const uint32_t* dcell, const 
 int orc_celldiv(const orc_cte* c, uint32_t np, uint32_t npb, const uint32_t* dcell, const typecode* code,
                 uint32_t* cellpart, uint32_t* sortpart, uint32_t* begincell, orc_div* d){
   uint32_t bmin[3],bmax[3],fmin[3],fmax[3];
-  limits_cell(npb,0,dcell,code,c->domcellcode,bmin,bmax);
+  limits_cell(np,1,dcell,code,c->domcellcode,bmin,bmax);
   if(bmin[0]>bmax[0]){ for(int k=0;k<3;k++){ bmin[k]=c->domcells[k]; bmax[k]=0; } }
-  limits_cell(np-npb,npb,dcell,code,c->domcellcode,fmin,fmax);
+  limits_cell(np,0,dcell,code,c->domcellcode,fmin,fmax);
   if(fmin[0]>fmax[0]){ for(int k=0;k<3;k++){ fmin[k]=c->domcells[k]; fmax[k]=0; } }
   const uint32_t sd=(uint32_t)c->scelldiv;
   for(int k=0;k<3;k++){
@@ -373,7 +378,8 @@ int orc_interaction(const orc_cte* c, const orc_div* d, const uint32_t* begincel
   if(d->npbok)forces_bound(c,d,begincell,dcell,pos,velrho,code,ftomassp,&viscdt,ar);
   if(c->tdensity!=0)for(uint32_t p=npb;p<np;p++)if(delta[p]!=FLT_MAX)ar[p]+=delta[p];   /* JSphCpuSingle.cpp:723-731 */
   { /* ComputeAceMaxSeq (JSphCpuSingle.cpp:793-805) */
-    float am=0; for(uint32_t p=npb;p<np;p++){ const float* a=ace+3*(size_t)p; const float a2=a[0]*a[0]+a[1]*a[1]+a[2]*a[2]; if(a2>am)am=a2; }
+    float am=0; for(uint32_t p=npb;p<np;p++){ if(c->periactive && CODE_SPECIAL(code[p])!=0)continue;   /* ComputeAceMaxSeq<checkcode> with periodic */
+      const float* a=ace+3*(size_t)p; const float a2=a[0]*a[0]+a[1]*a[1]+a[2]*a[2]; if(a2>am)am=a2; }
     *acemax=sqrt((double)am);
   }
   *viscdtmax=viscdt;
@@ -392,13 +398,37 @@ double orc_dtvariable(const orc_cte* c, double velmax, double acemax, float visc
 }
 
 /* JSphCpu::UpdatePos (JSphCpu.cpp:1458-1510), no periodic boundaries. */
+/* JSph::UpdatePeriodicPos / the periodic branch of JSphCpu::UpdatePos (JSph.cpp:2079-2103, JSphCpu.cpp:1477-1495): returns out. */
+static int periodic_wrap(const orc_cte* c, double* rx,double* ry,double* rz){
+  double dx=*rx-c->maprealposmin[0], dy=*ry-c->maprealposmin[1], dz=*rz-c->maprealposmin[2];
+  int out=(dx!=dx || dy!=dy || dz!=dz || dx<0 || dy<0 || dz<0 || dx>=c->maprealsize[0] || dy>=c->maprealsize[1] || dz>=c->maprealsize[2]);
+  if(c->periactive && out){
+    const int px=(c->periactive&1), py=(c->periactive&2), pz=(c->periactive&4);
+    if(px){
+      if(dx<0)                 { dx-=c->perinc[0][0]; dy-=c->perinc[0][1]; dz-=c->perinc[0][2]; }
+      if(dx>=c->maprealsize[0]){ dx+=c->perinc[0][0]; dy+=c->perinc[0][1]; dz+=c->perinc[0][2]; }
+    }
+    if(py){
+      if(dy<0)                 { dx-=c->perinc[1][0]; dy-=c->perinc[1][1]; dz-=c->perinc[1][2]; }
+      if(dy>=c->maprealsize[1]){ dx+=c->perinc[1][0]; dy+=c->perinc[1][1]; dz+=c->perinc[1][2]; }
+    }
+    if(pz){
+      if(dz<0)                 { dx-=c->perinc[2][0]; dy-=c->perinc[2][1]; dz-=c->perinc[2][2]; }
+      if(dz>=c->maprealsize[2]){ dx+=c->perinc[2][0]; dy+=c->perinc[2][1]; dz+=c->perinc[2][2]; }
+    }
+    out=((!px && (dx<0 || dx>=c->maprealsize[0])) || (!py && (dy<0 || dy>=c->maprealsize[1])) || (!pz && (dz<0 || dz>=c->maprealsize[2])));
+    *rx=dx+c->maprealposmin[0]; *ry=dy+c->maprealposmin[1]; *rz=dz+c->maprealposmin[2];
+  }
+  return out;
+}
+
+/* JSphCpu::UpdatePos (JSphCpu.cpp:1458-1516). */
 static void update_pos(const orc_cte* c, double rx,double ry,double rz,double movx,double movy,double movz,int outrho,
   uint32_t p,double* pos,uint32_t* cell,typecode* code)
 {
   const int outmov=(fabsf((float)movx)>c->movlimit || fabsf((float)movy)>c->movlimit || fabsf((float)movz)>c->movlimit);
   rx+=movx; ry+=movy; rz+=movz;
-  const double dx=rx-c->maprealposmin[0], dy=ry-c->maprealposmin[1], dz=rz-c->maprealposmin[2];
-  const int out=(dx!=dx || dy!=dy || dz!=dz || dx<0 || dy<0 || dz<0 || dx>=c->maprealsize[0] || dy>=c->maprealsize[1] || dz>=c->maprealsize[2]);
+  const int out=periodic_wrap(c,&rx,&ry,&rz);
   pos[3*(size_t)p]=rx; pos[3*(size_t)p+1]=ry; pos[3*(size_t)p+2]=rz;
   if(outrho || outmov || out){
     typecode rcode=code[p];
@@ -406,6 +436,8 @@ static void update_pos(const orc_cte* c, double rx,double ry,double rz,double mo
     code[p]=rcode; cell[p]=0xFFFFFFFFu;
   }
   else{
+    /* relative to DomPosMin; without periodic axes that is MapRealPosMin (JSphCpu.cpp:1508-1514) */
+    const double dx=rx-c->domposmin[0], dy=ry-c->domposmin[1], dz=rz-c->domposmin[2];
     const uint32_t cx=(uint32_t)(dx/c->scell), cy=(uint32_t)(dy/c->scell), cz=(uint32_t)(dz/c->scell);
     cell[p]=DCEL_CELL(c->domcellcode,cx,cy,cz);
   }
@@ -635,7 +667,8 @@ void orc_mdbc_vel0(const orc_cte* c, const orc_div* d, uint32_t n, const uint32_
     const float* nr=boundnor+3*p1;
     if(nr[0]==0 && nr[1]==0 && nr[2]==0)continue;
     float rhofinal=FLT_MAX;
-    const double gx=pos[3*p1]+(double)nr[0], gy=pos[3*p1+1]+(double)nr[1], gz=pos[3*p1+2]+(double)nr[2];
+    double gx=pos[3*p1]+(double)nr[0], gy=pos[3*p1+1]+(double)nr[1], gz=pos[3*p1+2]+(double)nr[2];
+    if(c->periactive)periodic_wrap(c,&gx,&gy,&gz);   /* UpdatePeriodicPos(gposp1), JSphCpu_mdbc.cpp:50 */
     float rhop1=0, grx=0, gry=0, grz=0;
     double a[4][4]; memset(a,0,sizeof(a));
     /* nsearch::Init(pos,...) (JCellSearch_inline.h:54-69) */

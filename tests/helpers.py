@@ -66,6 +66,20 @@ def params_from_case(casepath: str, options: dict | None = None):
     p.dt_allparticles = 1 if int(prm.get("DtAllParticles", 0)) == 1 else 0
     p.rhopoutmin, p.rhopoutmax = float(prm.get("RhopOutMin", 700)), float(prm.get("RhopOutMax", 1300))
     p.cellmode_half = int(prm.get("_cellmode_half", 0))
+    # periodic boundaries (JSph.cpp:815-827)
+    px = py = pz = False
+    if "XPeriodicIncY" in prm: p.perixinc[1] = float(prm["XPeriodicIncY"]); px = True    # noqa: E701
+    if "XPeriodicIncZ" in prm: p.perixinc[2] = float(prm["XPeriodicIncZ"]); px = True    # noqa: E701
+    if "YPeriodicIncX" in prm: p.periyinc[0] = float(prm["YPeriodicIncX"]); py = True    # noqa: E701
+    if "YPeriodicIncZ" in prm: p.periyinc[2] = float(prm["YPeriodicIncZ"]); py = True    # noqa: E701
+    if "ZPeriodicIncX" in prm: p.perizinc[0] = float(prm["ZPeriodicIncX"]); pz = True    # noqa: E701
+    if "ZPeriodicIncY" in prm: p.perizinc[1] = float(prm["ZPeriodicIncY"]); pz = True    # noqa: E701
+    for key, flags in (("XYPeriodic", (True, True, False)), ("XZPeriodic", (True, False, True)), ("YZPeriodic", (False, True, True))):
+        if key in prm:
+            px, py, pz = flags
+            for k in range(3):
+                p.perixinc[k] = p.periyinc[k] = p.perizinc[k] = 0.0
+    p.periactive = (1 if px else 0) | (2 if py else 0) | (4 if pz else 0)
     p.shiftmode = int(prm.get("Shifting", 0))
     p.shiftcoef, p.shifttfs = float(prm.get("ShiftCoef", -2)), float(prm.get("ShiftTFS", 0))
     pa = exe.find("particles")
@@ -81,7 +95,10 @@ def params_from_case(casepath: str, options: dict | None = None):
     pos = data["pos"]
     idp = data["Idp"]
     cmin, cmax = np.array(data["head"]["CasePosMin"]), np.array(data["head"]["CasePosMax"])
-    border = float(np.float32(p.kernelh)) * 0.05
+    border = np.full(3, float(np.float32(p.kernelh)) * 0.05)
+    for k in range(3):
+        if (p.periactive >> k) & 1:
+            border[k] = p.dp / 2.0          # JPartsLoad4::CalculeLimitsPos (JPartsLoad4.cpp:389-399)
     rmin, rmax = cmin - border, cmax + border
     sd = exe.find("parameters").find("simulationdomain")
     lo, hi = rmin.copy(), rmax.copy()
@@ -106,6 +123,8 @@ def params_from_case(casepath: str, options: dict | None = None):
                 else:
                     hi[k] = float(v)
     for k in range(3):
+        if (p.periactive >> k) & 1:
+            lo[k], hi[k] = rmin[k], rmax[k]     # periodic axes keep the particle limits (JSph.cpp:1472-1475)
         p.maprealposmin[k], p.maprealposmax[k] = lo[k], hi[k]
     lib = dsb.load_library()
     r = lib.b2s_config_finalize(C.byref(p))
