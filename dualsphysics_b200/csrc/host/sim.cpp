@@ -435,15 +435,22 @@ static void load_case(b2s_sim* s,const std::string& options){
         else if(c->name=="mvrectsinu"){
           d.m.type=B2S_MOV_RECTSINU;
           if(!read_xyz(c->child("freq"),d.m.v1)||!read_xyz(c->child("ampl"),d.m.v2))throw std::runtime_error("mvrectsinu: freq/ampl missing");
-          if(c->child("phase"))read_xyz(c->child("phase"),d.m.v3);
+          if(c->child("phase"))read_xyz(c->child("phase"),d.m.v3); else d.m.pad=1;   // no <phase>: PhasePrev (checked below)
           for(int k=0;k<3;k++)d.m.v3[k]*=torad;
         }
         else if(c->name=="mvrotsinu"){
           d.m.type=B2S_MOV_ROTSINU; axis();
           d.m.v1[0]=ang("freq","v",true,0); d.m.v2[0]=ang("ampl","v",true,0)*todeg; d.m.v3[0]=ang("phase","v",false,0)*torad;
+          if(!c->child("phase"))d.m.pad=1;
         }
         else throw std::runtime_error("motion <"+c->name+"> is not supported by this build (wait, mvrect, mvrectace, mvrot, mvrotace, mvrectsinu, mvrotsinu)");
         defs.push_back(d);
+      }
+      // a sinusoidal movement without <phase> continues with the phase of the movement before it (JMotionMovActive::NextMov,
+      // JMotionObj.cpp:262-280): only the first movement of a chain may omit it here (it then starts at phase 0 like the reference)
+      for(auto& q:defs)if(q.m.pad){
+        for(auto& o2:defs)if(o2.next==q.id)throw std::runtime_error("motion: a sinusoidal movement without <phase> after another movement (phase of the previous movement) is not supported by this build");
+        q.m.pad=0;
       }
       const double tlimit=(s->timemax>0? s->timemax: 1e30);
       for(auto& b:begins){

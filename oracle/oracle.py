@@ -111,7 +111,7 @@ class OracleSim:
     """Whole-step CPU oracle over numpy arrays (cell-sorted order, like the solver's state)."""
 
     def __init__(self, cte: Cte, idp, code, pos, velrho, npb: int, dtini: float, verletsteps: int = 40,
-                 ftomassp=None, boundnor=None, mdbc_corrector=False, damping=None):
+                 ftomassp=None, boundnor=None, mdbc_corrector=False, damping=None, motion=None):
         self.L = lib()
         self.c = cte
         self.idp = np.ascontiguousarray(idp, np.uint32).copy()
@@ -134,6 +134,8 @@ class OracleSim:
         self.mdbc_corrector = mdbc_corrector
         # damping zones: (nzones, 64) doubles in the layout of orc_damping (built by damping_zones() below)
         self.damping = None if damping is None or len(damping) == 0 else np.ascontiguousarray(damping, np.float64).reshape(-1, 64)
+        # predefined motion: (MotionOracle, idbegin, count) of the moving block, or None
+        self.motion = motion
         self.symplectic_dtpre = float(dtini)
         self.timestep, self.nstep, self.verletstep, self.verletsteps = 0.0, 0, 0, verletsteps
         self.div = Div()
@@ -266,6 +268,30 @@ class OracleSim:
             self.L.orc_damping(self.np_, self.npb, C.c_double(dt), int(self.damping.shape[0]), _p(self.damping), _p(self.pos),
                                _p(self.code), _p(self.velrho))
 
+    def run_motion(self, dt):
+        """CalcMotion + RunMotion (JSph.cpp CalcMotion, JSphCpu.cpp:2189-2210): MoveLinBound / MoveMatBound of the moving block."""
+        if self.motion is None:
+            return
+        mo, idbegin, count = self.motion
+        res = mo.proces_time(self.timestep, dt)
+        if res is None:
+            return
+        n = self.np_
+        sel = np.nonzero((self.idp[:n] >= idbegin) & (self.idp[:n] < idbegin + count) & ((self.code[:n] & 0xe000) == 0))[0].astype(np.uint32)
+        ps = self.pos[sel]
+        if res[0] == "lin":
+            mov = np.tile(res[1], (sel.size, 1))
+        else:
+            m = res[1]
+            mov = (ps @ m[:3, :3].T + m[:3, 3]) - ps
+            if self.boundnor is not None:
+                gs = ps + self.boundnor[sel].astype(np.float64)
+                gs2 = gs @ m[:3, :3].T + m[:3, 3]
+                self.boundnor[sel] = (gs2 - (ps + mov)).astype(np.float32)
+        mov = np.ascontiguousarray(mov, np.float64)
+        self.L.orc_move_particles(C.byref(self.c), int(sel.size), _p(sel), _p(mov), _p(self.pos), _p(self.dcell), _p(self.code))
+        self.velrho[sel, :3] = (mov / dt).astype(np.float32)
+
     def step(self) -> float:
         n = self.np_
         if self.tstep == 2:
@@ -301,10 +327,167 @@ class OracleSim:
             self.velrhom1 = self.velrho[:n]
             self.velrho = new
             self.run_damping(dt)
+        self.run_motion(dt)
         self.celldiv()
         self.timestep += dt
         self.nstep += 1
         return dt
+
+
+class MotionOracle:
+    """Predefined motion of ONE moving block, restated step by step like the reference does it (state carried from step to step:
+    active movement, its start/finish, accumulated phase / velocity) -- JMotion::ProcesTime (JMotion.cpp:579-597),
+    JMotionObj::ProcesTime (JMotionObj.cpp:446-640), JMotionMovActive (JMotionObj.cpp:40-55,100-118,262-280), JMotionPos
+    (JMotionPos.cpp:45-58), JMatrix4::MatrixRot (JMatrix4.h:465-499).  Single-level objects, movements wait / mvrect / mvrectace /
+    mvrot / mvrotace / mvrectsinu / mvrotsinu.  The CUDA path evaluates the same movements in closed form from the time."""
+
+    def __init__(self, objreal):
+        self.movs, self.events, self.active = {}, [], []
+        for e in objreal:
+            if e.tag.startswith("_"):
+                continue
+            if e.tag == "begin":
+                self.events.append([float(e.get("start", 0)), float(e.get("finish")) if e.get("finish") is not None else -1.0, int(e.get("mov"))])
+                continue
+            deg = e.get("anglesunits", "degrees") == "degrees"
+            todeg, torad = (1.0, np.pi / 180.0) if deg else (180.0 / np.pi, 1.0)
+            f3 = lambda n: np.array([float(e.find(n).get(a)) for a in "xyz"])  # noqa: E731
+            m = {"type": e.tag, "time": float(e.get("duration", 0)), "next": int(e.get("next", 0))}
+            if e.tag == "mvrect":
+                m["vel"] = f3("vel")
+            elif e.tag == "mvrectace":
+                m["ace"], m["vel"] = f3("ace"), f3("velini")
+            elif e.tag in ("mvrot", "mvrotace", "mvrotsinu"):
+                m["p1"], m["p2"] = f3("axisp1"), f3("axisp2")
+                if e.tag == "mvrot":
+                    m["velang"] = float(e.find("vel").get("ang")) * todeg
+                elif e.tag == "mvrotace":
+                    m["aceang"], m["velang"] = float(e.find("ace").get("ang")) * todeg, float(e.find("velini").get("ang")) * todeg
+                else:
+                    m["freq"], m["ampl"] = float(e.find("freq").get("v")), float(e.find("ampl").get("v")) * todeg
+                    m["phase"] = float(e.find("phase").get("v")) * torad if e.find("phase") is not None else 0.0
+            elif e.tag == "mvrectsinu":
+                m["freq"], m["ampl"] = f3("freq"), f3("ampl")
+                m["phase"] = f3("phase") * torad if e.find("phase") is not None else np.zeros(3)
+            elif e.tag != "wait":
+                raise ValueError(f"motion <{e.tag}> is not restated")
+            self.movs[int(e.get("id"))] = m
+        self.events.sort(key=lambda v: v[0])
+
+    @staticmethod
+    def _matrix_rot(ang, p1, p2):
+        rad = ang * np.pi / 180.0
+        v = p2 - p1
+        L, L1 = np.sqrt((v * v).sum()), np.sqrt(v[1] * v[1] + v[2] * v[2])
+        T, Tm = np.eye(4), np.eye(4)
+        T[:3, 3], Tm[:3, 3] = p1, -p1
+        rx, rxm = np.eye(4), np.eye(4)
+        if L1 == 0:
+            rx[1, 1], rx[1, 2], rx[2, 1], rx[2, 2] = 0, 1, -1, 0
+            rxm[1, 1], rxm[1, 2], rxm[2, 1], rxm[2, 2] = 0, -1, 1, 0
+        else:
+            rx[1, 1], rx[1, 2], rx[2, 1], rx[2, 2] = v[2] / L1, v[1] / L1, -v[1] / L1, v[2] / L1
+            rxm[1, 1], rxm[1, 2], rxm[2, 1], rxm[2, 2] = v[2] / L1, -v[1] / L1, v[1] / L1, v[2] / L1
+        ry, rym = np.eye(4), np.eye(4)
+        ry[0, 0], ry[0, 2], ry[2, 0], ry[2, 2] = L1 / L, v[0] / L, -v[0] / L, L1 / L
+        rym[0, 0], rym[0, 2], rym[2, 0], rym[2, 2] = L1 / L, -v[0] / L, v[0] / L, L1 / L
+        cs, sn = np.cos(rad), np.sin(rad)
+        rz = np.eye(4)
+        rz[0, 0], rz[0, 1], rz[1, 0], rz[1, 1] = cs, sn, -sn, cs
+        return T @ rx @ ry @ rz @ rym @ rxm @ Tm
+
+    def _activate(self, start, evfinish, movid):
+        m = self.movs[movid]
+        fin = start + m["time"]
+        if evfinish >= 0 and evfinish < fin:
+            fin = evfinish
+        a = {"id": movid, "start": start, "finish": fin, "evfinish": evfinish, "del": False}
+        self._config(a)
+        return a
+
+    def _config(self, a):
+        m = self.movs[a["id"]]
+        a["vel"] = np.array(m.get("vel", np.zeros(3)), np.float64).copy() if m["type"] in ("mvrect", "mvrectace") else np.zeros(3)
+        a["velang"] = m.get("velang", 0.0)
+        a["phase"] = np.array(m["phase"], np.float64).copy() if m["type"] == "mvrectsinu" else np.zeros(3)
+        a["phaseuni"] = m["phase"] if m["type"] == "mvrotsinu" else 0.0
+
+    def proces_time(self, timestep, dt):
+        """Returns None (nothing moves), ('lin', d[3]) or ('mat', M[4,4]) for the step [timestep, timestep+dt]."""
+        while self.events and self.events[0][0] < timestep + dt:
+            st, fin, mv = self.events.pop(0)
+            self.active.append(self._activate(st, fin, mv))
+        tfin = timestep + dt
+        simple, mat, modif = np.zeros(3), None, False
+        for a in list(self.active):
+            if a["del"]:
+                self.active.remove(a)
+                continue
+            dt2, ts2 = dt, timestep
+            while True:
+                rep = False
+                m = self.movs[a["id"]]
+                dtmov = (a["finish"] - ts2) if tfin > a["finish"] else dt2
+                dtover = dt2 - dtmov
+                if ts2 < a["start"]:
+                    dtmov -= (a["start"] - ts2)
+                if dtmov > 0:
+                    t = dtmov
+                    d, ang = None, None
+                    if m["type"] == "mvrect":
+                        d = m["vel"] * t
+                    elif m["type"] == "mvrectace":
+                        at = m["ace"] * t
+                        d = a["vel"] * t + 0.5 * at * t
+                        a["vel"] = a["vel"] + at
+                    elif m["type"] == "mvrot":
+                        ang = m["velang"] * t
+                    elif m["type"] == "mvrotace":
+                        at = m["aceang"] * t
+                        ang = a["velang"] * t + 0.5 * at * t
+                        a["velang"] += at
+                    elif m["type"] == "mvrectsinu":
+                        ph = a["phase"].copy()
+                        p1 = m["ampl"] * np.sin(ph)
+                        ph = ph + m["freq"] * (2 * np.pi) * t
+                        p2 = m["ampl"] * np.sin(ph)
+                        d = np.where(m["ampl"] != 0, p2 - p1, 0.0)
+                        a["phase"] = np.where(m["ampl"] != 0, ph, a["phase"])
+                    elif m["type"] == "mvrotsinu":
+                        ph = a["phaseuni"]
+                        a0 = m["ampl"] * np.sin(ph)
+                        ph += m["freq"] * (2 * np.pi) * t
+                        ang = m["ampl"] * np.sin(ph) - a0
+                        a["phaseuni"] = ph
+                    if d is not None:                       # JMotionPos::Move
+                        if mat is None:
+                            simple = simple + d
+                        else:
+                            mv = np.eye(4); mv[:3, 3] = d
+                            mat = mat @ mv
+                        modif = True
+                    if ang is not None:                     # JMotionPos::Rotate
+                        if mat is None:
+                            mat = np.eye(4); mat[:3, 3] = simple
+                        mat = mat @ self._matrix_rot(ang, m["p1"], m["p2"])
+                        modif = True
+                if (dtover > 0 or dtmov == 0) and m["next"] in self.movs:
+                    a["start"] += m["time"]                 # JMotionMovActive::NextMov
+                    a["id"] = m["next"]
+                    a["finish"] = a["start"] + self.movs[a["id"]]["time"]
+                    if a["evfinish"] >= 0 and a["evfinish"] < a["finish"]:
+                        a["finish"] = a["evfinish"]
+                    self._config(a)
+                    dt2, ts2 = dtover, a["start"]
+                    if ts2 <= a["finish"]:
+                        rep = True
+                if not rep:
+                    break
+            if tfin > a["finish"]:
+                a["del"] = True
+        if not modif:
+            return None
+        return ("lin", simple) if mat is None else ("mat", mat)
 
 
 def damping_zones(xml_damping) -> np.ndarray:

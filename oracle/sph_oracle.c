@@ -443,6 +443,15 @@ static void update_pos(const orc_cte* c, double rx,double ry,double rz,double mo
   }
 }
 
+/* JSphCpu::MoveLinBound / MoveMatBound position part (JSphCpu.cpp:2105-2173): UpdatePos with the displacement of each listed
+ * particle (outrho=false); the caller sets the velocities. */
+void orc_move_particles(const orc_cte* c, uint32_t n, const uint32_t* pidx, const double* mov, double* pos, uint32_t* dcell, typecode* code){
+  for(uint32_t k=0;k<n;k++){
+    const uint32_t p=pidx[k];
+    update_pos(c,pos[3*(size_t)p],pos[3*(size_t)p+1],pos[3*(size_t)p+2],mov[3*(size_t)k],mov[3*(size_t)k+1],mov[3*(size_t)k+2],0,p,pos,dcell,code);
+  }
+}
+
 /* JSphCpu::ComputeSymplecticPre (JSphCpu.cpp:1687-1850): (pospre,velrhopre) -> (pos,velrho) */
 void orc_symplectic_pre(const orc_cte* c, uint32_t np, uint32_t npb, double dt, const double* pospre, const float* velrhopre,
   const float* ar, const float* ace, double* pos, float* velrho, uint32_t* dcell, typecode* code)

@@ -142,9 +142,16 @@ def params_from_case(casepath: str, options: dict | None = None):
     code = codeofid[idp]
     velrho = np.concatenate([data["Vel"], data["Rhop"][:, None]], axis=1).astype(np.float32)
     sp = exe.find("special")
+    motion = None
+    mo = exe.find("motion")
+    if mo is not None and mo.find("objreal") is not None:
+        obj = mo.find("objreal")
+        for tag, beg, n, node in blocks:
+            if tag == "moving" and int(node.get("refmotion", -1)) == int(obj.get("ref", 0)):
+                motion = (orc.MotionOracle(obj), beg, n)
     arrays = {"idp": idp, "code": code, "pos": pos, "velrho": velrho, "boundnor": data.get("BoundNor"),
               "ftmassp": np.array(ftmassp, np.float32),
-              "damping": orc.damping_zones(sp.find("damping") if sp is not None else None)}
+              "damping": orc.damping_zones(sp.find("damping") if sp is not None else None), "motion": motion}
     return p, arrays
 
 
@@ -154,7 +161,7 @@ def oracle_sim_from_case(casepath: str, options: dict | None = None) -> "orc.Ora
     return orc.OracleSim(cte, a["idp"], a["code"], a["pos"], a["velrho"], npb=p.casenpb, dtini=p.dtini,
                          verletsteps=p.verletsteps, ftomassp=a["ftmassp"] if len(a["ftmassp"]) else None,
                          boundnor=None if a["boundnor"] is None else 2.0 * np.asarray(a["boundnor"], np.float32),
-                         damping=a["damping"])
+                         damping=a["damping"], motion=a["motion"])
 
 
 def rel_err(a, b, floor=None):
