@@ -111,7 +111,7 @@ class OracleSim:
     """Whole-step CPU oracle over numpy arrays (cell-sorted order, like the solver's state)."""
 
     def __init__(self, cte: Cte, idp, code, pos, velrho, npb: int, dtini: float, verletsteps: int = 40,
-                 ftomassp=None, boundnor=None, mdbc_corrector=False, damping=None, motion=None):
+                 ftomassp=None, boundnor=None, mdbc_corrector=False, damping=None, motion=None, floatings=None, ftpause=0.0):
         self.L = lib()
         self.c = cte
         self.idp = np.ascontiguousarray(idp, np.uint32).copy()
@@ -136,6 +136,8 @@ class OracleSim:
         self.damping = None if damping is None or len(damping) == 0 else np.ascontiguousarray(damping, np.float64).reshape(-1, 64)
         # predefined motion: (MotionOracle, idbegin, count) of the moving block, or None
         self.motion = motion
+        # floating bodies: list of dicts (begin, count, mass, massp, center[3] f64, angles/fvel/fomega[3] f32, inertiaini[3,3] f32)
+        self.floatings, self.ftpause = floatings or [], float(ftpause)
         self.symplectic_dtpre = float(dtini)
         self.timestep, self.nstep, self.verletstep, self.verletsteps = 0.0, 0, 0, verletsteps
         self.div = Div()
@@ -268,6 +270,48 @@ class OracleSim:
             self.L.orc_damping(self.np_, self.npb, C.c_double(dt), int(self.damping.shape[0]), _p(self.damping), _p(self.pos),
                                _p(self.code), _p(self.velrho))
 
+    def run_floating(self, dt, predictor):
+        """JSphCpuSingle::RunFloating (JSphCpuSingle.cpp:938-987): FtPartsSumAce (:1013-1039), JSph::FtComputeAceVel
+        (JSph.cpp:2565-2660, free bodies), FtPartsUpdate (:1044-1100), JSph::FtUpdateFloatings (JSph.cpp:2687-2701).
+        Sums run over the body's particles in id order, in float like the reference."""
+        if not self.floatings or self.timestep < self.ftpause:
+            return
+        f32 = np.float32
+        n = self.np_
+        grav = np.array([self.c.gravity[k] for k in range(3)], f32)
+        for ft in self.floatings:
+            sel = np.nonzero((self.idp[:n] >= ft["begin"]) & (self.idp[:n] < ft["begin"] + ft["count"]))[0]
+            sel = sel[np.argsort(self.idp[sel], kind="stable")].astype(np.uint32)
+            ace = self.ace[sel].astype(f32)
+            dist = (self.pos[sel] - ft["center"]).astype(f32)
+            acelin = np.array([np.cumsum(ace[:, k], dtype=f32)[-1] for k in range(3)], f32)
+            t = np.stack([ace[:, 2] * dist[:, 1] - ace[:, 1] * dist[:, 2], ace[:, 0] * dist[:, 2] - ace[:, 2] * dist[:, 0],
+                          ace[:, 1] * dist[:, 0] - ace[:, 0] * dist[:, 1]], axis=1).astype(f32)
+            aceang = np.array([np.cumsum(t[:, k], dtype=f32)[-1] for k in range(3)], f32)
+            fmassp, fmass = f32(ft["massp"]), f32(ft["mass"])
+            flin, fang = (acelin * fmassp).astype(f32), (aceang * fmassp).astype(f32)
+            alin = ((flin + grav * fmass) / fmass).astype(f32)
+            a = ft["angles"].astype(f32)
+            cx, cy, cz, sx, sy, sz = np.cos(a[0]), np.cos(a[1]), np.cos(a[2]), np.sin(a[0]), np.sin(a[1]), np.sin(a[2])
+            rot = np.array([[cy * cz, -cy * sz, sy], [sx * sy * cz + cx * sz, -sx * sy * sz + cx * cz, -sx * cy],
+                            [-cx * sy * cz + sx * sz, cx * sy * sz + sx * cz, cx * cy]], f32)
+            inert = ((rot @ ft["inertiaini"].astype(f32)).astype(f32) @ rot.T).astype(f32)
+            aang = (np.linalg.inv(inert.astype(np.float64)).astype(f32) @ fang).astype(f32)
+            fcenter = ft["center"] + dt * ft["fvel"].astype(np.float64)
+            fvel = (dt * alin.astype(np.float64) + ft["fvel"].astype(np.float64)).astype(f32)
+            fomega = (dt * aang.astype(np.float64) + ft["fomega"].astype(np.float64)).astype(f32)
+            # FtPartsUpdate: every particle moves with its own velocity, then takes the rigid-body velocity at its new position
+            mov = np.ascontiguousarray(dt * self.velrho[sel, :3].astype(np.float64))
+            self.L.orc_move_particles(C.byref(self.c), int(sel.size), _p(sel), _p(mov), _p(self.pos), _p(self.dcell), _p(self.code))
+            d2 = (self.pos[sel] - fcenter).astype(f32)
+            self.velrho[sel, 0] = fvel[0] + (fomega[1] * d2[:, 2] - fomega[2] * d2[:, 1])
+            self.velrho[sel, 1] = fvel[1] + (fomega[2] * d2[:, 0] - fomega[0] * d2[:, 2])
+            self.velrho[sel, 2] = fvel[2] + (fomega[0] * d2[:, 1] - fomega[1] * d2[:, 0])
+            if not predictor:
+                ft["center"] = fcenter
+                ft["angles"] = (ft["angles"].astype(np.float64) + fomega.astype(np.float64) * dt).astype(f32)
+                ft["fvel"], ft["fomega"] = fvel, fomega
+
     def run_motion(self, dt):
         """CalcMotion + RunMotion (JSph.cpp CalcMotion, JSphCpu.cpp:2189-2210): MoveLinBound / MoveMatBound of the moving block."""
         if self.motion is None:
@@ -301,6 +345,7 @@ class OracleSim:
             self.pos, self.velrho = self.pospre.copy(), self.velrhopre.copy()
             self.L.orc_symplectic_pre(C.byref(self.c), n, self.npb, C.c_double(dt), _p(self.pospre), _p(self.velrhopre),
                                       _p(self.ar), _p(self.ace), _p(self.pos), _p(self.velrho), _p(self.dcell), _p(self.code))
+            self.run_floating(dt * 0.5, True)
             self.celldiv()
             n = self.np_
             dt_c = self.interaction(corrector=True)
@@ -308,6 +353,7 @@ class OracleSim:
             self.L.orc_symplectic_corr(C.byref(self.c), n, self.npb, C.c_double(dt), _p(self.pospre), _p(self.velrhopre),
                                        _p(self.ar), _p(self.ace), _p(self.pos), _p(self.velrho), _p(self.dcell), _p(self.code),
                                        None if sh is None else _p(sh))
+            self.run_floating(dt, False)
             self.run_damping(dt)
             self.pospre = self.velrhopre = None
             self.symplectic_dtpre = min(dt_p, dt_c)
@@ -326,6 +372,7 @@ class OracleSim:
                               None if sh is None else _p(sh))
             self.velrhom1 = self.velrho[:n]
             self.velrho = new
+            self.run_floating(dt, False)
             self.run_damping(dt)
         self.run_motion(dt)
         self.celldiv()

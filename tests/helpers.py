@@ -141,6 +141,14 @@ def params_from_case(casepath: str, options: dict | None = None):
             ftmassp.append(float(node.find("masspart").get("value")))
     code = codeofid[idp]
     velrho = np.concatenate([data["Vel"], data["Rhop"][:, None]], axis=1).astype(np.float32)
+    floatings = []
+    for tag, beg, n, node in blocks:
+        if tag == "floating":
+            cen = np.array([float(node.find("center").get(a)) for a in "xyz"])
+            inert = np.array([[float(v.get(f"v{r + 1}{c + 1}")) for c in range(3)] for r, v in enumerate(node.find("inertia").findall("values"))], np.float32)
+            floatings.append({"begin": beg, "count": n, "mass": float(node.find("massbody").get("value")), "massp": float(node.find("masspart").get("value")),
+                              "center": cen, "angles": np.zeros(3, np.float32), "fvel": np.zeros(3, np.float32), "fomega": np.zeros(3, np.float32),
+                              "inertiaini": inert})
     sp = exe.find("special")
     motion = None
     mo = exe.find("motion")
@@ -151,7 +159,8 @@ def params_from_case(casepath: str, options: dict | None = None):
                 motion = (orc.MotionOracle(obj), beg, n)
     arrays = {"idp": idp, "code": code, "pos": pos, "velrho": velrho, "boundnor": data.get("BoundNor"),
               "ftmassp": np.array(ftmassp, np.float32),
-              "damping": orc.damping_zones(sp.find("damping") if sp is not None else None), "motion": motion}
+              "damping": orc.damping_zones(sp.find("damping") if sp is not None else None), "motion": motion,
+              "floatings": floatings, "ftpause": float(prm.get("FtPause", 0))}
     return p, arrays
 
 
@@ -161,7 +170,7 @@ def oracle_sim_from_case(casepath: str, options: dict | None = None) -> "orc.Ora
     return orc.OracleSim(cte, a["idp"], a["code"], a["pos"], a["velrho"], npb=p.casenpb, dtini=p.dtini,
                          verletsteps=p.verletsteps, ftomassp=a["ftmassp"] if len(a["ftmassp"]) else None,
                          boundnor=None if a["boundnor"] is None else 2.0 * np.asarray(a["boundnor"], np.float32),
-                         damping=a["damping"], motion=a["motion"])
+                         damping=a["damping"], motion=a["motion"], floatings=a["floatings"], ftpause=a["ftpause"])
 
 
 def rel_err(a, b, floor=None):
