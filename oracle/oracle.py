@@ -111,7 +111,8 @@ class OracleSim:
     """Whole-step CPU oracle over numpy arrays (cell-sorted order, like the solver's state)."""
 
     def __init__(self, cte: Cte, idp, code, pos, velrho, npb: int, dtini: float, verletsteps: int = 40,
-                 ftomassp=None, boundnor=None, mdbc_corrector=False, damping=None, motion=None, floatings=None, ftpause=0.0):
+                 ftomassp=None, boundnor=None, mdbc_corrector=False, damping=None, motion=None, floatings=None, ftpause=0.0,
+                 slipmode=1):
         self.L = lib()
         self.c = cte
         self.idp = np.ascontiguousarray(idp, np.uint32).copy()
@@ -131,7 +132,10 @@ class OracleSim:
             if boundnor is not None:
                 bn = np.asarray(boundnor, np.float32).reshape(-1, 3)
                 self.boundnor[:bn.shape[0]] = bn
-        self.mdbc_corrector = mdbc_corrector
+        self.slipmode = int(slipmode)                 # 1 vel0, 2 no-slip, 3 free-slip (mDBC2)
+        self.mdbc_corrector = mdbc_corrector or self.slipmode >= 2      # MdbcCorrector (JSph.cpp:899)
+        self.boundmode = self.tangenvel = None        # mDBC2: per interaction, in the current sorted order
+        self.motionace = np.zeros((self.np_, 3), np.float32) if (self.boundnor is not None and self.slipmode >= 2) else None
         # damping zones: (nzones, 64) doubles in the layout of orc_damping (built by damping_zones() below)
         self.damping = None if damping is None or len(damping) == 0 else np.ascontiguousarray(damping, np.float64).reshape(-1, 64)
         # predefined motion: (MotionOracle, idbegin, count) of the moving block, or None
@@ -149,7 +153,7 @@ class OracleSim:
         self.pospre = self.velrhopre = None
         self.celldiv()
 
-    _PER_ARRAYS = ("idp", "code", "dcell", "pos", "velrho", "velrhom1", "tau", "pospre", "velrhopre", "boundnor")
+    _PER_ARRAYS = ("idp", "code", "dcell", "pos", "velrho", "velrhom1", "tau", "pospre", "velrhopre", "boundnor", "motionace")
 
     def periodic(self):
         """JSphCpuSingle::RunPeriodic (JSphCpuSingle.cpp:416-504) with PeriodicMakeList / PeriodicDuplicate* (:210-372): the old
@@ -223,7 +227,7 @@ class OracleSim:
                                _p(self.sortpart), _p(self.begincell), C.byref(self.div))
         assert r == 0
         sp = self.sortpart[:n]
-        for name in ("idp", "code", "dcell", "pos", "velrho", "velrhom1", "tau", "pospre", "velrhopre", "boundnor"):
+        for name in self._PER_ARRAYS:
             a = getattr(self, name)
             if a is not None:
                 setattr(self, name, np.ascontiguousarray(a[:n][sp][:int(self.div.np)]))   # excluded / ignored particles sort to the end: dropped
@@ -235,6 +239,13 @@ class OracleSim:
     def mdbc(self):
         """MdbcBoundCorrection (JSphCpuSingle.cpp:745-760), SlipMode vel0."""
         if self.boundnor is None:
+            return
+        if self.slipmode >= 2:     # Interaction_Mdbc2Correction over the Npb boundary particles (JSphCpuSingle.cpp:763-771)
+            nb = self.npb
+            self.boundmode = np.zeros(max(self.np_, 1), np.uint8)
+            self.tangenvel = np.zeros((max(self.np_, 1), 3), np.float32)
+            self.L.orc_mdbc2(C.byref(self.c), C.byref(self.div), nb, _p(self.begincell), _p(self.pos), _p(self.code), _p(self.boundnor),
+                             _p(self.motionace), 1 if self.slipmode == 3 else 0, _p(self.velrho), _p(self.boundmode), _p(self.tangenvel))
             return
         n = self.np_ if self.c.use_floating else int(self.div.npbok)
         self.L.orc_mdbc_vel0(C.byref(self.c), C.byref(self.div), n, _p(self.begincell), _p(self.pos), _p(self.code),
@@ -251,7 +262,8 @@ class OracleSim:
         self.L.orc_interaction(C.byref(self.c), C.byref(self.div), _p(self.begincell), _p(self.dcell), _p(self.pos),
                                _p(self.velrho), _p(self.code), None if self.tau is None else _p(self.tau),
                                None if self.ftomassp is None else _p(self.ftomassp),
-                               _p(self.ace), _p(self.ar), _p(self.press), C.byref(vm), C.byref(am), C.byref(vd))
+                               _p(self.ace), _p(self.ar), _p(self.press), C.byref(vm), C.byref(am), C.byref(vd),
+                               None if self.boundmode is None else _p(self.boundmode), None if self.tangenvel is None else _p(self.tangenvel))
         self.velmax, self.acemax, self.viscdtmax = vm.value, am.value, vd.value
         return self.L.orc_dtvariable(C.byref(self.c), vm.value, am.value, vd.value)
 
@@ -318,10 +330,12 @@ class OracleSim:
             return
         mo, idbegin, count = self.motion
         res = mo.proces_time(self.timestep, dt)
-        if res is None:
-            return
         n = self.np_
         sel = np.nonzero((self.idp[:n] >= idbegin) & (self.idp[:n] < idbegin + count) & ((self.code[:n] & 0xe000) == 0))[0].astype(np.uint32)
+        if res is None:
+            if self.motionace is not None:
+                self.motionace[sel] = 0          # CopyMotionVelAce: the motion velocity did not change (JSphCpu_mdbc.cpp:472-490)
+            return
         ps = self.pos[sel]
         if res[0] == "lin":
             mov = np.tile(res[1], (sel.size, 1))
@@ -334,7 +348,10 @@ class OracleSim:
                 self.boundnor[sel] = (gs2 - (ps + mov)).astype(np.float32)
         mov = np.ascontiguousarray(mov, np.float64)
         self.L.orc_move_particles(C.byref(self.c), int(sel.size), _p(sel), _p(mov), _p(self.pos), _p(self.dcell), _p(self.code))
-        self.velrho[sel, :3] = (mov / dt).astype(np.float32)
+        vnew = (mov / dt).astype(np.float32)
+        if self.motionace is not None:
+            self.motionace[sel] = ((vnew.astype(np.float64) - self.velrho[sel, :3].astype(np.float64)) / dt).astype(np.float32)
+        self.velrho[sel, :3] = vnew
 
     def step(self) -> float:
         n = self.np_
@@ -344,7 +361,8 @@ class OracleSim:
             self.pospre, self.velrhopre = self.pos[:n].copy(), self.velrho[:n].copy()
             self.pos, self.velrho = self.pospre.copy(), self.velrhopre.copy()
             self.L.orc_symplectic_pre(C.byref(self.c), n, self.npb, C.c_double(dt), _p(self.pospre), _p(self.velrhopre),
-                                      _p(self.ar), _p(self.ace), _p(self.pos), _p(self.velrho), _p(self.dcell), _p(self.code))
+                                      _p(self.ar), _p(self.ace), _p(self.pos), _p(self.velrho), _p(self.dcell), _p(self.code),
+                                      None if self.boundmode is None else _p(self.boundmode))
             self.run_floating(dt * 0.5, True)
             self.celldiv()
             n = self.np_
@@ -352,7 +370,7 @@ class OracleSim:
             sh = self.shifting(dt)
             self.L.orc_symplectic_corr(C.byref(self.c), n, self.npb, C.c_double(dt), _p(self.pospre), _p(self.velrhopre),
                                        _p(self.ar), _p(self.ace), _p(self.pos), _p(self.velrho), _p(self.dcell), _p(self.code),
-                                       None if sh is None else _p(sh))
+                                       None if sh is None else _p(sh), None if self.boundmode is None else _p(self.boundmode))
             self.run_floating(dt, False)
             self.run_damping(dt)
             self.pospre = self.velrhopre = None
@@ -369,7 +387,7 @@ class OracleSim:
             sh = self.shifting(dt)
             self.L.orc_verlet(C.byref(self.c), n, self.npb, C.c_double(dt), 1 if euler else 0, _p(self.velrho), _p(v2),
                               _p(self.ar), _p(self.ace), _p(self.pos), _p(self.dcell), _p(self.code), _p(new),
-                              None if sh is None else _p(sh))
+                              None if sh is None else _p(sh), None if self.boundmode is None else _p(self.boundmode))
             self.velrhom1 = self.velrho[:n]
             self.velrho = new
             self.run_floating(dt, False)

@@ -5,7 +5,9 @@
  * parity checker for the CUDA path.  Each function cites the reference code it follows
  * (paths relative to /root/reference/src/source).  Pinned against the real reference: tests/test_oracle_vs_ref.py
  * compares every function here with dumps produced by the compiled reference (oracle/_ref/dsph_ref_probe,
- * fixtures under tests/golden/).  Compiled WITHOUT -ffast-math so that it is bit-reproducible; the reference
+ * fixtures under tests/golden/: all 20 of them, i.e. every feature of the CUDA path -- cell divide, interaction with SPS and all DDT modes,
+ * mDBC vel0 and mDBC2, Symplectic / Verlet, shifting, damping; periodic duplication, boundary motion and floating bodies live in
+ * oracle/oracle.py).  Compiled WITHOUT -ffast-math so that it is bit-reproducible; the reference
  * build uses -ffast-math, so float results agree to rounding (tolerances in the tests), integers exactly.
  */
 #include <stdint.h>
@@ -199,9 +201,11 @@ static inline ngs_t ngs_init(const orc_cte* c, const orc_div* d, uint32_t dcell)
  * delta[] follows the CPU build's DDTArray=true path (JSph.cpp:927; JSphCpu.cpp:1088-1091). */
 static void forces_fluid_pass(const orc_cte* c, const orc_div* d, int boundp2, float visco, const uint32_t* begincell,
   const uint32_t* dcell, const double* pos, const float* velrho, const typecode* code, const float* press,
-  const float* tau, float* two_strain, const float* ftomassp, float* viscdt_out, float* ar, float* ace, float* delta)
+  const float* tau, float* two_strain, const float* ftomassp, float* viscdt_out, float* ar, float* ace, float* delta,
+  const uint8_t* boundmode, const float* tangenvel)
 {
   float viscdt=*viscdt_out;
+  const int m2=(boundp2 && boundmode!=NULL);   /* mDBC2: boundary neighbours use boundmode / tangenvel (JSphCpu.cpp:851-853,990-995) */
   const uint32_t* beg=begincell+(boundp2? 0: d->box_fluid);
   #pragma omp parallel for schedule(guided) reduction(max:viscdt)
   for(int64_t p1=(int64_t)d->npb;p1<(int64_t)d->np;p1++){
@@ -229,13 +233,14 @@ static void forces_fluid_pass(const orc_cte* c, const orc_div* d, int boundp2, f
             if(ftp2)massp2=ftomassp[code[p2]&CODE_MASKVALUE];
             if(ftp2 && c->tdensity==1 && massp2<=(c->massfluid*1.2f))deltap1=FLT_MAX;   /* DELTA_HEAVYFLOATING */
           }
+          if(m2 && !ftp2 && boundmode[p2]==2)massp2=0;   /* BMODE_MDBC2OFF */
           const float v2x=velrho[4*(size_t)p2],v2y=velrho[4*(size_t)p2+1],v2z=velrho[4*(size_t)p2+2],rhop2=velrho[4*(size_t)p2+3];
           { /* momentum */
             const float prs=(pressp1+press[p2])/(rhop1*rhop2)+(c->tkernel==1? cubic_tensil(c,rr2,rhop1,pressp1,rhop2,press[p2]): 0);
             const float p_vpm=-prs*massp2;
             ax+=p_vpm*frx; ay+=p_vpm*fry; az+=p_vpm*frz;
           }
-          const float dvx=v1x-v2x,dvy=v1y-v2y,dvz=v1z-v2z;
+          float dvx=v1x-v2x,dvy=v1y-v2y,dvz=v1z-v2z;
           arp1+=massp2*(dvx*frx+dvy*fry+dvz*frz)*(rhop1/rhop2);
           const float cbar=(float)c->cs0;
           if(c->tdensity==1 && deltap1!=FLT_MAX){
@@ -254,6 +259,7 @@ static void forces_fluid_pass(const orc_cte* c, const orc_div* d, int boundp2, f
             deltap1=(boundp2? FLT_MAX: deltap1-delta_);
           }
           { /* viscosity */
+            if(m2 && !ftp2){ const float* tv=tangenvel+3*(size_t)p2; dvx=v1x-tv[0]; dvy=v1y-tv[1]; dvz=v1z-tv[2]; }
             const float dot=drx*dvx+dry*dvy+drz*dvz;
             const float dot_rr2=dot/(rr2+c->eta2);
             if(dot_rr2>visc)visc=dot_rr2;
@@ -357,7 +363,8 @@ static void sps_tau(const orc_cte* c, uint32_t n, uint32_t pini, const float* ve
  * Outputs: ace[3np], ar[np], press[np], maxima {velmax, acemax, viscdtmax}. tau (in/out) may be NULL. */
 int orc_interaction(const orc_cte* c, const orc_div* d, const uint32_t* begincell, const uint32_t* dcell, const double* pos,
   const float* velrho, const typecode* code, float* tau, const float* ftomassp,
-  float* ace, float* ar, float* press, double* velmax, double* acemax, float* viscdtmax)
+  float* ace, float* ar, float* press, double* velmax, double* acemax, float* viscdtmax,
+  const uint8_t* boundmode, const float* tangenvel)
 {
   const uint32_t np=d->np, npb=d->npb;
   memset(ace,0,sizeof(float)*3*(size_t)np); memset(ar,0,sizeof(float)*(size_t)np);
@@ -371,8 +378,8 @@ int orc_interaction(const orc_cte* c, const orc_div* d, const uint32_t* begincel
   }
   float viscdt=0;
   if(np>npb){
-    forces_fluid_pass(c,d,0,c->visco,begincell,dcell,pos,velrho,code,press,tau,s2,ftomassp,&viscdt,ar,ace,delta);
-    forces_fluid_pass(c,d,1,c->visco*c->viscoboundfactor,begincell,dcell,pos,velrho,code,press,tau,s2,ftomassp,&viscdt,ar,ace,delta);
+    forces_fluid_pass(c,d,0,c->visco,begincell,dcell,pos,velrho,code,press,tau,s2,ftomassp,&viscdt,ar,ace,delta,boundmode,tangenvel);
+    forces_fluid_pass(c,d,1,c->visco*c->viscoboundfactor,begincell,dcell,pos,velrho,code,press,tau,s2,ftomassp,&viscdt,ar,ace,delta,boundmode,tangenvel);
     if(c->tvisco==2)sps_tau(c,np-npb,npb,velrho,s2,tau);
   }
   if(d->npbok)forces_bound(c,d,begincell,dcell,pos,velrho,code,ftomassp,&viscdt,ar);
@@ -454,12 +461,15 @@ void orc_move_particles(const orc_cte* c, uint32_t n, const uint32_t* pidx, cons
 
 /* JSphCpu::ComputeSymplecticPre (JSphCpu.cpp:1687-1850): (pospre,velrhopre) -> (pos,velrho) */
 void orc_symplectic_pre(const orc_cte* c, uint32_t np, uint32_t npb, double dt, const double* pospre, const float* velrhopre,
-  const float* ar, const float* ace, double* pos, float* velrho, uint32_t* dcell, typecode* code)
+  const float* ar, const float* ace, double* pos, float* velrho, uint32_t* dcell, typecode* code, const uint8_t* boundmode)
 {
   const double dt05=dt*.5;
   for(uint32_t p=0;p<npb;p++){
-    float w=(float)((double)velrhopre[4*(size_t)p+3]+dt05*ar[p]);
-    w=(w<c->rhopzero? c->rhopzero: w);
+    float w=velrhopre[4*(size_t)p+3];
+    if(!boundmode || boundmode[p]<1){   /* DBC or mDBC vel0; mDBC2 keeps the extrapolated density (JSphCpu.cpp:1717) */
+      w=(float)((double)w+dt05*ar[p]);
+      w=(w<c->rhopzero? c->rhopzero: w);
+    }
     velrho[4*(size_t)p]=velrhopre[4*(size_t)p]; velrho[4*(size_t)p+1]=velrhopre[4*(size_t)p+1]; velrho[4*(size_t)p+2]=velrhopre[4*(size_t)p+2]; velrho[4*(size_t)p+3]=w;
     memcpy(pos+3*(size_t)p,pospre+3*(size_t)p,24);
   }
@@ -484,11 +494,12 @@ void orc_symplectic_pre(const orc_cte* c, uint32_t np, uint32_t npb, double dt, 
 
 /* JSphCpu::ComputeSymplecticCorr (JSphCpu.cpp:1856-2022): velrho holds the predicted state on entry. */
 void orc_symplectic_corr(const orc_cte* c, uint32_t np, uint32_t npb, double dt, const double* pospre, const float* velrhopre,
-  const float* ar, const float* ace, double* pos, float* velrho, uint32_t* dcell, typecode* code, const float* shiftpos)
+  const float* ar, const float* ace, double* pos, float* velrho, uint32_t* dcell, typecode* code, const float* shiftpos, const uint8_t* boundmode)
 {
   const double dt05=dt*.5;
   for(uint32_t p=0;p<np;p++){
     const float* vp=velrhopre+4*(size_t)p;
+    if(p<npb && boundmode && boundmode[p]>=1){ memcpy(velrho+4*(size_t)p,vp,16); continue; }   /* mDBC2: velrho of the start of the step (JSphCpu.cpp:1869-1875) */
     const double epsilon_rdot=(-(double)ar[p]/(double)velrho[4*(size_t)p+3])*dt;
     const float rhonew=(float)((double)vp[3]*(2.-epsilon_rdot)/(2.+epsilon_rdot));
     if(p<npb){ velrho[4*(size_t)p]=velrho[4*(size_t)p+1]=velrho[4*(size_t)p+2]=0; velrho[4*(size_t)p+3]=(rhonew<c->rhopzero? c->rhopzero: rhonew); continue; }
@@ -511,11 +522,12 @@ void orc_symplectic_corr(const orc_cte* c, uint32_t np, uint32_t npb, double dt,
 
 /* JSphCpu::ComputeVerlet (JSphCpu.cpp:1523-1680): new values -> velrhonew; velrho1=v(n), velrho2=v(n-1) or v(n) on Euler steps. */
 void orc_verlet(const orc_cte* c, uint32_t np, uint32_t npb, double dt, int euler, const float* velrho1, const float* velrho2,
-  const float* ar, const float* ace, double* pos, uint32_t* dcell, typecode* code, float* velrhonew, const float* shiftpos)
+  const float* ar, const float* ace, double* pos, uint32_t* dcell, typecode* code, float* velrhonew, const float* shiftpos, const uint8_t* boundmode)
 {
   const double dt2=(euler? dt: dt+dt), dt205=0.5*dt*dt;
   for(uint32_t p=0;p<np;p++){
     const float* v1=velrho1+4*(size_t)p; const float* v2=velrho2+4*(size_t)p;
+    if(p<npb && boundmode && boundmode[p]>=1){ memcpy(velrhonew+4*(size_t)p,v2,16); continue; }   /* ComputeVelrhoBound (JSphCpu.cpp:1616) */
     const float rhonew=(float)((double)v2[3]+dt2*ar[p]);
     float o[4];
     if(p<npb){ o[0]=o[1]=o[2]=0; o[3]=(rhonew<c->rhopzero? c->rhopzero: rhonew); }
@@ -634,7 +646,9 @@ void orc_damping(uint32_t np, uint32_t npb, double dt, uint32_t nzones, const do
       }
       const double redudt=dt*(fdis*fdis)*redumax;
       double rx=1.-redudt*fx, ry=1.-redudt*fy, rz=1.-redudt*fz;
-      if(rx<0)rx=0; if(ry<0)ry=0; if(rz<0)rz=0;
+      if(rx<0)rx=0;
+      if(ry<0)ry=0;
+      if(rz<0)rz=0;
       float* v=velrho+4*(size_t)p;
       v[0]=(float)(rx*v[0]); v[1]=(float)(ry*v[1]); v[2]=(float)(rz*v[2]);
     }
@@ -744,3 +758,106 @@ void orc_mdbc_vel0(const orc_cte* c, const orc_div* d, uint32_t n, const uint32_
     velrho[4*p1+3]=(rhofinal!=FLT_MAX? rhofinal: c->rhopzero);
   }
 }
+
+/* 4x4 inverse by cofactors (what fmath::Determinant4x4 / InverseMatrix4x4 compute); returns the determinant. */
+static double inv4(const double m[4][4], double inv[4][4]){
+  double det=0;
+  for(int i=0;i<4;i++)for(int j=0;j<4;j++){
+    double s3[3][3]; int r=0;
+    for(int a=0;a<4;a++){ if(a==i)continue; int q=0; for(int b=0;b<4;b++){ if(b==j)continue; s3[r][q++]=m[a][b]; } r++; }
+    const double minor=s3[0][0]*(s3[1][1]*s3[2][2]-s3[1][2]*s3[2][1])-s3[0][1]*(s3[1][0]*s3[2][2]-s3[1][2]*s3[2][0])+s3[0][2]*(s3[1][0]*s3[2][1]-s3[1][1]*s3[2][0]);
+    inv[j][i]=(((i+j)&1)? -minor: minor);   /* adjugate = transposed cofactors */
+  }
+  for(int j=0;j<4;j++)det+=m[0][j]*inv[j][0];
+  if(det)for(int i=0;i<4;i++)for(int j=0;j<4;j++)inv[i][j]/=det;
+  return det;
+}
+
+/* Interaction_Mdbc2Correction, 3-D (JSphCpu_mdbc.cpp:246-436): SlipMode 2 (no-slip) / 3 (free-slip).  For every boundary particle
+ * with a normal: submerged test of the ghost node, density by the corrected kernel (matrix inverse if well conditioned, Shepard
+ * otherwise), pressure cloning to the particle (Mdbc2PressClone, :182-207), velocity of the ghost node, boundmode and tangential
+ * velocity.  motionace may be NULL (fixed boundaries); the motion velocity is the one the particle carries (MDBC2_KEEPVEL). */
+void orc_mdbc2(const orc_cte* c, const orc_div* d, uint32_t n, const uint32_t* begincell, const double* pos, const typecode* code,
+  const float* boundnor, const float* motionace, int freeslip, float* velrho, uint8_t* boundmode, float* tangenvel)
+{
+  const uint32_t* beg=begincell+d->box_fluid;
+  #pragma omp parallel for schedule(guided)
+  for(int64_t p1=0;p1<(int64_t)n;p1++){
+    boundmode[p1]=0;
+    const float* nr=boundnor+3*p1;
+    if(nr[0]==0 && nr[1]==0 && nr[2]==0)continue;
+    double gx=pos[3*p1]+(double)nr[0], gy=pos[3*p1+1]+(double)nr[1], gz=pos[3*p1+2]+(double)nr[2];
+    if(c->periactive)periodic_wrap(c,&gx,&gy,&gz);
+    float rhop1=0, grx=0, gry=0, grz=0, sumwab=0, submerged=0;
+    double vx=0,vy=0,vz=0, a[4][4]; memset(a,0,sizeof(a));
+    const int cx=(int)((gx-c->domposmin[0])/c->scell)-(int)d->cellmin[0];
+    const int cy=(int)((gy-c->domposmin[1])/c->scell)-(int)d->cellmin[1];
+    const int cz=(int)((gz-c->domposmin[2])/c->scell)-(int)d->cellmin[2];
+    const int s=c->scelldiv, ncx=(int)d->ncx, ncy=(int)d->ncy, ncz=(int)d->ncz;
+    const int xini=cx-(cx<s? cx: s), xfin=cx+(ncx-cx-1<s? ncx-cx-1: s)+1;
+    const int yini=cy-(cy<s? cy: s), yfin=cy+(ncy-cy-1<s? ncy-cy-1: s)+1;
+    const int zini=cz-(cz<s? cz: s), zfin=cz+(ncz-cz-1<s? ncz-cz-1: s)+1;
+    if(xfin>xini && xini>=0 && yini>=0 && zini>=0)
+    for(int z=zini;z<zfin;z++)for(int y=yini;y<yfin;y++){
+      const uint32_t pini=beg[xini+y*ncx+z*(int)d->nsheet], pfin=beg[xfin+y*ncx+z*(int)d->nsheet];
+      for(uint32_t p2=pini;p2<pfin;p2++){
+        const float drx=(float)(gx-pos[3*(size_t)p2]), dry=(float)(gy-pos[3*(size_t)p2+1]), drz=(float)(gz-pos[3*(size_t)p2+2]);
+        const float rr2=(drx*drx+dry*dry+drz*drz);
+        if(rr2<=c->kernelsize2 && CODE_TYPE(code[p2])==CODE_TYPE_FLUID){
+          float fac; const float wab=kernel_wabfac(c,rr2,&fac);
+          const float frx=fac*drx,fry=fac*dry,frz=fac*drz;
+          const float* v2=velrho+4*(size_t)p2;
+          const float massp2=c->massfluid, volp2=massp2/v2[3];
+          submerged-=volp2*(drx*frx+dry*fry+drz*frz);
+          rhop1+=massp2*wab; grx+=massp2*frx; gry+=massp2*fry; grz+=massp2*frz;
+          const float vwab=wab*volp2,vfrx=frx*volp2,vfry=fry*volp2,vfrz=frz*volp2;
+          sumwab+=vwab;
+          vx+=vwab*v2[0]; vy+=vwab*v2[1]; vz+=vwab*v2[2];
+          a[0][0]+=vwab; a[0][1]-=drx*vwab; a[0][2]-=dry*vwab; a[0][3]-=drz*vwab;
+          a[1][0]+=vfrx; a[1][1]-=drx*vfrx; a[1][2]-=dry*vfrx; a[1][3]-=drz*vfrx;
+          a[2][0]+=vfry; a[2][1]-=drx*vfry; a[2][2]-=dry*vfry; a[2][3]-=drz*vfry;
+          a[3][0]+=vfrz; a[3][1]-=drx*vfrz; a[3][2]-=dry*vfrz; a[3][3]-=drz*vfrz;
+        }
+      }
+    }
+    const float snormal=sqrtf(nr[0]*nr[0]+nr[1]*nr[1]+nr[2]*nr[2]);
+    const float nx=nr[0]/snormal, ny=nr[1]/snormal, nz=nr[2]/snormal;
+    const float* vm=velrho+4*p1;
+    float rhofinal, v2x,v2y,v2z;
+    if(submerged>0.f){
+      boundmode[p1]=1;
+      if(sumwab<0.1f){ rhofinal=(float)(rhop1/a[0][0]); if(rhofinal<c->rhopzero)rhofinal=c->rhopzero; }
+      else{
+        double inv[4][4];
+        const double det=inv4(a,inv);
+        if(fabs(det)>=0.001){
+          float na=0, ni=0;
+          for(int i=0;i<4;i++){
+            const float ra=(float)(fabs(a[i][0])+fabs(a[i][1])+fabs(a[i][2])+fabs(a[i][3]));
+            const float ri=(float)(fabs(inv[i][0])+fabs(inv[i][1])+fabs(inv[i][2])+fabs(inv[i][3]));
+            if(ra>na)na=ra;
+            if(ri>ni)ni=ri;
+          }
+          const float condinf=(float)((double)c->dp*(double)c->dp)*na*ni;
+          if(condinf<=50)rhofinal=(float)(inv[0][0]*rhop1+inv[0][1]*grx+inv[0][2]*gry+inv[0][3]*grz);
+          else rhofinal=(float)(rhop1/a[0][0]);
+        }
+        else rhofinal=(float)(rhop1/a[0][0]);
+      }
+      const float pghost=(float)(c->cs0*c->cs0*(rhofinal-c->rhopzero));
+      const float normpos=(-nr[0])*nx+(-nr[1])*ny+(-nr[2])*nz;
+      const float ma[3]={motionace? motionace[3*p1]: 0.f, motionace? motionace[3*p1+1]: 0.f, motionace? motionace[3*p1+2]: 0.f};
+      const float normforce=c->rhopzero*((c->gravity[0]-ma[0])*nx+(c->gravity[1]-ma[1])*ny+(c->gravity[2]-ma[2])*nz);
+      const float pressfinal=pghost+normforce*normpos;
+      rhofinal=c->rhopzero+(float)(pressfinal/(c->cs0*c->cs0));
+      const float gvx=(float)(vx/a[0][0]), gvy=(float)(vy/a[0][0]), gvz=(float)(vz/a[0][0]);
+      if(freeslip){ v2x=gvx; v2y=gvy; v2z=gvz; }
+      else{ v2x=vm[0]+vm[0]-gvx; v2y=vm[1]+vm[1]-gvy; v2z=vm[2]+vm[2]-gvz; }
+    }
+    else{ boundmode[p1]=2; rhofinal=c->rhopzero; v2x=vm[0]; v2y=vm[1]; v2z=vm[2]; }
+    velrho[4*p1+3]=rhofinal;     /* MDBC2_KEEPVEL: only the density is written */
+    const float vdn=v2x*nx+v2y*ny+v2z*nz;
+    tangenvel[3*p1]=v2x-vdn*nx; tangenvel[3*p1+1]=v2y-vdn*ny; tangenvel[3*p1+2]=v2z-vdn*nz;
+  }
+}
+

@@ -170,7 +170,8 @@ def oracle_sim_from_case(casepath: str, options: dict | None = None) -> "orc.Ora
     return orc.OracleSim(cte, a["idp"], a["code"], a["pos"], a["velrho"], npb=p.casenpb, dtini=p.dtini,
                          verletsteps=p.verletsteps, ftomassp=a["ftmassp"] if len(a["ftmassp"]) else None,
                          boundnor=None if a["boundnor"] is None else 2.0 * np.asarray(a["boundnor"], np.float32),
-                         damping=a["damping"], motion=a["motion"], floatings=a["floatings"], ftpause=a["ftpause"])
+                         damping=a["damping"], motion=a["motion"], floatings=a["floatings"], ftpause=a["ftpause"],
+                         slipmode=p.slipmode if p.tboundary == 2 else 1)
 
 
 def rel_err(a, b, floor=None):
