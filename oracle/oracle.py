@@ -132,6 +132,7 @@ class OracleSim:
             if boundnor is not None:
                 bn = np.asarray(boundnor, np.float32).reshape(-1, 3)
                 self.boundnor[:bn.shape[0]] = bn
+        self.gauges = None                            # GaugeOracle, attached by the caller
         self.slipmode = int(slipmode)                 # 1 vel0, 2 no-slip, 3 free-slip (mDBC2)
         self.mdbc_corrector = mdbc_corrector or self.slipmode >= 2      # MdbcCorrector (JSph.cpp:899)
         self.boundmode = self.tangenvel = None        # mDBC2: per interaction, in the current sorted order
@@ -392,11 +393,209 @@ class OracleSim:
             self.velrho = new
             self.run_floating(dt, False)
             self.run_damping(dt)
+        if self.gauges is not None:
+            self.gauges.update(self, self.timestep + dt)     # RunGaugeSystem(TimeStep+stepdt) (JSphCpuSingle.cpp:1192)
         self.run_motion(dt)
         self.celldiv()
         self.timestep += dt
         self.nstep += 1
         return dt
+
+
+class GaugeOracle:
+    """Velocity / SWL / MaxZ / force gauges restated over an OracleSim state (numpy): JGaugeVelocity, JGaugeSwl, JGaugeMaxZ,
+    JGaugeForce::CalculeCpu (JDsGaugeItem.cpp:427-478, 728-790, 1023-1091, 1847-1908) with the timing rules of JGaugeItem
+    (computedt / outputdt; JDsGaugeItem.h:274-275, .cpp:239-249).  Like the reference after ComputeStep, the neighbour search
+    walks the cell table of the LAST divide while the particles already carry their new positions."""
+
+    def __init__(self, xml_gauges, params, blocks, timemax, timeout):
+        self.items, self.rows = [], {}
+        df = {"cdt": timeout, "cs": 0.0, "ce": timemax, "odt": timeout, "os": 0.0, "oe": timemax, "out": False}
+
+        def common(e, d):
+            d = dict(d)
+            if e is None:
+                return d
+            for tag, key, at in (("computedt", "cdt", "value"), ("outputdt", "odt", "value")):
+                if e.find(tag) is not None:
+                    d[key] = float(e.find(tag).get(at))
+            for tag, ks, ke in (("computetime", "cs", "ce"), ("outputtime", "os", "oe")):
+                c = e.find(tag)
+                if c is not None:
+                    if c.get("start") is not None:
+                        d[ks] = float(c.get("start"))
+                    if c.get("end") is not None:
+                        d[ke] = float(c.get("end"))
+            if e.find("output") is not None:
+                d["out"] = e.find("output").get("value", "false").lower() in ("true", "1")
+            return d
+        df = common(xml_gauges.find("default"), df)
+        f3 = lambda e: np.array([float(e.get(a)) for a in "xyz"])  # noqa: E731
+        for e in xml_gauges:
+            if e.tag in ("default",) or e.tag.startswith("_"):
+                continue
+            g = common(e, df)
+            g.update({"type": e.tag, "name": e.get("name"), "cnext": 0.0, "onext": 0.0})
+            if e.tag == "velocity":
+                g["point"] = f3(e.find("point"))
+            elif e.tag == "swl":
+                g["p0"], g["p2"] = f3(e.find("point0")), f3(e.find("point2"))
+                pd = e.find("pointdp")
+                pointdp = params.dp * float(pd.get("coefdp")) if pd.get("coefdp") is not None else float(np.float32(pd.get("value")))
+                ml = e.find("masslimit")
+                g["masslimit"] = np.float32(ml.get("value")) if ml is not None and ml.get("value") is not None else (
+                    np.float32(params.massfluid) * np.float32(ml.get("coef")) if ml is not None else np.float32(params.massfluid) * np.float32(0.5))
+                dv = g["p2"] - g["p0"]
+                dis = np.sqrt((dv * dv).sum())
+                npt = int(dis / pointdp)                       # JGaugeSwl::SetPoints (JDsGaugeItem.cpp:614-633)
+                if dis - pointdp * npt >= pointdp * 0.1:
+                    npt += 1
+                npt = max(npt, 1)
+                g["np"], g["dir"] = npt, dv / dis * (dis / npt)
+            elif e.tag == "maxz":
+                g["p0"] = f3(e.find("point0"))
+                g["height"] = float(np.float32(e.find("height").get("value")))
+                dl = e.find("distlimit")
+                g["distlimit"] = (np.float32(dl.get("value")) if dl.get("value") is not None else
+                                  np.float32(params.dp * float(np.float32(dl.get("coefdp")))) if dl.get("coefdp") is not None else
+                                  np.float32(float(params.kernelh) * float(np.float32(dl.get("coefh")))))
+            elif e.tag == "force":
+                mkb = int(e.find("target").get("mkbound"))
+                idx = {"fixed": 0, "moving": 0, "floating": 0, "fluid": 0}
+                tcode = {"fixed": 0x0000, "moving": 0x0800, "floating": 0x1000, "fluid": 0x1800}
+                for tag, beg, n, node in blocks:
+                    if tag != "fluid" and int(node.get("mkbound")) == mkb:
+                        g["code"], g["begin"], g["count"] = tcode[tag] | idx[tag], beg, n
+                    idx[tag] += 1
+            else:
+                raise ValueError(f"gauge <{e.tag}> is not restated")
+            self.items.append(g)
+            self.rows[g["name"]] = []
+
+    @staticmethod
+    def _wab(c, rr2):
+        rad = np.sqrt(rr2); qq = rad / np.float32(c.kernelh)
+        if c.tkernel == 2:
+            w1 = np.float32(1) - np.float32(0.5) * qq
+            return np.float32(c.awen) * (qq + qq + np.float32(1)) * (w1 * w1) * (w1 * w1)
+        w = np.where(rad > np.float32(c.kernelh), np.float32(c.cub_a24) * (np.float32(2) - qq) ** 3,
+                     np.float32(c.cub_a2) * (np.float32(1) + (np.float32(0.75) * qq - np.float32(1.5)) * qq * qq))
+        return w.astype(np.float32)
+
+    @staticmethod
+    def _neigh(sim, pt, fluid=True):
+        """Indices of the particles in the cell window of point pt (nsearch::Init(pos,...), JCellSearch_inline.h) in table order."""
+        c, d = sim.c, sim.div
+        sc = np.float64(np.float32(c.scell))
+        cel = [int((pt[k] - c.domposmin[k]) / sc) - int((d.cellmin_x, d.cellmin_y, d.cellmin_z)[k]) for k in range(3)]
+        n = (int(d.ncx), int(d.ncy), int(d.ncz)); s = int(c.scelldiv)
+        ini = [cel[k] - min(cel[k], s) for k in range(3)]
+        fin = [cel[k] + min(n[k] - cel[k] - 1, s) + 1 for k in range(3)]
+        if ini[0] < 0 or ini[1] < 0 or ini[2] < 0 or fin[0] <= ini[0]:
+            return np.zeros(0, np.int64)
+        beg = sim.begincell[int(d.box_fluid):] if fluid else sim.begincell
+        out = []
+        for z in range(ini[2], fin[2]):
+            for y in range(ini[1], fin[1]):
+                a, b = int(beg[ini[0] + y * n[0] + z * int(d.nsheet)]), int(beg[fin[0] + y * n[0] + z * int(d.nsheet)])
+                if b > a:
+                    out.append(np.arange(a, b))
+        return np.concatenate(out) if out else np.zeros(0, np.int64)
+
+    def _point_sums(self, sim, pt):
+        idx = self._neigh(sim, pt)
+        if idx.size == 0:
+            return 0.0, np.zeros(3)
+        dr = (pt - sim.pos[idx]).astype(np.float32)
+        rr2 = dr[:, 0] * dr[:, 0] + dr[:, 1] * dr[:, 1] + dr[:, 2] * dr[:, 2]
+        ok = (rr2 <= np.float32(sim.c.kernelsize2)) & (rr2 >= np.float32(1e-18)) & ((sim.code[idx] & 0x1800) == 0x1800)
+        idx, rr2 = idx[ok], rr2[ok]
+        w = (self._wab(sim.c, rr2) * (np.float32(sim.c.massfluid) / sim.velrho[idx, 3])).astype(np.float32)
+        return float(w.astype(np.float64).sum()), (w[:, None].astype(np.float64) * sim.velrho[idx, :3]).sum(axis=0)
+
+    def measure(self, sim, g):
+        c = sim.c
+        if g["type"] == "velocity":
+            _, sv = self._point_sums(sim, g["point"])
+            return [np.float32(v) for v in sv] + [np.float32(v) for v in g["point"]]
+        if g["type"] == "swl":
+            mpre, surf, pt = np.float32(0), None, g["p0"].copy()
+            for cp in range(g["np"] + 1):
+                sw, _ = self._point_sums(sim, pt)
+                mass = np.float32(sw * float(np.float32(c.massfluid)))
+                if mass > g["masslimit"]:
+                    mpre = mass
+                if mass < g["masslimit"] and mpre:
+                    fxm1 = (g["masslimit"] - mpre) / (mass - mpre) - np.float32(1)
+                    surf = pt + g["dir"] * float(fxm1)
+                    break
+                pt = pt + g["dir"]
+            if surf is None:
+                surf = g["p0"] + g["dir"] * (g["np"] if mpre else 0)
+            return [np.float32(v) for v in surf] + [np.float32(v) for v in g["p0"]] + [np.float32(v) for v in g["p2"]]
+        if g["type"] == "maxz":
+            d = sim.div
+            sc = np.float64(np.float32(c.scell))
+            cmin = (int(d.cellmin_x), int(d.cellmin_y), int(d.cellmin_z)); n = (int(d.ncx), int(d.ncy), int(d.ncz))
+            cel = [int((g["p0"][k] - c.domposmin[k]) / sc) - cmin[k] for k in range(3)]
+            cz2 = int((g["p0"][2] + g["height"] - c.domposmin[2]) / sc) - cmin[2]
+            ncel = int(np.ceil(float(g["distlimit"]) / sc))
+            x0, x1 = max(cel[0] - ncel, 0), min(cel[0] + ncel + 1, n[0])
+            y0, y1 = max(cel[1] - ncel, 0), min(cel[1] + ncel + 1, n[1])
+            z0, z1 = max(cel[2] - ncel, 0), min(cz2 + ncel + 1, n[2])
+            zmax = -np.inf
+            beg = sim.begincell[int(d.box_fluid):]
+            if x0 < x1:
+                for z in range(z0, z1):
+                    for y in range(y0, y1):
+                        a, b = int(beg[x0 + y * n[0] + z * int(d.nsheet)]), int(beg[x1 + y * n[0] + z * int(d.nsheet)])
+                        if b <= a:
+                            continue
+                        idx = np.arange(a, b)
+                        dx = (g["p0"][0] - sim.pos[idx, 0]).astype(np.float32); dy = (g["p0"][1] - sim.pos[idx, 1]).astype(np.float32)
+                        ok = (dx * dx + dy * dy <= g["distlimit"] * g["distlimit"]) & ((sim.code[idx] & 0x1800) == 0x1800)
+                        if ok.any():
+                            zmax = max(zmax, float(np.float32(sim.pos[idx[ok], 2].max())))
+            return [np.float32(max(zmax, float(np.float32(c.domposmin[2]))))] + [np.float32(v) for v in g["p0"]]
+        # force: pressure force of the fluid on the particles of the block
+        nb = int(sim.div.npbok)
+        sel = np.nonzero(((sim.code[:nb] & 0x1fff) == g["code"]) & ((sim.code[:nb] & 0xe000) == 0))[0]
+        ace = np.zeros((g["count"], 3), np.float32)
+        cte = sim.c
+        press = lambda rho: np.float32(cte.cteb) * ((rho / np.float32(cte.rhopzero)) ** np.float32(cte.gamma) - np.float32(1))  # noqa: E731
+        for p1 in sel:
+            idx = self._neigh(sim, sim.pos[p1])
+            if idx.size == 0:
+                continue
+            dr = (sim.pos[p1] - sim.pos[idx]).astype(np.float32)
+            rr2 = dr[:, 0] * dr[:, 0] + dr[:, 1] * dr[:, 1] + dr[:, 2] * dr[:, 2]
+            ok = (rr2 <= np.float32(cte.kernelsize2)) & (rr2 >= np.float32(1e-18)) & ((sim.code[idx] & 0x1800) == 0x1800)
+            idx, dr, rr2 = idx[ok], dr[ok], rr2[ok]
+            qq = np.sqrt(rr2) / np.float32(cte.kernelh)
+            w1 = np.float32(1) - np.float32(0.5) * qq
+            fac = np.float32(cte.bwenh) * w1 * w1 * w1                    # Wendland gradient also in cubic runs
+            rho1, rho2 = sim.velrho[p1, 3], sim.velrho[idx, 3]
+            pvpm = -((press(rho1) + press(rho2)) / (rho1 * rho2)) * np.float32(cte.massfluid)
+            ace[int(sim.idp[p1]) - g["begin"]] = ((pvpm * fac)[:, None] * dr).astype(np.float32).sum(axis=0, dtype=np.float32)
+        f = ace.sum(axis=0, dtype=np.float32) * np.float32(cte.massbound)
+        return [np.float32(np.sqrt(float(f[0]) ** 2 + float(f[1]) ** 2 + float(f[2]) ** 2)), f[0], f[1], f[2]]
+
+    def update(self, sim, t):
+        """JGaugeSystem::CalculeCpu at time t (JDsGaugeSystem.cpp) with JGaugeItem::Update / Output."""
+        for g in self.items:
+            if not (t >= g["cnext"] and g["cs"] <= t <= g["ce"]):
+                continue
+            if g["cdt"]:
+                nt = int(t / g["cdt"]); g["cnext"] = g["cdt"] * nt
+                if g["cnext"] <= t:
+                    g["cnext"] = g["cdt"] * (nt + 1)
+            res = self.measure(sim, g)
+            if g["out"] and t >= g["onext"] and g["os"] <= t <= g["oe"]:
+                self.rows[g["name"]].append([t] + [float(v) for v in res])
+                if g["odt"]:
+                    nt = int(t / g["odt"]); g["onext"] = g["odt"] * nt
+                    if g["onext"] <= t:
+                        g["onext"] = g["odt"] * (nt + 1)
 
 
 class MotionOracle:

@@ -160,13 +160,23 @@ def params_from_case(casepath: str, options: dict | None = None):
     arrays = {"idp": idp, "code": code, "pos": pos, "velrho": velrho, "boundnor": data.get("BoundNor"),
               "ftmassp": np.array(ftmassp, np.float32),
               "damping": orc.damping_zones(sp.find("damping") if sp is not None else None), "motion": motion,
-              "floatings": floatings, "ftpause": float(prm.get("FtPause", 0))}
+              "floatings": floatings, "ftpause": float(prm.get("FtPause", 0)),
+              "gauges_xml": sp.find("gauges") if sp is not None else None, "blocks": blocks,
+              "timemax": float(prm.get("TimeMax", 0)), "timeout": float(prm.get("TimeOut", 0))}
     return p, arrays
 
 
 def oracle_sim_from_case(casepath: str, options: dict | None = None) -> "orc.OracleSim":
     p, a = params_from_case(casepath, options)
     cte = orc.cte_from_params(p)
+    sim = _oracle_sim(p, a, cte)
+    if a["gauges_xml"] is not None:
+        sim.gauges = orc.GaugeOracle(a["gauges_xml"], p, a["blocks"], a["timemax"], a["timeout"])
+        sim.timemax = a["timemax"]
+    return sim
+
+
+def _oracle_sim(p, a, cte):
     return orc.OracleSim(cte, a["idp"], a["code"], a["pos"], a["velrho"], npb=p.casenpb, dtini=p.dtini,
                          verletsteps=p.verletsteps, ftomassp=a["ftmassp"] if len(a["ftmassp"]) else None,
                          boundnor=None if a["boundnor"] is None else 2.0 * np.asarray(a["boundnor"], np.float32),
