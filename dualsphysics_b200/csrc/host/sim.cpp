@@ -13,6 +13,7 @@
 #include "../../../include/b2s_host.h"
 #include "xml_lite.h"
 #include "bi4.h"
+#include "motionref.h"
 #include <cmath>
 #include <cfloat>
 #include <cstring>
@@ -60,6 +61,7 @@ struct b2s_sim {
   std::vector<MotionCfg> motions;
   std::vector<GaugeCfg> gauges;
   std::vector<DampCfg> dampings;
+  MotionRefSave motref; bool motref_ready=false;                       // PartMotionRef.ibi4
   bool initial_saved, head_saved; unsigned partbegin, partbeginfirst; std::string partbegindir; double partbegintime, partbegindtpre;   // restart (-partbegin)
   // run control (JSph members)
   double timemax, timepart, timepartnext; unsigned part, nstepsbreak; bool svallsteps, svposdouble, svdata;
@@ -860,6 +862,17 @@ static void save_part(b2s_sim* s){
     for(int a=0;a<10;a++)pf.add_array_ext(fn3[a],BT_FLOAT3,ftc,f3[a].data());
     bi4_save_listapp(s->dirdata+"PartFloatInfo.ibi4","JPartFloatInfoBi4",hd,&pf,fresh);
   }
+  if(p.casenmoving || p.casenfloat){ // PartMotionRef.ibi4 (JSph::ConfigSaveData, JSph.cpp:2772-2791; JSphCpuSingle.cpp:1272-1274)
+    const uint32_t nb=uint32_t(std::lower_bound(idp.begin(),idp.begin()+n,p.casenp-p.casenfluid)-idp.begin());   // ids ascending: the boundary first
+    unsigned mkboundfirst=0; for(auto& b:s->blocks)if(b.type!=3){ mkboundfirst=b.mk-b.mktype; break; }
+    if(!s->motref_ready){   // reference particles from the state of the first PART of the run (the initial or the restarted one)
+      for(int ty=1;ty<=2;ty++)for(auto& b:s->blocks)if(b.type==ty)s->motref.add_body(ty==2,uint16_t(b.mktype),b.begin,b.count);
+      s->motref.config(nb,idp.data(),pos.data());
+      s->motref_ready=true;
+    }
+    s->motref.save_part(s->dirdata,"b200sph v0.1 (DualSPHysics v5.4 case interface)",s->timepart,mkboundfirst,fresh,
+                        s->part,inf.timestep,inf.nstep,nb,idp.data(),pos.data());
+  }
   if(!s->head_saved){
     s->head_saved=true;
     // Part_Head.ibi4 (JPartDataHead::SaveFile, JPartDataHead.cpp): head values + MkBlocks
@@ -967,6 +980,21 @@ extern "C" int b2s_sim_slab_info(b2s_sim* s,uint32_t* cuts,uint32_t ncuts,uint32
 extern "C" int b2s_sim_free(b2s_sim* s){ if(!s)return B2S_OK; if(s->ctx)b2s_destroy(s->ctx); delete s; return B2S_OK; }
 extern "C" int b2s_sim_ctx(b2s_sim* s,b2s_ctx** out){ if(!s||!out)return B2S_ERR_ARG; *out=s->ctx; return B2S_OK; }
 extern "C" int b2s_sim_params(b2s_sim* s,b2s_params* out){ if(!s||!out)return B2S_ERR_ARG; *out=s->prm; return B2S_OK; }
+// Test entry point of the PartMotionRef.ibi4 writer on host arrays (include/b2s_host.h).
+extern "C" int b2s_host_motionref_write(const char* dirdata,uint32_t nbodies,const uint8_t* floating,const uint16_t* mkbound,
+    const uint32_t* begin,const uint32_t* count,double timeout,uint32_t mkboundfirst,uint32_t nparts,uint32_t n,const uint32_t* idp,
+    const double* pos,const double* timestep,const uint32_t* step)
+{
+  if(!dirdata || !nbodies || !floating || !mkbound || !begin || !count || !nparts || !idp || !pos || !timestep || !step){ g_host_err="b2s_host_motionref_write: null argument"; return B2S_ERR_ARG; }
+  try{
+    MotionRefSave m;
+    for(uint32_t c=0;c<nbodies;c++)m.add_body(floating[c]!=0,mkbound[c],begin[c],count[c]);
+    m.config(n,idp,pos);
+    for(uint32_t k=0;k<nparts;k++)m.save_part(dirdata,"b200sph v0.1 (DualSPHysics v5.4 case interface)",timeout,mkboundfirst,k==0,k,timestep[k],step[k],n,idp,pos+size_t(k)*n*3);
+  }catch(const std::exception& e){ g_host_err=e.what(); return B2S_ERR_IO; }
+  return 0;
+}
+
 extern "C" int b2s_sim_save_part(b2s_sim* s){
   if(!s)return B2S_ERR_ARG;
   if(s->dirdata.empty()){ g_host_err="no output directory configured"; return B2S_ERR_STATE; }

@@ -106,7 +106,7 @@ ABI_SYMBOLS = [
     "b2s_slab_histogram", "b2s_slab_set_range", "b2s_slab_drop_ghosts", "b2s_slab_record_bytes", "b2s_slab_pack", "b2s_slab_unpack", "b2s_slab_pack_both", "b2s_slab_unpack_both", "b2s_slab_dt_buffer", "b2s_slab_forces",
     "b2s_slab_apply_dt", "b2s_slab_integrate", "b2s_slab_step_end", "b2s_slab_ft_sums", "b2s_slab_ft_apply",
     "b2s_sim_load", "b2s_sim_load_slab", "b2s_sim_slab_info", "b2s_sim_free", "b2s_sim_ctx", "b2s_sim_params", "b2s_sim_save_part", "b2s_sim_run",
-    "b2s_host_last_error",
+    "b2s_host_motionref_write", "b2s_host_last_error",
 ]
 
 _lib = None
@@ -194,6 +194,8 @@ def load_library():
     lib.b2s_sim_params.argtypes = [vp, C.POINTER(Params)]
     lib.b2s_sim_save_part.argtypes = [vp]
     lib.b2s_sim_run.argtypes = [vp, C.c_uint32, C.POINTER(C.c_double), u32p]
+    lib.b2s_host_motionref_write.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                             C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
@@ -449,6 +451,26 @@ class Context:
         arr = (Floating * n)()
         self._chk(self._lib.b2s_get_floatings(self._h, n, arr))
         return list(arr)
+
+
+def motionref_write(dirdata: str, bodies, timeout: float, mkboundfirst: int, idp, pos, timestep, step) -> None:
+    """PartMotionRef.ibi4 from host arrays (b2s_host_motionref_write): bodies = [(floating, mkbound, begin, count)], idp[n] ascending,
+    pos[nparts, n, 3], timestep[nparts], step[nparts].  Host code only, no GPU needed."""
+    lib = load_library()
+    fl = np.ascontiguousarray([b[0] for b in bodies], dtype=np.uint8)
+    mk = np.ascontiguousarray([b[1] for b in bodies], dtype=np.uint16)
+    bg = np.ascontiguousarray([b[2] for b in bodies], dtype=np.uint32)
+    ct = np.ascontiguousarray([b[3] for b in bodies], dtype=np.uint32)
+    idp = np.ascontiguousarray(idp, dtype=np.uint32)
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, len(idp), 3)
+    ts = np.ascontiguousarray(timestep, dtype=np.float64)
+    st = np.ascontiguousarray(step, dtype=np.uint32)
+    d = dirdata if dirdata.endswith("/") else dirdata + "/"
+    r = lib.b2s_host_motionref_write(d.encode(), len(bodies), fl.ctypes.data, mk.ctypes.data, bg.ctypes.data, ct.ctypes.data,
+                                     float(timeout), int(mkboundfirst), pos.shape[0], len(idp), idp.ctypes.data, pos.ctypes.data,
+                                     ts.ctypes.data, st.ctypes.data)
+    if r:
+        raise B2SError(r, lib.b2s_host_last_error().decode())
 
 
 class Simulation:

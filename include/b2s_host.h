@@ -29,6 +29,14 @@ int b2s_sim_params(b2s_sim* sim, b2s_params* out);
 int b2s_sim_save_part(b2s_sim* sim);                     /* writes the next Part_XXXX.bi4 */
 /* Runs until TimeMax or nsteps_break steps (0: use -nsteps option / none). */
 int b2s_sim_run(b2s_sim* sim, uint32_t nsteps_break, double* time_out, uint32_t* steps_out);
+/* PartMotionRef.ibi4 (src/source/JDsPartMotionSave.cpp:118-235, JComputeMotionRef.cpp:127-236, JPartMotRefBi4Save.cpp:149-292) on host
+ * arrays: picks the three reference particles of each body (moving ones first) from the first set of positions and writes the head
+ * plus one PART item per set into dirdata.  idp[n] ascending, pos[nparts][n][3].  The driver calls the same code at every PART;
+ * this entry point lets the file be checked against the reference's own without a GPU. */
+int b2s_host_motionref_write(const char* dirdata, uint32_t nbodies, const uint8_t* floating, const uint16_t* mkbound,
+                             const uint32_t* begin, const uint32_t* count, double timeout, uint32_t mkboundfirst,
+                             uint32_t nparts, uint32_t n, const uint32_t* idp, const double* pos,
+                             const double* timestep, const uint32_t* step);
 const char* b2s_host_last_error(void);
 #ifdef __cplusplus
 }

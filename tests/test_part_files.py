@@ -170,3 +170,24 @@ def test_restart_with_floating_body(tmp_path, built_lib):
     ca = {it.get("Cpart"): it.array("center") for it in fa[1:]}
     cb = {it.get("Cpart"): it.array("center") for it in fb[1:]}
     assert set(cb) == {2, 3, 4} and all(np.max(np.abs(ca[k] - cb[k])) < 1e-6 for k in cb)
+
+
+@pytest.mark.gpu
+def test_driver_writes_motionref_file(tmp_path, built_lib):
+    """PartMotionRef.ibi4 from a run of the driver against the reference's file for the same case
+    (tests/golden/ref_part_motion/): same structure, the same three reference particles per body, their positions at every PART
+    within the tolerance of the body trajectories (piston 1e-9 m, floating box 1e-7 m).  The writer itself is pinned bit for
+    bit on the CPU by tests/test_motionref.py."""
+    import json
+    refdir = os.path.join(H.GOLDEN, "ref_part_motion")
+    H.write_case(tmp_path, **json.load(open(os.path.join(refdir, "fixture_motionref.json")))["spec"])
+    out = tmp_path / "out"
+    r = subprocess.run([CLI, str(tmp_path / "Case"), str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "Finished execution (code=0)" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    ours, ref = bi4.load_list(str(out / "data" / "PartMotionRef.ibi4")), bi4.load_list(os.path.join(refdir, "PartMotionRef.ibi4"))
+    assert _list_structure(ours) == _list_structure(ref)
+    for name in ("MkBound", "Nid", "Id", "Ps"):
+        assert np.array_equal(ours[0].array(name), ref[0].array(name)), name
+    for a, b in zip(ours[1:], ref[1:]):
+        assert a.get("Cpart") == b.get("Cpart") and a.get("Step") == b.get("Step")
+        assert np.max(np.abs(np.asarray(a.array("PosRef")) - np.asarray(b.array("PosRef")))) < 1e-7
