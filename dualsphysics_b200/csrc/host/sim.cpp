@@ -61,6 +61,7 @@ struct b2s_sim {
   std::vector<MotionCfg> motions;
   std::vector<GaugeCfg> gauges;
   std::vector<DampCfg> dampings;
+  unsigned out_total[4]={0,0,0,0};                                    // excluded particles written to PartOut so far, by motive (0: all)
   MotionRefSave motref; bool motref_ready=false;                       // PartMotionRef.ibi4
   bool initial_saved, head_saved; unsigned partbegin, partbeginfirst; std::string partbegindir; double partbegintime, partbegindtpre;   // restart (-partbegin)
   // run control (JSph members)
@@ -782,6 +783,7 @@ static void save_part(b2s_sim* s){
     r=b2s_out_fetch(s->ctx,ocap,&nout,oid.data(),opos.data(),ovel.data(),orho.data(),omot.data());
     if(r)throw std::runtime_error(std::string("b2s_out_fetch failed: ")+b2s_last_error(s->ctx));
     for(uint32_t i=0;i<nout;i++)nmot[omot[i]&3]++;
+    s->out_total[0]+=nout; for(int k=1;k<4;k++)s->out_total[k]+=nmot[k];
   }
   pt->set_uint("Cpart",s->part); pt->set_double("TimeStep",inf.timestep); pt->set_uint("Npok",n); pt->set_uint("Nout",nout);
   pt->set_uint("Step",inf.nstep); pt->set_double("RunTime",0);
@@ -980,6 +982,12 @@ extern "C" int b2s_sim_slab_info(b2s_sim* s,uint32_t* cuts,uint32_t ncuts,uint32
 extern "C" int b2s_sim_free(b2s_sim* s){ if(!s)return B2S_OK; if(s->ctx)b2s_destroy(s->ctx); delete s; return B2S_OK; }
 extern "C" int b2s_sim_ctx(b2s_sim* s,b2s_ctx** out){ if(!s||!out)return B2S_ERR_ARG; *out=s->ctx; return B2S_OK; }
 extern "C" int b2s_sim_params(b2s_sim* s,b2s_params* out){ if(!s||!out)return B2S_ERR_ARG; *out=s->prm; return B2S_OK; }
+extern "C" int b2s_sim_stats(b2s_sim* s,uint32_t* parts,uint32_t* excluded4){
+  if(!s)return B2S_ERR_ARG;
+  if(parts)*parts=s->part;
+  if(excluded4)for(int k=0;k<4;k++)excluded4[k]=s->out_total[k];
+  return B2S_OK;
+}
 // Test entry point of the PartMotionRef.ibi4 writer on host arrays (include/b2s_host.h).
 extern "C" int b2s_host_motionref_write(const char* dirdata,uint32_t nbodies,const uint8_t* floating,const uint16_t* mkbound,
     const uint32_t* begin,const uint32_t* count,double timeout,uint32_t mkboundfirst,uint32_t nparts,uint32_t n,const uint32_t* idp,

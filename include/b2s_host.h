@@ -26,6 +26,9 @@ int b2s_sim_slab_info(b2s_sim* sim, uint32_t* cuts, uint32_t ncuts, uint32_t* ma
 int b2s_sim_free(b2s_sim* sim);
 int b2s_sim_ctx(b2s_sim* sim, b2s_ctx** out);            /* borrowed: freed by b2s_sim_free */
 int b2s_sim_params(b2s_sim* sim, b2s_params* out);
+/* Number of the next PART and the excluded particles written to PartOut so far: [0] all, [1] position, [2] density, [3] velocity
+ * (what JSph::ShowResume / GetResInfo report, src/source/JSph.cpp:3471-3494,3522-3560). */
+int b2s_sim_stats(b2s_sim* sim, uint32_t* parts, uint32_t* excluded4);
 int b2s_sim_save_part(b2s_sim* sim);                     /* writes the next Part_XXXX.bi4 */
 /* Runs until TimeMax or nsteps_break steps (0: use -nsteps option / none). */
 int b2s_sim_run(b2s_sim* sim, uint32_t nsteps_break, double* time_out, uint32_t* steps_out);

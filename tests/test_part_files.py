@@ -191,3 +191,8 @@ def test_driver_writes_motionref_file(tmp_path, built_lib):
     for a, b in zip(ours[1:], ref[1:]):
         assert a.get("Cpart") == b.get("Cpart") and a.get("Step") == b.get("Step")
         assert np.max(np.abs(np.asarray(a.array("PosRef")) - np.asarray(b.array("PosRef")))) < 1e-7
+    # Run.out (the log) and Run.csv (one-line summary with the reference's columns, JSph::GetResInfo)
+    log = open(out / "Run.out").read()
+    assert "Finished execution (code=0)" in log and "Steps of simulation" in log and "PART files.......................: 5" in log
+    head, row = open(out / "Run.csv").read().strip().splitlines()
+    assert head.startswith("#RunName;") and len(head.split(";")) == len(row.split(";")) == 26
