@@ -61,6 +61,7 @@ struct b2s_sim {
   std::vector<MotionCfg> motions;
   std::vector<GaugeCfg> gauges;
   std::vector<DampCfg> dampings;
+  int variant=0;                                                        // -b2svariant
   unsigned out_total[4]={0,0,0,0};                                    // excluded particles written to PartOut so far, by motive (0: all)
   MotionRefSave motref; bool motref_ready=false;                       // PartMotionRef.ibi4
   bool initial_saved, head_saved; unsigned partbegin, partbeginfirst; std::string partbegindir; double partbegintime, partbegindtpre;   // restart (-partbegin)
@@ -226,6 +227,9 @@ static void load_case(b2s_sim* s,const std::string& options){
       }
       else if(w=="SVSTEPS")s->svallsteps=(a.empty()||atoi(a.c_str())!=0);
       else if(w=="SAVEPOSDOUBLE")s->svposdouble=(a.empty()||atoi(a.c_str())!=0);
+      else if(w=="B2SVARIANT"){   // interaction kernel (include/b2s.h b2s_set_interaction_variant): 0 = reference summation order (default), 5 = fastest
+        s->variant=atoi(a.c_str()); if(a.empty() || (s->variant!=0 && s->variant!=3 && s->variant!=4 && s->variant!=5))throw std::runtime_error("-b2svariant: 0, 3, 4 or 5");
+      }
       else if(w=="SV"){ s->svdata=(lower(a).find("none")==std::string::npos); }
       else throw std::runtime_error("option not supported by this build: "+tok);
     }
@@ -649,6 +653,7 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   }
   r=b2s_create(&p,device,npsel+extra_capacity,&s->ctx);
   if(r)throw std::runtime_error(std::string("b2s_create failed: ")+b2s_error_string(r));
+  if(s->variant && (r=b2s_set_interaction_variant(s->ctx,s->variant))!=0)throw std::runtime_error("b2s_set_interaction_variant failed");
   // floating bodies (JSph::InitFloatings subset, JSph.cpp:1190-1290); the radii were taken from the full particle set above
   if(p.casenfloat){
     std::vector<b2s_floating> fts;

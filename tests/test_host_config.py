@@ -39,6 +39,7 @@ REFUSED = [
     (dict(floating_box=(0.15, 0.25, 0.2, 0.1, 0.15, 0.1), open_axes="y", params={"YPeriodicIncZ": 0}), "", "floating"),
     (dict(), "-shifting:fulladv", "shifting mode"),
     (dict(), "-dem", "not supported"),
+    (dict(), "-b2svariant:2", "b2svariant"),
     (dict(params={"RigidAlgorithm": 2}), "", "RigidAlgorithm"),
     (dict(layers=4, normals=True, floating_box=(0.15, 0.25, 0.2, 0.1, 0.15, 0.1), params={"Boundary": 2, "SlipMode": 2}), "", "floating"),
 ]
@@ -54,6 +55,7 @@ def test_unsupported_configuration_is_refused_with_a_message(spec, options, need
 ACCEPTED = [
     (dict(params={"Shifting": 2, "ShiftCoef": -2, "ShiftTFS": 1.5}), ""),
     (dict(), "-shifting:nobound -cellmode:half"),
+    (dict(), "-b2svariant:5 -stable"),
     (dict(special_xml="<damping><dampingzone><limitmin x=\"1\" y=\"0\" z=\"0\" /><limitmax x=\"1.4\" y=\"0\" z=\"0\" /><overlimit value=\"0.1\" /></dampingzone>"
                       "<dampingbox><limitmin><pointini x=\"0.2\" y=\"0.2\" z=\"0.1\" /><pointend x=\"0.4\" y=\"0.4\" z=\"0.2\" /></limitmin>"
                       "<limitmax><pointini x=\"0.1\" y=\"0.1\" z=\"0\" /><pointend x=\"0.5\" y=\"0.5\" z=\"0.3\" /></limitmax><overlimit value=\"0.05\" />"
