@@ -62,7 +62,8 @@ struct Parser {
       if(s[i]=='/'){ if(i+1>=s.size()||s[i+1]!='>')fail("'/>' expected"); i+=2; return n; }
       if(s[i]=='>'){ i++; break; }
       std::string a=name(); ws();
-      if(i>=s.size()||s[i]!='=')fail("'=' expected"); i++; ws();
+      if(i>=s.size()||s[i]!='=')fail("'=' expected");
+      i++; ws();
       if(i>=s.size()||(s[i]!='"'&&s[i]!='\''))fail("quote expected");
       const char q=s[i++]; size_t e=s.find(q,i); if(e==std::string::npos)fail("unterminated attribute");
       n->attrs.emplace_back(a,unescape(s.substr(i,e-i))); i=e+1;
