@@ -34,6 +34,13 @@
 #define P2_EARLYV 0          // 1: load velrho of both candidates together with posp (no dependent load inside the body)
 #endif
 
+#ifndef P2_VNOW
+#define P2_VNOW 0            // 1 (experiment, not measured yet): the exact-test branch of a round also depends on the velrho gathers, so
+                             // that ptxas cannot sink them below it and a round waits once for four gathers instead of twice for two
+                             // (profiles/README.md: the wait at their first use holds 8.8% of the stall samples; a volatile load does
+                             // not help, the sinking happens in ptxas).  Mirror-row loop only.
+#endif
+
 // ---- f32x2 helpers (PTX ISA 8.6+, sm_100): a 64-bit register holds (lo,hi) ----------------------------------------------
 typedef unsigned long long f2;
 __device__ __forceinline__ f2 pk(float lo,float hi){ f2 r; asm("mov.b64 %0, {%1,%2};":"=l"(r):"f"(lo),"f"(hi)); return r; }
@@ -242,7 +249,11 @@ __global__ void __launch_bounds__(P2_BS,MINB) k_forces_fluid_pair2(ForcesArgs g,
               const f2 rr2=fma2(drz,drz,fma2(dry,dry,mul2(drx,drx)));   // b2s_rr2 order
               const float ra=lo(rr2), rb=hi(rr2);
               const bool ha=(ra<=c.kernelsize2 && ra>=B2S_ALMOSTZERO), hb=(two && rb<=c.kernelsize2 && rb>=B2S_ALMOSTZERO);
+#if P2_VNOW
+              if((ha||hb) && va.w==va.w && vb.w==vb.w){   // the branch waits for the velrho gathers too: ptxas cannot sink them below it
+#else
               if(ha||hb){
+#endif
                 if(pass==0)pair2_body<TDENS,false>(c,drx,dry,drz,rr2,ha,hb,velrhop1,pressp1,va,vb,pa.w,pb.w,c.visco_f,acc);
                 else       pair2_body<TDENS,true >(c,drx,dry,drz,rr2,ha,hb,velrhop1,pressp1,va,vb,pa.w,pb.w,c.visco_b,acc);
               }
