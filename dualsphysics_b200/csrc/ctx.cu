@@ -104,7 +104,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   if(q.tboundary==B2S_BC_MDBC && q.slipmode>=B2S_SLIP_NOSLIP){ TRY(dalloc(ctx->boundmode,cap)); TRY(dalloc(ctx->tangenvel,cap)); if(e==cudaSuccess){ cudaMemset(ctx->boundmode,0,cap); cudaMemset(ctx->tangenvel,0,size_t(cap)*16); } }
   if(q.tboundary==B2S_BC_MDBC && q.slipmode>=B2S_SLIP_NOSLIP && q.casenmoving){ TRY(dalloc(ctx->motionace,cap)); TRY(dalloc(ctx->motionace_alt,cap)); if(e==cudaSuccess){ cudaMemset(ctx->motionace,0,size_t(cap)*16); cudaMemset(ctx->motionace_alt,0,size_t(cap)*16);} }
   if(q.tboundary==B2S_BC_MDBC){ TRY(dalloc(ctx->boundnor,cap)); TRY(dalloc(ctx->boundnor_alt,cap)); if(e==cudaSuccess){ cudaMemset(ctx->boundnor,0,cap*16); cudaMemset(ctx->boundnor_alt,0,cap*16);} }
-  TRY(dalloc(ctx->posp,cap)); TRY(dalloc(ctx->acear,cap)); TRY(dalloc(ctx->posh,size_t(cap)/2+2));
+  TRY(dalloc(ctx->posp,cap)); TRY(dalloc(ctx->acear,cap)); TRY(dalloc(ctx->posh,size_t(cap)/2+2+16));   // +16 pairs: the pre-filter may read one chunk past the last pair (forces_pair2.cu P2_CHK2)
   TRY(dalloc(ctx->cellpart,cap)); TRY(dalloc(ctx->sortpart,cap)); TRY(dalloc(ctx->cellpart_alt,cap)); TRY(dalloc(ctx->sortpart_alt,cap));
   { uint32_t* b=NULL; TRY(dalloc(b,size_t(ctx->nctt_max)+2)); ctx->begincell=(int2*)b; }
   TRY(dalloc(ctx->nearbound,size_t(ctx->nct_max)+8));

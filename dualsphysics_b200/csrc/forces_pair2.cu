@@ -41,6 +41,11 @@
                              // not help, the sinking happens in ptxas).  Mirror-row loop only.
 #endif
 
+#ifndef P2_CHK2
+#define P2_CHK2 0            // 1 (experiment, not measured yet): leaner FP16 pre-filter of the mirror-row loop -- no per-pair index clamp
+                             // (posh is padded), mask bits as immediates, one x-block select per pair instead of two.
+#endif
+
 // ---- f32x2 helpers (PTX ISA 8.6+, sm_100): a 64-bit register holds (lo,hi) ----------------------------------------------
 typedef unsigned long long f2;
 __device__ __forceinline__ f2 pk(float lo,float hi){ f2 r; asm("mov.b64 %0, {%1,%2};":"=l"(r):"f"(lo),"f"(hi)); return r; }
@@ -194,6 +199,41 @@ __global__ void __launch_bounds__(P2_BS,MINB) k_forces_fluid_pair2(ForcesArgs g,
 #if P2_MASK==2 && P2_PIPE==0
     if(ROWMODE==1){
       //-FP16 pre-filter of one chunk of a row (same test as in the single-row loop below).
+#if P2_CHK2
+      auto check=[&](const Row& w,uint32_t jb,uint32_t j0,uint32_t n)->uint32_t{
+        const uint32_t pb0=(jb+j0)<<1;
+        if(pb0>=w.pend)return 0u;                          // this lane's row ended before the chunk (empty rows: pbeg=pend=0)
+        const uint32_t sy2=h2u(__float2half2_rn(w.sy*ovs)), sz2=h2u(__float2half2_rn(w.sz*ovs));
+        // No clamp of the pair index: the lane has a particle in the chunk, so the 16 pairs end at most 15 pairs behind the last
+        // one of the array, inside the padding of posh (ctx.cu); whatever is read there cannot set a bit that survives the range
+        // mask below.  The bits are immediates (full unroll), and x-block B starts at particle nA of the chunk: a pair is taken as
+        // (A,A) or (B,B) in the loop, the one pair that straddles (nA odd) is redone with (A,B) afterwards.
+        const uint4* __restrict__ q0=g.posh+(jb+j0);
+        const int nA=int(w.pmid)-int(pb0);
+        uint32_t mask=0;
+        auto one=[&](uint32_t k,uint32_t sx2){
+          const uint4 q=__ldg(q0+k);
+          const __half2 dx=__hsub2(u2h(sx2),u2h(q.x)), dy=__hsub2(u2h(sy2),u2h(q.y)), dz=__hsub2(u2h(sz2),u2h(q.z));
+          const __half2 rr=__hfma2(dz,dz,__hfma2(dy,dy,__hmul2(dx,dx)));
+          hit2_or(mask,h2u(rr),thr2,1u<<(2u*k),2u<<(2u*k));
+        };
+        #pragma unroll
+        for(uint32_t k0=0;k0<16u;k0+=4u){
+          if(k0<n){
+            #pragma unroll
+            for(uint32_t k=k0;k<k0+4u;k++)one(k,(int(2u*k+1u)<nA? hAA: hBB));
+          }
+        }
+        if((nA&1) && nA>0 && nA<32){
+          const uint32_t k=uint32_t(nA)>>1;
+          mask&=~(3u<<(2u*k));
+          one(k,hAB);
+        }
+        if(pb0<w.pbeg)mask&=~1u;
+        { const uint32_t v=w.pend-pb0; if(v<32u)mask&=((1u<<v)-1u); }
+        return mask;
+      };
+#else
       auto check=[&](const Row& w,uint32_t jb,uint32_t j0,uint32_t n)->uint32_t{
         const uint32_t pb0=(jb+j0)<<1;
         const uint32_t sy2=h2u(__float2half2_rn(w.sy*ovs)), sz2=h2u(__float2half2_rn(w.sz*ovs));
@@ -211,6 +251,7 @@ __global__ void __launch_bounds__(P2_BS,MINB) k_forces_fluid_pair2(ForcesArgs g,
         { const uint32_t v=(w.pend>pb0? w.pend-pb0: 0u); if(v<32u)mask&=((1u<<v)-1u); }
         return mask;
       };
+#endif
       const int half=nrows>>1;
       int za=r.cz-d, ya=r.cy-d, zb=r.cz+d, yb=r.cy+d;     // row i walks forward from the first row, its mirror backward from the last
       Row nextA=setup_row(za,ya);
