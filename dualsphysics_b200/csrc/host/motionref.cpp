@@ -37,9 +37,10 @@ void MotionRefSave::add_body(bool floating,uint16_t mkbound,uint32_t begin,uint3
 void MotionRefSave::config(uint32_t n,const uint32_t* idp,const double* pos){
   for(MotRefBody& b:bodies){
     auto P=[&](uint32_t k){ return P3{pos[size_t(k)*3],pos[size_t(k)*3+1],pos[size_t(k)*3+2]}; };
+    // ids ascending: the particles of the body that are still in the simulation are the slots [k0,k1)
+    const uint32_t k0=uint32_t(std::lower_bound(idp,idp+n,b.begin)-idp), k1=uint32_t(std::lower_bound(idp,idp+n,b.begin+b.np)-idp);
     P3 mn{DBL_MAX,DBL_MAX,DBL_MAX},mx{-DBL_MAX,-DBL_MAX,-DBL_MAX};
-    for(uint32_t id=b.begin;id<b.begin+b.np;id++){
-      const uint32_t k=find_id(n,idp,id); if(k>=n)continue;
+    for(uint32_t k=k0;k<k1;k++){
       const P3 p=P(k);
       mn.x=std::min(mn.x,p.x); mn.y=std::min(mn.y,p.y); mn.z=std::min(mn.z,p.z);
       mx.x=std::max(mx.x,p.x); mx.y=std::max(mx.y,p.y); mx.z=std::max(mx.z,p.z);
@@ -49,10 +50,9 @@ void MotionRefSave::config(uint32_t n,const uint32_t* idp,const double* pos){
       const bool xmax=(c==1||c==2||c==5||c==6), ymax=(c==2||c==3||c==6||c==7), zmax=(c>=4);
       const P3 corner{xmax? mx.x: mn.x, ymax? mx.y: mn.y, zmax? mx.z: mn.z};
       uint32_t best=b.begin; P3 pbest{0,0,0}; double dbest=DBL_MAX;
-      for(uint32_t id=b.begin;id<b.begin+b.np;id++){
-        const uint32_t k=find_id(n,idp,id); if(k>=n)continue;
+      for(uint32_t k=k0;k<k1;k++){
         const P3 p=P(k); const double d=dist(p,corner);
-        if(dbest>d){ dbest=d; best=id; pbest=p; }
+        if(dbest>d){ dbest=d; best=idp[k]; pbest=p; }
       }
       bool rep=false; for(unsigned r=0;r<nlim && !rep;r++)rep=(idlim[r]==best);
       if(!rep){ idlim[nlim]=best; plim[nlim]=pbest; nlim++; }
