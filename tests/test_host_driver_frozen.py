@@ -1,0 +1,141 @@
+"""The C++ host driver (csrc/host/sim.cpp: case parsing, run loop, PART schedule, every output file, restart) on the CPU: it is linked
+here with tests/frozen_device/frozen_device.cpp, a stand-in for the device half of the C-ABI that keeps the uploaded particles as they
+are and only advances the clock by 1/1024 s per step.  What the driver writes is compared with the files the reference CPU build wrote
+for the same cases (tests/golden/ref_part, ref_part_float, ref_part_motion): the same item trees, value and array names and types; with a
+frozen state the numbers that do not depend on the physics must be equal too (ids, initial positions, reference particles, PART
+schedule).  The numerical content of a real run is what the `-m gpu` tests of tests/test_part_files.py check."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+from dualsphysics_b200 import bi4
+
+CSRC = os.path.join(H.ROOT, "dualsphysics_b200", "csrc")
+DT = 1.0 / 1024.0
+
+
+@pytest.fixture(scope="module")
+def cli(tmp_path_factory):
+    d = tmp_path_factory.mktemp("frozen")
+    exe = str(d / "b200sph_frozen")
+    src = [os.path.join(CSRC, "config.cpp")] + [os.path.join(CSRC, "host", f) for f in ("sim.cpp", "bi4.cpp", "xml_lite.cpp", "motionref.cpp", "main.cpp")]
+    src.append(os.path.join(H.ROOT, "tests", "frozen_device", "frozen_device.cpp"))
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")   # csrc/config.cpp sees vector types through b2s_internal.h
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", os.path.join(H.ROOT, "include"), "-I", cuda_inc, "-x", "c++"] + src + ["-o", exe], check=True)
+    return exe
+
+
+def _structure(it, path=""):
+    out = [(path + it.name, tuple((n, t) for n, t, _ in it.values), tuple((n, t) for n, t, _ in it.arrays))]
+    for c in it.items:
+        out += _structure(c, path + it.name + "/")
+    return out
+
+
+def _list_structure(items):
+    return [(it.name, it.hide, tuple((n, t) for n, t, _ in it.values), tuple((n, t) for n, t, _ in it.arrays)) for it in items]
+
+
+def _run(cli, case, out, *opts):
+    r = subprocess.run([cli, str(case), str(out)] + list(opts), capture_output=True, text=True, timeout=120)
+    return r
+
+
+def test_part_files_and_head(cli, tmp_path):
+    H.write_case(tmp_path, dp=0.05, params={"TimeMax": 0.01, "TimeOut": 0.002})
+    out = tmp_path / "out"
+    r = _run(cli, tmp_path / "Case", out, "-symplectic", "-tmax:0.004", "-tout:0.002")
+    assert r.returncode == 0 and "Finished execution (code=0)" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    ref = os.path.join(H.GOLDEN, "ref_part")
+    for name in ("Part_0002.bi4", "Part_Head.ibi4"):
+        so, sr = _structure(bi4.load(str(out / "data" / name))), _structure(bi4.load(os.path.join(ref, name)))
+        assert so == sr, f"{name}: structure differs\nours={so}\nref ={sr}"
+    # PART schedule (JDsOutputTime::GetNextTime): the first step whose time reaches 0.002, 0.004
+    for k, tmin in ((0, 0.0), (1, 0.002), (2, 0.004)):
+        p = bi4.load_part(str(out / "data" / f"Part_{k:04d}.bi4"))
+        t = p["part"]["TimeStep"]
+        assert tmin <= t < tmin + DT and p["part"]["Step"] == round(t / DT), (k, t)
+    assert not (out / "data" / "Part_0003.bi4").exists()
+    # frozen state: the particles of the case file come back, ordered by id, positions to the bit
+    case = bi4.load_part(str(tmp_path / "Case.bi4"))
+    io = np.argsort(case["Idp"], kind="stable")
+    assert np.array_equal(p["Idp"], case["Idp"][io]) and np.array_equal(p["pos"], case["pos"][io])
+    g = bi4.load_part(os.path.join(ref, "Part_0002.bi4"))
+    assert len(p["Idp"]) == len(g["Idp"]) and np.array_equal(np.sort(g["Idp"]), p["Idp"])
+
+
+def test_list_files_of_a_case_with_piston_and_floating_body(cli, tmp_path):
+    spec = json.load(open(os.path.join(H.GOLDEN, "ref_part_motion", "fixture_motionref.json")))["spec"]
+    H.write_case(tmp_path, **spec)
+    out = tmp_path / "out"
+    r = _run(cli, tmp_path / "Case", out)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    data = out / "data"
+    reff, refm = os.path.join(H.GOLDEN, "ref_part_float"), os.path.join(H.GOLDEN, "ref_part_motion")
+    for name, refdir in (("PartInfo.ibi4", reff), ("PartFloatInfo.ibi4", reff), ("PartMotionRef.ibi4", refm)):
+        so, sr = _list_structure(bi4.load_list(str(data / name))), _list_structure(bi4.load_list(os.path.join(refdir, name)))
+        assert so == sr, f"{name}: structure differs\nours={so}\nref ={sr}"
+    # nothing is excluded by a frozen state: PartOut holds the head only, the same head as the reference's file
+    oo, rr = bi4.load_list(str(data / "PartOut_000.obi4")), bi4.load_list(os.path.join(reff, "PartOut_000.obi4"))
+    assert len(oo) == 1 and _list_structure(oo) == _list_structure(rr[:1])
+    # reference particles and their positions: the bodies do not move here, so every PART repeats the head positions
+    om, rm = bi4.load_list(str(data / "PartMotionRef.ibi4")), bi4.load_list(os.path.join(refm, "PartMotionRef.ibi4"))
+    for name in ("MkBound", "Nid", "Id", "Ps"):
+        assert np.array_equal(om[0].array(name), rm[0].array(name)), name
+    for name in ("TimeOut", "MkBoundFirst", "MkMovingCount", "MkFloatCount", "MkCount", "FormatVer", "MainFile"):
+        assert om[0].get(name) == rm[0].get(name), name
+    for it in om[1:]:
+        assert np.array_equal(it.array("PosRef"), om[0].array("Ps"))
+    # floating-body file: constant head data equal to the reference's, one item per PART
+    of, rf = bi4.load_list(str(data / "PartFloatInfo.ibi4")), bi4.load_list(os.path.join(reff, "PartFloatInfo.ibi4"))
+    for name in ("MkBound", "Beginp", "Countp", "Mass", "Massp"):
+        assert np.array_equal(of[0].array(name), rf[0].array(name)), name
+    assert [it.get("Cpart") for it in of[1:]] == [it.get("Cpart") for it in rf[1:]] == list(range(5))
+    assert np.max(np.abs(of[1].array("center") - rf[1].array("center"))) < 1e-12      # PART 0: the initial centre
+    # PartInfo: counts of every PART
+    oi = bi4.load_list(str(data / "PartInfo.ibi4"))
+    for k, it in enumerate(oi[1:]):
+        assert it.get("Cpart") == k and it.get("Npok") == 1650 and it.get("Nout") == 0 and it.get("npbin") == 1182 + 192
+        assert k == 0 or abs(it.get("dtmean") - DT) < 1e-15
+
+
+def test_restart_continues_numbering_time_and_list_files(cli, tmp_path):
+    spec = json.load(open(os.path.join(H.GOLDEN, "ref_part_motion", "fixture_motionref.json")))["spec"]
+    H.write_case(tmp_path, **spec)
+    a, b = tmp_path / "runA", tmp_path / "runB"
+    assert _run(cli, tmp_path / "Case", a, "-symplectic").returncode == 0
+    r = _run(cli, tmp_path / "Case", b, "-symplectic", "-partbegin:2", str(a / "data"))
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert sorted(f for f in os.listdir(b / "data") if f.startswith("Part_0")) == ["Part_0002.bi4", "Part_0003.bi4", "Part_0004.bi4"]
+    pa, pb = bi4.load_part(str(a / "data" / "Part_0002.bi4")), bi4.load_part(str(b / "data" / "Part_0002.bi4"))
+    assert pb["part"]["TimeStep"] == pa["part"]["TimeStep"] and np.array_equal(pa["pos"], pb["pos"]) and np.array_equal(pa["Idp"], pb["Idp"])
+    assert bi4.load_part(str(b / "data" / "Part_0004.bi4"))["part"]["TimeStep"] == bi4.load_part(str(a / "data" / "Part_0004.bi4"))["part"]["TimeStep"]
+    # the floating body restarts from PartFloatInfo.ibi4 of the first run; the list files of the restart hold PARTs 2..4
+    fb = bi4.load_list(str(b / "data" / "PartFloatInfo.ibi4"))
+    assert [it.get("Cpart") for it in fb[1:]] == [2, 3, 4]
+    mb = bi4.load_list(str(b / "data" / "PartMotionRef.ibi4"))
+    assert [it.get("Cpart") for it in mb[1:]] == [2, 3, 4]
+    # errors of the restart are loud
+    r = _run(cli, tmp_path / "Case", b, "-symplectic", "-partbegin:2")
+    assert r.returncode != 0 and "partbegin" in (r.stdout + r.stderr)
+    r = _run(cli, tmp_path / "Case", b, "-symplectic", "-partbegin:9", str(a / "data"))
+    assert r.returncode != 0
+
+
+def test_gauge_files(cli, tmp_path):
+    fx = json.load(open(os.path.join(H.GOLDEN, "gauges_force_ref", "fixture_gauges.json")))
+    H.write_case(tmp_path, **fx["spec"])
+    out = tmp_path / "out"
+    r = _run(cli, tmp_path / "Case", out, *fx["options"])
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    refdir = os.path.join(H.GOLDEN, "gauges_force_ref")
+    for name in ("GaugesForce_Tank.csv", "GaugesForce_Piston.csv", "GaugesMaxZ_Col.csv"):
+        ours, ref = open(out / name).read().splitlines(), open(os.path.join(refdir, name)).read().splitlines()
+        assert ours[0] == ref[0], name                                     # the reference's header line
+        assert len(ours) > 2 and all(len(ln.split(";")) == len(ref[1].split(";")) for ln in ours[1:]), name
+        t = np.array([float(ln.split(";")[0]) for ln in ours[1:]])
+        assert t[0] == 0.0 and np.all(np.diff(t) > 0)
