@@ -139,3 +139,16 @@ def test_gauge_files(cli, tmp_path):
         assert len(ours) > 2 and all(len(ln.split(";")) == len(ref[1].split(";")) for ln in ours[1:]), name
         t = np.array([float(ln.split(";")[0]) for ln in ours[1:]])
         assert t[0] == 0.0 and np.all(np.diff(t) > 0)
+
+
+def test_every_accepted_configuration_loads_and_steps(cli, tmp_path):
+    """The configurations tests/test_host_config.py expects to be accepted, taken past the point that test can reach without a
+    device: upload, registration of motions / damping zones / gauges / floating bodies, three steps, one PART."""
+    from test_host_config import ACCEPTED
+    for k, (spec, options) in enumerate(ACCEPTED):
+        d = tmp_path / f"c{k}"
+        d.mkdir()
+        H.write_case(d, dp=0.05, **spec)
+        r = _run(cli, d / "Case", d / "out", "-nsteps:3", *options.split())
+        assert r.returncode == 0 and "Finished execution (code=0)" in r.stdout, (k, r.stdout[-800:] + r.stderr[-800:])
+        assert (d / "out" / "data" / "Part_0000.bi4").exists() and "Steps of simulation..............: 3" in r.stdout
