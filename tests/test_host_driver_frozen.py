@@ -19,14 +19,22 @@ DT = 1.0 / 1024.0
 
 
 @pytest.fixture(scope="module")
-def cli(tmp_path_factory):
+def frozen(tmp_path_factory):
+    """Builds the host driver + frozen device once: a shared library (for ctypes) and the command line on top of it."""
     d = tmp_path_factory.mktemp("frozen")
-    exe = str(d / "b200sph_frozen")
-    src = [os.path.join(CSRC, "config.cpp")] + [os.path.join(CSRC, "host", f) for f in ("sim.cpp", "bi4.cpp", "xml_lite.cpp", "motionref.cpp", "main.cpp")]
+    src = [os.path.join(CSRC, "config.cpp")] + [os.path.join(CSRC, "host", f) for f in ("sim.cpp", "bi4.cpp", "xml_lite.cpp", "motionref.cpp")]
     src.append(os.path.join(H.ROOT, "tests", "frozen_device", "frozen_device.cpp"))
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")   # csrc/config.cpp sees vector types through b2s_internal.h
-    subprocess.run(["g++", "-O1", "-std=c++17", "-I", os.path.join(H.ROOT, "include"), "-I", cuda_inc, "-x", "c++"] + src + ["-o", exe], check=True)
-    return exe
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(H.ROOT, "include"), "-I", cuda_inc, "-x", "c++"] + src
+                   + ["-o", str(d / "libb200sph.so")], check=True)
+    subprocess.run(["g++", "-O1", "-std=c++17", os.path.join(CSRC, "host", "main.cpp"), "-o", str(d / "b200sph_frozen"), "-L", str(d), "-lb200sph",
+                    "-Wl,-rpath,$ORIGIN"], check=True)
+    return {"exe": str(d / "b200sph_frozen"), "lib": str(d / "libb200sph.so")}
+
+
+@pytest.fixture(scope="module")
+def cli(frozen):
+    return frozen["exe"]
 
 
 def _structure(it, path=""):
@@ -152,3 +160,48 @@ def test_every_accepted_configuration_loads_and_steps(cli, tmp_path):
         r = _run(cli, d / "Case", d / "out", "-nsteps:3", *options.split())
         assert r.returncode == 0 and "Finished execution (code=0)" in r.stdout, (k, r.stdout[-800:] + r.stderr[-800:])
         assert (d / "out" / "data" / "Part_0000.bi4").exists() and "Steps of simulation..............: 3" in r.stdout
+
+
+def test_slab_loading_partitions_the_case(frozen, tmp_path):
+    """b2s_sim_load_slab (one rank of a multi-GPU run): every rank derives the same cut planes from the particle histogram, the
+    slabs are disjoint, together they hold every particle of the case, and a rank holds exactly the particles of its cell planes."""
+    import ctypes as C
+    from dualsphysics_b200.lib import Params
+    lib = C.CDLL(frozen["lib"])
+    lib.b2s_host_last_error.restype = C.c_char_p
+    H.write_case(tmp_path, dp=0.03, piston=True)
+    case = str(tmp_path / "Case").encode()
+    allp = bi4.load_part(str(tmp_path / "Case.bi4"))
+    ntot = len(allp["Idp"])
+    for nranks in (1, 2, 3, 4):
+        seen, cuts0 = [], None
+        for rank in range(nranks):
+            sim = C.c_void_p()
+            r = lib.b2s_sim_load_slab(case, b"-symplectic", 0, rank, nranks, C.byref(sim))
+            assert r == 0, lib.b2s_host_last_error().decode()
+            cuts, mx = (C.c_uint32 * (nranks + 1))(), C.c_uint32()
+            assert lib.b2s_sim_slab_info(sim, cuts, nranks + 1, C.byref(mx)) == 0
+            cuts = list(cuts)
+            prm = Params()
+            assert lib.b2s_sim_params(sim, C.byref(prm)) == 0
+            assert cuts[0] == 0 and cuts[-1] == prm.domcells[0] and all(b > a for a, b in zip(cuts, cuts[1:]))
+            cuts0 = cuts0 or cuts
+            assert cuts == cuts0                                     # the same planes on every rank
+            ctx = C.c_void_p()
+            assert lib.b2s_sim_ctx(sim, C.byref(ctx)) == 0
+            n = C.c_uint32()
+            idp, pos = np.zeros(ntot, np.uint32), np.zeros((ntot, 3))
+            vel, rho = np.zeros((ntot, 3), np.float32), np.zeros(ntot, np.float32)
+            assert lib.b2s_download_particles_byid(ctx, C.byref(n), idp.ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p),
+                                                   vel.ctypes.data_as(C.c_void_p), rho.ctypes.data_as(C.c_void_p)) == 0
+            n = n.value
+            cx = np.clip(np.floor((pos[:n, 0] - prm.domposmin[0]) / float(prm.scell)).astype(np.int64), 0, prm.domcells[0] - 1)
+            assert n > 0 and np.all((cx >= cuts[rank]) & (cx < cuts[rank + 1])), (nranks, rank)
+            assert mx.value >= np.bincount(cx).max()
+            seen.append(idp[:n].copy())
+            lib.b2s_sim_free(sim)
+        ids = np.concatenate(seen)
+        assert len(ids) == ntot and np.array_equal(np.sort(ids), np.sort(allp["Idp"])), nranks
+        if nranks > 1:       # balanced within the granularity of one plane of cells
+            counts = np.array([len(x) for x in seen])
+            assert counts.max() <= ntot / nranks + mx.value
