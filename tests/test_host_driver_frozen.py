@@ -205,3 +205,34 @@ def test_slab_loading_partitions_the_case(frozen, tmp_path):
         if nranks > 1:       # balanced within the granularity of one plane of cells
             counts = np.array([len(x) for x in seen])
             assert counts.max() <= ntot / nranks + mx.value
+
+
+@pytest.mark.parametrize("refdir", ["gauges_ref", "gauges_force_ref"])
+def test_gauge_schedule_matches_the_restated_rules(cli, tmp_path, refdir):
+    """computedt / outputdt / start / end of every gauge (JGaugeItem::Update / Output): the rows the driver writes for the frozen clock
+    t = k/1024 against the oracle's restatement of the same rules (oracle/oracle.py GaugeOracle, itself pinned to the reference's
+    CSV files by tests/test_oracle_gauges.py) fed with the same times."""
+    import oracle.oracle as orc
+    fx = json.load(open(os.path.join(H.GOLDEN, refdir, "fixture_gauges.json")))
+    H.write_case(tmp_path, **fx["spec"])
+    out = tmp_path / "out"
+    r = _run(cli, tmp_path / "Case", out, *fx["options"])
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    p, a = H.params_from_case(str(tmp_path / "Case"), {"StepAlgorithm": 2} if "-symplectic" in fx["options"] else None)
+    go = orc.GaugeOracle(a["gauges_xml"], p, a["blocks"], a["timemax"], a["timeout"])
+    go.measure = lambda sim, g: [0.0]
+    t, k = 0.0, 0
+    go.update(None, 0.0)
+    while t < a["timemax"]:
+        k += 1
+        t = k * DT
+        go.update(None, t)
+    prefix = {"velocity": "GaugesVel_", "swl": "GaugesSWL_", "maxz": "GaugesMaxZ_", "force": "GaugesForce_"}
+    assert go.items
+    for g in go.items:
+        if not g["out"]:
+            continue
+        rows = open(out / (prefix[g["type"]] + g["name"] + ".csv")).read().splitlines()[1:]
+        ours = [float(ln.split(";")[0]) for ln in rows]
+        want = [row[0] for row in go.rows[g["name"]]]
+        assert len(ours) == len(want) and np.allclose(ours, want, atol=6e-7, rtol=0), (g["name"], ours[:5], want[:5])
