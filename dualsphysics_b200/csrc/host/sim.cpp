@@ -62,6 +62,7 @@ struct b2s_sim {
   std::vector<GaugeCfg> gauges;
   std::vector<DampCfg> dampings;
   int variant=0;                                                        // -b2svariant
+  std::string svextraparts;                                             // -svextraparts / SaveExtraParts: PARTs that get a PartExtra_XXXX.bi4
   unsigned out_total[4]={0,0,0,0};                                    // excluded particles written to PartOut so far, by motive (0: all)
   MotionRefSave motref; bool motref_ready=false;                       // PartMotionRef.ibi4
   bool initial_saved, head_saved; unsigned partbegin, partbeginfirst; std::string partbegindir; double partbegintime, partbegindtpre;   // restart (-partbegin)
@@ -169,6 +170,8 @@ static void load_case(b2s_sim* s,const std::string& options){
   if(ep.num("DtFixed",0)!=0)throw std::runtime_error("DtFixed is not supported by this build");
   p.rhopoutmin=float(ep.num("RhopOutMin",700)); p.rhopoutmax=float(ep.num("RhopOutMax",1300));
   s->svposdouble=(ep.inum("SavePosDouble",0)!=0);
+  s->svextraparts=ep.str("SaveExtraParts","");
+  if(s->svextraparts.find_first_not_of("0123456789,-")!=std::string::npos)throw std::runtime_error("SaveExtraParts: a PART interval or a list like 1,4,7-9");
   { // periodic boundaries (JSph.cpp:815-827)
     bool px=false,py=false,pz=false;
     for(int k=0;k<3;k++)p.perixinc[k]=p.periyinc[k]=p.perizinc[k]=0;
@@ -226,6 +229,7 @@ static void load_case(b2s_sim* s,const std::string& options){
         if(!s->partbegin)throw std::runtime_error("-partbegin:0 is not a restart");
       }
       else if(w=="SVSTEPS")s->svallsteps=(a.empty()||atoi(a.c_str())!=0);
+      else if(w=="SVEXTRAPARTS"){ if(a.empty() || a.find_first_not_of("0123456789,-")!=std::string::npos)throw std::runtime_error("-svextraparts: a PART interval or a list like 1,4,7-9"); s->svextraparts=a; }
       else if(w=="SAVEPOSDOUBLE")s->svposdouble=(a.empty()||atoi(a.c_str())!=0);
       else if(w=="B2SVARIANT"){   // interaction kernel (include/b2s.h b2s_set_interaction_variant): 0 = reference summation order (default), 5 = fastest
         s->variant=atoi(a.c_str()); if(a.empty() || (s->variant!=0 && s->variant!=3 && s->variant!=4 && s->variant!=5))throw std::runtime_error("-b2svariant: 0, 3, 4 or 5");
@@ -524,7 +528,6 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   std::unique_ptr<Bi4Item> pdata;
   std::vector<uint32_t> pb_idp; unsigned np_case=np;
   if(s->partbegin){
-    if(p.tboundary==B2S_BC_MDBC)throw std::runtime_error("restart with mDBC is not supported by this build (needs the normals extra data)");
     std::string dir=s->partbegindir; if(!dir.empty() && dir[dir.size()-1]!='/')dir+='/';
     char fn[64]; snprintf(fn,sizeof(fn),"Part_%04u.bi4",s->partbegin);
     pdata=bi4_load(dir+fn);
@@ -731,7 +734,22 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
     if(anor->count!=nbound)throw std::runtime_error("Size of loaded BoundNor data does not match number of boundary particles.");
     if(slab_nranks>0)nor=sel_nor;
     else nor.assign((const float*)anor->ptr(),(const float*)anor->ptr()+size_t(nbound)*3);
-    for(auto& v:nor)v*=2.f;   // boundary->interface normals doubled to reach the ghost node (JSph.cpp:1417)
+    if(!s->partbegin)for(auto& v:nor)v*=2.f;   // boundary->interface normals doubled to reach the ghost node (JSph.cpp:1417)
+    else{
+      // restart: the normals of that PART, already doubled (moving boundaries have turned theirs), from PartExtra_XXXX.bi4
+      // (JSph::ConfigBoundNormals, JSph.cpp:1396-1403; JDsExtraDataLoad::LoadNormals)
+      if(slab_nranks>0)throw std::runtime_error("restart with mDBC and slab decomposition is not supported by this build");
+      std::string dir=s->partbegindir; if(!dir.empty() && dir[dir.size()-1]!='/')dir+='/';
+      char fe[64]; snprintf(fe,sizeof(fe),"PartExtra_%04u.bi4",s->partbegin);
+      struct stat st; if(stat((dir+fe).c_str(),&st)!=0){ char m[128]; snprintf(m,sizeof(m),"No extra data available to restart at PART_%04u with mDBC.",s->partbegin); throw std::runtime_error(m); }
+      std::unique_ptr<Bi4Item> ex=bi4_load(dir+fe);
+      const Bi4Array* qn=ex->array("Normals");
+      const uint32_t nsize=nbound-p.casenfloat;
+      if(ex->get_uint("CaseNbound")!=nbound || !qn || qn->count<nsize)throw std::runtime_error(std::string("restart: ")+fe+" does not belong to this case");
+      std::fill(nor.begin(),nor.end(),0.f);
+      // (boundary particles are never excluded while a run goes on, so slot i of the restarted boundary is id i)
+      for(unsigned i=0;i<nbound && i<np;i++)if(idp[i]<nsize)for(int k=0;k<3;k++)nor[size_t(i)*3+k]=((const float*)qn->ptr())[size_t(idp[i])*3+k];
+    }
     norp=nor.data();
   }
   r=b2s_upload_particles(s->ctx,npsel,idp,code.data(),pos.data(),velrho.data(),norp);
@@ -750,6 +768,21 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
     r=b2s_slab_config(s->ctx,slab_rank,slab_nranks,s->slab_cuts[slab_rank],s->slab_cuts[slab_rank+1]);
     if(r)throw std::runtime_error(std::string("b2s_slab_config failed: ")+b2s_last_error(s->ctx));
   }
+}
+
+// JDsExtraDataSave::Config / CheckSave (JDsExtraData.cpp:70-88): "<n>" = every n-th PART, otherwise a list "1,4,7-9" (JRangeFilter);
+// PART 0 never carries extra data.
+static bool svextra_check(const std::string& cfg,unsigned cpart){
+  if(cfg.empty() || !cpart)return false;
+  if(cfg.find_first_not_of("0123456789")==std::string::npos){ const unsigned n=unsigned(atoi(cfg.c_str())); return n && cpart%n==0; }
+  std::stringstream ss(cfg); std::string tok;
+  while(std::getline(ss,tok,',')){
+    if(tok.empty())continue;
+    const size_t d=tok.find('-');
+    if(d==std::string::npos){ if(unsigned(atoi(tok.c_str()))==cpart)return true; }
+    else{ const unsigned a=unsigned(atoi(tok.substr(0,d).c_str())), b=unsigned(atoi(tok.substr(d+1).c_str())); if(cpart>=a && cpart<=b)return true; }
+  }
+  return false;
 }
 
 // ---- PART output (JSph::SavePartData / JPartDataBi4) ----------------------------------------------------
@@ -868,6 +901,25 @@ static void save_part(b2s_sim* s){
     static const char* fn3[10]={"fvel","fomega","facelin","faceang","extforcelin","extforceang","fluforcelin","fluforceang","preacelin","preaceang"};
     for(int a=0;a<10;a++)pf.add_array_ext(fn3[a],BT_FLOAT3,ftc,f3[a].data());
     bi4_save_listapp(s->dirdata+"PartFloatInfo.ibi4","JPartFloatInfoBi4",hd,&pf,fresh);
+  }
+  if(p.tboundary==B2S_BC_MDBC && svextra_check(s->svextraparts,s->part)){
+    // PartExtra_XXXX.bi4 (JSphCpuSingle::SaveExtraData, JSphCpuSingle.cpp:1309-1322; JDsExtraDataSave::InitPartData/AddNormals,
+    // JDsExtraData.cpp:96-133): the boundary normals by id as the solver holds them (boundary -> ghost node), what a restart needs
+    const uint32_t nsize=p.casenp-p.casenfluid-p.casenfloat;   // UseNormalsFt=false: fixed and moving boundary
+    std::vector<uint32_t> sid(inf.np); std::vector<float> snor(size_t(inf.np)*4);
+    size_t c1=0,c2=0;
+    r=b2s_get_array(s->ctx,"idp",sid.data(),sid.size()*4,&c1);
+    if(!r)r=b2s_get_array(s->ctx,"boundnor",snor.data(),snor.size()*4,&c2);
+    if(r || c1!=c2)throw std::runtime_error(std::string("reading the boundary normals failed: ")+b2s_last_error(s->ctx));
+    std::vector<float> vnor(size_t(nsize)*3,0.f);
+    for(size_t q=0;q<c1;q++)if(sid[q]<nsize)for(int k=0;k<3;k++)vnor[size_t(sid[q])*3+k]=snor[q*4+k];
+    Bi4Item e("JPartExtraBi4");
+    e.set_text("AppName","b200sph v0.1 (DualSPHysics v5.4 case interface)"); e.set_uint("FormatVer",211030);
+    e.set_uint("CaseNbound",p.casenp-p.casenfluid); e.set_uint("CaseNfloat",p.casenfloat);
+    e.set_int("Cpart",int(s->part)); e.set_uint("Step",inf.nstep); e.set_double("TimeStep",inf.timestep); e.set_bool("UseNormalsFt",false);
+    e.add_array_ext("Normals",BT_FLOAT3,nsize,vnor.data());
+    char fe[64]; snprintf(fe,sizeof(fe),"PartExtra_%04u.bi4",s->part);
+    bi4_save(s->dirdata+fe,e,"JPartExtraBi4");
   }
   if(p.casenmoving || p.casenfloat){ // PartMotionRef.ibi4 (JSph::ConfigSaveData, JSph.cpp:2772-2791; JSphCpuSingle.cpp:1272-1274)
     const uint32_t nb=uint32_t(std::lower_bound(idp.begin(),idp.begin()+n,p.casenp-p.casenfluid)-idp.begin());   // ids ascending: the boundary first

@@ -12,6 +12,7 @@
 struct b2s_ctx {
   b2s_params prm; uint32_t np=0; double time=0, dtpre=0; uint32_t nstep=0; int ngauges=0;
   std::vector<uint32_t> idp; std::vector<uint16_t> code; std::vector<double> pos; std::vector<float> velrho;
+  std::vector<float> nor4;            // boundary normals as the device keeps them (float4 per particle, zero for the fluid)
   std::vector<b2s_floating> fts;
 };
 static const double FROZEN_DT=1.0/1024.0;   // exact in binary: the PART schedule of a test is the same on every machine
@@ -20,8 +21,23 @@ extern "C" {
 int b2s_create(const b2s_params* p,int,uint32_t,b2s_ctx** out){ if(!p||!out)return B2S_ERR_ARG; b2s_ctx* c=new b2s_ctx; c->prm=*p; *out=c; return B2S_OK; }
 int b2s_destroy(b2s_ctx* c){ delete c; return B2S_OK; }
 const char* b2s_last_error(const b2s_ctx*){ return "frozen device"; }
-int b2s_upload_particles(b2s_ctx* c,uint32_t np,const uint32_t* idp,const uint16_t* code,const double* pos,const float* velrho,const float*){
+int b2s_upload_particles(b2s_ctx* c,uint32_t np,const uint32_t* idp,const uint16_t* code,const double* pos,const float* velrho,const float* boundnor){
   c->np=np; c->idp.assign(idp,idp+np); c->code.assign(code,code+np); c->pos.assign(pos,pos+size_t(np)*3); c->velrho.assign(velrho,velrho+size_t(np)*4);
+  c->nor4.assign(size_t(np)*4,0.f);
+  if(boundnor){   // one float3 per boundary particle, the boundary comes first
+    const uint32_t nbound=c->prm.casenp-c->prm.casenfluid;
+    uint32_t nb=0; while(nb<np && idp[nb]<nbound)nb++;
+    for(uint32_t i=0;i<nb;i++)for(int k=0;k<3;k++)c->nor4[size_t(i)*4+k]=boundnor[size_t(i)*3+k];
+  }
+  return B2S_OK;
+}
+int b2s_get_array(b2s_ctx* c,const char* name,void* dst,size_t capacity_bytes,size_t* count_out){
+  const void* src=NULL; size_t bytes=0;
+  if(!strcmp(name,"idp")){ src=c->idp.data(); bytes=size_t(c->np)*4; }
+  else if(!strcmp(name,"boundnor") && c->prm.tboundary==B2S_BC_MDBC){ src=c->nor4.data(); bytes=size_t(c->np)*16; }
+  else return B2S_ERR_ARG;
+  if(capacity_bytes<bytes)return B2S_ERR_ARG;
+  memcpy(dst,src,bytes); if(count_out)*count_out=c->np;
   return B2S_OK;
 }
 int b2s_download_particles_byid(b2s_ctx* c,uint32_t* np_out,uint32_t* idp,double* pos,float* vel,float* rhop){

@@ -236,3 +236,33 @@ def test_gauge_schedule_matches_the_restated_rules(cli, tmp_path, refdir):
         ours = [float(ln.split(";")[0]) for ln in rows]
         want = [row[0] for row in go.rows[g["name"]]]
         assert len(ours) == len(want) and np.allclose(ours, want, atol=6e-7, rtol=0), (g["name"], ours[:5], want[:5])
+
+
+def test_mdbc_restart_goes_through_the_extra_data_file(cli, tmp_path):
+    """-svextraparts writes PartExtra_XXXX.bi4 like the reference (tests/golden/ref_part_extra/: same item, values, array; for fixed
+    boundaries the same normals, i.e. twice the case's), and a restart with mDBC takes its normals from that file -- undoubled, so a
+    second generation of the file is identical to the first -- or stops with the reference's message when the file is missing."""
+    ref = os.path.join(H.GOLDEN, "ref_part_extra")
+    fx = json.load(open(os.path.join(ref, "fixture_extra.json")))
+    H.write_case(tmp_path, **fx["spec"])
+    a, b, c = tmp_path / "runA", tmp_path / "runB", tmp_path / "runC"
+    r = _run(cli, tmp_path / "Case", a, *fx["options"])
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert not (a / "data" / "PartExtra_0000.bi4").exists()
+    ours, theirs = bi4.load(str(a / "data" / "PartExtra_0001.bi4")), bi4.load(os.path.join(ref, "PartExtra_0001.bi4"))
+    assert _structure(ours) == _structure(theirs)
+    for name in ("FormatVer", "CaseNbound", "CaseNfloat", "Cpart", "UseNormalsFt"):
+        assert ours.get(name) == theirs.get(name), name
+    assert np.array_equal(ours.array("Normals"), theirs.array("Normals"))
+    # restart from PART 1 with the extra data, again saving extra data: PART 2 of the restart holds the same normals
+    r = _run(cli, tmp_path / "Case", b, "-partbegin:1", str(a / "data"), *fx["options"])
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    again = bi4.load(str(b / "data" / "PartExtra_0002.bi4"))
+    assert np.array_equal(again.array("Normals"), ours.array("Normals")) and again.get("Cpart") == 2
+    # without the file: the reference's error
+    os.remove(a / "data" / "PartExtra_0001.bi4")
+    r = _run(cli, tmp_path / "Case", c, "-partbegin:1", str(a / "data"))
+    assert r.returncode != 0 and "No extra data available to restart at PART_0001 with mDBC." in (r.stdout + r.stderr)
+    # the list form of the option
+    r = _run(cli, tmp_path / "Case", c, "-svextraparts:2,5-7")
+    assert r.returncode == 0 and sorted(f for f in os.listdir(c / "data") if f.startswith("PartExtra")) == ["PartExtra_0002.bi4"]
