@@ -62,6 +62,7 @@ struct b2s_sim {
   std::vector<GaugeCfg> gauges;
   std::vector<DampCfg> dampings;
   int variant=0;                                                        // -b2svariant
+  unsigned piece=0, npiece=1;                                           // slab rank / ranks: PART files are written as pieces (JPartDataBi4.cpp:99-127)
   std::string svextraparts;                                             // -svextraparts / SaveExtraParts: PARTs that get a PartExtra_XXXX.bi4
   unsigned out_total[4]={0,0,0,0};                                    // excluded particles written to PartOut so far, by motive (0: all)
   MotionRefSave motref; bool motref_ready=false;                       // PartMotionRef.ibi4
@@ -798,7 +799,8 @@ static void save_part(b2s_sim* s){
   // JPartDataHead::SaveFile, JSph::AddBasicInfo; checked against reference output by tests/test_part_files.py).
   Bi4Item d("JPartDataBi4");
   const double zero3[3]={0,0,0};
-  d.set_uint("Piece",0); d.set_uint("Npiece",1); d.set_text("RunCode",s->runcode); d.set_text("Date",s->date);
+  const bool pieces=(s->npiece>1);   // one piece per slab rank: list files that need the whole case are left to single-GPU runs
+  d.set_uint("Piece",s->piece); d.set_uint("Npiece",s->npiece); d.set_text("RunCode",s->runcode); d.set_text("Date",s->date);
   d.set_text("AppName","b200sph v0.1 (DualSPHysics v5.4 case interface)"); d.set_text("CaseName",s->casename); d.set_bool("Data2d",p.simulate2d!=0); d.set_double("Data2dPosY",0);
   d.set_double3("MapPosMin",p.maprealposmin); d.set_double3("MapPosMax",p.maprealposmax);
   d.set_int("PeriMode",0); d.set_double3("PeriXinc",zero3); d.set_double3("PeriYinc",zero3); d.set_double3("PeriZinc",zero3);
@@ -815,7 +817,7 @@ static void save_part(b2s_sim* s){
   // particles excluded since the previous PART (JSph::AddParticlesOut / PartsOut): drained from the device buffer
   uint32_t nout=0; unsigned nmot[4]={0,0,0,0};
   std::vector<uint32_t> oid; std::vector<double> opos; std::vector<float> ovel, orho; std::vector<uint8_t> omot;
-  {
+  if(!pieces){
     const uint32_t ocap=std::max(p.casenfluid,1024u);
     oid.resize(ocap); opos.resize(size_t(ocap)*3); ovel.resize(size_t(ocap)*3); orho.resize(ocap); omot.resize(ocap);
     r=b2s_out_fetch(s->ctx,ocap,&nout,oid.data(),opos.data(),ovel.data(),orho.data(),omot.data());
@@ -845,16 +847,18 @@ static void save_part(b2s_sim* s){
   else{ posf.resize(size_t(n)*3); for(size_t i=0;i<size_t(n)*3;i++)posf[i]=float(pos[i]); pt->add_array_ext("Pos",BT_FLOAT3,n,posf.data()); }
   pt->add_array_ext("Vel",BT_FLOAT3,n,vel.data());
   pt->add_array_ext("Rhop",BT_FLOAT,n,rho.data());
-  char fn[64]; snprintf(fn,sizeof(fn),"Part_%04u.bi4",s->part);
+  char fn[64];
+  if(pieces)snprintf(fn,sizeof(fn),"Part_p%02u_%04u.bi4",s->piece,s->part); else snprintf(fn,sizeof(fn),"Part_%04u.bi4",s->part);
   bi4_save(s->dirdata+fn,d,"JPartDataBi4");
   const bool firstsave=!s->head_saved;
   const bool fresh=(firstsave && !s->partbeginfirst);   // a restart that continues the numbering appends to the list files
   { // PartInfo.ibi4 (JPartDataBi4::SaveFileInfo, JPartDataBi4.cpp): the head values + one item of values per PART
     Bi4Item hd("JPartDataBi4"); hd.values=d.values;
     Bi4Item pi(nm); pi.hide=true; pi.values=pt->values;
-    bi4_save_listapp(s->dirdata+"PartInfo.ibi4","JPartDataBi4_Info",hd,&pi,fresh);
+    char fi[64]; if(pieces)snprintf(fi,sizeof(fi),"PartInfo_p%02u.ibi4",s->piece); else snprintf(fi,sizeof(fi),"PartInfo.ibi4");
+    bi4_save_listapp(s->dirdata+fi,"JPartDataBi4_Info",hd,&pi,fresh);
   }
-  { // PartOut_000.obi4 (JPartOutBi4Save::ConfigBasic/ConfigParticles/ConfigLimits/SavePartOut, JPartOutBi4Save.cpp:119-232)
+  if(!pieces){ // PartOut_000.obi4 (JPartOutBi4Save::ConfigBasic/ConfigParticles/ConfigLimits/SavePartOut, JPartOutBi4Save.cpp:119-232)
     Bi4Item hd("JPartOutBi4");
     hd.set_uint("Piece",0); hd.set_uint("Npiece",1); hd.set_text("RunCode",s->runcode); hd.set_text("Date",s->date);
     hd.set_text("AppName","b200sph v0.1 (DualSPHysics v5.4 case interface)"); hd.set_bool("Data2d",p.simulate2d!=0);
@@ -872,7 +876,7 @@ static void save_part(b2s_sim* s){
     po.add_array_ext("Vel",BT_FLOAT3,nout,ovel.data()); po.add_array_ext("Rhop",BT_FLOAT,nout,orho.data()); po.add_array_ext("Motive",BT_UCHAR,nout,omot.data());
     if(firstsave || nout)bi4_save_listapp(s->dirdata+"PartOut_000.obi4","JPartOutBi4",hd,(nout? &po: NULL),fresh);
   }
-  if(p.casenfloat){ // PartFloatInfo.ibi4 (JPartFloatInfoBi4Save::Config/MakeBdPartSingle/SaveBdPart, JPartFloatInfoBi4.cpp:464-602)
+  if(p.casenfloat && (!pieces || s->piece==0)){ // PartFloatInfo.ibi4 (every rank holds the same body state: rank 0 writes it) (JPartFloatInfoBi4Save::Config/MakeBdPartSingle/SaveBdPart, JPartFloatInfoBi4.cpp:464-602)
     std::vector<const PartBlock*> fb; for(auto& b:s->blocks)if(b.type==2)fb.push_back(&b);
     const unsigned ftc=unsigned(fb.size());
     std::vector<b2s_floating> fts(ftc);
@@ -902,7 +906,7 @@ static void save_part(b2s_sim* s){
     for(int a=0;a<10;a++)pf.add_array_ext(fn3[a],BT_FLOAT3,ftc,f3[a].data());
     bi4_save_listapp(s->dirdata+"PartFloatInfo.ibi4","JPartFloatInfoBi4",hd,&pf,fresh);
   }
-  if(p.tboundary==B2S_BC_MDBC && svextra_check(s->svextraparts,s->part)){
+  if(!pieces && p.tboundary==B2S_BC_MDBC && svextra_check(s->svextraparts,s->part)){
     // PartExtra_XXXX.bi4 (JSphCpuSingle::SaveExtraData, JSphCpuSingle.cpp:1309-1322; JDsExtraDataSave::InitPartData/AddNormals,
     // JDsExtraData.cpp:96-133): the boundary normals by id as the solver holds them (boundary -> ghost node), what a restart needs
     const uint32_t nsize=p.casenp-p.casenfluid-p.casenfloat;   // UseNormalsFt=false: fixed and moving boundary
@@ -921,7 +925,7 @@ static void save_part(b2s_sim* s){
     char fe[64]; snprintf(fe,sizeof(fe),"PartExtra_%04u.bi4",s->part);
     bi4_save(s->dirdata+fe,e,"JPartExtraBi4");
   }
-  if(p.casenmoving || p.casenfloat){ // PartMotionRef.ibi4 (JSph::ConfigSaveData, JSph.cpp:2772-2791; JSphCpuSingle.cpp:1272-1274)
+  if(!pieces && (p.casenmoving || p.casenfloat)){ // PartMotionRef.ibi4 (JSph::ConfigSaveData, JSph.cpp:2772-2791; JSphCpuSingle.cpp:1272-1274)
     const uint32_t nb=uint32_t(std::lower_bound(idp.begin(),idp.begin()+n,p.casenp-p.casenfluid)-idp.begin());   // ids ascending: the boundary first
     unsigned mkboundfirst=0; for(auto& b:s->blocks)if(b.type!=3){ mkboundfirst=b.mk-b.mktype; break; }
     if(!s->motref_ready){   // reference particles from the state of the first PART of the run (the initial or the restarted one)
@@ -932,6 +936,7 @@ static void save_part(b2s_sim* s){
     s->motref.save_part(s->dirdata,"b200sph v0.1 (DualSPHysics v5.4 case interface)",s->timepart,mkboundfirst,fresh,
                         s->part,inf.timestep,inf.nstep,nb,idp.data(),pos.data());
   }
+  if(!s->head_saved && s->piece!=0)s->head_saved=true;   // Part_Head.ibi4 comes from rank 0
   if(!s->head_saved){
     s->head_saved=true;
     // Part_Head.ibi4 (JPartDataHead::SaveFile, JPartDataHead.cpp): head values + MkBlocks
@@ -939,7 +944,7 @@ static void save_part(b2s_sim* s){
     h.set_uint("FmtVersion",180324);
     h.set_text("AppName","b200sph v0.1 (DualSPHysics v5.4 case interface)"); h.set_text("Date",s->date); h.set_text("RunCode",s->runcode);
     h.set_text("CaseName",s->casename); h.set_bool("Data2d",p.simulate2d!=0); h.set_double("Data2dPosY",0);
-    h.set_uint("Npiece",1); h.set_uint("FirstPart",0);
+    h.set_uint("Npiece",s->npiece); h.set_uint("FirstPart",0);
     h.set_double3("CasePosMin",s->caseposmin); h.set_double3("CasePosMax",s->caseposmax); h.set_bool("NpDynamic",false); h.set_bool("ReuseIds",false);
     h.set_double3("MapPosMin",p.maprealposmin); h.set_double3("MapPosMax",p.maprealposmax);
     h.set_int("PeriMode",0); h.set_double3("PeriXinc",zero3); h.set_double3("PeriYinc",zero3); h.set_double3("PeriZinc",zero3);
@@ -1023,11 +1028,19 @@ extern "C" int b2s_sim_load_slab(const char* casepath,const char* options,int de
     if(s->casepath.size()>4 && lower(s->casepath.substr(s->casepath.size()-4))==".xml")s->casepath.resize(s->casepath.size()-4);
     size_t sl=s->casepath.find_last_of('/');
     s->casename=(sl==std::string::npos? s->casepath: s->casepath.substr(sl+1));
+    s->piece=unsigned(rank); s->npiece=unsigned(nranks);
     load_case(s,options? options: "");
     load_particles_and_create(s,device,0,rank,nranks);
   }
   catch(const std::exception& e){ g_host_err=e.what(); if(s->ctx)b2s_destroy(s->ctx); delete s; return B2S_ERR_IO; }
   *out=s;
+  return B2S_OK;
+}
+// Output directory of a slab rank: every rank writes its own piece Part_pRR_XXXX.bi4 / PartInfo_pRR.ibi4, rank 0 also Part_Head.ibi4.
+extern "C" int b2s_sim_set_dirout(b2s_sim* s,const char* dirout){
+  if(!s||!dirout||!dirout[0])return B2S_ERR_ARG;
+  try{ s->dirout=dirout; if(s->dirout[s->dirout.size()-1]!='/')s->dirout+='/'; s->dirdata=s->dirout+"data/"; mkdirs(s->dirdata); }
+  catch(const std::exception& e){ g_host_err=e.what(); return B2S_ERR_IO; }
   return B2S_OK;
 }
 extern "C" int b2s_sim_slab_info(b2s_sim* s,uint32_t* cuts,uint32_t ncuts,uint32_t* max_plane_particles){

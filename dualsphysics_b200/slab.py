@@ -468,6 +468,18 @@ class SlabSimulation:
         """After re-uploading the owned particles: move migrants, rebuild halos, divide."""
         self._exchange()
 
+    def set_dirout(self, dirout: str):
+        """PART output of a multi-GPU run: every rank writes its own piece (Part_pRR_XXXX.bi4, the reference's piece format,
+        JPartDataBi4.cpp:99-127); nothing is gathered."""
+        for r in self.ranks:
+            r.sim.set_dirout(dirout)
+
+    def save_part(self):
+        """Writes the next PART: a rank saves the particles it owns (halo ghosts carry CODE_PERIODIC and are skipped by the
+        download), so every particle of the case lands in exactly one piece."""
+        for r in self.ranks:
+            r.sim.save_part()
+
     def gather_byid(self):
         """Owned particles of the local ranks, sorted by id: (idp, pos, velrho)."""
         ids, pos, vr = [], [], []

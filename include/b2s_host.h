@@ -21,6 +21,10 @@ int b2s_sim_load(const char* casepath, const char* dirout, const char* options, 
  * reads the same case, derives the same balanced cut planes along x from the particle histogram, uploads ONLY its slab
  * and calls b2s_slab_config.  With mDBC the halo is two kernel radii wide (boundary ghosts recompute their ghost-node density locally). */
 int b2s_sim_load_slab(const char* casepath, const char* options, int device, int rank, int nranks, b2s_sim** out);
+/* PART output of a slab rank: every rank writes its own piece of each PART the way the reference's format provides for
+ * (src/source/JPartDataBi4.cpp:99-127: Part_pRR_XXXX.bi4, PartInfo_pRR.ibi4, head values Piece / Npiece), rank 0 also Part_Head.ibi4
+ * and PartFloatInfo.ibi4; no gather.  Call once after b2s_sim_load_slab, then b2s_sim_save_part on every rank at the same step. */
+int b2s_sim_set_dirout(b2s_sim* sim, const char* dirout);
 /* cuts[nranks+1] (cell planes along x) and the particle count of the densest plane (sizes the exchange buffers). */
 int b2s_sim_slab_info(b2s_sim* sim, uint32_t* cuts, uint32_t ncuts, uint32_t* max_plane_particles);
 int b2s_sim_free(b2s_sim* sim);

@@ -266,3 +266,43 @@ def test_mdbc_restart_goes_through_the_extra_data_file(cli, tmp_path):
     # the list form of the option
     r = _run(cli, tmp_path / "Case", c, "-svextraparts:2,5-7")
     assert r.returncode == 0 and sorted(f for f in os.listdir(c / "data") if f.startswith("PartExtra")) == ["PartExtra_0002.bi4"]
+
+
+def test_slab_ranks_write_part_pieces(frozen, tmp_path):
+    """PART output of a multi-GPU run (b2s_sim_set_dirout + b2s_sim_save_part on every rank): one piece per rank in the reference's piece
+    format (JPartDataBi4.cpp:99-127: Part_pRR_XXXX.bi4 with Piece / Npiece in the head, PartInfo_pRR.ibi4), Part_Head.ibi4 from rank 0,
+    and the pieces of a PART hold every particle of the case exactly once."""
+    import ctypes as C
+    lib = C.CDLL(frozen["lib"])
+    lib.b2s_host_last_error.restype = C.c_char_p
+    H.write_case(tmp_path, dp=0.04, floating_box=(0.15, 0.25, 0.2, 0.1, 0.15, 0.1), floating_rel_density=0.5)
+    case, out = str(tmp_path / "Case").encode(), tmp_path / "out"
+    allp = bi4.load_part(str(tmp_path / "Case.bi4"))
+    nranks = 3
+    sims = []
+    for rank in range(nranks):
+        sim = C.c_void_p()
+        assert lib.b2s_sim_load_slab(case, b"-symplectic", 0, rank, nranks, C.byref(sim)) == 0, lib.b2s_host_last_error().decode()
+        assert lib.b2s_sim_set_dirout(sim, str(out).encode()) == 0
+        sims.append(sim)
+    for cpart in range(2):
+        for sim in sims:
+            assert lib.b2s_sim_save_part(sim) == 0, lib.b2s_host_last_error().decode()
+    files = sorted(os.listdir(out / "data"))
+    assert files == sorted([f"Part_p{r:02d}_{c:04d}.bi4" for r in range(nranks) for c in range(2)] + [f"PartInfo_p{r:02d}.ibi4" for r in range(nranks)]
+                           + ["Part_Head.ibi4", "PartFloatInfo.ibi4"])
+    ref = bi4.load(os.path.join(H.GOLDEN, "ref_part", "Part_0002.bi4"))
+    ids = []
+    for r in range(nranks):
+        root = bi4.load(str(out / "data" / f"Part_p{r:02d}_0001.bi4"))
+        assert root.get("Piece") == r and root.get("Npiece") == nranks and root.get("CaseNp") == len(allp["Idp"])
+        assert [(n, t) for n, t, _ in root.values] == [(n, t) for n, t, _ in ref.values]            # the reference's head
+        part = root.item("PART_0001")
+        assert [(n, t) for n, t, _ in part.arrays] == [(n, t) for n, t, _ in ref.item("PART_0002").arrays]
+        assert part.get("Npok") == len(part.array("Idp")) > 0
+        ids.append(np.asarray(part.array("Idp")))
+    ids = np.concatenate(ids)
+    assert len(ids) == len(allp["Idp"]) and np.array_equal(np.sort(ids), np.sort(allp["Idp"]))
+    assert bi4.load(str(out / "data" / "Part_Head.ibi4")).get("Npiece") == nranks
+    for sim in sims:
+        lib.b2s_sim_free(sim)
