@@ -9,6 +9,7 @@ python -m pytest tests -q -m gpu 2>&1 | tail -4 > gpurun_out/r02_gpu_tests.log; 
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_n1_base.json 2> gpurun_out/r02_bench_n1_base.err; head -c 330 gpurun_out/r02_bench_n1_base.json; echo
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_base.csv python bench.py --steps 2 --warmup 3 > gpurun_out/r02_launches_base.log 2>&1
 python tools/summarize_launches.py gpurun_out/r02_launches_base.csv 2>/dev/null | head -12
+python tools/gpu_r2_checks.py 2>&1 | tail -8 > gpurun_out/r02_host_checks.log; cat gpurun_out/r02_host_checks.log
 k=0
 for flags in "-DP2_VNOW=1" "-DP2_CHK2=1" "-DP2_VNOW=1 -DP2_CHK2=1"; do
   k=$((k+1))
