@@ -1058,6 +1058,14 @@ extern "C" int b2s_sim_stats(b2s_sim* s,uint32_t* parts,uint32_t* excluded4){
   if(excluded4)for(int k=0;k<4;k++)excluded4[k]=s->out_total[k];
   return B2S_OK;
 }
+// Test entry point of the XML reader (include/b2s_host.h): elements and attributes of a file, counted over the whole tree.
+static void xml_count(const XmlNode* n,uint32_t& ne,uint32_t& na){ ne++; na+=uint32_t(n->attrs.size()); for(auto& c:n->children)xml_count(c.get(),ne,na); }
+extern "C" int b2s_host_xml_stats(const char* file,uint32_t* elements,uint32_t* attributes){
+  if(!file)return B2S_ERR_ARG;
+  try{ std::unique_ptr<XmlNode> root=xml_load(file); uint32_t ne=0,na=0; xml_count(root.get(),ne,na); if(elements)*elements=ne; if(attributes)*attributes=na; }
+  catch(const std::exception& e){ g_host_err=e.what(); return B2S_ERR_IO; }
+  return B2S_OK;
+}
 // Test entry point of the PartMotionRef.ibi4 writer on host arrays (include/b2s_host.h).
 extern "C" int b2s_host_motionref_write(const char* dirdata,uint32_t nbodies,const uint8_t* floating,const uint16_t* mkbound,
     const uint32_t* begin,const uint32_t* count,double timeout,uint32_t mkboundfirst,uint32_t nparts,uint32_t n,const uint32_t* idp,

@@ -106,7 +106,7 @@ ABI_SYMBOLS = [
     "b2s_slab_histogram", "b2s_slab_set_range", "b2s_slab_drop_ghosts", "b2s_slab_record_bytes", "b2s_slab_pack", "b2s_slab_unpack", "b2s_slab_pack_both", "b2s_slab_unpack_both", "b2s_slab_dt_buffer", "b2s_slab_forces",
     "b2s_slab_apply_dt", "b2s_slab_integrate", "b2s_slab_step_end", "b2s_slab_ft_sums", "b2s_slab_ft_apply",
     "b2s_sim_load", "b2s_sim_load_slab", "b2s_sim_slab_info", "b2s_sim_free", "b2s_sim_ctx", "b2s_sim_params", "b2s_sim_stats", "b2s_sim_set_dirout", "b2s_sim_save_part", "b2s_sim_run",
-    "b2s_host_motionref_write", "b2s_host_last_error",
+    "b2s_host_motionref_write", "b2s_host_xml_stats", "b2s_host_last_error",
 ]
 
 _lib = None
@@ -194,6 +194,7 @@ def load_library():
     lib.b2s_sim_params.argtypes = [vp, C.POINTER(Params)]
     lib.b2s_sim_save_part.argtypes = [vp]
     lib.b2s_sim_set_dirout.argtypes = [vp, C.c_char_p]
+    lib.b2s_host_xml_stats.argtypes = [C.c_char_p, u32p, u32p]
     lib.b2s_sim_stats.argtypes = [vp, u32p, u32p]
     lib.b2s_sim_run.argtypes = [vp, C.c_uint32, C.POINTER(C.c_double), u32p]
     lib.b2s_host_motionref_write.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,

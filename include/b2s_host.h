@@ -44,6 +44,9 @@ int b2s_host_motionref_write(const char* dirdata, uint32_t nbodies, const uint8_
                              const uint32_t* begin, const uint32_t* count, double timeout, uint32_t mkboundfirst,
                              uint32_t nparts, uint32_t n, const uint32_t* idp, const double* pos,
                              const double* timestep, const uint32_t* step);
+/* The driver's XML reader (csrc/host/xml_lite.cpp, in place of the reference's tinyxml/JXml) on any file: number of elements and
+ * of attributes of the whole tree.  Test entry point: the reader is checked against every XML file the reference ships. */
+int b2s_host_xml_stats(const char* file, uint32_t* elements, uint32_t* attributes);
 const char* b2s_host_last_error(void);
 #ifdef __cplusplus
 }
