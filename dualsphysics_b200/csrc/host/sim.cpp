@@ -803,7 +803,7 @@ static void save_part(b2s_sim* s){
   d.set_uint("Piece",s->piece); d.set_uint("Npiece",s->npiece); d.set_text("RunCode",s->runcode); d.set_text("Date",s->date);
   d.set_text("AppName","b200sph v0.1 (DualSPHysics v5.4 case interface)"); d.set_text("CaseName",s->casename); d.set_bool("Data2d",p.simulate2d!=0); d.set_double("Data2dPosY",0);
   d.set_double3("MapPosMin",p.maprealposmin); d.set_double3("MapPosMax",p.maprealposmax);
-  d.set_int("PeriMode",0); d.set_double3("PeriXinc",zero3); d.set_double3("PeriYinc",zero3); d.set_double3("PeriZinc",zero3);
+  d.set_int("PeriMode",p.periactive); d.set_double3("PeriXinc",(p.periactive&1)? p.perixinc: zero3); d.set_double3("PeriYinc",(p.periactive&2)? p.periyinc: zero3); d.set_double3("PeriZinc",(p.periactive&4)? p.perizinc: zero3);   // TpPeriMode = axis bit mask (DualSphDef.h)
   d.set_int("AxisDiv",0);
   d.set_ullong("CaseNp",p.casenp); d.set_ullong("CaseNfixed",p.casenfixed); d.set_ullong("CaseNmoving",p.casenmoving);
   d.set_ullong("CaseNfloat",p.casenfloat); d.set_ullong("CaseNfluid",p.casenfluid);
@@ -947,7 +947,7 @@ static void save_part(b2s_sim* s){
     h.set_uint("Npiece",s->npiece); h.set_uint("FirstPart",0);
     h.set_double3("CasePosMin",s->caseposmin); h.set_double3("CasePosMax",s->caseposmax); h.set_bool("NpDynamic",false); h.set_bool("ReuseIds",false);
     h.set_double3("MapPosMin",p.maprealposmin); h.set_double3("MapPosMax",p.maprealposmax);
-    h.set_int("PeriMode",0); h.set_double3("PeriXinc",zero3); h.set_double3("PeriYinc",zero3); h.set_double3("PeriZinc",zero3);
+    h.set_int("PeriMode",p.periactive); h.set_double3("PeriXinc",(p.periactive&1)? p.perixinc: zero3); h.set_double3("PeriYinc",(p.periactive&2)? p.periyinc: zero3); h.set_double3("PeriZinc",(p.periactive&4)? p.perizinc: zero3);
     h.set_uint("ViscoType",unsigned(p.tvisco)); h.set_float("ViscoValue",p.visco); h.set_float("ViscoBoundFactor",p.viscoboundfactor);
     h.set_bool("Symmetry",false); h.set_bool("Splitting",false);
     h.set_double("Dp",s->casedp); h.set_double("H",s->caseh); h.set_double("B",s->caseb); h.set_double("Gamma",s->casegamma); h.set_double("RhopZero",s->caserhop0);

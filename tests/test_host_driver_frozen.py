@@ -162,6 +162,14 @@ def test_every_accepted_configuration_loads_and_steps(cli, tmp_path):
         r = _run(cli, d / "Case", d / "out", "-nsteps:3", *options.split())
         assert r.returncode == 0 and "Finished execution (code=0)" in r.stdout, (k, r.stdout[-800:] + r.stderr[-800:])
         assert (d / "out" / "data" / "Part_0000.bi4").exists() and "Steps of simulation..............: 3" in r.stdout
+        # periodic axes reach the heads of the PART files (TpPeri = axis bit mask, increment = minus the domain size on its axis)
+        mode = sum({"x": 1, "y": 2, "z": 4}[c] for c in spec.get("open_axes", ""))
+        for name, root in (("Part_Head.ibi4", None), ("Part_0000.bi4", None)):
+            root = bi4.load(str(d / "out" / "data" / name))
+            assert root.get("PeriMode") == mode, (k, name)
+            if mode & 2:
+                inc = root.get("PeriYinc")
+                assert inc[1] < 0 and abs(inc[1] + (root.get("MapPosMax")[1] - root.get("MapPosMin")[1])) < 1e-12
 
 
 def test_slab_loading_partitions_the_case(frozen, tmp_path):
