@@ -64,6 +64,18 @@ def test_part_files_and_head(cli, tmp_path):
     for name in ("Part_0002.bi4", "Part_Head.ibi4"):
         so, sr = _structure(bi4.load(str(out / "data" / name))), _structure(bi4.load(os.path.join(ref, name)))
         assert so == sr, f"{name}: structure differs\nours={so}\nref ={sr}"
+    # Part_Head.ibi4: every value and array of the reference's file (case constants, viscosity, MK blocks ...) except who wrote it and when
+    def same_values(a, b, path=""):
+        for (n, _, va), (_, _, vb) in zip(a.values, b.values):
+            if n in ("AppName", "Date", "RunCode"):
+                continue
+            ok = np.allclose(va, vb, rtol=1e-6, atol=0) if isinstance(va, (float, tuple, list, np.ndarray)) else va == vb
+            assert ok, (path + a.name, n, va, vb)
+        for (n, _, va), (_, _, vb) in zip(a.arrays, b.arrays):
+            assert np.allclose(np.asarray(va, np.float64), np.asarray(vb, np.float64), rtol=1e-6, atol=0), (path + a.name, n)
+        for ca, cb in zip(a.items, b.items):
+            same_values(ca, cb, path + a.name + "/")
+    same_values(bi4.load(str(out / "data" / "Part_Head.ibi4")), bi4.load(os.path.join(ref, "Part_Head.ibi4")))
     # PART schedule (JDsOutputTime::GetNextTime): the first step whose time reaches 0.002, 0.004
     for k, tmin in ((0, 0.0), (1, 0.002), (2, 0.004)):
         p = bi4.load_part(str(out / "data" / f"Part_{k:04d}.bi4"))
