@@ -14,7 +14,7 @@ k=0
 for flags in "-DP2_VNOW=1" "-DP2_CHK2=1" "-DP2_VNOW=1 -DP2_CHK2=1"; do
   k=$((k+1))
   touch dualsphysics_b200/csrc/forces_pair2.cu
-  make -C dualsphysics_b200/csrc EXTRA="$flags" 2>&1 | tail -1 | cut -c1-80
+  make -C dualsphysics_b200/csrc B2S_NVCC_EXTRA="$flags" 2>&1 | tail -1 | cut -c1-80
   echo "== experiment $k: $flags"
   python -m pytest tests/test_gpu_parity.py -q -m gpu 2>&1 | tail -3 > gpurun_out/r02_x${k}_parity.log; cat gpurun_out/r02_x${k}_parity.log
   timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_n1_x${k}.json 2> gpurun_out/r02_bench_n1_x${k}.err; head -c 330 gpurun_out/r02_bench_n1_x${k}.json; echo
