@@ -17,7 +17,7 @@ for flags in "-DP2_VNOW=1" "-DP2_CHK2=1" "-DP2_VNOW=1 -DP2_CHK2=1"; do
   make -C dualsphysics_b200/csrc B2S_NVCC_EXTRA="$flags" 2>&1 | tail -1 | cut -c1-80
   echo "== experiment $k: $flags"
   python -m pytest tests/test_gpu_parity.py -q -m gpu 2>&1 | tail -3 > gpurun_out/r02_x${k}_parity.log; cat gpurun_out/r02_x${k}_parity.log
-  timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_n1_x${k}.json 2> gpurun_out/r02_bench_n1_x${k}.err; head -c 330 gpurun_out/r02_bench_n1_x${k}.json; echo
+  timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r02_bench_n1_x${k}.json 2> gpurun_out/r02_bench_n1_x${k}.err; head -c 330 gpurun_out/r02_bench_n1_x${k}.json; echo
 done
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_forces_fluid_pair2 -s 2 -c 1 -f -o gpurun_out/r02_forces_pair2_x3_10M python tools/profile_forces.py 10000000 5 3 > gpurun_out/r02_prof_x3.log 2>&1
 tail -1 gpurun_out/r02_prof_x3.log
