@@ -35,14 +35,14 @@
 #endif
 
 #ifndef P2_VNOW
-#define P2_VNOW 0            // 1 (experiment, not measured yet): the exact-test branch of a round also depends on the velrho gathers, so
+#define P2_VNOW 1            // 1 (default since r02: 11.41 -> 10.91 ms at 10M, profiles/r02_pair2_ab.txt): the exact-test branch of a round also depends on the velrho gathers, so
                              // that ptxas cannot sink them below it and a round waits once for four gathers instead of twice for two
                              // (profiles/README.md: the wait at their first use holds 8.8% of the stall samples; a volatile load does
                              // not help, the sinking happens in ptxas).  Mirror-row loop only.
 #endif
 
 #ifndef P2_CHK2
-#define P2_CHK2 0            // 1 (experiment, not measured yet): leaner FP16 pre-filter of the mirror-row loop -- no per-pair index clamp
+#define P2_CHK2 1            // 1 (default since r02: 11.41 -> 10.55 ms, both together 10.16 ms): leaner FP16 pre-filter of the mirror-row loop -- no per-pair index clamp
                              // (posh is padded), mask bits as immediates, one x-block select per pair instead of two.
 #endif
 
