@@ -367,7 +367,7 @@ def main():
         fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12      # 148 SMs x 128 lanes x 2 flop x max SM clock
         gbs_k = BYTES_INTER * npf / (ms_k * 1e-3) / 1e9
         gbs_step = BYTES_STEP * np_total / (secs / a.steps) / 1e9
-        roofline = {"kernel": (f"k_forces_fluid_pair2 (fluid<-fluid+bound interaction, variant {a.variant})" if a.variant in (4, 5) else "k_forces_fluid_gather (fluid<-fluid+bound interaction)"), "bound": "fp32", "achieved": tf_ach, "peak": fp32_peak,
+        roofline = {"kernel": ({4: "k_forces_fluid_pair2", 5: "k_forces_fluid_pair2", 6: "k_forces_fluid_tile"}.get(a.variant, "k_forces_fluid_gather") + f" (fluid<-fluid+bound interaction, variant {a.variant})"), "bound": "fp32", "achieved": tf_ach, "peak": fp32_peak,
                     "unit": "TFLOP/s", "frac": tf_ach / fp32_peak, "traffic": int(NCU_TRAFFIC_BYTES * npf / NCU_TRAFFIC_NPF),
                     "traffic_note": "dram__bytes_read.sum+dram__bytes_write.sum per launch from profiles/r01c_ncu_forces_pair2_v5_10M.txt (ncu --set full), scaled by fluid count; algorithmic bytes = 50 B x fluid particles",
                     "peak_source": "148 SM x 128 FP32 lanes x 2 x clocks.max.sm (non-tensor FP32 issue; tensor cores do not apply to pairwise SPH)",

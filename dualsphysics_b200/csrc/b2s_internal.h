@@ -157,7 +157,7 @@ struct b2s_ctx {
   std::vector<Motion> motions; void* motion_dev; bool motion_dirty;
   // slab decomposition (slab.cu)
   bool slab_on; int slab_rank, slab_nranks; uint32_t slab_cxa, slab_cxb; uint32_t* slab_counts; uint8_t* slab_flags; size_t slab_counts_len;
-  bool defer_attr_set;   // forces_defer.cu: dynamic shared memory opt-in done
+  uint32_t* tile_bricks; uint32_t* tile_counters; int tile_nsm; uint32_t tile_cap;   // forces_tile.cu: list of non-empty bricks, its counters, SM count, tile capacity override (0 = default)
   // gauges (gauges.cu): device list + results of the last evaluation (device and pinned host)
   std::vector<int> gauge_types; std::vector<unsigned char> gauges_host; void* gauges_dev; float* gauge_res_dev; float* gauge_res_h; float* gauge_mass_dev; uint32_t gauge_points; float* gauge_force_dev; uint32_t gauge_force_n;
   // excluded particles (JSphGpuSingle::RunCellDivide -> AddParticlesOut -> PartsOut, JSphGpuSingle.cpp:455-470): 48-byte

@@ -450,7 +450,7 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   k_beginend<<<min(b2s_blocks(ctx->nctt_max,DIV_BS),148u*16u),DIV_BS,0,s>>>(ctx->div,ctx->cellpart,(uint32_t*)ctx->begincell); B2S_LAUNCHED(ctx);
   k_divcounts<<<1,32,0,s>>>(ctx->div,(const uint32_t*)ctx->begincell); B2S_LAUNCHED(ctx);
   ctx->nearbound_valid=false;
-  if(ctx->variant!=3 && ctx->npb_host){
+  if(ctx->npb_host){
     ctx->nearbound_valid=true;
     const unsigned gn=min(b2s_blocks(ctx->nct_max,DIV_BS),148u*16u);
     k_nearbound_clear<<<gn,DIV_BS,0,s>>>(ctx->div,(uint32_t*)ctx->nearbound); B2S_LAUNCHED(ctx);

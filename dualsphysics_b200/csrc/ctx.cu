@@ -77,7 +77,8 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   ctx->launches=0; ctx->variant=0; ctx->pre_active=false; ctx->bound_changed=true; ctx->ftcount=0;
   ctx->verletstep=0;
   ctx->slab_on=false; ctx->slab_rank=0; ctx->slab_nranks=1; ctx->slab_cxa=0; ctx->slab_cxb=0; ctx->slab_counts=NULL; ctx->slab_flags=NULL; ctx->slab_counts_len=0;
-  ctx->defer_attr_set=false; ctx->boundmode=NULL; ctx->tangenvel=NULL; ctx->shiftpos=NULL; ctx->damp_dev=NULL; ctx->damp_dirty=false; ctx->out_dev=NULL; ctx->out_count_dev=NULL; ctx->out_cap=0; ctx->motion_dev=NULL; ctx->motion_dirty=false; ctx->nearbound_valid=false;
+  ctx->tile_bricks=NULL; ctx->tile_counters=NULL; ctx->tile_nsm=0; ctx->tile_cap=0;
+  ctx->boundmode=NULL; ctx->tangenvel=NULL; ctx->shiftpos=NULL; ctx->damp_dev=NULL; ctx->damp_dirty=false; ctx->out_dev=NULL; ctx->out_count_dev=NULL; ctx->out_cap=0; ctx->motion_dev=NULL; ctx->motion_dirty=false; ctx->nearbound_valid=false;
   ctx->gauges_dev=NULL; ctx->gauge_res_dev=NULL; ctx->gauge_res_h=NULL; ctx->gauge_mass_dev=NULL; ctx->gauge_points=0; ctx->gauge_force_dev=NULL; ctx->gauge_force_n=0;
   ctx->ft_massp_dev=NULL; ctx->ft_sums_dev=NULL; ctx->ft_allsums_dev=NULL; ctx->ft_sums_h=NULL; ctx->ft_dev=NULL; ctx->scratch=NULL; ctx->scratch_bytes=0;
   ctx->pospre_xy=ctx->pospre_xy_alt=NULL; ctx->pospre_z=ctx->pospre_z_alt=NULL; ctx->velrhopre=ctx->velrhopre_alt=NULL;
@@ -132,7 +133,7 @@ extern "C" int b2s_destroy(b2s_ctx* ctx){
   cudaFree(ctx->velrhom1); cudaFree(ctx->velrhom1_alt);
   cudaFree(ctx->spstau); cudaFree(ctx->spstau_alt); cudaFree(ctx->spstau_new);
   cudaFree(ctx->boundnor); cudaFree(ctx->boundnor_alt); cudaFree(ctx->motionace); cudaFree(ctx->motionace_alt);
-  cudaFree(ctx->posp); cudaFree(ctx->acear); cudaFree(ctx->posh);
+  cudaFree(ctx->posp); cudaFree(ctx->acear); cudaFree(ctx->posh); cudaFree(ctx->tile_bricks); cudaFree(ctx->tile_counters);
   cudaFree(ctx->cellpart); cudaFree(ctx->sortpart); cudaFree(ctx->cellpart_alt); cudaFree(ctx->sortpart_alt);
   cudaFree(ctx->begincell); cudaFree(ctx->nearbound); cudaFree(ctx->radix_counts); cudaFree(ctx->ridp);
   cudaFree(ctx->div); cudaFree(ctx->step);
@@ -151,7 +152,10 @@ extern "C" const char* b2s_last_error(const b2s_ctx* ctx){ return ctx? ctx->err.
 extern "C" int b2s_get_params(const b2s_ctx* ctx, b2s_params* out){ if(!ctx||!out)return B2S_ERR_ARG; *out=ctx->prm; return B2S_OK; }
 extern "C" int b2s_get_stream(b2s_ctx* ctx, void** s){ if(!ctx||!s)return B2S_ERR_ARG; *s=(void*)ctx->stream; return B2S_OK; }
 extern "C" int b2s_launch_count(b2s_ctx* ctx, uint64_t* l, int reset){ if(!ctx)return B2S_ERR_ARG; if(l)*l=ctx->launches; if(reset)ctx->launches=0; return B2S_OK; }
-extern "C" int b2s_set_interaction_variant(b2s_ctx* ctx, int v){ if(!ctx||(v!=0&&v!=3&&v!=4&&v!=5))return B2S_ERR_ARG; ctx->variant=v; return B2S_OK; }
+extern "C" int b2s_set_interaction_variant(b2s_ctx* ctx, int v){ if(!ctx||(v!=0&&v!=5&&v!=6))return B2S_ERR_ARG; ctx->variant=v; return B2S_OK; }
+// Test hook: lowers the particle capacity of a shared-memory tile of interaction variant 6 (0 = default) so that small cases
+// exercise the column split and the global-memory fallback.
+extern "C" int b2s_debug_set_tile_cap(b2s_ctx* ctx, uint32_t cap){ if(!ctx)return B2S_ERR_ARG; ctx->tile_cap=cap; return B2S_OK; }
 
 // Copies DivState+StepState to pinned memory, synchronises, refreshes the host mirrors and checks device flags.
 int b2s_sync_info(b2s_ctx* ctx){

@@ -33,80 +33,9 @@ __global__ void __launch_bounds__(F_BS) k_forces_fluid_gather(ForcesArgs g, cons
   bool nearb=(g.nearbound==nullptr);
   if(valid1 && !nearb){ const CellRange q=cell_range(g.dcell[p1],c,ds); nearb=(g.nearbound[q.cx+q.cy*int(ds->ncx)+q.cz*int(ds->nsheet)]!=0); }
   const bool warpnearb=(__any_sync(0xffffffffu,nearb)!=0);
-  if(valid1){
-    const float4 pp1=g.posp[p1];
-    const float4 velrhop1=g.velrho[p1];
-    const float pressp1=pp1.w;
-    bool ftp1=false;
-    if(FLOATING)ftp1=B2S_CODE_ISFLOATING(g.code[p1]);
-    float taup1[6]={0,0,0,0,0,0};
-    if(TVISCO==B2S_VISCO_LAMINARSPS){
-      const float2* t=(const float2*)(g.tau+size_t(p1)*6);
-      const float2 t0=t[0],t1=t[1],t2=t[2];
-      taup1[0]=t0.x; taup1[1]=t0.y; taup1[2]=t1.x; taup1[3]=t1.y; taup1[4]=t2.x; taup1[5]=t2.y;
-    }
-    const CellRange r=cell_range(g.dcell[p1],c,ds);
-    const int ncx=int(ds->ncx), nsheet=int(ds->nsheet), cmx=int(ds->cellmin[0]);
-    const float xin=pp1.x-c.scell*float((r.cx+cmx)&((1<<B2S_XBLK)-1));   // x inside the own cell (row_trim only)
-    PairAcc af={0,0,0,0,0,0,0,0,0,0,0,0};
-    PairAcc ab={0,0,0,0,0,0,0,0,0,0,0,0};
-    if(FLOATING && ftp1 && TDENS!=B2S_DDT_NONE){ af.delta=FLT_MAX; ab.delta=FLT_MAX; }
-    //-Fluid/floating neighbours.
-    {
-      const uint32_t* beg=g.beg+ds->box_fluid;
-      for(int z=r.zini;z<r.zfin;z++)for(int y=r.yini;y<r.yfin;y++){
-        const int row=y*ncx+z*nsheet;
-        const float offy=c.scell*float(r.cy-y), offz=c.scell*float(r.cz-z);
-        int xa,xb;
-        if(!row_trim(c,r,xin,FADD(pp1.y,offy),FADD(pp1.z,offz),xa,xb))continue;
-        for(int x=xa;x<xb;x++){
-          const uint32_t pini=beg[row+x], pfin=beg[row+x+1];
-          const float offx=b2s_offx(c,r.cx+cmx,x+cmx);
-          for(uint32_t p2=pini;p2<pfin;p2++){
-            const float4 pp2=g.posp[p2];
-            const float drx=b2s_dr(pp1.x,pp2.x,offx), dry=b2s_dr(pp1.y,pp2.y,offy), drz=b2s_dr(pp1.z,pp2.z,offz);
-            const float rr2=b2s_rr2(drx,dry,drz);
-            if(rr2<=c.kernelsize2 && rr2>=B2S_ALMOSTZERO){
-              const typecode cod2=(FLOATING? g.code[p2]: typecode(0));
-              pair_fluid<TKER,TVISCO,TDENS,FLOATING,false>(c,drx,dry,drz,rr2,velrhop1,pressp1,ftp1,taup1,
-                g.velrho[p2],pp2.w,cod2,g.tau,p2,g.ftomassp,c.visco_f,af);
-            }
-          }
-        }
-      }
-    }
-    //-Boundary neighbours.
-    if(warpnearb){
-      const uint32_t* beg=g.beg;
-      for(int z=r.zini;z<r.zfin;z++)for(int y=r.yini;y<r.yfin;y++){
-        const int row=y*ncx+z*nsheet;
-        const float offy=c.scell*float(r.cy-y), offz=c.scell*float(r.cz-z);
-        int xa,xb;
-        if(!row_trim(c,r,xin,FADD(pp1.y,offy),FADD(pp1.z,offz),xa,xb))continue;
-        for(int x=xa;x<xb;x++){
-          const uint32_t pini=beg[row+x], pfin=beg[row+x+1];
-          const float offx=b2s_offx(c,r.cx+cmx,x+cmx);
-          for(uint32_t p2=pini;p2<pfin;p2++){
-            const float4 pp2=g.posp[p2];
-            const float drx=b2s_dr(pp1.x,pp2.x,offx), dry=b2s_dr(pp1.y,pp2.y,offy), drz=b2s_dr(pp1.z,pp2.z,offz);
-            const float rr2=b2s_rr2(drx,dry,drz);
-            if(rr2<=c.kernelsize2 && rr2>=B2S_ALMOSTZERO){
-              pair_fluid<TKER,TVISCO,TDENS,FLOATING,true>(c,drx,dry,drz,rr2,velrhop1,pressp1,ftp1,taup1,
-                g.velrho[p2],pp2.w,typecode(0),g.tau,p2,g.ftomassp,c.visco_b,ab,g.boundmode,g.tangenvel);
-            }
-          }
-        }
-      }
-    }
-    finalize_store<TVISCO,TDENS>(g,c,p1,velrhop1,af,ab,ace2,viscmax);
-  }
+  if(valid1)gather_particle<TKER,TVISCO,TDENS,FLOATING>(g,c,ds,p1,warpnearb,ace2,viscmax);
   //-Fused maxima: ViscDtMax and AceMax^2 (replaces ReduMaxFloat x2 + cudaMemcpy, JSphGpu_ker.cu:75-125).
-  #pragma unroll
-  for(int o=16;o;o>>=1){ viscmax=fmaxf(viscmax,__shfl_xor_sync(0xffffffffu,viscmax,o)); ace2=fmaxf(ace2,__shfl_xor_sync(0xffffffffu,ace2,o)); }
-  if((threadIdx.x&31)==0){
-    if(viscmax>0.f)atomicMax(&g.st->viscdtmax_bits,__float_as_uint(viscmax));
-    if(ace2>0.f)atomicMax(&g.st->acemax2_bits,__float_as_uint(ace2));
-  }
+  reduce_maxima(g.st,viscmax,ace2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -204,9 +133,10 @@ fluid_kernel_t b2s_pick_fluid_gather(const DevCte& c){
   return c.tkernel==B2S_KERNEL_WENDLAND? pick_visco<B2S_KERNEL_WENDLAND>(c.tvisco,c.tdensity,ft): pick_visco<B2S_KERNEL_CUBIC>(c.tvisco,c.tdensity,ft);
 }
 
-int b2s_forces_defer_launch(b2s_ctx* ctx, const ForcesArgs& g);  // forces_defer.cu
 int b2s_forces_pair2_launch(b2s_ctx* ctx, const ForcesArgs& g);  // forces_pair2.cu
 bool b2s_forces_pair2_supported(const DevCte& c);
+int b2s_forces_tile_launch(b2s_ctx* ctx, const ForcesArgs& g);   // forces_tile.cu
+bool b2s_forces_tile_supported(const DevCte& c);
 
 int b2s_forces_fluid_only(b2s_ctx* ctx){
   ForcesArgs g;
@@ -214,8 +144,8 @@ int b2s_forces_fluid_only(b2s_ctx* ctx){
   g.posp=ctx->posp; g.posh=ctx->posh; g.boundmode=ctx->boundmode; g.tangenvel=ctx->tangenvel; g.nearbound=(ctx->nearbound_valid? ctx->nearbound: NULL); g.velrho=ctx->cur.velrho; g.tau=ctx->spstau; g.tau_new=ctx->spstau_new; g.ftomassp=ctx->ft_massp_dev; g.acear=ctx->acear;
   const uint32_t npf=(ctx->np_host>ctx->npb_host? ctx->np_host-ctx->npb_host: 0u);
   if(!npf)return B2S_OK;
-  if(ctx->variant==3 && ctx->np_host<(1u<<26))return b2s_forces_defer_launch(ctx,g);   // queue entries hold 26-bit indices
-  if((ctx->variant==4 || ctx->variant==5) && b2s_forces_pair2_supported(ctx->cte))return b2s_forces_pair2_launch(ctx,g);
+  if(ctx->variant==6 && b2s_forces_tile_supported(ctx->cte))return b2s_forces_tile_launch(ctx,g);
+  if((ctx->variant==5 || ctx->variant==6) && b2s_forces_pair2_supported(ctx->cte))return b2s_forces_pair2_launch(ctx,g);
   fluid_kernel_t k=b2s_pick_fluid_gather(ctx->cte);
   k<<<b2s_blocks(npf,F_BS),F_BS,0,ctx->stream>>>(g,ctx->cte); B2S_LAUNCHED(ctx);
   return B2S_OK;

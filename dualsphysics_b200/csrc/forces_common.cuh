@@ -235,6 +235,79 @@ __device__ __forceinline__ void finalize_store(const ForcesArgs& g,const DevCte&
   }
 }
 
+// One fluid/floating particle against all its neighbours, from global memory, in the reference's order: fluid neighbours, then
+// boundary neighbours, rows of cells z-major (JSphCpu.cpp:736-1125; the walk of KerInteractionForcesFluid, JSphGpu_ker.cu:786-990).
+// This is variant 0's thread body (forces.cu) and the fallback of the tile kernel for columns that do not fit its shared memory.
+template<int TKER,int TVISCO,int TDENS,bool FLOATING>
+__device__ __forceinline__ void gather_particle(const ForcesArgs& g,const DevCte& c,const DivState* ds,uint32_t p1,bool warpnearb,float& ace2,float& viscmax)
+{
+  const float4 pp1=g.posp[p1];
+  const float4 velrhop1=g.velrho[p1];
+  const float pressp1=pp1.w;
+  bool ftp1=false;
+  if(FLOATING)ftp1=B2S_CODE_ISFLOATING(g.code[p1]);
+  float taup1[6]={0,0,0,0,0,0};
+  if(TVISCO==B2S_VISCO_LAMINARSPS){
+    const float2* t=(const float2*)(g.tau+size_t(p1)*6);
+    const float2 t0=t[0],t1=t[1],t2=t[2];
+    taup1[0]=t0.x; taup1[1]=t0.y; taup1[2]=t1.x; taup1[3]=t1.y; taup1[4]=t2.x; taup1[5]=t2.y;
+  }
+  const CellRange r=cell_range(g.dcell[p1],c,ds);
+  const int ncx=int(ds->ncx), nsheet=int(ds->nsheet), cmx=int(ds->cellmin[0]);
+  const float xin=pp1.x-c.scell*float((r.cx+cmx)&((1<<B2S_XBLK)-1));   // x inside the own cell (row_trim only)
+  PairAcc af={0,0,0,0,0,0,0,0,0,0,0,0};
+  PairAcc ab={0,0,0,0,0,0,0,0,0,0,0,0};
+  if(FLOATING && ftp1 && TDENS!=B2S_DDT_NONE){ af.delta=FLT_MAX; ab.delta=FLT_MAX; }
+  //-Fluid/floating neighbours.
+  {
+    const uint32_t* beg=g.beg+ds->box_fluid;
+    for(int z=r.zini;z<r.zfin;z++)for(int y=r.yini;y<r.yfin;y++){
+      const int row=y*ncx+z*nsheet;
+      const float offy=c.scell*float(r.cy-y), offz=c.scell*float(r.cz-z);
+      int xa,xb;
+      if(!row_trim(c,r,xin,FADD(pp1.y,offy),FADD(pp1.z,offz),xa,xb))continue;
+      for(int x=xa;x<xb;x++){
+        const uint32_t pini=beg[row+x], pfin=beg[row+x+1];
+        const float offx=b2s_offx(c,r.cx+cmx,x+cmx);
+        for(uint32_t p2=pini;p2<pfin;p2++){
+          const float4 pp2=g.posp[p2];
+          const float drx=b2s_dr(pp1.x,pp2.x,offx), dry=b2s_dr(pp1.y,pp2.y,offy), drz=b2s_dr(pp1.z,pp2.z,offz);
+          const float rr2=b2s_rr2(drx,dry,drz);
+          if(rr2<=c.kernelsize2 && rr2>=B2S_ALMOSTZERO){
+            const typecode cod2=(FLOATING? g.code[p2]: typecode(0));
+            pair_fluid<TKER,TVISCO,TDENS,FLOATING,false>(c,drx,dry,drz,rr2,velrhop1,pressp1,ftp1,taup1,
+              g.velrho[p2],pp2.w,cod2,g.tau,p2,g.ftomassp,c.visco_f,af);
+          }
+        }
+      }
+    }
+  }
+  //-Boundary neighbours.
+  if(warpnearb){
+    const uint32_t* beg=g.beg;
+    for(int z=r.zini;z<r.zfin;z++)for(int y=r.yini;y<r.yfin;y++){
+      const int row=y*ncx+z*nsheet;
+      const float offy=c.scell*float(r.cy-y), offz=c.scell*float(r.cz-z);
+      int xa,xb;
+      if(!row_trim(c,r,xin,FADD(pp1.y,offy),FADD(pp1.z,offz),xa,xb))continue;
+      for(int x=xa;x<xb;x++){
+        const uint32_t pini=beg[row+x], pfin=beg[row+x+1];
+        const float offx=b2s_offx(c,r.cx+cmx,x+cmx);
+        for(uint32_t p2=pini;p2<pfin;p2++){
+          const float4 pp2=g.posp[p2];
+          const float drx=b2s_dr(pp1.x,pp2.x,offx), dry=b2s_dr(pp1.y,pp2.y,offy), drz=b2s_dr(pp1.z,pp2.z,offz);
+          const float rr2=b2s_rr2(drx,dry,drz);
+          if(rr2<=c.kernelsize2 && rr2>=B2S_ALMOSTZERO){
+            pair_fluid<TKER,TVISCO,TDENS,FLOATING,true>(c,drx,dry,drz,rr2,velrhop1,pressp1,ftp1,taup1,
+              g.velrho[p2],pp2.w,typecode(0),g.tau,p2,g.ftomassp,c.visco_b,ab,g.boundmode,g.tangenvel);
+          }
+        }
+      }
+    }
+  }
+  finalize_store<TVISCO,TDENS>(g,c,p1,velrhop1,af,ab,ace2,viscmax);
+}
+
 // Warp max of the two dt quantities + one atomic per warp (replaces ReduMaxFloat x2 + cudaMemcpy, JSphGpu_ker.cu:75-125).
 __device__ __forceinline__ void reduce_maxima(StepState* st,float viscmax,float ace2){
   #pragma unroll

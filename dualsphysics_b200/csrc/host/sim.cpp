@@ -233,7 +233,7 @@ static void load_case(b2s_sim* s,const std::string& options){
       else if(w=="SVEXTRAPARTS"){ if(a.empty() || a.find_first_not_of("0123456789,-")!=std::string::npos)throw std::runtime_error("-svextraparts: a PART interval or a list like 1,4,7-9"); s->svextraparts=a; }
       else if(w=="SAVEPOSDOUBLE")s->svposdouble=(a.empty()||atoi(a.c_str())!=0);
       else if(w=="B2SVARIANT"){   // interaction kernel (include/b2s.h b2s_set_interaction_variant): 0 = reference summation order (default), 5 = fastest
-        s->variant=atoi(a.c_str()); if(a.empty() || (s->variant!=0 && s->variant!=3 && s->variant!=4 && s->variant!=5))throw std::runtime_error("-b2svariant: 0, 3, 4 or 5");
+        s->variant=atoi(a.c_str()); if(a.empty() || (s->variant!=0 && s->variant!=5 && s->variant!=6))throw std::runtime_error("-b2svariant: 0, 5 or 6");
       }
       else if(w=="SV"){ s->svdata=(lower(a).find("none")==std::string::npos); }
       else throw std::runtime_error("option not supported by this build: "+tok);

@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# B2S_LIB_PATH: developer override used by the kernel-tuning scripts (tools/tune_defer.sh) to load an alternative build
+# B2S_LIB_PATH: developer override used by the kernel-tuning scripts (tools/gpu_job.sh) to load an alternative build
 LIB_PATH = os.environ.get("B2S_LIB_PATH") or os.path.join(_HERE, "lib", "libb200sph.so")
 
 # enums (same numeric values as the reference)
@@ -102,7 +102,7 @@ ABI_SYMBOLS = [
     "b2s_compute_symplectic_corr", "b2s_compute_step", "b2s_run_steps", "b2s_add_motion_rectsinu", "b2s_add_motion", "b2s_add_damping_plane", "b2s_add_damping_box", "b2s_out_enable", "b2s_out_fetch", "b2s_gauge_add_force", "b2s_gauge_add_maxz",
     "b2s_move_linear", "b2s_set_floatings", "b2s_get_floatings", "b2s_count_pairs", "b2s_time_interaction",
     "b2s_gauge_add_velocity", "b2s_gauge_add_swl", "b2s_gauges_compute", "b2s_gauge_result",
-    "b2s_launch_count", "b2s_get_stream", "b2s_set_interaction_variant", "b2s_slab_config",
+    "b2s_launch_count", "b2s_get_stream", "b2s_set_interaction_variant", "b2s_debug_set_tile_cap", "b2s_slab_config",
     "b2s_slab_histogram", "b2s_slab_set_range", "b2s_slab_drop_ghosts", "b2s_slab_record_bytes", "b2s_slab_pack", "b2s_slab_unpack", "b2s_slab_pack_both", "b2s_slab_unpack_both", "b2s_slab_dt_buffer", "b2s_slab_forces",
     "b2s_slab_apply_dt", "b2s_slab_integrate", "b2s_slab_step_end", "b2s_slab_ft_sums", "b2s_slab_ft_apply",
     "b2s_sim_load", "b2s_sim_load_slab", "b2s_sim_slab_info", "b2s_sim_free", "b2s_sim_ctx", "b2s_sim_params", "b2s_sim_stats", "b2s_sim_set_dirout", "b2s_sim_save_part", "b2s_sim_run",
@@ -164,6 +164,7 @@ def load_library():
     lib.b2s_launch_count.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
     lib.b2s_get_stream.argtypes = [vp, C.POINTER(vp)]
     lib.b2s_set_interaction_variant.argtypes = [vp, C.c_int]
+    lib.b2s_debug_set_tile_cap.argtypes = [vp, C.c_uint32]
     lib.b2s_gauge_add_velocity.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.b2s_gauge_add_swl.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_float, C.POINTER(C.c_int)]
     lib.b2s_gauge_add_force.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int)]
@@ -332,6 +333,9 @@ class Context:
 
     def set_variant(self, v: int):
         self._chk(self._lib.b2s_set_interaction_variant(self._h, v))
+
+    def set_tile_cap(self, cap: int):
+        self._chk(self._lib.b2s_debug_set_tile_cap(self._h, cap))
 
     # ---- slab decomposition (include/b2s.h, "slab" section) ----
     def slab_config(self, rank, nranks, cx_begin, cx_end):

@@ -272,12 +272,16 @@ int b2s_launch_count(b2s_ctx* ctx, uint64_t* launches, int reset);
 /* CUDA stream the ctx launches on (cudaStream_t cast to void*), for external event timing. */
 int b2s_get_stream(b2s_ctx* ctx, void** stream_out);
 /* Selects the fluid interaction kernel variant: 0 = gather (one thread per particle, reference summation order; default),
- * 3 = gather with deferred pair bodies (csrc/forces_defer.cu; experimental, used below 2^26 particles; bit-identical to 0),
- * 4 = two hits per lane in packed FP32 with FP16 pre-filter (csrc/forces_pair2.cu; Wendland + artificial viscosity
- * without floating bodies, other configurations run variant 0; equal to 0 within summation rounding),
- * 5 = 4 with every neighbour row processed together with its point mirror (fastest; same scope and tolerance as 4).
+ * 5 = FP16 pre-filter into per-lane hit masks, two hits per lane and round in packed FP32, mirror rows (csrc/forces_pair2.cu;
+ *     Wendland + artificial viscosity without floating bodies, other configurations run variant 0; equal to 0 within rounding:
+ *     the pair terms are re-associated, csrc/forces_pair2.cuh),
+ * 6 = bricks of cells staged in shared memory in one FP32 frame per tile, per-lane hit lists over many rows, the same packed
+ *     pair body (csrc/forces_tile.cu; same scope as 5).
  * Other values: B2S_ERR_ARG. */
 int b2s_set_interaction_variant(b2s_ctx* ctx, int variant);
+/* Test hook for variant 6: particle capacity of a shared-memory tile (0 = built-in 4096).  A lower value makes small cases take
+ * the column split and the global-memory fallback of csrc/forces_tile.cu.  Results do not depend on it beyond rounding. */
+int b2s_debug_set_tile_cap(b2s_ctx* ctx, uint32_t cap);
 
 /* ---- slab decomposition over several GPUs (no reference counterpart) ----------- */
 /* One ctx per GPU owns the particles whose cell-x lies in [cx_begin,cx_end) of the GLOBAL cell grid.  Before every

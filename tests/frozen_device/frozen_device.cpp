@@ -62,6 +62,7 @@ int b2s_get_info(b2s_ctx* c,b2s_info* out){
 int b2s_set_time(b2s_ctx* c,double t,double dtpre){ c->time=t; c->dtpre=dtpre; return B2S_OK; }
 int b2s_compute_step(b2s_ctx* c,double* dt_out){ c->time+=FROZEN_DT; c->nstep++; if(dt_out)*dt_out=FROZEN_DT; return B2S_OK; }
 int b2s_set_interaction_variant(b2s_ctx*,int){ return B2S_OK; }
+int b2s_debug_set_tile_cap(b2s_ctx*,uint32_t){ return B2S_OK; }
 int b2s_slab_config(b2s_ctx*,int,int,uint32_t,uint32_t){ return B2S_OK; }
 int b2s_add_motion(b2s_ctx*,const b2s_motion*){ return B2S_OK; }
 int b2s_out_enable(b2s_ctx*,uint32_t){ return B2S_OK; }

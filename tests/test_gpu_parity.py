@@ -69,7 +69,7 @@ def _check_forces(ctx, g, p, label, report, wide=False):
     assert e["acemax"] < ta and e["velmax"] < 1e-4 and e["viscdtmax"] < 1e-3, (label, e)
 
 
-@pytest.mark.parametrize("variant", [0, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 5, 6])
 @pytest.mark.parametrize("fx", FIXTURES)
 def test_golden_reference_parity(fx, variant, tmp_path, built_lib):
     meta = json.load(open(os.path.join(H.GOLDEN, fx, "fixture.json")))
@@ -196,42 +196,53 @@ def test_errors_are_loud(tmp_path, built_lib):
     sim.close()
 
 
-@pytest.mark.parametrize("options", ["", "-cellmode:half"])
-@pytest.mark.parametrize("opts", [{}, {"ViscoTreatment": 2, "Visco": 1e-6, "DensityDT": 3}, {"Kernel": 1, "DensityDT": 1}])
-def test_deferred_variant_is_bit_identical_to_gather(opts, options, tmp_path, built_lib):
-    """Variant 3 (deferred pair bodies, csrc/forces_defer.cu) visits the hits of every particle in the order of variant 0
-    and uses the same explicitly rounded arithmetic, so ace/ar, the maxima and the state after several steps must be equal
-    bit for bit."""
-    H.write_case(tmp_path, dp=0.02, params=opts)
+@pytest.mark.parametrize("cap", [0, 700, 150])
+@pytest.mark.parametrize("options", ["", "-cellmode:half", "-cellmode:half -ddt:1", "-cellmode:half -ddt:3", "-ddt:0"])
+def test_tile_variant_matches_gather(options, cap, tmp_path, built_lib):
+    """Variant 6 (bricks of cells staged in shared memory, csrc/forces_tile.cu) against variant 0 on the SAME state: per pair the
+    operations of variant 0, but dr comes from the FP32 frame of the tile (|x| < 7 cells, rounded once from FP64) instead of the
+    cell-relative frame, and the sums are grouped by hit list.  Stated: 2e-5 of max|ace| (measured: profiles/parity_r02.json),
+    ar 2e-4 of its floor scale.  cap lowers the tile capacity so that this 20k-particle case also takes the column split
+    (700 particles per tile) and the global-memory fallback for single columns (150)."""
+    H.write_case(tmp_path, dp=0.02)
     case = str(tmp_path / "Case")
-    res = []
-    for variant in (0, 3):
-        sim = dsb.Simulation(case, options=options)
-        sim.ctx.set_variant(variant)
-        sim.ctx.run_steps(6)
-        sim.ctx.interaction(dsb.lib.INTER_SYMPREDICTOR)
-        info = sim.ctx.info()
-        res.append((sim.ctx.array("acear").copy(), sim.ctx.array("velrho").copy(), info.acemax, info.viscdtmax, info.dt_last))
-        sim.close()
-    a0, a3 = res
-    assert np.array_equal(a0[1].view(np.uint32), a3[1].view(np.uint32)), "state after 6 steps differs between variants"
-    assert np.array_equal(a0[0].view(np.uint32), a3[0].view(np.uint32)), "ace/ar differ between variants"
-    assert a0[2:] == a3[2:]
+    inter = dsb.lib.INTER_SYMPREDICTOR
+    for nsteps, tol_ace, tol_state in ((0, 2e-5, 0.0), (6, 5e-4, 2e-6)):
+        res = []
+        for variant in (0, 6):
+            sim = dsb.Simulation(case, options=options)
+            sim.ctx.set_variant(variant)
+            sim.ctx.set_tile_cap(cap)
+            if nsteps:
+                sim.ctx.run_steps(nsteps)
+            sim.ctx.interaction(inter)
+            info = sim.ctx.info()
+            p = sim.params
+            res.append((sim.ctx.array("acear").copy(), sim.ctx.array("velrho").copy(), info.acemax, info.viscdtmax, info.dt_last,
+                        float(p.rhopzero) * p.cs0 / float(p.kernelh) * 1e-4))
+            sim.close()
+        a0, a6 = res
+        e_ace = H.rel_err(a6[0][:, :3], a0[0][:, :3])
+        e_ar = H.rel_err(a6[0][:, 3], a0[0][:, 3], floor=a0[5])
+        e_state = H.rel_err(a6[1], a0[1])
+        print(f"\n[variant 6 vs 0, {options!r}, cap {cap}, after {nsteps} steps] ace {e_ace:.2e} ar {e_ar:.2e} state {e_state:.2e} dt {a0[4]} {a6[4]}")
+        assert e_ace < tol_ace and e_ar < max(tol_ace, 2e-4) and e_state <= tol_state
+        assert abs(a6[4] - a0[4]) <= (2e-6 if nsteps == 0 else 2e-5) * a0[4]
 
 
 @pytest.mark.parametrize("options", ["", "-cellmode:half", "-cellmode:half -ddt:1", "-cellmode:half -ddt:3", "-ddt:0"])
 def test_packed_variant_matches_gather(options, tmp_path, built_lib):
-    """Variant 4 (two hits per lane in f32x2 registers, csrc/forces_pair2.cu) performs per pair exactly the operations of
-    variant 0 but adds the two halves of its packed accumulators at the end, so on the SAME state it agrees to summation
-    rounding: 5e-6 of max|ace|, dt 1e-6; ar 2e-4 of its floor scale rho0*cs0/h*1e-4 (at rest ar is a sum of cancelling
+    """Variant 5 (two hits per lane in f32x2 registers, csrc/forces_pair2.cu) evaluates the pair terms of variant 0 re-associated
+    (csrc/forces_pair2.cuh pack_body) and adds the two halves of its packed accumulators at the end, so on the SAME state it agrees to
+    rounding: 2e-5 of max|ace|, dt 2e-6; ar 2e-4 of its floor scale rho0*cs0/h*1e-4 (at rest ar is a sum of cancelling
     density-diffusion terms, so the order of the additions shows; the reference tolerance on the same scale is 5e-4).  After 6 independent steps the two runs differ by
     1e-6 in the state, which the Tait EOS turns into ~1e-4 in ace (same effect as between the reference builds)."""
     H.write_case(tmp_path, dp=0.02)
     case = str(tmp_path / "Case")
     inter = dsb.lib.INTER_SYMPREDICTOR
-    for nsteps, tol_ace, tol_state in ((0, 5e-6, 0.0), (6, 5e-4, 1e-6)):
+    for nsteps, tol_ace, tol_state in ((0, 2e-5, 0.0), (6, 5e-4, 2e-6)):
         res = []
-        for variant in (0, 4):
+        for variant in (0, 5):
             sim = dsb.Simulation(case, options=options)
             sim.ctx.set_variant(variant)
             if nsteps:
@@ -246,9 +257,9 @@ def test_packed_variant_matches_gather(options, tmp_path, built_lib):
         e_ace = H.rel_err(a4[0][:, :3], a0[0][:, :3])
         e_ar = H.rel_err(a4[0][:, 3], a0[0][:, 3], floor=a0[5])
         e_state = H.rel_err(a4[1], a0[1])
-        print(f"\n[variant 4 vs 0, {options!r}, after {nsteps} steps] ace {e_ace:.2e} ar {e_ar:.2e} state {e_state:.2e} dt {a0[4]} {a4[4]}")
+        print(f"\n[variant 5 vs 0, {options!r}, after {nsteps} steps] ace {e_ace:.2e} ar {e_ar:.2e} state {e_state:.2e} dt {a0[4]} {a4[4]}")
         assert e_ace < tol_ace and e_ar < max(tol_ace, 2e-4) and e_state <= tol_state
-        assert abs(a4[4] - a0[4]) <= (1e-6 if nsteps == 0 else 2e-5) * a0[4]
+        assert abs(a4[4] - a0[4]) <= (2e-6 if nsteps == 0 else 2e-5) * a0[4]
 
 
 def test_periodic_properties_large(tmp_path, built_lib):

@@ -1,0 +1,28 @@
+#!/bin/bash
+# One parametrised GPU job (replaces the numbered one-shot scripts of round 1).  Usage (inside gpurun):
+#   bash tools/gpu_job.sh TAG [steps...]      steps: tile_parity golden6 memcheck bench6 bench5 ncu6 suite microbench
+# Outputs go to gpurun_out/TAG_*.
+TAG=$1; shift
+mkdir -p gpurun_out
+for step in "$@"; do
+case $step in
+  build=*) flags=$(echo "${step#build=}" | tr ',' ' '); touch dualsphysics_b200/csrc/forces_tile.cu dualsphysics_b200/csrc/forces_pair2.cu; make -C dualsphysics_b200/csrc B2S_NVCC_EXTRA="$flags" 2>&1 | grep -E "error|rror:" ; echo "== rebuilt with: $flags"; TAG=${TAG}x;;
+  microbench) ./tools/microbench > gpurun_out/${TAG}_microbench.txt 2>&1; cat gpurun_out/${TAG}_microbench.txt;;
+  pack_parity) timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "packed_variant or (golden and 5)" -s 2>&1 | grep -E "variant 5 vs 0|passed|failed|Error|error|assert" | head -40 > gpurun_out/${TAG}_pack_vs_gather.log; tail -12 gpurun_out/${TAG}_pack_vs_gather.log;;
+  tile_parity) timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "tile_variant" -s 2>&1 | grep -E "variant 6 vs 0|passed|failed|Error|error|assert" | head -60 > gpurun_out/${TAG}_tile_vs_gather.log; tail -3 gpurun_out/${TAG}_tile_vs_gather.log;;
+  golden6) timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "golden and 6" 2>&1 | tail -5 > gpurun_out/${TAG}_golden_v6.log; cat gpurun_out/${TAG}_golden_v6.log;;
+  memcheck) timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_small.py 2 > gpurun_out/${TAG}_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -2 gpurun_out/${TAG}_memcheck.log;;
+  racecheck) timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_small.py 1 > gpurun_out/${TAG}_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -2 gpurun_out/${TAG}_racecheck.log;;
+  bench[0-9]) v=${step#bench}
+    timeout 600 python bench.py --steps 10 --warmup 3 --variant $v --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_n1_v$v.json 2> gpurun_out/${TAG}_bench_n1_v$v.err; tail -2 gpurun_out/${TAG}_bench_n1_v$v.err
+    python -c "import json; d=json.load(open('gpurun_out/${TAG}_bench_n1_v$v.json')); print('variant $v ms/step', d['ms_per_step'], 'ms/interaction', d['roofline']['ms_per_launch'], 'frac', d['roofline']['frac'])";;
+  benchfull6) B2S_BENCH_EXTRA_OPTS=' -cellmode:full' timeout 600 python bench.py --steps 10 --warmup 3 --variant 6 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_n1_v6_fullcells.json 2> gpurun_out/${TAG}_bench_n1_v6_fullcells.err; tail -2 gpurun_out/${TAG}_bench_n1_v6_fullcells.err
+    python -c "import json; d=json.load(open('gpurun_out/${TAG}_bench_n1_v6_fullcells.json')); print('variant 6 full cells ms/step', d['ms_per_step'], 'ms/interaction', d['roofline']['ms_per_launch'])";;
+  fullbench) timeout 1200 python bench.py > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err; tail -2 gpurun_out/${TAG}_bench_n1.err; head -c 400 gpurun_out/${TAG}_bench_n1.json; echo;;
+  ncu[0-9]) v=${step#ncu}
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_forces_fluid -s 2 -c 1 -f -o gpurun_out/${TAG}_forces_v${v}_10M python tools/profile_forces.py 10000000 $v 3 > gpurun_out/${TAG}_prof_v$v.log 2>&1; tail -1 gpurun_out/${TAG}_prof_v$v.log;;
+  launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_launches.log 2>&1; python tools/summarize_launches.py gpurun_out/${TAG}_launches.csv 2>/dev/null | head -14;;
+  suite) python -m pytest tests -q -m gpu -x 2>&1 | tail -4 > gpurun_out/${TAG}_gpu_tests.log; cat gpurun_out/${TAG}_gpu_tests.log;;
+  *) echo "unknown step $step";;
+esac
+done

@@ -12,14 +12,14 @@
 #include <stdio.h>
 #include <stdint.h>
 
-#define ITERS 2048
+#define ITERS 8192
 #define UNROLL 8
 #define CHECK(x) do{ cudaError_t e=(x); if(e!=cudaSuccess){ printf("CUDA error %s at %d\n",cudaGetErrorString(e),__LINE__); return 1; } }while(0)
 
 typedef unsigned long long u64;
 
 enum { M_FFMA=0, M_FFMA2, M_FADD2, M_FMUL2, M_FADD, M_HFMA2, M_RCP, M_RSQ, M_FFMA2_ALU, M_FFMA2_MUFU, M_LDS128_BC, M_LDS128_SEQ, M_LDS128_RND,
-       M_LDS64_RND, M_LDS32_RND, M_FFMA2_LDS, M_LOP3, M_FSETP, M_COUNT };
+       M_LDS64_RND, M_LDS32_RND, M_LDS128_NEAR, M_FFMA2_LDS, M_LOP3, M_FSETP, M_COUNT };
 
 template<int MODE> __global__ void __launch_bounds__(256) k_bench(float* out, float seed, u64* span){
   extern __shared__ float4 smem[];
@@ -71,7 +71,7 @@ template<int MODE> __global__ void __launch_bounds__(256) k_bench(float* out, fl
         else if(MODE==M_FFMA2_LDS){    // 4 FFMA2 + 1 random LDS.128
           float4 v; u0=u0*1664525u+1013904223u;
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3},[%4];":"=f"(v.x),"=f"(v.y),"=f"(v.z),"=f"(v.w):"r"(sbase+((u0>>8)&2047u)*16u));
-          a4+=v.x;
+          a4+=v.x; a5+=v.y; a6+=v.z; a7+=v.w;
         }
         else{
           asm volatile("fma.rn.f32x2 %0,%0,%1,%2;":"+l"(p4):"l"(pb),"l"(pc)); asm volatile("fma.rn.f32x2 %0,%0,%1,%2;":"+l"(p5):"l"(pb),"l"(pc));
@@ -131,19 +131,21 @@ template<int MODE> __global__ void __launch_bounds__(256) k_bench(float* out, fl
       if(MODE==M_LDS128_BC || MODE==M_LDS128_SEQ){   // 8 loads per turn, addresses advance by a register stride (no address math inside)
         const uint32_t ad=(MODE==M_LDS128_BC? adr_bc: adr_seq);
         float4 v;
-        #define LDSK(K) asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3},[%4+" #K "];":"=f"(v.x),"=f"(v.y),"=f"(v.z),"=f"(v.w):"r"(ad)); a0+=v.x;
+        #define LDSK(K) asm volatile("ld.volatile.shared.v4.f32 {%0,%1,%2,%3},[%4+" #K "];":"=f"(v.x),"=f"(v.y),"=f"(v.z),"=f"(v.w):"r"(ad)); a0+=v.x; a1+=v.y; a2+=v.z; a3+=v.w;
         LDSK(0) LDSK(512) LDSK(1024) LDSK(1536) LDSK(2048) LDSK(2560) LDSK(3072) LDSK(3584)
         #undef LDSK
       }
-      if(MODE==M_LDS128_RND || MODE==M_LDS64_RND || MODE==M_LDS32_RND){   // 4 loads per turn at per-lane pseudo-random 16-byte slots (+ the LCG: IMAD, SHF/LOP, LEA)
+      if(MODE==M_LDS128_RND || MODE==M_LDS64_RND || MODE==M_LDS32_RND || MODE==M_LDS128_NEAR){   // 4 loads per turn at per-lane pseudo-random 16-byte slots (+ the LCG: IMAD, SHF, LOP, LEA)
         #pragma unroll
         for(int k=0;k<4;k++){
-          u0=u0*1664525u+1013904223u; const uint32_t ad=sbase+((u0>>8)&2047u)*16u;
+          u0=u0*1664525u+1013904223u;
+          // NEAR: the lanes of a warp read inside one window of 64 slots (1 KB) that moves with the turn: the pattern of hit lists of neighbouring targets
+          const uint32_t slot=(MODE==M_LDS128_NEAR? ((uint32_t(i)*37u+(u0>>26))&2047u): ((u0>>8)&2047u));
+          const uint32_t ad=sbase+slot*16u;
           float4 v=make_float4(0,0,0,0);
-          if(MODE==M_LDS128_RND)asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3},[%4];":"=f"(v.x),"=f"(v.y),"=f"(v.z),"=f"(v.w):"r"(ad));
-          if(MODE==M_LDS64_RND)asm volatile("ld.shared.v2.f32 {%0,%1},[%2];":"=f"(v.x),"=f"(v.y):"r"(ad));
-          if(MODE==M_LDS32_RND)asm volatile("ld.shared.f32 %0,[%1];":"=f"(v.x):"r"(ad));
-          a0+=v.x;
+          if(MODE==M_LDS128_RND || MODE==M_LDS128_NEAR){ asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3},[%4];":"=f"(v.x),"=f"(v.y),"=f"(v.z),"=f"(v.w):"r"(ad)); a0+=v.x; a1+=v.y; a2+=v.z; a3+=v.w; }
+          if(MODE==M_LDS64_RND){ asm volatile("ld.shared.v2.f32 {%0,%1},[%2];":"=f"(v.x),"=f"(v.y):"r"(ad)); a0+=v.x; a1+=v.y; }
+          if(MODE==M_LDS32_RND){ asm volatile("ld.shared.f32 %0,[%1];":"=f"(v.x):"r"(ad)); a0+=v.x; }
         }
       }
     }
@@ -155,6 +157,7 @@ template<int MODE> __global__ void __launch_bounds__(256) k_bench(float* out, fl
   if(tid==0)span[blockIdx.x]=tmax-tmin;
 }
 
+static double g_smclk_khz=1965000.0;
 struct Probe { const char* name; double target_per_turn; double other_per_turn; };
 
 template<int MODE> static int run(const char* name,double target,double other,int nsm,float* dout,u64* dspan){
@@ -172,7 +175,10 @@ template<int MODE> static int run(const char* name,double target,double other,in
   // per SM: 4 CTAs x 8 warps, each ITERS turns of UNROLL x (target + other) instructions + 2 of loop control
   const double warps=4.0*(threads/32);
   const double wt=double(ITERS)*UNROLL*target*warps, wall=double(ITERS)*(UNROLL*(target+other)+2.0)*warps;
-  printf("%-44s %7.3f ms %9.0f cyc  target %6.3f  all %6.3f warp-inst/clk/SM  (%.2f GHz seen)\n",name,ms,cyc,wt/cyc,wall/cyc,cyc/(ms*1e6));
+  // clock64() does not tick at the SM clock on this part (its rate against the event time changes from probe to probe), so the
+  // rates are taken from the event time of the whole launch at the SM clock the device reports (launch overhead included: a lower bound)
+  const double smclk=g_smclk_khz*1e3, clk=ms*1e-3*smclk;
+  printf("%-46s %8.3f ms  target %6.3f  all %6.3f warp-inst/clk/SM   [clock64 span %.0f = %.2f GHz]\n",name,ms,wt/clk,wall/clk,cyc,cyc/(ms*1e6));
   return 0;
 }
 
@@ -180,7 +186,7 @@ int main(){
   int dev=0; cudaDeviceProp pr; CHECK(cudaGetDeviceProperties(&pr,dev));
   printf("device: %s  SMs=%d  clock=%d kHz\n",pr.name,pr.multiProcessorCount,pr.clockRate);
   printf("rates: 'target' counts the probed instruction only, 'all' adds the companions and loop control; an SM issues at most 4 warp-inst/clk\n");
-  const int nsm=pr.multiProcessorCount;
+  const int nsm=pr.multiProcessorCount; g_smclk_khz=pr.clockRate;
   float* dout; u64* dspan;
   CHECK(cudaMalloc(&dout,sizeof(float)*nsm*4*256)); CHECK(cudaMalloc(&dspan,sizeof(u64)*8192));
   run<M_FFMA>("FFMA (8 chains)",8,0,nsm,dout,dspan);
@@ -194,11 +200,12 @@ int main(){
   run<M_RSQ>("MUFU.RSQ (8 chains)",8,0,nsm,dout,dspan);
   run<M_FFMA2_ALU>("4 FFMA2 + 4 LOP3",4,4,nsm,dout,dspan);
   run<M_FFMA2_MUFU>("4 FFMA2 + 1 MUFU.RSQ",4,1,nsm,dout,dspan);
-  run<M_FFMA2_LDS>("4 FFMA2 + 1 LDS.128 random (+3 addr +1 FADD)",4,5,nsm,dout,dspan);
-  run<M_LDS128_BC>("LDS.128 broadcast (8 + 8 FADD)",8,8,nsm,dout,dspan);
-  run<M_LDS128_SEQ>("LDS.128 lane-consecutive (8 + 8 FADD)",8,8,nsm,dout,dspan);
-  run<M_LDS128_RND>("LDS.128 random 16B slots (4 + 4x4 addr/FADD)",4,16,nsm,dout,dspan);
-  run<M_LDS64_RND>("LDS.64 random 16B slots (4 + 4x4)",4,16,nsm,dout,dspan);
-  run<M_LDS32_RND>("LDS.32 random 16B slots (4 + 4x4)",4,16,nsm,dout,dspan);
+  run<M_FFMA2_LDS>("4 FFMA2 + 1 LDS.128 random (+4 addr +4 FADD)",4,9,nsm,dout,dspan);
+  run<M_LDS128_BC>("LDS.128 broadcast (8 + 32 FADD)",8,32,nsm,dout,dspan);
+  run<M_LDS128_SEQ>("LDS.128 lane-consecutive (8 + 32 FADD)",8,32,nsm,dout,dspan);
+  run<M_LDS128_RND>("LDS.128 random 16B slots in 32 KB (4 + 4x8)",4,32,nsm,dout,dspan);
+  run<M_LDS128_NEAR>("LDS.128 random inside a 1 KB window (4 + 4x10)",4,40,nsm,dout,dspan);
+  run<M_LDS64_RND>("LDS.64 random 16B slots (4 + 4x6)",4,24,nsm,dout,dspan);
+  run<M_LDS32_RND>("LDS.32 random 16B slots (4 + 4x5)",4,20,nsm,dout,dspan);
   return 0;
 }
