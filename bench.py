@@ -29,11 +29,17 @@ METRIC = "particle-steps/sec (whole box) at 1/2/4/8 B200; interaction-kernel roo
 UNIT = "particle-steps/s"
 OPTIONS = "-symplectic -wendland -viscoart:0.1 -ddt:2 -ddtvalue:0.1 -dbc -cellmode:half" + os.environ.get("B2S_BENCH_EXTRA_OPTS", "")
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the fluid interaction kernel at the 10M-particle
-# workload, from the `ncu --set full` capture summarised in profiles/r01c_ncu_forces_pair2_v5_10M.txt (451.0 MB + 145.3 MB);
-# scaled by the fluid count when the bench runs another size
-NCU_TRAFFIC_BYTES, NCU_TRAFFIC_NPF = 596275200, 9281220
+# workload, from the `ncu --set full` captures summarised under profiles/ (file, read MB + write MB); scaled by the fluid count
+# when the bench runs another size.  A variant without a capture reports traffic null instead of a stale number.
+NCU_TRAFFIC = {5: ("profiles/r02j_ncu_forces_pair2_v5_10M.txt", 451007232 + 147835392),
+               6: ("profiles/r02i_ncu_forces_tile_v6_10M.txt", None)}
+NCU_TRAFFIC_NPF = 9281220
+# Non-tensor FP32 peak: tools/microbench.cu measures 3.798 FFMA warp-instructions per clock and SM of the nominal 4
+# (profiles/r02b_microbench.txt), i.e. 148 SM x 128 lanes x 2 flop x clock x 0.9495
+FP32_MEASURED_FRACTION = 3.798 / 4.0
 NP_TARGET = int(os.environ.get("B2S_BENCH_NP", "10000000"))
 CPU_SAMPLE_NP = int(os.environ.get("B2S_BENCH_CPU_NP", "1000000"))
+PREROLL = int(os.environ.get("B2S_BENCH_PREROLL", "200"))
 # flop model of SURVEY 8(d): per checked pair 16 flop, per real pair (r<2h) 90 flop
 FLOP_CHK, FLOP_REAL = 16.0, 90.0
 # algorithmic HBM bytes: interaction pass 50 B per fluid particle; whole Symplectic step 0.71 KB per particle
@@ -100,29 +106,41 @@ class ClockSampler:
         return out
 
 
-def run_reference_sample(np_target, steps, warmup, threads=None):
-    """Times the compiled reference CPU solver (oracle/_ref/dsph_ref_probe, unmodified DualSPHysics v5.4 objects)."""
+def run_reference_stock(np_target, steps, warmup, threads=None, tag="cpu"):
+    """Times the reference's own stock CPU/OpenMP solver (oracle/_ref/DualSPHysics5.4CPU_linux64, compiled from the unmodified
+    sources by oracle/Makefile) the way BASELINE.md prescribes: `-nsteps:K -sv:none -svtimers:1`, "Simulation Runtime" and
+    "Steps of simulation" from Run.out (src/source/JSph.cpp:3534-3542, JSphCfgRun.cpp:243).  The solver always starts at t=0, so
+    the warm-up steps are a second, shorter run whose simulation time is subtracted."""
     from oracle import oracle as orc
-    if not os.path.exists(orc.REF_PROBE):
+    if not os.path.exists(orc.REF_SOLVER):
         return None
-    case = make_case(np_target, "cpu")
+    case = make_case(np_target, tag)
     ncores = os.cpu_count() or 1
     th = min(threads or ncores, 64)          # OMP_MAXTHREADS 64 (src/source/OmpDefs.h:39)
-    out = tempfile.mkdtemp(prefix="b2s_ref_")
 
     def once(n):
-        cmd = [orc.REF_PROBE, case, out, str(n), "-dumplevel:0", "-sv:none", f"-ompthreads:{th}"] + OPTIONS.split()
+        out = tempfile.mkdtemp(prefix="b2s_ref_")
+        cmd = [orc.REF_SOLVER, case, out, "-cpu", f"-ompthreads:{th}", "-sv:none", "-svtimers:1", f"-nsteps:{n}"] + OPTIONS.split()
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        m = re.search(r"PROBE_RESULT steps=(\d+) np=(\d+) seconds=([0-9.eE+-]+) omp_threads=(\d+)", r.stdout)
-        if not m:
-            raise RuntimeError("reference probe failed: " + r.stdout[-2000:])
-        return int(m.group(1)), int(m.group(2)), float(m.group(3)), int(m.group(4))
-    # the probe always starts from t=0; warm-up steps are timed separately and subtracted
-    s_w, npc, t_w, thr = once(warmup) if warmup else (0, 0, 0.0, th)
-    s_a, npc, t_a, thr = once(warmup + steps)
+        txt = r.stdout
+        runout = os.path.join(out, "Run.out")
+        if os.path.exists(runout):
+            txt = open(runout, errors="replace").read()
+        m1 = re.search(r"Simulation Runtime\.*: *([0-9.eE+-]+) sec", txt)
+        m2 = re.search(r"Steps of simulation\.*: *([0-9,]+)", txt)
+        m3 = re.search(r"Particles of simulation \(initial\): *([0-9,]+)", txt) or re.search(r"\bNp=([0-9]+)", txt)
+        if not (m1 and m2):
+            raise RuntimeError("reference solver failed: " + txt[-1500:])
+        subprocess.run(["rm", "-rf", out])
+        return int(m2.group(1).replace(",", "")), float(m1.group(1)), (int(m3.group(1).replace(",", "")) if m3 else 0)
+    s_w, t_w, npc = once(warmup) if warmup else (0, 0.0, 0)
+    s_a, t_a, npc = once(warmup + steps)
+    if not npc:
+        from dualsphysics_b200 import bi4
+        npc = int(bi4.read_case_counts(case + ".bi4")) if hasattr(bi4, "read_case_counts") else np_target
+    nst = max(s_a - s_w, 1)
     secs = max(t_a - t_w, 1e-9)
-    return {"value": npc * steps / secs, "np": npc, "steps": steps, "seconds": secs, "cores": thr,
-            "ms_per_step": secs / steps * 1e3}
+    return {"value": npc * nst / secs, "np": npc, "steps": nst, "seconds": secs, "cores": th, "ms_per_step": secs / nst * 1e3}
 
 
 def main():
@@ -135,6 +153,7 @@ def main():
     ap.add_argument("--variant", type=int, default=int(os.environ.get("B2S_VARIANT", "5")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the variant-0 cross-check on the bench state")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e with one block only (no double buffering)")
     a = ap.parse_args()
     # the contract is ONE JSON line on stdout: libraries that write to fd 1 (NCCL prints its version there) go to stderr
@@ -155,15 +174,24 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        res = run_reference_sample(CPU_SAMPLE_NP, max(1, min(a.steps, 5)), min(a.warmup, 1))
+        # Same block as the GPU arm (a.np particles) when the host has the cores to finish K steps in minutes (~2M
+        # particle-steps/s on 16 threads); otherwise, or with B2S_BENCH_CPU_NP_REF, a smaller block of the same shape.
+        ncores = os.cpu_count() or 1
+        np_ref = int(os.environ.get("B2S_BENCH_CPU_NP_REF", str(a.np if ncores >= 12 else CPU_SAMPLE_NP)))
+        st, wu = max(1, a.steps), max(0, min(a.warmup, 5))
+        res = run_reference_stock(np_ref, st, wu, tag=("gpu" if np_ref == a.np else "cpu"))
         if res is None:
             emit({"impl": "reference", "unavailable": "oracle/_ref was not built (needs /root/reference in the build container)"})
             return 0
-        sample = f"{res['np']} particles x {res['steps']} steps of the same dam-break block (lattice start), {res['cores']} OpenMP threads"
+        same = (np_ref == a.np)
+        sample = (f"{res['np']} particles x {res['steps']} steps (after {wu} warm-up steps, subtracted) of the dam-break block"
+                  + (" = the GPU arm's block" if same else " (smaller block of the same shape)") + f", lattice start, stock DualSPHysics5.4CPU_linux64 "
+                  f"-cpu -ompthreads:{res['cores']} -nsteps -sv:none -svtimers:1, Simulation Runtime from Run.out")
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": res["steps"],
-                "warmup": min(a.warmup, 1), "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "warmup": wu, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"synthetic 3D dam-break block, {OPTIONS}; reference CPU/OpenMP build on a bounded sample", "np": res["np"]},
+                "config": {"workload": f"synthetic 3D dam-break block (BASELINE configs[1]), {OPTIONS}; the reference's stock CPU/OpenMP solver",
+                           "np": res["np"], "same_block_as_gpu_arm": same},
                 "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference", "sample": sample},
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         emit(line)
@@ -222,6 +250,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- untimed pre-roll: the lattice start disorders (200 steps), so that the timed steps see the memory access
+    #      pattern of a running simulation, not of a crystal
+    run(PREROLL)
     # ---- warm-up (the clock sampler starts here: the warm-up is the same workload and nvidia-smi needs ~100 ms per sample)
     sampler = ClockSampler(dev) if rank == 0 else None
     run(warmup)
@@ -260,6 +291,26 @@ def main():
     # ---- dominant kernel alone: CUDA events on the ctx stream (b2s_time_interaction), flop model from pair counts
     ms_k = ctx.time_interaction(5)
     chk, real = ctx.count_pairs()
+    # ---- parity on the bench state itself (outside every timed region): the benched variant against variant 0 (reference
+    #      summation order, the kernel every golden fixture pins) on the SAME particle state; max difference relative to max|field|
+    parity = None
+    if ss is None and a.variant != 0 and not a.no_parity:
+        import numpy as np
+        inter = dsb.lib.INTER_SYMPREDICTOR
+        ctx.interaction(inter)
+        fast = ctx.array("acear").copy()
+        ctx.set_variant(0)
+        ctx.interaction(inter)
+        ref0 = ctx.array("acear").copy()
+        ctx.set_variant(a.variant)
+        own = (ctx.array("code") & 0xf800) == 0x1800          # fluid, not a ghost
+        sc_a = float(np.abs(ref0[own, :3]).max()) or 1.0
+        p_ = sim.params
+        sc_r = max(float(np.abs(ref0[own, 3]).max()), float(p_.rhopzero) * p_.cs0 / float(p_.kernelh) * 1e-4)
+        parity = {"against": "variant 0 on the same state", "particles": int(own.sum()),
+                  "ace_max_rel": float(np.abs(fast[own, :3] - ref0[own, :3]).max()) / sc_a,
+                  "ar_max_rel": float(np.abs(fast[own, 3] - ref0[own, 3]).max()) / sc_r}
+        del fast, ref0
     # ---- e2e: host buffers in, host buffers out, every step (pinned memory; copies inside the timed region)
     e2e = None
     if not a.no_e2e:
@@ -354,23 +405,23 @@ def main():
             sp = time.perf_counter() - t0
             for s_ in sims:
                 s_.close()
-            e2e = {"value": sum(done) / sp, "unit": UNIT, "h2d_bytes_per_step": sum(done) // (depth * ksteps) * bytes_pp,
-                   "d2h_bytes_per_step": sum(done) // (depth * ksteps) * bytes_pp, "steps": ksteps, "pipeline_depth": depth,
-                   "serial_value": moved_all / se,
-                   "note": note + f"; {depth} independent blocks in flight (one context, host thread and set of pinned buffers each) so "
-                           "that the copies of one block overlap the kernels of the others; serial_value = one block alone"}
+            # headline = ONE block (upload, step, download strictly in sequence); the figure with several blocks in flight is secondary
+            e2e["pipelined"] = {"value": sum(done) / sp, "blocks_in_flight": depth,
+                                "note": f"{depth} independent blocks (one context, host thread and set of pinned buffers each): the copies of "
+                                        "one block overlap the kernels of the others; every step of every block still uploads, steps and downloads"}
 
     line = None
     if rank == 0:
         flops = FLOP_CHK * chk + FLOP_REAL * real
         tf_ach = flops / (ms_k * 1e-3) / 1e12
-        fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12      # 148 SMs x 128 lanes x 2 flop x max SM clock
+        fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12 * FP32_MEASURED_FRACTION
+        tr_file, tr_bytes = NCU_TRAFFIC.get(a.variant, (None, None))
         gbs_k = BYTES_INTER * npf / (ms_k * 1e-3) / 1e9
         gbs_step = BYTES_STEP * np_total / (secs / a.steps) / 1e9
         roofline = {"kernel": ({4: "k_forces_fluid_pair2", 5: "k_forces_fluid_pair2", 6: "k_forces_fluid_tile"}.get(a.variant, "k_forces_fluid_gather") + f" (fluid<-fluid+bound interaction, variant {a.variant})"), "bound": "fp32", "achieved": tf_ach, "peak": fp32_peak,
-                    "unit": "TFLOP/s", "frac": tf_ach / fp32_peak, "traffic": int(NCU_TRAFFIC_BYTES * npf / NCU_TRAFFIC_NPF),
-                    "traffic_note": "dram__bytes_read.sum+dram__bytes_write.sum per launch from profiles/r01c_ncu_forces_pair2_v5_10M.txt (ncu --set full), scaled by fluid count; algorithmic bytes = 50 B x fluid particles",
-                    "peak_source": "148 SM x 128 FP32 lanes x 2 x clocks.max.sm (non-tensor FP32 issue; tensor cores do not apply to pairwise SPH)",
+                    "unit": "TFLOP/s", "frac": tf_ach / fp32_peak, "traffic": (int(tr_bytes * npf / NCU_TRAFFIC_NPF) if tr_bytes else None),
+                    "traffic_note": f"dram__bytes_read.sum+dram__bytes_write.sum per launch from {tr_file} (ncu --set full), scaled by fluid count; algorithmic bytes = 50 B x fluid particles",
+                    "peak_source": "measured: 148 SM x 128 FP32 lanes x 2 x clocks.max.sm x 0.9495 = the FFMA issue rate tools/microbench.cu reaches on this part (profiles/r02b_microbench.txt); non-tensor FP32, tensor cores do not apply to pairwise SPH",
                     "ms_per_launch": ms_k, "pairs_checked": chk, "pairs_real": real, "flop_model": "16*checked + 90*real (SURVEY 8d)",
                     "share_of_step": 2 * ms_k / (secs / a.steps * 1e3),
                     "hbm": {"bound": "hbm", "achieved": gbs_k, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs_k / hbm_gbs,
@@ -381,23 +432,23 @@ def main():
         cpu = None
         if not a.no_cpu_baseline and world == 1:
             try:
-                res = run_reference_sample(CPU_SAMPLE_NP, 3, 1)
+                res = run_reference_stock(CPU_SAMPLE_NP, 5, 1)
                 if res:
                     cpu = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
-                           "sample": f"{res['np']} particles x {res['steps']} steps of the same dam-break block, oracle/_ref/dsph_ref_probe (unmodified DualSPHysics v5.4 CPU objects), {res['cores']} OpenMP threads"}
+                           "sample": f"{res['np']} particles x {res['steps']} steps (1 warm-up step subtracted) of a smaller block of the same shape, stock oracle/_ref/DualSPHysics5.4CPU_linux64 (unmodified DualSPHysics v5.4 sources) -cpu -nsteps -sv:none, Simulation Runtime from Run.out, {res['cores']} OpenMP threads; the full block is timed by `bench.py --impl reference`"}
             except Exception as ex:  # noqa: BLE001
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warmup,
                 "ms_per_step": secs / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"synthetic 3D dam-break block (BASELINE configs[1]), {OPTIONS}, lattice start"
+                "config": {"workload": f"synthetic 3D dam-break block (BASELINE configs[1]), {OPTIONS}, lattice start + {PREROLL} untimed steps"
                                        + ("" if world == 1 else f", block {world}x longer along x"),
                            "np_per_gpu": np_per_rank, "np_total": np_all, "fluid_rank0": npf, "interaction_variant": a.variant,
                            "parallelism": "single GPU" if world == 1 else f"{world} slabs along x, one rank per GPU; per interaction: migrants+halos over NCCL send/recv, dt by all-reduce(MAX)",
                            "exchanged_bytes_per_step": xbytes_all // max(a.steps, 1),
                            "l2_note": "inputs larger than L2: working set ~2.3 GB per GPU >> 126 MB L2",
                            "timing": "CUDA events on the kernel stream, max over ranks", "wall_ms_per_step": wall / a.steps * 1e3},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks}
+                "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks}
     if ss is not None:
         rep = ss.profile_report()
         if rep and rank == 0:
