@@ -224,3 +224,22 @@ def part_observables(datadir, dp):
         out.append(rec)
         k += 1
     return out
+
+
+def parity_report(key: str, values: dict) -> None:
+    """Appends one measured-error record to the JSON-lines file named by B2S_PARITY_REPORT (the GPU job collects it into
+    profiles/parity_r02.json); no-op when the variable is not set."""
+    path = os.environ.get("B2S_PARITY_REPORT")
+    if not path:
+        return
+    import json
+    with open(path, "a") as f:
+        f.write(json.dumps({"key": key, **values}) + "\n")
+
+
+def table_hash(a) -> int:
+    """Checksum of tools/make_golden_large.py: sum_i a[i]*(i*0x9E3779B1+1) mod 2^64."""
+    a = np.ascontiguousarray(a).reshape(-1).astype(np.uint64)
+    w = np.arange(a.size, dtype=np.uint64) * np.uint64(0x9E3779B1) + np.uint64(1)
+    with np.errstate(over="ignore"):
+        return int(np.sum(a * w, dtype=np.uint64))

@@ -61,6 +61,7 @@ def _check_forces(ctx, g, p, label, report, wide=False):
     e["viscdtmax"] = abs(info.viscdtmax - float(g["viscdtmax"])) / max(float(g["viscdtmax"]), 1e-6)
     e["velmax"] = abs(info.velmax - float(g["velmax"])) / max(float(g["velmax"]), 1e-6)
     report[label] = e
+    H.parity_report(report.get("_key", "?"), {"dump": label, **e})
     # mDBC fixtures: ill-conditioned 4x4 inverse per boundary particle -> wider pressure/ace tolerance (see test_oracle_vs_ref)
     tp, ta = (2e-3, 2e-3) if wide else (TOL_PRESS, TOL_ACE)
     assert e["press"] < tp, (label, e)
@@ -82,7 +83,7 @@ def test_golden_reference_parity(fx, variant, tmp_path, built_lib):
         sim.close()
         pytest.skip("interaction variant not built")
     p = sim.params
-    report = {}
+    report = {"_key": f"{fx}/variant{variant}"}
     g0 = _load(fx, "s0000_init")
     _check_tables(ctx, g0, p.casenpb, "init")
     # interaction through the fine-grained entry point, on separate contexts (with SPS the call updates tau,
@@ -117,6 +118,7 @@ def test_golden_reference_parity(fx, variant, tmp_path, built_lib):
             epos = float(np.max(np.abs(ctx.array("pos") - ge["pos"].reshape(-1, 3))))
             evr = H.rel_err(ctx.array("velrho"), ge["velrho"].reshape(-1, 4))
             report[f"s{s} end"] = {"pos": epos, "velrho": evr}
+            H.parity_report(report["_key"], {"dump": f"s{s:04d}_end", "pos_abs_m": epos, "velrho": evr})
             assert epos < TOL_POS and evr < (1e-5 if "mdbc" in fx else TOL_STATE), (s, epos, evr)
             assert abs(ctx.info().timestep - float(ge["timestep"])) <= 1e-6 * float(ge["timestep"])
             if "ft_center" in ge:
