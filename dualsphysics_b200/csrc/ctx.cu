@@ -74,7 +74,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   make_devcte(ctx->prm,ctx->cte);
   ctx->cap=std::max<uint32_t>(capacity_np,1024u);
   ctx->np_host=ctx->npb_host=ctx->npbok_host=0;
-  ctx->launches=0; ctx->variant=0; ctx->pre_active=false; ctx->bound_changed=true; ctx->ftcount=0;
+  ctx->launches=0; ctx->variant=5; ctx->pre_active=false; ctx->bound_changed=true; ctx->ftcount=0;
   ctx->verletstep=0;
   ctx->slab_on=false; ctx->slab_rank=0; ctx->slab_nranks=1; ctx->slab_cxa=0; ctx->slab_cxb=0; ctx->slab_counts=NULL; ctx->slab_flags=NULL; ctx->slab_counts_len=0;
   ctx->tile_bricks=NULL; ctx->tile_counters=NULL; ctx->tile_nsm=0; ctx->tile_cap=0;

@@ -37,8 +37,14 @@ __device__ __forceinline__ void hit2_or(uint32_t& mask,uint32_t rr2,uint32_t thr
 __device__ __forceinline__ uint32_t h2u(__half2 h){ return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 u2h(uint32_t u){ return *reinterpret_cast<__half2*>(&u); }
 
-template<int TDENS,int MINB>
-__global__ void __launch_bounds__(P2_BS,MINB) k_forces_fluid_pair2(ForcesArgs g, const PackCte k, const __grid_constant__ DevCte c)
+// Resident blocks per SM the register allocation aims at: the base configuration (Wendland + artificial viscosity, no floating
+// bodies) was tuned at 7 (72 registers); laminar+SPS carries 6 more packed sums and 12 stress components per round.
+template<int TKER,int TVISCO,bool FLOATING> struct P2Cfg {
+  static constexpr int MINB=(TVISCO==B2S_VISCO_LAMINARSPS? 4: ((FLOATING || TKER!=B2S_KERNEL_WENDLAND || TVISCO!=B2S_VISCO_ARTIFICIAL)? 6: P2_MINB));
+};
+
+template<int TKER,int TVISCO,int TDENS,bool FLOATING,bool MDBC2>
+__global__ void __launch_bounds__(P2_BS,(P2Cfg<TKER,TVISCO,FLOATING>::MINB)) k_forces_fluid_pair2(ForcesArgs g, const PackCte k, const __grid_constant__ DevCte c)
 {
   const DivState* ds=g.ds;
   const uint32_t npb=ds->npb, np=ds->np;
@@ -50,6 +56,16 @@ __global__ void __launch_bounds__(P2_BS,MINB) k_forces_fluid_pair2(ForcesArgs g,
   CellRange r; r.cx=r.cy=r.cz=0; r.xini=r.xfin=r.yini=r.yfin=r.zini=r.zfin=0;
   if(valid){ pp1=g.posp[p1]; velrhop1=g.velrho[p1]; r=cell_range(g.dcell[p1],c,ds); }
   const float pressp1=pp1.w, ovrhop1=b2s_rcp(velrhop1.w);
+  PackTarget tg; tg.tensil=0.f; tg.ft=false;
+  #pragma unroll
+  for(int q=0;q<6;q++)tg.tau[q]=0.f;
+  if(TKER==B2S_KERNEL_CUBIC)tg.tensil=FMUL(FMUL(pressp1,b2s_rcp(FMUL(velrhop1.w,velrhop1.w))),(pressp1>0.f? 0.01f: -0.2f));
+  if(FLOATING && valid)tg.ft=B2S_CODE_ISFLOATING(g.code[p1]);
+  if(TVISCO==B2S_VISCO_LAMINARSPS && valid){
+    const float2* tp=(const float2*)(g.tau+size_t(p1)*6);
+    const float2 t0=tp[0],t1=tp[1],t2=tp[2];
+    tg.tau[0]=t0.x; tg.tau[1]=t0.y; tg.tau[2]=t1.x; tg.tau[3]=t1.y; tg.tau[4]=t2.x; tg.tau[5]=t2.y;
+  }
   const int d=c.scelldiv, ncx=int(ds->ncx), nsheet=int(ds->nsheet), cmx=int(ds->cellmin[0]);
   const float xin=pp1.x-c.scell*float((r.cx+cmx)&((1<<B2S_XBLK)-1));   // x inside the own cell (row_trim only)
   // the untrimmed x window touches at most two blocks of 2^B2S_XBLK cells: A (of xini) and B (of xfin-1)
@@ -63,7 +79,7 @@ __global__ void __launch_bounds__(P2_BS,MINB) k_forces_fluid_pair2(ForcesArgs g,
   const float kc=c.kernelsize2*ovs*ovs;
   const uint32_t thr2=h2u(__float2half2_rn(kc*1.015f+0.02f));
   PackAcc acc;
-  acc.ax=acc.ay=acc.az=acc.ar=acc.delta=0ull; acc.visc=0.f; acc.mark=false;
+  pack_zero(acc);
   PairAcc sbnd={0,0,0,0,0,0,0,0,0,0,0,0};
   // Whole boundary pass skipped for warps whose particles have no boundary particle in their neighbour windows (one byte per
   // particle from the per-cell flags of the divide instead of 2 x 25 begin-table loads): most of the fluid is far from a wall.
@@ -162,29 +178,68 @@ __global__ void __launch_bounds__(P2_BS,MINB) k_forces_fluid_pair2(ForcesArgs g,
             f2 rr2=fma2(drz,drz,fma2(dry,dry,mul2(drx,drx)));   // b2s_rr2 order
             if(!two)rr2=pk(lo(rr2),1e30f);                      // the repeated hit of a lone round: far outside the kernel, no contribution
             // No exact test and no branch: false positives of the pre-filter (rr2>(2h)^2) and the particle itself (rr2=0) contribute 0.
-            if(pass==0)pack_body<TDENS,false>(c,k,drx,dry,drz,rr2,velrhop1,pressp1,ovrhop1,va,vb,pa.w,pb.w,acc);
-            else       pack_body<TDENS,true >(c,k,drx,dry,drz,rr2,velrhop1,pressp1,ovrhop1,va,vb,pa.w,pb.w,acc);
+            PackNeigh nb; nb.mu=pk1(1.f); nb.plain=pk1(1.f); nb.heavy_a=nb.heavy_b=false; nb.taua=nb.taub=nullptr;
+            if(pass==0){
+              if(FLOATING){
+                const typecode ca=g.code[p2a], cb=g.code[p2b];
+                const bool fla=B2S_CODE_ISFLOATING(ca), flb=B2S_CODE_ISFLOATING(cb);
+                float ma=1.f, mb=1.f;
+                if(fla){ const float m=g.ftomassp[B2S_CODE_TYPEVALUE(ca)]; ma=FMUL(m,k.ovmassf); nb.heavy_a=(m<=c.massf*1.2f); }
+                if(flb){ const float m=g.ftomassp[B2S_CODE_TYPEVALUE(cb)]; mb=FMUL(m,k.ovmassf); nb.heavy_b=(m<=c.massf*1.2f); }
+                nb.mu=pk(ma,mb); nb.plain=pk(fla? 0.f: 1.f,flb? 0.f: 1.f);
+              }
+              if(TVISCO==B2S_VISCO_LAMINARSPS){ nb.taua=(const float2*)(g.tau+size_t(p2a)*6); nb.taub=(const float2*)(g.tau+size_t(p2b)*6); }
+              pack_body<TKER,TVISCO,TDENS,FLOATING,MDBC2,false>(c,k,drx,dry,drz,rr2,velrhop1,pressp1,ovrhop1,tg,va,vb,pa.w,pb.w,nb,acc);
+            }
+            else{
+              if(MDBC2){   // mDBC2: no mass without a submerged ghost node, tangential velocity for the viscous terms (JSphCpu.cpp:851-853,990-995)
+                nb.tva=__ldg(g.tangenvel+p2a); nb.tvb=__ldg(g.tangenvel+p2b);
+                nb.mu=pk(g.boundmode[p2a]==B2S_BMODE_MDBC2OFF? 0.f: 1.f,g.boundmode[p2b]==B2S_BMODE_MDBC2OFF? 0.f: 1.f);
+              }
+              pack_body<TKER,TVISCO,TDENS,FLOATING,MDBC2,true>(c,k,drx,dry,drz,rr2,velrhop1,pressp1,ovrhop1,tg,va,vb,pa.w,pb.w,nb,acc);
+            }
           }
         }
       }
     }
     if(pass==1){ // scale and keep the boundary sums, restart the accumulators for the fluid pass
-      pack_finish<TDENS,true>(c,k,acc,velrhop1.w,sbnd);
-      acc.ax=acc.ay=acc.az=acc.ar=acc.delta=0ull; acc.visc=0.f; acc.mark=false;
+      pack_finish<TKER,TVISCO,TDENS,true>(c,k,acc,velrhop1.w,(FLOATING && tg.ft),sbnd);
+      pack_zero(acc);
     }
   }
   if(valid){
     PairAcc sf={0,0,0,0,0,0,0,0,0,0,0,0};
-    pack_finish<TDENS,false>(c,k,acc,velrhop1.w,sf);
-    finalize_store<B2S_VISCO_ARTIFICIAL,TDENS>(g,c,p1,velrhop1,sf,sbnd,ace2,viscmax);
+    pack_finish<TKER,TVISCO,TDENS,false>(c,k,acc,velrhop1.w,(FLOATING && tg.ft),sf);
+    finalize_store<TVISCO,TDENS>(g,c,p1,velrhop1,sf,sbnd,ace2,viscmax);
   }
   //-Fused maxima: ViscDtMax and AceMax^2 (replaces ReduMaxFloat x2 + cudaMemcpy, JSphGpu_ker.cu:75-125).
   reduce_maxima(g.st,viscmax,ace2);
 }
 
 // ------------------------------------------------------------------------------------------------
-bool b2s_forces_pair2_supported(const DevCte& c){
-  return c.tkernel==B2S_KERNEL_WENDLAND && c.tvisco==B2S_VISCO_ARTIFICIAL && !c.use_floating && !c.mdbc2 && (2*c.scelldiv+1)<=5;
+// Every axis of the reference's dispatch (JSphGpu_ker.cu:1080-1179) has a packed instantiation; only windows wider than 5x5 rows
+// (cells smaller than h) are left to variant 0.
+bool b2s_forces_pair2_supported(const DevCte& c){ return (2*c.scelldiv+1)<=5; }
+
+typedef void (*pair2_kernel_t)(ForcesArgs, const PackCte, const DevCte);
+template<int TKER,int TVISCO,int TDENS> static pair2_kernel_t p2_pick_ft(bool ft,bool m2){
+  if(m2)return ft? (pair2_kernel_t)k_forces_fluid_pair2<TKER,TVISCO,TDENS,true,true>: (pair2_kernel_t)k_forces_fluid_pair2<TKER,TVISCO,TDENS,false,true>;
+  return ft? (pair2_kernel_t)k_forces_fluid_pair2<TKER,TVISCO,TDENS,true,false>: (pair2_kernel_t)k_forces_fluid_pair2<TKER,TVISCO,TDENS,false,false>;
+}
+template<int TKER,int TVISCO> static pair2_kernel_t p2_pick_dens(int td,bool ft,bool m2){
+  switch(td){
+    case B2S_DDT_NONE:      return p2_pick_ft<TKER,TVISCO,B2S_DDT_NONE>(ft,m2);
+    case B2S_DDT_MOLTENI:   return p2_pick_ft<TKER,TVISCO,B2S_DDT_MOLTENI>(ft,m2);
+    case B2S_DDT_FOURTAKAS: return p2_pick_ft<TKER,TVISCO,B2S_DDT_FOURTAKAS>(ft,m2);
+    default:                return p2_pick_ft<TKER,TVISCO,B2S_DDT_FOURTAKASFULL>(ft,m2);
+  }
+}
+template<int TKER> static pair2_kernel_t p2_pick_visco(int tv,int td,bool ft,bool m2){
+  switch(tv){
+    case B2S_VISCO_ARTIFICIAL: return p2_pick_dens<TKER,B2S_VISCO_ARTIFICIAL>(td,ft,m2);
+    case B2S_VISCO_LAMINARSPS: return p2_pick_dens<TKER,B2S_VISCO_LAMINARSPS>(td,ft,m2);
+    default:                   return p2_pick_dens<TKER,B2S_VISCO_LAMINAR>(td,ft,m2);
+  }
 }
 
 int b2s_forces_pair2_launch(b2s_ctx* ctx, const ForcesArgs& g){
@@ -192,14 +247,9 @@ int b2s_forces_pair2_launch(b2s_ctx* ctx, const ForcesArgs& g){
   const uint32_t npf=ctx->np_host-ctx->npb_host;
   const unsigned gb=b2s_blocks(npf,P2_BS);
   const PackCte k=pack_cte(c);
-  // Builds for 6 and 8 resident blocks per SM were timed too (80 registers: 11.75 ms, 64 registers with 400 bytes of spills:
-  // 11.46 ms, against 11.42 ms at 7 blocks / 72 registers; profiles/r01_pair2_tuning.txt)
-  switch(c.tdensity){
-    case B2S_DDT_NONE:      k_forces_fluid_pair2<B2S_DDT_NONE,P2_MINB><<<gb,P2_BS,0,ctx->stream>>>(g,k,c); break;
-    case B2S_DDT_MOLTENI:   k_forces_fluid_pair2<B2S_DDT_MOLTENI,P2_MINB><<<gb,P2_BS,0,ctx->stream>>>(g,k,c); break;
-    case B2S_DDT_FOURTAKAS: k_forces_fluid_pair2<B2S_DDT_FOURTAKAS,P2_MINB><<<gb,P2_BS,0,ctx->stream>>>(g,k,c); break;
-    default:                k_forces_fluid_pair2<B2S_DDT_FOURTAKASFULL,P2_MINB><<<gb,P2_BS,0,ctx->stream>>>(g,k,c); break;
-  }
+  const bool ft=(c.use_floating!=0), m2=(c.mdbc2 && g.boundmode!=nullptr);
+  const pair2_kernel_t kern=(c.tkernel==B2S_KERNEL_WENDLAND? p2_pick_visco<B2S_KERNEL_WENDLAND>(c.tvisco,c.tdensity,ft,m2): p2_pick_visco<B2S_KERNEL_CUBIC>(c.tvisco,c.tdensity,ft,m2));
+  kern<<<gb,P2_BS,0,ctx->stream>>>(g,k,c);
   B2S_LAUNCHED(ctx);
   B2S_CUDA(ctx,cudaGetLastError());
   return B2S_OK;

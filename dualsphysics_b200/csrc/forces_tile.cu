@@ -273,7 +273,9 @@ __global__ void T_KATTR k_forces_fluid_tile(ForcesArgs g, TileArgs ta, const __g
         uint32_t mthr2; { const __half2 t=__float2half2_rn(-float(G::H*G::H)*1.0125f); mthr2=*reinterpret_cast<const uint32_t*>(&t); }
         const uint32_t selfadr=s_tpos+si*16u;         // list base of the target itself as the zero-contribution partner (see pack_body)
         PackAcc acc;
-        acc.ax=acc.ay=acc.az=acc.ar=acc.delta=0ull; acc.visc=0.f; acc.mark=false;
+        pack_zero(acc);
+        PackTarget tgt; tgt.tensil=0.f; tgt.ft=false;      // Wendland + artificial viscosity without floating bodies: unused
+        PackNeigh nbx; nbx.mu=nbx.plain=pk1(1.f); nbx.heavy_a=nbx.heavy_b=false; nbx.taua=nbx.taub=nullptr;
         PairAcc sbnd={0,0,0,0,0,0,0,0,0,0,0,0};
         #pragma unroll 1
         for(int pass=(hasbound? 1: 0);pass>=0;pass--){
@@ -331,8 +333,8 @@ __global__ void T_KATTR k_forces_fluid_tile(ForcesArgs g, TileArgs ta, const __g
                 auto eval=[&](const float4& pa,const float4& pb,const float4& va,const float4& vb){
                   const f2 drx=pk(FSUB(pp1.x,pa.x),FSUB(pp1.x,pb.x)), dry=pk(FSUB(pp1.y,pa.y),FSUB(pp1.y,pb.y)), drz=pk(FSUB(pp1.z,pa.z),FSUB(pp1.z,pb.z));
                   const f2 rr2=fma2(drz,drz,fma2(dry,dry,mul2(drx,drx)));   // b2s_rr2 order
-                  if(pass==0)pack_body<TDENS,false>(c,ta.k,drx,dry,drz,rr2,velrhop1,pressp1,ovrhop1,va,vb,pa.w,pb.w,acc);
-                  else       pack_body<TDENS,true >(c,ta.k,drx,dry,drz,rr2,velrhop1,pressp1,ovrhop1,va,vb,pa.w,pb.w,acc);
+                  if(pass==0)pack_body<B2S_KERNEL_WENDLAND,B2S_VISCO_ARTIFICIAL,TDENS,false,false,false>(c,ta.k,drx,dry,drz,rr2,velrhop1,pressp1,ovrhop1,tgt,va,vb,pa.w,pb.w,nbx,acc);
+                  else       pack_body<B2S_KERNEL_WENDLAND,B2S_VISCO_ARTIFICIAL,TDENS,false,false,true >(c,ta.k,drx,dry,drz,rr2,velrhop1,pressp1,ovrhop1,tgt,va,vb,pa.w,pb.w,nbx,acc);
                 };
                 //-four hits per turn: two independent packed evaluations in flight (the kernel runs at 4-5 warps per scheduler,
                 // so the instruction-level parallelism has to come from inside the warp)
@@ -351,13 +353,13 @@ __global__ void T_KATTR k_forces_fluid_tile(ForcesArgs g, TileArgs ta, const __g
             }while(c0<maxlen);
           }
           if(pass==1){ // scale and keep the boundary sums, restart the accumulators for the fluid pass
-            pack_finish<TDENS,true>(c,ta.k,acc,velrhop1.w,sbnd);
-            acc.ax=acc.ay=acc.az=acc.ar=acc.delta=0ull; acc.visc=0.f; acc.mark=false;
+            pack_finish<B2S_KERNEL_WENDLAND,B2S_VISCO_ARTIFICIAL,TDENS,true>(c,ta.k,acc,velrhop1.w,false,sbnd);
+            pack_zero(acc);
           }
         }
         if(valid){
           PairAcc sf={0,0,0,0,0,0,0,0,0,0,0,0};
-          pack_finish<TDENS,false>(c,ta.k,acc,velrhop1.w,sf);
+          pack_finish<B2S_KERNEL_WENDLAND,B2S_VISCO_ARTIFICIAL,TDENS,false>(c,ta.k,acc,velrhop1.w,false,sf);
           float a2=0.f,vm=0.f;
           finalize_store<B2S_VISCO_ARTIFICIAL,TDENS>(g,c,p1,velrhop1,sf,sbnd,a2,vm);
           ace2=fmaxf(ace2,a2); viscmax=fmaxf(viscmax,vm);

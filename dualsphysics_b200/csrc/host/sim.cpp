@@ -61,7 +61,7 @@ struct b2s_sim {
   std::vector<MotionCfg> motions;
   std::vector<GaugeCfg> gauges;
   std::vector<DampCfg> dampings;
-  int variant=0;                                                        // -b2svariant
+  int variant=-1;                                                       // -b2svariant (-1: the library default, variant 5)
   unsigned piece=0, npiece=1;                                           // slab rank / ranks: PART files are written as pieces (JPartDataBi4.cpp:99-127)
   std::string svextraparts;                                             // -svextraparts / SaveExtraParts: PARTs that get a PartExtra_XXXX.bi4
   unsigned out_total[4]={0,0,0,0};                                    // excluded particles written to PartOut so far, by motive (0: all)
@@ -165,6 +165,8 @@ static void load_case(b2s_sim* s,const std::string& options){
     p.shiftmode=sm; p.shiftcoef=float(ep.num("ShiftCoef",-2)); p.shifttfs=float(ep.num("ShiftTFS",0));
   }
   p.ftpause=ep.num("FtPause",0);
+  // TimeMax and TimeOut are mandatory in the reference (GetValueDouble without a default, JSph.cpp:786-787)
+  if(!ep.exists("TimeMax") || !ep.exists("TimeOut"))throw std::runtime_error("Case.xml: the parameters TimeMax and TimeOut are mandatory");
   s->timemax=ep.num("TimeMax",0); s->timepart=ep.num("TimeOut",0);
   p.dtini=std::max(0.0,ep.num("DtIni",0)); p.dtmin=std::max(0.0,ep.num("DtMin",0)); p.coefdtmin=double(float(ep.num("CoefDtMin",0.05)));
   p.dt_allparticles=(ep.inum("DtAllParticles",0)==1);
@@ -232,7 +234,7 @@ static void load_case(b2s_sim* s,const std::string& options){
       else if(w=="SVSTEPS")s->svallsteps=(a.empty()||atoi(a.c_str())!=0);
       else if(w=="SVEXTRAPARTS"){ if(a.empty() || a.find_first_not_of("0123456789,-")!=std::string::npos)throw std::runtime_error("-svextraparts: a PART interval or a list like 1,4,7-9"); s->svextraparts=a; }
       else if(w=="SAVEPOSDOUBLE")s->svposdouble=(a.empty()||atoi(a.c_str())!=0);
-      else if(w=="B2SVARIANT"){   // interaction kernel (include/b2s.h b2s_set_interaction_variant): 0 = reference summation order (default), 5 = fastest
+      else if(w=="B2SVARIANT"){   // interaction kernel (include/b2s.h b2s_set_interaction_variant): 5 = packed FP32, fastest (default); 0 = reference summation order
         s->variant=atoi(a.c_str()); if(a.empty() || (s->variant!=0 && s->variant!=5 && s->variant!=6))throw std::runtime_error("-b2svariant: 0, 5 or 6");
       }
       else if(w=="SV"){ s->svdata=(lower(a).find("none")==std::string::npos); }
@@ -240,6 +242,9 @@ static void load_case(b2s_sim* s,const std::string& options){
     }
   }
   if(opt_boundary>0){ p.tboundary=(opt_boundary==2? B2S_BC_MDBC: B2S_BC_DBC); p.slipmode=(opt_boundary==2? opt_slip: 0); }
+  // after the -tmax / -tout overrides: a zero TimeOut would never advance the PART schedule (JDsOutputTime needs a positive step)
+  if(!(s->timemax>0))throw std::runtime_error("TimeMax (or -tmax) must be greater than zero");
+  if(!(s->timepart>0) && !s->svallsteps)throw std::runtime_error("TimeOut (or -tout) must be greater than zero");
   if(p.tboundary==B2S_BC_MDBC && p.slipmode>=B2S_SLIP_NOSLIP && p.viscoboundfactor!=1.f)throw std::runtime_error("ViscoBoundFactor must be 1 with mDBC2 (JSph.cpp:1603)");
   if(p.tboundary==B2S_BC_MDBC && (p.slipmode<1 || p.slipmode>3))throw std::runtime_error("mDBC slip mode is invalid; use SlipMode=1");
   p.mdbc_corrector=(p.slipmode>=B2S_SLIP_NOSLIP)? 1: 0;   // MdbcCorrector (JSph.cpp:899)
@@ -657,7 +662,7 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   }
   r=b2s_create(&p,device,npsel+extra_capacity,&s->ctx);
   if(r)throw std::runtime_error(std::string("b2s_create failed: ")+b2s_error_string(r));
-  if(s->variant && (r=b2s_set_interaction_variant(s->ctx,s->variant))!=0)throw std::runtime_error("b2s_set_interaction_variant failed");
+  if(s->variant>=0 && (r=b2s_set_interaction_variant(s->ctx,s->variant))!=0)throw std::runtime_error("b2s_set_interaction_variant failed");
   // floating bodies (JSph::InitFloatings subset, JSph.cpp:1190-1290); the radii were taken from the full particle set above
   if(p.casenfloat){
     std::vector<b2s_floating> fts;
@@ -766,6 +771,7 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
     s->part=s->partbeginfirst;
   }
   if(slab_nranks>0){
+    if(slab_nranks>1 && !s->gauges.empty())throw std::runtime_error("gauges (<special><gauges>) are not evaluated in slab-decomposed runs: remove them or run on one GPU");
     r=b2s_slab_config(s->ctx,slab_rank,slab_nranks,s->slab_cuts[slab_rank],s->slab_cuts[slab_rank+1]);
     if(r)throw std::runtime_error(std::string("b2s_slab_config failed: ")+b2s_last_error(s->ctx));
   }

@@ -1,246 +1,267 @@
-// mdbc.cu -- modified Dynamic Boundary Condition, ghost-node density extrapolation (SlipMode=1, "vel0").
+// mdbc.cu -- modified Dynamic Boundary Condition: density (and, for mDBC2, velocity) extrapolated from the fluid to the ghost
+// node of every boundary particle that carries a normal.
 //
-// Replaces cusph::Interaction_MdbcCorrection -> KerInteractionMdbcCorrection_Fast (src/source/JSphGpu_mdbc_iker.cu:33-213),
-// called from JSphGpuSingle::MdbcBoundCorrection (src/source/JSphGpuSingle.cpp:686-712).  The arithmetic follows the CPU
-// statement JSphCpu::InteractionMdbcCorrectionT2 (src/source/JSphCpu_mdbc.cpp:36-150): FP32 sums of rho, grad(rho); the
-// 4x4 correction matrix accumulated and inverted in FP64 (fmath::Determinant4x4 / InverseMatrix4x4, FunctionsMath.h:210-306);
-// first-order result if |det|>=1e-3, zeroth order if a11>0, else rho0.  The boundary normals arrive already doubled
-// (boundary -> ghost node, JSph.cpp:1417).  One thread per boundary particle; the pressure cached for the interaction
-// (posp.w) is refreshed for the corrected density.  mDBC2 (SlipMode 2/3): k_mdbc2 below.
+// Replaces cusph::Interaction_MdbcCorrection / Interaction_Mdbc2Correction (src/source/JSphGpu_mdbc_iker.cu:33-213,289-582),
+// called from JSphGpuSingle::MdbcBoundCorrection (src/source/JSphGpuSingle.cpp:686-712); the reference's CPU statement of the
+// same mathematics is JSphCpu::InteractionMdbcCorrectionT2 / InteractionMdbc2CorrectionT2 (src/source/JSphCpu_mdbc.cpp:36-150,
+// 246-436).  What has to be computed per ghost node g (boundary particle + 2*normal, JSph.cpp:1417):
+//     b  = sum_j m_j (W, gradW)                      Shepard density and its gradient (4 numbers)
+//     A  = sum_j V_j (W, gradW) (x) (1, r_g - r_j)    the first-order consistency matrix (4x4), V_j = m_j/rho_j
+//   then  x = A^-1 b:  rho_g = x0,  grad(rho)_g = -x[1..3]  (first order, if A is well conditioned), else Shepard b0/A00, else rho0.
+//
+// B200 design (the reference runs one thread per boundary particle over ~250 neighbours with 20 running sums):
+//   * ONE WARP per ghost node.  Every row of neighbour cells (fixed y,z) is one contiguous range of the cell-sorted arrays, so the
+//     32 lanes stride over the row: coalesced 128-bit loads of posp/velrho, the begin-table reads are warp-uniform broadcasts.
+//   * Every lane keeps the 20 (mDBC2: 25) partial sums in FP64 registers; five xor-shuffle rounds leave the totals in all lanes.
+//   * The 4x4 system is solved by Gaussian elimination with row pivoting on [A | b] (mDBC2: [A | I], its condition number needs
+//     the inverse), FP64, fully unrolled in registers, uniform across the warp; the determinant the reference thresholds on is
+//     the signed product of the pivots.
+// The boundary normals arrive already doubled (boundary -> ghost node).  The pressure cached for the interaction (posp.w) is
+// refreshed for the corrected density.
 #include "b2s_internal.h"
 #include <float.h>
 
-#define M_BS 128
+#define M_BS 128                 // 4 ghost nodes per block
+#define M_WARPS (M_BS/32)
 
-__device__ __forceinline__ float m_rcp(float x){ float r; asm("rcp.approx.ftz.f32 %0, %1;":"=f"(r):"f"(x)); return r; }
+// ---- neighbour window of a ghost node and the walk over it ---------------------------------------------------------------
+struct GhostNode {
+  float gx,gy,gz;                // position relative to the origin of its own cell (y,z) / of its block of cells (x): the posp frame
+  int acx;                       // absolute cell x (selects the x block)
+  int cx,cy,cz;                  // cell relative to the divide's cell domain
+  int xini,xfin,yini,yfin,zini,zfin;
+};
 
+__device__ __forceinline__ GhostNode ghost_node(const DevCte& c,const DivState* ds,double px,double py,double pz,const float4 nor){
+  GhostNode g;
+  double x=px+double(nor.x), y=py+double(nor.y), z=pz+double(nor.z);
+  if(c.periactive){ uint32_t cell; b2s_pos_to_cell(c,x,y,z,cell); }   // a ghost node behind a periodic face is wrapped (JSphCpu_mdbc.cpp:50,267)
+  const double rx=x-c.domposmin[0], ry=y-c.domposmin[1], rz=z-c.domposmin[2];
+  const int ax=int(rx/c.scell_d), ay=int(ry/c.scell_d), az=int(rz/c.scell_d);
+  g.acx=ax;
+  g.gx=float(rx-c.scell_d*double((ax>>B2S_XBLK)<<B2S_XBLK)); g.gy=float(ry-c.scell_d*double(ay)); g.gz=float(rz-c.scell_d*double(az));
+  g.cx=ax-int(ds->cellmin[0]); g.cy=ay-int(ds->cellmin[1]); g.cz=az-int(ds->cellmin[2]);
+  const int d=c.scelldiv, ncx=int(ds->ncx), ncy=int(ds->ncy), ncz=int(ds->ncz);
+  g.xini=g.cx-min(g.cx,d); g.xfin=g.cx+min(ncx-g.cx-1,d)+1;
+  g.yini=g.cy-min(g.cy,d); g.yfin=g.cy+min(ncy-g.cy-1,d)+1;
+  g.zini=g.cz-min(g.cz,d); g.zfin=g.cz+min(ncz-g.cz-1,d)+1;
+  if(!(g.xfin>g.xini && g.xini>=0 && g.yini>=0 && g.zini>=0)){ g.zini=0; g.zfin=0; }   // node outside the cell domain: no neighbours
+  return g;
+}
 
-__global__ void __launch_bounds__(M_BS) k_mdbc_vel0(const DivState* __restrict__ ds, const uint32_t* __restrict__ begt,
-  const double2* __restrict__ posxy, const double* __restrict__ posz, const typecode* __restrict__ code, const float4* __restrict__ boundnor,
-  const uint32_t* __restrict__ dcell, float4* posp, float4* velrho, const __grid_constant__ DevCte c)
+// Partial sums of one lane.  s[0..3] = b, a[r][k] = A, and for mDBC2 the Shepard velocity sum, sum V W, and the divergence-of-position
+// test value of the reference ("submerged").
+template<bool MDBC2> struct GhostSums {
+  double s[4]; double a[4][4]; double v[3]; double sub;
+  __device__ __forceinline__ void zero(){
+    #pragma unroll
+    for(int r=0;r<4;r++){ s[r]=0;
+      #pragma unroll
+      for(int k=0;k<4;k++)a[r][k]=0; }
+    v[0]=v[1]=v[2]=0; sub=0;
+  }
+  __device__ __forceinline__ void warp_total(){
+    #pragma unroll
+    for(int o=16;o;o>>=1){
+      #pragma unroll
+      for(int r=0;r<4;r++){ s[r]+=__shfl_xor_sync(0xffffffffu,s[r],o);
+        #pragma unroll
+        for(int k=0;k<4;k++)a[r][k]+=__shfl_xor_sync(0xffffffffu,a[r][k],o); }
+      if(MDBC2){ v[0]+=__shfl_xor_sync(0xffffffffu,v[0],o); v[1]+=__shfl_xor_sync(0xffffffffu,v[1],o); v[2]+=__shfl_xor_sync(0xffffffffu,v[2],o); sub+=__shfl_xor_sync(0xffffffffu,sub,o); }
+    }
+  }
+};
+
+// The lanes of the warp stride over every neighbour row of g.  sgn = +1: the matrix holds (r_g - r_j) (mDBC), -1: (r_j - r_g) (mDBC2),
+// which is how the two reference kernels orient their first-order terms.
+template<bool MDBC2> __device__ __forceinline__ void ghost_walk(const DevCte& c,const DivState* ds,const uint32_t* __restrict__ begt,
+  const float4* __restrict__ posp,const float4* __restrict__ velrho,const typecode* __restrict__ code,bool fluidonly,const GhostNode& g,int lane,GhostSums<MDBC2>& u)
 {
-  const uint32_t p1=blockIdx.x*blockDim.x+threadIdx.x;
-  const uint32_t n=(c.use_floating? ds->np: ds->npbok);    // UseNormalsFt is approximated by use_floating (normals of floatings are zero unless given)
-  if(p1>=n)return;
-  const float4 nor=boundnor[p1];
-  if(nor.x==0.f && nor.y==0.f && nor.z==0.f)return;
-  float rhofinal=FLT_MAX;
-  //-Ghost node position (double, like the reference) and its cell.
-  const double2 xy=posxy[p1];
-  double gx=xy.x+double(nor.x), gy=xy.y+double(nor.y), gz=posz[p1]+double(nor.z);
-  if(c.periactive){ uint32_t gcell; b2s_pos_to_cell(c,gx,gy,gz,gcell); }   // UpdatePeriodicPos of the ghost node (JSphCpu_mdbc.cpp:50,267)
-  const int gcx=int((gx-c.domposmin[0])/c.scell_d), gcy=int((gy-c.domposmin[1])/c.scell_d), gcz=int((gz-c.domposmin[2])/c.scell_d);
-  const int cx=gcx-int(ds->cellmin[0]), cy=gcy-int(ds->cellmin[1]), cz=gcz-int(ds->cellmin[2]);
-  const int d=c.scelldiv, ncx=int(ds->ncx), ncy=int(ds->ncy), ncz=int(ds->ncz), nsheet=int(ds->nsheet);
-  const int xini=cx-(cx<d? cx: d), xfin=cx+(ncx-cx-1<d? ncx-cx-1: d)+1;
-  const int yini=cy-(cy<d? cy: d), yfin=cy+(ncy-cy-1<d? ncy-cy-1: d)+1;
-  const int zini=cz-(cz<d? cz: d), zfin=cz+(ncz-cz-1<d? ncz-cz-1: d)+1;
-  //-Ghost position relative to its own cell origin (same frame as posp).
-  const float grx=float((gx-c.domposmin[0])-c.scell_d*double((gcx>>B2S_XBLK)<<B2S_XBLK));
-  const float gry=float((gy-c.domposmin[1])-c.scell_d*double(gcy));
-  const float grz=float((gz-c.domposmin[2])-c.scell_d*double(gcz));
-  float rhop1=0.f, grdx=0.f, grdy=0.f, grdz=0.f;
-  double a11=0,a12=0,a13=0,a14=0,a21=0,a22=0,a23=0,a24=0,a31=0,a32=0,a33=0,a34=0,a41=0,a42=0,a43=0,a44=0;
   const uint32_t* beg=begt+ds->box_fluid;
-  if(xfin>xini && xini>=0 && yini>=0 && zini>=0)
-  for(int z=zini;z<zfin;z++)for(int y=yini;y<yfin;y++){
-    const int row=y*ncx+z*nsheet;
-    const float offy=c.scell*float(cy-y), offz=c.scell*float(cz-z);
-    for(int x=xini;x<xfin;x++){
-      const uint32_t pini=beg[row+x], pfin=beg[row+x+1];
-      const float offx=b2s_offx(c,gcx,x+int(ds->cellmin[0]));
-      for(uint32_t p2=pini;p2<pfin;p2++){
-        const float4 pp2=posp[p2];
-        const float drx=(grx+offx)-pp2.x, dry=(gry+offy)-pp2.y, drz=(grz+offz)-pp2.z;
-        const float rr2=drx*drx+dry*dry+drz*drz;
-        if(rr2<=c.kernelsize2 && (!c.use_floating || B2S_CODE_ISFLUID(code[p2]))){
-          float fac;
-          const float wab=wab_fac(c.tkernel,rr2,c,fac);
-          const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
-          const float massp2=c.massf;
-          const float volp2=massp2/velrho[p2].w;
-          rhop1+=massp2*wab; grdx+=massp2*frx; grdy+=massp2*fry; grdz+=massp2*frz;
-          const float vwab=wab*volp2, vfrx=frx*volp2, vfry=fry*volp2, vfrz=frz*volp2;
-          a11+=vwab;  a12+=drx*vwab;  a13+=dry*vwab;  a14+=drz*vwab;
-          a21+=vfrx;  a22+=drx*vfrx;  a23+=dry*vfrx;  a24+=drz*vfrx;
-          a31+=vfry;  a32+=drx*vfry;  a33+=dry*vfry;  a34+=drz*vfry;
-          a41+=vfrz;  a42+=drx*vfrz;  a43+=dry*vfrz;  a44+=drz*vfrz;
+  const int ncx=int(ds->ncx), nsheet=int(ds->nsheet), cmx=int(ds->cellmin[0]);
+  // the window touches at most two x blocks of the posp frame: A (of xini) and B (of xfin-1)
+  const float sxa=g.gx+b2s_offx(c,g.acx,g.xini+cmx), sxb=g.gx+b2s_offx(c,g.acx,g.xfin-1+cmx);
+  const int xmid=(((g.xfin-1+cmx)>>B2S_XBLK)<<B2S_XBLK)-cmx;             // first cell of block B
+  const float sgn=(MDBC2? -1.f: 1.f);
+  for(int z=g.zini;z<g.zfin;z++)for(int y=g.yini;y<g.yfin;y++){
+    const uint32_t* brow=beg+(y*ncx+z*nsheet);
+    const uint32_t pbeg=brow[g.xini], pend=brow[g.xfin];
+    if(pbeg>=pend)continue;
+    const uint32_t pmid=(xmid<=g.xini? pbeg: (xmid>=g.xfin? pend: brow[xmid]));
+    const float sy=g.gy+c.scell*float(g.cy-y), sz=g.gz+c.scell*float(g.cz-z);
+    for(uint32_t p2=pbeg+uint32_t(lane);p2<pend;p2+=32u){
+      const float4 pp2=__ldg(posp+p2);
+      const float drx=(p2>=pmid? sxb: sxa)-pp2.x, dry=sy-pp2.y, drz=sz-pp2.z;
+      const float rr2=drx*drx+dry*dry+drz*drz;
+      if(rr2<=c.kernelsize2 && (!fluidonly || B2S_CODE_ISFLUID(code[p2]))){
+        float fac;
+        const float wab=wab_fac(c.tkernel,rr2,c,fac);
+        const float4 v2=__ldg(velrho+p2);
+        const float vol=c.massf/v2.w;
+        const float w[4]={wab,fac*drx,fac*dry,fac*drz};                  // (W, gradW)
+        const float e[4]={1.f,sgn*drx,sgn*dry,sgn*drz};
+        #pragma unroll
+        for(int r=0;r<4;r++){
+          u.s[r]+=double(c.massf*w[r]);
+          const float vw=w[r]*vol;
+          #pragma unroll
+          for(int k=0;k<4;k++)u.a[r][k]+=double(k? e[k]*vw: vw);
+        }
+        if(MDBC2){
+          const float vw=wab*vol;
+          u.v[0]+=double(vw*v2.x); u.v[1]+=double(vw*v2.y); u.v[2]+=double(vw*v2.z);
+          u.sub-=double(vol*(drx*w[1]+dry*w[2]+drz*w[3]));
         }
       }
     }
   }
-  {
-    const float dpx=-nor.x, dpy=-nor.y, dpz=-nor.z;   // boundary particle - ghost node
-    const double det=(a14*a23*a32*a41 - a13*a24*a32*a41 - a14*a22*a33*a41 + a12*a24*a33*a41 +
-                      a13*a22*a34*a41 - a12*a23*a34*a41 - a14*a23*a31*a42 + a13*a24*a31*a42 +
-                      a14*a21*a33*a42 - a11*a24*a33*a42 - a13*a21*a34*a42 + a11*a23*a34*a42 +
-                      a14*a22*a31*a43 - a12*a24*a31*a43 - a14*a21*a32*a43 + a11*a24*a32*a43 +
-                      a12*a21*a34*a43 - a11*a22*a34*a43 - a13*a22*a31*a44 + a12*a23*a31*a44 +
-                      a13*a21*a32*a44 - a11*a23*a32*a44 - a12*a21*a33*a44 + a11*a22*a33*a44);
-    if(fabs(det)>=double(1e-3f)){
-      const double i11=(a22*(a33*a44-a34*a43)+a23*(a34*a42-a32*a44)+a24*(a32*a43-a33*a42))/det;
-      const double i21=(a21*(a34*a43-a33*a44)+a23*(a31*a44-a34*a41)+a24*(a33*a41-a31*a43))/det;
-      const double i31=(a21*(a32*a44-a34*a42)+a22*(a34*a41-a31*a44)+a24*(a31*a42-a32*a41))/det;
-      const double i41=(a21*(a33*a42-a32*a43)+a22*(a31*a43-a33*a41)+a23*(a32*a41-a31*a42))/det;
-      const double i12=(a12*(a34*a43-a33*a44)+a13*(a32*a44-a34*a42)+a14*(a33*a42-a32*a43))/det;
-      const double i22=(a11*(a33*a44-a34*a43)+a13*(a34*a41-a31*a44)+a14*(a31*a43-a33*a41))/det;
-      const double i32=(a11*(a34*a42-a32*a44)+a12*(a31*a44-a34*a41)+a14*(a32*a41-a31*a42))/det;
-      const double i42=(a11*(a32*a43-a33*a42)+a12*(a33*a41-a31*a43)+a13*(a31*a42-a32*a41))/det;
-      const double i13=(a12*(a23*a44-a24*a43)+a13*(a24*a42-a22*a44)+a14*(a22*a43-a23*a42))/det;
-      const double i23=(a11*(a24*a43-a23*a44)+a13*(a21*a44-a24*a41)+a14*(a23*a41-a21*a43))/det;
-      const double i33=(a11*(a22*a44-a24*a42)+a12*(a24*a41-a21*a44)+a14*(a21*a42-a22*a41))/det;
-      const double i43=(a11*(a23*a42-a22*a43)+a12*(a21*a43-a23*a41)+a13*(a22*a41-a21*a42))/det;
-      const double i14=(a12*(a24*a33-a23*a34)+a13*(a22*a34-a24*a32)+a14*(a23*a32-a22*a33))/det;
-      const double i24=(a11*(a23*a34-a24*a33)+a13*(a24*a31-a21*a34)+a14*(a21*a33-a23*a31))/det;
-      const double i34=(a11*(a24*a32-a22*a34)+a12*(a21*a34-a24*a31)+a14*(a22*a31-a21*a32))/det;
-      const double i44=(a11*(a22*a33-a23*a32)+a12*(a23*a31-a21*a33)+a13*(a21*a32-a22*a31))/det;
-      const float rhoghost=float(i11*rhop1+i12*grdx+i13*grdy+i14*grdz);
-      const float ggx=-float(i21*rhop1+i22*grdx+i23*grdy+i24*grdz);
-      const float ggy=-float(i31*rhop1+i32*grdx+i33*grdy+i34*grdz);
-      const float ggz=-float(i41*rhop1+i42*grdx+i43*grdy+i44*grdz);
-      rhofinal=(rhoghost+ggx*dpx+ggy*dpy+ggz*dpz);
-    }
-    else if(a11>0)rhofinal=float(double(rhop1)/a11);
-  }
-  rhofinal=(rhofinal!=FLT_MAX? rhofinal: c.rhopzero);
-  float4 vr=velrho[p1]; vr.w=rhofinal; velrho[p1]=vr;
-  float4 pp=posp[p1]; pp.w=b2s_press(rhofinal,c); posp[p1]=pp;
 }
 
-// ------------------------------------------------------------------------------------------------
-// mDBC2 (SlipMode 2 no-slip / 3 free-slip): JSphCpu::InteractionMdbc2CorrectionT2 (src/source/JSphCpu_mdbc.cpp:246-436; GPU
-// KerInteractionMdbc2Correction_Fast, JSphGpu_mdbc_iker.cu:289-582) with MDBC2_KEEPVEL defined as in the reference
-// (DualSphDef.h:471): the boundary particle keeps its velocity, only its density is replaced.
-//   submerged ghost node : boundmode=MDBC2; density from the first-order matrix if |det|>=1e-3 and the scaled condition number
-//                          dp^2*|A|inf*|A^-1|inf <= 50, else Shepard (sumwab<0.1: max(rho0,Shepard)); then pressure cloning
-//                          P = cs0^2 (rho_g - rho0) + rho0 ((g - a_motion).n)(dpos.n), rho = rho0 + P/cs0^2;
-//                          ghost velocity by Shepard sum; tangenvel = tangential part of (2 v_motion - v_ghost) [no-slip] or v_ghost [free-slip]
+// Gaussian elimination with row pivoting on the augmented rows m[4][4+NB], everything in registers (all loops unroll, the row
+// exchange is a predicated swap).  Leaves the NB solutions in the last NB columns and returns det(A) = signed product of pivots.
+template<int NB> __device__ __forceinline__ double eliminate4(double (&m)[4][4+NB]){
+  double det=1.0;
+  #pragma unroll
+  for(int k=0;k<4;k++){
+    #pragma unroll
+    for(int r=k+1;r<4;r++){
+      const bool sw=(fabs(m[r][k])>fabs(m[k][k]));
+      #pragma unroll
+      for(int q=k;q<4+NB;q++){ const double t=m[k][q]; m[k][q]=(sw? m[r][q]: t); m[r][q]=(sw? t: m[r][q]); }
+      det=(sw? -det: det);
+    }
+    det*=m[k][k];
+    const double ipiv=1.0/m[k][k];
+    #pragma unroll
+    for(int r=k+1;r<4;r++){
+      const double f=m[r][k]*ipiv;
+      #pragma unroll
+      for(int q=k+1;q<4+NB;q++)m[r][q]-=f*m[k][q];
+    }
+    #pragma unroll
+    for(int q=k+1;q<4+NB;q++)m[k][q]*=ipiv;                               // row k normalised: back substitution needs no division
+  }
+  #pragma unroll
+  for(int b=0;b<NB;b++){
+    #pragma unroll
+    for(int r=2;r>=0;r--){
+      #pragma unroll
+      for(int q=r+1;q<4;q++)m[r][4+b]-=m[r][q]*m[q][4+b];
+    }
+  }
+  return det;
+}
+
+// ---- SlipMode 1 ("vel0"): density only ------------------------------------------------------------------------------------
+// First-order result if |det A| >= 1e-3, Shepard if A00 > 0, else rho0 (JSphCpu_mdbc.cpp:112-147).
+__global__ void __launch_bounds__(M_BS) k_mdbc_vel0(const DivState* __restrict__ ds, const uint32_t* __restrict__ begt,
+  const double2* __restrict__ posxy, const double* __restrict__ posz, const typecode* __restrict__ code, const float4* __restrict__ boundnor,
+  float4* posp, float4* velrho, const __grid_constant__ DevCte c)
+{
+  const uint32_t p1=blockIdx.x*M_WARPS+(threadIdx.x>>5);
+  const int lane=threadIdx.x&31;
+  const uint32_t n=(c.use_floating? ds->np: ds->npbok);    // floating particles may carry normals too (UseNormalsFt)
+  if(p1>=n)return;
+  const float4 nor=boundnor[p1];
+  if(nor.x==0.f && nor.y==0.f && nor.z==0.f)return;
+  const double2 xy=posxy[p1];
+  const GhostNode g=ghost_node(c,ds,xy.x,xy.y,posz[p1],nor);
+  GhostSums<false> u; u.zero();
+  ghost_walk<false>(c,ds,begt,posp,velrho,code,c.use_floating!=0,g,lane,u);
+  u.warp_total();
+  const float b0=float(u.s[0]), b1=float(u.s[1]), b2=float(u.s[2]), b3=float(u.s[3]);
+  double m[4][5];
+  #pragma unroll
+  for(int r=0;r<4;r++){
+    #pragma unroll
+    for(int k=0;k<4;k++)m[r][k]=u.a[r][k];
+  }
+  m[0][4]=double(b0); m[1][4]=double(b1); m[2][4]=double(b2); m[3][4]=double(b3);
+  const double a00=u.a[0][0];
+  const double det=eliminate4<1>(m);
+  float rhofinal=c.rhopzero;
+  if(fabs(det)>=double(1e-3f)){
+    // value at the boundary particle = value at the ghost node + gradient . (particle - node), particle - node = -normal
+    const float rhog=float(m[0][4]), gx=-float(m[1][4]), gy=-float(m[2][4]), gz=-float(m[3][4]);
+    rhofinal=rhog+gx*(-nor.x)+gy*(-nor.y)+gz*(-nor.z);
+  }
+  else if(a00>0)rhofinal=float(double(b0)/a00);
+  if(lane==0){
+    float4 vr=velrho[p1]; vr.w=rhofinal; velrho[p1]=vr;
+    float4 pp=posp[p1]; pp.w=b2s_press(rhofinal,c); posp[p1]=pp;
+  }
+}
+
+// ---- SlipMode 2 (no-slip) / 3 (free-slip): mDBC2 ---------------------------------------------------------------------------
+// JSphCpu_mdbc.cpp:246-436 with MDBC2_KEEPVEL as the reference defines it (DualSphDef.h:471): the boundary particle keeps its
+// velocity, only its density is replaced.
+//   submerged ghost node : boundmode=MDBC2; density from the first-order system if |det|>=1e-3 and the scaled condition number
+//                          dp^2*|A|inf*|A^-1|inf <= 50 (JSphCpu_mdbc.cpp:222-229), else Shepard (sum V W < 0.1: max(rho0,Shepard));
+//                          then pressure cloning P = cs0^2 (rho_g - rho0) + rho0 ((g - a_motion).n)(dpos.n), rho = rho0 + P/cs0^2
+//                          (JSphCpu_mdbc.cpp:182-207); ghost velocity by Shepard sum; tangenvel = tangential part of
+//                          (2 v_motion - v_ghost) [no-slip] or of v_ghost [free-slip]
 //   not submerged        : boundmode=MDBC2OFF (the interaction then uses mass 0), rho=rho0, tangenvel from the motion velocity.
-// Fixed boundaries only in this build: v_motion = a_motion = 0 (moving/floating + mDBC2 is rejected by the loader).
-// ------------------------------------------------------------------------------------------------
+// v_motion = the velocity the boundary particle carries, a_motion = MotionAce of the last motion step (zero for fixed boundaries).
 __global__ void __launch_bounds__(M_BS) k_mdbc2(const DivState* __restrict__ ds, const uint32_t* __restrict__ begt,
   const double2* __restrict__ posxy, const double* __restrict__ posz, const typecode* __restrict__ code, const float4* __restrict__ boundnor,
   float4* posp, float4* velrho, uint8_t* boundmode, float4* tangenvel, const float4* __restrict__ motionace, int freeslip, const __grid_constant__ DevCte c)
 {
-  const uint32_t p1=blockIdx.x*blockDim.x+threadIdx.x;
+  const uint32_t p1=blockIdx.x*M_WARPS+(threadIdx.x>>5);
+  const int lane=threadIdx.x&31;
   if(p1>=ds->npb)return;
-  boundmode[p1]=B2S_BMODE_DBC;
   const float4 nor=boundnor[p1];
-  if(nor.x==0.f && nor.y==0.f && nor.z==0.f)return;
+  if(nor.x==0.f && nor.y==0.f && nor.z==0.f){ if(lane==0)boundmode[p1]=B2S_BMODE_DBC; return; }
   const double2 xy=posxy[p1];
-  double gx=xy.x+double(nor.x), gy=xy.y+double(nor.y), gz=posz[p1]+double(nor.z);
-  if(c.periactive){ uint32_t gcell; b2s_pos_to_cell(c,gx,gy,gz,gcell); }   // UpdatePeriodicPos of the ghost node (JSphCpu_mdbc.cpp:50,267)
-  const int gcx=int((gx-c.domposmin[0])/c.scell_d), gcy=int((gy-c.domposmin[1])/c.scell_d), gcz=int((gz-c.domposmin[2])/c.scell_d);
-  const int cx=gcx-int(ds->cellmin[0]), cy=gcy-int(ds->cellmin[1]), cz=gcz-int(ds->cellmin[2]);
-  const int d=c.scelldiv, ncx=int(ds->ncx), ncy=int(ds->ncy), ncz=int(ds->ncz), nsheet=int(ds->nsheet);
-  const int xini=cx-(cx<d? cx: d), xfin=cx+(ncx-cx-1<d? ncx-cx-1: d)+1;
-  const int yini=cy-(cy<d? cy: d), yfin=cy+(ncy-cy-1<d? ncy-cy-1: d)+1;
-  const int zini=cz-(cz<d? cz: d), zfin=cz+(ncz-cz-1<d? ncz-cz-1: d)+1;
-  const float grx=float((gx-c.domposmin[0])-c.scell_d*double((gcx>>B2S_XBLK)<<B2S_XBLK));
-  const float gry=float((gy-c.domposmin[1])-c.scell_d*double(gcy));
-  const float grz=float((gz-c.domposmin[2])-c.scell_d*double(gcz));
-  float rhop1=0.f, grdx=0.f, grdy=0.f, grdz=0.f, sumwab=0.f, submerged=0.f;
-  double vx=0,vy=0,vz=0;
-  double a11=0,a12=0,a13=0,a14=0,a21=0,a22=0,a23=0,a24=0,a31=0,a32=0,a33=0,a34=0,a41=0,a42=0,a43=0,a44=0;
-  const uint32_t* beg=begt+ds->box_fluid;
-  if(xfin>xini && xini>=0 && yini>=0 && zini>=0)
-  for(int z=zini;z<zfin;z++)for(int y=yini;y<yfin;y++){
-    const int row=y*ncx+z*nsheet;
-    const float offy=c.scell*float(cy-y), offz=c.scell*float(cz-z);
-    for(int x=xini;x<xfin;x++){
-      const uint32_t pini=beg[row+x], pfin=beg[row+x+1];
-      const float offx=b2s_offx(c,gcx,x+int(ds->cellmin[0]));
-      for(uint32_t p2=pini;p2<pfin;p2++){
-        const float4 pp2=posp[p2];
-        const float drx=(grx+offx)-pp2.x, dry=(gry+offy)-pp2.y, drz=(grz+offz)-pp2.z;
-        const float rr2=drx*drx+dry*dry+drz*drz;
-        if(rr2<=c.kernelsize2 && B2S_CODE_ISFLUID(code[p2])){
-          float fac;
-          const float wab=wab_fac(c.tkernel,rr2,c,fac);
-          const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
-          const float4 v2=velrho[p2];
-          const float massp2=c.massf;
-          const float volp2=massp2/v2.w;
-          submerged-=volp2*(drx*frx+dry*fry+drz*frz);
-          rhop1+=massp2*wab; grdx+=massp2*frx; grdy+=massp2*fry; grdz+=massp2*frz;
-          const float vwab=wab*volp2, vfrx=frx*volp2, vfry=fry*volp2, vfrz=frz*volp2;
-          sumwab+=vwab;
-          vx+=vwab*v2.x; vy+=vwab*v2.y; vz+=vwab*v2.z;
-          a11+=vwab;  a12-=drx*vwab;  a13-=dry*vwab;  a14-=drz*vwab;
-          a21+=vfrx;  a22-=drx*vfrx;  a23-=dry*vfrx;  a24-=drz*vfrx;
-          a31+=vfry;  a32-=drx*vfry;  a33-=dry*vfry;  a34-=drz*vfry;
-          a41+=vfrz;  a42-=drx*vfrz;  a43-=dry*vfrz;  a44-=drz*vfrz;
-        }
-      }
-    }
-  }
+  const GhostNode g=ghost_node(c,ds,xy.x,xy.y,posz[p1],nor);
+  GhostSums<true> u; u.zero();
+  ghost_walk<true>(c,ds,begt,posp,velrho,code,true,g,lane,u);
+  u.warp_total();
   const float snormal=sqrtf(nor.x*nor.x+nor.y*nor.y+nor.z*nor.z);
   const float nx=nor.x/snormal, ny=nor.y/snormal, nz=nor.z/snormal;
-  float rhofinal, tvx,tvy,tvz;
-  if(submerged>0.f){
-    boundmode[p1]=B2S_BMODE_MDBC2;
-    if(sumwab<0.1f)rhofinal=fmaxf(c.rhopzero,float(double(rhop1)/a11));
+  const float4 vm=velrho[p1];
+  float rhofinal, v2x=vm.x, v2y=vm.y, v2z=vm.z;
+  uint8_t mode=B2S_BMODE_MDBC2OFF;
+  if(float(u.sub)>0.f){
+    mode=B2S_BMODE_MDBC2;
+    const float b0=float(u.s[0]), b1=float(u.s[1]), b2=float(u.s[2]), b3=float(u.s[3]);
+    const double a00=u.a[0][0];
+    const float shepard=float(double(b0)/a00);
+    if(float(a00)<0.1f)rhofinal=fmaxf(c.rhopzero,shepard);
     else{
-      const double det=(a14*a23*a32*a41 - a13*a24*a32*a41 - a14*a22*a33*a41 + a12*a24*a33*a41 +
-                        a13*a22*a34*a41 - a12*a23*a34*a41 - a14*a23*a31*a42 + a13*a24*a31*a42 +
-                        a14*a21*a33*a42 - a11*a24*a33*a42 - a13*a21*a34*a42 + a11*a23*a34*a42 +
-                        a14*a22*a31*a43 - a12*a24*a31*a43 - a14*a21*a32*a43 + a11*a24*a32*a43 +
-                        a12*a21*a34*a43 - a11*a22*a34*a43 - a13*a22*a31*a44 + a12*a23*a31*a44 +
-                        a13*a21*a32*a44 - a11*a23*a32*a44 - a12*a21*a33*a44 + a11*a22*a33*a44);
-      if(fabs(det)>=0.001){
-        const double i11=(a22*(a33*a44-a34*a43)+a23*(a34*a42-a32*a44)+a24*(a32*a43-a33*a42))/det;
-        const double i21=(a21*(a34*a43-a33*a44)+a23*(a31*a44-a34*a41)+a24*(a33*a41-a31*a43))/det;
-        const double i31=(a21*(a32*a44-a34*a42)+a22*(a34*a41-a31*a44)+a24*(a31*a42-a32*a41))/det;
-        const double i41=(a21*(a33*a42-a32*a43)+a22*(a31*a43-a33*a41)+a23*(a32*a41-a31*a42))/det;
-        const double i12=(a12*(a34*a43-a33*a44)+a13*(a32*a44-a34*a42)+a14*(a33*a42-a32*a43))/det;
-        const double i22=(a11*(a33*a44-a34*a43)+a13*(a34*a41-a31*a44)+a14*(a31*a43-a33*a41))/det;
-        const double i32=(a11*(a34*a42-a32*a44)+a12*(a31*a44-a34*a41)+a14*(a32*a41-a31*a42))/det;
-        const double i42=(a11*(a32*a43-a33*a42)+a12*(a33*a41-a31*a43)+a13*(a31*a42-a32*a41))/det;
-        const double i13=(a12*(a23*a44-a24*a43)+a13*(a24*a42-a22*a44)+a14*(a22*a43-a23*a42))/det;
-        const double i23=(a11*(a24*a43-a23*a44)+a13*(a21*a44-a24*a41)+a14*(a23*a41-a21*a43))/det;
-        const double i33=(a11*(a22*a44-a24*a42)+a12*(a24*a41-a21*a44)+a14*(a21*a42-a22*a41))/det;
-        const double i43=(a11*(a23*a42-a22*a43)+a12*(a21*a43-a23*a41)+a13*(a22*a41-a21*a42))/det;
-        const double i14=(a12*(a24*a33-a23*a34)+a13*(a22*a34-a24*a32)+a14*(a23*a32-a22*a33))/det;
-        const double i24=(a11*(a23*a34-a24*a33)+a13*(a24*a31-a21*a34)+a14*(a21*a33-a23*a31))/det;
-        const double i34=(a11*(a24*a32-a22*a34)+a12*(a21*a34-a24*a31)+a14*(a22*a31-a21*a32))/det;
-        const double i44=(a11*(a22*a33-a23*a32)+a12*(a23*a31-a21*a33)+a13*(a21*a32-a22*a31))/det;
-        // scaled condition number with infinity norms (Mdbc2InfNorm4x4, JSphCpu_mdbc.cpp:222-229)
-        const float na=fmaxf(fmaxf(float(fabs(a11)+fabs(a12)+fabs(a13)+fabs(a14)),float(fabs(a21)+fabs(a22)+fabs(a23)+fabs(a24))),
-                             fmaxf(float(fabs(a31)+fabs(a32)+fabs(a33)+fabs(a34)),float(fabs(a41)+fabs(a42)+fabs(a43)+fabs(a44))));
-        const float ni=fmaxf(fmaxf(float(fabs(i11)+fabs(i12)+fabs(i13)+fabs(i14)),float(fabs(i21)+fabs(i22)+fabs(i23)+fabs(i24))),
-                             fmaxf(float(fabs(i31)+fabs(i32)+fabs(i33)+fabs(i34)),float(fabs(i41)+fabs(i42)+fabs(i43)+fabs(i44))));
-        const float condinf=c.dp2*na*ni;
-        if(condinf<=50.f)rhofinal=float(i11*rhop1+i12*grdx+i13*grdy+i14*grdz);
-        else rhofinal=float(double(rhop1)/a11);
+      double m[4][8];
+      float na=0.f;
+      #pragma unroll
+      for(int r=0;r<4;r++){
+        double rowsum=0;
+        #pragma unroll
+        for(int k=0;k<4;k++){ m[r][k]=u.a[r][k]; m[r][4+k]=(r==k? 1.0: 0.0); rowsum+=fabs(u.a[r][k]); }
+        na=fmaxf(na,float(rowsum));
       }
-      else rhofinal=float(double(rhop1)/a11);
+      const double det=eliminate4<4>(m);
+      rhofinal=shepard;
+      if(fabs(det)>=0.001){
+        float ni=0.f;
+        #pragma unroll
+        for(int r=0;r<4;r++)ni=fmaxf(ni,float(fabs(m[r][4])+fabs(m[r][5])+fabs(m[r][6])+fabs(m[r][7])));
+        if(c.dp2*na*ni<=50.f)rhofinal=float(m[0][4]*b0+m[0][5]*b1+m[0][6]*b2+m[0][7]*b3);
+      }
     }
-    // pressure cloning (Mdbc2PressClone, JSphCpu_mdbc.cpp:182-207); dpos = boundary particle - ghost node = -normal
     const float pghost=float(c.cs0_d*c.cs0_d*double(rhofinal-c.rhopzero));
-    const float normpos=(-nor.x)*nx+(-nor.y)*ny+(-nor.z)*nz;
-    // force = gravity - acceleration of the imposed motion (zero for fixed boundaries; MotionAce of the last RunMotion otherwise)
+    const float normpos=(-nor.x)*nx+(-nor.y)*ny+(-nor.z)*nz;             // (particle - node) . n
     const float4 mace=(motionace? motionace[p1]: make_float4(0.f,0.f,0.f,0.f));
     const float normforce=c.rhopzero*((c.gravity[0]-mace.x)*nx+(c.gravity[1]-mace.y)*ny+(c.gravity[2]-mace.z)*nz);
-    const float pressfinal=pghost+normforce*normpos;
-    rhofinal=c.rhopzero+float(double(pressfinal)/(c.cs0_d*c.cs0_d));
-    const float gvx=float(vx/a11), gvy=float(vy/a11), gvz=float(vz/a11);
-    // no-slip: v2 = 2*v_motion - v_ghost ; free-slip: v2 = v_ghost.  v_motion = the velocity the boundary particle carries
-    // (MDBC2_KEEPVEL, DualSphDef.h:471: velrho of a boundary particle is never overwritten, so it equals MotionVel)
-    const float4 vm=velrho[p1];
-    const float v2x=(freeslip? gvx: vm.x+vm.x-gvx), v2y=(freeslip? gvy: vm.y+vm.y-gvy), v2z=(freeslip? gvz: vm.z+vm.z-gvz);
+    rhofinal=c.rhopzero+float(double(pghost+normforce*normpos)/(c.cs0_d*c.cs0_d));
+    const float gvx=float(u.v[0]/a00), gvy=float(u.v[1]/a00), gvz=float(u.v[2]/a00);
+    v2x=(freeslip? gvx: vm.x+vm.x-gvx); v2y=(freeslip? gvy: vm.y+vm.y-gvy); v2z=(freeslip? gvz: vm.z+vm.z-gvz);
+  }
+  else rhofinal=c.rhopzero;
+  if(lane==0){
     const float vdn=v2x*nx+v2y*ny+v2z*nz;
-    tvx=v2x-vdn*nx; tvy=v2y-vdn*ny; tvz=v2z-vdn*nz;
+    boundmode[p1]=mode;
+    float4 vr=vm; vr.w=rhofinal; velrho[p1]=vr;
+    float4 pp=posp[p1]; pp.w=b2s_press(rhofinal,c); posp[p1]=pp;
+    tangenvel[p1]=make_float4(v2x-vdn*nx,v2y-vdn*ny,v2z-vdn*nz,0.f);
   }
-  else{
-    boundmode[p1]=B2S_BMODE_MDBC2OFF;
-    rhofinal=c.rhopzero;
-    const float4 vm=velrho[p1];   // tangential part of the motion velocity
-    const float vdn=vm.x*nx+vm.y*ny+vm.z*nz;
-    tvx=vm.x-vdn*nx; tvy=vm.y-vdn*ny; tvz=vm.z-vdn*nz;
-  }
-  float4 vr=velrho[p1]; vr.w=rhofinal; velrho[p1]=vr;
-  float4 pp=posp[p1]; pp.w=b2s_press(rhofinal,c); posp[p1]=pp;
-  tangenvel[p1]=make_float4(tvx,tvy,tvz,0.f);
 }
 
 int b2s_mdbc_impl(b2s_ctx* ctx){
@@ -249,15 +270,15 @@ int b2s_mdbc_impl(b2s_ctx* ctx){
     if(ctx->cte.use_floating)return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"mDBC2 (SlipMode 2/3) with floating bodies is not supported");
     if(ctx->prm.casenmoving && ctx->slab_on)return b2s_fail(ctx,B2S_ERR_UNSUPPORTED,"mDBC2 (SlipMode 2/3) with moving boundaries is not supported with slab decomposition");
     if(!ctx->npb_host)return B2S_OK;
-    k_mdbc2<<<b2s_blocks(ctx->npb_host,M_BS),M_BS,0,ctx->stream>>>(ctx->div,(const uint32_t*)ctx->begincell,ctx->cur.posxy,ctx->cur.posz,ctx->cur.code,
+    k_mdbc2<<<b2s_blocks(ctx->npb_host,M_WARPS),M_BS,0,ctx->stream>>>(ctx->div,(const uint32_t*)ctx->begincell,ctx->cur.posxy,ctx->cur.posz,ctx->cur.code,
       ctx->boundnor,ctx->posp,ctx->cur.velrho,ctx->boundmode,ctx->tangenvel,ctx->motionace,ctx->prm.slipmode==B2S_SLIP_FREESLIP? 1: 0,ctx->cte); B2S_LAUNCHED(ctx);
     B2S_CUDA(ctx,cudaGetLastError());
     return B2S_OK;
   }
   const uint32_t n=(ctx->cte.use_floating? ctx->np_host: ctx->npb_host);
   if(!n)return B2S_OK;
-  k_mdbc_vel0<<<b2s_blocks(n,M_BS),M_BS,0,ctx->stream>>>(ctx->div,(const uint32_t*)ctx->begincell,ctx->cur.posxy,ctx->cur.posz,ctx->cur.code,
-    ctx->boundnor,ctx->cur.dcell,ctx->posp,ctx->cur.velrho,ctx->cte); B2S_LAUNCHED(ctx);
+  k_mdbc_vel0<<<b2s_blocks(n,M_WARPS),M_BS,0,ctx->stream>>>(ctx->div,(const uint32_t*)ctx->begincell,ctx->cur.posxy,ctx->cur.posz,ctx->cur.code,
+    ctx->boundnor,ctx->posp,ctx->cur.velrho,ctx->cte); B2S_LAUNCHED(ctx);
   B2S_CUDA(ctx,cudaGetLastError());
   return B2S_OK;
 }

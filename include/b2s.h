@@ -271,12 +271,15 @@ int b2s_time_interaction(b2s_ctx* ctx, int reps, float* ms_per_launch);
 int b2s_launch_count(b2s_ctx* ctx, uint64_t* launches, int reset);
 /* CUDA stream the ctx launches on (cudaStream_t cast to void*), for external event timing. */
 int b2s_get_stream(b2s_ctx* ctx, void** stream_out);
-/* Selects the fluid interaction kernel variant: 0 = gather (one thread per particle, reference summation order; default),
- * 5 = FP16 pre-filter into per-lane hit masks, two hits per lane and round in packed FP32, mirror rows (csrc/forces_pair2.cu;
- *     Wendland + artificial viscosity without floating bodies, other configurations run variant 0; equal to 0 within rounding:
- *     the pair terms are re-associated, csrc/forces_pair2.cuh),
+/* Selects the fluid interaction kernel variant:
+ * 5 = (default) FP16 pre-filter into per-lane hit masks, two hits per lane and round in packed FP32, mirror rows
+ *     (csrc/forces_pair2.cu); instantiated for every axis of the reference's dispatch (JSphGpu_ker.cu:1080-1179: Wendland / cubic,
+ *     artificial / laminar / laminar+SPS, every DDT mode, floating bodies, mDBC2); equal to 0 within rounding: the pair terms are
+ *     re-associated (csrc/forces_pair2.cuh);
+ * 0 = gather: one thread per particle, the reference's summation order (the parity anchor of the golden fixtures);
  * 6 = bricks of cells staged in shared memory in one FP32 frame per tile, per-lane hit lists over many rows, the same packed
- *     pair body (csrc/forces_tile.cu; same scope as 5).
+ *     pair body (csrc/forces_tile.cu; Wendland + artificial viscosity without floating bodies, otherwise runs 5; measured slower
+ *     than 5, kept as the record of the shared-memory design: profiles/README.md).
  * Other values: B2S_ERR_ARG. */
 int b2s_set_interaction_variant(b2s_ctx* ctx, int variant);
 /* Test hook for variant 6: particle capacity of a shared-memory tile (0 = built-in 4096).  A lower value makes small cases take

@@ -5,10 +5,12 @@ Checkers, in order of authority:
      ace/ar/dt/state within the per-field tolerances below;
   2. the C restatement (oracle/) on freshly generated cases at other sizes;
   3. size-independent properties at larger N (sortedness / permutation / begin-table consistency).
-Tolerances (relative to max|field| over particles, absolute floor where the field can vanish):
-  ace 5e-4, ar 5e-4 (floor rho0*cs0/h*1e-4), press 3e-4, dt 2e-5, pos 1e-7 m absolute, vel/rho 2e-6 after 10 steps.
-They are set by what the reference itself reproduces: its -ffast-math CPU build and the IEEE oracle already differ
-by 1e-4 in ace because the Tait EOS turns one ulp of rho/rho0 into ~3e-5 of max|P| (measured).
+Tolerances (relative to max|field| over particles, absolute floor where the field can vanish; ar: floor rho0*cs0/h*1e-4; positions
+absolute in m): per fixture and field from tests/tolerances.py = max(3 x the error measured on the B200, the reference's own
+build-to-build noise (-ffast-math against plain -O3, profiles/ref_noise_r02.json), north_star's 1e-5).  Typical values: ace 1e-4,
+ar 2e-4, press 1.5e-4, dt 1e-6, pos 1.4e-8 m, vel/rho 1e-6 after 10 steps; mDBC fixtures (ill-conditioned 4x4 system per boundary
+particle, where the two reference builds differ by 6e-4 themselves) press 2e-3, ace 4e-4..1.2e-3.
+The oracle-based tests below (no reference dump) keep the looser class values TOL_*.
 """
 import json
 import os
@@ -17,6 +19,7 @@ import numpy as np
 import pytest
 
 import helpers as H
+import tolerances as T
 import dualsphysics_b200 as dsb
 from dualsphysics_b200 import b2sd
 
@@ -62,7 +65,12 @@ def _check_forces(ctx, g, p, label, report, wide=False):
     e["velmax"] = abs(info.velmax - float(g["velmax"])) / max(float(g["velmax"]), 1e-6)
     report[label] = e
     H.parity_report(report.get("_key", "?"), {"dump": label, **e})
-    # mDBC fixtures: ill-conditioned 4x4 inverse per boundary particle -> wider pressure/ace tolerance (see test_oracle_vs_ref)
+    fx = report.get("_fx")
+    if fx is not None:      # reference fixture: measured per-field tolerances (tests/tolerances.py)
+        for f in ("press", "ace", "ar", "acemax", "velmax", "viscdtmax"):
+            assert e[f] <= T.tol(fx, f), (label, f, e[f], T.tol(fx, f))
+        return
+    # oracle-based checks: class values (mDBC: ill-conditioned 4x4 system per boundary particle)
     tp, ta = (2e-3, 2e-3) if wide else (TOL_PRESS, TOL_ACE)
     assert e["press"] < tp, (label, e)
     assert e["ace"] < ta, (label, e)
@@ -83,7 +91,7 @@ def test_golden_reference_parity(fx, variant, tmp_path, built_lib):
         sim.close()
         pytest.skip("interaction variant not built")
     p = sim.params
-    report = {"_key": f"{fx}/variant{variant}"}
+    report = {"_key": f"{fx}/variant{variant}", "_fx": fx}
     g0 = _load(fx, "s0000_init")
     _check_tables(ctx, g0, p.casenpb, "init")
     # interaction through the fine-grained entry point, on separate contexts (with SPS the call updates tau,
@@ -106,20 +114,22 @@ def test_golden_reference_parity(fx, variant, tmp_path, built_lib):
             raise
         _check_forces(sim2.ctx, gp, p, tag, report, wide=("mdbc" in fx))
         key = "dt_p" if "dt_p" in gp else "dt"
-        assert abs(sim2.ctx.info().dt_last - float(gp[key])) <= TOL_DT * float(gp[key])
+        edt = abs(sim2.ctx.info().dt_last - float(gp[key])) / float(gp[key])
+        H.parity_report(report["_key"], {"dump": tag, "dt": edt})
+        assert edt <= T.tol(fx, "dt"), (tag, edt)
         sim2.close()
     # whole steps
     for s in range(meta["nsteps"]):
         dt = ctx.compute_step()
         ge = _load(fx, f"s{s:04d}_end")
         if ge is not None:
-            assert abs(dt - float(ge["stepdt"])) <= TOL_DT * float(ge["stepdt"]), (s, dt, float(ge["stepdt"]))
+            assert abs(dt - float(ge["stepdt"])) <= T.tol(fx, "dt") * float(ge["stepdt"]), (s, dt, float(ge["stepdt"]))
             _check_tables(ctx, ge, p.casenpb, f"end of step {s}")
             epos = float(np.max(np.abs(ctx.array("pos") - ge["pos"].reshape(-1, 3))))
             evr = H.rel_err(ctx.array("velrho"), ge["velrho"].reshape(-1, 4))
             report[f"s{s} end"] = {"pos": epos, "velrho": evr}
             H.parity_report(report["_key"], {"dump": f"s{s:04d}_end", "pos_abs_m": epos, "velrho": evr})
-            assert epos < TOL_POS and evr < (1e-5 if "mdbc" in fx else TOL_STATE), (s, epos, evr)
+            assert epos <= T.tol(fx, "pos_abs_m") and evr <= T.tol(fx, "velrho"), (s, epos, evr, T.tol(fx, "pos_abs_m"), T.tol(fx, "velrho"))
             assert abs(ctx.info().timestep - float(ge["timestep"])) <= 1e-6 * float(ge["timestep"])
             if "ft_center" in ge:
                 # floating body state: centre to 1e-8 m, linear/angular velocity to 1e-5 of |v|max (+1e-7 floor)

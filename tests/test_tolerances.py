@@ -1,0 +1,52 @@
+"""CPU checks of the measured parity tolerances (tests/tolerances.py) and of the reference build-to-build noise they rest on."""
+import json
+import os
+import sys
+
+import pytest
+
+import helpers as H
+import tolerances as T
+
+sys.path.insert(0, os.path.join(H.ROOT, "tools"))
+
+
+def test_tolerance_table_is_backed_by_committed_measurements():
+    noise = json.load(open(os.path.join(H.ROOT, "profiles", "ref_noise_r02.json")))
+    gpu = json.load(open(os.path.join(H.ROOT, "profiles", "parity_r02.json")))
+    assert len(noise["records"]) > 50 and len(gpu["records"]) > 100
+    tab = T.table()
+    fixtures = sorted(d for d in os.listdir(H.GOLDEN) if os.path.exists(os.path.join(H.GOLDEN, d, "fixture.json")))
+    for fx in fixtures:
+        assert fx in tab, fx
+        for f in T.FIELDS:
+            t = tab[fx][f]
+            assert T.FLOOR[f] <= t <= T.CAP[f], (fx, f, t)
+            assert t >= min(T._NOISE.get(fx, {}).get(f, 0.0), T.CAP[f])      # never below what the reference reproduces of itself
+    # the headline statement of DESIGN.md: outside the mDBC fixtures ace/ar are asserted at <= 4.5e-4, typically 1-2e-4
+    base = [fx for fx in fixtures if "mdbc" not in fx]
+    assert max(tab[fx]["ace"] for fx in base) <= 2e-4 and max(tab[fx]["ar"] for fx in base) <= 4.5e-4
+    assert max(tab[fx]["dt"] for fx in fixtures) <= 1e-6
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(H.orc.REF_DIR, "dsph_ref_probe_nofm")) or not H.have_ref(),
+                    reason="needs both reference probes (make -C oracle ref refnofm; build container only)")
+def test_reference_fastmath_noise(tmp_path):
+    """Two builds of the unmodified reference on one fixture: they differ, and by about what profiles/ref_noise_r02.json records."""
+    import make_golden
+    import measure_ref_noise as M
+    from dualsphysics_b200 import b2sd, casegen
+    name = "sym_wend_art_ddt2"
+    kw, opts, nsteps, keep = make_golden.specs()[name]
+    casegen.write_case(str(tmp_path), "Case", casegen.DamBreakSpec(**kw))
+    saved = H.orc.REF_PROBE
+    try:
+        H.orc.REF_PROBE = M.NOFM
+        pn = H.orc.run_ref_probe(str(tmp_path / "Case"), str(tmp_path / "outn"), nsteps, options=opts, threads=1)
+    finally:
+        H.orc.REF_PROBE = saved
+    gn = b2sd.load(os.path.join(pn, "s0009_pred.b2sd"))
+    gf = b2sd.load(os.path.join(H.GOLDEN, name, "s0009_pred.b2sd"))
+    e = M.compare(gn, gf, 1.0)
+    rec = T._NOISE[name]
+    assert 1e-6 < e["ace"] <= 1.01 * rec["ace"] and 1e-6 < e["press"] <= 1.01 * rec["press"], (e, rec)

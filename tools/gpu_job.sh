@@ -1,6 +1,6 @@
 #!/bin/bash
 # One parametrised GPU job (replaces the numbered one-shot scripts of round 1).  Usage (inside gpurun):
-#   bash tools/gpu_job.sh TAG [steps...]      steps: tile_parity golden6 memcheck bench6 bench5 ncu6 suite microbench
+#   bash tools/gpu_job.sh TAG [steps...]      steps: see the case labels below (suite, bench5, ncu5, launches, refgpu, parity_report, memcheck ...)
 # Outputs go to gpurun_out/TAG_*.
 TAG=$1; shift
 mkdir -p gpurun_out
@@ -23,7 +23,8 @@ case $step in
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_forces_fluid -s 2 -c 1 -f -o gpurun_out/${TAG}_forces_v${v}_10M python tools/profile_forces.py 10000000 $v 3 > gpurun_out/${TAG}_prof_v$v.log 2>&1; tail -1 gpurun_out/${TAG}_prof_v$v.log;;
   launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_launches.log 2>&1; python tools/summarize_launches.py gpurun_out/${TAG}_launches.csv 2>/dev/null | head -14;;
   parity_report) rm -f gpurun_out/${TAG}_parity.jsonl; B2S_PARITY_REPORT=$PWD/gpurun_out/${TAG}_parity.jsonl timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity_large.py -q -m gpu -k "golden or large" 2>&1 | tail -4 > gpurun_out/${TAG}_parity_tests.log; cat gpurun_out/${TAG}_parity_tests.log; wc -l gpurun_out/${TAG}_parity.jsonl;;
-  suite) python -m pytest tests -q -m gpu -x 2>&1 | tail -4 > gpurun_out/${TAG}_gpu_tests.log; cat gpurun_out/${TAG}_gpu_tests.log;;
+  refgpu) timeout 1500 python tools/ref_gpu_ab.py 10000000 20 > gpurun_out/${TAG}_ref_gpu_ab.json 2> gpurun_out/${TAG}_ref_gpu_ab.err; tail -3 gpurun_out/${TAG}_ref_gpu_ab.err; head -c 3000 gpurun_out/${TAG}_ref_gpu_ab.json; echo;;
+  suite) python -m pytest tests -q -m gpu 2>&1 | tail -40 > gpurun_out/${TAG}_gpu_tests.log; cat gpurun_out/${TAG}_gpu_tests.log;;
   *) echo "unknown step $step";;
 esac
 done
