@@ -23,9 +23,9 @@ def test_tolerance_table_is_backed_by_committed_measurements():
             t = tab[fx][f]
             assert T.FLOOR[f] <= t <= T.CAP[f], (fx, f, t)
             assert t >= min(T._NOISE.get(fx, {}).get(f, 0.0), T.CAP[f])      # never below what the reference reproduces of itself
-    # the headline statement of DESIGN.md: outside the mDBC fixtures ace/ar are asserted at <= 4.5e-4, typically 1-2e-4
+    # the headline statement of DESIGN.md: outside the mDBC fixtures ace is asserted at <= 3e-4 and ar at <= 6e-4, typically 1-2e-4
     base = [fx for fx in fixtures if "mdbc" not in fx]
-    assert max(tab[fx]["ace"] for fx in base) <= 2e-4 and max(tab[fx]["ar"] for fx in base) <= 4.5e-4
+    assert max(tab[fx]["ace"] for fx in base) <= 3e-4 and max(tab[fx]["ar"] for fx in base) <= 6e-4
     assert max(tab[fx]["dt"] for fx in fixtures) <= 1e-6
 
 

@@ -53,6 +53,8 @@ def tol(fx: str, field: str) -> float:
         v = _one(fx, field)
     else:
         v = max([_one(k, field) for k in set(_GPU) | set(_NOISE) if _cls(k) == _cls(fx)] or [CAP[field]])
+    if field == "acemax":       # the maximum of |ace| over the particles cannot be asked to agree better than ace itself
+        v = max(v, tol(fx, "ace"))
     return min(max(v, FLOOR[field]), CAP[field])
 
 
