@@ -242,8 +242,7 @@ def main():
         if ss is None:
             ctx.run_steps(n)
         else:
-            for _ in range(n):
-                ss.step()
+            ss.run_steps(n)       # the whole slab step runs inside the library (csrc/slab_comm.cu), one host sync per step
 
     def barrier():
         if dist is not None:
@@ -263,6 +262,7 @@ def main():
     ctx.launch_count(reset=True)
     if ss is not None:
         ss.exchanged_bytes = 0
+        ss.comm_stats(reset=True)
     barrier()
     t0 = time.perf_counter()
     ev0.record(kstream)
@@ -273,10 +273,19 @@ def main():
     secs = ev0.elapsed_time(ev1) * 1e-3
     launches = ctx.launch_count()
     xbytes = ss.exchanged_bytes if ss is not None else 0
+    comm = None
+    if ss is not None and ss.native:
+        ms_x, nx, bytes_x, nrecut, _ = ss.comm_stats()
+        xbytes = bytes_x
+        comm = [ms_x / a.steps, nx / a.steps, float(nrecut)]
     if dist is not None:
         t = torch.tensor([secs, wall], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         secs, wall = float(t[0].item()), float(t[1].item())
+        if comm is not None:
+            tc = torch.tensor(comm, device="cuda", dtype=torch.float64)
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            comm = [float(v) for v in tc.tolist()]
         cnt = torch.tensor([float(np_total), float(launches), float(xbytes)], device="cuda", dtype=torch.float64)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         np_all, launches_all, xbytes_all = int(cnt[0].item()), int(cnt[1].item()), int(cnt[2].item())
@@ -444,7 +453,9 @@ def main():
                 "config": {"workload": f"synthetic 3D dam-break block (BASELINE configs[1]), {OPTIONS}, lattice start + {PREROLL} untimed steps"
                                        + ("" if world == 1 else f", block {world}x longer along x"),
                            "np_per_gpu": np_per_rank, "np_total": np_all, "fluid_rank0": npf, "interaction_variant": a.variant,
-                           "parallelism": "single GPU" if world == 1 else f"{world} slabs along x, one rank per GPU; per interaction: migrants+halos over NCCL send/recv, dt by all-reduce(MAX)",
+                           "parallelism": "single GPU" if world == 1 else f"{world} slabs along x (cuts balance work: fluid particle = 3 boundary particles), one rank per GPU; per interaction: migrants+halos in one fixed-size message per neighbour over ncclSend/ncclRecv issued by the library (counts stay on the device), dt maxima by ncclAllReduce(MAX); one host sync per step",
+                           "comm": (None if comm is None else {"t_exposed_comm_ms_per_step": comm[0], "exchanges_per_step": comm[1], "recuts": comm[2],
+                                                              "note": "max over ranks of the CUDA-event time inside pack + ncclSend/ncclRecv + unpack on the kernel stream; the exchange is serial with the kernels (not overlapped), so this whole time is exposed; it includes waiting for a slower neighbour"}),
                            "exchanged_bytes_per_step": xbytes_all // max(a.steps, 1),
                            "l2_note": "inputs larger than L2: working set ~2.3 GB per GPU >> 126 MB L2",
                            "timing": "CUDA events on the kernel stream, max over ranks", "wall_ms_per_step": wall / a.steps * 1e3},

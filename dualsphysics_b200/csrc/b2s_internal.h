@@ -118,6 +118,7 @@ struct b2s_ctx {
   cudaStream_t stream;
   uint32_t cap;                 // particle capacity
   uint32_t np_host, npb_host, npbok_host;   // host mirrors (upper bounds for launches)
+  uint32_t npf_host;                        // upper bound of np-npb (a slab unpack raises np and npb by the same bound, so their difference is none)
   uint32_t nct_max, nctt_max;   // table capacity
   std::string err;
   uint64_t launches;
@@ -156,6 +157,7 @@ struct b2s_ctx {
   void* ft_dev; // device copy of per-floating update data
   std::vector<Motion> motions; void* motion_dev; bool motion_dirty;
   // slab decomposition (slab.cu)
+  void* slab_comm;              // slab_comm.cu: transport + exchange buffers (NULL until b2s_slab_comm_init*)
   bool slab_on; int slab_rank, slab_nranks; uint32_t slab_cxa, slab_cxb; uint32_t* slab_counts; uint8_t* slab_flags; size_t slab_counts_len;
   uint32_t* tile_bricks; uint32_t* tile_counters; int tile_nsm; uint32_t tile_cap;   // forces_tile.cu: list of non-empty bricks, its counters, SM count, tile capacity override (0 = default)
   // gauges (gauges.cu): device list + results of the last evaluation (device and pinned host)

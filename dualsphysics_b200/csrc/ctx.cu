@@ -73,7 +73,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   if(cudaSetDevice(device)!=cudaSuccess){ delete ctx; return B2S_ERR_NODEVICE; }
   make_devcte(ctx->prm,ctx->cte);
   ctx->cap=std::max<uint32_t>(capacity_np,1024u);
-  ctx->np_host=ctx->npb_host=ctx->npbok_host=0;
+  ctx->np_host=ctx->npb_host=ctx->npbok_host=ctx->npf_host=0; ctx->slab_comm=NULL;
   ctx->launches=0; ctx->variant=5; ctx->pre_active=false; ctx->bound_changed=true; ctx->ftcount=0;
   ctx->verletstep=0;
   ctx->slab_on=false; ctx->slab_rank=0; ctx->slab_nranks=1; ctx->slab_cxa=0; ctx->slab_cxb=0; ctx->slab_counts=NULL; ctx->slab_flags=NULL; ctx->slab_counts_len=0;
@@ -127,6 +127,7 @@ extern "C" int b2s_destroy(b2s_ctx* ctx){
   if(!ctx)return B2S_OK;
   cudaSetDevice(ctx->device);
   if(ctx->stream)cudaStreamSynchronize(ctx->stream);
+  b2s_slab_comm_free(ctx);
   free_partset(ctx->cur); free_partset(ctx->alt);
   cudaFree(ctx->pospre_xy); cudaFree(ctx->pospre_z); cudaFree(ctx->velrhopre);
   cudaFree(ctx->pospre_xy_alt); cudaFree(ctx->pospre_z_alt); cudaFree(ctx->velrhopre_alt);
@@ -162,7 +163,7 @@ int b2s_sync_info(b2s_ctx* ctx){
   B2S_CUDA(ctx,cudaMemcpyAsync(ctx->div_h,ctx->div,sizeof(DivState),cudaMemcpyDeviceToHost,ctx->stream));
   B2S_CUDA(ctx,cudaMemcpyAsync(ctx->step_h,ctx->step,sizeof(StepState),cudaMemcpyDeviceToHost,ctx->stream));
   B2S_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
-  ctx->np_host=ctx->div_h->np; ctx->npb_host=ctx->div_h->npb; ctx->npbok_host=ctx->div_h->npbok;
+  ctx->np_host=ctx->div_h->np; ctx->npb_host=ctx->div_h->npb; ctx->npbok_host=ctx->div_h->npbok; ctx->npf_host=ctx->np_host-ctx->npb_host;
   if(ctx->div_h->error==2u)return b2s_fail(ctx,B2S_ERR_NOMEM,"particle capacity %u exceeded by the periodic duplicates",ctx->cap);
   if(ctx->div_h->error)return b2s_fail(ctx,B2S_ERR_BOUNDOUT,"boundary particles were excluded from the domain (%u)",ctx->div_h->npb_out);
   if(ctx->step_h->error)return b2s_fail(ctx,ctx->step_h->error,"%s (acemax=%g velmax=%g viscdtmax=%g nstep=%u)",b2s_error_string(ctx->step_h->error),ctx->step_h->acemax,ctx->step_h->velmax,(double)ctx->step_h->viscdtmax,ctx->step_h->nstep);
@@ -252,7 +253,7 @@ extern "C" int b2s_upload_particles(b2s_ctx* ctx, uint32_t np, const uint32_t* i
   k_init_state<<<1,1,0,s>>>(ctx->div,ctx->step,np,npb,q.dtini); B2S_LAUNCHED(ctx);
   B2S_CUDA(ctx,cudaStreamSynchronize(s));
   if(herr)return b2s_fail(ctx,B2S_ERR_ARG,"found initial particles outside the domain (JSph::LoadDcellParticles)");
-  ctx->np_host=np; ctx->npb_host=npb; ctx->npbok_host=npb;
+  ctx->np_host=np; ctx->npb_host=npb; ctx->npbok_host=npb; ctx->npf_host=np-npb;
   ctx->pre_active=false; ctx->bound_changed=true; ctx->verletstep=0;
   if(ctx->velrhom1)B2S_CUDA(ctx,cudaMemcpyAsync(ctx->velrhom1,ctx->cur.velrho,size_t(np)*16,cudaMemcpyDeviceToDevice,s));  // InitRunGpu: VelrhoM1=Velrho
   if(ctx->motionace)B2S_CUDA(ctx,cudaMemsetAsync(ctx->motionace,0,size_t(ctx->cap)*16,s));
@@ -565,12 +566,18 @@ extern "C" int b2s_slab_integrate(b2s_ctx* ctx, int mode){
   else if(mode==0)b2s_set_dt_device(ctx,1);   // Verlet: dt=DtVariable(true)
   return b2s_integrate_impl(ctx,mode,0,true);
 }
-extern "C" int b2s_slab_step_end(b2s_ctx* ctx, double* dt_out){
-  if(!ctx)return B2S_ERR_ARG;
-  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+// tail of the step without the synchronisation (slab_comm.cu synchronises once, after the last exchange of the step)
+int b2s_slab_step_end_enqueue(b2s_ctx* ctx){
   { int r=b2s_damping_impl(ctx); if(r)return r; }
   if(!ctx->motions.empty()){ int r=b2s_motion_impl(ctx,0,0); if(r)return r; }
   k_step_end<<<1,1,0,ctx->stream>>>(ctx->step,ctx->prm.tstep==B2S_STEP_SYMPLECTIC? 1: 0); B2S_LAUNCHED(ctx);
+  B2S_CUDA(ctx,cudaGetLastError());
+  return B2S_OK;
+}
+extern "C" int b2s_slab_step_end(b2s_ctx* ctx, double* dt_out){
+  if(!ctx)return B2S_ERR_ARG;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  { int r=b2s_slab_step_end_enqueue(ctx); if(r)return r; }
   int r=b2s_sync_info(ctx);
   if(dt_out)*dt_out=ctx->step_h->dt;
   return r;

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) k_damping(const DampOp* __restrict__ ops,
 
 int b2s_damping_impl(b2s_ctx* ctx){
   if(ctx->damp_host.empty())return B2S_OK;
-  const uint32_t npf=(ctx->np_host>ctx->npb_host? ctx->np_host-ctx->npb_host: 0u);
+  const uint32_t npf=ctx->npf_host;
   if(!npf)return B2S_OK;
   const int nops=int(ctx->damp_host.size()/sizeof(DampOp));
   if(ctx->damp_dirty){

@@ -142,7 +142,7 @@ int b2s_forces_fluid_only(b2s_ctx* ctx){
   ForcesArgs g;
   g.ds=ctx->div; g.st=ctx->step; g.beg=(const uint32_t*)ctx->begincell; g.dcell=ctx->cur.dcell; g.code=ctx->cur.code;
   g.posp=ctx->posp; g.posh=ctx->posh; g.boundmode=ctx->boundmode; g.tangenvel=ctx->tangenvel; g.nearbound=(ctx->nearbound_valid? ctx->nearbound: NULL); g.velrho=ctx->cur.velrho; g.tau=ctx->spstau; g.tau_new=ctx->spstau_new; g.ftomassp=ctx->ft_massp_dev; g.acear=ctx->acear;
-  const uint32_t npf=(ctx->np_host>ctx->npb_host? ctx->np_host-ctx->npb_host: 0u);
+  const uint32_t npf=ctx->npf_host;
   if(!npf)return B2S_OK;
   if(ctx->variant==6 && b2s_forces_tile_supported(ctx->cte))return b2s_forces_tile_launch(ctx,g);
   if((ctx->variant==5 || ctx->variant==6) && b2s_forces_pair2_supported(ctx->cte))return b2s_forces_pair2_launch(ctx,g);

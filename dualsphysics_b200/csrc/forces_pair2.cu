@@ -244,7 +244,7 @@ template<int TKER> static pair2_kernel_t p2_pick_visco(int tv,int td,bool ft,boo
 
 int b2s_forces_pair2_launch(b2s_ctx* ctx, const ForcesArgs& g){
   const DevCte& c=ctx->cte;
-  const uint32_t npf=ctx->np_host-ctx->npb_host;
+  const uint32_t npf=ctx->npf_host;
   const unsigned gb=b2s_blocks(npf,P2_BS);
   const PackCte k=pack_cte(c);
   const bool ft=(c.use_floating!=0), m2=(c.mdbc2 && g.boundmode!=nullptr);

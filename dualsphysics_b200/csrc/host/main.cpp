@@ -8,6 +8,9 @@
 #include <ctime>
 #include <string>
 #include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
 
 static FILE* g_runout=NULL;
 static void say(const char* fmt,...){
@@ -26,8 +29,43 @@ int main(int argc,char** argv){
   std::string opts;
   for(int c=3;c<argc;c++){ opts+=argv[c]; opts+=' '; }
   b2s_sim* sim=NULL;
-  int r=b2s_sim_load(argv[1],argv[2],opts.c_str(),-1,0,&sim);
+  // Several GPUs: one process per GPU, started by any launcher that sets RANK / WORLD_SIZE / LOCAL_RANK (torchrun, mpirun wrappers,
+  // a shell loop).  Rank 0 makes the NCCL id and leaves it in a file every rank can read (one node); each rank then loads its slab
+  // of the case, connects (csrc/slab_comm.cu) and b2s_sim_run steps collectively, writing its piece of every PART.
+  const char* ews=getenv("WORLD_SIZE"); const int world=(ews? atoi(ews): 1);
+  const int rank=(getenv("RANK")? atoi(getenv("RANK")): 0), local=(getenv("LOCAL_RANK")? atoi(getenv("LOCAL_RANK")): rank);
+  int r;
+  if(world>1){
+    std::string idfile=(getenv("B2S_NCCL_ID_FILE")? getenv("B2S_NCCL_ID_FILE"): std::string("/tmp/b2s_nccl_")+(getenv("MASTER_PORT")? getenv("MASTER_PORT"): "0")+".id");
+    uint8_t id[128];
+    if(rank==0){
+      if(b2s_slab_comm_id(id)){ fprintf(stderr,"*** NCCL is not available\n"); return 1; }
+      FILE* f=fopen((idfile+".tmp").c_str(),"wb"); if(!f || fwrite(id,1,128,f)!=128){ fprintf(stderr,"*** cannot write %s\n",idfile.c_str()); return 1; }
+      fclose(f); rename((idfile+".tmp").c_str(),idfile.c_str());
+    }
+    else{
+      bool got=false;
+      for(int k=0;k<6000 && !got;k++){   // up to 10 minutes: rank 0 may still be reading a large case
+        FILE* f=fopen(idfile.c_str(),"rb");
+        if(f){ got=(fread(id,1,128,f)==128); fclose(f); }
+        if(!got)std::this_thread::sleep_for(std::chrono::milliseconds(100));
+      }
+      if(!got){ fprintf(stderr,"*** rank %d: no NCCL id in %s\n",rank,idfile.c_str()); return 1; }
+    }
+    r=b2s_sim_load_slab(argv[1],opts.c_str(),local,rank,world,&sim);
+    if(!r)r=b2s_sim_set_dirout(sim,argv[2]);
+    if(!r)r=b2s_sim_slab_connect(sim,id);
+    if(rank==0)remove(idfile.c_str());   // every rank is connected once rank 0's collective init returns
+  }
+  else r=b2s_sim_load(argv[1],argv[2],opts.c_str(),-1,0,&sim);
   if(r){ fprintf(stderr,"*** load failed (%d): %s\n",r,b2s_host_last_error()); return 1; }
+  if(rank!=0){   // the other ranks run silently; rank 0 reports
+    double t=0; uint32_t steps=0;
+    r=b2s_sim_run(sim,0,&t,&steps);
+    if(r)fprintf(stderr,"*** rank %d: run failed (%d): %s\n",rank,r,b2s_host_last_error());
+    b2s_sim_free(sim);
+    return r? 1: 0;
+  }
   std::string dirout=argv[2];
   if(!dirout.empty() && dirout.back()!='/')dirout+='/';
   if(!dirout.empty())g_runout=fopen((dirout+"Run.out").c_str(),"w");   // the directory exists: b2s_sim_load created it
@@ -73,8 +111,8 @@ int main(int argc,char** argv){
       fprintf(f,"#RunName;Rcode-VersionInfo;DateTime;Np;TSimul;TSeg;TTotal;MemCpu;MemGpu;MemGpuCells;Steps;GPIPS;PhysicalTime;PartFiles;PartsOut;"
                 "MaxParticles;MaxCells;Hardware;RunMode;Configuration;Nbound;Nfixed;Dp;H;PartsOutRho;PartsOutVel\n");
       std::string name=argv[1]; { const size_t k=name.find_last_of('/'); if(k!=std::string::npos)name=name.substr(k+1); }
-      fprintf(f,"%s;b200sph v0.1;%s;%u;%g;%g;%g;;;;%u;;%.15g;%u;%u;%u;%u;B200;SingleGPU;%s;%u;%u;%g;%g;%u;%u\n",name.c_str(),date,p.casenp,
-        secs,t>0? secs/t: 0.0,ttot,steps,t,parts,nout[0],inf.np,inf.nct,opts.c_str(),p.casenp-p.casenfluid,p.casenfixed,(double)p.dp,(double)p.kernelh,nout[2],nout[3]);
+      fprintf(f,"%s;b200sph v0.1;%s;%u;%g;%g;%g;;;;%u;;%.15g;%u;%u;%u;%u;B200;%s;%s;%u;%u;%g;%g;%u;%u\n",name.c_str(),date,p.casenp,
+        secs,t>0? secs/t: 0.0,ttot,steps,t,parts,nout[0],inf.np,inf.nct,world>1? "MultiGPU-slabs": "SingleGPU",opts.c_str(),p.casenp-p.casenfluid,p.casenfixed,(double)p.dp,(double)p.kernelh,nout[2],nout[3]);
       fclose(f);
     }
   }

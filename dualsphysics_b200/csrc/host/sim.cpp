@@ -14,6 +14,7 @@
 #include "xml_lite.h"
 #include "bi4.h"
 #include "motionref.h"
+#include "../slab_cuts.h"
 #include <cmath>
 #include <cfloat>
 #include <cstring>
@@ -487,25 +488,6 @@ static void load_case(b2s_sim* s,const std::string& options){
   }
 }
 
-// Balanced cut planes along x: prefix sum of the particles per x cell plane, every cut at the plane whose cumulative count
-// is nearest to r*Np/G (the same rule as dualsphysics_b200/slab.py compute_cuts; tests compare both).
-static std::vector<uint32_t> slab_compute_cuts(const std::vector<uint64_t>& hist,int nranks,uint32_t minw){
-  const uint32_t ncx=uint32_t(hist.size());
-  std::vector<uint64_t> cum(ncx); uint64_t t=0; for(uint32_t i=0;i<ncx;i++){ t+=hist[i]; cum[i]=t; }
-  std::vector<uint32_t> cuts; cuts.push_back(0);
-  for(int r=1;r<nranks;r++){
-    const double target=double(t)*r/nranks;
-    uint32_t i=0; while(i<ncx && double(cum[i])<target)i++;      // searchsorted(cum,target,'left')
-    uint32_t c=i+1;
-    if(c>=2 && c-1<ncx && fabs(double(cum[c-2])-target)<fabs(double(cum[c-1])-target))c--;
-    if(c<cuts.back()+minw)c=cuts.back()+minw;                          // a slab is at least as wide as the halo (scelldiv planes)
-    if(c>ncx-uint32_t(nranks-r)*minw)c=ncx-uint32_t(nranks-r)*minw;
-    cuts.push_back(c);
-  }
-  cuts.push_back(ncx);
-  return cuts;
-}
-
 static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capacity,int slab_rank=0,int slab_nranks=0){
   b2s_params& p=s->prm;
   std::unique_ptr<Bi4Item> data=bi4_load(s->casepath+".bi4");
@@ -634,9 +616,13 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
     if(uint32_t(slab_nranks)*halow>ncx)throw std::runtime_error("more slabs than the cell planes along x allow (a slab is at least as wide as the halo)");
     const double sc=double(p.scell);
     std::vector<uint32_t> cx(np);
-    std::vector<uint64_t> hist(ncx,0);
-    for(unsigned i=0;i<np;i++){ const double d=(pos[size_t(i)*3]-p.domposmin[0])/sc; uint32_t c=(d<0? 0u: uint32_t(d)); if(c>=ncx)c=ncx-1; cx[i]=c; hist[c]++; }
-    s->slab_cuts=slab_compute_cuts(hist,slab_nranks,halow);
+    // cuts balance the WORK (fluid particles weigh more than boundary particles, slab_cuts.h), capacities follow the counts
+    std::vector<uint64_t> hist(ncx,0), work(ncx,0);
+    for(unsigned i=0;i<np;i++){
+      const double d=(pos[size_t(i)*3]-p.domposmin[0])/sc; uint32_t c=(d<0? 0u: uint32_t(d)); if(c>=ncx)c=ncx-1; cx[i]=c; hist[c]++;
+      work[c]+=(idp[i]>=p.casenbound? B2S_SLAB_WEIGHT_FLUID: B2S_SLAB_WEIGHT_BOUND);
+    }
+    s->slab_cuts=b2s_slab_compute_cuts(work,slab_nranks,halow);
     s->slab_maxplane=uint32_t(*std::max_element(hist.begin(),hist.end()));
     const uint32_t ca=s->slab_cuts[slab_rank], cb=s->slab_cuts[slab_rank+1];
     unsigned w=0;
@@ -1049,6 +1035,14 @@ extern "C" int b2s_sim_set_dirout(b2s_sim* s,const char* dirout){
   catch(const std::exception& e){ g_host_err=e.what(); return B2S_ERR_IO; }
   return B2S_OK;
 }
+// Transport of a slab rank (csrc/slab_comm.cu): NCCL communicator from the id rank 0 made, then the first halo exchange.
+extern "C" int b2s_sim_slab_connect(b2s_sim* s,const uint8_t* nccl_id128){
+  if(!s||!nccl_id128||s->slab_cuts.empty())return B2S_ERR_ARG;
+  int r=b2s_slab_comm_init(s->ctx,nccl_id128,s->slab_maxplane);
+  if(!r)r=b2s_slab_exchange(s->ctx);
+  if(r)g_host_err=b2s_last_error(s->ctx);
+  return r;
+}
 extern "C" int b2s_sim_slab_info(b2s_sim* s,uint32_t* cuts,uint32_t ncuts,uint32_t* max_plane_particles){
   if(!s||s->slab_cuts.empty())return B2S_ERR_STATE;
   if(cuts){ if(ncuts!=s->slab_cuts.size())return B2S_ERR_ARG; for(uint32_t i=0;i<ncuts;i++)cuts[i]=s->slab_cuts[i]; }
@@ -1115,7 +1109,7 @@ extern "C" int b2s_sim_run(b2s_sim* s,uint32_t nsteps_break,double* time_out,uin
     double t=inf.timestep;
     while(t<s->timemax){
       double dt=0;
-      r=b2s_compute_step(s->ctx,&dt);
+      r=(s->npiece>1? b2s_slab_step(s->ctx,&dt): b2s_compute_step(s->ctx,&dt));   // slab rank: collective step over NCCL (b2s_sim_slab_connect)
       if(r){ g_host_err=b2s_last_error(s->ctx); return r; }
       r=b2s_get_info(s->ctx,&inf); if(r){ g_host_err=b2s_last_error(s->ctx); return r; }
       t=inf.timestep; nstep++;
@@ -1126,7 +1120,7 @@ extern "C" int b2s_sim_run(b2s_sim* s,uint32_t nsteps_break,double* time_out,uin
         if(s->svallsteps)s->timepartnext=t;
         else{ unsigned ct=unsigned(t/s->timepart); double tn=s->timepart*ct; for(;tn<=t;ct++)tn=s->timepart*ct; s->timepartnext=tn; }  // JDsOutputTime::GetNextTime
       }
-      if(inf.np<=inf.npb){ g_host_err="no fluid particles left"; break; }
+      if(s->npiece<=1 && inf.np<=inf.npb){ g_host_err="no fluid particles left"; break; }
       if(nbreak && nstep>=nbreak)break;
     }
     if(time_out)*time_out=t;

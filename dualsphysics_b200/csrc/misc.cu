@@ -216,7 +216,7 @@ __global__ void k_reset_pairs(StepState* st){ st->pairs_checked=0; st->pairs_rea
 extern "C" int b2s_count_pairs(b2s_ctx* ctx, uint64_t* checked, uint64_t* real){
   if(!ctx)return B2S_ERR_ARG;
   B2S_CUDA(ctx,cudaSetDevice(ctx->device));
-  const uint32_t npf=(ctx->np_host>ctx->npb_host? ctx->np_host-ctx->npb_host: 0u);
+  const uint32_t npf=ctx->npf_host;
   k_reset_pairs<<<1,1,0,ctx->stream>>>(ctx->step); B2S_LAUNCHED(ctx);
   if(npf){ k_count_pairs<<<b2s_blocks(npf,128),128,0,ctx->stream>>>(ctx->div,ctx->step,(const uint32_t*)ctx->begincell,ctx->cur.dcell,ctx->posp,ctx->cte); B2S_LAUNCHED(ctx); }
   int r=b2s_sync_info(ctx); if(r)return r;

@@ -161,7 +161,7 @@ int b2s_periodic_impl(b2s_ctx* ctx){
       nper[ctype]+=cnt; np+=cnt;
     }
   }
-  ctx->np_host=np; ctx->npb_host=npb0+nper[0];
+  ctx->np_host=np; ctx->npb_host=npb0+nper[0]; ctx->npf_host=ctx->np_host-ctx->npb_host;
   ctx->bound_changed=true;
   B2S_CUDA(ctx,cudaGetLastError());
   return B2S_OK;

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(F_BS) k_shifting(ShiftArgs g, const __grid_con
 // Displacement of the coming position update; StepState.dt must already hold the dt of the sub-step.
 int b2s_shifting_impl(b2s_ctx* ctx){
   if(!ctx->prm.shiftmode)return B2S_OK;
-  const uint32_t npf=(ctx->np_host>ctx->npb_host? ctx->np_host-ctx->npb_host: 0u);
+  const uint32_t npf=ctx->npf_host;
   if(!npf)return B2S_OK;
   ShiftArgs g;
   g.ds=ctx->div; g.st=ctx->step; g.beg=(const uint32_t*)ctx->begincell; g.dcell=ctx->cur.dcell; g.code=ctx->cur.code;

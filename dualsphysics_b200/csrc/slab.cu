@@ -13,8 +13,10 @@
 //   migrants append: [f32 velrhopre[4] f64 pospre[3] pad8] (Symplectic, predictor active) | [f32 velrhom1[4]] (Verlet)
 //   both append:     [f32 boundnor[4]] (mDBC) | [f32 tau[6] pad8] (Laminar+SPS); records are multiples of 16 B
 #include "b2s_internal.h"
+#include "slab_cuts.h"
 
 #define S_BS 256
+#define B2S_SLAB_HDR 16        // bytes in front of the records of a device-counted message (k_slab_header)
 
 // Halo width in cell planes: one kernel radius (scelldiv planes).  With mDBC the boundary ghosts must carry the density the
 // owner extrapolates at their ghost node; instead of a second exchange after the mDBC pass every rank recomputes it locally,
@@ -101,13 +103,70 @@ __global__ void __launch_bounds__(S_BS) k_slab_scatter(const DivState* __restric
   if(kind==1 && f)a.code[p]=typecode(B2S_CODE_SETNORMAL(a.code[p])|migcode);
 }
 
+// ---- the same exchange without the host: counts stay on the device (slab_comm.cu) -------------------------------------------
+// Message of one side: [u32 nmigrants | u32 nhalo | 8 B pad][migrant records][halo records], sent with a fixed size (the
+// capacities), so neither side needs the other's counts on the host.  tot_l / tot_r: device totals of the flag scan.
+__global__ void __launch_bounds__(S_BS) k_slab_scatter_dev(const DivState* __restrict__ ds, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ offs,
+  uint32_t nblocks, SlabLayout l, SlabArrays a, int kind, char* left, char* right, uint32_t cap,
+  const uint32_t* __restrict__ migtot_l, const uint32_t* __restrict__ migtot_r, uint32_t migcap, uint32_t migbytes, typecode migcode)
+{
+  __shared__ uint32_t wl[S_BS/32], wr[S_BS/32];
+  const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
+  const int lane=threadIdx.x&31, w=threadIdx.x>>5;
+  const uint8_t f=(p<ds->np? flags[p]: uint8_t(0));
+  const uint32_t bl=__ballot_sync(0xffffffffu,f&1), br=__ballot_sync(0xffffffffu,f&2);
+  if(lane==0){ wl[w]=__popc(bl); wr[w]=__popc(br); }
+  __syncthreads();
+  uint32_t pl=0, pr=0;
+  for(int k=0;k<w;k++){ pl+=wl[k]; pr+=wr[k]; }
+  const uint32_t lm=(1u<<lane)-1u;
+  // halo records start behind the migrant records of the same message
+  const size_t basel=B2S_SLAB_HDR+(migtot_l? size_t(min(*migtot_l,migcap))*migbytes: 0), baser=B2S_SLAB_HDR+(migtot_r? size_t(min(*migtot_r,migcap))*migbytes: 0);
+  bool sent=false;
+  if(f&1){ const uint32_t i=offs[blockIdx.x]+pl+__popc(bl&lm); if(i<cap){ slab_write(left+basel+size_t(i)*l.bytes,l,a,p); sent=true; } }
+  if(f&2){ const uint32_t i=offs[nblocks+1+blockIdx.x]+pr+__popc(br&lm); if(i<cap){ slab_write(right+baser+size_t(i)*l.bytes,l,a,p); sent=true; } }
+  if(kind==1 && sent)a.code[p]=typecode(B2S_CODE_SETNORMAL(a.code[p])|migcode);   // a migrant that did not fit stays (the error flag is raised by k_slab_header)
+}
+__global__ void k_slab_header(StepState* st, const uint32_t* __restrict__ cM, const uint32_t* __restrict__ cH, uint32_t nb, uint32_t migcap, uint32_t halocap,
+  char* left, char* right, uint32_t* sent_total)
+{
+  if(threadIdx.x||blockIdx.x)return;
+  const uint32_t ml=(cM? cM[nb]: 0u), mr=(cM? cM[2*nb+1]: 0u), hl=(cH? cH[nb]: 0u), hr=(cH? cH[2*nb+1]: 0u);
+  if(ml>migcap || mr>migcap || hl>halocap || hr>halocap)st->error=B2S_ERR_NOMEM;
+  if(left){ uint32_t* h=reinterpret_cast<uint32_t*>(left); h[0]=min(ml,migcap); h[1]=min(hl,halocap); h[2]=0; h[3]=0; }
+  if(right){ uint32_t* h=reinterpret_cast<uint32_t*>(right); h[0]=min(mr,migcap); h[1]=min(hr,halocap); h[2]=0; h[3]=0; }
+  if(sent_total){ sent_total[0]=ml+mr; sent_total[1]=hl+hr; sent_total[2]+=ml+mr; }   // [2]: migrants since b2s_slab_comm_init
+}
+
+__device__ __forceinline__ void slab_unpack_record(DivState* ds, uint32_t p, const char* rec, const SlabLayout& l, const SlabArrays& a, int kind, const DevCte& c);
+
+__global__ void __launch_bounds__(S_BS) k_slab_unpack_msg(DivState* ds, StepState* st, const char* __restrict__ msg, SlabLayout lM, SlabLayout lH, SlabArrays a,
+  uint32_t cap, const __grid_constant__ DevCte c)
+{
+  const uint32_t* h=reinterpret_cast<const uint32_t*>(msg);
+  const uint32_t nm=h[0], nh=h[1];
+  const uint32_t i=blockIdx.x*blockDim.x+threadIdx.x;
+  if(i>=nm+nh)return;
+  if(uint64_t(ds->np)+nm+nh>cap){ if(i==0)st->error=B2S_ERR_NOMEM; return; }
+  const bool mig=(i<nm);
+  const char* rec=msg+B2S_SLAB_HDR+(mig? size_t(i)*lM.bytes: size_t(nm)*lM.bytes+size_t(i-nm)*lH.bytes);
+  slab_unpack_record(ds,ds->np+i,rec,mig? lM: lH,a,mig? 1: 0,c);
+}
+__global__ void k_slab_unpack_msg_commit(DivState* ds, const char* __restrict__ msg, uint32_t cap){
+  const uint32_t* h=reinterpret_cast<const uint32_t*>(msg);
+  if(uint64_t(ds->np)+h[0]+h[1]<=cap){ ds->np+=h[0]+h[1]; ds->npb+=ds->slab_nbound_tmp; }
+  ds->slab_nbound_tmp=0;
+}
+
 __global__ void __launch_bounds__(S_BS) k_slab_unpack(DivState* ds, const char* __restrict__ buf, uint32_t n, SlabLayout l, SlabArrays a, int kind,
   const __grid_constant__ DevCte c)
 {
   const uint32_t i=blockIdx.x*blockDim.x+threadIdx.x;
   if(i>=n)return;
-  const uint32_t p=ds->np+i;
-  const char* rec=buf+size_t(i)*l.bytes;
+  slab_unpack_record(ds,ds->np+i,buf+size_t(i)*l.bytes,l,a,kind,c);
+}
+__device__ __forceinline__ void slab_unpack_record(DivState* ds, uint32_t p, const char* rec, const SlabLayout& l, const SlabArrays& a, int kind, const DevCte& c)
+{
   const uint32_t id=*reinterpret_cast<const uint32_t*>(rec);
   typecode cod=typecode(*reinterpret_cast<const uint32_t*>(rec+4));
   if(kind==0)cod=typecode(B2S_CODE_SETNORMAL(cod)|B2S_CODE_PERIODIC);   // halo ghost
@@ -178,7 +237,11 @@ __global__ void __launch_bounds__(S_BS) k_slab_hist(const DivState* __restrict__
   const uint32_t cx=B2S_DCEL_CELLX(dcc,rc);
   // particles of a warp mostly share a few planes: aggregate equal planes before the atomic
   const uint32_t peers=__match_any_sync(__activemask(),cx);
-  if((__ffs(peers)-1)==int(threadIdx.x&31) && cx<ncx)atomicAdd(&hist[cx],uint32_t(__popc(peers)));
+  // work units, not heads: a fluid particle weighs B2S_SLAB_WEIGHT_FLUID boundary particles (slab_cuts.h)
+  const uint32_t w=(B2S_CODE_TYPE(code[p])<B2S_CODE_TYPE_FLOATING? B2S_SLAB_WEIGHT_BOUND: B2S_SLAB_WEIGHT_FLUID);
+  uint32_t sum=0;
+  for(uint32_t m=peers;m;m&=m-1)sum+=__shfl_sync(peers,w,__ffs(m)-1);
+  if((__ffs(peers)-1)==int(threadIdx.x&31) && cx<ncx)atomicAdd(&hist[cx],sum);
 }
 extern "C" int b2s_slab_histogram(b2s_ctx* ctx, void* dev_u32_ncx){
   if(!ctx || !ctx->slab_on || !dev_u32_ncx)return B2S_ERR_ARG;
@@ -207,6 +270,12 @@ extern "C" int b2s_slab_set_range(b2s_ctx* ctx, uint32_t cx_begin, uint32_t cx_e
   if(!ctx || !ctx->slab_on || cx_begin>=cx_end || cx_end>ctx->prm.domcells[0])return B2S_ERR_ARG;
   if(ctx->slab_nranks>1 && cx_end-cx_begin<slab_halo_planes(ctx))return b2s_fail(ctx,B2S_ERR_ARG,"slab [%u,%u) is thinner than the halo (%u cell planes)",cx_begin,cx_end,slab_halo_planes(ctx));
   ctx->slab_cxa=cx_begin; ctx->slab_cxb=cx_end;
+  return B2S_OK;
+}
+
+extern "C" int b2s_slab_get_range(b2s_ctx* ctx, uint32_t* range2){
+  if(!ctx || !ctx->slab_on || !range2)return B2S_ERR_ARG;
+  range2[0]=ctx->slab_cxa; range2[1]=ctx->slab_cxb;
   return B2S_OK;
 }
 
@@ -298,7 +367,7 @@ extern "C" int b2s_slab_unpack(b2s_ctx* ctx, int kind, const void* dev_buf, uint
   const SlabLayout l=slab_layout(ctx,kind);
   k_slab_unpack<<<b2s_blocks(count,S_BS),S_BS,0,ctx->stream>>>(ctx->div,(const char*)dev_buf,count,l,slab_arrays(ctx),kind,ctx->cte); B2S_LAUNCHED(ctx);
   k_slab_unpack_commit<<<1,1,0,ctx->stream>>>(ctx->div,count); B2S_LAUNCHED(ctx);
-  ctx->np_host+=count; ctx->npb_host+=count;   // host mirrors are upper bounds until the next sync
+  ctx->np_host+=count; ctx->npb_host+=count; ctx->npf_host+=count;   // host mirrors are upper bounds until the next sync
   ctx->bound_changed=true;
   B2S_CUDA(ctx,cudaGetLastError());
   return B2S_OK;
@@ -307,5 +376,53 @@ extern "C" int b2s_slab_unpack(b2s_ctx* ctx, int kind, const void* dev_buf, uint
 extern "C" int b2s_slab_dt_buffer(b2s_ctx* ctx, void** dev_u32x3){
   if(!ctx || !dev_u32x3)return B2S_ERR_ARG;
   *dev_u32x3=(void*)ctx->step;    // StepState starts with {velmax2_bits, acemax2_bits, viscdtmax_bits}: ordered uints, all-reduce with MAX
+  return B2S_OK;
+}
+
+// ---- device-counted exchange: pack / unpack without a host synchronisation (driven by slab_comm.cu) -----------------------
+// mode bit0: migrants, bit1: halos.  With both, a migrant stays on the sender as a halo ghost of its new owner (merged exchange,
+// see b2s_slab_pack_both); migrants alone (re-cut rounds) are dropped by the sender's next divide.
+int b2s_slab_pack_msg(b2s_ctx* ctx, char* dev_left, char* dev_right, uint32_t migcap, uint32_t halocap, int mode, uint32_t* dev_sent_total){
+  cudaStream_t s=ctx->stream;
+  const uint32_t n=ctx->np_host;
+  const int hl=(ctx->slab_rank>0), hr=(ctx->slab_rank<ctx->slab_nranks-1);
+  const uint32_t nb=b2s_blocks(std::max(n,1u),S_BS);
+  if(4*(size_t(nb)+1)>ctx->slab_counts_len)return b2s_fail(ctx,B2S_ERR_STATE,"slab exchange: count buffer too small for %u particles",n);
+  const bool mig=(mode&1)!=0, halo=(mode&2)!=0;
+  if(halo && ctx->slab_nranks>1 && ctx->slab_cxb-ctx->slab_cxa<=slab_halo_planes(ctx))
+    return b2s_fail(ctx,B2S_ERR_STATE,"the device-counted exchange needs slabs wider than the halo (%u planes)",slab_halo_planes(ctx));
+  uint32_t* cM=ctx->slab_counts; uint32_t* cH=ctx->slab_counts+2*(nb+1);
+  uint8_t* fM=ctx->slab_flags; uint8_t* fH=ctx->slab_flags+ctx->cap;
+  B2S_CUDA(ctx,cudaMemsetAsync(ctx->slab_counts,0,size_t(4)*(nb+1)*4,s));
+  const SlabLayout lM=slab_layout(ctx,1), lH=slab_layout(ctx,0);
+  const SlabArrays a=slab_arrays(ctx);
+  if(n){
+    if(mig){ k_slab_flag<<<nb,S_BS,0,s>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,1,hl,hr,ctx->slab_cxa,ctx->slab_cxb,slab_halo_planes(ctx),fM,cM,nb); B2S_LAUNCHED(ctx); }
+    if(halo){ k_slab_flag<<<nb,S_BS,0,s>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,0,hl,hr,ctx->slab_cxa,ctx->slab_cxb,slab_halo_planes(ctx),fH,cH,nb); B2S_LAUNCHED(ctx); }
+    if(mig){ b2s_launch_scan_excl(s,cM,nb+1); b2s_launch_scan_excl(s,cM+nb+1,nb+1); ctx->launches+=2; }
+    if(halo){ b2s_launch_scan_excl(s,cH,nb+1); b2s_launch_scan_excl(s,cH+nb+1,nb+1); ctx->launches+=2; }
+  }
+  k_slab_header<<<1,32,0,s>>>(ctx->step,cM,cH,nb,migcap,halocap,hl? dev_left: NULL,hr? dev_right: NULL,dev_sent_total); B2S_LAUNCHED(ctx);
+  if(n){
+    if(mig){ k_slab_scatter_dev<<<nb,S_BS,0,s>>>(ctx->div,fM,cM,nb,lM,a,1,dev_left,dev_right,migcap,NULL,NULL,0,0,typecode(halo? B2S_CODE_PERIODIC: B2S_CODE_OUTIGNORE)); B2S_LAUNCHED(ctx); }
+    if(halo){ k_slab_scatter_dev<<<nb,S_BS,0,s>>>(ctx->div,fH,cH,nb,lH,a,0,dev_left,dev_right,halocap,cM+nb,cM+2*nb+1,migcap,lM.bytes,typecode(B2S_CODE_OUTIGNORE)); B2S_LAUNCHED(ctx); }
+  }
+  ctx->bound_changed=true;
+  B2S_CUDA(ctx,cudaGetLastError());
+  return B2S_OK;
+}
+uint64_t b2s_slab_msg_bytes(b2s_ctx* ctx, uint32_t migcap, uint32_t halocap){
+  return uint64_t(B2S_SLAB_HDR)+uint64_t(migcap)*slab_layout(ctx,1).bytes+uint64_t(halocap)*slab_layout(ctx,0).bytes;
+}
+int b2s_slab_unpack_msg(b2s_ctx* ctx, const char* dev_msg, uint32_t migcap, uint32_t halocap){
+  const uint32_t nmax=migcap+halocap;
+  k_slab_unpack_msg<<<b2s_blocks(nmax,S_BS),S_BS,0,ctx->stream>>>(ctx->div,ctx->step,dev_msg,slab_layout(ctx,1),slab_layout(ctx,0),slab_arrays(ctx),ctx->cap,ctx->cte); B2S_LAUNCHED(ctx);
+  k_slab_unpack_msg_commit<<<1,1,0,ctx->stream>>>(ctx->div,dev_msg,ctx->cap); B2S_LAUNCHED(ctx);
+  // host mirrors: upper bounds until the next b2s_sync_info (never above the capacity: the device refuses what does not fit)
+  ctx->np_host=uint32_t(std::min<uint64_t>(uint64_t(ctx->np_host)+nmax,ctx->cap));
+  ctx->npb_host=uint32_t(std::min<uint64_t>(uint64_t(ctx->npb_host)+nmax,ctx->cap));
+  ctx->npf_host=uint32_t(std::min<uint64_t>(uint64_t(ctx->npf_host)+nmax,ctx->cap));
+  ctx->bound_changed=true;
+  B2S_CUDA(ctx,cudaGetLastError());
   return B2S_OK;
 }

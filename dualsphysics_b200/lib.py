@@ -104,8 +104,10 @@ ABI_SYMBOLS = [
     "b2s_gauge_add_velocity", "b2s_gauge_add_swl", "b2s_gauges_compute", "b2s_gauge_result",
     "b2s_launch_count", "b2s_get_stream", "b2s_set_interaction_variant", "b2s_debug_set_tile_cap", "b2s_slab_config",
     "b2s_slab_histogram", "b2s_slab_set_range", "b2s_slab_drop_ghosts", "b2s_slab_record_bytes", "b2s_slab_pack", "b2s_slab_unpack", "b2s_slab_pack_both", "b2s_slab_unpack_both", "b2s_slab_dt_buffer", "b2s_slab_forces",
-    "b2s_slab_apply_dt", "b2s_slab_integrate", "b2s_slab_step_end", "b2s_slab_ft_sums", "b2s_slab_ft_apply",
-    "b2s_sim_load", "b2s_sim_load_slab", "b2s_sim_slab_info", "b2s_sim_free", "b2s_sim_ctx", "b2s_sim_params", "b2s_sim_stats", "b2s_sim_set_dirout", "b2s_sim_save_part", "b2s_sim_run",
+    "b2s_slab_apply_dt", "b2s_slab_integrate", "b2s_slab_step_end", "b2s_slab_ft_sums", "b2s_slab_ft_apply", "b2s_slab_get_range",
+    "b2s_slab_comm_id", "b2s_slab_comm_init", "b2s_slab_comm_init_local", "b2s_slab_comm_free", "b2s_slab_comm_set_recut", "b2s_slab_comm_stats",
+    "b2s_slab_exchange", "b2s_slab_step", "b2s_slab_run_steps", "b2s_slab_recut",
+    "b2s_sim_load", "b2s_sim_load_slab", "b2s_sim_slab_connect", "b2s_sim_slab_info", "b2s_sim_free", "b2s_sim_ctx", "b2s_sim_params", "b2s_sim_stats", "b2s_sim_set_dirout", "b2s_sim_save_part", "b2s_sim_run",
     "b2s_host_motionref_write", "b2s_host_xml_stats", "b2s_host_last_error",
 ]
 
@@ -192,6 +194,18 @@ def load_library():
     lib.b2s_sim_load.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_uint32, C.POINTER(vp)]
     lib.b2s_sim_free.argtypes = [vp]
     lib.b2s_sim_ctx.argtypes = [vp, C.POINTER(vp)]
+    lib.b2s_slab_get_range.argtypes = [vp, u32p]
+    lib.b2s_slab_comm_id.argtypes = [C.c_void_p]
+    lib.b2s_slab_comm_init.argtypes = [vp, C.c_void_p, C.c_uint32]
+    lib.b2s_slab_comm_init_local.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_uint32]
+    lib.b2s_slab_comm_free.argtypes = [vp]
+    lib.b2s_slab_comm_set_recut.argtypes = [vp, C.c_uint32]
+    lib.b2s_slab_comm_stats.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
+    lib.b2s_slab_exchange.argtypes = [vp]
+    lib.b2s_slab_step.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.b2s_slab_run_steps.argtypes = [vp, C.c_uint32, C.POINTER(C.c_double)]
+    lib.b2s_slab_recut.argtypes = [vp, u32p, C.c_uint32]
+    lib.b2s_sim_slab_connect.argtypes = [vp, C.c_void_p]
     lib.b2s_sim_params.argtypes = [vp, C.POINTER(Params)]
     lib.b2s_sim_save_part.argtypes = [vp]
     lib.b2s_sim_set_dirout.argtypes = [vp, C.c_char_p]
@@ -347,6 +361,11 @@ class Context:
     def slab_set_range(self, cx_begin, cx_end):
         self._chk(self._lib.b2s_slab_set_range(self._h, cx_begin, cx_end))
 
+    def slab_get_range(self):
+        rng = (C.c_uint32 * 2)()
+        self._chk(self._lib.b2s_slab_get_range(self._h, rng))
+        return int(rng[0]), int(rng[1])
+
     def slab_drop_ghosts(self):
         self._chk(self._lib.b2s_slab_drop_ghosts(self._h))
 
@@ -397,6 +416,38 @@ class Context:
         dt = C.c_double(0)
         self._chk(self._lib.b2s_slab_step_end(self._h, C.byref(dt)))
         return dt.value
+
+    # ---- the slab step inside the library (csrc/slab_comm.cu): NCCL transport, no host synchronisation inside a step ----
+    def slab_comm_init(self, nccl_id: bytes, max_plane_particles: int):
+        assert len(nccl_id) == 128
+        self._chk(self._lib.b2s_slab_comm_init(self._h, (C.c_uint8 * 128).from_buffer_copy(nccl_id), max_plane_particles))
+
+    def slab_comm_set_recut(self, every_steps: int):
+        self._chk(self._lib.b2s_slab_comm_set_recut(self._h, every_steps))
+
+    def slab_comm_stats(self, reset=False):
+        """(ms inside pack+transfer+unpack, exchanges, bytes sent, re-cuts) since the last reset, migrants sent since init."""
+        out = (C.c_double * 5)()
+        self._chk(self._lib.b2s_slab_comm_stats(self._h, out, int(reset)))
+        return out[0], int(out[1]), int(out[2]), int(out[3]), int(out[4])
+
+    def slab_exchange(self):
+        self._chk(self._lib.b2s_slab_exchange(self._h))
+
+    def slab_step(self) -> float:
+        dt = C.c_double(0)
+        self._chk(self._lib.b2s_slab_step(self._h, C.byref(dt)))
+        return dt.value
+
+    def slab_run_steps(self, n: int) -> float:
+        t = C.c_double(0)
+        self._chk(self._lib.b2s_slab_run_steps(self._h, n, C.byref(t)))
+        return t.value
+
+    def slab_recut(self):
+        rng = (C.c_uint32 * 2)()
+        self._chk(self._lib.b2s_slab_recut(self._h, rng, 2))
+        return int(rng[0]), int(rng[1])
 
     def stream(self):
         p = C.c_void_p()
@@ -478,6 +529,23 @@ def motionref_write(dirdata: str, bodies, timeout: float, mkboundfirst: int, idp
                                      ts.ctypes.data, st.ctypes.data)
     if r:
         raise B2SError(r, lib.b2s_host_last_error().decode())
+
+
+def slab_comm_id() -> bytes:
+    """The 128-byte NCCL id of a new communicator (rank 0 makes it, every rank passes it to Context.slab_comm_init)."""
+    buf = (C.c_uint8 * 128)()
+    r = load_library().b2s_slab_comm_id(buf)
+    if r:
+        raise B2SError(r, "b2s_slab_comm_id: NCCL not available")
+    return bytes(buf)
+
+
+def slab_comm_init_local(ctxs, max_plane_particles: int):
+    """Test transport: all ranks of the run live in this process on one device (csrc/slab_comm.cu)."""
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    r = load_library().b2s_slab_comm_init_local(arr, len(ctxs), max_plane_particles)
+    if r:
+        raise B2SError(r, "b2s_slab_comm_init_local")
 
 
 class Simulation:

@@ -80,11 +80,21 @@ class SlabRank:
         self.cap_records = int(2 * self.halo_planes * maxplane + 4096)
         self.symplectic = (self.p.tstep == L.STEP_SYMPLECTIC)
         maxbytes = 48 + 48 + 16 + 16 + 32     # largest record csrc/slab.cu can produce (the size varies with the step phase)
-        mk = lambda: torch.empty(self.cap_records * maxbytes, dtype=torch.uint8, device=self.dev)  # noqa: E731
-        self.send_l, self.send_r, self.recv_l, self.recv_r = mk(), mk(), mk(), mk()
+        self._bufbytes = self.cap_records * maxbytes
+        self._bufs = None        # allocated on first use: the native step keeps its own buffers inside the library
         self._ext = None
         self._dt_t = None
         self._ft_t = None
+
+    def _buf(self, k):
+        if self._bufs is None:
+            self._bufs = [self.torch.empty(self._bufbytes, dtype=self.torch.uint8, device=self.dev) for _ in range(4)]
+        return self._bufs[k]
+
+    send_l = property(lambda self: self._buf(0))
+    send_r = property(lambda self: self._buf(1))
+    recv_l = property(lambda self: self._buf(2))
+    recv_r = property(lambda self: self._buf(3))
 
     def on_stream(self):
         """Context that makes the ctx's CUDA stream torch's current stream: NCCL operations issued inside are ordered with
@@ -251,7 +261,12 @@ class SlabSimulation:
     ``dist`` = torch.distributed (already initialised, NCCL): this process owns ONE rank.
     ``dist`` = None: all ranks are created in this process on ``device`` (LocalTransport, for tests)."""
 
-    def __init__(self, casepath, options="", nranks=1, dist=None, device=0, recut_every=0, merged=True):
+    def __init__(self, casepath, options="", nranks=1, dist=None, device=0, recut_every=0, merged=True, native=None):
+        """``native``: the whole step runs inside the library (csrc/slab_comm.cu: ncclSend/ncclRecv/ncclAllReduce issued from
+        C++, counts kept on the device, one host synchronisation per step); Python only hands over the NCCL id.  Default: on
+        whenever the slabs are wider than the halo (what the device-counted exchange needs).  ``native=False`` keeps the
+        round-1 orchestration in this file (torch.distributed P2P ops, two host waits per exchange); with ``dist=None`` the
+        native path uses the library's local test transport."""
         import torch
         self.torch, self.dist = torch, dist
         if dist is None:
@@ -267,6 +282,23 @@ class SlabSimulation:
         import os
         self._prof = [] if (os.environ.get("B2S_SLAB_PROFILE") and dist is not None) else None
         self.cuts = self.ranks[0].cuts
+        if native is None:
+            native = os.environ.get("B2S_SLAB_NATIVE", "1") != "0"
+        self.native = bool(native) and nranks > 1 and self._merged_ok()
+        if self.native:
+            _, maxplane = self.ranks[0].sim.slab_info(nranks)
+            if dist is None:
+                L.slab_comm_init_local([r.ctx for r in self.ranks], maxplane)
+            else:
+                # rank 0 makes the NCCL id; it travels once through torch.distributed (plumbing), the data plane is the library's
+                ids = [L.slab_comm_id() if dist.get_rank() == 0 else None]
+                dist.broadcast_object_list(ids, src=0)
+                self.ranks[0].ctx.slab_comm_init(ids[0], maxplane)
+            if self.recut_every:
+                for r in self.ranks:
+                    r.ctx.slab_comm_set_recut(self.recut_every)
+            self.ranks[0].ctx.slab_exchange()
+            return
         self._exchange(first=True)
 
     # migrants then halos, then the cell divide (RunCellDivide with the ghosts in place)
@@ -375,7 +407,31 @@ class SlabSimulation:
         nsteps = max(cnt.get("step_end", 1), 1)
         return {k: v / nsteps for k, v in acc.items()}
 
+    def comm_stats(self, reset=False):
+        """Native path: (ms inside pack+transfer+unpack on rank 0 of this process, exchanges, bytes sent, re-cuts)."""
+        return self.ranks[0].ctx.slab_comm_stats(reset) if self.native else (0.0, 0, 0, 0, 0)
+
+    def migrated_total(self) -> int:
+        """Particles that changed owner so far (this process's ranks)."""
+        if self.native:
+            return sum(r.ctx.slab_comm_stats()[4] for r in self.ranks)
+        return self.migrated
+
+    def run_steps(self, n: int):
+        if self.native:
+            self.ranks[0].ctx.slab_run_steps(n)
+            self.nstep += n
+        else:
+            for _ in range(n):
+                self.step()
+
     def step(self, final_exchange=True) -> float:
+        if self.native and final_exchange:
+            dt = self.ranks[0].ctx.slab_step()      # local transport: one call drives every rank of the group
+            self.nstep += 1
+            if self.recut_every and self.nstep % self.recut_every == 0:
+                self._refresh_cuts()
+            return dt
         self._mark("begin")
         if self.symplectic:
             self._interaction(L.INTER_SYMPREDICTOR)
@@ -411,10 +467,22 @@ class SlabSimulation:
             self._mark("exchange_end+celldiv")
         return dts[0]
 
+    def _refresh_cuts(self):
+        for r in self.ranks:
+            r.cxa, r.cxb = r.ctx.slab_get_range()
+        if self.dist is None:
+            self.cuts = [self.ranks[0].cxa] + [r.cxb for r in self.ranks]
+            for r in self.ranks:
+                r.cuts = self.cuts
+
     def recut(self, cuts=None):
         """Dynamic load balance: new cut planes from the global particle histogram along x (all-reduced), then the particles
         outside their slab's new range migrate (one neighbour hop per round, repeated until nobody has migrants left), then
         halos + divide.  Call between steps.  ``cuts`` overrides the balanced cuts (tests)."""
+        if self.native and cuts is None:
+            self.ranks[0].ctx.slab_recut()
+            self._refresh_cuts()
+            return self.cuts
         torch = self.torch
         ncx = int(self.ranks[0].p.domcells[0])
         nranks = self.ranks[0].nranks
@@ -456,6 +524,8 @@ class SlabSimulation:
         else:
             raise RuntimeError("recut: migrants left after nranks rounds")
         self._exchange(first=True)
+        if self.native and not self._merged_ok():
+            self.native = False          # forced cuts no wider than the halo: back to the host-counted exchange of this file
         return self.cuts
 
     def host_roundtrip_begin(self):
@@ -466,7 +536,10 @@ class SlabSimulation:
 
     def host_roundtrip_end(self):
         """After re-uploading the owned particles: move migrants, rebuild halos, divide."""
-        self._exchange()
+        if self.native:
+            self.ranks[0].ctx.slab_exchange()
+        else:
+            self._exchange()
 
     def set_dirout(self, dirout: str):
         """PART output of a multi-GPU run: every rank writes its own piece (Part_pRR_XXXX.bi4, the reference's piece format,

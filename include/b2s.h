@@ -318,6 +318,7 @@ int b2s_slab_dt_buffer(b2s_ctx* ctx, void** dev_u32x3);
  * the particles now outside leave through the normal migrant exchange (repeat it until no rank has migrants left). */
 int b2s_slab_histogram(b2s_ctx* ctx, void* dev_u32_ncx);
 int b2s_slab_set_range(b2s_ctx* ctx, uint32_t cx_begin, uint32_t cx_end);
+int b2s_slab_get_range(b2s_ctx* ctx, uint32_t* range2);   /* current [cx_begin,cx_end) of this rank (changes with a re-cut) */
 /* Marks the halo ghosts of the last exchange for removal by the next divide (needed when halos are rebuilt between steps). */
 int b2s_slab_drop_ghosts(b2s_ctx* ctx);
 int b2s_slab_forces(b2s_ctx* ctx, int interstep);
@@ -330,6 +331,32 @@ int b2s_slab_step_end(b2s_ctx* ctx, double* dt_out);
  * every rank, and update of the owned floating particles).  predictor: 1 after SymplecticPre, 0 otherwise. */
 int b2s_slab_ft_sums(b2s_ctx* ctx, void** dev_f32, uint32_t* count);
 int b2s_slab_ft_apply(b2s_ctx* ctx, int predictor);
+/* ---- the slab step inside the library (csrc/slab_comm.cu): NCCL transport, no host synchronisation inside a step ----------
+ * One process per GPU.  Rank 0 makes the 128-byte NCCL id (b2s_slab_comm_id) and hands it to every rank by whatever means the
+ * launcher has (torch.distributed broadcast in bench.py / slab.py, a file in the CLI); every rank then calls b2s_slab_comm_init
+ * after b2s_slab_config.  max_plane_particles (b2s_sim_slab_info) sizes the exchange buffers.  NCCL is dlopen'ed here, so
+ * single-GPU runs do not need it.  Collective calls (every rank, same order):
+ *   b2s_slab_exchange   migrants + halos to both neighbours in one fixed-size message per side whose header carries the counts
+ *                       (they never visit the host), then the cell divide; call once after b2s_slab_comm_init
+ *   b2s_slab_step       one whole ComputeStep (JSphGpuSingle.cpp:761-819 + run-loop tail :1003-1008): interactions with the dt
+ *                       maxima all-reduced (MAX), integrators, floating-body sums all-reduced (SUM), the exchanges, an optional
+ *                       re-cut; ONE host synchronisation at its end
+ *   b2s_slab_recut      dynamic load balance: all-reduced work histogram along x -> new cut planes -> migrant rounds -> halos
+ * b2s_slab_comm_set_recut: b2s_slab_step re-cuts every that many steps (0 = never).
+ * b2s_slab_comm_stats: out[0] ms inside pack + transfer + unpack (events on the context's stream: includes waiting for a slower
+ *   neighbour), [1] exchanges, [2] bytes sent, [3] re-cuts since the last reset, [4] migrants sent since b2s_slab_comm_init.
+ * b2s_slab_comm_init_local: test transport -- all ranks in this process on one device (device copies, host reductions); one call
+ *   of a collective entry point on any context of the group then drives every rank. */
+int b2s_slab_comm_id(uint8_t* id128);
+int b2s_slab_comm_init(b2s_ctx* ctx, const uint8_t* id128, uint32_t max_plane_particles);
+int b2s_slab_comm_init_local(b2s_ctx** ctxs, int nranks, uint32_t max_plane_particles);
+int b2s_slab_comm_free(b2s_ctx* ctx);
+int b2s_slab_comm_set_recut(b2s_ctx* ctx, uint32_t every_steps);
+int b2s_slab_comm_stats(b2s_ctx* ctx, double* out5, int reset);
+int b2s_slab_exchange(b2s_ctx* ctx);
+int b2s_slab_step(b2s_ctx* ctx, double* dt_out);
+int b2s_slab_run_steps(b2s_ctx* ctx, uint32_t nsteps, double* time_out);
+int b2s_slab_recut(b2s_ctx* ctx, uint32_t* range_out, uint32_t n2);
 
 #ifdef __cplusplus
 }

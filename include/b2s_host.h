@@ -21,6 +21,9 @@ int b2s_sim_load(const char* casepath, const char* dirout, const char* options, 
  * reads the same case, derives the same balanced cut planes along x from the particle histogram, uploads ONLY its slab
  * and calls b2s_slab_config.  With mDBC the halo is two kernel radii wide (boundary ghosts recompute their ghost-node density locally). */
 int b2s_sim_load_slab(const char* casepath, const char* options, int device, int rank, int nranks, b2s_sim** out);
+/* Connects a slab rank to the others (csrc/slab_comm.cu): NCCL communicator from the 128-byte id rank 0 obtained with
+ * b2s_slab_comm_id, then the first halo exchange.  Afterwards b2s_sim_run steps collectively (b2s_slab_step) and writes pieces. */
+int b2s_sim_slab_connect(b2s_sim* sim, const uint8_t* nccl_id128);
 /* PART output of a slab rank: every rank writes its own piece of each PART the way the reference's format provides for
  * (src/source/JPartDataBi4.cpp:99-127: Part_pRR_XXXX.bi4, PartInfo_pRR.ibi4, head values Piece / Npiece), rank 0 also Part_Head.ibi4
  * and PartFloatInfo.ibi4; no gather.  Call once after b2s_sim_load_slab, then b2s_sim_save_part on every rank at the same step. */

@@ -35,7 +35,7 @@ def main():
     buf[:len(ids), 4:8] = torch.from_numpy(vr.astype(np.float64)).cuda()
     allb = [torch.zeros_like(buf) for _ in range(world)]
     dist.all_gather(allb, buf)
-    migrated = torch.tensor([ss.migrated], device="cuda", dtype=torch.int64)
+    migrated = torch.tensor([ss.migrated_total()], device="cuda", dtype=torch.int64)
     dist.all_reduce(migrated)
     if rank == 0:
         rows = np.concatenate([b[:c].cpu().numpy() for b, c in zip(allb, counts)])

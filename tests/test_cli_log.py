@@ -20,6 +20,10 @@ int b2s_sim_stats(b2s_sim*,uint32_t* parts,uint32_t* e){ *parts=5; e[0]=3; e[1]=
 int b2s_sim_ctx(b2s_sim*,b2s_ctx** c){ *c=&C; return 0; }
 int b2s_get_info(b2s_ctx*,b2s_info* i){ memset(i,0,sizeof(*i)); i->np=997; i->nct=4321; return 0; }
 int b2s_sim_free(b2s_sim*){ return 0; }
+int b2s_slab_comm_id(uint8_t*){ return -1; }                       // the multi-GPU branch of main.cpp is not taken here (WORLD_SIZE unset)
+int b2s_sim_load_slab(const char*,const char*,int,int,int,b2s_sim**){ return -1; }
+int b2s_sim_set_dirout(b2s_sim*,const char*){ return -1; }
+int b2s_sim_slab_connect(b2s_sim*,const uint8_t*){ return -1; }
 const char* b2s_host_last_error(void){ return "xml: cannot open"; }
 }
 '''

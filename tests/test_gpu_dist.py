@@ -34,3 +34,36 @@ def test_nccl_slabs_match_single_context(options, nsteps, recut, tmp_path, built
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     print(r.stdout[-1500:])
     assert r.returncode == 0 and "SLAB_NCCL_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-4000:]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_cli_two_ranks_write_pieces(tmp_path, built_lib):
+    """The C++ command line on two GPUs: one b200sph process per GPU (RANK / WORLD_SIZE / LOCAL_RANK in the environment, the NCCL id
+    through a file), collective steps inside the library (csrc/slab_comm.cu), one piece of every PART per rank.  The union of the
+    pieces must be the particle set of the single-GPU run of the same command, positions to rounding."""
+    import numpy as np
+    from dualsphysics_b200 import bi4
+    H.write_case(tmp_path, dp=0.03, params={"TimeMax": 0.02, "TimeOut": 0.005})
+    exe = os.path.join(H.ROOT, "dualsphysics_b200", "lib", "b200sph")
+    opts = ["-symplectic", "-cellmode:half", "-tmax:0.01", "-tout:0.005"]
+    one = subprocess.run([exe, str(tmp_path / "Case"), str(tmp_path / "out1")] + opts, capture_output=True, text=True, timeout=600)
+    assert one.returncode == 0, one.stdout[-2000:] + one.stderr[-2000:]
+    idfile = str(tmp_path / "nccl.id")
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), B2S_NCCL_ID_FILE=idfile)
+        procs.append(subprocess.Popen([exe, str(tmp_path / "Case"), str(tmp_path / "out2")] + opts, env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[-2000:] for o in outs)
+    assert "Finished execution (code=0)" in outs[0]
+    k = 0
+    while os.path.exists(str(tmp_path / "out1" / "data" / f"Part_{k:04d}.bi4")):
+        ref = bi4.load_part(str(tmp_path / "out1" / "data" / f"Part_{k:04d}.bi4"))
+        pieces = [bi4.load_part(str(tmp_path / "out2" / "data" / f"Part_p{r:02d}_{k:04d}.bi4")) for r in range(2)]
+        ids = np.concatenate([p["Idp"] for p in pieces]); pos = np.concatenate([p["pos"] for p in pieces])
+        o, ro = np.argsort(ids, kind="stable"), np.argsort(ref["Idp"], kind="stable")
+        assert np.array_equal(ids[o], ref["Idp"][ro]), f"PART {k}: the pieces do not add up to the particle set"
+        assert float(np.max(np.abs(pos[o] - ref["pos"][ro]))) < 1e-6, k
+        k += 1
+    assert k >= 3, k
