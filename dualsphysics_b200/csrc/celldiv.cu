@@ -146,21 +146,25 @@ __global__ void __launch_bounds__(DIV_BS) k_presort(const DivState* __restrict__
 #define RDX_ITEMS 16
 #define RDX_TILE (DIV_BS*RDX_ITEMS)
 
-__global__ void __launch_bounds__(DIV_BS) k_radix_hist(const uint32_t* __restrict__ keys, const DivState* __restrict__ ds,
+// NBINS = 256 or 512: the passes split ceil(log2(maxkey)) bits as evenly as they can, so the ~25 key bits of a 10M-particle dam
+// break (2*Nct+5 boxes) take three passes of 9+8+8 bits instead of four of 8 (radix_plan).
+template<int NBINS> __global__ void __launch_bounds__(DIV_BS) k_radix_hist(const uint32_t* __restrict__ keys, const DivState* __restrict__ ds,
   int shift, uint32_t ntiles, uint32_t* __restrict__ counts)
 {
-  __shared__ uint32_t h[256];
+  __shared__ uint32_t h[NBINS];
   const uint32_t n=ds->nptot;
-  h[threadIdx.x]=0;
+  #pragma unroll
+  for(int b=threadIdx.x;b<NBINS;b+=DIV_BS)h[b]=0;
   __syncthreads();
   const uint32_t base=blockIdx.x*RDX_TILE;
   #pragma unroll
   for(int r=0;r<RDX_ITEMS;r++){
     const uint32_t i=base+r*DIV_BS+threadIdx.x;
-    if(i<n)atomicAdd(&h[(keys[i]>>shift)&255u],1u);
+    if(i<n)atomicAdd(&h[(keys[i]>>shift)&uint32_t(NBINS-1)],1u);
   }
   __syncthreads();
-  counts[threadIdx.x*ntiles+blockIdx.x]=h[threadIdx.x];
+  #pragma unroll
+  for(int b=threadIdx.x;b<NBINS;b+=DIV_BS)counts[size_t(b)*ntiles+blockIdx.x]=h[b];
 }
 
 // Exclusive scan of n uints (n = 256*ntiles, ~6e5 at 10M particles).  Blocks of 4096 elements:
@@ -234,26 +238,30 @@ int b2s_scan_excl(cudaStream_t s, uint32_t* data, uint32_t n, uint32_t* scratch)
   return 3;
 }
 
-__global__ void __launch_bounds__(DIV_BS) k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+template<int NBINS> __global__ void __launch_bounds__(DIV_BS) k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ offsets,
   const DivState* __restrict__ ds, int shift, uint32_t ntiles)
 {
-  __shared__ uint32_t s_base[256];
-  __shared__ uint32_t s_wc[DIV_BS/32][256];
+  __shared__ uint32_t s_base[NBINS];
+  __shared__ uint32_t s_wc[DIV_BS/32][NBINS];
   const uint32_t n=ds->nptot;
   const int lane=threadIdx.x&31, w=threadIdx.x>>5;
-  s_base[threadIdx.x]=offsets[threadIdx.x*ntiles+blockIdx.x];
+  #pragma unroll
+  for(int b=threadIdx.x;b<NBINS;b+=DIV_BS)s_base[b]=offsets[size_t(b)*ntiles+blockIdx.x];
   const uint32_t base=blockIdx.x*RDX_TILE;
   for(int r=0;r<RDX_ITEMS;r++){
     const uint32_t i=base+r*DIV_BS+threadIdx.x;
     const bool valid=(i<n);
     const uint32_t key=(valid? keys_in[i]: 0u);
     const uint32_t val=(valid? vals_in[i]: 0u);
-    const uint32_t digit=(key>>shift)&255u;
+    const uint32_t digit=(key>>shift)&uint32_t(NBINS-1);
     #pragma unroll
-    for(int k=0;k<DIV_BS/32;k++)s_wc[k][threadIdx.x]=0;
+    for(int b=threadIdx.x;b<NBINS;b+=DIV_BS){
+      #pragma unroll
+      for(int k=0;k<DIV_BS/32;k++)s_wc[k][b]=0;
+    }
     __syncthreads();
-    const uint32_t peers=__match_any_sync(0xffffffffu,(valid? digit: (256u+lane)));
+    const uint32_t peers=__match_any_sync(0xffffffffu,(valid? digit: (uint32_t(NBINS)+lane)));
     const uint32_t lower=peers&((1u<<lane)-1u);
     if(valid && lower==0)s_wc[w][digit]=__popc(peers);
     __syncthreads();
@@ -264,10 +272,13 @@ __global__ void __launch_bounds__(DIV_BS) k_radix_scatter(const uint32_t* __rest
       keys_out[pos]=key; vals_out[pos]=val;
     }
     __syncthreads();
-    uint32_t tot=0;
     #pragma unroll
-    for(int k=0;k<DIV_BS/32;k++)tot+=s_wc[k][threadIdx.x];
-    s_base[threadIdx.x]+=tot;
+    for(int b=threadIdx.x;b<NBINS;b+=DIV_BS){
+      uint32_t tot=0;
+      #pragma unroll
+      for(int k=0;k<DIV_BS/32;k++)tot+=s_wc[k][b];
+      s_base[b]+=tot;
+    }
     __syncthreads();
   }
 }
@@ -414,7 +425,13 @@ __global__ void k_reset_step_maxima(StepState* st){
 }
 
 // ------------------------------------------------------------------------------------------------
-static inline int radix_passes(uint32_t maxkey){ int bits=1; while((maxkey>>bits)!=0)bits++; return (bits+7)/8; }
+// Passes of the LSD sort over the bits of the largest key: as few as 9-bit digits allow, the bits spread evenly (8 or 9 per pass).
+static inline int radix_plan(uint32_t maxkey,int* digitbits){
+  int bits=1; while(bits<32 && (maxkey>>bits)!=0)bits++;
+  const int passes=(bits+8)/9;
+  for(int k=0;k<passes;k++)digitbits[k]=std::max(8,(bits+passes-1-k)/passes);   // e.g. 25 bits -> 9,8,8
+  return passes;
+}
 
 int b2s_celldiv_impl(b2s_ctx* ctx){
   cudaStream_t s=ctx->stream;
@@ -434,12 +451,20 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   k_presort<<<b2s_blocks(nptot,DIV_BS),DIV_BS,0,s>>>(ctx->div,ctx->cur.dcell,ctx->cur.code,c.domcellcode,ctx->cellpart,ctx->sortpart); B2S_LAUNCHED(ctx);
   // 3. stable radix sort
   const uint32_t ntiles=b2s_blocks(nptot,RDX_TILE);
-  const int passes=radix_passes(2u*ctx->nct_max+5u);
+  int dbits[4];
+  const int passes=radix_plan(2u*ctx->nct_max+5u,dbits);
   uint32_t *kin=ctx->cellpart,*vin=ctx->sortpart,*kout=ctx->cellpart_alt,*vout=ctx->sortpart_alt;
-  for(int ps=0;ps<passes;ps++){
-    k_radix_hist<<<ntiles,DIV_BS,0,s>>>(kin,ctx->div,ps*8,ntiles,ctx->radix_counts); B2S_LAUNCHED(ctx);
-    ctx->launches+=b2s_scan_excl(s,ctx->radix_counts,256u*ntiles,ctx->radix_counts+ctx->radix_counts_len);
-    k_radix_scatter<<<ntiles,DIV_BS,0,s>>>(kin,vin,kout,vout,ctx->radix_counts,ctx->div,ps*8,ntiles); B2S_LAUNCHED(ctx);
+  for(int ps=0,shift=0;ps<passes;shift+=dbits[ps],ps++){
+    if(dbits[ps]>8){
+      k_radix_hist<512><<<ntiles,DIV_BS,0,s>>>(kin,ctx->div,shift,ntiles,ctx->radix_counts); B2S_LAUNCHED(ctx);
+      ctx->launches+=b2s_scan_excl(s,ctx->radix_counts,512u*ntiles,ctx->radix_counts+ctx->radix_counts_len);
+      k_radix_scatter<512><<<ntiles,DIV_BS,0,s>>>(kin,vin,kout,vout,ctx->radix_counts,ctx->div,shift,ntiles); B2S_LAUNCHED(ctx);
+    }
+    else{
+      k_radix_hist<256><<<ntiles,DIV_BS,0,s>>>(kin,ctx->div,shift,ntiles,ctx->radix_counts); B2S_LAUNCHED(ctx);
+      ctx->launches+=b2s_scan_excl(s,ctx->radix_counts,256u*ntiles,ctx->radix_counts+ctx->radix_counts_len);
+      k_radix_scatter<256><<<ntiles,DIV_BS,0,s>>>(kin,vin,kout,vout,ctx->radix_counts,ctx->div,shift,ntiles); B2S_LAUNCHED(ctx);
+    }
     uint32_t* t=kin; kin=kout; kout=t; t=vin; vin=vout; vout=t;
   }
   if(kin!=ctx->cellpart){ // odd number of passes: sorted data sits in the alt buffers -> swap names

@@ -109,7 +109,7 @@ extern "C" int b2s_create(const b2s_params* p, int device, uint32_t capacity_np,
   TRY(dalloc(ctx->cellpart,cap)); TRY(dalloc(ctx->sortpart,cap)); TRY(dalloc(ctx->cellpart_alt,cap)); TRY(dalloc(ctx->sortpart_alt,cap));
   { uint32_t* b=NULL; TRY(dalloc(b,size_t(ctx->nctt_max)+2)); ctx->begincell=(int2*)b; }
   TRY(dalloc(ctx->nearbound,size_t(ctx->nct_max)+8));
-  ctx->radix_counts_len=size_t(256)*((cap+4095)/4096+1);
+  ctx->radix_counts_len=size_t(512)*((cap+4095)/4096+1);   // digit histograms per tile: up to 9-bit digits (celldiv.cu radix_plan)
   TRY(dalloc(ctx->radix_counts,ctx->radix_counts_len+ctx->radix_counts_len/4096+8));   // + block totals of the scan (celldiv.cu)
   TRY(dalloc(ctx->ridp,size_t(q.casenmoving)+q.casenfloat+1));
   TRY(dalloc(ctx->div,1)); TRY(dalloc(ctx->step,1));

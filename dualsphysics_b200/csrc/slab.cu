@@ -127,6 +127,58 @@ __global__ void __launch_bounds__(S_BS) k_slab_scatter_dev(const DivState* __res
   if(f&2){ const uint32_t i=offs[nblocks+1+blockIdx.x]+pr+__popc(br&lm); if(i<cap){ slab_write(right+baser+size_t(i)*l.bytes,l,a,p); sent=true; } }
   if(kind==1 && sent)a.code[p]=typecode(B2S_CODE_SETNORMAL(a.code[p])|migcode);   // a migrant that did not fit stays (the error flag is raised by k_slab_header)
 }
+// Both kinds in one pass (the per-interaction exchange): flags + block counts of migrants and halo particles ...
+__global__ void __launch_bounds__(S_BS) k_slab_flag2(const DivState* __restrict__ ds, const typecode* __restrict__ code, const uint32_t* __restrict__ dcell,
+  uint32_t dcc, int has_left, int has_right, uint32_t cxa, uint32_t cxb, uint32_t d, uint8_t* flagsM, uint8_t* flagsH, uint32_t* cM, uint32_t* cH, uint32_t nblocks)
+{
+  __shared__ uint32_t cnt[4];
+  if(threadIdx.x<4)cnt[threadIdx.x]=0;
+  __syncthreads();
+  const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
+  uint8_t fm=0, fh=0;
+  if(p<ds->np){
+    if(B2S_CODE_SPECIAL(code[p])==B2S_CODE_NORMAL){
+      const uint32_t cx=B2S_DCEL_CELLX(dcc,dcell[p]);
+      if(has_left){ if(cx<cxa)fm|=1; else if(cx<cxa+d)fh|=1; }
+      if(has_right){ if(cx>=cxb)fm|=2; else if(cx+d>=cxb)fh|=2; }
+    }
+    flagsM[p]=fm; flagsH[p]=fh;
+  }
+  const uint32_t b0=__ballot_sync(0xffffffffu,fm&1), b1=__ballot_sync(0xffffffffu,fm&2), b2=__ballot_sync(0xffffffffu,fh&1), b3=__ballot_sync(0xffffffffu,fh&2);
+  if((threadIdx.x&31)==0){ if(b0)atomicAdd(&cnt[0],__popc(b0)); if(b1)atomicAdd(&cnt[1],__popc(b1)); if(b2)atomicAdd(&cnt[2],__popc(b2)); if(b3)atomicAdd(&cnt[3],__popc(b3)); }
+  __syncthreads();
+  if(threadIdx.x==0){ cM[blockIdx.x]=cnt[0]; cM[nblocks+1+blockIdx.x]=cnt[1]; cH[blockIdx.x]=cnt[2]; cH[nblocks+1+blockIdx.x]=cnt[3]; }
+}
+// ... and their records: a migrant is never a halo particle of the same exchange (slabs are wider than the halo), so the two
+// writes of a thread never touch the same particle's code.
+__global__ void __launch_bounds__(S_BS) k_slab_scatter2(const DivState* __restrict__ ds, const uint8_t* __restrict__ flagsM, const uint8_t* __restrict__ flagsH,
+  const uint32_t* __restrict__ cM, const uint32_t* __restrict__ cH, uint32_t nblocks, SlabLayout lM, SlabLayout lH, SlabArrays a,
+  char* left, char* right, uint32_t migcap, uint32_t halocap, typecode migcode)
+{
+  __shared__ uint32_t wc[4][S_BS/32];
+  const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
+  const int lane=threadIdx.x&31, w=threadIdx.x>>5;
+  const bool in=(p<ds->np);
+  const uint8_t fm=(in? flagsM[p]: uint8_t(0)), fh=(in? flagsH[p]: uint8_t(0));
+  const uint32_t b[4]={__ballot_sync(0xffffffffu,fm&1),__ballot_sync(0xffffffffu,fm&2),__ballot_sync(0xffffffffu,fh&1),__ballot_sync(0xffffffffu,fh&2)};
+  if(lane==0){ wc[0][w]=__popc(b[0]); wc[1][w]=__popc(b[1]); wc[2][w]=__popc(b[2]); wc[3][w]=__popc(b[3]); }
+  __syncthreads();
+  if(!(fm|fh))return;
+  const uint32_t lm=(1u<<lane)-1u;
+  const uint32_t totl=min(cM[nblocks],migcap), totr=min(cM[2*nblocks+1],migcap);      // migrant records in front of the halo records
+  #pragma unroll
+  for(int k=0;k<4;k++){
+    const bool mig=(k<2), lft=((k&1)==0);
+    if(!((mig? fm: fh)&(lft? 1: 2)))continue;
+    uint32_t pre=0; for(int q=0;q<w;q++)pre+=wc[k][q];
+    const uint32_t* offs=(mig? cM: cH)+(lft? 0u: nblocks+1u);
+    const uint32_t i=offs[blockIdx.x]+pre+__popc(b[k]&lm);
+    if(i>=(mig? migcap: halocap))continue;                    // does not fit: k_slab_header raises the error flag
+    char* base=(lft? left: right)+B2S_SLAB_HDR+(mig? size_t(0): size_t(lft? totl: totr)*lM.bytes);
+    slab_write(base+size_t(i)*(mig? lM.bytes: lH.bytes),mig? lM: lH,a,p);
+    if(mig)a.code[p]=typecode(B2S_CODE_SETNORMAL(a.code[p])|migcode);
+  }
+}
 __global__ void k_slab_header(StepState* st, const uint32_t* __restrict__ cM, const uint32_t* __restrict__ cH, uint32_t nb, uint32_t migcap, uint32_t halocap,
   char* left, char* right, uint32_t* sent_total)
 {
@@ -397,13 +449,17 @@ int b2s_slab_pack_msg(b2s_ctx* ctx, char* dev_left, char* dev_right, uint32_t mi
   const SlabLayout lM=slab_layout(ctx,1), lH=slab_layout(ctx,0);
   const SlabArrays a=slab_arrays(ctx);
   if(n){
-    if(mig){ k_slab_flag<<<nb,S_BS,0,s>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,1,hl,hr,ctx->slab_cxa,ctx->slab_cxb,slab_halo_planes(ctx),fM,cM,nb); B2S_LAUNCHED(ctx); }
-    if(halo){ k_slab_flag<<<nb,S_BS,0,s>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,0,hl,hr,ctx->slab_cxa,ctx->slab_cxb,slab_halo_planes(ctx),fH,cH,nb); B2S_LAUNCHED(ctx); }
+    if(mig && halo){ k_slab_flag2<<<nb,S_BS,0,s>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,hl,hr,ctx->slab_cxa,ctx->slab_cxb,slab_halo_planes(ctx),fM,fH,cM,cH,nb); B2S_LAUNCHED(ctx); }
+    else if(mig){ k_slab_flag<<<nb,S_BS,0,s>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,1,hl,hr,ctx->slab_cxa,ctx->slab_cxb,slab_halo_planes(ctx),fM,cM,nb); B2S_LAUNCHED(ctx); }
+    else if(halo){ k_slab_flag<<<nb,S_BS,0,s>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,0,hl,hr,ctx->slab_cxa,ctx->slab_cxb,slab_halo_planes(ctx),fH,cH,nb); B2S_LAUNCHED(ctx); }
     if(mig){ b2s_launch_scan_excl(s,cM,nb+1); b2s_launch_scan_excl(s,cM+nb+1,nb+1); ctx->launches+=2; }
     if(halo){ b2s_launch_scan_excl(s,cH,nb+1); b2s_launch_scan_excl(s,cH+nb+1,nb+1); ctx->launches+=2; }
   }
   k_slab_header<<<1,32,0,s>>>(ctx->step,cM,cH,nb,migcap,halocap,hl? dev_left: NULL,hr? dev_right: NULL,dev_sent_total); B2S_LAUNCHED(ctx);
-  if(n){
+  if(n && mig && halo){
+    k_slab_scatter2<<<nb,S_BS,0,s>>>(ctx->div,fM,fH,cM,cH,nb,lM,lH,a,dev_left,dev_right,migcap,halocap,typecode(B2S_CODE_PERIODIC)); B2S_LAUNCHED(ctx);
+  }
+  else if(n){
     if(mig){ k_slab_scatter_dev<<<nb,S_BS,0,s>>>(ctx->div,fM,cM,nb,lM,a,1,dev_left,dev_right,migcap,NULL,NULL,0,0,typecode(halo? B2S_CODE_PERIODIC: B2S_CODE_OUTIGNORE)); B2S_LAUNCHED(ctx); }
     if(halo){ k_slab_scatter_dev<<<nb,S_BS,0,s>>>(ctx->div,fH,cH,nb,lH,a,0,dev_left,dev_right,halocap,cM+nb,cM+2*nb+1,migcap,lM.bytes,typecode(B2S_CODE_OUTIGNORE)); B2S_LAUNCHED(ctx); }
   }

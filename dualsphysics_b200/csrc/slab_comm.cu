@@ -26,6 +26,7 @@
 #include <nccl.h>
 #include <dlfcn.h>
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 int b2s_slab_pack_msg(b2s_ctx* ctx, char* dev_left, char* dev_right, uint32_t migcap, uint32_t halocap, int mode, uint32_t* dev_sent_total);   // slab.cu
@@ -73,7 +74,11 @@ struct SlabComm {
   uint32_t recut_every; uint64_t nstep;
   std::vector<cudaEvent_t> ev; size_t evused;   // event pairs around the exchanges of the current step
   double ms_exchange; uint64_t nexchange, bytes_sent, nrecut;
+  // B2S_SLAB_PROFILE=1: events at the phase boundaries of a step, ms per phase accumulated at the step's synchronisation
+  bool profile; std::vector<cudaEvent_t> pev; std::vector<int> pid; size_t pused; double pms[16]; uint64_t psteps;
 };
+enum { PH_FORCES=0, PH_REDUCE, PH_INTEGRATE, PH_PACK, PH_TRANSFER, PH_UNPACK, PH_DIVIDE, PH_STEPEND, PH_COUNT };
+static const char* PH_NAME[PH_COUNT]={"forces(+mdbc,bound)","allreduce+dtvariable","integrate(+floating)","exchange:pack","exchange:send/recv","exchange:unpack","celldivide","step_end(damping,motion)"};
 static inline SlabComm* comm_of(b2s_ctx* ctx){ return (SlabComm*)ctx->slab_comm; }
 
 static int comm_alloc(b2s_ctx* ctx, uint32_t max_plane_particles){
@@ -83,11 +88,13 @@ static int comm_alloc(b2s_ctx* ctx, uint32_t max_plane_particles){
   SlabComm* c=new SlabComm();
   c->comm=NULL; c->nccl=false; c->sent_dev=NULL; c->hist_dev=NULL; c->recut_every=0; c->nstep=0; c->evused=0;
   c->ms_exchange=0; c->nexchange=0; c->bytes_sent=0; c->nrecut=0;
+  c->profile=(getenv("B2S_SLAB_PROFILE")!=NULL && getenv("B2S_SLAB_PROFILE")[0]=='1'); c->pused=0; c->psteps=0; for(int k=0;k<16;k++)c->pms[k]=0;
   for(int k=0;k<2;k++){ c->send[k]=NULL; c->recv[k]=NULL; }
-  // halo: scelldiv (mDBC: 2*scelldiv) cell planes per side at the density of the fullest plane, twice over; migrants of one
-  // sub-step are a small fraction of a plane
+  // halo: scelldiv (mDBC: 2*scelldiv) cell planes per side at the density of the fullest plane of the initial state, with half as
+  // much again (WCSPH keeps the density within a few percent; what does not fit raises B2S_ERR_NOMEM at the step's sync);
+  // migrants of one sub-step are a small fraction of a plane
   const uint32_t planes=uint32_t(ctx->prm.scelldiv)*(ctx->prm.tboundary==B2S_BC_MDBC? 2u: 1u);
-  c->halocap=2u*planes*std::max(max_plane_particles,1u)+4096u;
+  c->halocap=(3u*planes*std::max(max_plane_particles,1u))/2u+4096u;
   c->migcap=std::max(4096u,c->halocap/8u);
   c->msg_bytes=b2s_slab_msg_bytes(ctx,c->migcap,c->halocap);
   c->ncx=ctx->prm.domcells[0];
@@ -142,6 +149,7 @@ extern "C" int b2s_slab_comm_free(b2s_ctx* ctx){
   for(int k=0;k<2;k++){ cudaFree(c->send[k]); cudaFree(c->recv[k]); }
   cudaFree(c->sent_dev); cudaFree(c->hist_dev);
   for(cudaEvent_t e:c->ev)cudaEventDestroy(e);
+  for(cudaEvent_t e:c->pev)cudaEventDestroy(e);
   delete c; ctx->slab_comm=NULL;
   return B2S_OK;
 }
@@ -174,6 +182,32 @@ static int ev_collect(b2s_ctx* ctx){   // after a synchronisation: adds up the b
   SlabComm* c=comm_of(ctx);
   for(size_t k=0;k+1<c->evused;k+=2){ float ms=0; if(cudaEventElapsedTime(&ms,c->ev[k],c->ev[k+1])==cudaSuccess)c->ms_exchange+=ms; }
   c->evused=0;
+  return B2S_OK;
+}
+
+// profile: the time since the previous mark is booked to `phase`
+static int ph_mark(b2s_ctx* ctx,int phase){
+  SlabComm* c=comm_of(ctx);
+  if(!c->profile)return B2S_OK;
+  if(c->pused==c->pev.size()){ cudaEvent_t e; B2S_CUDA(ctx,cudaEventCreate(&e)); c->pev.push_back(e); c->pid.push_back(0); }
+  c->pid[c->pused]=phase;
+  B2S_CUDA(ctx,cudaEventRecord(c->pev[c->pused++],ctx->stream));
+  return B2S_OK;
+}
+static void ph_collect(b2s_ctx* ctx){
+  SlabComm* c=comm_of(ctx);
+  if(!c->profile)return;
+  for(size_t k=1;k<c->pused;k++){ float ms=0; if(c->pid[k]>=0 && cudaEventElapsedTime(&ms,c->pev[k-1],c->pev[k])==cudaSuccess)c->pms[c->pid[k]]+=ms; }
+  c->pused=0; c->psteps++;
+}
+// ms per step and phase since b2s_slab_comm_init (B2S_SLAB_PROFILE=1), as text; empty without the profile
+extern "C" int b2s_slab_comm_profile(b2s_ctx* ctx, char* out, uint32_t outlen){
+  if(!ctx || !ctx->slab_comm || !out || !outlen)return B2S_ERR_ARG;
+  SlabComm* c=comm_of(ctx);
+  out[0]=0;
+  if(!c->profile || !c->psteps)return B2S_OK;
+  size_t w=0;
+  for(int k=0;k<PH_COUNT && w+64<outlen;k++)w+=size_t(snprintf(out+w,outlen-w,"%s%s=%.4f",k? ", ": "",PH_NAME[k],c->pms[k]/double(c->psteps)));
   return B2S_OK;
 }
 
@@ -242,7 +276,9 @@ static int slab_divide(b2s_ctx* ctx){
 static int grp_exchange(std::vector<b2s_ctx*>& g, int mode, bool divide){
   FOR_GROUP(g,ev_mark(ctx));
   FOR_GROUP(g,b2s_slab_pack_msg(ctx,comm_of(ctx)->send[0],comm_of(ctx)->send[1],comm_of(ctx)->migcap,comm_of(ctx)->halocap,mode,comm_of(ctx)->sent_dev));
+  FOR_GROUP(g,ph_mark(ctx,PH_PACK));
   { int r=xfer_messages(g); if(r)return r; }
+  FOR_GROUP(g,ph_mark(ctx,PH_TRANSFER));
   for(b2s_ctx* ctx:g){
     B2S_CUDA(ctx,cudaSetDevice(ctx->device));
     SlabComm* c=comm_of(ctx);
@@ -250,13 +286,16 @@ static int grp_exchange(std::vector<b2s_ctx*>& g, int mode, bool divide){
     c->nexchange++;
   }
   FOR_GROUP(g,ev_mark(ctx));
-  if(divide)FOR_GROUP(g,slab_divide(ctx));
+  FOR_GROUP(g,ph_mark(ctx,PH_UNPACK));
+  if(divide){ FOR_GROUP(g,slab_divide(ctx)); FOR_GROUP(g,ph_mark(ctx,PH_DIVIDE)); }
   return B2S_OK;
 }
 static int grp_interaction(std::vector<b2s_ctx*>& g, int interstep){
   FOR_GROUP(g,b2s_slab_forces(ctx,interstep));
+  FOR_GROUP(g,ph_mark(ctx,PH_FORCES));
   { int r=xfer_allreduce(g,buf_dtmax,3,false,true); if(r)return r; }
   FOR_GROUP(g,b2s_dtvariable_impl(ctx,interstep));
+  FOR_GROUP(g,ph_mark(ctx,PH_REDUCE));
   return B2S_OK;
 }
 static int grp_floating(std::vector<b2s_ctx*>& g, bool predictor){
@@ -298,21 +337,26 @@ static int grp_recut(std::vector<b2s_ctx*>& g){
 static int grp_step(std::vector<b2s_ctx*>& g, double* dt_out){
   const bool sym=(g[0]->prm.tstep==B2S_STEP_SYMPLECTIC);
   int r;
+  FOR_GROUP(g,ph_mark(ctx,-1));
   if(sym){
     r=grp_interaction(g,B2S_INTER_SYMPREDICTOR); if(r)return r;
     FOR_GROUP(g,b2s_slab_integrate(ctx,1));
     r=grp_floating(g,true); if(r)return r;
+    FOR_GROUP(g,ph_mark(ctx,PH_INTEGRATE));
     r=grp_exchange(g,3,true); if(r)return r;
     r=grp_interaction(g,B2S_INTER_SYMCORRECTOR); if(r)return r;
     FOR_GROUP(g,b2s_slab_integrate(ctx,2));
     r=grp_floating(g,false); if(r)return r;
+    FOR_GROUP(g,ph_mark(ctx,PH_INTEGRATE));
   }
   else{
     r=grp_interaction(g,B2S_INTER_VERLET); if(r)return r;
     FOR_GROUP(g,b2s_slab_integrate(ctx,0));
     r=grp_floating(g,false); if(r)return r;
+    FOR_GROUP(g,ph_mark(ctx,PH_INTEGRATE));
   }
   FOR_GROUP(g,b2s_slab_step_end_enqueue(ctx));
+  FOR_GROUP(g,ph_mark(ctx,PH_STEPEND));
   r=grp_exchange(g,3,true); if(r)return r;
   SlabComm* c0=comm_of(g[0]);
   for(b2s_ctx* ctx:g)comm_of(ctx)->nstep++;
@@ -320,6 +364,7 @@ static int grp_step(std::vector<b2s_ctx*>& g, double* dt_out){
   // the one synchronisation of the step: exact counts for the next launch bounds, error flags of every kernel of the step
   FOR_GROUP(g,b2s_sync_info(ctx));
   FOR_GROUP(g,ev_collect(ctx));
+  for(b2s_ctx* x:g)ph_collect(x);
   if(dt_out)*dt_out=g[0]->step_h->dt;
   return B2S_OK;
 }

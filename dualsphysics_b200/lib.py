@@ -105,7 +105,7 @@ ABI_SYMBOLS = [
     "b2s_launch_count", "b2s_get_stream", "b2s_set_interaction_variant", "b2s_debug_set_tile_cap", "b2s_slab_config",
     "b2s_slab_histogram", "b2s_slab_set_range", "b2s_slab_drop_ghosts", "b2s_slab_record_bytes", "b2s_slab_pack", "b2s_slab_unpack", "b2s_slab_pack_both", "b2s_slab_unpack_both", "b2s_slab_dt_buffer", "b2s_slab_forces",
     "b2s_slab_apply_dt", "b2s_slab_integrate", "b2s_slab_step_end", "b2s_slab_ft_sums", "b2s_slab_ft_apply", "b2s_slab_get_range",
-    "b2s_slab_comm_id", "b2s_slab_comm_init", "b2s_slab_comm_init_local", "b2s_slab_comm_free", "b2s_slab_comm_set_recut", "b2s_slab_comm_stats",
+    "b2s_slab_comm_id", "b2s_slab_comm_init", "b2s_slab_comm_init_local", "b2s_slab_comm_free", "b2s_slab_comm_set_recut", "b2s_slab_comm_stats", "b2s_slab_comm_profile",
     "b2s_slab_exchange", "b2s_slab_step", "b2s_slab_run_steps", "b2s_slab_recut",
     "b2s_sim_load", "b2s_sim_load_slab", "b2s_sim_slab_connect", "b2s_sim_slab_info", "b2s_sim_free", "b2s_sim_ctx", "b2s_sim_params", "b2s_sim_stats", "b2s_sim_set_dirout", "b2s_sim_save_part", "b2s_sim_run",
     "b2s_host_motionref_write", "b2s_host_xml_stats", "b2s_host_last_error",
@@ -201,6 +201,7 @@ def load_library():
     lib.b2s_slab_comm_free.argtypes = [vp]
     lib.b2s_slab_comm_set_recut.argtypes = [vp, C.c_uint32]
     lib.b2s_slab_comm_stats.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
+    lib.b2s_slab_comm_profile.argtypes = [vp, C.c_char_p, C.c_uint32]
     lib.b2s_slab_exchange.argtypes = [vp]
     lib.b2s_slab_step.argtypes = [vp, C.POINTER(C.c_double)]
     lib.b2s_slab_run_steps.argtypes = [vp, C.c_uint32, C.POINTER(C.c_double)]
@@ -430,6 +431,11 @@ class Context:
         out = (C.c_double * 5)()
         self._chk(self._lib.b2s_slab_comm_stats(self._h, out, int(reset)))
         return out[0], int(out[1]), int(out[2]), int(out[3]), int(out[4])
+
+    def slab_comm_profile(self) -> str:
+        buf = C.create_string_buffer(1024)
+        self._chk(self._lib.b2s_slab_comm_profile(self._h, buf, 1024))
+        return buf.value.decode()
 
     def slab_exchange(self):
         self._chk(self._lib.b2s_slab_exchange(self._h))

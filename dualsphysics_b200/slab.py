@@ -395,6 +395,9 @@ class SlabSimulation:
 
     def profile_report(self):
         """Mean milliseconds per phase since construction (None unless B2S_SLAB_PROFILE=1)."""
+        if self.native:
+            txt = self.ranks[0].ctx.slab_comm_profile()
+            return txt or None
         if not self._prof:
             return None
         self.torch.cuda.synchronize()

@@ -353,6 +353,9 @@ int b2s_slab_comm_init_local(b2s_ctx** ctxs, int nranks, uint32_t max_plane_part
 int b2s_slab_comm_free(b2s_ctx* ctx);
 int b2s_slab_comm_set_recut(b2s_ctx* ctx, uint32_t every_steps);
 int b2s_slab_comm_stats(b2s_ctx* ctx, double* out5, int reset);
+/* B2S_SLAB_PROFILE=1 in the environment: ms per step spent in every phase of b2s_slab_step (CUDA events at the phase boundaries,
+ * collected at the step's synchronisation) as one line of text; empty otherwise. */
+int b2s_slab_comm_profile(b2s_ctx* ctx, char* out, uint32_t outlen);
 int b2s_slab_exchange(b2s_ctx* ctx);
 int b2s_slab_step(b2s_ctx* ctx, double* dt_out);
 int b2s_slab_run_steps(b2s_ctx* ctx, uint32_t nsteps, double* time_out);

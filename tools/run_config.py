@@ -116,7 +116,12 @@ def main():
         secs = float(t.item())
     n1 = total(owned())
     info = ctx.info()
-    out = {"config": a.config, "n_gpus": world, "np_total": n0, "np_after": n1, "casenp": int(p.casenp), "steps": a.steps, "warmup": a.warmup,
+    comm = None
+    if ss is not None and ss.native:
+        ms_x, nx, bytes_x, _, _ = ss.comm_stats()
+        comm = {"t_exposed_comm_ms_per_step_rank0": ms_x / max(len(dts), 1), "exchanges": nx, "bytes_sent_rank0": bytes_x, "phases_ms_per_step_rank0": ss.profile_report()}
+    out = {"slab_step": (None if ss is None else ("library (csrc/slab_comm.cu, NCCL)" if ss.native else "slab.py (torch.distributed)")), "comm": comm,
+           "interaction_variant": 5, "config": a.config, "n_gpus": world, "np_total": n0, "np_after": n1, "casenp": int(p.casenp), "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": secs / a.steps * 1e3, "particle_steps_per_s": n0 * a.steps / secs, "options": options,
            "dt_first": dts[0], "dt_last": dts[-1], "dt_min": min(dts), "timestep": info.timestep, "case_seconds": t_gen,
            "cells": [int(info.ncx), int(info.ncy), int(info.ncz)]}
