@@ -226,7 +226,7 @@ def main():
         ctx = sim.ctx
     else:
         ss = slab.SlabSimulation(case, options=OPTIONS, nranks=world, dist=dist, device=dev,
-                                 recut_every=int(os.environ.get("B2S_RECUT_EVERY", "0")))
+                                 recut_every=int(os.environ.get("B2S_RECUT_EVERY", "50")))   # dynamic load balance on measured time (csrc/slab_comm.cu grp_recut)
         sim = ss.ranks[0].sim
         ctx = ss.ranks[0].ctx
     ctx.set_variant(a.variant)
@@ -278,6 +278,12 @@ def main():
         ms_x, nx, bytes_x, nrecut, _ = ss.comm_stats()
         xbytes = bytes_x
         comm = [ms_x / a.steps, nx / a.steps, float(nrecut)]
+        rep = ss.profile_report()       # B2S_SLAB_PROFILE=1: ms per step and phase of the timed steps, every rank
+        if rep:
+            reps = [None] * world
+            dist.all_gather_object(reps, f"rank {rank} (np {np_total}, fluid {npf}): {rep}")
+            if rank == 0:
+                print("slab phase profile, timed steps:\n  " + "\n  ".join(reps), file=sys.stderr)
     if dist is not None:
         t = torch.tensor([secs, wall], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -461,9 +467,6 @@ def main():
                            "timing": "CUDA events on the kernel stream, max over ranks", "wall_ms_per_step": wall / a.steps * 1e3},
                 "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks}
     if ss is not None:
-        rep = ss.profile_report()
-        if rep and rank == 0:
-            print("slab phase profile (ms per step, rank 0, includes warm-up and e2e steps): " + json.dumps(rep), file=sys.stderr)
         ss.close()
     else:
         sim.close()

@@ -50,6 +50,8 @@ class DamBreakSpec:
     open_axes: str = ""                     # "y", "xy": no tank walls across these axes (periodic cases); the lattice then
                                             # covers [0, n-1] along them so that the period is n*dp
     fluid_vel: tuple = (0.0, 0.0, 0.0)      # initial velocity of the fluid particles
+    two_d: bool = False                     # 2-D case (<data2d value="true">): one lattice plane at y=0, no walls across y,
+                                            # h = coefh*sqrt(2)*dp, particle mass = rho0*dp^2 (GenCase's 2-D conventions)
     params: dict = field(default_factory=dict)   # overrides for <parameters>
     special_xml: str = ""                   # raw xml placed inside <special>
 
@@ -82,13 +84,15 @@ def build_particles(spec: DamBreakSpec) -> dict:
     # -- boundary shell: lattice box [-(nl-1) .. n+(nl-1)] minus the interior, open top
     lo = -(nl - 1)
     ox, oy = "x" in spec.open_axes, "y" in spec.open_axes
+    if spec.two_d:
+        oy, ny = True, 1                    # the single plane j=0
     full = _lattice(0 if ox else lo, nx - 1 if ox else nx + nl - 1, 0 if oy else lo, ny - 1 if oy else ny + nl - 1, lo, nz)
     i, j, k = full[:, 0], full[:, 1], full[:, 2]
     interior = (ox | ((i >= 1) & (i <= nx - 1))) & (oy | ((j >= 1) & (j <= ny - 1))) & (k >= 1)
     fixed = full[~interior]
     # -- fluid column
     fx = min(nx - 1, int(math.floor(spec.fluid[0] / dp + 1e-9)))
-    fy = min(ny - 1, int(math.floor(spec.fluid[1] / dp + 1e-9)))
+    fy = 0 if spec.two_d else min(ny - 1, int(math.floor(spec.fluid[1] / dp + 1e-9)))
     fz = min(nz - 1, int(math.floor(spec.fluid[2] / dp + 1e-9)))
     fluid = _lattice(0 if ox else 1, fx, 0 if oy else 1, fy, 1, fz)
     moving = np.zeros((0, 3), dtype=np.int64)
@@ -134,10 +138,10 @@ def constants(spec: DamBreakSpec, parts: dict) -> dict:
     dp = spec.dp
     g = abs(spec.gravity[2])
     hswl = parts["fz_top"] * dp  # fluid top (z of highest fluid particle) measured from z=0... GenCase uses fluid height
-    h = spec.coefh * math.sqrt(3.0 * dp * dp)
+    h = spec.coefh * math.sqrt((2.0 if spec.two_d else 3.0) * dp * dp)
     cs0 = spec.coefsound * math.sqrt(g * hswl)
     b = cs0 * cs0 * spec.rhop0 / spec.gamma
-    mass = spec.rhop0 * dp ** 3
+    mass = spec.rhop0 * dp ** (2 if spec.two_d else 3)
     return {"dp": dp, "h": h, "b": b, "cs0": cs0, "hswl": hswl, "massfluid": mass, "massbound": mass}
 
 
@@ -175,7 +179,7 @@ def write_case(dirpath: str, name: str, spec: DamBreakSpec) -> dict:
     root = bi4.make_case_item(name, np_total=n, nfixed=nfixed, nmoving=nmoving, nfloat=nfloat,
                               nfluid=nfluid, posmin=posmin, posmax=posmax, dp=dp, h=c["h"], b=c["b"],
                               rhop0=spec.rhop0, gamma=spec.gamma, massbound=c["massbound"],
-                              massfluid=c["massfluid"])
+                              massfluid=c["massfluid"], data2d=bool(spec.two_d), data2dposy=0.0)
     bi4.add_part(root, 0, timestep=0.0, idp=idp, pos=pos, vel=vel, rhop=rhop, posdouble=True,
                  boundnor=boundnor)
     bi4.save(os.path.join(dirpath, name + ".bi4"), root)
@@ -241,7 +245,7 @@ def write_case(dirpath: str, name: str, spec: DamBreakSpec) -> dict:
     x.append(f'      <fluid mkfluid="0" mk="1" begin="{begin}" count="{nfluid}" />')
     x.append('    </particles>')
     x.append('    <constants>')
-    x.append('      <data2d value="false" />')
+    x.append('      <data2d value="true" posy="0" />' if spec.two_d else '      <data2d value="false" />')
     x.append(f'      <gravity x="{spec.gravity[0]!r}" y="{spec.gravity[1]!r}" z="{spec.gravity[2]!r}" />')
     x.append(f'      <cflnumber value="{spec.cfl!r}" />')
     x.append(f'      <gamma value="{spec.gamma!r}" />')

@@ -76,6 +76,8 @@ struct SlabComm {
   double ms_exchange; uint64_t nexchange, bytes_sent, nrecut;
   // B2S_SLAB_PROFILE=1: events at the phase boundaries of a step, ms per phase accumulated at the step's synchronisation
   bool profile; std::vector<cudaEvent_t> pev; std::vector<int> pid; size_t pused; double pms[16]; uint64_t psteps;
+  // measured load of this rank since the last re-cut: ms in its own kernels (everything but the waits inside the collectives)
+  bool timing; double busy_ms; uint64_t busy_steps; float* busy_dev;
 };
 enum { PH_FORCES=0, PH_REDUCE, PH_INTEGRATE, PH_PACK, PH_TRANSFER, PH_UNPACK, PH_DIVIDE, PH_STEPEND, PH_COUNT };
 static const char* PH_NAME[PH_COUNT]={"forces(+mdbc,bound)","allreduce+dtvariable","integrate(+floating)","exchange:pack","exchange:send/recv","exchange:unpack","celldivide","step_end(damping,motion)"};
@@ -89,6 +91,7 @@ static int comm_alloc(b2s_ctx* ctx, uint32_t max_plane_particles){
   c->comm=NULL; c->nccl=false; c->sent_dev=NULL; c->hist_dev=NULL; c->recut_every=0; c->nstep=0; c->evused=0;
   c->ms_exchange=0; c->nexchange=0; c->bytes_sent=0; c->nrecut=0;
   c->profile=(getenv("B2S_SLAB_PROFILE")!=NULL && getenv("B2S_SLAB_PROFILE")[0]=='1'); c->pused=0; c->psteps=0; for(int k=0;k<16;k++)c->pms[k]=0;
+  c->timing=c->profile; c->busy_ms=0; c->busy_steps=0; c->busy_dev=NULL;
   for(int k=0;k<2;k++){ c->send[k]=NULL; c->recv[k]=NULL; }
   // halo: scelldiv (mDBC: 2*scelldiv) cell planes per side at the density of the fullest plane of the initial state, with half as
   // much again (WCSPH keeps the density within a few percent; what does not fit raises B2S_ERR_NOMEM at the step's sync);
@@ -107,6 +110,7 @@ static int comm_alloc(b2s_ctx* ctx, uint32_t max_plane_particles){
   B2S_CUDA(ctx,cudaMalloc((void**)&c->sent_dev,4*sizeof(uint32_t)));
   B2S_CUDA(ctx,cudaMemsetAsync(c->sent_dev,0,4*sizeof(uint32_t),ctx->stream));
   B2S_CUDA(ctx,cudaMalloc((void**)&c->hist_dev,size_t(c->ncx)*4));
+  B2S_CUDA(ctx,cudaMalloc((void**)&c->busy_dev,size_t(2*ctx->slab_nranks)*4));
   ctx->slab_comm=c;
   return B2S_OK;
 }
@@ -147,7 +151,7 @@ extern "C" int b2s_slab_comm_free(b2s_ctx* ctx){
   cudaStreamSynchronize(ctx->stream);
   if(c->nccl && c->comm)g_nccl.CommDestroy(c->comm);
   for(int k=0;k<2;k++){ cudaFree(c->send[k]); cudaFree(c->recv[k]); }
-  cudaFree(c->sent_dev); cudaFree(c->hist_dev);
+  cudaFree(c->sent_dev); cudaFree(c->hist_dev); cudaFree(c->busy_dev);
   for(cudaEvent_t e:c->ev)cudaEventDestroy(e);
   for(cudaEvent_t e:c->pev)cudaEventDestroy(e);
   delete c; ctx->slab_comm=NULL;
@@ -156,6 +160,7 @@ extern "C" int b2s_slab_comm_free(b2s_ctx* ctx){
 extern "C" int b2s_slab_comm_set_recut(b2s_ctx* ctx, uint32_t every_steps){
   if(!ctx || !ctx->slab_comm)return B2S_ERR_ARG;
   comm_of(ctx)->recut_every=every_steps;
+  if(every_steps)comm_of(ctx)->timing=true;      // the re-cut balances MEASURED time: events at the phase boundaries of every step
   return B2S_OK;
 }
 // out[0] ms spent in pack + transfer + unpack (CUDA events on the context's stream, so it includes waiting for a slower
@@ -167,7 +172,7 @@ extern "C" int b2s_slab_comm_stats(b2s_ctx* ctx, double* out5, int reset){
   double* out4=out5;
   { uint32_t h[4]={0,0,0,0}; B2S_CUDA(ctx,cudaSetDevice(ctx->device)); B2S_CUDA(ctx,cudaMemcpyAsync(h,c->sent_dev,16,cudaMemcpyDeviceToHost,ctx->stream)); B2S_CUDA(ctx,cudaStreamSynchronize(ctx->stream)); out5[4]=double(h[2]); }
   out4[0]=c->ms_exchange; out4[1]=double(c->nexchange); out4[2]=double(c->bytes_sent); out4[3]=double(c->nrecut);
-  if(reset){ c->ms_exchange=0; c->nexchange=0; c->bytes_sent=0; c->nrecut=0; }
+  if(reset){ c->ms_exchange=0; c->nexchange=0; c->bytes_sent=0; c->nrecut=0; c->psteps=0; for(int k=0;k<16;k++)c->pms[k]=0; }
   return B2S_OK;
 }
 
@@ -188,7 +193,7 @@ static int ev_collect(b2s_ctx* ctx){   // after a synchronisation: adds up the b
 // profile: the time since the previous mark is booked to `phase`
 static int ph_mark(b2s_ctx* ctx,int phase){
   SlabComm* c=comm_of(ctx);
-  if(!c->profile)return B2S_OK;
+  if(!c->timing)return B2S_OK;
   if(c->pused==c->pev.size()){ cudaEvent_t e; B2S_CUDA(ctx,cudaEventCreate(&e)); c->pev.push_back(e); c->pid.push_back(0); }
   c->pid[c->pused]=phase;
   B2S_CUDA(ctx,cudaEventRecord(c->pev[c->pused++],ctx->stream));
@@ -196,9 +201,15 @@ static int ph_mark(b2s_ctx* ctx,int phase){
 }
 static void ph_collect(b2s_ctx* ctx){
   SlabComm* c=comm_of(ctx);
-  if(!c->profile)return;
-  for(size_t k=1;k<c->pused;k++){ float ms=0; if(c->pid[k]>=0 && cudaEventElapsedTime(&ms,c->pev[k-1],c->pev[k])==cudaSuccess)c->pms[c->pid[k]]+=ms; }
-  c->pused=0; c->psteps++;
+  if(!c->timing)return;
+  for(size_t k=1;k<c->pused;k++){
+    float ms=0;
+    if(c->pid[k]>=0 && cudaEventElapsedTime(&ms,c->pev[k-1],c->pev[k])==cudaSuccess){
+      c->pms[c->pid[k]]+=ms;
+      if(c->pid[k]!=PH_REDUCE && c->pid[k]!=PH_TRANSFER)c->busy_ms+=ms;      // the waits for the other ranks sit in the collectives
+    }
+  }
+  c->pused=0; c->psteps++; c->busy_steps++;
 }
 // ms per step and phase since b2s_slab_comm_init (B2S_SLAB_PROFILE=1), as text; empty without the profile
 extern "C" int b2s_slab_comm_profile(b2s_ctx* ctx, char* out, uint32_t outlen){
@@ -318,6 +329,34 @@ static int grp_recut(std::vector<b2s_ctx*>& g){
   std::vector<uint32_t> h(ncx);
   { b2s_ctx* ctx=g[0]; B2S_CUDA(ctx,cudaSetDevice(ctx->device)); B2S_CUDA(ctx,cudaMemcpyAsync(h.data(),comm_of(ctx)->hist_dev,size_t(ncx)*4,cudaMemcpyDeviceToHost,ctx->stream)); B2S_CUDA(ctx,cudaStreamSynchronize(ctx->stream)); }
   std::vector<uint64_t> work(h.begin(),h.end());
+  { // Feedback from the clock: every rank knows how long its own kernels took per step since the last re-cut.  The work units of
+    // its planes are priced at (its ms) / (its units), so the new cuts balance predicted TIME; the static weights (slab_cuts.h)
+    // only shape the distribution inside a slab.  (A rank full of free-surface fluid is cheaper per particle than one deep inside
+    // the column: measured 1.90 against 1.99 us per fluid particle and interaction at 10M particles per GPU.)
+    std::vector<float> b(size_t(2*n),0.f);
+    bool have=true;
+    for(b2s_ctx* x:g){
+      SlabComm* cx=comm_of(x);
+      std::vector<float> mine(size_t(2*n),0.f);
+      mine[x->slab_rank]=(cx->busy_steps? float(cx->busy_ms/double(cx->busy_steps)): 0.f);
+      mine[n+x->slab_rank]=float(x->slab_cxa);
+      B2S_CUDA(x,cudaSetDevice(x->device));
+      B2S_CUDA(x,cudaMemcpyAsync(cx->busy_dev,mine.data(),size_t(2*n)*4,cudaMemcpyHostToDevice,x->stream));
+      B2S_CUDA(x,cudaStreamSynchronize(x->stream));      // `mine` leaves scope; a re-cut synchronises anyway
+    }
+    { int r=xfer_allreduce(g,[](b2s_ctx* x)->void*{ return (void*)comm_of(x)->busy_dev; },size_t(2*n),true,false); if(r)return r; }
+    { b2s_ctx* ctx=g[0]; B2S_CUDA(ctx,cudaSetDevice(ctx->device)); B2S_CUDA(ctx,cudaMemcpyAsync(b.data(),comm_of(ctx)->busy_dev,size_t(2*n)*4,cudaMemcpyDeviceToHost,ctx->stream)); B2S_CUDA(ctx,cudaStreamSynchronize(ctx->stream)); }
+    for(int r=0;r<n;r++)if(!(b[r]>0.f))have=false;
+    if(have){
+      for(int r=0;r<n;r++){
+        const uint32_t xa=uint32_t(b[n+r]), xb=(r+1<n? uint32_t(b[n+r+1]): ncx);
+        uint64_t units=0; for(uint32_t x=xa;x<xb && x<ncx;x++)units+=h[x];
+        const double price=(units? double(b[r])/double(units): 0.0);           // ms per work unit on rank r
+        for(uint32_t x=xa;x<xb && x<ncx;x++)work[x]=uint64_t(double(h[x])*price*1e9+0.5);
+      }
+    }
+    for(b2s_ctx* x:g){ comm_of(x)->busy_ms=0; comm_of(x)->busy_steps=0; }
+  }
   const uint32_t planes=uint32_t(g[0]->prm.scelldiv)*(g[0]->prm.tboundary==B2S_BC_MDBC? 2u: 1u);
   // the device-counted exchange needs slabs WIDER than the halo
   const std::vector<uint32_t> cuts=b2s_slab_compute_cuts(work,n,planes+1u);
