@@ -245,7 +245,9 @@ def write_case(dirpath: str, name: str, spec: DamBreakSpec) -> dict:
     x.append(f'      <fluid mkfluid="0" mk="1" begin="{begin}" count="{nfluid}" />')
     x.append('    </particles>')
     x.append('    <constants>')
-    x.append('      <data2d value="true" posy="0" />' if spec.two_d else '      <data2d value="false" />')
+    x.append('      <data2d value="true" />' if spec.two_d else '      <data2d value="false" />')
+    if spec.two_d:
+        x.append('      <data2dposy value="0" />')
     x.append(f'      <gravity x="{spec.gravity[0]!r}" y="{spec.gravity[1]!r}" z="{spec.gravity[2]!r}" />')
     x.append(f'      <cflnumber value="{spec.cfl!r}" />')
     x.append(f'      <gamma value="{spec.gamma!r}" />')

@@ -62,6 +62,7 @@ struct b2s_sim {
   std::vector<MotionCfg> motions;
   std::vector<GaugeCfg> gauges;
   std::vector<DampCfg> dampings;
+  double posy2d=0;                                                       // Simulate2DPosY
   int variant=-1;                                                       // -b2svariant (-1: the library default, variant 5)
   unsigned piece=0, npiece=1;                                           // slab rank / ranks: PART files are written as pieces (JPartDataBi4.cpp:99-127)
   std::string svextraparts;                                             // -svextraparts / SaveExtraParts: PARTs that get a PartExtra_XXXX.bi4
@@ -131,7 +132,9 @@ static void load_case(b2s_sim* s,const std::string& options){
   if(!ct)throw std::runtime_error("Case.xml: <execution><constants> not found");
   auto cval=[&](const char* n,bool opt=false,double def=0){ const XmlNode* e=ct->child(n); if(!e){ if(opt)return def; throw std::runtime_error(std::string("Case.xml: constant missing: ")+n); } return todouble(e->attr("value","0")); };
   { const XmlNode* e=ct->child("data2d"); const std::string v=(e? lower(e->attr("value","false")): "false"); p.simulate2d=(v=="true"||v=="1")? 1: 0; }
-  if(p.simulate2d)throw std::runtime_error("2-D cases are not supported by this build");
+  // 2-D (JSph.cpp:646-647): one plane of particles at y=data2dposy; the second component of the acceleration is zeroed
+  // (JSphCpuSingle.cpp:717-724) and the kernel constants are the 2-D ones (b2s_config_finalize)
+  s->posy2d=(p.simulate2d? cval("data2dposy",true,0): 0);
   double g[3]; if(!read_xyz(ct->child("gravity"),g))throw std::runtime_error("Case.xml: gravity missing");
   for(int k=0;k<3;k++)p.gravity[k]=float(g[k]);
   p.cflnumber=cval("cflnumber"); p.gamma=float(cval("gamma")); p.rhopzero=float(cval("rhop0")); p.dp=cval("dp");
@@ -299,6 +302,11 @@ static void load_case(b2s_sim* s,const std::string& options){
   }
   p.casenfixed=cnt[0]; p.casenmoving=cnt[1]; p.casenfloat=cnt[2]; p.casenfluid=cnt[3]; p.casenp=cnt[0]+cnt[1]+cnt[2]+cnt[3];
   if(p.tboundary==B2S_BC_MDBC && p.slipmode>=B2S_SLIP_NOSLIP && p.casenfloat)throw std::runtime_error("mDBC2 (SlipMode 2/3) with floating bodies is not supported by this build");
+  // 2-D: the ghost-node systems of mDBC are 3x3 there (JSphCpu_mdbc.cpp:158,448) and a floating body is locked to the plane
+  // (JSph.cpp:2629-2640): neither is built
+  if(p.simulate2d && p.tboundary==B2S_BC_MDBC)throw std::runtime_error("2-D cases with mDBC are not supported by this build");
+  if(p.simulate2d && p.casenfloat)throw std::runtime_error("2-D cases with floating bodies are not supported by this build");
+  if(p.simulate2d && (p.periactive&2))throw std::runtime_error("Cannot use periodic conditions in Y with 2D simulations");
   { const unsigned np=unsigned(strtoul(pa->attr("np","0").c_str(),NULL,10)), nb=unsigned(strtoul(pa->attr("nb","0").c_str(),NULL,10)), nbf=unsigned(strtoul(pa->attr("nbf","0").c_str(),NULL,10));
     if(np!=p.casenp || nb!=p.casenp-p.casenfluid || nbf!=p.casenfixed)throw std::runtime_error("The amount of particles does not match the header."); }
   // -- gauges (JGaugeSystem::LoadXml "case.execution.special.gauges"): velocity and swl
@@ -497,7 +505,7 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   if(data->get_uint("CaseNp")!=p.casenp || data->get_uint("CaseNfixed")!=p.casenfixed || data->get_uint("CaseNmoving")!=p.casenmoving
      || data->get_uint("CaseNfloat")!=p.casenfloat || data->get_uint("CaseNfluid")!=p.casenfluid)
     throw std::runtime_error("Particle number does not match the configuration of the case.");
-  if(data->get_bool("Data2d"))throw std::runtime_error("Data file does not match the dimension of the case (2D/3D).");
+  if(data->get_bool("Data2d")!=(p.simulate2d!=0))throw std::runtime_error("Data file does not match the dimension of the case (2D/3D).");
   unsigned np=unsigned(part->get_uint("Npok"));
   const Bi4Array* aid=part->array("Idp"); const Bi4Array* apd=part->array("Posd"); const Bi4Array* apf=part->array("Pos");
   const Bi4Array* avel=part->array("Vel"); const Bi4Array* arho=part->array("Rhop"); const Bi4Array* anor=part->array("BoundNor");
@@ -793,7 +801,7 @@ static void save_part(b2s_sim* s){
   const double zero3[3]={0,0,0};
   const bool pieces=(s->npiece>1);   // one piece per slab rank: list files that need the whole case are left to single-GPU runs
   d.set_uint("Piece",s->piece); d.set_uint("Npiece",s->npiece); d.set_text("RunCode",s->runcode); d.set_text("Date",s->date);
-  d.set_text("AppName","b200sph v0.1 (DualSPHysics v5.4 case interface)"); d.set_text("CaseName",s->casename); d.set_bool("Data2d",p.simulate2d!=0); d.set_double("Data2dPosY",0);
+  d.set_text("AppName","b200sph v0.1 (DualSPHysics v5.4 case interface)"); d.set_text("CaseName",s->casename); d.set_bool("Data2d",p.simulate2d!=0); d.set_double("Data2dPosY",s->posy2d);
   d.set_double3("MapPosMin",p.maprealposmin); d.set_double3("MapPosMax",p.maprealposmax);
   d.set_int("PeriMode",p.periactive); d.set_double3("PeriXinc",(p.periactive&1)? p.perixinc: zero3); d.set_double3("PeriYinc",(p.periactive&2)? p.periyinc: zero3); d.set_double3("PeriZinc",(p.periactive&4)? p.perizinc: zero3);   // TpPeriMode = axis bit mask (DualSphDef.h)
   d.set_int("AxisDiv",0);
@@ -935,7 +943,7 @@ static void save_part(b2s_sim* s){
     Bi4Item h("JPartDataHead");
     h.set_uint("FmtVersion",180324);
     h.set_text("AppName","b200sph v0.1 (DualSPHysics v5.4 case interface)"); h.set_text("Date",s->date); h.set_text("RunCode",s->runcode);
-    h.set_text("CaseName",s->casename); h.set_bool("Data2d",p.simulate2d!=0); h.set_double("Data2dPosY",0);
+    h.set_text("CaseName",s->casename); h.set_bool("Data2d",p.simulate2d!=0); h.set_double("Data2dPosY",s->posy2d);
     h.set_uint("Npiece",s->npiece); h.set_uint("FirstPart",0);
     h.set_double3("CasePosMin",s->caseposmin); h.set_double3("CasePosMax",s->caseposmax); h.set_bool("NpDynamic",false); h.set_bool("ReuseIds",false);
     h.set_double3("MapPosMin",p.maprealposmin); h.set_double3("MapPosMax",p.maprealposmax);

@@ -180,11 +180,12 @@ __global__ void __launch_bounds__(S_BS) k_slab_scatter2(const DivState* __restri
   }
 }
 __global__ void k_slab_header(StepState* st, const uint32_t* __restrict__ cM, const uint32_t* __restrict__ cH, uint32_t nb, uint32_t migcap, uint32_t halocap,
-  char* left, char* right, uint32_t* sent_total)
+  char* left, char* right, uint32_t* sent_total, int strict)
 {
   if(threadIdx.x||blockIdx.x)return;
   const uint32_t ml=(cM? cM[nb]: 0u), mr=(cM? cM[2*nb+1]: 0u), hl=(cH? cH[nb]: 0u), hr=(cH? cH[2*nb+1]: 0u);
-  if(ml>migcap || mr>migcap || hl>halocap || hr>halocap)st->error=B2S_ERR_NOMEM;
+  // strict: what does not fit is an error (a step cannot go on without it); otherwise (re-cut rounds) it travels in the next round
+  if(strict && (ml>migcap || mr>migcap || hl>halocap || hr>halocap))st->error=B2S_ERR_NOMEM;
   if(left){ uint32_t* h=reinterpret_cast<uint32_t*>(left); h[0]=min(ml,migcap); h[1]=min(hl,halocap); h[2]=0; h[3]=0; }
   if(right){ uint32_t* h=reinterpret_cast<uint32_t*>(right); h[0]=min(mr,migcap); h[1]=min(hr,halocap); h[2]=0; h[3]=0; }
   if(sent_total){ sent_total[0]=ml+mr; sent_total[1]=hl+hr; sent_total[2]+=ml+mr; }   // [2]: migrants since b2s_slab_comm_init
@@ -434,7 +435,7 @@ extern "C" int b2s_slab_dt_buffer(b2s_ctx* ctx, void** dev_u32x3){
 // ---- device-counted exchange: pack / unpack without a host synchronisation (driven by slab_comm.cu) -----------------------
 // mode bit0: migrants, bit1: halos.  With both, a migrant stays on the sender as a halo ghost of its new owner (merged exchange,
 // see b2s_slab_pack_both); migrants alone (re-cut rounds) are dropped by the sender's next divide.
-int b2s_slab_pack_msg(b2s_ctx* ctx, char* dev_left, char* dev_right, uint32_t migcap, uint32_t halocap, int mode, uint32_t* dev_sent_total){
+int b2s_slab_pack_msg(b2s_ctx* ctx, char* dev_left, char* dev_right, uint32_t migcap, uint32_t halocap, int mode, uint32_t* dev_sent_total, int strict){
   cudaStream_t s=ctx->stream;
   const uint32_t n=ctx->np_host;
   const int hl=(ctx->slab_rank>0), hr=(ctx->slab_rank<ctx->slab_nranks-1);
@@ -455,7 +456,7 @@ int b2s_slab_pack_msg(b2s_ctx* ctx, char* dev_left, char* dev_right, uint32_t mi
     if(mig){ b2s_launch_scan_excl(s,cM,nb+1); b2s_launch_scan_excl(s,cM+nb+1,nb+1); ctx->launches+=2; }
     if(halo){ b2s_launch_scan_excl(s,cH,nb+1); b2s_launch_scan_excl(s,cH+nb+1,nb+1); ctx->launches+=2; }
   }
-  k_slab_header<<<1,32,0,s>>>(ctx->step,cM,cH,nb,migcap,halocap,hl? dev_left: NULL,hr? dev_right: NULL,dev_sent_total); B2S_LAUNCHED(ctx);
+  k_slab_header<<<1,32,0,s>>>(ctx->step,cM,cH,nb,migcap,halocap,hl? dev_left: NULL,hr? dev_right: NULL,dev_sent_total,strict); B2S_LAUNCHED(ctx);
   if(n && mig && halo){
     k_slab_scatter2<<<nb,S_BS,0,s>>>(ctx->div,fM,fH,cM,cH,nb,lM,lH,a,dev_left,dev_right,migcap,halocap,typecode(B2S_CODE_PERIODIC)); B2S_LAUNCHED(ctx);
   }
@@ -470,6 +471,8 @@ int b2s_slab_pack_msg(b2s_ctx* ctx, char* dev_left, char* dev_right, uint32_t mi
 uint64_t b2s_slab_msg_bytes(b2s_ctx* ctx, uint32_t migcap, uint32_t halocap){
   return uint64_t(B2S_SLAB_HDR)+uint64_t(migcap)*slab_layout(ctx,1).bytes+uint64_t(halocap)*slab_layout(ctx,0).bytes;
 }
+// migrant records a message of msg_bytes can carry when it carries nothing else (re-cut rounds)
+uint32_t b2s_slab_migrants_per_msg(b2s_ctx* ctx, uint64_t msg_bytes){ return uint32_t((msg_bytes-B2S_SLAB_HDR)/slab_layout(ctx,1).bytes); }
 int b2s_slab_unpack_msg(b2s_ctx* ctx, const char* dev_msg, uint32_t migcap, uint32_t halocap){
   const uint32_t nmax=migcap+halocap;
   k_slab_unpack_msg<<<b2s_blocks(nmax,S_BS),S_BS,0,ctx->stream>>>(ctx->div,ctx->step,dev_msg,slab_layout(ctx,1),slab_layout(ctx,0),slab_arrays(ctx),ctx->cap,ctx->cte); B2S_LAUNCHED(ctx);

@@ -29,7 +29,8 @@
 #include <cstdlib>
 #include <vector>
 
-int b2s_slab_pack_msg(b2s_ctx* ctx, char* dev_left, char* dev_right, uint32_t migcap, uint32_t halocap, int mode, uint32_t* dev_sent_total);   // slab.cu
+int b2s_slab_pack_msg(b2s_ctx* ctx, char* dev_left, char* dev_right, uint32_t migcap, uint32_t halocap, int mode, uint32_t* dev_sent_total, int strict);   // slab.cu
+uint32_t b2s_slab_migrants_per_msg(b2s_ctx* ctx, uint64_t msg_bytes);
 int b2s_slab_unpack_msg(b2s_ctx* ctx, const char* dev_msg, uint32_t migcap, uint32_t halocap);
 uint64_t b2s_slab_msg_bytes(b2s_ctx* ctx, uint32_t migcap, uint32_t halocap);
 int b2s_dtvariable_impl(b2s_ctx* ctx, int interstep);       // forces.cu
@@ -285,15 +286,18 @@ static int slab_divide(b2s_ctx* ctx){
 
 // migrants (+ halos) to the neighbours, then the cell divide with the ghosts in place
 static int grp_exchange(std::vector<b2s_ctx*>& g, int mode, bool divide){
+  // migrants alone (re-cut rounds) may fill the whole message, and what does not fit waits for the next round
+  const bool recutround=(mode==1);
+  const uint32_t migcap=(recutround? b2s_slab_migrants_per_msg(g[0],comm_of(g[0])->msg_bytes): comm_of(g[0])->migcap), halocap=(recutround? 0u: comm_of(g[0])->halocap);
   FOR_GROUP(g,ev_mark(ctx));
-  FOR_GROUP(g,b2s_slab_pack_msg(ctx,comm_of(ctx)->send[0],comm_of(ctx)->send[1],comm_of(ctx)->migcap,comm_of(ctx)->halocap,mode,comm_of(ctx)->sent_dev));
+  FOR_GROUP(g,b2s_slab_pack_msg(ctx,comm_of(ctx)->send[0],comm_of(ctx)->send[1],migcap,halocap,mode,comm_of(ctx)->sent_dev,recutround? 0: 1));
   FOR_GROUP(g,ph_mark(ctx,PH_PACK));
   { int r=xfer_messages(g); if(r)return r; }
   FOR_GROUP(g,ph_mark(ctx,PH_TRANSFER));
   for(b2s_ctx* ctx:g){
     B2S_CUDA(ctx,cudaSetDevice(ctx->device));
     SlabComm* c=comm_of(ctx);
-    for(int k=0;k<2;k++)if(c->recv[k]){ int r=b2s_slab_unpack_msg(ctx,c->recv[k],c->migcap,c->halocap); if(r)return r; }
+    for(int k=0;k<2;k++)if(c->recv[k]){ int r=b2s_slab_unpack_msg(ctx,c->recv[k],migcap,halocap); if(r)return r; }
     c->nexchange++;
   }
   FOR_GROUP(g,ev_mark(ctx));
@@ -361,9 +365,11 @@ static int grp_recut(std::vector<b2s_ctx*>& g){
   // the device-counted exchange needs slabs WIDER than the halo
   const std::vector<uint32_t> cuts=b2s_slab_compute_cuts(work,n,planes+1u);
   for(b2s_ctx* ctx:g){ int r=b2s_slab_set_range(ctx,cuts[ctx->slab_rank],cuts[ctx->slab_rank+1]); if(r)return r; }
+  // a round moves what one message holds one neighbour hop further; no divide in between (arrivals are appended with their cell
+  // and a normal code, so the next round's flags see them; what left is marked and skipped)
   for(int round=0;;round++){
-    if(round>n)return b2s_fail(g[0],B2S_ERR_STATE,"re-cut: migrants left after %d rounds",n);
-    { int r=grp_exchange(g,1,true); if(r)return r; }
+    if(round>64+n)return b2s_fail(g[0],B2S_ERR_STATE,"re-cut: migrants left after %d rounds",round);
+    { int r=grp_exchange(g,1,false); if(r)return r; }
     { int r=xfer_allreduce(g,buf_sent,2,false,false); if(r)return r; }
     uint32_t moved[2]={0,0};
     { b2s_ctx* ctx=g[0]; B2S_CUDA(ctx,cudaSetDevice(ctx->device)); B2S_CUDA(ctx,cudaMemcpyAsync(moved,comm_of(ctx)->sent_dev,8,cudaMemcpyDeviceToHost,ctx->stream)); B2S_CUDA(ctx,cudaStreamSynchronize(ctx->stream)); }

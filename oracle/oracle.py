@@ -37,7 +37,7 @@ class Cte(C.Structure):
         ("domposmin", C.c_double * 3), ("maprealposmin", C.c_double * 3), ("maprealsize", C.c_double * 3),
         ("domcellcode", C.c_uint32), ("domcells", C.c_uint32 * 3),
         ("shiftmode", C.c_int32), ("shiftcoef", C.c_float), ("shifttfs", C.c_float), ("dp", C.c_float),
-        ("periactive", C.c_int32), ("pad0", C.c_int32), ("perinc", (C.c_double * 3) * 3),
+        ("periactive", C.c_int32), ("simulate2d", C.c_int32), ("perinc", (C.c_double * 3) * 3),
         ("mapposmin", C.c_double * 3), ("mapposmax", C.c_double * 3),
     ]
 
@@ -97,6 +97,7 @@ def cte_from_params(p) -> Cte:
     c.domcellcode = p.domcellcode
     c.shiftmode, c.shiftcoef, c.shifttfs, c.dp = p.shiftmode, p.shiftcoef, p.shifttfs, p.dp
     c.periactive = p.periactive
+    c.simulate2d = int(getattr(p, "simulate2d", 0))
     for k in range(3):
         c.perinc[0][k], c.perinc[1][k], c.perinc[2][k] = p.perixinc[k], p.periyinc[k], p.perizinc[k]
         c.mapposmin[k], c.mapposmax[k] = p.map_posmin[k], p.map_posmax[k]

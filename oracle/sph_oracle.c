@@ -53,7 +53,7 @@ typedef struct orc_cte {
   uint32_t domcellcode, domcells[3];
   int32_t shiftmode;               /* TpShifting 0-3 (JSph.cpp:744-758) */
   float shiftcoef, shifttfs, dp;   /* ShiftCoef, ShiftTFS, float(Dp) */
-  int32_t periactive, pad0;        /* periodic axes: bit0 X, bit1 Y, bit2 Z (JSph::PeriActive) */
+  int32_t periactive, simulate2d;  /* periodic axes: bit0 X, bit1 Y, bit2 Z (JSph::PeriActive); Simulate2D (JSph.cpp:646) */
   double perinc[3][3];             /* PeriXinc, PeriYinc, PeriZinc (JSph.cpp:2186-2188) */
   double mapposmin[3], mapposmax[3]; /* Map_PosMin/Max: the real map widened by KernelSize on periodic axes (JSph.cpp:2191-2195) */
 } orc_cte;
@@ -383,6 +383,7 @@ int orc_interaction(const orc_cte* c, const orc_div* d, const uint32_t* begincel
     if(c->tvisco==2)sps_tau(c,np-npb,npb,velrho,s2,tau);
   }
   if(d->npbok)forces_bound(c,d,begincell,dcell,pos,velrho,code,ftomassp,&viscdt,ar);
+  if(c->simulate2d)for(uint32_t p=npb;p<np;p++)ace[3*(size_t)p+1]=0.f;                   /* JSphCpuSingle.cpp:717-724 */
   if(c->tdensity!=0)for(uint32_t p=npb;p<np;p++)if(delta[p]!=FLT_MAX)ar[p]+=delta[p];   /* JSphCpuSingle.cpp:723-731 */
   { /* ComputeAceMaxSeq (JSphCpuSingle.cpp:793-805) */
     float am=0; for(uint32_t p=npb;p<np;p++){ if(c->periactive && CODE_SPECIAL(code[p])!=0)continue;   /* ComputeAceMaxSeq<checkcode> with periodic */
@@ -551,7 +552,7 @@ void orc_shifting(const orc_cte* c, const orc_div* d, const uint32_t* begincell,
   const float* velrho, const typecode* code, const float* ftomassp, double dt, float* shiftpos)
 {
   const double coefumagn=dt*(double)c->shiftcoef*(double)c->kernelh;
-  const double coeftfs=3.0-(double)c->shifttfs;
+  const double coeftfs=(c->simulate2d? 2.0: 3.0)-(double)c->shifttfs;   /* JSphShifting.cpp:400 */
   const float maxdist=(float)((double)c->dp*0.1);
   memset(shiftpos,0,sizeof(float)*4*(size_t)d->np);
   #pragma omp parallel for schedule(guided)

@@ -50,6 +50,8 @@ def params_from_case(casepath: str, options: dict | None = None):
     val = lambda n: float(ct.find(n).get("value"))  # noqa: E731
     p.cflnumber, p.gamma, p.rhopzero, p.dp = val("cflnumber"), val("gamma"), val("rhop0"), val("dp")
     p.kernelh, p.cteb, p.massbound, p.massfluid = val("h"), val("b"), val("massbound"), val("massfluid")
+    d2 = ct.find("data2d")
+    p.simulate2d = 1 if (d2 is not None and d2.get("value", "false").lower() in ("true", "1")) else 0
     p.tkernel = int(prm.get("Kernel", 2))
     p.tstep = int(prm.get("StepAlgorithm", 1))
     p.verletsteps = int(prm.get("VerletSteps", 40))

@@ -58,7 +58,8 @@ def compare(gn, gf, floor):
     return e
 
 
-def main():
+def main(names=None):
+    """names: only these fixtures; their records replace the old ones in profiles/ref_noise_r02.json, the others are kept."""
     if not os.path.exists(NOFM):
         raise SystemExit("build it first: make -C oracle -j6 refnofm")
     orc_probe = orc.REF_PROBE
@@ -66,6 +67,8 @@ def main():
     jobs = [(name, kw, opts, nsteps, keep, None) for name, (kw, opts, nsteps, keep) in make_golden.specs().items()]
     jobs.append(("c1_170k_bench_half", dict(dp=0.0085), make_golden_large.OPTS, 10, make_golden_large.KEEP, "fresh"))
     for name, kw, opts, nsteps, keep, mode in jobs:
+        if names and name not in names:
+            continue
         with tempfile.TemporaryDirectory() as td:
             casegen.write_case(td, "Case", casegen.DamBreakSpec(**kw))
             xml = open(os.path.join(td, "Case.xml")).read()
@@ -93,6 +96,9 @@ def main():
                 e = compare(gn, gf, rho0 * cs0 / h * 1e-4)
                 records.append({"key": name, "dump": tag, **e})
                 print(name, tag, json.dumps(e), flush=True)
+    outpath = os.path.join(ROOT, "profiles", "ref_noise_r02.json")
+    if names and os.path.exists(outpath):
+        records = [r for r in json.load(open(outpath))["records"] if r["key"] not in names] + records
     agg = {}
     for r in records:
         for k, v in r.items():
@@ -101,10 +107,10 @@ def main():
     out = {"what": "max difference per field between two builds of the unmodified reference CPU solver (g++ -O3 -fopenmp with and "
                    "without -ffast-math) on the parity fixtures; relative to max|field| (ar: floor rho0*cs0/h*1e-4; pos absolute in m); "
                    "tools/measure_ref_noise.py", "max_over_fixtures": agg, "records": records}
-    with open(os.path.join(ROOT, "profiles", "ref_noise_r02.json"), "w") as f:
+    with open(outpath, "w") as f:
         json.dump(out, f, indent=1)
     print("max over fixtures:", json.dumps(agg))
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:])
