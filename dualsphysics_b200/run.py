@@ -64,6 +64,9 @@ def main(argv=None) -> int:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ss = slab.SlabSimulation(case, options=" ".join(options), nranks=world, dist=dist, device=local)
     ss.set_dirout(dirout)
+    if rank == 0 and world > 1:
+        print(f"b200sph x{world}: slab step {'inside the library (NCCL from C++)' if ss.native else 'driven by slab.py (torch.distributed)'}; "
+              "PART files are written as pieces; PartOut / PartMotionRef / PartExtra are not written in multi-GPU runs and gauges are refused")
     ctx = ss.ranks[0].ctx
     t = ctx.info().timestep
     ss.save_part()
