@@ -14,6 +14,8 @@
 // reference's fluid-only divide because its boundary block is already in cell order (JCellDivGpuSingle.cpp:193-197).
 #include "b2s_internal.h"
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include <cuda_fp16.h>
 
 #define DIV_BS 256
@@ -355,45 +357,58 @@ struct ReorderArgs {
 };
 
 
-__global__ void __launch_bounds__(DIV_BS) k_reorder(const DivState* __restrict__ ds, StepState* st, const uint32_t* __restrict__ sortpart,
+// PPT particles per thread (independent gathers in flight), PAIRH: the FP16 copy of a PAIR of particles is one 16-byte store by its
+// even lane (partner values through a shuffle) instead of three 2-byte stores per particle into a sector that is never filled.
+template<int PPT,bool PAIRH> __global__ void __launch_bounds__(DIV_BS) k_reorder(const DivState* __restrict__ ds, StepState* st, const uint32_t* __restrict__ sortpart,
   ReorderArgs a, const __grid_constant__ DevCte cte)
 {
-  const uint32_t p=blockIdx.x*blockDim.x+threadIdx.x;
   const uint32_t n=ds->nptot;
   float v2=0.f;
-  if(p<n){
-    const uint32_t s=sortpart[p];
-    const uint32_t id=a.src.idp[s];
-    const typecode cod=a.src.code[s];
-    const uint32_t dc=a.src.dcell[s];
-    const double2 xy=a.src.posxy[s];
-    const double z=a.src.posz[s];
-    const float4 vr=a.src.velrho[s];
-    a.dst.idp[p]=id; a.dst.code[p]=cod; a.dst.dcell[p]=dc; a.dst.posxy[p]=xy; a.dst.posz[p]=z; a.dst.velrho[p]=vr;
-    if(a.pre_v_s){ a.pre_xy_d[p]=a.pre_xy_s[s]; a.pre_z_d[p]=a.pre_z_s[s]; a.pre_v_d[p]=a.pre_v_s[s]; }
-    if(a.m1_s)a.m1_d[p]=a.m1_s[s];
-    if(a.tau_s){
-      const float2* ts=(const float2*)(a.tau_s+size_t(s)*6); float2* td=(float2*)(a.tau_d+size_t(p)*6);
-      td[0]=ts[0]; td[1]=ts[1]; td[2]=ts[2];
-    }
-    if(a.nor_s)a.nor_d[p]=a.nor_s[s];
-    if(a.mace_s)a.mace_d[p]=a.mace_s[s];
-    if(p<ds->np){
-      // position relative to the origin of the particle's own cell (x: of its block of cells) (PosCell idea, JSphGpuSimple_ker.cu:46-57)
-      const uint32_t cx=B2S_DCEL_CELLX(cte.domcellcode,dc), cy=B2S_DCEL_CELLY(cte.domcellcode,dc), cz=B2S_DCEL_CELLZ(cte.domcellcode,dc);
-      float4 pp;
-      pp.x=float((xy.x-cte.domposmin[0])-cte.scell_d*double((cx>>B2S_XBLK)<<B2S_XBLK));   // block-relative x (b2s_internal.h)
-      pp.y=float((xy.y-cte.domposmin[1])-cte.scell_d*double(cy));
-      pp.z=float((z   -cte.domposmin[2])-cte.scell_d*double(cz));
-      pp.w=b2s_press(vr.w,cte);
-      a.posp[p]=pp;
-      { // FP16 pre-filter copy in cell units (pair-interleaved, see b2s_internal.h posh)
-        __half* h=reinterpret_cast<__half*>(a.posh+(p>>1))+(p&1u);
-        const float ovs=1.0f/cte.scell;
-        h[0]=__float2half_rn(pp.x*ovs); h[2]=__float2half_rn(pp.y*ovs); h[4]=__float2half_rn(pp.z*ovs);
+  #pragma unroll
+  for(int it=0;it<PPT;it++){
+    const uint32_t p=(blockIdx.x*PPT+it)*blockDim.x+threadIdx.x;
+    uint32_t hx=0,hy=0,hz=0; bool live=false;
+    if(p<n){
+      const uint32_t s=sortpart[p];
+      const uint32_t id=a.src.idp[s];
+      const typecode cod=a.src.code[s];
+      const uint32_t dc=a.src.dcell[s];
+      const double2 xy=a.src.posxy[s];
+      const double z=a.src.posz[s];
+      const float4 vr=a.src.velrho[s];
+      a.dst.idp[p]=id; a.dst.code[p]=cod; a.dst.dcell[p]=dc; a.dst.posxy[p]=xy; a.dst.posz[p]=z; a.dst.velrho[p]=vr;
+      if(a.pre_v_s){ a.pre_xy_d[p]=a.pre_xy_s[s]; a.pre_z_d[p]=a.pre_z_s[s]; a.pre_v_d[p]=a.pre_v_s[s]; }
+      if(a.m1_s)a.m1_d[p]=a.m1_s[s];
+      if(a.tau_s){
+        const float2* ts=(const float2*)(a.tau_s+size_t(s)*6); float2* td=(float2*)(a.tau_d+size_t(p)*6);
+        td[0]=ts[0]; td[1]=ts[1]; td[2]=ts[2];
       }
-      if((p>=ds->npb || cte.dt_allparticles) && B2S_CODE_ISNORMAL(cod))v2=vr.x*vr.x+vr.y*vr.y+vr.z*vr.z;   // ghosts (slab halos) excluded
-      if(a.ridp && id>=a.casenfixed && id<a.casenbound && B2S_CODE_ISNORMAL(cod))a.ridp[id-a.casenfixed]=p;   // never a duplicate (CalcRidp with PeriActive, JSphCpu.cpp)
+      if(a.nor_s)a.nor_d[p]=a.nor_s[s];
+      if(a.mace_s)a.mace_d[p]=a.mace_s[s];
+      if(p<ds->np){
+        // position relative to the origin of the particle's own cell (x: of its block of cells) (PosCell idea, JSphGpuSimple_ker.cu:46-57)
+        const uint32_t cx=B2S_DCEL_CELLX(cte.domcellcode,dc), cy=B2S_DCEL_CELLY(cte.domcellcode,dc), cz=B2S_DCEL_CELLZ(cte.domcellcode,dc);
+        float4 pp;
+        pp.x=float((xy.x-cte.domposmin[0])-cte.scell_d*double((cx>>B2S_XBLK)<<B2S_XBLK));   // block-relative x (b2s_internal.h)
+        pp.y=float((xy.y-cte.domposmin[1])-cte.scell_d*double(cy));
+        pp.z=float((z   -cte.domposmin[2])-cte.scell_d*double(cz));
+        pp.w=b2s_press(vr.w,cte);
+        a.posp[p]=pp;
+        { // FP16 pre-filter copy in cell units (pair-interleaved, see b2s_internal.h posh)
+          const float ovs=1.0f/cte.scell;
+          const __half h0=__float2half_rn(pp.x*ovs), h1=__float2half_rn(pp.y*ovs), h2=__float2half_rn(pp.z*ovs);
+          if(PAIRH){ hx=__half_as_ushort(h0); hy=__half_as_ushort(h1); hz=__half_as_ushort(h2); live=true; }
+          else{ __half* h=reinterpret_cast<__half*>(a.posh+(p>>1))+(p&1u); h[0]=h0; h[2]=h1; h[4]=h2; }
+        }
+        if((p>=ds->npb || cte.dt_allparticles) && B2S_CODE_ISNORMAL(cod))v2=fmaxf(v2,vr.x*vr.x+vr.y*vr.y+vr.z*vr.z);   // ghosts (slab halos) excluded
+        if(a.ridp && id>=a.casenfixed && id<a.casenbound && B2S_CODE_ISNORMAL(cod))a.ridp[id-a.casenfixed]=p;   // never a duplicate (CalcRidp with PeriActive, JSphCpu.cpp)
+      }
+    }
+    if(PAIRH){
+      // lanes (2k, 2k+1) hold particles (p, p+1) of one 16-byte record (p is even for even lanes: blockDim is a multiple of 32)
+      const uint32_t ox=__shfl_down_sync(0xffffffffu,hx,1), oy=__shfl_down_sync(0xffffffffu,hy,1), oz=__shfl_down_sync(0xffffffffu,hz,1);
+      const bool olive=__shfl_down_sync(0xffffffffu,live? 1: 0,1)!=0;
+      if(live && !(threadIdx.x&1))a.posh[p>>1]=make_uint4(hx|((olive? ox: 0u)<<16),hy|((olive? oy: 0u)<<16),hz|((olive? oz: 0u)<<16),0u);
     }
   }
   // block max -> one atomic per warp (values >=0 so uint order == float order)
@@ -497,7 +512,15 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   a.ridp=(ctx->prm.casenmoving+ctx->prm.casenfloat? ctx->ridp: NULL);
   a.casenfixed=ctx->prm.casenfixed; a.casenbound=ctx->prm.casenbound;
   if(a.ridp)B2S_CUDA(ctx,cudaMemsetAsync(ctx->ridp,0xff,size_t(ctx->prm.casenmoving+ctx->prm.casenfloat)*4,s));
-  k_reorder<<<b2s_blocks(nptot,DIV_BS),DIV_BS,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte); B2S_LAUNCHED(ctx);
+  { // B2S_REORDER=<particles per thread 1|2><pair store 0|1>[,threads]: experiment switch of tools/gpu_job.sh reorder_ab
+    static int mode=-1, bs=DIV_BS;
+    if(mode<0){ const char* e=getenv("B2S_REORDER"); mode=(e? atoi(e): 10); if(e && strchr(e,','))bs=atoi(strchr(e,',')+1); if(bs<32||bs>DIV_BS||(bs&31))bs=DIV_BS; }
+    const int ppt=(mode/10==2? 2: 1); const bool pairh=(mode%10)!=0;
+    const unsigned gb=b2s_blocks(nptot,unsigned(bs*ppt));
+    if(ppt==2){ if(pairh)k_reorder<2,true><<<gb,bs,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte); else k_reorder<2,false><<<gb,bs,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte); }
+    else{ if(pairh)k_reorder<1,true><<<gb,bs,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte); else k_reorder<1,false><<<gb,bs,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte); }
+    B2S_LAUNCHED(ctx);
+  }
   { PartSet t=ctx->cur; ctx->cur=ctx->alt; ctx->alt=t; }
   if(ctx->out_dev){ k_collect_out<<<32,DIV_BS,0,s>>>(ctx->div,ctx->cur,(OutRec*)ctx->out_dev,ctx->out_count_dev,ctx->out_cap); B2S_LAUNCHED(ctx); }
   if(ctx->pre_active){

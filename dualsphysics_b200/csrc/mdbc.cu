@@ -11,7 +11,9 @@
 //
 // B200 design (the reference runs one thread per boundary particle over ~250 neighbours with 20 running sums):
 //   * ONE WARP per ghost node.  Every row of neighbour cells (fixed y,z) is one contiguous range of the cell-sorted arrays, so the
-//     32 lanes stride over the row: coalesced 128-bit loads of posp/velrho, the begin-table reads are warp-uniform broadcasts.
+//     32 lanes stride over the row: coalesced 128-bit loads of posp, the begin-table reads are warp-uniform broadcasts.
+//   * Test first, evaluate later: the hits of the rows are compacted through a per-warp queue in shared memory, so the kernel
+//     function and the FP64 accumulations run on 32 hits at a time (a quarter of the candidates are hits).
 //   * Every lane keeps the 20 (mDBC2: 25) partial sums in FP64 registers; five xor-shuffle rounds leave the totals in all lanes.
 //   * The 4x4 system is solved by Gaussian elimination with row pivoting on [A | b] (mDBC2: [A | I], its condition number needs
 //     the inverse), FP64, fully unrolled in registers, uniform across the warp; the determinant the reference thresholds on is
@@ -72,10 +74,16 @@ template<bool MDBC2> struct GhostSums {
   }
 };
 
-// The lanes of the warp stride over every neighbour row of g.  sgn = +1: the matrix holds (r_g - r_j) (mDBC), -1: (r_j - r_g) (mDBC2),
-// which is how the two reference kernels orient their first-order terms.
+// The lanes of the warp stride over every neighbour row of g and first only TEST their candidate (one 128-bit position load, FP32
+// distance).  About a quarter of the candidates of the window lie inside the kernel sphere, so the hits are compacted through a small
+// per-warp queue in shared memory (ballot + prefix count) and the expensive part -- kernel, 20 to 25 FP64 accumulations -- always
+// runs on 32 hits at once instead of on the few lanes of a row that happened to hit.
+// sgn = +1: the matrix holds (r_g - r_j) (mDBC), -1: (r_j - r_g) (mDBC2), which is how the two reference kernels orient their
+// first-order terms.
+#define M_QLEN 64                // queue entries per warp: at most 31 waiting + 32 new
 template<bool MDBC2> __device__ __forceinline__ void ghost_walk(const DevCte& c,const DivState* ds,const uint32_t* __restrict__ begt,
-  const float4* __restrict__ posp,const float4* __restrict__ velrho,const typecode* __restrict__ code,bool fluidonly,const GhostNode& g,int lane,GhostSums<MDBC2>& u)
+  const float4* __restrict__ posp,const float4* __restrict__ velrho,const typecode* __restrict__ code,bool fluidonly,const GhostNode& g,int lane,
+  float4* qd,uint32_t* qi,GhostSums<MDBC2>& u)
 {
   const uint32_t* beg=begt+ds->box_fluid;
   const int ncx=int(ds->ncx), nsheet=int(ds->nsheet), cmx=int(ds->cellmin[0]);
@@ -83,38 +91,64 @@ template<bool MDBC2> __device__ __forceinline__ void ghost_walk(const DevCte& c,
   const float sxa=g.gx+b2s_offx(c,g.acx,g.xini+cmx), sxb=g.gx+b2s_offx(c,g.acx,g.xfin-1+cmx);
   const int xmid=(((g.xfin-1+cmx)>>B2S_XBLK)<<B2S_XBLK)-cmx;             // first cell of block B
   const float sgn=(MDBC2? -1.f: 1.f);
+  const uint32_t lt=(1u<<lane)-1u;
+  uint32_t q=0;                                                          // entries waiting in the queue (warp-uniform)
+  // one hit of this lane: (W, gradW) and the sums
+  auto hit_body=[&](const float4 e,uint32_t p2){
+    if(fluidonly && !B2S_CODE_ISFLUID(code[p2]))return;
+    const float drx=e.x, dry=e.y, drz=e.z;
+    float fac;
+    const float wab=wab_fac(c.tkernel,e.w,c,fac);
+    const float4 v2=__ldg(velrho+p2);
+    const float vol=c.massf/v2.w;
+    const float w[4]={wab,fac*drx,fac*dry,fac*drz};                      // (W, gradW)
+    const float d[4]={1.f,sgn*drx,sgn*dry,sgn*drz};
+    #pragma unroll
+    for(int r=0;r<4;r++){
+      u.s[r]+=double(c.massf*w[r]);
+      const float vw=w[r]*vol;
+      #pragma unroll
+      for(int k=0;k<4;k++)u.a[r][k]+=double(k? d[k]*vw: vw);
+    }
+    if(MDBC2){
+      const float vw=wab*vol;
+      u.v[0]+=double(vw*v2.x); u.v[1]+=double(vw*v2.y); u.v[2]+=double(vw*v2.z);
+      u.sub-=double(vol*(drx*w[1]+dry*w[2]+drz*w[3]));
+    }
+  };
+  // the first cnt (<=32) entries are evaluated, one per lane; the rest moves to the front
+  auto drain=[&](uint32_t cnt){
+    __syncwarp();
+    if(uint32_t(lane)<cnt)hit_body(qd[lane],qi[lane]);
+    const uint32_t rest=q-cnt;
+    float4 e=make_float4(0,0,0,0); uint32_t i=0;
+    if(uint32_t(lane)<rest){ e=qd[cnt+lane]; i=qi[cnt+lane]; }
+    __syncwarp();
+    if(uint32_t(lane)<rest){ qd[lane]=e; qi[lane]=i; }
+    q=rest;
+  };
   for(int z=g.zini;z<g.zfin;z++)for(int y=g.yini;y<g.yfin;y++){
     const uint32_t* brow=beg+(y*ncx+z*nsheet);
     const uint32_t pbeg=brow[g.xini], pend=brow[g.xfin];
     if(pbeg>=pend)continue;
     const uint32_t pmid=(xmid<=g.xini? pbeg: (xmid>=g.xfin? pend: brow[xmid]));
     const float sy=g.gy+c.scell*float(g.cy-y), sz=g.gz+c.scell*float(g.cz-z);
-    for(uint32_t p2=pbeg+uint32_t(lane);p2<pend;p2+=32u){
-      const float4 pp2=__ldg(posp+p2);
-      const float drx=(p2>=pmid? sxb: sxa)-pp2.x, dry=sy-pp2.y, drz=sz-pp2.z;
-      const float rr2=drx*drx+dry*dry+drz*drz;
-      if(rr2<=c.kernelsize2 && (!fluidonly || B2S_CODE_ISFLUID(code[p2]))){
-        float fac;
-        const float wab=wab_fac(c.tkernel,rr2,c,fac);
-        const float4 v2=__ldg(velrho+p2);
-        const float vol=c.massf/v2.w;
-        const float w[4]={wab,fac*drx,fac*dry,fac*drz};                  // (W, gradW)
-        const float e[4]={1.f,sgn*drx,sgn*dry,sgn*drz};
-        #pragma unroll
-        for(int r=0;r<4;r++){
-          u.s[r]+=double(c.massf*w[r]);
-          const float vw=w[r]*vol;
-          #pragma unroll
-          for(int k=0;k<4;k++)u.a[r][k]+=double(k? e[k]*vw: vw);
-        }
-        if(MDBC2){
-          const float vw=wab*vol;
-          u.v[0]+=double(vw*v2.x); u.v[1]+=double(vw*v2.y); u.v[2]+=double(vw*v2.z);
-          u.sub-=double(vol*(drx*w[1]+dry*w[2]+drz*w[3]));
-        }
+    for(uint32_t base=pbeg;base<pend;base+=32u){
+      const uint32_t p2=base+uint32_t(lane);
+      bool hit=false; float4 e=make_float4(0,0,0,0);
+      if(p2<pend){
+        const float4 pp2=__ldg(posp+p2);
+        e.x=(p2>=pmid? sxb: sxa)-pp2.x; e.y=sy-pp2.y; e.z=sz-pp2.z;
+        e.w=e.x*e.x+e.y*e.y+e.z*e.z;
+        hit=(e.w<=c.kernelsize2);
       }
+      const uint32_t m=__ballot_sync(0xffffffffu,hit);
+      if(hit){ const uint32_t slot=q+__popc(m&lt); qd[slot]=e; qi[slot]=p2; }
+      q+=__popc(m);
+      if(q>=32u)drain(32u);
     }
   }
+  if(q)drain(q);
 }
 
 // Gaussian elimination with row pivoting on the augmented rows m[4][4+NB], everything in registers (all loops unroll, the row
@@ -166,8 +200,10 @@ __global__ void __launch_bounds__(M_BS) k_mdbc_vel0(const DivState* __restrict__
   if(nor.x==0.f && nor.y==0.f && nor.z==0.f)return;
   const double2 xy=posxy[p1];
   const GhostNode g=ghost_node(c,ds,xy.x,xy.y,posz[p1],nor);
+  __shared__ float4 s_qd[M_WARPS][M_QLEN];
+  __shared__ uint32_t s_qi[M_WARPS][M_QLEN];
   GhostSums<false> u; u.zero();
-  ghost_walk<false>(c,ds,begt,posp,velrho,code,c.use_floating!=0,g,lane,u);
+  ghost_walk<false>(c,ds,begt,posp,velrho,code,c.use_floating!=0,g,lane,s_qd[threadIdx.x>>5],s_qi[threadIdx.x>>5],u);
   u.warp_total();
   const float b0=float(u.s[0]), b1=float(u.s[1]), b2=float(u.s[2]), b3=float(u.s[3]);
   double m[4][5];
@@ -213,8 +249,10 @@ __global__ void __launch_bounds__(M_BS) k_mdbc2(const DivState* __restrict__ ds,
   if(nor.x==0.f && nor.y==0.f && nor.z==0.f){ if(lane==0)boundmode[p1]=B2S_BMODE_DBC; return; }
   const double2 xy=posxy[p1];
   const GhostNode g=ghost_node(c,ds,xy.x,xy.y,posz[p1],nor);
+  __shared__ float4 s_qd[M_WARPS][M_QLEN];
+  __shared__ uint32_t s_qi[M_WARPS][M_QLEN];
   GhostSums<true> u; u.zero();
-  ghost_walk<true>(c,ds,begt,posp,velrho,code,true,g,lane,u);
+  ghost_walk<true>(c,ds,begt,posp,velrho,code,true,g,lane,s_qd[threadIdx.x>>5],s_qi[threadIdx.x>>5],u);
   u.warp_total();
   const float snormal=sqrtf(nor.x*nor.x+nor.y*nor.y+nor.z*nor.z);
   const float nx=nor.x/snormal, ny=nor.y/snormal, nz=nor.z/snormal;

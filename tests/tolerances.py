@@ -49,10 +49,9 @@ def _one(fx, field):
 
 
 def tol(fx: str, field: str) -> float:
-    if fx in _GPU or fx in _NOISE:
-        v = _one(fx, field)
-    else:
-        v = max([_one(k, field) for k in set(_GPU) | set(_NOISE) if _cls(k) == _cls(fx)] or [CAP[field]])
+    v = _one(fx, field) if (fx in _GPU or fx in _NOISE) else 0.0
+    if fx not in _GPU:          # no measurement of this path yet for the fixture: the largest value of its class
+        v = max([v] + [_one(k, field) for k in set(_GPU) if _cls(k) == _cls(fx)] or [CAP[field]])
     if field == "acemax":       # the maximum of |ace| over the particles cannot be asked to agree better than ace itself
         v = max(v, tol(fx, "ace"))
     return min(max(v, FLOOR[field]), CAP[field])
