@@ -514,10 +514,13 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   if(a.ridp)B2S_CUDA(ctx,cudaMemsetAsync(ctx->ridp,0xff,size_t(ctx->prm.casenmoving+ctx->prm.casenfloat)*4,s));
   { // B2S_REORDER=<particles per thread 1|2><pair store 0|1>[,threads]: experiment switch of tools/gpu_job.sh reorder_ab
     static int mode=-1, bs=DIV_BS;
-    if(mode<0){ const char* e=getenv("B2S_REORDER"); mode=(e? atoi(e): 10); if(e && strchr(e,','))bs=atoi(strchr(e,',')+1); if(bs<32||bs>DIV_BS||(bs&31))bs=DIV_BS; }
-    const int ppt=(mode/10==2? 2: 1); const bool pairh=(mode%10)!=0;
+    // measured on the B200 at 10M particles (profiles/r02w_reorder_ab.txt, ms per step): 10: 21.18, 11: 21.22, 20: 20.71, 21: 20.84,
+    // 128-thread blocks: worse.  Two particles per thread (more independent gathers in flight) is the default.
+    if(mode<0){ const char* e=getenv("B2S_REORDER"); mode=(e? atoi(e): 20); if(e && strchr(e,','))bs=atoi(strchr(e,',')+1); if(bs<32||bs>DIV_BS||(bs&31))bs=DIV_BS; }
+    const int ppt=(mode/10==4? 4: (mode/10==2? 2: 1)); const bool pairh=(mode%10)!=0;
     const unsigned gb=b2s_blocks(nptot,unsigned(bs*ppt));
-    if(ppt==2){ if(pairh)k_reorder<2,true><<<gb,bs,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte); else k_reorder<2,false><<<gb,bs,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte); }
+    if(ppt==4)k_reorder<4,false><<<gb,bs,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte);
+    else if(ppt==2){ if(pairh)k_reorder<2,true><<<gb,bs,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte); else k_reorder<2,false><<<gb,bs,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte); }
     else{ if(pairh)k_reorder<1,true><<<gb,bs,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte); else k_reorder<1,false><<<gb,bs,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte); }
     B2S_LAUNCHED(ctx);
   }

@@ -12,6 +12,8 @@
 // B200 design (the reference runs one thread per boundary particle over ~250 neighbours with 20 running sums):
 //   * ONE WARP per ghost node.  Every row of neighbour cells (fixed y,z) is one contiguous range of the cell-sorted arrays, so the
 //     32 lanes stride over the row: coalesced 128-bit loads of posp, the begin-table reads are warp-uniform broadcasts.
+//   * The whole neighbour window is ONE dense candidate list: lane r reads the begin table of row r (one load latency for all 25
+//     rows), a warp scan of the row lengths orders the candidates, and the lanes walk that list 32 at a time.
 //   * Test first, evaluate later: the hits of the rows are compacted through a per-warp queue in shared memory, so the kernel
 //     function and the FP64 accumulations run on 32 hits at a time (a quarter of the candidates are hits).
 //   * Every lane keeps the 20 (mDBC2: 25) partial sums in FP64 registers; five xor-shuffle rounds leave the totals in all lanes.
@@ -81,9 +83,12 @@ template<bool MDBC2> struct GhostSums {
 // sgn = +1: the matrix holds (r_g - r_j) (mDBC), -1: (r_j - r_g) (mDBC2), which is how the two reference kernels orient their
 // first-order terms.
 #define M_QLEN 64                // queue entries per warp: at most 31 waiting + 32 new
+#define M_ROWS 32                // rows of the neighbour window: (2*scelldiv+1)^2 <= 25
+struct GhostRows { uint32_t pbeg[M_ROWS], pmid[M_ROWS], excl[M_ROWS+1]; float sy[M_ROWS], sz[M_ROWS]; };   // per warp, shared memory
+
 template<bool MDBC2> __device__ __forceinline__ void ghost_walk(const DevCte& c,const DivState* ds,const uint32_t* __restrict__ begt,
   const float4* __restrict__ posp,const float4* __restrict__ velrho,const typecode* __restrict__ code,bool fluidonly,const GhostNode& g,int lane,
-  float4* qd,uint32_t* qi,GhostSums<MDBC2>& u)
+  float4* qd,uint32_t* qi,GhostRows& rw,GhostSums<MDBC2>& u)
 {
   const uint32_t* beg=begt+ds->box_fluid;
   const int ncx=int(ds->ncx), nsheet=int(ds->nsheet), cmx=int(ds->cellmin[0]);
@@ -92,6 +97,29 @@ template<bool MDBC2> __device__ __forceinline__ void ghost_walk(const DevCte& c,
   const int xmid=(((g.xfin-1+cmx)>>B2S_XBLK)<<B2S_XBLK)-cmx;             // first cell of block B
   const float sgn=(MDBC2? -1.f: 1.f);
   const uint32_t lt=(1u<<lane)-1u;
+  // ---- all rows of the window at once: lane r reads the begin table of row r (one load latency instead of one per row), a warp
+  //      scan of the row lengths turns the window into ONE dense list of candidates
+  const int ny=g.yfin-g.yini, nrows=ny*(g.zfin-g.zini);
+  uint32_t total;
+  {
+    uint32_t pb=0,pe=0,pm=0; float sy=0.f,sz=0.f;
+    if(lane<nrows){
+      const int y=g.yini+lane%ny, z=g.zini+lane/ny;
+      const uint32_t* brow=beg+(y*ncx+z*nsheet);
+      pb=brow[g.xini]; pe=brow[g.xfin];
+      pm=(xmid<=g.xini? pb: (xmid>=g.xfin? pe: brow[xmid]));
+      sy=g.gy+c.scell*float(g.cy-y); sz=g.gz+c.scell*float(g.cz-z);
+    }
+    const uint32_t len=pe-pb;
+    uint32_t incl=len;
+    #pragma unroll
+    for(int o=1;o<32;o<<=1){ const uint32_t t=__shfl_up_sync(0xffffffffu,incl,o); if(lane>=o)incl+=t; }
+    total=__shfl_sync(0xffffffffu,incl,31);
+    __syncwarp();
+    rw.pbeg[lane]=pb; rw.pmid[lane]=pm; rw.excl[lane]=incl-len; rw.sy[lane]=sy; rw.sz[lane]=sz;
+    if(lane==31)rw.excl[32]=total;
+    __syncwarp();
+  }
   uint32_t q=0;                                                          // entries waiting in the queue (warp-uniform)
   // one hit of this lane: (W, gradW) and the sums
   auto hit_body=[&](const float4 e,uint32_t p2){
@@ -127,26 +155,23 @@ template<bool MDBC2> __device__ __forceinline__ void ghost_walk(const DevCte& c,
     if(uint32_t(lane)<rest){ qd[lane]=e; qi[lane]=i; }
     q=rest;
   };
-  for(int z=g.zini;z<g.zfin;z++)for(int y=g.yini;y<g.yfin;y++){
-    const uint32_t* brow=beg+(y*ncx+z*nsheet);
-    const uint32_t pbeg=brow[g.xini], pend=brow[g.xfin];
-    if(pbeg>=pend)continue;
-    const uint32_t pmid=(xmid<=g.xini? pbeg: (xmid>=g.xfin? pend: brow[xmid]));
-    const float sy=g.gy+c.scell*float(g.cy-y), sz=g.gz+c.scell*float(g.cz-z);
-    for(uint32_t base=pbeg;base<pend;base+=32u){
-      const uint32_t p2=base+uint32_t(lane);
-      bool hit=false; float4 e=make_float4(0,0,0,0);
-      if(p2<pend){
-        const float4 pp2=__ldg(posp+p2);
-        e.x=(p2>=pmid? sxb: sxa)-pp2.x; e.y=sy-pp2.y; e.z=sz-pp2.z;
-        e.w=e.x*e.x+e.y*e.y+e.z*e.z;
-        hit=(e.w<=c.kernelsize2);
-      }
-      const uint32_t m=__ballot_sync(0xffffffffu,hit);
-      if(hit){ const uint32_t slot=q+__popc(m&lt); qd[slot]=e; qi[slot]=p2; }
-      q+=__popc(m);
-      if(q>=32u)drain(32u);
+  // ---- the dense candidate list, 32 at a time; a lane's row only ever moves forward
+  int r=0;
+  for(uint32_t c0=0;c0<total;c0+=32u){
+    const uint32_t cnd=c0+uint32_t(lane);
+    bool hit=false; float4 e=make_float4(0,0,0,0); uint32_t p2=0;
+    if(cnd<total){
+      while(cnd>=rw.excl[r+1])r++;
+      p2=rw.pbeg[r]+(cnd-rw.excl[r]);
+      const float4 pp2=__ldg(posp+p2);
+      e.x=(p2>=rw.pmid[r]? sxb: sxa)-pp2.x; e.y=rw.sy[r]-pp2.y; e.z=rw.sz[r]-pp2.z;
+      e.w=e.x*e.x+e.y*e.y+e.z*e.z;
+      hit=(e.w<=c.kernelsize2);
     }
+    const uint32_t m=__ballot_sync(0xffffffffu,hit);
+    if(hit){ const uint32_t slot=q+__popc(m&lt); qd[slot]=e; qi[slot]=p2; }
+    q+=__popc(m);
+    if(q>=32u)drain(32u);
   }
   if(q)drain(q);
 }
@@ -202,8 +227,9 @@ __global__ void __launch_bounds__(M_BS) k_mdbc_vel0(const DivState* __restrict__
   const GhostNode g=ghost_node(c,ds,xy.x,xy.y,posz[p1],nor);
   __shared__ float4 s_qd[M_WARPS][M_QLEN];
   __shared__ uint32_t s_qi[M_WARPS][M_QLEN];
+  __shared__ GhostRows s_rw[M_WARPS];
   GhostSums<false> u; u.zero();
-  ghost_walk<false>(c,ds,begt,posp,velrho,code,c.use_floating!=0,g,lane,s_qd[threadIdx.x>>5],s_qi[threadIdx.x>>5],u);
+  ghost_walk<false>(c,ds,begt,posp,velrho,code,c.use_floating!=0,g,lane,s_qd[threadIdx.x>>5],s_qi[threadIdx.x>>5],s_rw[threadIdx.x>>5],u);
   u.warp_total();
   const float b0=float(u.s[0]), b1=float(u.s[1]), b2=float(u.s[2]), b3=float(u.s[3]);
   double m[4][5];
@@ -251,8 +277,9 @@ __global__ void __launch_bounds__(M_BS) k_mdbc2(const DivState* __restrict__ ds,
   const GhostNode g=ghost_node(c,ds,xy.x,xy.y,posz[p1],nor);
   __shared__ float4 s_qd[M_WARPS][M_QLEN];
   __shared__ uint32_t s_qi[M_WARPS][M_QLEN];
+  __shared__ GhostRows s_rw[M_WARPS];
   GhostSums<true> u; u.zero();
-  ghost_walk<true>(c,ds,begt,posp,velrho,code,true,g,lane,s_qd[threadIdx.x>>5],s_qi[threadIdx.x>>5],u);
+  ghost_walk<true>(c,ds,begt,posp,velrho,code,true,g,lane,s_qd[threadIdx.x>>5],s_qi[threadIdx.x>>5],s_rw[threadIdx.x>>5],u);
   u.warp_total();
   const float snormal=sqrtf(nor.x*nor.x+nor.y*nor.y+nor.z*nor.z);
   const float nx=nor.x/snormal, ny=nor.y/snormal, nz=nor.z/snormal;

@@ -3,7 +3,7 @@
     compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_small.py [steps] [what,...]
 
 what: dbc (variants 5, 0, 6; half and full cells; tile capacities that force the column split and the global fallback),
-mdbc (warp-per-ghost-node kernels, SlipMode 1 and 2, laminar+SPS), float (floating box + piston), slab (three slabs in one
+mdbc (warp-per-ghost-node kernels, SlipMode 1 and 2, laminar+SPS), float (floating box + piston), slab (two slabs in one
 process through the library's device-counted exchange and a re-cut), 2d.  tests/test_gpu_sanitizer.py runs it under pytest."""
 import os
 import sys
@@ -53,13 +53,13 @@ with tempfile.TemporaryDirectory() as d:
         H.write_case(d / "t", dp=0.01, two_d=True)
         run(str(d / "t" / "Case"), "", 5)
     if "slab" in what:
-        H.write_case(d / "s", dp=0.04)
-        ss = slab.SlabSimulation(str(d / "s" / "Case"), options="-cellmode:half", nranks=3, dist=None)
-        assert ss.native
+        H.write_case(d / "s", dp=0.03)
+        ss = slab.SlabSimulation(str(d / "s" / "Case"), options="-cellmode:half", nranks=2, dist=None)
+        assert ss.native, ss.cuts
         for _ in range(steps):
             ss.step()
         ss.recut()
         ss.step()
-        print(f"slabs x3: cuts {ss.cuts} owned {ss.owned_counts()}", flush=True)
+        print(f"slabs x2: cuts {ss.cuts} owned {ss.owned_counts()}", flush=True)
         ss.close()
 print("sanitize_small done")
