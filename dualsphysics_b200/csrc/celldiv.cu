@@ -240,7 +240,7 @@ int b2s_scan_excl(cudaStream_t s, uint32_t* data, uint32_t n, uint32_t* scratch)
   return 3;
 }
 
-template<int NBINS> __global__ void __launch_bounds__(DIV_BS) k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+template<int NBINS,int PRE> __global__ void __launch_bounds__(DIV_BS) k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ offsets,
   const DivState* __restrict__ ds, int shift, uint32_t ntiles)
 {
@@ -251,11 +251,18 @@ template<int NBINS> __global__ void __launch_bounds__(DIV_BS) k_radix_scatter(co
   #pragma unroll
   for(int b=threadIdx.x;b<NBINS;b+=DIV_BS)s_base[b]=offsets[size_t(b)*ntiles+blockIdx.x];
   const uint32_t base=blockIdx.x*RDX_TILE;
+  // PRE keys and values at a time into registers first: 2*PRE independent loads in flight per thread instead of two between barriers
+  uint32_t rk[PRE], rv[PRE];
+  #pragma unroll
   for(int r=0;r<RDX_ITEMS;r++){
+    if(r%PRE==0){
+      #pragma unroll
+      for(int k=0;k<PRE;k++){ const uint32_t i2=base+(r+k)*DIV_BS+threadIdx.x; rk[k]=(i2<n? keys_in[i2]: 0u); rv[k]=(i2<n? vals_in[i2]: 0u); }
+    }
     const uint32_t i=base+r*DIV_BS+threadIdx.x;
     const bool valid=(i<n);
-    const uint32_t key=(valid? keys_in[i]: 0u);
-    const uint32_t val=(valid? vals_in[i]: 0u);
+    const uint32_t key=rk[r%PRE];
+    const uint32_t val=rv[r%PRE];
     const uint32_t digit=(key>>shift)&uint32_t(NBINS-1);
     #pragma unroll
     for(int b=threadIdx.x;b<NBINS;b+=DIV_BS){
@@ -466,6 +473,8 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   k_presort<<<b2s_blocks(nptot,DIV_BS),DIV_BS,0,s>>>(ctx->div,ctx->cur.dcell,ctx->cur.code,c.domcellcode,ctx->cellpart,ctx->sortpart); B2S_LAUNCHED(ctx);
   // 3. stable radix sort
   const uint32_t ntiles=b2s_blocks(nptot,RDX_TILE);
+  static int rpre=-1;     // B2S_RADIX_PRE=1|4|8|16: keys preloaded per batch in the scatter (experiment switch, tools/gpu_job.sh radix_ab)
+  if(rpre<0){ const char* e=getenv("B2S_RADIX_PRE"); rpre=(e? atoi(e): 1); }
   int dbits[4];
   const int passes=radix_plan(2u*ctx->nct_max+5u,dbits);
   uint32_t *kin=ctx->cellpart,*vin=ctx->sortpart,*kout=ctx->cellpart_alt,*vout=ctx->sortpart_alt;
@@ -473,12 +482,20 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
     if(dbits[ps]>8){
       k_radix_hist<512><<<ntiles,DIV_BS,0,s>>>(kin,ctx->div,shift,ntiles,ctx->radix_counts); B2S_LAUNCHED(ctx);
       ctx->launches+=b2s_scan_excl(s,ctx->radix_counts,512u*ntiles,ctx->radix_counts+ctx->radix_counts_len);
-      k_radix_scatter<512><<<ntiles,DIV_BS,0,s>>>(kin,vin,kout,vout,ctx->radix_counts,ctx->div,shift,ntiles); B2S_LAUNCHED(ctx);
+      if(rpre==16)k_radix_scatter<512,16><<<ntiles,DIV_BS,0,s>>>(kin,vin,kout,vout,ctx->radix_counts,ctx->div,shift,ntiles);
+      else if(rpre==8)k_radix_scatter<512,8><<<ntiles,DIV_BS,0,s>>>(kin,vin,kout,vout,ctx->radix_counts,ctx->div,shift,ntiles);
+      else if(rpre==4)k_radix_scatter<512,4><<<ntiles,DIV_BS,0,s>>>(kin,vin,kout,vout,ctx->radix_counts,ctx->div,shift,ntiles);
+      else k_radix_scatter<512,1><<<ntiles,DIV_BS,0,s>>>(kin,vin,kout,vout,ctx->radix_counts,ctx->div,shift,ntiles);
+      B2S_LAUNCHED(ctx);
     }
     else{
       k_radix_hist<256><<<ntiles,DIV_BS,0,s>>>(kin,ctx->div,shift,ntiles,ctx->radix_counts); B2S_LAUNCHED(ctx);
       ctx->launches+=b2s_scan_excl(s,ctx->radix_counts,256u*ntiles,ctx->radix_counts+ctx->radix_counts_len);
-      k_radix_scatter<256><<<ntiles,DIV_BS,0,s>>>(kin,vin,kout,vout,ctx->radix_counts,ctx->div,shift,ntiles); B2S_LAUNCHED(ctx);
+      if(rpre==16)k_radix_scatter<256,16><<<ntiles,DIV_BS,0,s>>>(kin,vin,kout,vout,ctx->radix_counts,ctx->div,shift,ntiles);
+      else if(rpre==8)k_radix_scatter<256,8><<<ntiles,DIV_BS,0,s>>>(kin,vin,kout,vout,ctx->radix_counts,ctx->div,shift,ntiles);
+      else if(rpre==4)k_radix_scatter<256,4><<<ntiles,DIV_BS,0,s>>>(kin,vin,kout,vout,ctx->radix_counts,ctx->div,shift,ntiles);
+      else k_radix_scatter<256,1><<<ntiles,DIV_BS,0,s>>>(kin,vin,kout,vout,ctx->radix_counts,ctx->div,shift,ntiles);
+      B2S_LAUNCHED(ctx);
     }
     uint32_t* t=kin; kin=kout; kout=t; t=vin; vin=vout; vout=t;
   }
@@ -515,8 +532,9 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   { // B2S_REORDER=<particles per thread 1|2><pair store 0|1>[,threads]: experiment switch of tools/gpu_job.sh reorder_ab
     static int mode=-1, bs=DIV_BS;
     // measured on the B200 at 10M particles (profiles/r02w_reorder_ab.txt, ms per step): 10: 21.18, 11: 21.22, 20: 20.71, 21: 20.84,
-    // 128-thread blocks: worse.  Two particles per thread (more independent gathers in flight) is the default.
-    if(mode<0){ const char* e=getenv("B2S_REORDER"); mode=(e? atoi(e): 20); if(e && strchr(e,','))bs=atoi(strchr(e,',')+1); if(bs<32||bs>DIV_BS||(bs&31))bs=DIV_BS; }
+    // 128-thread blocks: worse; profiles/r02x_reorder_ab.txt: 40: 20.64).  Four particles per thread (more independent gathers in
+    // flight) is the default.
+    if(mode<0){ const char* e=getenv("B2S_REORDER"); mode=(e? atoi(e): 40); if(e && strchr(e,','))bs=atoi(strchr(e,',')+1); if(bs<32||bs>DIV_BS||(bs&31))bs=DIV_BS; }
     const int ppt=(mode/10==4? 4: (mode/10==2? 2: 1)); const bool pairh=(mode%10)!=0;
     const unsigned gb=b2s_blocks(nptot,unsigned(bs*ppt));
     if(ppt==4)k_reorder<4,false><<<gb,bs,0,s>>>(ctx->div,ctx->step,ctx->sortpart,a,ctx->cte);

@@ -29,6 +29,7 @@ case $step in
     timeout 1500 ncu --set full --clock-control none --profile-from-start off --metrics sm__sass_thread_inst_executed_op_fadd_pred_on.sum,sm__sass_thread_inst_executed_op_fmul_pred_on.sum,sm__sass_thread_inst_executed_op_ffma_pred_on.sum -f -o gpurun_out/${TAG}_step_${kind} python tools/profile_step.py $kind $npk 30 > gpurun_out/${TAG}_step_${kind}.log 2>&1; tail -1 gpurun_out/${TAG}_step_${kind}.log
     python tools/ncu_step_summary.py gpurun_out/${TAG}_step_${kind}.ncu-rep > gpurun_out/${TAG}_ncu_step_${kind}.md 2>&1; rm -f gpurun_out/${TAG}_step_${kind}.ncu-rep   # the report of a whole step exceeds what a GPU job may return: the summary travels
     head -14 gpurun_out/${TAG}_ncu_step_${kind}.md | cut -c1-330;;
+  radix_ab) for m in 1 4 8 16; do B2S_RADIX_PRE=$m timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-parity > gpurun_out/${TAG}_radix_$m.json 2>/dev/null; python -c "import json; d=json.load(open('gpurun_out/${TAG}_radix_$m.json')); print('B2S_RADIX_PRE=$m ms/step', round(d['ms_per_step'],3), 'ms/interaction', round(d['roofline']['ms_per_launch'],3))"; done | tee gpurun_out/${TAG}_radix_ab.txt;;
   reorder_ab) for m in ${REORDER_MODES:-10 20 40}; do B2S_REORDER=$m timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-parity > gpurun_out/${TAG}_reorder_$m.json 2>/dev/null; python -c "import json; d=json.load(open('gpurun_out/${TAG}_reorder_$m.json')); print('B2S_REORDER=$m ms/step', round(d['ms_per_step'],3), 'ms/interaction', round(d['roofline']['ms_per_launch'],3))"; done | tee gpurun_out/${TAG}_reorder_ab.txt;;
   launches_c3) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/${TAG}_launches_c3.csv python tools/run_config.py c3 --npgpu 4000000 --steps 2 --warmup 3 > gpurun_out/${TAG}_launches_c3.log 2>&1; python tools/summarize_launches.py gpurun_out/${TAG}_launches_c3.csv 2>/dev/null | head -12;;
   c3small) timeout 900 python tools/run_config.py c3 --npgpu 4000000 --steps 10 > gpurun_out/${TAG}_c3_4M.json 2> gpurun_out/${TAG}_c3_4M.err; tail -c 600 gpurun_out/${TAG}_c3_4M.json; echo;;
