@@ -33,11 +33,12 @@ __global__ void __launch_bounds__(DIV_BS) k_limits(uint32_t n, uint32_t pini, co
   const typecode* __restrict__ code, uint32_t dcc, uint32_t* lim)
 {
   uint32_t mn[3]={0xffffffffu,0xffffffffu,0xffffffffu}, mx[3]={0,0,0};
+  #pragma unroll 8
   for(uint32_t i=blockIdx.x*blockDim.x+threadIdx.x; i<n; i+=gridDim.x*blockDim.x){
     const uint32_t p=pini+i;
     const typecode c=code[p];
+    const uint32_t rc=dcell[p];          // unconditional: the loads of the unrolled iterations go out together
     if(B2S_CODE_SPECIAL(c)<B2S_CODE_OUTIGNORE){
-      const uint32_t rc=dcell[p];
       const uint32_t cx=B2S_DCEL_CELLX(dcc,rc), cy=B2S_DCEL_CELLY(dcc,rc), cz=B2S_DCEL_CELLZ(dcc,rc);
       mn[0]=min(mn[0],cx); mn[1]=min(mn[1],cy); mn[2]=min(mn[2],cz);
       mx[0]=max(mx[0],cx); mx[1]=max(mx[1],cy); mx[2]=max(mx[2],cz);
@@ -474,7 +475,7 @@ int b2s_celldiv_impl(b2s_ctx* ctx){
   // 3. stable radix sort
   const uint32_t ntiles=b2s_blocks(nptot,RDX_TILE);
   static int rpre=-1;     // B2S_RADIX_PRE=1|4|8|16: keys preloaded per batch in the scatter (experiment switch, tools/gpu_job.sh radix_ab)
-  if(rpre<0){ const char* e=getenv("B2S_RADIX_PRE"); rpre=(e? atoi(e): 1); }
+  if(rpre<0){ const char* e=getenv("B2S_RADIX_PRE"); rpre=(e? atoi(e): 8); }   // profiles/r02y_radix_ab.txt: 1: 20.62, 4: 20.76, 8: 20.58, 16: 20.56 ms per step
   int dbits[4];
   const int passes=radix_plan(2u*ctx->nct_max+5u,dbits);
   uint32_t *kin=ctx->cellpart,*vin=ctx->sortpart,*kout=ctx->cellpart_alt,*vout=ctx->sortpart_alt;
