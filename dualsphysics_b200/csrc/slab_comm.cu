@@ -96,10 +96,11 @@ static int comm_alloc(b2s_ctx* ctx, uint32_t max_plane_particles){
   for(int k=0;k<2;k++){ c->send[k]=NULL; c->recv[k]=NULL; }
   // halo: scelldiv (mDBC: 2*scelldiv) cell planes per side at the density of the fullest plane of the initial state, with half as
   // much again (WCSPH keeps the density within a few percent; what does not fit raises B2S_ERR_NOMEM at the step's sync);
-  // migrants of one sub-step are a small fraction of a plane
+  // migrants of one sub-step are a few thousand (a thirty-second of the halo capacity is ~4x what the collapsing column
+  // sends at 10M particles per GPU)
   const uint32_t planes=uint32_t(ctx->prm.scelldiv)*(ctx->prm.tboundary==B2S_BC_MDBC? 2u: 1u);
   c->halocap=(3u*planes*std::max(max_plane_particles,1u))/2u+4096u;
-  c->migcap=std::max(4096u,c->halocap/8u);
+  c->migcap=std::max(8192u,c->halocap/32u);
   c->msg_bytes=b2s_slab_msg_bytes(ctx,c->migcap,c->halocap);
   c->ncx=ctx->prm.domcells[0];
   for(int k=0;k<2;k++){
