@@ -596,3 +596,23 @@ extern "C" int b2s_out_fetch(b2s_ctx* ctx, uint32_t maxcount, uint32_t* count_ou
 }
 
 void b2s_launch_scan_excl(cudaStream_t s, uint32_t* data, uint32_t n){ k_scan_excl<<<1,1024,0,s>>>(data,n); }   // small inputs (slab.cu)
+// nseg independent exclusive scans of n elements each, segment k at data+k*n: one block per segment, one launch (slab.cu: the four
+// count arrays of an exchange)
+__global__ void __launch_bounds__(1024) k_scan_excl_seg(uint32_t* data, uint32_t n){
+  __shared__ uint32_t wsum[32];
+  uint32_t* d=data+size_t(blockIdx.x)*n;
+  uint32_t carry=0;
+  for(uint32_t base=0; base<n; base+=SCAN_BLK){
+    const uint32_t i0=base+threadIdx.x*4;
+    uint32_t v[4];
+    #pragma unroll
+    for(int k=0;k<4;k++)v[k]=(i0+k<n? d[i0+k]: 0u);
+    uint32_t total;
+    uint32_t excl=carry+block_excl_scan4(v,wsum,total);
+    #pragma unroll
+    for(int k=0;k<4;k++){ if(i0+k<n)d[i0+k]=excl; excl+=v[k]; }
+    carry+=total;
+    __syncthreads();
+  }
+}
+void b2s_launch_scan_excl_seg(cudaStream_t s, uint32_t* data, uint32_t n, uint32_t nseg){ k_scan_excl_seg<<<nseg,1024,0,s>>>(data,n); }

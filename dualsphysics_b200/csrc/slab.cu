@@ -24,6 +24,7 @@
 static inline uint32_t slab_halo_planes(const b2s_ctx* ctx){ return uint32_t(ctx->prm.scelldiv)*(ctx->prm.tboundary==B2S_BC_MDBC? 2u: 1u); }
 
 void b2s_launch_scan_excl(cudaStream_t s, uint32_t* data, uint32_t n);   // celldiv.cu
+void b2s_launch_scan_excl_seg(cudaStream_t s, uint32_t* data, uint32_t n, uint32_t nseg);
 
 struct SlabLayout { uint32_t bytes, off_pre, off_m1, off_tau, off_nor; };
 
@@ -453,8 +454,10 @@ int b2s_slab_pack_msg(b2s_ctx* ctx, char* dev_left, char* dev_right, uint32_t mi
     if(mig && halo){ k_slab_flag2<<<nb,S_BS,0,s>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,hl,hr,ctx->slab_cxa,ctx->slab_cxb,slab_halo_planes(ctx),fM,fH,cM,cH,nb); B2S_LAUNCHED(ctx); }
     else if(mig){ k_slab_flag<<<nb,S_BS,0,s>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,1,hl,hr,ctx->slab_cxa,ctx->slab_cxb,slab_halo_planes(ctx),fM,cM,nb); B2S_LAUNCHED(ctx); }
     else if(halo){ k_slab_flag<<<nb,S_BS,0,s>>>(ctx->div,ctx->cur.code,ctx->cur.dcell,ctx->cte.domcellcode,0,hl,hr,ctx->slab_cxa,ctx->slab_cxb,slab_halo_planes(ctx),fH,cH,nb); B2S_LAUNCHED(ctx); }
-    if(mig){ b2s_launch_scan_excl(s,cM,nb+1); b2s_launch_scan_excl(s,cM+nb+1,nb+1); ctx->launches+=2; }
-    if(halo){ b2s_launch_scan_excl(s,cH,nb+1); b2s_launch_scan_excl(s,cH+nb+1,nb+1); ctx->launches+=2; }
+    // cM = [left | right] and cH = [left | right] are four consecutive segments of nb+1 counts
+    if(mig && halo){ b2s_launch_scan_excl_seg(s,cM,nb+1,4); B2S_LAUNCHED(ctx); }
+    else if(mig){ b2s_launch_scan_excl_seg(s,cM,nb+1,2); B2S_LAUNCHED(ctx); }
+    else if(halo){ b2s_launch_scan_excl_seg(s,cH,nb+1,2); B2S_LAUNCHED(ctx); }
   }
   k_slab_header<<<1,32,0,s>>>(ctx->step,cM,cH,nb,migcap,halocap,hl? dev_left: NULL,hr? dev_right: NULL,dev_sent_total,strict); B2S_LAUNCHED(ctx);
   if(n && mig && halo){

@@ -18,6 +18,7 @@ case $step in
     python -c "import json; d=json.load(open('gpurun_out/${TAG}_bench_n1_v$v.json')); print('variant $v ms/step', d['ms_per_step'], 'ms/interaction', d['roofline']['ms_per_launch'], 'frac', d['roofline']['frac'])";;
   benchfull6) B2S_BENCH_EXTRA_OPTS=' -cellmode:full' timeout 600 python bench.py --steps 10 --warmup 3 --variant 6 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_n1_v6_fullcells.json 2> gpurun_out/${TAG}_bench_n1_v6_fullcells.err; tail -2 gpurun_out/${TAG}_bench_n1_v6_fullcells.err
     python -c "import json; d=json.load(open('gpurun_out/${TAG}_bench_n1_v6_fullcells.json')); print('variant 6 full cells ms/step', d['ms_per_step'], 'ms/interaction', d['roofline']['ms_per_launch'])";;
+  bench25) B2S_BENCH_NP=25000000 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_n1_25M.json 2> gpurun_out/${TAG}_bench_n1_25M.err; tail -2 gpurun_out/${TAG}_bench_n1_25M.err; python -c "import json; d=json.load(open('gpurun_out/${TAG}_bench_n1_25M.json')); print('25M: ms/step', d['ms_per_step'], 'value', d['value'], 'ms/interaction', d['roofline']['ms_per_launch'], 'frac', d['roofline']['frac'])";;
   fullbench) timeout 1200 python bench.py > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err; tail -2 gpurun_out/${TAG}_bench_n1.err; head -c 400 gpurun_out/${TAG}_bench_n1.json; echo;;
   ncu[0-9]) v=${step#ncu}
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_forces_fluid -s 2 -c 1 -f -o gpurun_out/${TAG}_forces_v${v}_10M python tools/profile_forces.py 10000000 $v 3 > gpurun_out/${TAG}_prof_v$v.log 2>&1; tail -1 gpurun_out/${TAG}_prof_v$v.log
