@@ -307,6 +307,27 @@ extern "C" int b2s_download_particles_byid(b2s_ctx* ctx, uint32_t* np_out, uint3
   int r=b2s_sync_info(ctx); if(r)return r;
   const uint32_t np=ctx->np_host, idmax=ctx->prm.casenp;
   cudaStream_t s=ctx->stream;
+  if(ctx->slab_on && ctx->slab_nranks>1){
+    // A slab rank owns 1/N of the case: everything is sized by what it holds (np), not by the case (casenp) -- the particle arrays
+    // come down as they are and the owned particles are ordered by id on the host.
+    std::vector<uint32_t> hid(np); std::vector<typecode> hcode(np); std::vector<double2> hxy(np); std::vector<double> hz(np); std::vector<float4> hvr(np);
+    B2S_CUDA(ctx,cudaMemcpyAsync(hid.data(),ctx->cur.idp,size_t(np)*4,cudaMemcpyDeviceToHost,s));
+    B2S_CUDA(ctx,cudaMemcpyAsync(hcode.data(),ctx->cur.code,size_t(np)*sizeof(typecode),cudaMemcpyDeviceToHost,s));
+    B2S_CUDA(ctx,cudaMemcpyAsync(hxy.data(),ctx->cur.posxy,size_t(np)*16,cudaMemcpyDeviceToHost,s));
+    B2S_CUDA(ctx,cudaMemcpyAsync(hz.data(),ctx->cur.posz,size_t(np)*8,cudaMemcpyDeviceToHost,s));
+    B2S_CUDA(ctx,cudaMemcpyAsync(hvr.data(),ctx->cur.velrho,size_t(np)*16,cudaMemcpyDeviceToHost,s));
+    B2S_CUDA(ctx,cudaStreamSynchronize(s));
+    std::vector<uint32_t> order; order.reserve(np);
+    for(uint32_t p=0;p<np;p++)if(B2S_CODE_ISNORMAL(hcode[p]) && hid[p]<idmax)order.push_back(p);   // ghosts and excluded particles stay out (k_scatter_byid's rule)
+    std::sort(order.begin(),order.end(),[&](uint32_t a,uint32_t b){ return hid[a]<hid[b]; });
+    uint32_t n=0;
+    for(uint32_t p:order){
+      idp[n]=hid[p]; pos[size_t(n)*3]=hxy[p].x; pos[size_t(n)*3+1]=hxy[p].y; pos[size_t(n)*3+2]=hz[p];
+      vel[size_t(n)*3]=hvr[p].x; vel[size_t(n)*3+1]=hvr[p].y; vel[size_t(n)*3+2]=hvr[p].z; rhop[n]=hvr[p].w; n++;
+    }
+    if(np_out)*np_out=n;
+    return B2S_OK;
+  }
   const size_t bytes=size_t(idmax)*(24+12+4+4)+64;
   r=ensure_scratch(ctx,bytes); if(r)return r;
   char* base=(char*)ctx->scratch;

@@ -789,7 +789,9 @@ static bool svextra_check(const std::string& cfg,unsigned cpart){
 // ---- PART output (JSph::SavePartData / JPartDataBi4) ----------------------------------------------------
 static void save_part(b2s_sim* s){
   const b2s_params& p=s->prm;
-  const unsigned cap=p.casenp;
+  // a slab rank holds 1/N of the case: its buffers follow what it holds (b2s_download_particles_byid returns at most np)
+  unsigned cap=p.casenp;
+  if(s->npiece>1){ b2s_info i0; if(b2s_get_info(s->ctx,&i0)==0)cap=std::min<unsigned>(p.casenp,i0.np); }
   std::vector<uint32_t> idp(cap); std::vector<double> pos(size_t(cap)*3); std::vector<float> vel(size_t(cap)*3), rho(cap);
   uint32_t n=0;
   int r=b2s_download_particles_byid(s->ctx,&n,idp.data(),pos.data(),vel.data(),rho.data());
