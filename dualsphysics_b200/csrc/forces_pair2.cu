@@ -15,18 +15,30 @@
 //   * row i of the window is processed together with row (last-i), its point mirror (y,z)<->(-y,-z): a lane close to one side
 //     of its cell has many hits in one of the two and few in the other, so the sum is flat across the warp and fewer rounds are
 //     lost to the lane with most hits (tools/analyze_rounds.py: 121 -> 103 rounds per particle);
-//   * built for Wendland + artificial viscosity without floating bodies (every DDT mode, DBC and mDBC); other
-//     configurations run variant 0.
+//   * ROW DESCRIPTORS: the window is walked in phases of one z plane and its mirror plane.  At the head of a phase a lane works
+//     out the rows of all its turns (trim, then three begin-table loads per row that depend on nothing but the trim) and parks them
+//     in its own shared-memory slots; a turn then costs one LDS.128.  The former set-up of every row right before its use (two
+//     set-ups of ~130 instructions with three dependent loads per turn, spilling the cell range) was 27% of the executed
+//     instructions: 9.07 -> 8.08 ms at 10M particles (profiles/README.md, r02E);
+//   * every axis of the reference's dispatch is a template parameter (kernel, viscosity, DDT, floating bodies, mDBC2).
 // History of the rejected builds (consecutive candidates instead of masks, software-pipelined rounds, velrho with the positions,
-// single rows = the former variant 4): profiles/r01_pair2_tuning.txt, profiles/r02_pair2_ab.txt.
+// single rows = the former variant 4, rows set up one ahead of their use): profiles/r01_pair2_tuning.txt, profiles/r02_pair2_ab.txt,
+// profiles/README.md.
 #include "forces_pair2.cuh"
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #ifndef P2_BS
 #define P2_BS 128
 #endif
+#ifndef P2_MINB_SPS
+#define P2_MINB_SPS 5
+#endif
+#ifndef P2_MINB_OTHER
+#define P2_MINB_OTHER 8
+#endif
 #ifndef P2_MINB
-#define P2_MINB 7            // resident blocks per SM the register allocation aims at
+#define P2_MINB 8            // resident blocks per SM the register allocation aims at (64 registers)
 #endif
 
 // FP16 pre-filter: rr2 of two candidates (half2) against the threshold; sets bit0/bit1 in mask for lo/hi
@@ -37,15 +49,16 @@ __device__ __forceinline__ void hit2_or(uint32_t& mask,uint32_t rr2,uint32_t thr
 __device__ __forceinline__ uint32_t h2u(__half2 h){ return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 u2h(uint32_t u){ return *reinterpret_cast<__half2*>(&u); }
 
-// Resident blocks per SM the register allocation aims at: the base configuration (Wendland + artificial viscosity, no floating
-// bodies) was tuned at 7 (72 registers); laminar+SPS carries 6 more packed sums and 12 stress components per round.
+// Resident blocks per SM the register allocation aims at (measured, profiles/README.md r02E-r02H): 8 (64 registers) for everything
+// but laminar+SPS, which carries 6 more packed sums and 12 stress components per round: 5 (96 registers).
 template<int TKER,int TVISCO,bool FLOATING> struct P2Cfg {
-  static constexpr int MINB=(TVISCO==B2S_VISCO_LAMINARSPS? 4: ((FLOATING || TKER!=B2S_KERNEL_WENDLAND || TVISCO!=B2S_VISCO_ARTIFICIAL)? 6: P2_MINB));
+  static constexpr int MINB=(TVISCO==B2S_VISCO_LAMINARSPS? P2_MINB_SPS: ((FLOATING || TKER!=B2S_KERNEL_WENDLAND || TVISCO!=B2S_VISCO_ARTIFICIAL)? P2_MINB_OTHER: P2_MINB));
 };
 
 template<int TKER,int TVISCO,int TDENS,bool FLOATING,bool MDBC2>
 __global__ void __launch_bounds__(P2_BS,(P2Cfg<TKER,TVISCO,FLOATING>::MINB)) k_forces_fluid_pair2(ForcesArgs g, const PackCte k, const __grid_constant__ DevCte c)
 {
+  __shared__ uint4 sdesc[5][P2_BS];   // row descriptors of one phase, one slot per thread and turn (see the phase loop)
   const DivState* ds=g.ds;
   const uint32_t npb=ds->npb, np=ds->np;
   const uint32_t p1=npb+blockIdx.x*blockDim.x+threadIdx.x;
@@ -80,6 +93,7 @@ __global__ void __launch_bounds__(P2_BS,(P2Cfg<TKER,TVISCO,FLOATING>::MINB)) k_f
   const uint32_t thr2=h2u(__float2half2_rn(kc*1.015f+0.02f));
   PackAcc acc;
   pack_zero(acc);
+  uint32_t lenor=0;   // OR of the row lengths
   PairAcc sbnd={0,0,0,0,0,0,0,0,0,0,0,0};
   // Whole boundary pass skipped for warps whose particles have no boundary particle in their neighbour windows (one byte per
   // particle from the per-cell flags of the divide instead of 2 x 25 begin-table loads): most of the fluid is far from a wall.
@@ -89,23 +103,7 @@ __global__ void __launch_bounds__(P2_BS,(P2Cfg<TKER,TVISCO,FLOATING>::MINB)) k_f
   for(int pass=1;pass>=0;pass--){
     if(pass==1 && !warpnearb)continue;
     const uint32_t* beg=(pass==0? g.beg+ds->box_fluid: g.beg);   // pass 1: boundary neighbours (first), pass 0: fluid neighbours
-    // Rows (z,y) of the neighbour window, software-pipelined: the begin-table loads of row i+1 are issued before row i is
-    // processed, so their latency (three dependent loads after the trim) hides behind the pair work of the current row.
     struct Row { uint32_t pbeg,pend,pmid; float sy,sz; };
-    auto setup_row=[&](int z,int y)->Row{
-      Row w; w.pbeg=w.pend=w.pmid=0;
-      w.sz=FADD(pp1.z,c.scell*float(r.cz-z)); w.sy=FADD(pp1.y,c.scell*float(r.cy-y));
-      int xa,xb;
-      if(z>=r.zini && z<r.zfin && y>=r.yini && y<r.yfin){
-        const uint32_t* brow=beg+(y*ncx+z*nsheet);
-        // boundary pass: most fluid particles have no boundary particle anywhere in the row -> two loads settle it, no trim
-        if((pass==0 || brow[r.xini]!=brow[r.xfin]) && row_trim(c,r,xin,w.sy,w.sz,xa,xb)){
-          w.pbeg=brow[xa]; w.pend=brow[xb];
-          w.pmid=(oneblk || xmid0<=xa? w.pbeg: (xmid0>=xb? w.pend: brow[xmid0]));
-        }
-      }
-      return w;
-    };
     //-FP16 pre-filter of one chunk (16 candidate pairs) of a row.
     auto check=[&](const Row& w,uint32_t jb,uint32_t j0,uint32_t n)->uint32_t{
       const uint32_t pb0=(jb+j0)<<1;
@@ -140,63 +138,102 @@ __global__ void __launch_bounds__(P2_BS,(P2Cfg<TKER,TVISCO,FLOATING>::MINB)) k_f
       { const uint32_t v=w.pend-pb0; if(v<32u)mask&=((1u<<v)-1u); }
       return mask;
     };
-    const int nrows=(2*d+1)*(2*d+1), half=nrows>>1;
-    int za=r.cz-d, ya=r.cy-d, zb=r.cz+d, yb=r.cy+d;     // row i walks forward from the first row, its mirror backward from the last
-    Row nextA=setup_row(za,ya);
+    // Row descriptors.  The window is walked in phases of one z plane and its mirror plane: first a lane works out the rows of
+    // ALL turns of the phase -- trim to the sphere, then three begin-table loads per row that depend on nothing but the trim, so
+    // the loads of the (up to) 10 rows of a phase are in flight together -- and parks them in its own shared-memory slots
+    // (sdesc[turn][thread] = {pbegA, lenA | midA<<16, pbegB, lenB | midB<<16}; no other thread reads them: no barrier).  The turn
+    // loop then costs one LDS.128 instead of two row set-ups with three dependent loads each.
+    const int n1=2*d+1;
     #pragma unroll 1
-    for(int i=0;i<=half;i++){
-      const Row A=nextA;
-      Row B; B.pbeg=B.pend=B.pmid=0; B.sy=B.sz=0.f;
-      if(i<half)B=setup_row(zb,yb);                      // the centre row (i==half) has no mirror
-      if(++ya>r.cy+d){ ya=r.cy-d; za++; }
-      if(--yb<r.cy-d){ yb=r.cy+d; zb--; }
-      if(i<half)nextA=setup_row(za,ya);
-      const uint32_t jbA=A.pbeg>>1, npA=__reduce_max_sync(0xffffffffu,((A.pend+1u)>>1)-jbA);
-      const uint32_t jbB=B.pbeg>>1, npB=__reduce_max_sync(0xffffffffu,((B.pend+1u)>>1)-jbB);
-      const uint32_t npmax=max(npA,npB);
+    for(int ph=0;ph<=d;ph++){
+      const int nw=(ph<d? n1: d+1);                      // the last phase is the centre plane: its second half mirrors its first
+      const int zA=r.cz-d+ph, zB=r.cz+d-ph;
+      float kzo=c.scell*float(d-ph);
+      asm volatile("":"+f"(kzo));   // opaque: kept (in a uniform register) instead of being rebuilt from the loop counters in every round: 8.08 -> 7.95 ms
+      const float szA=FADD(pp1.z,kzo), szB=FADD(pp1.z,-kzo);
+      const bool zokA=(valid && zA>=r.zini && zA<r.zfin), zokB=(valid && zB>=r.zini && zB<r.zfin);
+      const float dzA=fmaxf(0.f,fmaxf(szA-c.scell,-szA)), dzB=fmaxf(0.f,fmaxf(szB-c.scell,-szB));
+      const float kzA=c.kernelsize2*1.0002f-dzA*dzA, kzB=c.kernelsize2*1.0002f-dzB*dzB;
+      auto desc_row=[&](bool zok,int z,int y,float sy,float kz)->uint2{
+        // row_trim (forces_common.cuh) without branches: an empty or outside row reads three times beg[0] and gets len 0
+        const float dy=fmaxf(0.f,fmaxf(sy-c.scell,-sy));
+        const float xh2=kz-dy*dy;
+        const float xh=xh2*b2s_rsqrt(xh2)+c.scell*1e-4f;
+        int xa=max(r.xini,r.cx+int(floorf((xin-xh)*ovs)));
+        int xb=min(r.xfin,r.cx+int(floorf((xin+xh)*ovs))+1);
+        const bool ok=(zok && y>=r.yini && y<r.yfin && xh2>0.f && xa<xb);
+        uint32_t off=uint32_t(y*ncx+z*nsheet);             // 32-bit unsigned table indices: one IMAD.WIDE per address
+        if(!ok){ xa=xb=0; off=0u; }
+        const int xm=(oneblk? xa: min(max(xmid0,xa),xb));
+        const uint32_t pbeg=beg[off+uint32_t(xa)], pend=beg[off+uint32_t(xb)], pmid=beg[off+uint32_t(xm)];
+        const uint32_t len=pend-pbeg;
+        lenor|=len;                                        // tested once at the end of the kernel
+        return make_uint2(len? pbeg: 0u,len|((pmid-pbeg)<<16));   // empty rows at 0: an odd begin would cost a chunk turn
+      };
+      #pragma unroll
+      for(int w=0;w<5;w++){
+        if(w<nw){
+          const float syA=FADD(pp1.y,c.scell*float(d-w)), syB=FADD(pp1.y,c.scell*float(w-d));
+          const uint2 a=desc_row(zokA,zA,r.cy-d+w,syA,kzA);
+          const uint2 b=desc_row(zokB && (ph<d || w<d),zB,r.cy+d-w,syB,kzB);   // the centre row has no mirror
+          sdesc[w][threadIdx.x]=make_uint4(a.x,a.y,b.x,b.y);
+        }
+      }
       #pragma unroll 1
-      for(uint32_t j0=0;j0<npmax;j0+=16){
-        uint32_t maskA=(j0<npA? check(A,jbA,j0,min(16u,npA-j0)): 0u);
-        uint32_t maskB=(j0<npB? check(B,jbB,j0,min(16u,npB-j0)): 0u);
-        const uint32_t mine=((uint32_t(__popc(maskA))+1u)>>1)+((uint32_t(__popc(maskB))+1u)>>1);
+      for(int w=0;w<nw;w++){
+        const uint4 dq=sdesc[w][threadIdx.x];
+        float kyA=c.scell*float(d-w);
+        asm volatile("":"+f"(kyA));
+        Row A,B;
+        A.pbeg=dq.x; A.pend=dq.x+(dq.y&0xffffu); A.pmid=dq.x+(dq.y>>16); A.sy=FADD(pp1.y,kyA); A.sz=szA;
+        B.pbeg=dq.z; B.pend=dq.z+(dq.w&0xffffu); B.pmid=dq.z+(dq.w>>16); B.sy=FADD(pp1.y,-kyA); B.sz=szB;
+        const uint32_t jbA=A.pbeg>>1, npA=__reduce_max_sync(0xffffffffu,((A.pend+1u)>>1)-jbA);
+        const uint32_t jbB=B.pbeg>>1, npB=__reduce_max_sync(0xffffffffu,((B.pend+1u)>>1)-jbB);
+        const uint32_t npmax=max(npA,npB);
         #pragma unroll 1
-        for(uint32_t it=__reduce_max_sync(0xffffffffu,mine);it;it--){
-          const bool ua=(maskA!=0u);
-          uint32_t m=(ua? maskA: maskB);
-          if(m){
-            const uint32_t ka=__ffs(m)-1u; m&=m-1u;
-            const bool two=(m!=0u);
-            const uint32_t kb=(two? __ffs(m)-1u: ka); m&=m-1u;
-            if(ua)maskA=m; else maskB=m;
-            const uint32_t pb0=((ua? jbA: jbB)+j0)<<1, pmid=(ua? A.pmid: B.pmid);
-            const float sy=(ua? A.sy: B.sy), sz=(ua? A.sz: B.sz);
-            const uint32_t p2a=pb0+ka, p2b=pb0+kb;
-            const float4 pa=__ldg(g.posp+p2a), pb=__ldg(g.posp+p2b);
-            const float4 va=__ldg(g.velrho+p2a), vb=__ldg(g.velrho+p2b);
-            const f2 drx=pk(FSUB(p2a>=pmid? sxB: sxA,pa.x),FSUB(p2b>=pmid? sxB: sxA,pb.x));
-            const f2 dry=pk(FSUB(sy,pa.y),FSUB(sy,pb.y)), drz=pk(FSUB(sz,pa.z),FSUB(sz,pb.z));
-            f2 rr2=fma2(drz,drz,fma2(dry,dry,mul2(drx,drx)));   // b2s_rr2 order
-            if(!two)rr2=pk(lo(rr2),1e30f);                      // the repeated hit of a lone round: far outside the kernel, no contribution
-            // No exact test and no branch: false positives of the pre-filter (rr2>(2h)^2) and the particle itself (rr2=0) contribute 0.
-            PackNeigh nb; nb.mu=pk1(1.f); nb.plain=pk1(1.f); nb.heavy_a=nb.heavy_b=false; nb.taua=nb.taub=nullptr;
-            if(pass==0){
-              if(FLOATING){
-                const typecode ca=g.code[p2a], cb=g.code[p2b];
-                const bool fla=B2S_CODE_ISFLOATING(ca), flb=B2S_CODE_ISFLOATING(cb);
-                float ma=1.f, mb=1.f;
-                if(fla){ const float m=g.ftomassp[B2S_CODE_TYPEVALUE(ca)]; ma=FMUL(m,k.ovmassf); nb.heavy_a=(m<=c.massf*1.2f); }
-                if(flb){ const float m=g.ftomassp[B2S_CODE_TYPEVALUE(cb)]; mb=FMUL(m,k.ovmassf); nb.heavy_b=(m<=c.massf*1.2f); }
-                nb.mu=pk(ma,mb); nb.plain=pk(fla? 0.f: 1.f,flb? 0.f: 1.f);
+        for(uint32_t j0=0;j0<npmax;j0+=16){
+          uint32_t maskA=(j0<npA? check(A,jbA,j0,min(16u,npA-j0)): 0u);
+          uint32_t maskB=(j0<npB? check(B,jbB,j0,min(16u,npB-j0)): 0u);
+          const uint32_t mine=((uint32_t(__popc(maskA))+1u)>>1)+((uint32_t(__popc(maskB))+1u)>>1);
+          #pragma unroll 1
+          for(uint32_t it=__reduce_max_sync(0xffffffffu,mine);it;it--){
+            const bool ua=(maskA!=0u);
+            uint32_t m=(ua? maskA: maskB);
+            if(m){
+              const uint32_t ka=__ffs(m)-1u; m&=m-1u;
+              const bool two=(m!=0u);
+              const uint32_t kb=(two? __ffs(m)-1u: ka); m&=m-1u;
+              if(ua)maskA=m; else maskB=m;
+              const uint32_t pb0=((ua? jbA: jbB)+j0)<<1, pmid=(ua? A.pmid: B.pmid);
+              const float sg=(ua? 1.f: -1.f), sy=FFMA(sg,kyA,pp1.y), sz=FFMA(sg,kzo,pp1.z);   // = A.sy/A.sz or B.sy/B.sz: the mirror row sits at the negated offset
+              const uint32_t p2a=pb0+ka, p2b=pb0+kb;
+              const float4 pa=__ldg(g.posp+p2a), pb=__ldg(g.posp+p2b);
+              const float4 va=__ldg(g.velrho+p2a), vb=__ldg(g.velrho+p2b);
+              const f2 drx=pk(FSUB(p2a>=pmid? sxB: sxA,pa.x),FSUB(p2b>=pmid? sxB: sxA,pb.x));
+              const f2 dry=pk(FSUB(sy,pa.y),FSUB(sy,pb.y)), drz=pk(FSUB(sz,pa.z),FSUB(sz,pb.z));
+              f2 rr2=fma2(drz,drz,fma2(dry,dry,mul2(drx,drx)));   // b2s_rr2 order
+              if(!two)rr2=pk(lo(rr2),1e30f);                      // the repeated hit of a lone round: far outside the kernel, no contribution
+              // No exact test and no branch: false positives of the pre-filter (rr2>(2h)^2) and the particle itself (rr2=0) contribute 0.
+              PackNeigh nb; nb.mu=pk1(1.f); nb.plain=pk1(1.f); nb.heavy_a=nb.heavy_b=false; nb.taua=nb.taub=nullptr;
+              if(pass==0){
+                if(FLOATING){
+                  const typecode ca=g.code[p2a], cb=g.code[p2b];
+                  const bool fla=B2S_CODE_ISFLOATING(ca), flb=B2S_CODE_ISFLOATING(cb);
+                  float ma=1.f, mb=1.f;
+                  if(fla){ const float m=g.ftomassp[B2S_CODE_TYPEVALUE(ca)]; ma=FMUL(m,k.ovmassf); nb.heavy_a=(m<=c.massf*1.2f); }
+                  if(flb){ const float m=g.ftomassp[B2S_CODE_TYPEVALUE(cb)]; mb=FMUL(m,k.ovmassf); nb.heavy_b=(m<=c.massf*1.2f); }
+                  nb.mu=pk(ma,mb); nb.plain=pk(fla? 0.f: 1.f,flb? 0.f: 1.f);
+                }
+                if(TVISCO==B2S_VISCO_LAMINARSPS){ nb.taua=(const float2*)(g.tau+size_t(p2a)*6); nb.taub=(const float2*)(g.tau+size_t(p2b)*6); }
+                pack_body<TKER,TVISCO,TDENS,FLOATING,MDBC2,false>(c,k,drx,dry,drz,rr2,velrhop1,pressp1,ovrhop1,tg,va,vb,pa.w,pb.w,nb,acc);
               }
-              if(TVISCO==B2S_VISCO_LAMINARSPS){ nb.taua=(const float2*)(g.tau+size_t(p2a)*6); nb.taub=(const float2*)(g.tau+size_t(p2b)*6); }
-              pack_body<TKER,TVISCO,TDENS,FLOATING,MDBC2,false>(c,k,drx,dry,drz,rr2,velrhop1,pressp1,ovrhop1,tg,va,vb,pa.w,pb.w,nb,acc);
-            }
-            else{
-              if(MDBC2){   // mDBC2: no mass without a submerged ghost node, tangential velocity for the viscous terms (JSphCpu.cpp:851-853,990-995)
-                nb.tva=__ldg(g.tangenvel+p2a); nb.tvb=__ldg(g.tangenvel+p2b);
-                nb.mu=pk(g.boundmode[p2a]==B2S_BMODE_MDBC2OFF? 0.f: 1.f,g.boundmode[p2b]==B2S_BMODE_MDBC2OFF? 0.f: 1.f);
+              else{
+                if(MDBC2){   // mDBC2: no mass without a submerged ghost node, tangential velocity for the viscous terms (JSphCpu.cpp:851-853,990-995)
+                  nb.tva=__ldg(g.tangenvel+p2a); nb.tvb=__ldg(g.tangenvel+p2b);
+                  nb.mu=pk(g.boundmode[p2a]==B2S_BMODE_MDBC2OFF? 0.f: 1.f,g.boundmode[p2b]==B2S_BMODE_MDBC2OFF? 0.f: 1.f);
+                }
+                pack_body<TKER,TVISCO,TDENS,FLOATING,MDBC2,true>(c,k,drx,dry,drz,rr2,velrhop1,pressp1,ovrhop1,tg,va,vb,pa.w,pb.w,nb,acc);
               }
-              pack_body<TKER,TVISCO,TDENS,FLOATING,MDBC2,true>(c,k,drx,dry,drz,rr2,velrhop1,pressp1,ovrhop1,tg,va,vb,pa.w,pb.w,nb,acc);
             }
           }
         }
@@ -212,6 +249,7 @@ __global__ void __launch_bounds__(P2_BS,(P2Cfg<TKER,TVISCO,FLOATING>::MINB)) k_f
     pack_finish<TKER,TVISCO,TDENS,false>(c,k,acc,velrhop1.w,(FLOATING && tg.ft),sf);
     finalize_store<TVISCO,TDENS>(g,c,p1,velrhop1,sf,sbnd,ace2,viscmax);
   }
+  if(lenor>0xffffu)g.st->error=B2S_ERR_UNSUPPORTED;   // a trimmed row of more than 65535 particles does not fit its descriptor: not a state to go on with
   //-Fused maxima: ViscDtMax and AceMax^2 (replaces ReduMaxFloat x2 + cudaMemcpy, JSphGpu_ker.cu:75-125).
   reduce_maxima(g.st,viscmax,ace2);
 }
@@ -249,6 +287,7 @@ int b2s_forces_pair2_launch(b2s_ctx* ctx, const ForcesArgs& g){
   const PackCte k=pack_cte(c);
   const bool ft=(c.use_floating!=0), m2=(c.mdbc2 && g.boundmode!=nullptr);
   const pair2_kernel_t kern=(c.tkernel==B2S_KERNEL_WENDLAND? p2_pick_visco<B2S_KERNEL_WENDLAND>(c.tvisco,c.tdensity,ft,m2): p2_pick_visco<B2S_KERNEL_CUBIC>(c.tvisco,c.tdensity,ft,m2));
+  { static const char* cv=getenv("B2S_P2_CARVEOUT"); if(cv)cudaFuncSetAttribute((const void*)kern,cudaFuncAttributePreferredSharedMemoryCarveout,atoi(cv)); }   // experiment: share of the SM's memory taken from L1
   kern<<<gb,P2_BS,0,ctx->stream>>>(g,k,c);
   B2S_LAUNCHED(ctx);
   B2S_CUDA(ctx,cudaGetLastError());

@@ -7,6 +7,7 @@ mkdir -p gpurun_out
 for step in "$@"; do
 case $step in
   build=*) flags=$(echo "${step#build=}" | tr ',' ' '); touch dualsphysics_b200/csrc/forces_tile.cu dualsphysics_b200/csrc/forces_pair2.cu; make -C dualsphysics_b200/csrc B2S_NVCC_EXTRA="$flags" 2>&1 | grep -E "error|rror:" ; echo "== rebuilt with: $flags"; TAG=${TAG}x;;
+  ab=*) for n in $(echo "${step#ab=}" | tr ',' ' '); do B2S_LIB_PATH=$PWD/dualsphysics_b200/lib/ab/$n/libb200sph.so timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ab_$n.json 2> gpurun_out/${TAG}_ab_$n.err; python -c "import json; d=json.load(open('gpurun_out/${TAG}_ab_$n.json')); print('$n: ms/step', round(d['ms_per_step'],3), 'ms/interaction', round(d['roofline']['ms_per_launch'],3), 'parity', d.get('parity'))"; done | tee gpurun_out/${TAG}_ab.txt;;   # libraries prebuilt by tools/build_ab.sh
   microbench) ./tools/microbench > gpurun_out/${TAG}_microbench.txt 2>&1; cat gpurun_out/${TAG}_microbench.txt;;
   pack_parity) timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "packed_variant or (golden and 5)" -s 2>&1 | grep -E "variant 5 vs 0|passed|failed|Error|error|assert" | head -40 > gpurun_out/${TAG}_pack_vs_gather.log; tail -12 gpurun_out/${TAG}_pack_vs_gather.log;;
   tile_parity) timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "tile_variant" -s 2>&1 | grep -E "variant 6 vs 0|passed|failed|Error|error|assert" | head -60 > gpurun_out/${TAG}_tile_vs_gather.log; tail -3 gpurun_out/${TAG}_tile_vs_gather.log;;
