@@ -519,6 +519,14 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   const float* vel=(const float*)avel->ptr(); const float* rho=(const float*)arho->ptr();
   std::vector<float> velrho(size_t(np)*4);
   for(unsigned i=0;i<np;i++){ velrho[size_t(i)*4]=vel[size_t(i)*3]; velrho[size_t(i)*4+1]=vel[size_t(i)*3+1]; velrho[size_t(i)*4+2]=vel[size_t(i)*3+2]; velrho[size_t(i)*4+3]=rho[i]; }
+  // radius of every floating body = max distance particle-centre (JSph::InitFloatings), from the FULL particle set of Case.bi4,
+  // i.e. before a restart replaces the positions: the body's initial centre belongs to the initial positions
+  std::vector<float> ftradius;
+  for(auto& b:s->blocks)if(b.type==2){
+    double r2max=0;
+    for(unsigned i=0;i<np;i++)if(idp[i]>=b.begin && idp[i]<b.begin+b.count){ double d2=0; for(int k=0;k<3;k++){ const double d=pos[size_t(i)*3+k]-b.center[k]; d2+=d*d; } r2max=std::max(r2max,d2); }
+    ftradius.push_back(float(sqrt(r2max)));
+  }
   // Restart (JPartsLoad4::LoadParticles with partbegin, JPartsLoad4.cpp:181-224): particle data of dir/Part_<begin>.bi4 replace the
   // initial state; the case definition (counts, constants, mk blocks) still comes from Case.xml/Case.bi4.
   std::unique_ptr<Bi4Item> pdata;
@@ -607,13 +615,6 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   s->casemassb=data->get_double("MassBound",p.massbound); s->casemassf=data->get_double("MassFluid",p.massfluid);
   int r=b2s_config_finalize(&p);
   if(r)throw std::runtime_error(std::string("configuration failed: ")+b2s_error_string(r));
-  // radius of every floating body = max distance particle-centre (JSph::InitFloatings), from the FULL particle set
-  std::vector<float> ftradius;
-  for(auto& b:s->blocks)if(b.type==2){
-    double r2max=0;
-    for(unsigned i=0;i<np;i++)if(idp[i]>=b.begin && idp[i]<b.begin+b.count){ double d2=0; for(int k=0;k<3;k++){ const double d=pos[size_t(i)*3+k]-b.center[k]; d2+=d*d; } r2max=std::max(r2max,d2); }
-    ftradius.push_back(float(sqrt(r2max)));
-  }
   // slab loading: only the particles of [cuts[rank],cuts[rank+1]) reach the device; capacity is sized for the slab
   unsigned npsel=np;
   std::vector<uint32_t> sel_idp;
