@@ -31,7 +31,7 @@ OPTIONS = "-symplectic -wendland -viscoart:0.1 -ddt:2 -ddtvalue:0.1 -dbc -cellmo
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the fluid interaction kernel at the 10M-particle
 # workload, from the `ncu --set full` captures summarised under profiles/ (file, read MB + write MB); scaled by the fluid count
 # when the bench runs another size.  A variant without a capture reports traffic null instead of a stale number.
-NCU_TRAFFIC = {5: ("profiles/r02v_ncu_step_bench.md", 452900000 + 148000000),
+NCU_TRAFFIC = {5: ("profiles/r02K_ncu_forces_pair2_v5_10M.txt", 459204352 + 180592128),
                6: ("profiles/r02i_ncu_forces_tile_v6_10M.txt", None)}
 NCU_TRAFFIC_NPF = 9281220
 # Non-tensor FP32 peak: tools/microbench.cu measures 3.798 FFMA warp-instructions per clock and SM of the nominal 4
