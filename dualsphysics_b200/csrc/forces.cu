@@ -56,27 +56,35 @@ __global__ void __launch_bounds__(F_BS) k_forces_bound(ForcesArgs g, const __gri
       const CellRange r=cell_range(g.dcell[p1],c,ds);
       const int ncx=int(ds->ncx), nsheet=int(ds->nsheet), cmx=int(ds->cellmin[0]);
       const uint32_t* beg=g.beg+ds->box_fluid;
+      // A row of neighbour cells is ONE index range (x-contiguous cells, block-relative x: at most two x offsets, b2s_internal.h
+      // B2S_XBLK), settled with two loads when it holds no fluid (most of a tank's walls) and trimmed to the cells the kernel sphere
+      // reaches.  Same particles in the same order as the cell-by-cell walk: the trim only drops cells beyond 2h.
+      const float xin=pp1.x-c.scell*float((r.cx+cmx)&((1<<B2S_XBLK)-1));
+      const bool oneblk=(((r.xini+cmx)>>B2S_XBLK)==((r.xfin-1+cmx)>>B2S_XBLK));
+      const int xmid0=(((r.xfin-1+cmx)>>B2S_XBLK)<<B2S_XBLK)-cmx;          // first cell of the second block
+      const float offxA=b2s_offx(c,r.cx+cmx,r.xini+cmx), offxB=b2s_offx(c,r.cx+cmx,r.xfin-1+cmx);
       for(int z=r.zini;z<r.zfin;z++)for(int y=r.yini;y<r.yfin;y++){
-        const int row=y*ncx+z*nsheet;
+        const uint32_t* brow=beg+(y*ncx+z*nsheet);
+        if(brow[r.xini]==brow[r.xfin])continue;
         const float offy=c.scell*float(r.cy-y), offz=c.scell*float(r.cz-z);
-        for(int x=r.xini;x<r.xfin;x++){
-          const uint32_t pini=beg[row+x], pfin=beg[row+x+1];
-          const float offx=b2s_offx(c,r.cx+cmx,x+cmx);
-          for(uint32_t p2=pini;p2<pfin;p2++){
-            const float4 pp2=g.posp[p2];
-            const float drx=b2s_dr(pp1.x,pp2.x,offx), dry=b2s_dr(pp1.y,pp2.y,offy), drz=b2s_dr(pp1.z,pp2.z,offz);
-            const float rr2=b2s_rr2(drx,dry,drz);
-            if(rr2<=c.kernelsize2 && rr2>=B2S_ALMOSTZERO){
-              const float fac=kernel_fac<TKER>(rr2,c);
-              const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
-              float massp2=c.massf;
-              if(FLOATING){ const typecode cod=g.code[p2]; if(B2S_CODE_ISFLOATING(cod))massp2=g.ftomassp[B2S_CODE_TYPEVALUE(cod)]; }
-              const float4 velrhop2=g.velrho[p2];
-              const float dvx=velrhop1.x-velrhop2.x, dvy=velrhop1.y-velrhop2.y, dvz=velrhop1.z-velrhop2.z;
-              arp1+=massp2*(dvx*frx+dvy*fry+dvz*frz)*(velrhop1.w*b2s_rcp(velrhop2.w));
-              const float dot=drx*dvx+dry*dvy+drz*dvz;
-              visc=fmaxf(dot*b2s_rcp(rr2+c.eta2),visc);
-            }
+        int xa,xb;
+        if(!row_trim(c,r,xin,FADD(pp1.y,offy),FADD(pp1.z,offz),xa,xb))continue;
+        const uint32_t pini=brow[xa], pfin=brow[xb];
+        const uint32_t pmid=(oneblk || xmid0<=xa? pini: (xmid0>=xb? pfin: brow[xmid0]));
+        for(uint32_t p2=pini;p2<pfin;p2++){
+          const float4 pp2=g.posp[p2];
+          const float drx=b2s_dr(pp1.x,pp2.x,(p2>=pmid? offxB: offxA)), dry=b2s_dr(pp1.y,pp2.y,offy), drz=b2s_dr(pp1.z,pp2.z,offz);
+          const float rr2=b2s_rr2(drx,dry,drz);
+          if(rr2<=c.kernelsize2 && rr2>=B2S_ALMOSTZERO){
+            const float fac=kernel_fac<TKER>(rr2,c);
+            const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
+            float massp2=c.massf;
+            if(FLOATING){ const typecode cod=g.code[p2]; if(B2S_CODE_ISFLOATING(cod))massp2=g.ftomassp[B2S_CODE_TYPEVALUE(cod)]; }
+            const float4 velrhop2=g.velrho[p2];
+            const float dvx=velrhop1.x-velrhop2.x, dvy=velrhop1.y-velrhop2.y, dvz=velrhop1.z-velrhop2.z;
+            arp1+=massp2*(dvx*frx+dvy*fry+dvz*frz)*(velrhop1.w*b2s_rcp(velrhop2.w));
+            const float dot=drx*dvx+dry*dvy+drz*dvz;
+            visc=fmaxf(dot*b2s_rcp(rr2+c.eta2),visc);
           }
         }
       }
