@@ -208,6 +208,29 @@ def test_errors_are_loud(tmp_path, built_lib):
     sim.close()
 
 
+def test_row_overflow_is_reported(tmp_path, built_lib):
+    """A row descriptor of the packed kernel keeps the length of a trimmed row in 16 bits (csrc/forces_pair2.cu, ROW DESCRIPTORS):
+    70000 fluid particles on one point make a row longer than that.  The kernel has to raise the context's error flag --
+    the next synchronisation fails -- instead of dropping neighbours silently; the gather kernel (variant 0) takes the same state."""
+    H.write_case(tmp_path, dp=0.01)
+    sim = dsb.Simulation(str(tmp_path / "Case"), options="-cellmode:half")
+    ctx = sim.ctx
+    idp, code, pos, velrho = (ctx.array(n).copy() for n in ("idp", "code", "pos", "velrho"))
+    fluid = np.nonzero((code >> 11) == 3)[0]
+    assert fluid.size > 70000, fluid.size
+    pos[fluid[:70000]] = pos[fluid[0]]
+    ctx.set_variant(0)
+    ctx.upload(idp, code, pos, velrho)
+    ctx.interaction(dsb.lib.INTER_SYMPREDICTOR)
+    assert ctx.info().np == idp.size                      # variant 0: no limit, the synchronisation passes
+    ctx.set_variant(5)
+    ctx.upload(idp, code, pos, velrho)
+    with pytest.raises(dsb.B2SError):
+        ctx.interaction(dsb.lib.INTER_SYMPREDICTOR)           # the flag surfaces at the synchronisation that ends the call
+        ctx.info()
+    sim.close()
+
+
 @pytest.mark.parametrize("cap", [0, 700, 150])
 @pytest.mark.parametrize("options", ["", "-cellmode:half", "-cellmode:half -ddt:1", "-cellmode:half -ddt:3", "-ddt:0"])
 def test_tile_variant_matches_gather(options, cap, tmp_path, built_lib):
