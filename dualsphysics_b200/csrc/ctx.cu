@@ -375,6 +375,37 @@ __global__ void k_beginend_int2(uint32_t nboxes, const uint32_t* __restrict__ be
   out[c]=(a==b? make_int2(0,0): make_int2(int(a),int(b)));
 }
 
+// ---- positions by id through ridp (include/b2s.h) ---------------------------------------------------------------------------
+__global__ void k_pos_byid(uint32_t n,const uint32_t* __restrict__ ids,const uint32_t* __restrict__ ridp,uint32_t nfixed,uint32_t nmot,uint32_t np,
+  const uint32_t* __restrict__ idp,const double2* __restrict__ posxy,const double* __restrict__ posz,double* __restrict__ out)
+{
+  const uint32_t i=blockIdx.x*blockDim.x+threadIdx.x;
+  if(i>=n)return;
+  const double nan=__longlong_as_double(0x7ff8000000000000ll);
+  double x=nan,y=nan,z=nan;
+  const uint32_t id=ids[i];
+  if(id>=nfixed && id-nfixed<nmot){
+    const uint32_t p=ridp[id-nfixed];
+    if(p<np && idp[p]==id){ const double2 xy=posxy[p]; x=xy.x; y=xy.y; z=posz[p]; }   // a stale entry (particle excluded since) fails the id test
+  }
+  out[size_t(i)*3]=x; out[size_t(i)*3+1]=y; out[size_t(i)*3+2]=z;
+}
+extern "C" int b2s_get_pos_byid(b2s_ctx* ctx, uint32_t n, const uint32_t* ids, double* pos_out){
+  if(!ctx || (n && (!ids || !pos_out)))return B2S_ERR_ARG;
+  if(!n)return B2S_OK;
+  B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  int r=b2s_sync_info(ctx); if(r)return r;
+  r=ensure_scratch(ctx,size_t(n)*(4+24)+64); if(r)return r;
+  cudaStream_t s=ctx->stream;
+  uint32_t* dids=(uint32_t*)ctx->scratch; double* dout=(double*)((char*)ctx->scratch+((size_t(n)*4+63)/64)*64);
+  B2S_CUDA(ctx,cudaMemcpyAsync(dids,ids,size_t(n)*4,cudaMemcpyHostToDevice,s));
+  k_pos_byid<<<b2s_blocks(n,128),128,0,s>>>(n,dids,ctx->ridp,ctx->prm.casenfixed,ctx->prm.casenmoving+ctx->prm.casenfloat,ctx->np_host,
+                                           ctx->cur.idp,ctx->cur.posxy,ctx->cur.posz,dout); B2S_LAUNCHED(ctx);
+  B2S_CUDA(ctx,cudaMemcpyAsync(pos_out,dout,size_t(n)*24,cudaMemcpyDeviceToHost,s));
+  B2S_CUDA(ctx,cudaStreamSynchronize(s));
+  return B2S_OK;
+}
+
 extern "C" int b2s_get_array(b2s_ctx* ctx, const char* name, void* dst, size_t capacity_bytes, size_t* count_out){
   if(!ctx || !name || !dst)return B2S_ERR_ARG;
   int r=b2s_sync_info(ctx); if(r)return r;

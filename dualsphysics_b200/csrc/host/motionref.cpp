@@ -75,21 +75,30 @@ void MotionRefSave::config(uint32_t n,const uint32_t* idp,const double* pos){
   }
 }
 
+namespace {
+// Head of PartMotionRef.ibi4 / PartMotionRef2.ibi4 (JPartMotRefBi4Save::Config, JPartMotRefBi4Save.cpp:149-191).  The arrays live in `st`.
+struct HeadStore { std::vector<uint16_t> mkb; std::vector<uint32_t> nid,id; std::vector<double> ps,dis; };
+void make_head(Bi4Item& hd,HeadStore& st,const std::vector<MotRefBody>& bodies,unsigned nmoving,unsigned nfloat,
+               const std::string& appname,bool mainfile,double timeout,unsigned mkboundfirst){
+  const unsigned nmk=unsigned(bodies.size());
+  hd.set_text("AppName",appname); hd.set_uint("FormatVer",230729); hd.set_bool("MainFile",mainfile); hd.set_double("TimeOut",timeout);
+  { Bi4Value v; v.name="MkBoundFirst"; v.type=BT_USHORT; v.i=0; v.u=mkboundfirst; v.d=0; v.d3[0]=v.d3[1]=v.d3[2]=0; hd.values.push_back(v); }
+  hd.set_uint("MkMovingCount",nmoving); hd.set_uint("MkFloatCount",nfloat); hd.set_uint("MkCount",nmk);
+  st.mkb.resize(nmk); st.nid.resize(nmk); st.id.resize(size_t(nmk)*3); st.ps.resize(size_t(nmk)*9); st.dis.resize(size_t(nmk)*3);
+  for(unsigned c=0;c<nmk;c++){
+    const MotRefBody& b=bodies[c]; st.mkb[c]=b.mkbound; st.nid[c]=b.nid;
+    for(unsigned i=0;i<3;i++){ st.id[c*3+i]=b.id[i]; st.dis[c*3+i]=b.dis[i]; for(int k=0;k<3;k++)st.ps[(c*3+i)*3+k]=b.ps[i][k]; }
+  }
+  hd.add_array_ext("MkBound",BT_USHORT,nmk,st.mkb.data()); hd.add_array_ext("Nid",BT_UINT,nmk,st.nid.data());
+  hd.add_array_ext("Id",BT_UINT,nmk*3,st.id.data()); hd.add_array_ext("Ps",BT_DOUBLE3,nmk*3,st.ps.data()); hd.add_array_ext("Dis",BT_DOUBLE,nmk*3,st.dis.data());
+}
+}
+
 void MotionRefSave::save_part(const std::string& dirdata,const std::string& appname,double timeout,unsigned mkboundfirst,bool fresh,
                               unsigned cpart,double timestep,unsigned step,uint32_t n,const uint32_t* idp,const double* pos){
   const unsigned nmk=unsigned(bodies.size()); if(!nmk)return;
-  // head (JPartMotRefBi4Save::Config, JPartMotRefBi4Save.cpp:149-191)
-  Bi4Item hd("JPartMotRefBi4");
-  hd.set_text("AppName",appname); hd.set_uint("FormatVer",230729); hd.set_bool("MainFile",true); hd.set_double("TimeOut",timeout);
-  { Bi4Value v; v.name="MkBoundFirst"; v.type=BT_USHORT; v.i=0; v.u=mkboundfirst; v.d=0; v.d3[0]=v.d3[1]=v.d3[2]=0; hd.values.push_back(v); }
-  hd.set_uint("MkMovingCount",nmoving); hd.set_uint("MkFloatCount",nfloat); hd.set_uint("MkCount",nmk);
-  std::vector<uint16_t> mkb(nmk); std::vector<uint32_t> nid(nmk),id(size_t(nmk)*3); std::vector<double> ps(size_t(nmk)*9),dis(size_t(nmk)*3);
-  for(unsigned c=0;c<nmk;c++){
-    const MotRefBody& b=bodies[c]; mkb[c]=b.mkbound; nid[c]=b.nid;
-    for(unsigned i=0;i<3;i++){ id[c*3+i]=b.id[i]; dis[c*3+i]=b.dis[i]; for(int k=0;k<3;k++)ps[(c*3+i)*3+k]=b.ps[i][k]; }
-  }
-  hd.add_array_ext("MkBound",BT_USHORT,nmk,mkb.data()); hd.add_array_ext("Nid",BT_UINT,nmk,nid.data());
-  hd.add_array_ext("Id",BT_UINT,nmk*3,id.data()); hd.add_array_ext("Ps",BT_DOUBLE3,nmk*3,ps.data()); hd.add_array_ext("Dis",BT_DOUBLE,nmk*3,dis.data());
+  Bi4Item hd("JPartMotRefBi4"); HeadStore st;
+  make_head(hd,st,bodies,nmoving,nfloat,appname,true,timeout,mkboundfirst);
   // current positions of the reference particles (JDsPartMotionSave::LoadPosRefCpu, JDsPartMotionSave.cpp:188-208)
   std::vector<double> posref(size_t(nmk)*9,0.0);
   for(unsigned c=0;c<nmk;c++)for(unsigned i=0;i<3;i++){
@@ -104,6 +113,29 @@ void MotionRefSave::save_part(const std::string& dirdata,const std::string& appn
   pt.set_uint("Cpart",cpart); pt.set_double("TimeStep",timestep); pt.set_uint("Step",step);
   pt.add_array_ext("PosRef",BT_DOUBLE3,nmk*3,posref.data());
   bi4_save_listapp(dirdata+"PartMotionRef.ibi4","JPartMotRefBi4",hd,&pt,fresh);
+}
+
+std::vector<uint32_t> MotionRefSave::ref_ids()const{
+  std::vector<uint32_t> ids;
+  for(const MotRefBody& b:bodies)for(unsigned i=0;i<3;i++){
+    if(i>=b.nid)throw std::runtime_error("PartMotionRef: a body has fewer than three distinct reference particles");
+    ids.push_back(b.id[i]);
+  }
+  return ids;
+}
+
+void MotionRefSave::save_extra(const std::string& dirdata,const std::string& appname,double timeout2,unsigned mkboundfirst,bool fresh,
+                               unsigned cpart,unsigned count,const double* times,const uint32_t* steps,const double* posref){
+  const unsigned nmk=unsigned(bodies.size()); if(!nmk || !count)return;
+  Bi4Item hd("JPartMotRefBi4"); HeadStore st;
+  make_head(hd,st,bodies,nmoving,nfloat,appname,false,timeout2,mkboundfirst);
+  char nm[32]; snprintf(nm,sizeof(nm),"PART_%04u",cpart);
+  Bi4Item pt(nm); pt.hide=true;
+  pt.set_uint("Cpart",cpart);
+  if(count==1){ pt.set_double("TimeStep",times[0]); pt.set_uint("Step",steps[0]); }   // MakeBdPartSingle
+  else{ pt.set_uint("Count",count); pt.add_array_ext("TimeStep",BT_DOUBLE,count,times); pt.add_array_ext("Step",BT_UINT,count,steps); }   // MakeBdPartArray
+  pt.add_array_ext("PosRef",BT_DOUBLE3,count*nmk*3,posref);
+  bi4_save_listapp(dirdata+"PartMotionRef2.ibi4","JPartMotRefBi4",hd,&pt,fresh);
 }
 
 } // namespace b2s

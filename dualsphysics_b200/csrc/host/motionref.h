@@ -22,6 +22,13 @@ public:
   // Appends PART_<cpart> (head written when `fresh`, JPartMotRefBi4Save::SaveInitial + SavePart).
   void save_part(const std::string& dirdata,const std::string& appname,double timeout,unsigned mkboundfirst,bool fresh,
                  unsigned cpart,double timestep,unsigned step,uint32_t n,const uint32_t* idp,const double* pos);
+  // The extra-frequency file PartMotionRef2.ibi4 (TimeOutExtra / -toutx; JDsPartMotionSave::AddDataExtra*, JPartMotRefBi4Save::
+  // AddDataPart / SaveStoredData, JPartMotRefBi4Save.cpp:225-278): `count` records (time, step, 3 positions per body) collected while
+  // PART <cpart> was the next one to be written; one record is stored like a PART of the main file, several as arrays.
+  void save_extra(const std::string& dirdata,const std::string& appname,double timeout2,unsigned mkboundfirst,bool fresh,
+                  unsigned cpart,unsigned count,const double* times,const uint32_t* steps,const double* posref);
+  // ids of the reference particles, three per body in file order (what posref of save_extra holds, 9 doubles per body)
+  std::vector<uint32_t> ref_ids()const;
   size_t body_count()const{ return bodies.size(); }
   const MotRefBody& body(size_t c)const{ return bodies[c]; }
 private:

@@ -68,6 +68,11 @@ struct b2s_sim {
   std::string svextraparts;                                             // -svextraparts / SaveExtraParts: PARTs that get a PartExtra_XXXX.bi4
   unsigned out_total[4]={0,0,0,0};                                    // excluded particles written to PartOut so far, by motive (0: all)
   MotionRefSave motref; bool motref_ready=false;                       // PartMotionRef.ibi4
+  // Extra-frequency output of the body data (TimeOutExtra / -toutx; JSph.cpp:789-790,859-870): PartFloatInfo2.ibi4 and PartMotionRef2.ibi4.
+  // Records are collected at the end of the steps that reach the schedule and written with the next PART (JSphCpuSingle.cpp:1201-1206).
+  double timepartextra=-1, timepartextranext=DBL_MAX;
+  struct ExtraStore { std::vector<double> time; std::vector<uint32_t> step; std::vector<double> cen, posref; std::vector<float> f3[10]; void clear(){ time.clear(); step.clear(); cen.clear(); posref.clear(); for(auto& v:f3)v.clear(); } };
+  ExtraStore xfloat, xmotion; bool xfloat_fresh=true, xmotion_fresh=true;
   bool initial_saved, head_saved; unsigned partbegin, partbeginfirst; std::string partbegindir; double partbegintime, partbegindtpre;   // restart (-partbegin)
   // run control (JSph members)
   double timemax, timepart, timepartnext; unsigned part, nstepsbreak; bool svallsteps, svposdouble, svdata;
@@ -172,6 +177,7 @@ static void load_case(b2s_sim* s,const std::string& options){
   // TimeMax and TimeOut are mandatory in the reference (GetValueDouble without a default, JSph.cpp:786-787)
   if(!ep.exists("TimeMax") || !ep.exists("TimeOut"))throw std::runtime_error("Case.xml: the parameters TimeMax and TimeOut are mandatory");
   s->timemax=ep.num("TimeMax",0); s->timepart=ep.num("TimeOut",0);
+  s->timepartextra=ep.num("TimeOutExtra",-1);                            // optional (JSph.cpp:789)
   p.dtini=std::max(0.0,ep.num("DtIni",0)); p.dtmin=std::max(0.0,ep.num("DtMin",0)); p.coefdtmin=double(float(ep.num("CoefDtMin",0.05)));
   p.dt_allparticles=(ep.inum("DtAllParticles",0)==1);
   if(ep.num("DtFixed",0)!=0)throw std::runtime_error("DtFixed is not supported by this build");
@@ -229,6 +235,7 @@ static void load_case(b2s_sim* s,const std::string& options){
       else if(w=="FTPAUSE")p.ftpause=atof(a.c_str());
       else if(w=="TMAX")s->timemax=atof(a.c_str());
       else if(w=="TOUT")s->timepart=atof(a.c_str());
+      else if(w=="TOUTX")s->timepartextra=atof(a.c_str());                // JSphCfgRun.cpp:494-496
       else if(w=="NSTEPS")s->nstepsbreak=unsigned(atoi(a.c_str()));
       else if(w=="PARTBEGIN"){   // -partbegin:begin[:first] dir  (JSphCfgRun.cpp:462-470): restart from dir/Part_<begin>.bi4
         s->partbegin=unsigned(atoi(a2(0).c_str())); s->partbeginfirst=(a2(1).empty()? s->partbegin: unsigned(atoi(a2(1).c_str())));
@@ -766,6 +773,7 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
     s->part=s->partbeginfirst;
   }
   if(slab_nranks>0){
+    if(slab_nranks>1 && s->timepartextra>=0)throw std::runtime_error("TimeOutExtra / -toutx (PartFloatInfo2, PartMotionRef2) is not written in slab-decomposed runs: remove it or run on one GPU");
     if(slab_nranks>1 && !s->gauges.empty())throw std::runtime_error("gauges (<special><gauges>) are not evaluated in slab-decomposed runs: remove them or run on one GPU");
     r=b2s_slab_config(s->ctx,slab_rank,slab_nranks,s->slab_cuts[slab_rank],s->slab_cuts[slab_rank+1]);
     if(r)throw std::runtime_error(std::string("b2s_slab_config failed: ")+b2s_last_error(s->ctx));
@@ -788,6 +796,40 @@ static bool svextra_check(const std::string& cfg,unsigned cpart){
 }
 
 // ---- PART output (JSph::SavePartData / JPartDataBi4) ----------------------------------------------------
+// One record of the extra-frequency body output (JSphCpuSingle.cpp:1201-1206: PartFloatSave->AddDataExtra + PartMotionSave->AddDataExtraCpu
+// at the end of a step that reached TimePartExtraNext): the state of the floating bodies and the positions of the reference particles.
+static void extra_collect(b2s_sim* s,const b2s_info& inf){
+  const b2s_params& p=s->prm;
+  if(p.casenfloat){
+    std::vector<const PartBlock*> fb; for(auto& b:s->blocks)if(b.type==2)fb.push_back(&b);
+    const unsigned ftc=unsigned(fb.size());
+    std::vector<b2s_floating> fts(ftc);
+    if(b2s_get_floatings(s->ctx,ftc,fts.data()))throw std::runtime_error(std::string("b2s_get_floatings failed: ")+b2s_last_error(s->ctx));
+    b2s_sim::ExtraStore& x=s->xfloat;
+    x.time.push_back(inf.timestep); x.step.push_back(inf.nstep);
+    for(unsigned cf=0;cf<ftc;cf++)for(int k=0;k<3;k++){
+      x.cen.push_back(fts[cf].center[k]);
+      const float v[10]={fts[cf].fvel[k],fts[cf].fomega[k],fts[cf].facelin[k],fts[cf].faceang[k],0.f,0.f,fts[cf].fluforcelin[k],fts[cf].fluforceang[k],fts[cf].preacelin[k],fts[cf].preaceang[k]};
+      for(int a=0;a<10;a++)x.f3[a].push_back(v[a]);
+    }
+  }
+  if((p.casenmoving || p.casenfloat) && s->motref_ready){
+    const std::vector<uint32_t> ids=s->motref.ref_ids();
+    std::vector<double> pr(ids.size()*3);
+    if(b2s_get_pos_byid(s->ctx,uint32_t(ids.size()),ids.data(),pr.data()))throw std::runtime_error(std::string("b2s_get_pos_byid failed: ")+b2s_last_error(s->ctx));
+    for(size_t k=0;k<ids.size();k++)if(pr[k*3]!=pr[k*3])throw std::runtime_error("PartMotionRef2: reference particle "+std::to_string(ids[k])+" is not in the simulation any more");
+    b2s_sim::ExtraStore& x=s->xmotion;
+    x.time.push_back(inf.timestep); x.step.push_back(inf.nstep); x.posref.insert(x.posref.end(),pr.begin(),pr.end());
+  }
+}
+// JSph::TimeOutExtraUpdate (JSph.cpp:859-870)
+static void extra_update_next(b2s_sim* s,double t){
+  if(s->timepartextra<0)return;
+  double tn=t;
+  if(s->timepartextra){ unsigned ct=unsigned(t/s->timepartextra); tn=s->timepartextra*ct; for(;tn<=t;ct++)tn=s->timepartextra*ct; }
+  s->timepartextranext=tn;
+}
+
 static void save_part(b2s_sim* s){
   const b2s_params& p=s->prm;
   // a slab rank holds 1/N of the case: its buffers follow what it holds (b2s_download_particles_byid returns at most np)
@@ -886,11 +928,14 @@ static void save_part(b2s_sim* s){
     r=b2s_get_floatings(s->ctx,ftc,fts.data());
     if(r)throw std::runtime_error(std::string("b2s_get_floatings failed: ")+b2s_last_error(s->ctx));
     unsigned mkboundfirst=0; for(auto& b:s->blocks)if(b.type!=3){ mkboundfirst=b.mk-b.mktype; break; }
-    Bi4Item hd("JPartFloatInfoBi4");
-    hd.set_text("AppName","b200sph v0.1 (DualSPHysics v5.4 case interface)"); hd.set_uint("FormatVer",230729); hd.set_bool("MainFile",true);
-    hd.set_double("TimeOut",s->timepart);
+    Bi4Item hd("JPartFloatInfoBi4"), hd2("JPartFloatInfoBi4");   // hd2: the head of PartFloatInfo2.ibi4 (MainFile=false, its own TimeOut)
+    for(Bi4Item* h:{&hd,&hd2}){
+    Bi4Item& hd=*h;
+    hd.set_text("AppName","b200sph v0.1 (DualSPHysics v5.4 case interface)"); hd.set_uint("FormatVer",230729); hd.set_bool("MainFile",h!=&hd2);
+    hd.set_double("TimeOut",h!=&hd2? s->timepart: s->timepartextra);
     { Bi4Value v; v.name="MkBoundFirst"; v.type=BT_USHORT; v.i=0; v.u=mkboundfirst; v.d=0; v.d3[0]=v.d3[1]=v.d3[2]=0; hd.values.push_back(v); }
     hd.set_uint("FtCount",ftc); hd.set_uint("FptCount",0);
+    }
     std::vector<uint16_t> mkb(ftc); std::vector<uint32_t> beg(ftc),cnt(ftc); std::vector<float> mass(ftc),massp(ftc),radi(ftc);
     std::vector<double> cen(size_t(ftc)*3); std::vector<float> f3[10]; for(auto& v:f3)v.assign(size_t(ftc)*3,0.f);
     for(unsigned cf=0;cf<ftc;cf++){
@@ -900,14 +945,34 @@ static void save_part(b2s_sim* s){
         f3[6][cf*3+k]=fts[cf].fluforcelin[k]; f3[7][cf*3+k]=fts[cf].fluforceang[k]; f3[8][cf*3+k]=fts[cf].preacelin[k]; f3[9][cf*3+k]=fts[cf].preaceang[k];
       }
     }
-    hd.add_array_ext("MkBound",BT_USHORT,ftc,mkb.data()); hd.add_array_ext("Beginp",BT_UINT,ftc,beg.data()); hd.add_array_ext("Countp",BT_UINT,ftc,cnt.data());
-    hd.add_array_ext("Mass",BT_FLOAT,ftc,mass.data()); hd.add_array_ext("Massp",BT_FLOAT,ftc,massp.data()); hd.add_array_ext("Radius",BT_FLOAT,ftc,radi.data());
+    for(Bi4Item* h:{&hd,&hd2}){
+      h->add_array_ext("MkBound",BT_USHORT,ftc,mkb.data()); h->add_array_ext("Beginp",BT_UINT,ftc,beg.data()); h->add_array_ext("Countp",BT_UINT,ftc,cnt.data());
+      h->add_array_ext("Mass",BT_FLOAT,ftc,mass.data()); h->add_array_ext("Massp",BT_FLOAT,ftc,massp.data()); h->add_array_ext("Radius",BT_FLOAT,ftc,radi.data());
+    }
     Bi4Item pf(nm); pf.hide=true;
     pf.set_uint("Cpart",s->part); pf.set_double("TimeStep",inf.timestep); pf.set_uint("Step",inf.nstep);
     pf.add_array_ext("center",BT_DOUBLE3,ftc,cen.data());
     static const char* fn3[10]={"fvel","fomega","facelin","faceang","extforcelin","extforceang","fluforcelin","fluforceang","preacelin","preaceang"};
     for(int a=0;a<10;a++)pf.add_array_ext(fn3[a],BT_FLOAT3,ftc,f3[a].data());
     bi4_save_listapp(s->dirdata+"PartFloatInfo.ibi4","JPartFloatInfoBi4",hd,&pf,fresh);
+    if(s->timepartextra>=0){   // PartFloatInfo2.ibi4: what was collected since the last PART (JDsPartFloatSave::SaveDataExtra, JPartFloatInfoBi4Save::SaveStoredData)
+      b2s_sim::ExtraStore& x=s->xfloat;
+      if(s->xfloat_fresh && x.time.empty()){   // the first PART of the run is also the first extra record (JSph.cpp:2804-2806)
+        x.time.push_back(inf.timestep); x.step.push_back(inf.nstep); x.cen.insert(x.cen.end(),cen.begin(),cen.end());
+        for(int a=0;a<10;a++)x.f3[a].insert(x.f3[a].end(),f3[a].begin(),f3[a].end());
+      }
+      const unsigned cnt2=unsigned(x.time.size());
+      if(cnt2){
+        Bi4Item pe(nm); pe.hide=true;
+        pe.set_uint("Cpart",s->part);
+        if(cnt2==1){ pe.set_double("TimeStep",x.time[0]); pe.set_uint("Step",x.step[0]); }
+        else{ pe.set_uint("Count",cnt2); pe.add_array_ext("TimeStep",BT_DOUBLE,cnt2,x.time.data()); pe.add_array_ext("Step",BT_UINT,cnt2,x.step.data()); }
+        pe.add_array_ext("center",BT_DOUBLE3,ftc*cnt2,x.cen.data());
+        for(int a=0;a<10;a++)pe.add_array_ext(fn3[a],BT_FLOAT3,ftc*cnt2,x.f3[a].data());
+        bi4_save_listapp(s->dirdata+"PartFloatInfo2.ibi4","JPartFloatInfoBi4",hd2,&pe,s->xfloat_fresh);
+        s->xfloat_fresh=false; x.clear();
+      }
+    }
   }
   if(!pieces && p.tboundary==B2S_BC_MDBC && svextra_check(s->svextraparts,s->part)){
     // PartExtra_XXXX.bi4 (JSphCpuSingle::SaveExtraData, JSphCpuSingle.cpp:1309-1322; JDsExtraDataSave::InitPartData/AddNormals,
@@ -938,6 +1003,23 @@ static void save_part(b2s_sim* s){
     }
     s->motref.save_part(s->dirdata,"b200sph v0.1 (DualSPHysics v5.4 case interface)",s->timepart,mkboundfirst,fresh,
                         s->part,inf.timestep,inf.nstep,nb,idp.data(),pos.data());
+    if(s->timepartextra>=0){   // PartMotionRef2.ibi4 (JDsPartMotionSave::SaveDataExtra)
+      b2s_sim::ExtraStore& x=s->xmotion;
+      if(s->xmotion_fresh && x.time.empty()){   // the first PART of the run is also the first extra record (JSph.cpp:2787-2788)
+        const std::vector<uint32_t> ids=s->motref.ref_ids();
+        x.time.push_back(inf.timestep); x.step.push_back(inf.nstep);
+        for(uint32_t id:ids){
+          const uint32_t* q=std::lower_bound(idp.data(),idp.data()+nb,id);
+          if(q==idp.data()+nb || *q!=id)throw std::runtime_error("PartMotionRef2: reference particle "+std::to_string(id)+" is not in the simulation any more");
+          for(int k=0;k<3;k++)x.posref.push_back(pos[size_t(q-idp.data())*3+k]);
+        }
+      }
+      if(!x.time.empty()){
+        s->motref.save_extra(s->dirdata,"b200sph v0.1 (DualSPHysics v5.4 case interface)",s->timepartextra,mkboundfirst,s->xmotion_fresh,
+                             s->part,unsigned(x.time.size()),x.time.data(),x.step.data(),x.posref.data());
+        s->xmotion_fresh=false; x.clear();
+      }
+    }
   }
   if(!s->head_saved && s->piece!=0)s->head_saved=true;   // Part_Head.ibi4 comes from rank 0
   if(!s->head_saved){
@@ -1113,6 +1195,7 @@ extern "C" int b2s_sim_run(b2s_sim* s,uint32_t nsteps_break,double* time_out,uin
     if(save && !s->initial_saved){   // the initial PART (PartIni: 0, or the first PART number of a restart)
       save_part(s); s->part++; s->initial_saved=true;
       const double t0=inf.timestep;
+      extra_update_next(s,t0);
       if(s->svallsteps)s->timepartnext=t0;
       else{ unsigned ct=unsigned(t0/s->timepart); double tn=s->timepart*ct; for(;tn<=t0;ct++)tn=s->timepart*ct; s->timepartnext=tn; }
     }
@@ -1126,6 +1209,7 @@ extern "C" int b2s_sim_run(b2s_sim* s,uint32_t nsteps_break,double* time_out,uin
       t=inf.timestep; nstep++;
       s->part_dtmin=std::min(s->part_dtmin,dt); s->part_dtmax=std::max(s->part_dtmax,dt);
       if(!s->gauges.empty())gauges_record(s,t);
+      if(save && s->timepartextra>=0 && t>=s->timepartextranext){ extra_collect(s,inf); extra_update_next(s,t); }
       if(save && t>=s->timepartnext){
         save_part(s); s->part++;
         if(s->svallsteps)s->timepartnext=t;

@@ -162,6 +162,11 @@ int b2s_download_particles_byid(b2s_ctx* ctx, uint32_t* np_out, uint32_t* idp, d
  * fails with B2S_ERR_ARG if capacity_bytes is too small. */
 int b2s_get_array(b2s_ctx* ctx, const char* name, void* dst, size_t capacity_bytes, size_t* count_out);
 int b2s_get_info(b2s_ctx* ctx, b2s_info* out);
+/* Positions of n particles of the moving / floating blocks by id (CaseNfixed <= id < CaseNbound), through the device-side
+ * id -> index table of the last divide (RidpMot, JSphGpu.cpp:1173-1180): what JDsPartMotionSave::AddDataExtraGpu
+ * (JDsPartMotionSave.cpp:301-313) reads for the extra-frequency motion file.  pos_out[3n]; a particle that left the
+ * simulation comes back as NaN. */
+int b2s_get_pos_byid(b2s_ctx* ctx, uint32_t n, const uint32_t* ids, double* pos_out);
 /* Restart support (JSph.cpp:2214-2225, -partbegin): sets the simulated time and, if >0, SymplecticDtPre (the dt the next
  * Symplectic step starts with).  Call after b2s_upload_particles. */
 int b2s_set_time(b2s_ctx* ctx, double timestep, double symplectic_dtpre);

@@ -51,6 +51,15 @@ int b2s_download_particles_byid(b2s_ctx* c,uint32_t* np_out,uint32_t* idp,double
   if(np_out)*np_out=c->np;
   return B2S_OK;
 }
+int b2s_get_pos_byid(b2s_ctx* c,uint32_t n,const uint32_t* ids,double* pos_out){
+  for(uint32_t k=0;k<n;k++){
+    const auto it=std::find(c->idp.begin(),c->idp.end(),ids[k]);
+    if(it==c->idp.end())return B2S_ERR_ARG;
+    const size_t i=size_t(it-c->idp.begin());
+    for(int d=0;d<3;d++)pos_out[size_t(k)*3+d]=c->pos[i*3+d];
+  }
+  return B2S_OK;
+}
 int b2s_get_info(b2s_ctx* c,b2s_info* out){
   memset(out,0,sizeof(*out));
   const uint32_t npb=c->prm.casenfixed+c->prm.casenmoving;
