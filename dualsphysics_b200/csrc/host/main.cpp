@@ -22,7 +22,7 @@ static void say(const char* fmt,...){
 int main(int argc,char** argv){
   if(argc<3){
     printf("usage: %s <case (without .xml)> <dirout> [-symplectic|-verlet] [-wendland|-cubic] [-viscoart:v|-viscolam:v|-viscolamsps:v]\n"
-           "          [-ddt:0-3] [-ddtvalue:v] [-dbc|-mdbc] [-cellmode:full|half] [-tmax:t] [-tout:t] [-nsteps:n] [-svsteps:1] [-sv:none]\n",argv[0]);
+           "          [-ddt:0-3] [-ddtvalue:v] [-dbc|-mdbc] [-cellmode:full|half] [-tmax:t] [-tout:t] [-toutx:t] [-nsteps:n] [-svsteps:1] [-sv:none]\n",argv[0]);
     return 1;
   }
   const auto tstart=std::chrono::steady_clock::now();

@@ -100,7 +100,7 @@ ABI_SYMBOLS = [
     "b2s_upload_particles", "b2s_download_particles", "b2s_download_particles_byid", "b2s_get_array",
     "b2s_get_info", "b2s_set_time", "b2s_celldiv", "b2s_interaction", "b2s_compute_verlet", "b2s_compute_symplectic_pre",
     "b2s_compute_symplectic_corr", "b2s_compute_step", "b2s_run_steps", "b2s_add_motion_rectsinu", "b2s_add_motion", "b2s_add_damping_plane", "b2s_add_damping_box", "b2s_out_enable", "b2s_out_fetch", "b2s_gauge_add_force", "b2s_gauge_add_maxz",
-    "b2s_move_linear", "b2s_set_floatings", "b2s_get_floatings", "b2s_count_pairs", "b2s_time_interaction",
+    "b2s_move_linear", "b2s_set_floatings", "b2s_get_floatings", "b2s_get_pos_byid", "b2s_count_pairs", "b2s_time_interaction",
     "b2s_gauge_add_velocity", "b2s_gauge_add_swl", "b2s_gauges_compute", "b2s_gauge_result",
     "b2s_launch_count", "b2s_get_stream", "b2s_set_interaction_variant", "b2s_debug_set_tile_cap", "b2s_slab_config",
     "b2s_slab_histogram", "b2s_slab_set_range", "b2s_slab_drop_ghosts", "b2s_slab_record_bytes", "b2s_slab_pack", "b2s_slab_unpack", "b2s_slab_pack_both", "b2s_slab_unpack_both", "b2s_slab_dt_buffer", "b2s_slab_forces",
@@ -161,6 +161,7 @@ def load_library():
     lib.b2s_move_linear.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     lib.b2s_set_floatings.argtypes = [vp, C.c_uint32, C.POINTER(Floating)]
     lib.b2s_get_floatings.argtypes = [vp, C.c_uint32, C.POINTER(Floating)]
+    lib.b2s_get_pos_byid.argtypes = [vp, C.c_uint32, vp, vp]
     lib.b2s_count_pairs.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.b2s_time_interaction.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     lib.b2s_launch_count.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
@@ -510,6 +511,13 @@ class Context:
     def set_floatings(self, fts):
         arr = (Floating * len(fts))(*fts)
         self._chk(self._lib.b2s_set_floatings(self._h, len(fts), arr))
+
+    def pos_byid(self, ids) -> np.ndarray:
+        """Positions of moving / floating particles by id (b2s_get_pos_byid); NaN rows for particles that left the simulation."""
+        ids = np.ascontiguousarray(ids, np.uint32)
+        out = np.empty((ids.shape[0], 3), np.float64)
+        self._chk(self._lib.b2s_get_pos_byid(self._h, ids.shape[0], ids.ctypes.data, out.ctypes.data))
+        return out
 
     def get_floatings(self, n):
         arr = (Floating * n)()

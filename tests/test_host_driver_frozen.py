@@ -328,3 +328,63 @@ def test_slab_ranks_write_part_pieces(frozen, tmp_path):
     assert bi4.load(str(out / "data" / "Part_Head.ibi4")).get("Npiece") == nranks
     for sim in sims:
         lib.b2s_sim_free(sim)
+
+
+def test_extra_frequency_body_files(cli, tmp_path):
+    """-toutx / TimeOutExtra: PartFloatInfo2.ibi4 and PartMotionRef2.ibi4 (JSph.cpp:789-790,859-870, JSphCpuSingle.cpp:1201-1206,
+    JPartMotRefBi4Save.cpp:225-278).  The records a PART item holds follow from the two schedules alone, so the frozen clock pins
+    them: a step whose end reaches the extra schedule adds a record to the PART that is written next; one record is stored like a
+    PART of the main file, several as arrays.  Heads and item structures equal the reference's files
+    (tests/golden/ref_part_extra2, tools/make_ref_part_extra2.py)."""
+    refdir = os.path.join(H.GOLDEN, "ref_part_extra2")
+    fx = json.load(open(os.path.join(refdir, "fixture_extra2.json")))
+    H.write_case(tmp_path, **fx["spec"])
+    out = tmp_path / "out"
+    r = _run(cli, tmp_path / "Case", out, "-toutx:%g" % fx["toutx"])
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    # the schedule restated: t_n = n/1024; extra records first, then the PART of the same step (JSphCpuSingle.cpp:1201-1230)
+    tmax, tout, toutx = fx["spec"]["params"]["TimeMax"], fx["spec"]["params"]["TimeOut"], fx["toutx"]
+
+    def nxt(t, period):
+        ct = int(t / period)
+        tn = period * ct
+        while tn <= t:
+            tn = period * ct
+            ct += 1
+        return tn
+    expect, pending, part = {0: [(0.0, 0)]}, [], 1
+    n, t, nx, npart = 0, 0.0, nxt(0.0, toutx), nxt(0.0, tout)
+    while t < tmax:
+        n += 1
+        t = n * DT
+        if t >= nx:
+            pending.append((t, n)); nx = nxt(t, toutx)
+        if t >= npart:
+            if pending:
+                expect[part] = pending
+            pending, part, npart = [], part + 1, nxt(t, tout)
+    for name, arr in (("PartFloatInfo2.ibi4", "center"), ("PartMotionRef2.ibi4", "PosRef")):
+        ours, ref = bi4.load_list(str(out / "data" / name)), bi4.load_list(os.path.join(refdir, name))
+        assert _list_structure(ours[:1]) == _list_structure(ref[:1]), name
+        for key in ("FormatVer", "MainFile", "TimeOut", "MkBoundFirst"):
+            assert ours[0].get(key) == ref[0].get(key), (name, key)
+        assert ours[0].get("MainFile") is False or ours[0].get("MainFile") == 0
+        single = next(_list_structure([it])[0][2:] for it in ref[1:] if it.get("Count") is None)
+        multi = next(_list_structure([it])[0][2:] for it in ref[1:] if it.get("Count") is not None)
+        assert [it.get("Cpart") for it in ours[1:]] == sorted(expect), name
+        per = 1 if arr == "center" else 6                      # one floating body; two bodies x three reference particles
+        for it in ours[1:]:
+            rec = expect[it.get("Cpart")]
+            if len(rec) == 1:
+                assert _list_structure([it])[0][2:] == single and it.get("Step") == rec[0][1] and abs(it.get("TimeStep") - rec[0][0]) < 1e-15
+            else:
+                assert _list_structure([it])[0][2:] == multi and it.get("Count") == len(rec)
+                assert list(it.array("Step")) == [s for _, s in rec] and np.allclose(it.array("TimeStep"), [x for x, _ in rec], atol=1e-15)
+            assert np.asarray(it.array(arr)).reshape(-1, 3).shape[0] == per * len(rec)
+    # frozen bodies: every record repeats the reference positions of the head
+    om = bi4.load_list(str(out / "data" / "PartMotionRef2.ibi4"))
+    for it in om[1:]:
+        pr = np.asarray(it.array("PosRef")).reshape(-1, 6, 3)
+        assert all(np.array_equal(q, np.asarray(om[0].array("Ps")).reshape(6, 3)) for q in pr)
+    # slab-decomposed runs refuse the option instead of dropping the files
+    assert os.path.exists(out / "data" / "PartFloatInfo.ibi4") and os.path.exists(out / "data" / "PartMotionRef.ibi4")

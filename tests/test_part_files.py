@@ -196,3 +196,34 @@ def test_driver_writes_motionref_file(tmp_path, built_lib):
     assert "Finished execution (code=0)" in log and "Steps of simulation" in log and "PART files.......................: 5" in log
     head, row = open(out / "Run.csv").read().strip().splitlines()
     assert head.startswith("#RunName;") and len(head.split(";")) == len(row.split(";")) == 26
+
+
+@pytest.mark.gpu
+def test_driver_writes_extra_frequency_files(tmp_path, built_lib):
+    """-toutx (TimeOutExtra): PartFloatInfo2.ibi4 / PartMotionRef2.ibi4 from a run of the driver against the reference's files for
+    the same case and switch (tests/golden/ref_part_extra2): same items (one per PART, a single record stored like a PART of the main
+    file, several as arrays), the same steps in every record, reference-particle positions and floating-body centre within 1e-7 m,
+    body velocities within 1e-3 of their maximum.  The positions come through b2s_get_pos_byid (device-side id table of the last
+    divide); schedule and item layout are pinned on the CPU by tests/test_host_driver_frozen.py."""
+    import json
+    refdir = os.path.join(H.GOLDEN, "ref_part_extra2")
+    fx = json.load(open(os.path.join(refdir, "fixture_extra2.json")))
+    H.write_case(tmp_path, **fx["spec"])
+    out = tmp_path / "out"
+    r = subprocess.run([CLI, str(tmp_path / "Case"), str(out), "-toutx:%g" % fx["toutx"]], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "Finished execution (code=0)" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    for name, arrs in (("PartFloatInfo2.ibi4", (("center", 1e-7, False), ("fvel", 1e-3, True), ("fomega", 1e-3, True))),
+                       ("PartMotionRef2.ibi4", (("PosRef", 1e-7, False),))):
+        ours, ref = bi4.load_list(str(out / "data" / name)), bi4.load_list(os.path.join(refdir, name))
+        assert _list_structure(ours) == _list_structure(ref), name
+        for a, b in zip(ours[1:], ref[1:]):
+            assert a.get("Cpart") == b.get("Cpart") and a.get("Count") == b.get("Count")
+            if b.get("Count") is None:
+                assert a.get("Step") == b.get("Step") and abs(a.get("TimeStep") - b.get("TimeStep")) <= 2e-6 * max(b.get("TimeStep"), 1e-3)
+            else:
+                assert np.array_equal(a.array("Step"), b.array("Step"))
+                assert np.allclose(a.array("TimeStep"), b.array("TimeStep"), rtol=2e-6)
+            for arr, tol, rel in arrs:
+                x, y = np.asarray(a.array(arr), np.float64), np.asarray(b.array(arr), np.float64)
+                scale = max(float(np.abs(y).max()), 1e-3) if rel else 1.0
+                assert np.max(np.abs(x - y)) <= tol * scale, (name, a.name, arr, float(np.max(np.abs(x - y))), scale)
