@@ -260,4 +260,4 @@ int b2s_damping_impl(b2s_ctx* ctx);    // damping.cu: RunDamping with StepState.
 int b2s_floating_impl(b2s_ctx* ctx, double dt, bool predictor, bool dt_from_device);
 int b2s_motion_impl(b2s_ctx* ctx, double timestep, double dt);
 int b2s_sync_info(b2s_ctx* ctx);
-int b2s_gauges_run(b2s_ctx* ctx, int stepdt_ahead);   // gauges.cu: evaluates every gauge on the current particle state
+int b2s_gauges_run(b2s_ctx* ctx, int phase);   // gauges.cu: evaluates every gauge on the current particle state (0: one context; 1, 2: around the all-reduce of a slab run)

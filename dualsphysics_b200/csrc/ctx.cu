@@ -138,7 +138,8 @@ extern "C" int b2s_destroy(b2s_ctx* ctx){
   cudaFree(ctx->cellpart); cudaFree(ctx->sortpart); cudaFree(ctx->cellpart_alt); cudaFree(ctx->sortpart_alt);
   cudaFree(ctx->begincell); cudaFree(ctx->nearbound); cudaFree(ctx->radix_counts); cudaFree(ctx->ridp);
   cudaFree(ctx->div); cudaFree(ctx->step);
-  cudaFree(ctx->gauges_dev); cudaFree(ctx->gauge_res_dev); cudaFree(ctx->gauge_mass_dev); cudaFree(ctx->gauge_force_dev); if(ctx->gauge_res_h)cudaFreeHost(ctx->gauge_res_h);
+  cudaFree(ctx->gauges_dev); cudaFree(ctx->gauge_res_dev); cudaFree(ctx->gauge_force_dev);   // gauge_mass_dev lives inside gauge_res_dev
+  if(ctx->gauge_res_h)cudaFreeHost(ctx->gauge_res_h);
   cudaFree(ctx->motion_dev); cudaFree(ctx->out_dev); cudaFree(ctx->out_count_dev); cudaFree(ctx->damp_dev); cudaFree(ctx->shiftpos); cudaFree(ctx->boundmode); cudaFree(ctx->tangenvel); cudaFree(ctx->slab_counts); cudaFree(ctx->slab_flags);
   cudaFree(ctx->ft_massp_dev); cudaFree(ctx->ft_sums_dev); cudaFree(ctx->ft_allsums_dev); cudaFree(ctx->ft_dev); cudaFree(ctx->scratch);
   if(ctx->ft_sums_h)cudaFreeHost(ctx->ft_sums_h);
@@ -552,7 +553,7 @@ static int enqueue_step(b2s_ctx* ctx){
   r=b2s_damping_impl(ctx); if(r)return r;                           // RunDamping(dt), JSphCpuSingle.cpp:885,928
   // Run-loop tail (JSphGpuSingle.cpp:1003-1008): RunMotion, RunCellDivide, TimeStep+=dt
   // RunGaugeSystem(TimeStep+stepdt) (JSphCpuSingle.cpp:1192): new particle state, cell table of the last divide
-  r=b2s_gauges_run(ctx,1); if(r)return r;
+  r=b2s_gauges_run(ctx,0); if(r)return r;
   if(!ctx->motions.empty()){ r=b2s_motion_impl(ctx,0,0); if(r)return r; }
   k_step_end<<<1,1,0,ctx->stream>>>(ctx->step,q.tstep==B2S_STEP_SYMPLECTIC? 1: 0); B2S_LAUNCHED(ctx);
   r=divide_full(ctx); if(r)return r;

@@ -52,7 +52,7 @@ __device__ void gauge_point(const DivState* ds,const uint32_t* begt,const double
 // one thread per measurement point (velocity gauges have one, SWL gauges PointNp+1)
 __global__ void __launch_bounds__(G_BS) k_gauge_points(const GaugeDev* __restrict__ gs, uint32_t ng, uint32_t npoints, const DivState* ds,
   const uint32_t* __restrict__ begt, const double2* __restrict__ posxy, const double* __restrict__ posz, const typecode* __restrict__ code,
-  const float4* __restrict__ velrho, float* mass, float* res, const __grid_constant__ DevCte c)
+  const float4* __restrict__ velrho, float* mass, float* res, const __grid_constant__ DevCte c, uint32_t own_cxa, uint32_t own_cxb)
 {
   const uint32_t i=blockIdx.x*blockDim.x+threadIdx.x;
   if(i>=npoints)return;
@@ -61,8 +61,10 @@ __global__ void __launch_bounds__(G_BS) k_gauge_points(const GaugeDev* __restric
   const GaugeDev& gd=gs[cg];
   const uint32_t cp=i-gd.first;
   const double px=gd.p0[0]+gd.dir[0]*double(cp), py=gd.p0[1]+gd.dir[1]*double(cp), pz=gd.p0[2]+gd.dir[2]*double(cp);
-  double sw,vx,vy,vz;
-  gauge_point(ds,begt,posxy,posz,code,velrho,c,px,py,pz,sw,vx,vy,vz);
+  double sw=0,vx=0,vy=0,vz=0;
+  // slab runs: the rank whose slab holds the point's cell evaluates it (it has every neighbour, owned or ghost), the others add zeros
+  const double acx=floor((px-c.domposmin[0])/c.scell_d);
+  if(acx>=double(own_cxa) && acx<double(own_cxb))gauge_point(ds,begt,posxy,posz,code,velrho,c,px,py,pz,sw,vx,vy,vz);
   if(gd.type==GAUGE_VEL){ res[cg*4]=float(vx); res[cg*4+1]=float(vy); res[cg*4+2]=float(vz); res[cg*4+3]=0.f; }
   else mass[i]=float(sw*double(c.massf));
 }
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(256) k_gauge_force_sum(GaugeDev gd, int cg, co
 // window is the same number.  One block per gauge: threads stride over the (y,z) cell rows, then a block maximum.
 // GaugeDev use: p0 = point0, dir[0] = Height, masslimit = DistLimit.
 __global__ void __launch_bounds__(G_BS) k_gauge_maxz(GaugeDev gd, int cg, const DivState* ds, const uint32_t* __restrict__ begt, const double2* __restrict__ posxy,
-  const double* __restrict__ posz, const typecode* __restrict__ code, float* res, const __grid_constant__ DevCte c)
+  const double* __restrict__ posz, const typecode* __restrict__ code, float* res, const __grid_constant__ DevCte c, float* rawmax)
 {
   __shared__ float sh[G_BS];
   const float distlimit=gd.masslimit, maxdist2=distlimit*distlimit;
@@ -185,19 +187,29 @@ __global__ void __launch_bounds__(G_BS) k_gauge_maxz(GaugeDev gd, int cg, const 
   sh[threadIdx.x]=zmax;
   __syncthreads();
   for(int o=G_BS/2;o;o>>=1){ if(int(threadIdx.x)<o)sh[threadIdx.x]=fmaxf(sh[threadIdx.x],sh[threadIdx.x+o]); __syncthreads(); }
-  if(threadIdx.x==0){ res[cg*4]=fmaxf(sh[0],float(c.domposmin[2])); res[cg*4+1]=0.f; res[cg*4+2]=0.f; res[cg*4+3]=0.f; }
+  if(threadIdx.x==0){
+    if(rawmax){ rawmax[cg]=sh[0]; res[cg*4]=0.f; }   // slab runs: the maximum over the ranks comes first (k_gauge_maxz_finish)
+    else res[cg*4]=fmaxf(sh[0],float(c.domposmin[2]));
+    res[cg*4+1]=0.f; res[cg*4+2]=0.f; res[cg*4+3]=0.f;
+  }
+}
+__global__ void k_gauge_maxz_finish(const GaugeDev* __restrict__ gs, uint32_t ng, const float* __restrict__ rawmax, float* res, float zmin){
+  const uint32_t cg=blockIdx.x*blockDim.x+threadIdx.x;
+  if(cg<ng && gs[cg].type==GAUGE_MAXZ)res[cg*4]=fmaxf(rawmax[cg],zmin);
 }
 
 static int gauges_upload(b2s_ctx* ctx, const std::vector<GaugeDev>& h){
-  cudaFree(ctx->gauges_dev); cudaFree(ctx->gauge_res_dev); cudaFree(ctx->gauge_mass_dev); if(ctx->gauge_res_h)cudaFreeHost(ctx->gauge_res_h);
+  cudaFree(ctx->gauges_dev); cudaFree(ctx->gauge_res_dev); if(ctx->gauge_res_h)cudaFreeHost(ctx->gauge_res_h);   // gauge_mass_dev lives inside gauge_res_dev
   ctx->gauges_dev=NULL; ctx->gauge_res_dev=NULL; ctx->gauge_mass_dev=NULL; ctx->gauge_res_h=NULL;
   const size_t ng=h.size();
   B2S_CUDA(ctx,cudaMalloc(&ctx->gauges_dev,sizeof(GaugeDev)*ng));
-  B2S_CUDA(ctx,cudaMalloc((void**)&ctx->gauge_res_dev,sizeof(float)*4*ng));
-  B2S_CUDA(ctx,cudaMalloc((void**)&ctx->gauge_mass_dev,sizeof(float)*std::max<size_t>(ctx->gauge_points,1)));
+  // one buffer [results 4*ng | point masses | raw maxima ng]: a slab run all-reduces the first two parts in one call (slab_comm.cu)
+  const size_t npts=std::max<size_t>(ctx->gauge_points,1);
+  B2S_CUDA(ctx,cudaMalloc((void**)&ctx->gauge_res_dev,sizeof(float)*(4*ng+npts+ng)));
+  ctx->gauge_mass_dev=ctx->gauge_res_dev+4*ng;
   B2S_CUDA(ctx,cudaMallocHost((void**)&ctx->gauge_res_h,sizeof(float)*4*ng));
   B2S_CUDA(ctx,cudaMemcpy(ctx->gauges_dev,h.data(),sizeof(GaugeDev)*ng,cudaMemcpyHostToDevice));
-  B2S_CUDA(ctx,cudaMemset(ctx->gauge_res_dev,0,sizeof(float)*4*ng));
+  B2S_CUDA(ctx,cudaMemset(ctx->gauge_res_dev,0,sizeof(float)*(4*ng+npts+ng)));
   return B2S_OK;
 }
 // the host copy of the gauge list lives in the ctx as raw bytes (GaugeDev is private to this file)
@@ -272,35 +284,45 @@ extern "C" int b2s_gauge_add_swl(b2s_ctx* ctx, const double point0[3], const dou
   if(id)*id=int(h.size())-1;
   return gauges_upload(ctx,h);
 }
-int b2s_gauges_run(b2s_ctx* ctx, int){
+// phase 0: everything (one context).  Slab runs (slab_comm.cu grp_gauges): phase 1 = the partial results of this rank (points it owns,
+// boundary particles it owns, the highest particle it sees), then the all-reduce over the ranks (sum of results and point masses,
+// maximum of the raw maxima), then phase 2 = what follows from the reduced values (surface search, maxz clamp) and the copy to the host.
+int b2s_gauges_run(b2s_ctx* ctx, int phase){
   const uint32_t ng=uint32_t(ctx->gauge_types.size());
   if(!ng)return B2S_OK;
   cudaStream_t s=ctx->stream;
-  {
+  const bool slab=(phase!=0);
+  float* rawmax=ctx->gauge_mass_dev+std::max<size_t>(ctx->gauge_points,1);
+  if(phase!=2){
+    if(slab)B2S_CUDA(ctx,cudaMemsetAsync(ctx->gauge_res_dev,0,sizeof(float)*(4*size_t(ng)+std::max<size_t>(ctx->gauge_points,1)),s));
     const std::vector<GaugeDev> h=host_list(ctx);
     for(uint32_t cg=0;cg<ng;cg++)if(h[cg].type==GAUGE_MAXZ){
-      k_gauge_maxz<<<1,G_BS,0,s>>>(h[cg],int(cg),ctx->div,(const uint32_t*)ctx->begincell,ctx->cur.posxy,ctx->cur.posz,ctx->cur.code,ctx->gauge_res_dev,ctx->cte); B2S_LAUNCHED(ctx);
+      k_gauge_maxz<<<1,G_BS,0,s>>>(h[cg],int(cg),ctx->div,(const uint32_t*)ctx->begincell,ctx->cur.posxy,ctx->cur.posz,ctx->cur.code,ctx->gauge_res_dev,ctx->cte,slab? rawmax: (float*)NULL); B2S_LAUNCHED(ctx);
     }
-  }
-  if(ctx->gauge_force_n){
-    B2S_CUDA(ctx,cudaMemsetAsync(ctx->gauge_force_dev,0,size_t(ctx->gauge_force_n)*12,s));
-    const std::vector<GaugeDev> h=host_list(ctx);
-    for(uint32_t cg=0;cg<ng;cg++)if(h[cg].type==GAUGE_FORCE && ctx->npbok_host){
-      k_gauge_force_ace<<<b2s_blocks(ctx->npbok_host,G_BS),G_BS,0,s>>>(h[cg],ctx->div,(const uint32_t*)ctx->begincell,ctx->cur.posxy,ctx->cur.posz,
-        ctx->cur.code,ctx->cur.idp,ctx->cur.velrho,ctx->gauge_force_dev,ctx->cte); B2S_LAUNCHED(ctx);
-      k_gauge_force_sum<<<1,256,0,s>>>(h[cg],int(cg),ctx->gauge_force_dev,ctx->gauge_res_dev,ctx->cte.massb); B2S_LAUNCHED(ctx);
+    if(ctx->gauge_force_n){
+      B2S_CUDA(ctx,cudaMemsetAsync(ctx->gauge_force_dev,0,size_t(ctx->gauge_force_n)*12,s));
+      for(uint32_t cg=0;cg<ng;cg++)if(h[cg].type==GAUGE_FORCE && ctx->npbok_host){
+        k_gauge_force_ace<<<b2s_blocks(ctx->npbok_host,G_BS),G_BS,0,s>>>(h[cg],ctx->div,(const uint32_t*)ctx->begincell,ctx->cur.posxy,ctx->cur.posz,
+          ctx->cur.code,ctx->cur.idp,ctx->cur.velrho,ctx->gauge_force_dev,ctx->cte); B2S_LAUNCHED(ctx);
+        k_gauge_force_sum<<<1,256,0,s>>>(h[cg],int(cg),ctx->gauge_force_dev,ctx->gauge_res_dev,ctx->cte.massb); B2S_LAUNCHED(ctx);
+      }
     }
+    const uint32_t cxa=(slab? ctx->slab_cxa: 0u), cxb=(slab? ctx->slab_cxb: 0xffffffffu);
+    if(ctx->gauge_points)k_gauge_points<<<b2s_blocks(ctx->gauge_points,G_BS),G_BS,0,s>>>((const GaugeDev*)ctx->gauges_dev,ng,ctx->gauge_points,ctx->div,(const uint32_t*)ctx->begincell,
+      ctx->cur.posxy,ctx->cur.posz,ctx->cur.code,ctx->cur.velrho,ctx->gauge_mass_dev,ctx->gauge_res_dev,ctx->cte,cxa,cxb); B2S_LAUNCHED(ctx);
   }
-  if(ctx->gauge_points)k_gauge_points<<<b2s_blocks(ctx->gauge_points,G_BS),G_BS,0,s>>>((const GaugeDev*)ctx->gauges_dev,ng,ctx->gauge_points,ctx->div,(const uint32_t*)ctx->begincell,
-    ctx->cur.posxy,ctx->cur.posz,ctx->cur.code,ctx->cur.velrho,ctx->gauge_mass_dev,ctx->gauge_res_dev,ctx->cte); B2S_LAUNCHED(ctx);
-  k_gauge_swl<<<b2s_blocks(ng,32),32,0,s>>>((const GaugeDev*)ctx->gauges_dev,ng,ctx->gauge_mass_dev,ctx->gauge_res_dev); B2S_LAUNCHED(ctx);
-  B2S_CUDA(ctx,cudaMemcpyAsync(ctx->gauge_res_h,ctx->gauge_res_dev,sizeof(float)*4*ng,cudaMemcpyDeviceToHost,s));
+  if(phase!=1){
+    if(slab){ k_gauge_maxz_finish<<<b2s_blocks(ng,32),32,0,s>>>((const GaugeDev*)ctx->gauges_dev,ng,rawmax,ctx->gauge_res_dev,float(ctx->cte.domposmin[2])); B2S_LAUNCHED(ctx); }
+    k_gauge_swl<<<b2s_blocks(ng,32),32,0,s>>>((const GaugeDev*)ctx->gauges_dev,ng,ctx->gauge_mass_dev,ctx->gauge_res_dev); B2S_LAUNCHED(ctx);
+    B2S_CUDA(ctx,cudaMemcpyAsync(ctx->gauge_res_h,ctx->gauge_res_dev,sizeof(float)*4*ng,cudaMemcpyDeviceToHost,s));
+  }
   B2S_CUDA(ctx,cudaGetLastError());
   return B2S_OK;
 }
 extern "C" int b2s_gauges_compute(b2s_ctx* ctx){
   if(!ctx)return B2S_ERR_ARG;
   B2S_CUDA(ctx,cudaSetDevice(ctx->device));
+  if(ctx->slab_on && ctx->slab_nranks>1)return b2s_fail(ctx,B2S_ERR_STATE,"gauges of a slab rank are evaluated collectively: b2s_slab_gauges_compute");
   int r=b2s_gauges_run(ctx,0); if(r)return r;
   B2S_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
   return B2S_OK;

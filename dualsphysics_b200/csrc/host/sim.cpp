@@ -774,7 +774,6 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   }
   if(slab_nranks>0){
     if(slab_nranks>1 && s->timepartextra>=0)throw std::runtime_error("TimeOutExtra / -toutx (PartFloatInfo2, PartMotionRef2) is not written in slab-decomposed runs: remove it or run on one GPU");
-    if(slab_nranks>1 && !s->gauges.empty())throw std::runtime_error("gauges (<special><gauges>) are not evaluated in slab-decomposed runs: remove them or run on one GPU");
     r=b2s_slab_config(s->ctx,slab_rank,slab_nranks,s->slab_cuts[slab_rank],s->slab_cuts[slab_rank+1]);
     if(r)throw std::runtime_error(std::string("b2s_slab_config failed: ")+b2s_last_error(s->ctx));
   }
@@ -1061,6 +1060,10 @@ static void gauges_record(b2s_sim* s,double t){
     float res[3]={0,0,0};
     if(b2s_gauge_result(s->ctx,g.id,res))throw std::runtime_error("gauge result not available");
     if(!(g.output && t>=g.outputnext && g.outputstart<=t && t<=g.outputend) || s->dirout.empty())continue;
+    if(s->piece!=0){   // every slab rank holds the same results: rank 0 writes the files, the others only keep the schedule
+      if(g.outputdt){ const unsigned nt=unsigned(t/g.outputdt); g.outputnext=g.outputdt*nt; if(g.outputnext<=t)g.outputnext=g.outputdt*(nt+1); }
+      continue;
+    }
     const std::string fn=s->dirout+(g.type==1? "GaugesVel_": (g.type==3? "GaugesForce_": (g.type==4? "GaugesMaxZ_": "GaugesSWL_")))+g.name+".csv";
     FILE* f=fopen(fn.c_str(),g.headdone? "a": "w");
     if(!f)throw std::runtime_error("cannot write "+fn);
@@ -1189,7 +1192,7 @@ extern "C" int b2s_sim_run(b2s_sim* s,uint32_t nsteps_break,double* time_out,uin
   try{
     b2s_info inf; int r=b2s_get_info(s->ctx,&inf); if(r){ g_host_err=b2s_last_error(s->ctx); return r; }
     if(!s->gauges.empty() && inf.nstep==0){   // initial measurement (JSphCpuSingle.cpp:1110-1111)
-      r=b2s_gauges_compute(s->ctx); if(r){ g_host_err=b2s_last_error(s->ctx); return r; }
+      r=(s->npiece>1? b2s_slab_gauges_compute(s->ctx): b2s_gauges_compute(s->ctx)); if(r){ g_host_err=b2s_last_error(s->ctx); return r; }   // slab ranks: collectively, every rank ends with the same results
       gauges_record(s,inf.timestep);
     }
     if(save && !s->initial_saved){   // the initial PART (PartIni: 0, or the first PART number of a restart)

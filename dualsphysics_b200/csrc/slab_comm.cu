@@ -258,12 +258,14 @@ static int xfer_allreduce(std::vector<b2s_ctx*>& g, void* (*buf)(b2s_ctx*), size
   int r=group_sync(g); if(r)return r;
   std::vector<uint32_t> acc(count,0u), tmp(count);
   std::vector<float> facc(count,0.f);
+  bool first=true;
   for(b2s_ctx* x:g){
     B2S_CUDA(x,cudaMemcpy(tmp.data(),buf(x),count*4,cudaMemcpyDeviceToHost));
     for(size_t i=0;i<count;i++){
-      if(isfloat){ float v; memcpy(&v,&tmp[i],4); facc[i]=(ismax? std::max(facc[i],v): facc[i]+v); }
+      if(isfloat){ float v; memcpy(&v,&tmp[i],4); facc[i]=(ismax? (first? v: std::max(facc[i],v)): facc[i]+v); }
       else acc[i]=(ismax? std::max(acc[i],tmp[i]): acc[i]+tmp[i]);
     }
+    first=false;
   }
   for(b2s_ctx* x:g)B2S_CUDA(x,cudaMemcpy(buf(x),isfloat? (void*)facc.data(): (void*)acc.data(),count*4,cudaMemcpyHostToDevice));
   return B2S_OK;
@@ -272,6 +274,8 @@ static void* buf_dtmax(b2s_ctx* x){ return (void*)x->step; }          // StepSta
 static void* buf_ftsums(b2s_ctx* x){ return (void*)x->ft_allsums_dev; }
 static void* buf_hist(b2s_ctx* x){ return (void*)comm_of(x)->hist_dev; }
 static void* buf_sent(b2s_ctx* x){ return (void*)comm_of(x)->sent_dev; }
+static void* buf_gsum(b2s_ctx* x){ return (void*)x->gauge_res_dev; }   // [results 4*ng | point masses] (gauges.cu gauges_upload)
+static void* buf_gmax(b2s_ctx* x){ return (void*)(x->gauge_mass_dev+std::max<size_t>(x->gauge_points,1)); }   // raw maxima of the maxz gauges
 
 #define FOR_GROUP(g,expr) do{ for(b2s_ctx* ctx:(g)){ B2S_CUDA(ctx,cudaSetDevice(ctx->device)); int _r=(expr); if(_r)return _r; } }while(0)
 
@@ -319,6 +323,21 @@ static int grp_floating(std::vector<b2s_ctx*>& g, bool predictor){
   for(b2s_ctx* ctx:g){ B2S_CUDA(ctx,cudaSetDevice(ctx->device)); void* p; uint32_t n; int r=b2s_slab_ft_sums(ctx,&p,&n); if(r)return r; }
   { int r=xfer_allreduce(g,buf_ftsums,6u*g[0]->ftcount,true,false); if(r)return r; }
   FOR_GROUP(g,b2s_slab_ft_apply(ctx,predictor? 1: 0));
+  return B2S_OK;
+}
+
+// Gauges of a slab run (gauges.cu b2s_gauges_run): evaluated after the last exchange and divide of the step, when every rank holds
+// fresh ghosts.  A measurement point belongs to the rank whose slab holds its cell, a boundary particle of a force gauge to its owner;
+// what the ranks found is summed (exactly one of them contributes to a point), the maxz gauges take the maximum; every rank ends
+// with the same results.  (One context evaluates before the end-of-step divide like the reference, JSphCpuSingle.cpp:1192: same
+// particles, the sums in another order.)
+static int grp_gauges(std::vector<b2s_ctx*>& g){
+  const size_t ng=g[0]->gauge_types.size();
+  if(!ng)return B2S_OK;
+  FOR_GROUP(g,b2s_gauges_run(ctx,1));
+  { int r=xfer_allreduce(g,buf_gsum,4*ng+std::max<size_t>(g[0]->gauge_points,1),true,false); if(r)return r; }
+  { int r=xfer_allreduce(g,buf_gmax,ng,true,true); if(r)return r; }
+  FOR_GROUP(g,b2s_gauges_run(ctx,2));
   return B2S_OK;
 }
 
@@ -404,6 +423,7 @@ static int grp_step(std::vector<b2s_ctx*>& g, double* dt_out){
   FOR_GROUP(g,b2s_slab_step_end_enqueue(ctx));
   FOR_GROUP(g,ph_mark(ctx,PH_STEPEND));
   r=grp_exchange(g,3,true); if(r)return r;
+  r=grp_gauges(g); if(r)return r;
   SlabComm* c0=comm_of(g[0]);
   for(b2s_ctx* ctx:g)comm_of(ctx)->nstep++;
   if(c0->recut_every && c0->nstep%c0->recut_every==0){ r=grp_recut(g); if(r)return r; }
@@ -427,6 +447,12 @@ extern "C" int b2s_slab_exchange(b2s_ctx* ctx){
   std::vector<b2s_ctx*>* g; int r=group_of(ctx,g); if(r)return r;
   r=grp_exchange(*g,3,true); if(r)return r;
   for(b2s_ctx* x:*g){ r=b2s_sync_info(x); if(r)return r; ev_collect(x); }
+  return B2S_OK;
+}
+extern "C" int b2s_slab_gauges_compute(b2s_ctx* ctx){
+  std::vector<b2s_ctx*>* g; int r=group_of(ctx,g); if(r)return r;
+  r=grp_gauges(*g); if(r)return r;
+  for(b2s_ctx* x:*g){ r=b2s_sync_info(x); if(r)return r; }
   return B2S_OK;
 }
 extern "C" int b2s_slab_step(b2s_ctx* ctx, double* dt_out){

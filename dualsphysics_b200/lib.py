@@ -100,7 +100,7 @@ ABI_SYMBOLS = [
     "b2s_upload_particles", "b2s_download_particles", "b2s_download_particles_byid", "b2s_get_array",
     "b2s_get_info", "b2s_set_time", "b2s_celldiv", "b2s_interaction", "b2s_compute_verlet", "b2s_compute_symplectic_pre",
     "b2s_compute_symplectic_corr", "b2s_compute_step", "b2s_run_steps", "b2s_add_motion_rectsinu", "b2s_add_motion", "b2s_add_damping_plane", "b2s_add_damping_box", "b2s_out_enable", "b2s_out_fetch", "b2s_gauge_add_force", "b2s_gauge_add_maxz",
-    "b2s_move_linear", "b2s_set_floatings", "b2s_get_floatings", "b2s_get_pos_byid", "b2s_count_pairs", "b2s_time_interaction",
+    "b2s_move_linear", "b2s_set_floatings", "b2s_get_floatings", "b2s_get_pos_byid", "b2s_slab_gauges_compute", "b2s_count_pairs", "b2s_time_interaction",
     "b2s_gauge_add_velocity", "b2s_gauge_add_swl", "b2s_gauges_compute", "b2s_gauge_result",
     "b2s_launch_count", "b2s_get_stream", "b2s_set_interaction_variant", "b2s_debug_set_tile_cap", "b2s_slab_config",
     "b2s_slab_histogram", "b2s_slab_set_range", "b2s_slab_drop_ghosts", "b2s_slab_record_bytes", "b2s_slab_pack", "b2s_slab_unpack", "b2s_slab_pack_both", "b2s_slab_unpack_both", "b2s_slab_dt_buffer", "b2s_slab_forces",
@@ -173,6 +173,7 @@ def load_library():
     lib.b2s_gauge_add_force.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int)]
     lib.b2s_gauge_add_maxz.argtypes = [vp, C.POINTER(C.c_double), C.c_double, C.c_float, C.POINTER(C.c_int)]
     lib.b2s_gauges_compute.argtypes = [vp]
+    lib.b2s_slab_gauges_compute.argtypes = [vp]
     lib.b2s_gauge_result.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     lib.b2s_slab_config.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32]
     lib.b2s_slab_histogram.argtypes = [vp, vp]
@@ -477,8 +478,17 @@ class Context:
         self._chk(self._lib.b2s_gauge_add_force(self._h, idbegin, count, typevalue, C.byref(gid)))
         return gid.value
 
+    def gauge_add_maxz(self, point0, height, distlimit):
+        gid = C.c_int(-1)
+        self._chk(self._lib.b2s_gauge_add_maxz(self._h, (C.c_double * 3)(*point0), height, distlimit, C.byref(gid)))
+        return gid.value
+
     def gauges_compute(self):
         self._chk(self._lib.b2s_gauges_compute(self._h))
+
+    def slab_gauges_compute(self):
+        """Gauges of a slab-decomposed run, collectively (b2s_slab_gauges_compute); b2s_slab_step evaluates them after every step."""
+        self._chk(self._lib.b2s_slab_gauges_compute(self._h))
 
     def gauge_result(self, gid):
         out = (C.c_float * 3)()

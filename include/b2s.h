@@ -358,6 +358,11 @@ int b2s_slab_comm_init_local(b2s_ctx** ctxs, int nranks, uint32_t max_plane_part
 int b2s_slab_comm_free(b2s_ctx* ctx);
 int b2s_slab_comm_set_recut(b2s_ctx* ctx, uint32_t every_steps);
 int b2s_slab_comm_stats(b2s_ctx* ctx, double* out5, int reset);
+/* Gauges of a slab-decomposed run, evaluated collectively (every rank calls it; all ranks end with the same b2s_gauge_result): the
+ * rank whose slab holds a measurement point evaluates it, force gauges sum over the owners of the boundary particles, maxz gauges
+ * take the maximum over the ranks.  b2s_slab_step does the same at the end of every step; this call is for the measurement before
+ * the first step (JSphCpuSingle.cpp:1110-1111).  The same gauges have to be registered on every rank. */
+int b2s_slab_gauges_compute(b2s_ctx* ctx);
 /* B2S_SLAB_PROFILE=1 in the environment: ms per step spent in every phase of b2s_slab_step (CUDA events at the phase boundaries,
  * collected at the step's synchronisation) as one line of text; empty otherwise. */
 int b2s_slab_comm_profile(b2s_ctx* ctx, char* out, uint32_t outlen);

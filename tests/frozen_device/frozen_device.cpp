@@ -77,6 +77,7 @@ int b2s_slab_comm_id(uint8_t* id){ memset(id,0,128); return B2S_OK; }
 int b2s_slab_comm_init(b2s_ctx*,const uint8_t*,uint32_t){ return B2S_OK; }
 int b2s_slab_exchange(b2s_ctx*){ return B2S_OK; }
 int b2s_slab_step(b2s_ctx* c,double* dt_out){ return b2s_compute_step(c,dt_out); }
+int b2s_slab_gauges_compute(b2s_ctx*){ return B2S_OK; }
 int b2s_add_motion(b2s_ctx*,const b2s_motion*){ return B2S_OK; }
 int b2s_out_enable(b2s_ctx*,uint32_t){ return B2S_OK; }
 int b2s_out_fetch(b2s_ctx*,uint32_t,uint32_t* count_out,uint32_t*,double*,float*,float*,uint8_t*){ if(count_out)*count_out=0; return B2S_OK; }

@@ -243,3 +243,55 @@ def test_slab_periodic_y(nranks, tmp_path, built_lib):
     print(f"\n[slab periodic-y x{nranks}] cuts={ss.cuts} pos_err={epos:.3e} velrho_err={evr:.3e}")
     assert epos < 1e-7 and evr < 2e-6
     ss.close(); ref.close()
+
+
+def test_slab_gauges(tmp_path, built_lib):
+    """Gauges in slab runs (csrc/slab_comm.cu grp_gauges): velocity points, an SWL line, a force gauge on the piston and a maxz gauge,
+    three slabs against the single context.  The rank whose slab holds a point evaluates it, the force gauge sums over the owners of
+    the boundary particles, maxz takes the maximum; every rank ends with the same numbers.  The single context evaluates before the
+    end-of-step divide (the reference's order), the slabs after it: same particles, the sums in another order -> 2e-5 of the scale."""
+    H.write_case(tmp_path, dp=0.04, piston=True, piston_ampl=0.05, piston_freq=2.0)
+    case = str(tmp_path / "Case")
+    opts = "-symplectic -cellmode:half"
+    ref = dsb.Simulation(case, options=opts)
+    ss = slab.SlabSimulation(case, options=opts, nranks=3, dist=None)
+    p = ref.params
+    code, idp, pos = ref.ctx.array("code"), ref.ctx.array("idp"), ref.ctx.array("pos")
+    mov = np.nonzero((code & 0x1800) == 0x0800)[0]
+    assert mov.size
+    fluid = pos[(code & 0x1800) == 0x1800]
+    scell, dom0 = float(p.scell), float(p.domposmin[0])
+    xcuts = [dom0 + c * scell for c in ss.cuts[1:-1]]                 # x of the two inner cut planes
+    ymid, zlow = float(fluid[:, 1].mean()), float(fluid[:, 2].min()) + 3 * float(p.dp)
+    points = [(x + dx, ymid, zlow) for x in xcuts for dx in (-0.3 * scell, 0.3 * scell)] + [(float(fluid[:, 0].mean()), ymid, zlow)]
+    ctxs = [ref.ctx] + [r.ctx for r in ss.ranks]
+    gids = []
+    for c in ctxs:
+        g = [c.gauge_add_velocity(pt) for pt in points]
+        g.append(c.gauge_add_swl((xcuts[0], ymid, float(fluid[:, 2].min())), (xcuts[0], ymid, float(fluid[:, 2].max()) + 0.1), float(p.dp), 0.5 * float(p.massfluid)))
+        g.append(c.gauge_add_force(int(idp[mov].min()), int(mov.size), int(code[mov[0]] & 0x1fff)))
+        g.append(c.gauge_add_maxz((xcuts[-1], ymid, float(fluid[:, 2].min())), 1.0, 4 * float(p.dp)))
+        gids.append(g)
+    assert all(g == gids[0] for g in gids)
+    ref.ctx.gauges_compute(); ss.ranks[0].ctx.slab_gauges_compute()   # the measurement before the first step
+
+    def compare(label):
+        worst = 0.0
+        for k, gid in enumerate(gids[0]):
+            r0 = np.array(ref.ctx.gauge_result(gid))
+            rs = [np.array(r.ctx.gauge_result(gid)) for r in ss.ranks]
+            assert all(np.array_equal(rs[0], x) for x in rs), (label, k, rs)       # every rank holds the same results
+            scale = max(float(np.abs(r0).max()), 1e-3)
+            worst = max(worst, float(np.abs(rs[0] - r0).max()) / scale)
+            assert np.abs(rs[0] - r0).max() <= 2e-5 * scale, (label, k, r0, rs[0])
+        return worst
+    w0 = compare("initial")
+    for s in range(30):
+        dt_ref, dt = ref.ctx.compute_step(), ss.step()
+        assert abs(dt - dt_ref) <= 2e-5 * dt_ref, (s, dt, dt_ref)
+    w1 = compare("after 30 steps")
+    fz = np.array(ref.ctx.gauge_result(gids[0][-2]))
+    vel = np.array(ref.ctx.gauge_result(gids[0][0]))
+    print(f"\n[slab gauges] cuts={ss.cuts} worst rel diff: initial {w0:.2e}, after 30 steps {w1:.2e}; piston force {fz}, velocity at the first point {vel}")
+    assert np.abs(fz).max() > 0 and np.abs(vel).max() > 0            # the gauges measure something
+    ss.close(); ref.close()
