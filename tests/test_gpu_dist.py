@@ -67,3 +67,34 @@ def test_cli_two_ranks_write_pieces(tmp_path, built_lib):
         assert float(np.max(np.abs(pos[o] - ref["pos"][ro]))) < 1e-6, k
         k += 1
     assert k >= 3, k
+
+
+def test_cli_two_ranks_gauges(tmp_path, built_lib):
+    """Gauges in a slab-decomposed run of the command line (csrc/slab_comm.cu grp_gauges over NCCL; rank 0 writes the CSV files): the
+    reference's gauge fixture (a velocity point, a vertical SWL line, an SWL line along x that crosses the cut) on two GPUs against
+    the single-GPU run of the same command: the same rows and times, values within 1e-5 of their scale."""
+    import json
+    import numpy as np
+    fx = json.load(open(os.path.join(H.GOLDEN, "gauges_ref", "fixture_gauges.json")))
+    H.write_case(tmp_path, **fx["spec"])
+    exe = os.path.join(H.ROOT, "dualsphysics_b200", "lib", "b200sph")
+    opts = list(fx["options"]) + ["-cellmode:half", "-tmax:0.02"]
+    one = subprocess.run([exe, str(tmp_path / "Case"), str(tmp_path / "out1")] + opts, capture_output=True, text=True, timeout=600)
+    assert one.returncode == 0, one.stdout[-2000:] + one.stderr[-2000:]
+    idfile = str(tmp_path / "nccl.id")
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), B2S_NCCL_ID_FILE=idfile)
+        procs.append(subprocess.Popen([exe, str(tmp_path / "Case"), str(tmp_path / "out2")] + opts, env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[-2000:] for o in outs)
+    names = sorted(f for f in os.listdir(tmp_path / "out1") if f.startswith("Gauges") and f.endswith(".csv"))
+    assert len(names) == 3, names
+    for f in names:
+        a, b = open(tmp_path / "out1" / f).read().strip().splitlines(), open(tmp_path / "out2" / f).read().strip().splitlines()
+        assert a[0] == b[0] and len(a) == len(b) and len(a) > 5, (f, len(a), len(b))
+        x = np.array([[float(v) for v in row.split(";")] for row in a[1:]]); y = np.array([[float(v) for v in row.split(";")] for row in b[1:]])
+        assert np.array_equal(x[:, 0], y[:, 0]), f                       # the same times
+        scale = np.maximum(np.abs(x).max(axis=0), 1e-3)
+        assert np.max(np.abs(x - y) / scale) <= 1e-5, (f, float(np.max(np.abs(x - y) / scale)))

@@ -250,11 +250,12 @@ def test_slab_gauges(tmp_path, built_lib):
     three slabs against the single context.  The rank whose slab holds a point evaluates it, the force gauge sums over the owners of
     the boundary particles, maxz takes the maximum; every rank ends with the same numbers.  The single context evaluates before the
     end-of-step divide (the reference's order), the slabs after it: same particles, the sums in another order -> 2e-5 of the scale."""
-    H.write_case(tmp_path, dp=0.04, piston=True, piston_ampl=0.05, piston_freq=2.0)
+    H.write_case(tmp_path, dp=0.025, piston=True, piston_ampl=0.05, piston_freq=2.0)
     case = str(tmp_path / "Case")
     opts = "-symplectic -cellmode:half"
     ref = dsb.Simulation(case, options=opts)
     ss = slab.SlabSimulation(case, options=opts, nranks=3, dist=None)
+    assert ss.native, ss.cuts                                        # the library's step (the gauges are part of it) needs slabs wider than the halo
     p = ref.params
     code, idp, pos = ref.ctx.array("code"), ref.ctx.array("idp"), ref.ctx.array("pos")
     mov = np.nonzero((code & 0x1800) == 0x0800)[0]
@@ -275,9 +276,13 @@ def test_slab_gauges(tmp_path, built_lib):
     assert all(g == gids[0] for g in gids)
     ref.ctx.gauges_compute(); ss.ranks[0].ctx.slab_gauges_compute()   # the measurement before the first step
 
-    def compare(label):
+    kforce = len(gids[0]) - 2
+
+    def compare(label, skip=()):
         worst = 0.0
         for k, gid in enumerate(gids[0]):
+            if k in skip:
+                continue
             r0 = np.array(ref.ctx.gauge_result(gid))
             rs = [np.array(r.ctx.gauge_result(gid)) for r in ss.ranks]
             assert all(np.array_equal(rs[0], x) for x in rs), (label, k, rs)       # every rank holds the same results
@@ -289,7 +294,13 @@ def test_slab_gauges(tmp_path, built_lib):
     for s in range(30):
         dt_ref, dt = ref.ctx.compute_step(), ss.step()
         assert abs(dt - dt_ref) <= 2e-5 * dt_ref, (s, dt, dt_ref)
-    w1 = compare("after 30 steps")
+    # In its step the single context evaluates before RunMotion and the end-of-step divide (the reference's order,
+    # JSphCpuSingle.cpp:1192), the slabs after them: identical for everything but a force gauge on a block that moves -- the piston
+    # is one step's displacement further for the slabs.  Evaluated on the same state (b2s_gauges_compute after the step) it agrees too.
+    w1 = compare("after 30 steps, in-step values", skip=(kforce,))
+    ref.ctx.gauges_compute()
+    w2 = compare("after 30 steps, same state")
+    w1 = max(w1, w2)
     fz = np.array(ref.ctx.gauge_result(gids[0][-2]))
     vel = np.array(ref.ctx.gauge_result(gids[0][0]))
     print(f"\n[slab gauges] cuts={ss.cuts} worst rel diff: initial {w0:.2e}, after 30 steps {w1:.2e}; piston force {fz}, velocity at the first point {vel}")
