@@ -72,7 +72,8 @@ def test_cli_two_ranks_write_pieces(tmp_path, built_lib):
 def test_cli_two_ranks_gauges(tmp_path, built_lib):
     """Gauges in a slab-decomposed run of the command line (csrc/slab_comm.cu grp_gauges over NCCL; rank 0 writes the CSV files): the
     reference's gauge fixture (a velocity point, a vertical SWL line, an SWL line along x that crosses the cut) on two GPUs against
-    the single-GPU run of the same command: the same rows and times, values within 1e-5 of their scale."""
+    the single-GPU run of the same command: the same rows and times, values within 1e-4 of their column's scale (the two runs differ by
+    2e-6 of max|v| in the state, tests/test_gpu_slab.py, and the files print six digits)."""
     import json
     import numpy as np
     fx = json.load(open(os.path.join(H.GOLDEN, "gauges_ref", "fixture_gauges.json")))
@@ -97,4 +98,4 @@ def test_cli_two_ranks_gauges(tmp_path, built_lib):
         x = np.array([[float(v) for v in row.split(";")] for row in a[1:]]); y = np.array([[float(v) for v in row.split(";")] for row in b[1:]])
         assert np.array_equal(x[:, 0], y[:, 0]), f                       # the same times
         scale = np.maximum(np.abs(x).max(axis=0), 1e-3)
-        assert np.max(np.abs(x - y) / scale) <= 1e-5, (f, float(np.max(np.abs(x - y) / scale)))
+        assert np.max(np.abs(x - y) / scale) <= 1e-4, (f, float(np.max(np.abs(x - y) / scale)))
