@@ -66,8 +66,16 @@ def main(argv=None) -> int:
     ss.set_dirout(dirout)
     if rank == 0 and world > 1:
         print(f"b200sph x{world}: slab step {'inside the library (NCCL from C++)' if ss.native else 'driven by slab.py (torch.distributed)'}; "
-              "PART files are written as pieces; PartOut / PartMotionRef / PartExtra are not written in multi-GPU runs and gauges are refused")
+              "PART files are written as pieces; PartOut / PartMotionRef / PartExtra are not written in multi-GPU runs")
     ctx = ss.ranks[0].ctx
+    try:                                     # a case with <special><gauges> registers them in the library: this runner has no CSV writer
+        ctx.gauge_result(0)
+        has_gauges = True
+    except Exception:
+        has_gauges = False
+    if has_gauges:
+        raise SystemExit("this case configures gauges: run it with the command-line driver (dualsphysics_b200/lib/b200sph, one process per GPU), "
+                         "which evaluates them over the slabs and writes the CSV files; this runner would drop them")
     t = ctx.info().timestep
     ss.save_part()
     tnext, parts, steps, t0 = next_part_time(t, tout), 1, 0, time.time()
