@@ -66,6 +66,7 @@ struct b2s_sim {
   int variant=-1;                                                       // -b2svariant (-1: the library default, variant 5)
   unsigned piece=0, npiece=1;                                           // slab rank / ranks: PART files are written as pieces (JPartDataBi4.cpp:99-127)
   std::string svextraparts;                                             // -svextraparts / SaveExtraParts: PARTs that get a PartExtra_XXXX.bi4
+  uint32_t out_cap=0; bool out_saved=false;                           // capacity of the device buffer of excluded particles; PartOut head written
   unsigned out_total[4]={0,0,0,0};                                    // excluded particles written to PartOut so far, by motive (0: all)
   MotionRefSave motref; bool motref_ready=false;                       // PartMotionRef.ibi4
   // Extra-frequency output of the body data (TimeOutExtra / -toutx; JSph.cpp:789-790,859-870): PartFloatInfo2.ibi4 and PartMotionRef2.ibi4.
@@ -503,6 +504,14 @@ static void load_case(b2s_sim* s,const std::string& options){
   }
 }
 
+// Device buffer of the excluded particles (drained at every PART): the whole fluid on one GPU, twice its share on a slab rank.
+static void enable_out(b2s_sim* s,int nranks){
+  if(s->out_cap)return;
+  const b2s_params& p=s->prm;
+  s->out_cap=(nranks>1? std::max(std::min(p.casenfluid,2u*(p.casenfluid/unsigned(nranks))+65536u),1024u): std::max(p.casenfluid,1024u));
+  if(b2s_out_enable(s->ctx,s->out_cap))throw std::runtime_error(std::string("b2s_out_enable failed: ")+b2s_last_error(s->ctx));
+}
+
 static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capacity,int slab_rank=0,int slab_nranks=0){
   b2s_params& p=s->prm;
   std::unique_ptr<Bi4Item> data=bi4_load(s->casepath+".bi4");
@@ -763,9 +772,8 @@ static void load_particles_and_create(b2s_sim* s,int device,unsigned extra_capac
   r=b2s_upload_particles(s->ctx,npsel,idp,code.data(),pos.data(),velrho.data(),norp);
   if(r)throw std::runtime_error(std::string("b2s_upload_particles failed: ")+b2s_last_error(s->ctx));
   s->np0=np;
-  if(!s->dirdata.empty() && slab_nranks<=0){   // excluded particles -> PartOut_000.obi4
-    r=b2s_out_enable(s->ctx,std::max(p.casenfluid,1024u));
-    if(r)throw std::runtime_error(std::string("b2s_out_enable failed: ")+b2s_last_error(s->ctx));
+  if(!s->dirdata.empty()){   // excluded particles -> PartOut_000.obi4 (a slab rank collects what its own particles lose: PartOut_pRR_000.obi4)
+    enable_out(s,slab_nranks);
   }
   if(s->partbegin){   // TimeStepIni / SymplecticDtPre / PartIni of the restart (JSph.cpp:2214-2225)
     r=b2s_set_time(s->ctx,(s->partbeginfirst? s->partbegintime: 0.0),s->partbegindtpre);
@@ -861,8 +869,8 @@ static void save_part(b2s_sim* s){
   // particles excluded since the previous PART (JSph::AddParticlesOut / PartsOut): drained from the device buffer
   uint32_t nout=0; unsigned nmot[4]={0,0,0,0};
   std::vector<uint32_t> oid; std::vector<double> opos; std::vector<float> ovel, orho; std::vector<uint8_t> omot;
-  if(!pieces){
-    const uint32_t ocap=std::max(p.casenfluid,1024u);
+  {
+    const uint32_t ocap=(s->out_cap? s->out_cap: std::max(p.casenfluid,1024u));
     oid.resize(ocap); opos.resize(size_t(ocap)*3); ovel.resize(size_t(ocap)*3); orho.resize(ocap); omot.resize(ocap);
     r=b2s_out_fetch(s->ctx,ocap,&nout,oid.data(),opos.data(),ovel.data(),orho.data(),omot.data());
     if(r)throw std::runtime_error(std::string("b2s_out_fetch failed: ")+b2s_last_error(s->ctx));
@@ -902,9 +910,9 @@ static void save_part(b2s_sim* s){
     char fi[64]; if(pieces)snprintf(fi,sizeof(fi),"PartInfo_p%02u.ibi4",s->piece); else snprintf(fi,sizeof(fi),"PartInfo.ibi4");
     bi4_save_listapp(s->dirdata+fi,"JPartDataBi4_Info",hd,&pi,fresh);
   }
-  if(!pieces){ // PartOut_000.obi4 (JPartOutBi4Save::ConfigBasic/ConfigParticles/ConfigLimits/SavePartOut, JPartOutBi4Save.cpp:119-232)
+  { // PartOut_000.obi4, PartOut_pRR_000.obi4 for the piece of a slab rank (JPartOutBi4Save::GetFileNamePart/ConfigBasic/ConfigParticles/ConfigLimits/SavePartOut, JPartOutBi4Save.cpp:102-232)
     Bi4Item hd("JPartOutBi4");
-    hd.set_uint("Piece",0); hd.set_uint("Npiece",1); hd.set_text("RunCode",s->runcode); hd.set_text("Date",s->date);
+    hd.set_uint("Piece",s->piece); hd.set_uint("Npiece",s->npiece); hd.set_text("RunCode",s->runcode); hd.set_text("Date",s->date);
     hd.set_text("AppName","b200sph v0.1 (DualSPHysics v5.4 case interface)"); hd.set_bool("Data2d",p.simulate2d!=0);
     hd.set_uint("FmtVersion",180320); hd.set_uint("Block",0);
     hd.set_double3("MapPosMin",p.maprealposmin); hd.set_double3("MapPosMax",p.maprealposmax);
@@ -918,7 +926,10 @@ static void save_part(b2s_sim* s){
     if(s->svposdouble)po.add_array_ext("Posd",BT_DOUBLE3,nout,opos.data());
     else{ oposf.resize(size_t(nout)*3); for(size_t i=0;i<size_t(nout)*3;i++)oposf[i]=float(opos[i]); po.add_array_ext("Pos",BT_FLOAT3,nout,oposf.data()); }
     po.add_array_ext("Vel",BT_FLOAT3,nout,ovel.data()); po.add_array_ext("Rhop",BT_FLOAT,nout,orho.data()); po.add_array_ext("Motive",BT_UCHAR,nout,omot.data());
-    if(firstsave || nout)bi4_save_listapp(s->dirdata+"PartOut_000.obi4","JPartOutBi4",hd,(nout? &po: NULL),fresh);
+    char fo[64]; if(pieces)snprintf(fo,sizeof(fo),"PartOut_p%02u_000.obi4",s->piece); else snprintf(fo,sizeof(fo),"PartOut_000.obi4");
+    const bool firstout=(pieces? !s->out_saved: firstsave);   // Part_Head.ibi4 (what firstsave follows) comes from rank 0 only
+    if(firstout || nout)bi4_save_listapp(s->dirdata+fo,"JPartOutBi4",hd,(nout? &po: NULL),pieces? (firstout && !s->partbeginfirst): fresh);
+    s->out_saved=true;
   }
   if(p.casenfloat && (!pieces || s->piece==0)){ // PartFloatInfo.ibi4 (every rank holds the same body state: rank 0 writes it) (JPartFloatInfoBi4Save::Config/MakeBdPartSingle/SaveBdPart, JPartFloatInfoBi4.cpp:464-602)
     std::vector<const PartBlock*> fb; for(auto& b:s->blocks)if(b.type==2)fb.push_back(&b);
@@ -1127,7 +1138,7 @@ extern "C" int b2s_sim_load_slab(const char* casepath,const char* options,int de
 // Output directory of a slab rank: every rank writes its own piece Part_pRR_XXXX.bi4 / PartInfo_pRR.ibi4, rank 0 also Part_Head.ibi4.
 extern "C" int b2s_sim_set_dirout(b2s_sim* s,const char* dirout){
   if(!s||!dirout||!dirout[0])return B2S_ERR_ARG;
-  try{ s->dirout=dirout; if(s->dirout[s->dirout.size()-1]!='/')s->dirout+='/'; s->dirdata=s->dirout+"data/"; mkdirs(s->dirdata); }
+  try{ s->dirout=dirout; if(s->dirout[s->dirout.size()-1]!='/')s->dirout+='/'; s->dirdata=s->dirout+"data/"; mkdirs(s->dirdata); enable_out(s,int(s->npiece)); }
   catch(const std::exception& e){ g_host_err=e.what(); return B2S_ERR_IO; }
   return B2S_OK;
 }

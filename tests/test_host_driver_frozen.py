@@ -312,7 +312,13 @@ def test_slab_ranks_write_part_pieces(frozen, tmp_path):
             assert lib.b2s_sim_save_part(sim) == 0, lib.b2s_host_last_error().decode()
     files = sorted(os.listdir(out / "data"))
     assert files == sorted([f"Part_p{r:02d}_{c:04d}.bi4" for r in range(nranks) for c in range(2)] + [f"PartInfo_p{r:02d}.ibi4" for r in range(nranks)]
-                           + ["Part_Head.ibi4", "PartFloatInfo.ibi4"])
+                           + [f"PartOut_p{r:02d}_000.obi4" for r in range(nranks)] + ["Part_Head.ibi4", "PartFloatInfo.ibi4"])
+    # excluded particles: one list file per piece (JPartOutBi4Save::GetFileNamePart, JPartOutBi4Save.cpp:102-113) with the reference's head
+    refout = bi4.load_list(os.path.join(H.GOLDEN, "ref_part_float", "PartOut_000.obi4"))[0]
+    for r in range(nranks):
+        oo = bi4.load_list(str(out / "data" / f"PartOut_p{r:02d}_000.obi4"))
+        assert len(oo) == 1 and _list_structure(oo) == _list_structure([refout])       # a frozen state excludes nothing: the head only
+        assert oo[0].get("Piece") == r and oo[0].get("Npiece") == nranks
     ref = bi4.load(os.path.join(H.GOLDEN, "ref_part", "Part_0002.bi4"))
     ids = []
     for r in range(nranks):
