@@ -99,3 +99,44 @@ def test_cli_two_ranks_gauges(tmp_path, built_lib):
         assert np.array_equal(x[:, 0], y[:, 0]), f                       # the same times
         scale = np.maximum(np.abs(x).max(axis=0), 1e-3)
         assert np.max(np.abs(x - y) / scale) <= 1e-4, (f, float(np.max(np.abs(x - y) / scale)))
+
+
+def test_cli_two_ranks_partout(tmp_path, built_lib):
+    """Excluded particles of a slab-decomposed run: every rank writes what its own particles lose as PartOut_pRR_000.obi4 (the
+    reference's piece naming, JPartOutBi4Save.cpp:102-113).  A tight density window (-rhopout) excludes particles early in the dam
+    break; the pieces of the two ranks together hold the particles the single-GPU run excluded (a particle whose density sits at the
+    limit to rounding may differ: at most 2% of them), and PART pieces + excluded particles still add up to the case."""
+    import numpy as np
+    from dualsphysics_b200 import bi4
+    H.write_case(tmp_path, dp=0.03, params={"TimeMax": 0.02, "TimeOut": 0.005})
+    exe = os.path.join(H.ROOT, "dualsphysics_b200", "lib", "b200sph")
+    opts = ["-symplectic", "-cellmode:half", "-tmax:0.015", "-tout:0.005", "-rhopout:700:1001.2"]
+    one = subprocess.run([exe, str(tmp_path / "Case"), str(tmp_path / "out1")] + opts, capture_output=True, text=True, timeout=600)
+    assert one.returncode == 0, one.stdout[-2000:] + one.stderr[-2000:]
+    idfile = str(tmp_path / "nccl.id")
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), B2S_NCCL_ID_FILE=idfile)
+        procs.append(subprocess.Popen([exe, str(tmp_path / "Case"), str(tmp_path / "out2")] + opts, env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[-2000:] for o in outs)
+
+    def out_ids(path):
+        items = bi4.load_list(path)
+        return items[0], np.concatenate([np.asarray(it.array("Idp")) for it in items[1:]] + [np.zeros(0, np.uint32)])
+    h1, ids1 = out_ids(str(tmp_path / "out1" / "data" / "PartOut_000.obi4"))
+    pieces = [out_ids(str(tmp_path / "out2" / "data" / f"PartOut_p{r:02d}_000.obi4")) for r in range(2)]
+    assert [h.get("Piece") for h, _ in pieces] == [0, 1] and all(h.get("Npiece") == 2 for h, _ in pieces)
+    assert [(n, t) for n, t, _ in pieces[0][0].values] == [(n, t) for n, t, _ in h1.values]
+    ids2 = np.concatenate([i for _, i in pieces])
+    assert len(ids1) > 20, len(ids1)                                   # the window does exclude particles
+    assert len(np.unique(ids2)) == len(ids2)                           # nobody is excluded twice
+    assert len(np.setxor1d(ids1, ids2)) <= max(2, len(ids1) // 50), (len(ids1), len(ids2), len(np.setxor1d(ids1, ids2)))
+    # last PART: the pieces and everything excluded so far partition the case
+    k = 0
+    while os.path.exists(str(tmp_path / "out2" / "data" / f"Part_p00_{k + 1:04d}.bi4")):
+        k += 1
+    last = np.concatenate([bi4.load_part(str(tmp_path / "out2" / "data" / f"Part_p{r:02d}_{k:04d}.bi4"))["Idp"] for r in range(2)])
+    allids = np.concatenate([last, ids2])
+    assert len(np.unique(allids)) == len(allids) == len(bi4.load_part(str(tmp_path / "Case.bi4"))["Idp"])
