@@ -103,14 +103,14 @@ def test_cli_two_ranks_gauges(tmp_path, built_lib):
 
 def test_cli_two_ranks_partout(tmp_path, built_lib):
     """Excluded particles of a slab-decomposed run: every rank writes what its own particles lose as PartOut_pRR_000.obi4 (the
-    reference's piece naming, JPartOutBi4Save.cpp:102-113).  A tight density window (-rhopout) excludes particles early in the dam
-    break; the pieces of the two ranks together hold the particles the single-GPU run excluded (a particle whose density sits at the
+    reference's piece naming, JPartOutBi4Save.cpp:102-113).  A lower density limit just under rho0 (-rhopout:999.5:1300, the window of the reference's
+    list-file fixture) excludes particles early in the dam break; the pieces of the two ranks together hold the particles the single-GPU run excluded (a particle whose density sits at the
     limit to rounding may differ: at most 2% of them), and PART pieces + excluded particles still add up to the case."""
     import numpy as np
     from dualsphysics_b200 import bi4
     H.write_case(tmp_path, dp=0.03, params={"TimeMax": 0.02, "TimeOut": 0.005})
     exe = os.path.join(H.ROOT, "dualsphysics_b200", "lib", "b200sph")
-    opts = ["-symplectic", "-cellmode:half", "-tmax:0.015", "-tout:0.005", "-rhopout:700:1001.2"]
+    opts = ["-symplectic", "-cellmode:half", "-tmax:0.015", "-tout:0.005", "-rhopout:999.5:1300"]
     one = subprocess.run([exe, str(tmp_path / "Case"), str(tmp_path / "out1")] + opts, capture_output=True, text=True, timeout=600)
     assert one.returncode == 0, one.stdout[-2000:] + one.stderr[-2000:]
     idfile = str(tmp_path / "nccl.id")
@@ -130,7 +130,7 @@ def test_cli_two_ranks_partout(tmp_path, built_lib):
     assert [h.get("Piece") for h, _ in pieces] == [0, 1] and all(h.get("Npiece") == 2 for h, _ in pieces)
     assert [(n, t) for n, t, _ in pieces[0][0].values] == [(n, t) for n, t, _ in h1.values]
     ids2 = np.concatenate([i for _, i in pieces])
-    assert len(ids1) > 20, len(ids1)                                   # the window does exclude particles
+    assert len(ids1) > 5, len(ids1)                                    # the window does exclude particles
     assert len(np.unique(ids2)) == len(ids2)                           # nobody is excluded twice
     assert len(np.setxor1d(ids1, ids2)) <= max(2, len(ids1) // 50), (len(ids1), len(ids2), len(np.setxor1d(ids1, ids2)))
     # last PART: the pieces and everything excluded so far partition the case
