@@ -66,7 +66,7 @@ def main(argv=None) -> int:
     ss.set_dirout(dirout)
     if rank == 0 and world > 1:
         print(f"b200sph x{world}: slab step {'inside the library (NCCL from C++)' if ss.native else 'driven by slab.py (torch.distributed)'}; "
-              "PART files are written as pieces; PartOut / PartMotionRef / PartExtra are not written in multi-GPU runs")
+              "PART and PartOut files are written as pieces; PartMotionRef / PartExtra are not written in multi-GPU runs")
     ctx = ss.ranks[0].ctx
     try:                                     # a case with <special><gauges> registers them in the library: this runner has no CSV writer
         ctx.gauge_result(0)
