@@ -20,6 +20,20 @@ def _ngpu():
         return 0
 
 
+def _wait_all(procs, limit=600):
+    """Output of every rank; a rank that exits with an error takes the others down (they would wait in a collective for ever)."""
+    import time
+    t0 = time.time()
+    while any(p.poll() is None for p in procs):
+        if any(p.poll() not in (None, 0) for p in procs) or time.time() - t0 > limit:
+            for p in procs:
+                if p.poll() is None:
+                    p.kill()
+            break
+        time.sleep(0.2)
+    return [p.communicate()[0] for p in procs]
+
+
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("options,nsteps,recut", [("-symplectic -cellmode:half", 12, ""), ("-verlet", 12, ""),
                                                     ("-symplectic -cellmode:half", 400, "recut")])
@@ -54,7 +68,7 @@ def test_cli_two_ranks_write_pieces(tmp_path, built_lib):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), B2S_NCCL_ID_FILE=idfile)
         procs.append(subprocess.Popen([exe, str(tmp_path / "Case"), str(tmp_path / "out2")] + opts, env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.STDOUT, text=True))
-    outs = [p.communicate(timeout=600)[0] for p in procs]
+    outs = _wait_all(procs)
     assert all(p.returncode == 0 for p in procs), "\n".join(o[-2000:] for o in outs)
     assert "Finished execution (code=0)" in outs[0]
     k = 0
@@ -69,6 +83,7 @@ def test_cli_two_ranks_write_pieces(tmp_path, built_lib):
     assert k >= 3, k
 
 
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
 def test_cli_two_ranks_gauges(tmp_path, built_lib):
     """Gauges in a slab-decomposed run of the command line (csrc/slab_comm.cu grp_gauges over NCCL; rank 0 writes the CSV files): the
     reference's gauge fixture (a velocity point, a vertical SWL line, an SWL line along x that crosses the cut) on two GPUs against
@@ -88,7 +103,7 @@ def test_cli_two_ranks_gauges(tmp_path, built_lib):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), B2S_NCCL_ID_FILE=idfile)
         procs.append(subprocess.Popen([exe, str(tmp_path / "Case"), str(tmp_path / "out2")] + opts, env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.STDOUT, text=True))
-    outs = [p.communicate(timeout=600)[0] for p in procs]
+    outs = _wait_all(procs)
     assert all(p.returncode == 0 for p in procs), "\n".join(o[-2000:] for o in outs)
     names = sorted(f for f in os.listdir(tmp_path / "out1") if f.startswith("Gauges") and f.endswith(".csv"))
     assert len(names) == 3, names
@@ -101,6 +116,7 @@ def test_cli_two_ranks_gauges(tmp_path, built_lib):
         assert np.max(np.abs(x - y) / scale) <= 1e-4, (f, float(np.max(np.abs(x - y) / scale)))
 
 
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
 def test_cli_two_ranks_partout(tmp_path, built_lib):
     """Excluded particles of a slab-decomposed run: every rank writes what its own particles lose as PartOut_pRR_000.obi4 (the
     reference's piece naming, JPartOutBi4Save.cpp:102-113).  A lower density limit just under rho0 (-rhopout:999.5:1300, the window of the reference's
@@ -119,7 +135,7 @@ def test_cli_two_ranks_partout(tmp_path, built_lib):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), B2S_NCCL_ID_FILE=idfile)
         procs.append(subprocess.Popen([exe, str(tmp_path / "Case"), str(tmp_path / "out2")] + opts, env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.STDOUT, text=True))
-    outs = [p.communicate(timeout=600)[0] for p in procs]
+    outs = _wait_all(procs)
     assert all(p.returncode == 0 for p in procs), "\n".join(o[-2000:] for o in outs)
 
     def out_ids(path):
