@@ -18,8 +18,9 @@
 //   * ROW DESCRIPTORS: the window is walked in phases of one z plane and its mirror plane.  At the head of a phase a lane works
 //     out the rows of all its turns (trim, then three begin-table loads per row that depend on nothing but the trim) and parks them
 //     in its own shared-memory slots; a turn then costs one LDS.128.  The former set-up of every row right before its use (two
-//     set-ups of ~130 instructions with three dependent loads per turn, spilling the cell range) was 27% of the executed
-//     instructions: 9.07 -> 8.08 ms at 10M particles (profiles/README.md, r02E);
+//     set-ups of ~130 instructions per turn, each with three dependent loads and the reloads of the spilled cell range) cost
+//     more in stalls than in instructions: issue slots 67 -> 74% busy, 72 -> 64 registers (8 blocks per SM), 9.07 -> 7.95 ms
+//     at 10M particles (profiles/README.md, r02E-r02K);
 //   * every axis of the reference's dispatch is a template parameter (kernel, viscosity, DDT, floating bodies, mDBC2).
 // History of the rejected builds (consecutive candidates instead of masks, software-pipelined rounds, velrho with the positions,
 // single rows = the former variant 4, rows set up one ahead of their use): profiles/r01_pair2_tuning.txt, profiles/r02_pair2_ab.txt,
