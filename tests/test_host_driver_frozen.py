@@ -392,5 +392,22 @@ def test_extra_frequency_body_files(cli, tmp_path):
     for it in om[1:]:
         pr = np.asarray(it.array("PosRef")).reshape(-1, 6, 3)
         assert all(np.array_equal(q, np.asarray(om[0].array("Ps")).reshape(6, 3)) for q in pr)
+    assert os.path.exists(out / "data" / "PartFloatInfo.ibi4") and os.path.exists(out / "data" / "PartMotionRef.ibi4")   # the main files stay
+    # the same schedule from the case file (<parameter key="TimeOutExtra">, JSph.cpp:789) instead of the switch: identical files
+    spec2 = dict(fx["spec"]); spec2["params"] = dict(spec2["params"], TimeOutExtra=fx["toutx"])
+    (tmp_path / "b").mkdir()
+    H.write_case(tmp_path / "b", **spec2)
+    r2 = _run(cli, tmp_path / "b" / "Case", tmp_path / "out_b")
+    assert r2.returncode == 0, r2.stdout[-1500:] + r2.stderr[-1500:]
+    for name in ("PartFloatInfo2.ibi4", "PartMotionRef2.ibi4"):
+        assert open(out / "data" / name, "rb").read() == open(tmp_path / "out_b" / "data" / name, "rb").read(), name
+    # without the option nothing extra is written
+    r3 = _run(cli, tmp_path / "Case", tmp_path / "out_c")
+    assert r3.returncode == 0 and not os.path.exists(tmp_path / "out_c" / "data" / "PartFloatInfo2.ibi4")
     # slab-decomposed runs refuse the option instead of dropping the files
-    assert os.path.exists(out / "data" / "PartFloatInfo.ibi4") and os.path.exists(out / "data" / "PartMotionRef.ibi4")
+    import ctypes as C
+    lib = C.CDLL(os.path.join(os.path.dirname(cli), "libb200sph.so"))
+    lib.b2s_host_last_error.restype = C.c_char_p
+    sim = C.c_void_p()
+    assert lib.b2s_sim_load_slab(str(tmp_path / "Case").encode(), b"-toutx:0.002", 0, 0, 2, C.byref(sim)) != 0
+    assert b"toutx" in lib.b2s_host_last_error()
