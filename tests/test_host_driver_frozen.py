@@ -411,3 +411,46 @@ def test_extra_frequency_body_files(cli, tmp_path):
     sim = C.c_void_p()
     assert lib.b2s_sim_load_slab(str(tmp_path / "Case").encode(), b"-toutx:0.002", 0, 0, 2, C.byref(sim)) != 0
     assert b"toutx" in lib.b2s_host_last_error()
+
+
+def _spawn_ranks(cli, case, out, world, ranks, idfile, opts=(), env_extra=None, rank_opts=None):
+    procs = []
+    for r in ranks:
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), B2S_NCCL_ID_FILE=idfile, **(env_extra or {}))
+        o = list(opts) + list((rank_opts or {}).get(r, ()))
+        procs.append(subprocess.Popen([cli, str(case), str(out)] + o, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    return procs
+
+
+def test_multi_rank_start_roll_call(cli, tmp_path):
+    """Start of a multi-process run (csrc/host/main.cpp): after loading its slab every rank answers a roll call in files next to the
+    NCCL id, so that a rank that could not start (no such device, bad switch) stops its peers instead of leaving them inside the
+    communicator's initialisation for ever, and a rank that never shows up is given up after B2S_START_TIMEOUT seconds."""
+    import time
+    H.write_case(tmp_path, dp=0.05, params={"TimeMax": 0.01, "TimeOut": 0.005})
+    case = tmp_path / "Case"
+    # 1. both ranks come up: the run goes through and writes its pieces
+    idf = str(tmp_path / "id1")
+    procs = _spawn_ranks(cli, case, tmp_path / "o1", 2, (0, 1), idf)
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert "Finished execution (code=0)" in outs[0]
+    assert os.path.exists(tmp_path / "o1" / "data" / "Part_p01_0001.bi4")
+    assert not any(os.path.exists(idf + s) for s in ("", ".r0", ".r1"))           # nothing is left behind
+    # 2. rank 1 cannot load (an unsupported switch): rank 0 stops at once with its reason
+    idf = str(tmp_path / "id2")
+    t0 = time.time()
+    procs = _spawn_ranks(cli, case, tmp_path / "o2", 2, (0, 1), idf, rank_opts={1: ["-shifting:fulladv"]})
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert procs[0].returncode == 1 and procs[1].returncode == 1, outs
+    assert "rank 1 could not start" in outs[0] and time.time() - t0 < 60
+    # 3. rank 1 never shows up: rank 0 gives up after the limit
+    idf = str(tmp_path / "id3")
+    t0 = time.time()
+    procs = _spawn_ranks(cli, case, tmp_path / "o3", 2, (0,), idf, env_extra={"B2S_START_TIMEOUT": "2"})
+    out0 = procs[0].communicate(timeout=120)[0]
+    assert procs[0].returncode == 1 and "not every rank of 2 came up" in out0 and time.time() - t0 < 60, out0
+    # a later run with the same id file is not confused by what case 3 left behind
+    procs = _spawn_ranks(cli, case, tmp_path / "o4", 2, (0, 1), idf)
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
